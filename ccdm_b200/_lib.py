@@ -1,0 +1,118 @@
+"""ctypes binding of libccdm_b200.so (the C ABI declared in include/ccdm_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libccdm_b200.so")
+
+MAX_SRC, MAX_Z, STEP_NCOEF = 4, 4, 12
+
+EPI_BIAS, EPI_ROWSCALE, EPI_RMSNORM, EPI_SS = 0x1, 0x2, 0x4, 0x8
+EPI_SILU, EPI_RESID, EPI_QSOFTMAX, EPI_SUMSQ_OUT, EPI_OUT_F32 = 0x10, 0x20, 0x40, 0x80, 0x100
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU = 0, 1, 2, 3
+OBJ = {"pred_noise": 0, "pred_x0": 1, "pred_v": 2}
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class View(C.Structure):
+    _fields_ = [("ptr", vp), ("C", i32), ("W", i32), ("H", i32), ("B", i32), ("sW", i64), ("sH", i64), ("sB", i64)]
+
+
+class TapGemmArgs(C.Structure):
+    _fields_ = [
+        ("n_src", i32), ("src", View * MAX_SRC),
+        ("gW", i32), ("gH", i32), ("gB", i32), ("tw", i32), ("th", i32), ("tb", i32),
+        ("nz", i32), ("nkb", i32), ("sched", vp), ("wpacked", vp),
+        ("n_rows", i32), ("w_batch_rows", i32), ("N", i32), ("n_tile", i32), ("flags", C.c_uint32),
+        ("bias", vp), ("rowss", vp), ("gain", vp), ("gain_mul", f32), ("scale_shift", vp), ("ss_ld", i32), ("ss_off", i32),
+        ("resid", vp), ("rsW", i64), ("rsH", i64), ("rsB", i64),
+        ("out", vp), ("osW", i64), ("osH", i64), ("osB", i64), ("ooff", i64 * MAX_Z),
+        ("out_rowss", vp), ("q_scale", f32), ("q_cols", i32),
+    ]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [
+        ("out_cond", vp), ("out_null", vp), ("x", vp), ("noise", vp), ("pred_noise", vp), ("pred_x0", vp),
+        ("B", i32), ("chw", i32), ("cond_scale", f32), ("rescaled_phi", f32), ("keep_parallel_frac", f32),
+        ("remove_parallel", i32), ("objective", i32), ("clip_x0", i32), ("cfg_plus_plus", i32), ("sampler", i32),
+        ("coef", vp), ("step_counter", vp), ("advance", i32),
+    ]
+
+
+class QSampleArgs(C.Structure):
+    _fields_ = [
+        ("img01", vp), ("noise", vp), ("noise2", vp), ("cov", vp), ("keep", vp), ("t", vp), ("sqrt_acp", vp),
+        ("sqrt_1m_acp", vp), ("x0", vp), ("noise_out", vp), ("x_t", vp), ("B", i32), ("chw", i32),
+    ]
+
+
+class LossArgs(C.Structure):
+    _fields_ = [
+        ("model_out", vp), ("x0", vp), ("noise", vp), ("cov", vp), ("keep", vp), ("t", vp), ("sqrt_acp", vp),
+        ("sqrt_1m_acp", vp), ("loss_weight", vp), ("row_weight", vp), ("per_sample", vp), ("loss", vp),
+        ("grad_out", vp), ("B", i32), ("chw", i32), ("objective", i32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/ccdm_b200.h declares
+SIGNATURES = {
+    "ccdm_version": (C.c_int, []),
+    "ccdm_last_error": (C.c_char_p, []),
+    "ccdm_launch_count": (i64, []),
+    "ccdm_struct_size": (C.c_int, [C.c_int]),
+    "ccdm_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), vp]),
+    "ccdm_pack_weights": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, vp, vp]),
+    "ccdm_stem_conv7": (C.c_int, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp]),
+    "ccdm_head_conv1": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "ccdm_linattn_context": (C.c_int, [vp, vp, i32, i32, i32, vp]),
+    "ccdm_linattn_fold": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "ccdm_attention_small": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp]),
+    "ccdm_linear_small": (C.c_int, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, i64, vp]),
+    "ccdm_time_features": (C.c_int, [vp, i32, i32, vp, vp]),
+    "ccdm_select_null": (C.c_int, [vp, vp, i32, vp, i32, i32, vp]),
+    "ccdm_silu_concat_bf16": (C.c_int, [vp, i32, vp, i32, i32, vp, vp]),
+    "ccdm_sampler_step": (C.c_int, [C.POINTER(StepArgs), vp]),
+    "ccdm_cfg_combine": (C.c_int, [vp, vp, vp, i32, i32, f32, f32, i32, f32, vp]),
+    "ccdm_q_sample": (C.c_int, [C.POINTER(QSampleArgs), vp]),
+    "ccdm_vicinal_loss": (C.c_int, [C.POINTER(LossArgs), vp]),
+    "ccdm_vicinal_weights": (C.c_int, [vp, i32, i32, i32, i32, vp, f32, vp, vp, vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C ccdm_b200/csrc` (there is no CPU or PyTorch fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the header and the library disagree
+            fn.restype, fn.argtypes = res, args
+        for which, struct in enumerate((TapGemmArgs, View, StepArgs, QSampleArgs, LossArgs)):
+            if handle.ccdm_struct_size(which) != C.sizeof(struct):
+                raise RuntimeError(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes here, "
+                                   f"{handle.ccdm_struct_size(which)} in {LIB_PATH}")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().ccdm_last_error().decode(errors="replace")
+        raise RuntimeError(f"ccdm_b200 {what} failed ({rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,453 @@
+// CUDA-core kernels around the tap-GEMM: stem / head boundary convs, attention cores, embedding MLPs.
+// All are bandwidth- or latency-bound; see DESIGN.md for the per-kernel roofline.
+#include <cfloat>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ccdm {
+
+// ============================================================================ stem: 7x7 conv, NCHW fp32 -> NHWC bf16
+// unet.py:271,418.  Cin is 1 or 3: too thin for a TMA im2col, so this is a direct convolution on CUDA cores.
+// Block = 16x16 output pixels, one pixel per thread, 32 output channels per pass; weights [tap][cin][cout] and the
+// 22x22 input halo patch live in shared memory, weight reads are warp-wide broadcasts.
+constexpr int kStemTile = 16;
+constexpr int kStemHalo = kStemTile + 6;
+
+__global__ void __launch_bounds__(256) stem_conv7_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ out, int Cin, int H, int W,
+                                                         int Cout, int CoutPad, long long out_pix_stride,
+                                                         int x_batch) {
+  extern __shared__ float s_stem[];
+  float* sw = s_stem;                                   // [49*Cin][CoutPad]
+  float* sx = s_stem + 49 * Cin * CoutPad;              // [Cin][22][23]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int b = blockIdx.z;
+  const int w0 = blockIdx.x * kStemTile, h0 = blockIdx.y * kStemTile;
+
+  for (int i = tid; i < 49 * Cin * CoutPad; i += 256) {
+    const int co = i % CoutPad;
+    const int tc = i / CoutPad;       // tap*Cin + ci
+    const int ci = tc % Cin, tap = tc / Cin;
+    sw[i] = co < Cout ? w[(co * Cin + ci) * 49 + tap] : 0.f;
+  }
+  for (int i = tid; i < Cin * kStemHalo * kStemHalo; i += 256) {
+    const int xx = i % kStemHalo, yy = (i / kStemHalo) % kStemHalo, ci = i / (kStemHalo * kStemHalo);
+    const int gx = w0 + xx - 3, gy = h0 + yy - 3;
+    float v = 0.f;
+    if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = x[((long long)((b % x_batch) * Cin + ci) * H + gy) * W + gx];
+    sx[(ci * kStemHalo + yy) * (kStemHalo + 1) + xx] = v;
+  }
+  __syncthreads();
+
+  const int ox = w0 + tx, oy = h0 + ty;
+  const bool valid = ox < W && oy < H;
+  __nv_bfloat16* orow = out + ((long long)(b * H + (valid ? oy : 0)) * W + (valid ? ox : 0)) * out_pix_stride;
+
+  for (int cg = 0; cg < CoutPad; cg += 32) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = (cg + j < Cout) ? bias[cg + j] : 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      for (int r = 0; r < 7; ++r) {
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+          const float xv = sx[(ci * kStemHalo + ty + r) * (kStemHalo + 1) + tx + s];
+          const float4* wp = reinterpret_cast<const float4*>(sw + ((r * 7 + s) * Cin + ci) * CoutPad + cg);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 wv = wp[j4];
+            acc[j4 * 4 + 0] = fmaf(xv, wv.x, acc[j4 * 4 + 0]);
+            acc[j4 * 4 + 1] = fmaf(xv, wv.y, acc[j4 * 4 + 1]);
+            acc[j4 * 4 + 2] = fmaf(xv, wv.z, acc[j4 * 4 + 2]);
+            acc[j4 * 4 + 3] = fmaf(xv, wv.w, acc[j4 * 4 + 3]);
+          }
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (cg + g * 8 < Cout) {
+          uint4 u;
+          u.x = pack_bf16(acc[g * 8 + 0], acc[g * 8 + 1]);
+          u.y = pack_bf16(acc[g * 8 + 2], acc[g * 8 + 3]);
+          u.z = pack_bf16(acc[g * 8 + 4], acc[g * 8 + 5]);
+          u.w = pack_bf16(acc[g * 8 + 6], acc[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(orow + cg + g * 8) = u;
+        }
+      }
+    }
+  }
+}
+
+// ============================================================================ head: 1x1 conv, NHWC bf16 -> NCHW fp32
+// unet.py:348,455.  One pixel per thread; reads the pixel row once, writes Cout planes coalesced.
+__global__ void __launch_bounds__(256) head_conv1_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float* __restrict__ out, long long npix_total, int HW, int Cin,
+                                                         int Cout) {
+  extern __shared__ float s_head[];  // [Cout][Cin] + [Cout]
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) s_head[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_head[Cout * Cin + i] = bias[i];
+  __syncthreads();
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= npix_total) return;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = o < Cout ? s_head[Cout * Cin + o] : 0.f;
+  const uint4* row = reinterpret_cast<const uint4*>(x + p * Cin);
+  for (int c8 = 0; c8 < Cin / 8; ++c8) {
+    const uint4 u = __ldg(row + c8);
+    const float v[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                        bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      if (o < Cout) {
+        const float* wr = s_head + o * Cin + c8 * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o] = fmaf(v[j], wr[j], acc[o]);
+      }
+    }
+  }
+  const long long b = p / HW, hw = p % HW;
+  for (int o = 0; o < Cout; ++o) out[(b * Cout + o) * HW + hw] = acc[o];
+}
+
+// ============================================================================ linear attention: context
+// unet.py:208,212.  One CTA per (sample, head): streaming softmax over the n tokens of k (running max, rescaled
+// sums) fused with the 32x32 context accumulation.  128 threads; thread (d, eg) owns context[d][8*eg .. 8*eg+8).
+constexpr int kCtxRows = 64;
+
+__global__ void __launch_bounds__(128) linattn_context_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                              float* __restrict__ ctx, int n, int heads) {
+  __shared__ float ks[kCtxRows][33];
+  __shared__ __align__(16) float vs[kCtxRows][32];
+  const int t = threadIdx.x;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int ld = 3 * heads * 32;
+  const __nv_bfloat16* kbase = qkv + (long long)b * n * ld + heads * 32 + h * 32;
+  const __nv_bfloat16* vbase = kbase + heads * 32;
+  const int d = t >> 2, eg = t & 3;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  float ssum = 0.f, m_run = -FLT_MAX;
+
+  for (int r0 = 0; r0 < n; r0 += kCtxRows) {
+    const int rows = min(kCtxRows, n - r0);
+#pragma unroll
+    for (int i = 0; i < kCtxRows / 16; ++i) {
+      const int row = (t >> 3) + 16 * i, c4 = (t & 7) * 4;
+      float k4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX}, v4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row < rows) {
+        const uint2 ku = __ldg(reinterpret_cast<const uint2*>(kbase + (long long)(r0 + row) * ld + c4));
+        const uint2 vu = __ldg(reinterpret_cast<const uint2*>(vbase + (long long)(r0 + row) * ld + c4));
+        k4[0] = bf16_lo(ku.x); k4[1] = bf16_hi(ku.x); k4[2] = bf16_lo(ku.y); k4[3] = bf16_hi(ku.y);
+        v4[0] = bf16_lo(vu.x); v4[1] = bf16_hi(vu.x); v4[2] = bf16_lo(vu.y); v4[3] = bf16_hi(vu.y);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ks[row][c4 + j] = k4[j];
+        vs[row][c4 + j] = v4[j];
+      }
+    }
+    __syncthreads();
+    float mx = -FLT_MAX;
+    for (int row = eg; row < rows; row += 4) mx = fmaxf(mx, ks[row][d]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);
+    const float sc = __expf(m_run - m_new);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= sc;
+    ssum *= sc;
+    m_run = m_new;
+    for (int row = eg; row < rows; row += 4) ks[row][d] = __expf(ks[row][d] - m_new);
+    __syncthreads();
+    for (int row = 0; row < rows; ++row) {
+      const float pk = ks[row][d];
+      const float4 va = *reinterpret_cast<const float4*>(&vs[row][eg * 8]);
+      const float4 vb = *reinterpret_cast<const float4*>(&vs[row][eg * 8 + 4]);
+      acc[0] = fmaf(pk, va.x, acc[0]); acc[1] = fmaf(pk, va.y, acc[1]);
+      acc[2] = fmaf(pk, va.z, acc[2]); acc[3] = fmaf(pk, va.w, acc[3]);
+      acc[4] = fmaf(pk, vb.x, acc[4]); acc[5] = fmaf(pk, vb.y, acc[5]);
+      acc[6] = fmaf(pk, vb.z, acc[6]); acc[7] = fmaf(pk, vb.w, acc[7]);
+      ssum += pk;
+    }
+    __syncthreads();
+  }
+  const float inv = 1.f / ssum;
+  float* o = ctx + ((long long)blockIdx.x * 32 + d) * 32 + eg * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = acc[j] * inv;
+}
+
+// ============================================================================ linear attention: fold context into W_out
+// wfold[b][c][h*32+d] = sum_e w_out[c][h*32+e] * ctx[b][h][d][e].  One CTA per (sample, 32-row slab of c).
+__global__ void linattn_fold_kernel(const float* __restrict__ w_out, const float* __restrict__ ctx,
+                                    __nv_bfloat16* __restrict__ wfold, int C, int n_rows, int heads) {
+  extern __shared__ float s_fold[];          // ws[32][hid]
+  const int hid = heads * 32;
+  const int t = threadIdx.x;                 // column (h, d), blockDim.x == hid
+  const int b = blockIdx.x;
+  const int c0 = blockIdx.y * 32;
+  float cr[32];                              // ctx[b][h][d][0..32)
+  const float* crow = ctx + ((long long)b * hid + t) * 32;
+#pragma unroll
+  for (int e4 = 0; e4 < 8; ++e4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(crow) + e4);
+    cr[e4 * 4] = v.x; cr[e4 * 4 + 1] = v.y; cr[e4 * 4 + 2] = v.z; cr[e4 * 4 + 3] = v.w;
+  }
+  for (int i = t; i < 32 * hid; i += hid) {
+    const int c = c0 + i / hid;
+    s_fold[i] = c < C ? w_out[(long long)c * hid + i % hid] : 0.f;
+  }
+  __syncthreads();
+  const int hbase = (t >> 5) * 32;
+  for (int cc = 0; cc < 32; ++cc) {
+    const int c = c0 + cc;
+    if (c >= n_rows) break;
+    float acc = 0.f;
+    const float* wr = s_fold + cc * hid + hbase;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc = fmaf(wr[e], cr[e], acc);
+    wfold[((long long)b * n_rows + c) * hid + t] = __float2bfloat16(acc);
+  }
+}
+
+// ============================================================================ bottleneck softmax attention
+// unet.py:228-240.  One CTA per (sample, head), one thread per query token (n <= 64, dim_head <= 64).
+__global__ void __launch_bounds__(64) attention_small_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                             __nv_bfloat16* __restrict__ out, int n, int heads,
+                                                             int dh, float scale) {
+  extern __shared__ float s_att[];
+  const int pitch = dh + 1;
+  float* sq = s_att;
+  float* sk = sq + n * pitch;
+  float* sv = sk + n * pitch;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int hid = heads * dh, ld = 3 * hid;
+  const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * dh;
+  for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
+    const int tok = i / dh, dd = i % dh;
+    const __nv_bfloat16* p = base + (long long)tok * ld + dd;
+    sq[tok * pitch + dd] = __bfloat162float(p[0]) * scale;
+    sk[tok * pitch + dd] = __bfloat162float(p[hid]);
+    sv[tok * pitch + dd] = __bfloat162float(p[2 * hid]);
+  }
+  __syncthreads();
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  float sim[64];
+  float mx = -FLT_MAX;
+  for (int j = 0; j < n; ++j) {
+    float s = 0.f;
+    for (int dd = 0; dd < dh; ++dd) s = fmaf(sq[i * pitch + dd], sk[j * pitch + dd], s);
+    sim[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.f;
+  for (int j = 0; j < n; ++j) {
+    sim[j] = __expf(sim[j] - mx);
+    sum += sim[j];
+  }
+  const float inv = 1.f / sum;
+  __nv_bfloat16* o = out + ((long long)b * n + i) * hid + h * dh;
+  for (int dd = 0; dd < dh; ++dd) {
+    float a = 0.f;
+    for (int j = 0; j < n; ++j) a = fmaf(sim[j], sv[j * pitch + dd], a);
+    o[dd] = __float2bfloat16(a * inv);
+  }
+}
+
+// ============================================================================ embedding MLPs
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case CCDM_ACT_RELU: return fmaxf(v, 0.f);
+    case CCDM_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // nn.GELU() default (erf)
+    case CCDM_ACT_SILU: return v / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+// One warp per output feature: dot products over the batch, optional BatchNorm1d (batch or running stats), act.
+__global__ void __launch_bounds__(128) linear_small_kernel(const float* __restrict__ x, int B, int in_dim,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           int out_dim, const float* __restrict__ bn_w,
+                                                           const float* __restrict__ bn_b, float* bn_mean,
+                                                           float* bn_var, int bn_train, int act, float* __restrict__ y,
+                                                           long long y_ld) {
+  const int o = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= out_dim) return;
+  const float* wr = w + (long long)o * in_dim;
+  const float bo = bias ? bias[o] : 0.f;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float* xr = x + (long long)b * in_dim;
+    float acc = 0.f;
+    for (int k = lane; k < in_dim; k += 32) acc = fmaf(xr[k], wr[k], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    acc += bo;
+    if (bn_w && bn_train) {
+      s1 += acc;
+      s2 += (double)acc * acc;
+      if (lane == 0) y[(long long)b * y_ld + o] = acc;
+    } else {
+      if (bn_w) acc = (acc - bn_mean[o]) * rsqrtf(bn_var[o] + 1e-5f) * bn_w[o] + bn_b[o];
+      if (lane == 0) y[(long long)b * y_ld + o] = act_apply(acc, act);
+    }
+  }
+  if (bn_w && bn_train) {
+    const double mean = s1 / B;
+    double var = s2 / B - mean * mean;
+    if (var < 0) var = 0;
+    const float inv = rsqrtf((float)var + 1e-5f);
+    __syncwarp();
+    for (int b = lane; b < B; b += 32) {
+      const float v = (y[(long long)b * y_ld + o] - (float)mean) * inv * bn_w[o] + bn_b[o];
+      y[(long long)b * y_ld + o] = act_apply(v, act);
+    }
+    if (lane == 0) {
+      bn_mean[o] = 0.9f * bn_mean[o] + 0.1f * (float)mean;
+      bn_var[o] = 0.9f * bn_var[o] + 0.1f * (float)(var * B / (B > 1 ? B - 1 : 1));
+    }
+  }
+}
+
+// unet.py:107-115: sin | cos of t * exp(-log(1e4) * i / (half-1))
+__global__ void time_features_kernel(const long long* __restrict__ t, int B, int dim, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= B * half) return;
+  const int b = idx / half, i = idx % half;
+  const float k = logf(10000.f) / (float)(half - 1);
+  const float ang = (float)t[b] * expf((float)i * -k);
+  out[(long long)b * dim + i] = sinf(ang);
+  out[(long long)b * dim + half + i] = cosf(ang);
+}
+
+__global__ void select_null_kernel(float* __restrict__ c, const uint8_t* __restrict__ keep, int all_null,
+                                   const float* __restrict__ null_emb, int B, int dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * dim) return;
+  const int b = idx / dim;
+  if (all_null || !keep[b]) c[idx] = null_emb[idx % dim];
+}
+
+__global__ void silu_concat_kernel(const float* __restrict__ t_emb, int dt, const float* __restrict__ c_emb, int dc,
+                                   int B, __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ld = dt + dc;
+  if (idx >= B * ld) return;
+  const int b = idx / ld, j = idx % ld;
+  const float v = j < dt ? t_emb[(long long)b * dt + j] : c_emb[(long long)b * dc + (j - dt)];
+  out[idx] = __float2bfloat16(v / (1.f + expf(-v)));
+}
+
+}  // namespace ccdm
+
+using namespace ccdm;
+
+// ---------------------------------------------------------------------------- C ABI
+
+extern "C" int ccdm_stem_conv7(const float* x, int32_t x_batch, const float* w, const float* bias, void* out, int32_t B,
+                               int32_t Cin, int32_t H, int32_t W, int32_t Cout, int64_t out_pix_stride, void* stream) {
+  CCDM_REQUIRE(x && w && bias && out && x_batch > 0, CCDM_ERR_BAD_ARG, "stem_conv7: null pointer");
+  CCDM_REQUIRE(B > 0 && Cin > 0 && Cin <= 4 && H > 0 && W > 0 && Cout % 8 == 0 && out_pix_stride % 8 == 0,
+               CCDM_ERR_UNSUPPORTED_SHAPE, "stem_conv7: B=%d Cin=%d H=%d W=%d Cout=%d", B, Cin, H, W, Cout);
+  const int cpad = (Cout + 31) / 32 * 32;
+  const size_t smem = (size_t)(49 * Cin * cpad + Cin * kStemHalo * (kStemHalo + 1)) * sizeof(float);
+  CCDM_REQUIRE(smem <= 200 * 1024, CCDM_ERR_UNSUPPORTED_SHAPE, "stem_conv7: Cout=%d too wide", Cout);
+  static size_t max_set = 48 * 1024;
+  if (smem > max_set) {
+    cudaError_t e = cudaFuncSetAttribute(stem_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "stem_conv7: cudaFuncSetAttribute");
+    max_set = 200 * 1024;
+  }
+  dim3 grid((W + kStemTile - 1) / kStemTile, (H + kStemTile - 1) / kStemTile, B);
+  stem_conv7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (__nv_bfloat16*)out, Cin, H, W, Cout, cpad,
+                                                               out_pix_stride, x_batch);
+  return after_launch("stem_conv7_kernel");
+}
+
+extern "C" int ccdm_head_conv1(const void* x, const float* w, const float* bias, float* out, int32_t B, int32_t H,
+                               int32_t W, int32_t Cin, int32_t Cout, void* stream) {
+  CCDM_REQUIRE(x && w && bias && out, CCDM_ERR_BAD_ARG, "head_conv1: null pointer");
+  CCDM_REQUIRE(Cin % 8 == 0 && Cout >= 1 && Cout <= 8 && Cin <= 1024, CCDM_ERR_UNSUPPORTED_SHAPE,
+               "head_conv1: Cin=%d Cout=%d", Cin, Cout);
+  const long long npix = (long long)B * H * W;
+  const size_t smem = (size_t)(Cout * Cin + Cout) * sizeof(float);
+  head_conv1_kernel<<<(unsigned)((npix + 255) / 256), 256, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, w, bias, out, npix, H * W, Cin, Cout);
+  return after_launch("head_conv1_kernel");
+}
+
+extern "C" int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads, void* stream) {
+  CCDM_REQUIRE(qkv && ctx && B > 0 && n > 0 && heads > 0, CCDM_ERR_BAD_ARG, "linattn_context: bad args");
+  linattn_context_kernel<<<B * heads, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, ctx, n, heads);
+  return after_launch("linattn_context_kernel");
+}
+
+extern "C" int ccdm_linattn_fold(const float* w_out, const float* ctx, void* wfold, int32_t B, int32_t C,
+                                 int32_t n_rows, int32_t heads, void* stream) {
+  CCDM_REQUIRE(w_out && ctx && wfold && B > 0 && C > 0 && n_rows >= C && heads > 0 && heads <= 8, CCDM_ERR_BAD_ARG,
+               "linattn_fold: bad args");
+  const int hid = heads * 32;
+  dim3 grid(B, (n_rows + 31) / 32);
+  linattn_fold_kernel<<<grid, hid, (size_t)32 * hid * sizeof(float), (cudaStream_t)stream>>>(
+      w_out, ctx, (__nv_bfloat16*)wfold, C, n_rows, heads);
+  return after_launch("linattn_fold_kernel");
+}
+
+extern "C" int ccdm_attention_small(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head,
+                                    float scale, void* stream) {
+  CCDM_REQUIRE(qkv && out && B > 0, CCDM_ERR_BAD_ARG, "attention_small: bad args");
+  CCDM_REQUIRE(n >= 1 && n <= 64 && dim_head >= 1 && dim_head <= 64, CCDM_ERR_UNSUPPORTED_SHAPE,
+               "attention_small: n=%d dim_head=%d (bottleneck attention handles <= 64 tokens of <= 64 dims)", n,
+               dim_head);
+  const size_t smem = (size_t)3 * n * (dim_head + 1) * sizeof(float);
+  CCDM_REQUIRE(smem <= 48 * 1024, CCDM_ERR_UNSUPPORTED_SHAPE, "attention_small: n=%d x dim_head=%d too large", n,
+               dim_head);
+  attention_small_kernel<<<B * heads, 64, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n,
+                                                                     heads, dim_head, scale);
+  return after_launch("attention_small_kernel");
+}
+
+extern "C" int ccdm_linear_small(const float* x, int32_t B, int32_t in_dim, const float* w, const float* bias,
+                                 int32_t out_dim, const float* bn_w, const float* bn_b, float* bn_mean, float* bn_var,
+                                 int32_t bn_train, int32_t act, float* y, int64_t y_ld, void* stream) {
+  CCDM_REQUIRE(x && w && y && B > 0 && in_dim > 0 && out_dim > 0 && y_ld >= out_dim, CCDM_ERR_BAD_ARG,
+               "linear_small: bad args");
+  CCDM_REQUIRE(!bn_w || (bn_b && bn_mean && bn_var), CCDM_ERR_BAD_ARG, "linear_small: incomplete BatchNorm pointers");
+  linear_small_kernel<<<(out_dim + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x, B, in_dim, w, bias, out_dim, bn_w, bn_b,
+                                                                           bn_mean, bn_var, bn_train, act, y, y_ld);
+  return after_launch("linear_small_kernel");
+}
+
+extern "C" int ccdm_time_features(const int64_t* t, int32_t B, int32_t dim, float* out, void* stream) {
+  CCDM_REQUIRE(t && out && B > 0 && dim >= 4 && dim % 2 == 0, CCDM_ERR_BAD_ARG, "time_features: bad args");
+  const int n = B * (dim / 2);
+  time_features_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const long long*)t, B, dim, out);
+  return after_launch("time_features_kernel");
+}
+
+extern "C" int ccdm_select_null(float* c, const uint8_t* keep, int32_t all_null, const float* null_emb, int32_t B,
+                                int32_t dim, void* stream) {
+  CCDM_REQUIRE(c && null_emb && (keep || all_null), CCDM_ERR_BAD_ARG, "select_null: bad args");
+  const int n = B * dim;
+  select_null_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c, keep, all_null, null_emb, B, dim);
+  return after_launch("select_null_kernel");
+}
+
+extern "C" int ccdm_silu_concat_bf16(const float* t_emb, int32_t dt, const float* c_emb, int32_t dc, int32_t B,
+                                     void* out, void* stream) {
+  CCDM_REQUIRE(t_emb && c_emb && out && B > 0, CCDM_ERR_BAD_ARG, "silu_concat: bad args");
+  const int n = B * (dt + dc);
+  silu_concat_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t_emb, dt, c_emb, dc, B, (__nv_bfloat16*)out);
+  return after_launch("silu_concat_kernel");
+}

@@ -1,0 +1,340 @@
+// Guidance + sampler-step kernel and the training-side elementwise kernels (q_sample, vicinal loss).
+// All HBM-bound: one pass (or a few L2-resident passes) over [B][C*H*W] fp32 state.
+#include "common.cuh"
+
+namespace ccdm {
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// Sum K doubles across the block; result valid in every thread.  blockDim.x <= 1024.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* scratch /* [32*K] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0)
+    for (int k = 0; k < K; ++k) scratch[warp * K + k] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += scratch[w * K + k];
+    v[k] = s;
+  }
+}
+
+// Coefficients of "guided = A*cond + Bn*null" before the std rescale, from per-sample reductions
+// (unet.py:51-62, 365-371):  update = cond - null;  par = <update,unit> unit, unit = cond/max(|cond|,1e-12);
+// update' = (update - par) + par*kpf;  scaled = cond + update' * (s-1).
+struct CfgCoef {
+  float a_cond, a_null;
+};
+__device__ __forceinline__ CfgCoef cfg_coef(double uc, double cc, float cond_scale, int remove_parallel, float kpf) {
+  // scaled = cond + (s-1) * (u - (1-kpf) * par),  par = (uc / max(|c|,eps)^2) * c
+  double pc = 0.0;
+  if (remove_parallel) {
+    const double nrm = fmax(sqrt(cc), 1e-12);
+    pc = (1.0 - (double)kpf) * uc / (nrm * nrm);
+  }
+  const double s1 = (double)cond_scale - 1.0;
+  CfgCoef r;
+  r.a_cond = (float)(1.0 + s1 * (1.0 - pc));
+  r.a_null = (float)(-s1);
+  return r;
+}
+
+// One CTA per sample.
+__global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args a) {
+  __shared__ double scratch[32 * 4];
+  const int b = blockIdx.x;
+  const long long base = (long long)b * a.chw;
+  const float* cond = a.out_cond + base;
+  const float* nul = a.out_null ? a.out_null + base : nullptr;
+  const int step = a.step_counter ? *a.step_counter : 0;
+  const float* cf = a.x ? a.coef + (long long)step * CCDM_STEP_NCOEF : nullptr;
+
+  float a_cond = 1.f, a_null = 0.f, resc = 1.f;
+  if (nul) {
+    double v[4] = {0, 0, 0, 0};  // <u,c>, <c,c>, sum c, sum c^2
+    for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
+      const double c = cond[i], n = nul[i];
+      v[0] += (c - n) * c;
+      v[1] += c * c;
+      v[2] += c;
+    }
+    block_sum<4>(v, scratch);
+    const CfgCoef k = cfg_coef(v[0], v[1], a.cond_scale, a.remove_parallel, a.keep_parallel_frac);
+    a_cond = k.a_cond;
+    a_null = k.a_null;
+    if (a.rescaled_phi != 0.f) {
+      // unbiased std of cond and of scaled (torch.std default), second pass for centred sums
+      const double mean_c = v[2] / a.chw;
+      double w[4] = {0, 0, 0, 0};  // sum scaled, sum (c-mean_c)^2
+      for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
+        const double c = cond[i];
+        const double s = (double)(a_cond * cond[i] + a_null * nul[i]);
+        w[0] += s;
+        w[1] += (c - mean_c) * (c - mean_c);
+      }
+      block_sum<4>(w, scratch);
+      const double mean_s = w[0] / a.chw;
+      double u[4] = {0, 0, 0, 0};
+      for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
+        const double s = (double)(a_cond * cond[i] + a_null * nul[i]) - mean_s;
+        u[0] += s * s;
+      }
+      block_sum<4>(u, scratch);
+      const double std_c = sqrt(w[1] / (a.chw - 1)), std_s = sqrt(u[0] / (a.chw - 1));
+      resc = (float)(std_c / std_s) * a.rescaled_phi + (1.f - a.rescaled_phi);
+    }
+  }
+
+  float* x = a.x ? a.x + base : nullptr;
+  const float c_recip = x ? cf[0] : 0.f, c_recipm1 = x ? cf[1] : 1.f, c_sa = x ? cf[2] : 0.f, c_s1m = x ? cf[3] : 0.f;
+  for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
+    const float c = cond[i];
+    const float n = nul ? nul[i] : 0.f;
+    const float g = (a_cond * c + a_null * n) * resc;  // guided model output
+    if (!x) {                                          // guidance only (ccdm_cfg_combine)
+      a.pred_x0[base + i] = g;
+      continue;
+    }
+    const float xt = x[i];
+    float x0, eps;
+    if (a.objective == CCDM_OBJ_PRED_NOISE) {
+      x0 = c_recip * xt - c_recipm1 * g;
+      if (a.clip_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+      eps = a.cfg_plus_plus ? n : g;
+    } else if (a.objective == CCDM_OBJ_PRED_X0) {
+      x0 = a.clip_x0 ? fminf(fmaxf(g, -1.f), 1.f) : g;
+      float xe = x0;
+      if (a.cfg_plus_plus) xe = a.clip_x0 ? fminf(fmaxf(n, -1.f), 1.f) : n;
+      eps = (c_recip * xt - xe) / c_recipm1;
+    } else {
+      x0 = c_sa * xt - c_s1m * g;
+      if (a.clip_x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+      float xe = x0;
+      if (a.cfg_plus_plus) {
+        xe = c_sa * xt - c_s1m * n;
+        if (a.clip_x0) xe = fminf(fmaxf(xe, -1.f), 1.f);
+      }
+      eps = (c_recip * xt - xe) / c_recipm1;
+    }
+    if (a.pred_noise) a.pred_noise[base + i] = eps;
+    if (a.pred_x0) a.pred_x0[base + i] = x0;
+    float xn;
+    if (a.sampler == 0) {  // DDIM, diffusion.py:450-464
+      if (cf[7] != 0.f) {
+        xn = x0;
+      } else {
+        xn = x0 * cf[4] + cf[5] * eps;
+        if (cf[6] != 0.f) xn += cf[6] * a.noise[base + i];
+      }
+    } else {               // DDPM, diffusion.py:344-373 (x0 always clamped there)
+      const float x0c = fminf(fmaxf(x0, -1.f), 1.f);
+      xn = cf[8] * x0c + cf[9] * xt;
+      if (cf[10] != 0.f) xn += cf[10] * a.noise[base + i];
+    }
+    x[i] = xn;
+  }
+}
+
+// The step counter is bumped by its own 1-thread launch after the step kernel, so every CTA of the step kernel
+// has read the old value (stream order) before it changes.
+__global__ void advance_counter_kernel(int* c) { *c += 1; }
+
+// ---------------------------------------------------------------------------- q_sample
+__global__ void q_sample_kernel(const ccdm_qsample_args a) {
+  const long long total = (long long)a.B * a.chw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / a.chw);
+    const long long t = a.t[b];
+    const float x0 = a.img01[i] * 2.f - 1.f;
+    float nz = a.noise[i];
+    if (a.cov) {
+      if (a.keep[b]) nz *= sqrtf(a.cov[i]);
+      else if (a.noise2) nz = a.noise2[i];
+    }
+    a.x0[i] = x0;
+    a.noise_out[i] = nz;
+    a.x_t[i] = a.sqrt_acp[t] * x0 + a.sqrt_1m_acp[t] * nz;
+  }
+}
+
+// ---------------------------------------------------------------------------- vicinal loss
+// per_sample[b] = loss_weight[t_b] * sum_i (out - target)^2 / cov      (cov = 1 on null rows / without Hy)
+__global__ void __launch_bounds__(512) loss_rows_kernel(const ccdm_loss_args a) {
+  __shared__ double scratch[32];
+  const int b = blockIdx.x;
+  const long long base = (long long)b * a.chw;
+  const long long t = a.t[b];
+  const float sa = a.sqrt_acp[t], s1 = a.sqrt_1m_acp[t];
+  const bool use_cov = a.cov != nullptr && a.keep[b];
+  double v[1] = {0.0};
+  for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
+    const float x0 = a.x0[base + i], nz = a.noise[base + i];
+    const float target = a.objective == CCDM_OBJ_PRED_NOISE ? nz : (a.objective == CCDM_OBJ_PRED_X0 ? x0 : sa * nz - s1 * x0);
+    const float d = a.model_out[base + i] - target;
+    float e = d * d;
+    if (use_cov) e /= a.cov[base + i];
+    v[0] += e;
+  }
+  block_sum<1>(v, scratch);
+  if (threadIdx.x == 0) a.per_sample[b] = a.loss_weight[t] * (float)v[0];
+}
+
+__global__ void loss_final_kernel(const ccdm_loss_args a) {
+  __shared__ double scratch[32];
+  double v[1] = {0.0};
+  for (int b = threadIdx.x; b < a.B; b += blockDim.x)
+    v[0] += (double)a.per_sample[b] * (a.row_weight ? (double)a.row_weight[b] : 1.0);
+  block_sum<1>(v, scratch);
+  if (threadIdx.x == 0) a.loss[0] = (float)(v[0] / ((double)a.B * a.chw));
+}
+
+__global__ void loss_grad_kernel(const ccdm_loss_args a) {
+  const long long total = (long long)a.B * a.chw;
+  const float norm = 2.f / ((float)a.B * (float)a.chw);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / a.chw);
+    const long long t = a.t[b];
+    const float x0 = a.x0[i], nz = a.noise[i];
+    const float target = a.objective == CCDM_OBJ_PRED_NOISE
+                             ? nz
+                             : (a.objective == CCDM_OBJ_PRED_X0 ? x0 : a.sqrt_acp[t] * nz - a.sqrt_1m_acp[t] * x0);
+    float g = (a.model_out[i] - target) * norm * a.loss_weight[t] * (a.row_weight ? a.row_weight[b] : 1.f);
+    if (a.cov && a.keep[b]) g /= a.cov[i];
+    a.grad_out[i] = g;
+  }
+}
+
+// In-batch vicinal weights; one thread per row i, loops over j.
+__global__ void vicinal_weights_kernel(const float* __restrict__ proj, int B, int P, int euclid, int hard,
+                                       const float* __restrict__ thr, float nu, const uint8_t* __restrict__ keep,
+                                       float* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float acc = 0.f;
+  if (euclid) {
+    for (int j = 0; j < B; ++j) {
+      float d2 = 0.f;
+      for (int p = 0; p < P; ++p) {
+        const float d = proj[i * P + p] - proj[j * P + p];
+        d2 += d * d;
+      }
+      const float dist = sqrtf(d2);
+      acc += hard ? (dist <= thr[0] ? 1.f : 0.f) : expf(-nu * dist * dist);
+    }
+  } else {
+    for (int p = 0; p < P; ++p) {
+      float s = 0.f;
+      for (int j = 0; j < B; ++j) {
+        const float d = proj[i * P + p] - proj[j * P + p];
+        s += hard ? (fabsf(d) <= thr[p] ? 1.f : 0.f) : expf(-nu * d * d);
+      }
+      acc += s / (float)P;
+    }
+  }
+  acc /= (float)B;
+  if (keep && !keep[i]) acc = 1.f;
+  w[i] = acc;
+}
+
+}  // namespace ccdm
+
+using namespace ccdm;
+
+static int check_step(const ccdm_step_args* a) {
+  CCDM_REQUIRE(a && a->out_cond && a->coef && a->B > 0 && a->chw > 1, CCDM_ERR_BAD_ARG, "sampler_step: bad args");
+  CCDM_REQUIRE(a->noise || a->sampler == 0, CCDM_ERR_BAD_ARG, "sampler_step: the DDPM update needs a noise draw");
+  CCDM_REQUIRE(a->objective >= 0 && a->objective <= 2 && (a->sampler == 0 || a->sampler == 1), CCDM_ERR_BAD_ARG,
+               "sampler_step: objective=%d sampler=%d", a->objective, a->sampler);
+  CCDM_REQUIRE(a->out_null || a->cond_scale == 1.f, CCDM_ERR_BAD_ARG,
+               "sampler_step: cond_scale != 1 needs the unconditional output");
+  return CCDM_OK;
+}
+
+extern "C" int ccdm_sampler_step(const ccdm_step_args* a, void* stream) {
+  int rc = check_step(a);
+  if (rc != CCDM_OK) return rc;
+  CCDM_REQUIRE(a->x, CCDM_ERR_BAD_ARG, "sampler_step: null state");
+  ccdm_step_args k = *a;
+  if (k.cond_scale == 1.f) k.out_null = nullptr;
+  sampler_step_kernel<<<k.B, 512, 0, (cudaStream_t)stream>>>(k);
+  rc = after_launch("sampler_step_kernel");
+  if (rc != CCDM_OK) return rc;
+  if (a->advance && a->step_counter) {
+    advance_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->step_counter);
+    rc = after_launch("advance_counter_kernel");
+  }
+  return rc;
+}
+
+extern "C" int ccdm_cfg_combine(const float* cond, const float* null_out, float* guided, int32_t B, int32_t chw,
+                                float cond_scale, float rescaled_phi, int32_t remove_parallel,
+                                float keep_parallel_frac, void* stream) {
+  CCDM_REQUIRE(cond && null_out && guided && B > 0 && chw > 1, CCDM_ERR_BAD_ARG, "cfg_combine: bad args");
+  ccdm_step_args k = {};
+  k.out_cond = cond;
+  k.out_null = null_out;
+  k.x = nullptr;
+  k.pred_x0 = guided;
+  k.B = B;
+  k.chw = chw;
+  k.cond_scale = cond_scale;
+  k.rescaled_phi = rescaled_phi;
+  k.keep_parallel_frac = keep_parallel_frac;
+  k.remove_parallel = remove_parallel;
+  k.coef = nullptr;  // x == nullptr: guidance only, no sampler coefficients are read
+  sampler_step_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(k);
+  return after_launch("sampler_step_kernel(cfg)");
+}
+
+extern "C" int ccdm_q_sample(const ccdm_qsample_args* a, void* stream) {
+  CCDM_REQUIRE(a && a->img01 && a->noise && a->t && a->sqrt_acp && a->sqrt_1m_acp && a->x0 && a->noise_out && a->x_t,
+               CCDM_ERR_BAD_ARG, "q_sample: null pointer");
+  CCDM_REQUIRE(!a->cov || a->keep, CCDM_ERR_BAD_ARG, "q_sample: cov needs the keep mask");
+  const long long total = (long long)a->B * a->chw;
+  long long blocks = (total + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  q_sample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+  return after_launch("q_sample_kernel");
+}
+
+extern "C" int ccdm_vicinal_loss(const ccdm_loss_args* a, void* stream) {
+  CCDM_REQUIRE(a && a->model_out && a->x0 && a->noise && a->t && a->sqrt_acp && a->sqrt_1m_acp && a->loss_weight &&
+                   a->per_sample && a->loss,
+               CCDM_ERR_BAD_ARG, "vicinal_loss: null pointer");
+  CCDM_REQUIRE(!a->cov || a->keep, CCDM_ERR_BAD_ARG, "vicinal_loss: cov needs the keep mask");
+  CCDM_REQUIRE(a->objective >= 0 && a->objective <= 2, CCDM_ERR_BAD_ARG, "vicinal_loss: objective");
+  cudaStream_t s = (cudaStream_t)stream;
+  loss_rows_kernel<<<a->B, 512, 0, s>>>(*a);
+  int rc = after_launch("loss_rows_kernel");
+  if (rc != CCDM_OK) return rc;
+  loss_final_kernel<<<1, 256, 0, s>>>(*a);
+  rc = after_launch("loss_final_kernel");
+  if (rc != CCDM_OK) return rc;
+  if (a->grad_out) {
+    const long long total = (long long)a->B * a->chw;
+    long long blocks = (total + 255) / 256;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    loss_grad_kernel<<<(unsigned)blocks, 256, 0, s>>>(*a);
+    rc = after_launch("loss_grad_kernel");
+  }
+  return rc;
+}
+
+extern "C" int ccdm_vicinal_weights(const float* proj, int32_t B, int32_t P, int32_t euclid, int32_t hard,
+                                    const float* thr, float nu, const uint8_t* keep, float* w, void* stream) {
+  CCDM_REQUIRE(proj && w && B > 0 && P > 0 && (!hard || thr), CCDM_ERR_BAD_ARG, "vicinal_weights: bad args");
+  vicinal_weights_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(proj, B, P, euclid, hard, thr, nu, keep, w);
+  return after_launch("vicinal_weights_kernel");
+}

@@ -1,0 +1,482 @@
+// Tap-GEMM: implicit-GEMM convolution / linear engine for sm_100a.
+//
+//   D[128 pixels x n_tile] (fp32, TMEM)  +=  A[128 x 64] (bf16, smem via TMA)  .  B[n_tile x 64]^T (bf16, smem via TMA)
+//
+// One CTA owns one 128-row output tile (a tb x th x tw box of output positions) and n_tile output channels.
+// Warp 0 / lane 0 : TMA producer.  One K block = one (source view, filter tap, 64-channel chunk): a 4-D box
+//                   {64ch, tw, th, tb} read at the tap-shifted position; out-of-range coordinates are
+//                   zero-filled by TMA, which is the convolution's zero padding.  Rows land 128 B apart in the
+//                   canonical SWIZZLE_128B K-major layout that tcgen05.mma consumes directly.
+// Warp 1 / lane 0 : tcgen05.mma issuer (M=128, N<=256 per instruction, K=16; up to two N halves), accumulators in
+//                   TMEM; tcgen05.commit releases smem stages and finally signals the epilogue.
+// Warps 2..5      : epilogue.  tcgen05.ld 32x32b gives every thread one pixel row, so the channel RMSNorm, the
+//                   scale/shift, SiLU, q-softmax and residual add are per-thread loops with no shuffles; the row
+//                   is read from TMEM twice (norm pass, output pass) instead of being held in registers.
+//
+// Replaces the nn.Conv2d / nn.Linear call sites listed in include/ccdm_b200.h.
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ccdm {
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kABytes = kTileM * kBlockK * 2;  // 16 KiB
+
+struct TapGemmMaps {
+  CUtensorMap a[CCDM_MAX_SRC];
+  CUtensorMap b;
+};
+
+struct TapGemmDev {
+  int gW, gH, gB, tw, th, tb, tiles_w, tiles_h;
+  int nkb, n_rows, N, n_tile, n_sub, nsub, stages, w_batch_rows;
+  const int4* sched;
+  uint32_t flags, tmem_cols;
+  const float *bias, *rowss, *gain, *ss;
+  int ss_ld, ss_off;
+  const __nv_bfloat16* resid;
+  long long rsW, rsH, rsB;
+  void* out;
+  long long osW, osH, osB;
+  long long ooff[CCDM_MAX_Z];
+  float* out_rowss;
+  float q_scale, gain_mul;
+  int q_cols;
+};
+
+// aux smem block (after the stage ring): barriers, tmem slot, bias, gain, schedule
+constexpr int kAuxBarBytes = 256;
+constexpr int kAuxVecFloats = 512;
+
+__global__ void __launch_bounds__(kThreads) tapgemm_kernel(const __grid_constant__ TapGemmMaps maps,
+                                                           const TapGemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  uint8_t* aux = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* accum_bar = empty_bar + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(aux + kAuxBarBytes);
+  float* s_gain = s_bias + kAuxVecFloats;
+  int4* s_sched = reinterpret_cast<int4*>(s_gain + kAuxVecFloats);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  const int tile = blockIdx.x;
+  const int w0 = (tile % p.tiles_w) * p.tw;
+  const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
+  const int b0 = (tile / (p.tiles_w * p.tiles_h)) * p.tb;
+  const int n0 = blockIdx.y * p.n_tile;
+  const int z = blockIdx.z;
+
+  // ---------------------------------------------------------------- one-time setup
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(&maps.a[0]);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (tid == 64) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < p.n_tile; i += kThreads) {
+    const bool ok = (n0 + i) < p.N;
+    s_bias[i] = ((p.flags & CCDM_EPI_BIAS) && ok) ? p.bias[n0 + i] : 0.f;
+    s_gain[i] = ((p.flags & CCDM_EPI_RMSNORM) && ok) ? p.gain[n0 + i] * p.gain_mul : 0.f;
+  }
+  for (int i = tid; i < p.nkb; i += kThreads) s_sched[i] = p.sched[z * p.nkb + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================================================== TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (kb / p.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        const int4 e = s_sched[kb];
+        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
+        tma_load_4d(&maps.a[e.x], &full_bar[s], st, e.w, w0 + e.y, h0 + e.z, b0);
+        for (int sub = 0; sub < p.nsub; ++sub)
+          tma_load_2d(&maps.b, &full_bar[s], st + kABytes + sub * p.n_sub * 128, kb * kBlockK,
+                      b0 * p.w_batch_rows + z * p.n_rows + n0 + sub * p.n_sub);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kTileM, p.n_sub);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (kb / p.stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t adesc = umma_desc_sw128(a_addr + k * 32);
+          for (int sub = 0; sub < p.nsub; ++sub) {
+            const uint64_t bdesc = umma_desc_sw128(b_addr + sub * p.n_sub * 128 + k * 32);
+            umma_bf16_ss(tmem_base + sub * p.n_sub, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+      }
+      umma_commit(accum_bar);  // accumulators complete
+    }
+  } else {
+    // ============================================================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    const int lw = m % p.tw;
+    const int lh = (m / p.tw) % p.th;
+    const int lb = m / (p.tw * p.th);
+    const int w = w0 + lw, h = h0 + lh, b = b0 + lb;
+    const bool valid = (w < p.gW) && (h < p.gH) && (b < p.gB);
+    const int bs = b < p.gB ? b : p.gB - 1;
+    const long long pix = (static_cast<long long>(bs) * p.gH + (h < p.gH ? h : 0)) * p.gW + (w < p.gW ? w : 0);
+    const uint32_t flags = p.flags;
+
+    float rs = 1.f;
+    if (flags & CCDM_EPI_ROWSCALE) rs = valid ? 1.f / fmaxf(sqrtf(p.rowss[pix]), 1e-12f) : 0.f;
+
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int nchunk = p.n_tile / 32;
+    uint32_t r[32];
+
+    float inv = 1.f;
+    if (flags & CCDM_EPI_RMSNORM) {
+      float ssq = 0.f;
+      for (int c = 0; c < nchunk; ++c) {
+        tmem_ld32(trow + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]) * rs + s_bias[c * 32 + j];
+          ssq += v * v;
+        }
+      }
+      inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
+    }
+
+    const float* ssrow = (flags & CCDM_EPI_SS) ? p.ss + static_cast<long long>(bs) * p.ss_ld + p.ss_off + n0 : nullptr;
+    const long long ro = static_cast<long long>(bs) * p.rsB + static_cast<long long>(h) * p.rsH +
+                         static_cast<long long>(w) * p.rsW + n0;
+    const long long oo = p.ooff[z] + static_cast<long long>(bs) * p.osB + static_cast<long long>(h) * p.osH +
+                         static_cast<long long>(w) * p.osW + n0;
+    float out_ss = 0.f;
+
+    for (int c = 0; c < nchunk; ++c) {
+      tmem_ld32(trow + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs + s_bias[c * 32 + j];
+      if (flags & CCDM_EPI_RMSNORM) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= inv * s_gain[c * 32 + j];
+      }
+      if (flags & CCDM_EPI_SS) {
+        const float4* sc = reinterpret_cast<const float4*>(ssrow + c * 32);
+        const float4* sh = reinterpret_cast<const float4*>(ssrow + p.N + c * 32);
+        const bool in_n = (n0 + c * 32 + 32) <= p.N;
+        if (in_n) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 a = __ldg(sc + j4), d = __ldg(sh + j4);
+            v[j4 * 4 + 0] = v[j4 * 4 + 0] * (1.f + a.x) + d.x;
+            v[j4 * 4 + 1] = v[j4 * 4 + 1] * (1.f + a.y) + d.y;
+            v[j4 * 4 + 2] = v[j4 * 4 + 2] * (1.f + a.z) + d.z;
+            v[j4 * 4 + 3] = v[j4 * 4 + 3] * (1.f + a.w) + d.w;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c * 32 + j < p.N) v[j] = v[j] * (1.f + ssrow[c * 32 + j]) + ssrow[p.N + c * 32 + j];
+        }
+      }
+      if (flags & CCDM_EPI_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+      }
+      if ((flags & CCDM_EPI_QSOFTMAX) && (n0 + c * 32 < p.q_cols)) {
+        float mx = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __expf(v[j] - mx);
+          sum += v[j];
+        }
+        const float k = p.q_scale / sum;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= k;
+      }
+      if (valid) {
+        if (flags & CCDM_EPI_RESID) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + c * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (n0 + c * 32 + g * 8 < p.N) {
+              const uint4 u = __ldg(rp + g);
+              v[g * 8 + 0] += bf16_lo(u.x); v[g * 8 + 1] += bf16_hi(u.x);
+              v[g * 8 + 2] += bf16_lo(u.y); v[g * 8 + 3] += bf16_hi(u.y);
+              v[g * 8 + 4] += bf16_lo(u.z); v[g * 8 + 5] += bf16_hi(u.z);
+              v[g * 8 + 6] += bf16_lo(u.w); v[g * 8 + 7] += bf16_hi(u.w);
+            }
+          }
+        }
+        if (flags & CCDM_EPI_OUT_F32) {
+          float* op = reinterpret_cast<float*>(p.out) + oo + c * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (n0 + c * 32 + g * 4 < p.N)
+              *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + oo + c * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (n0 + c * 32 + g * 8 < p.N) {
+              uint4 u;
+              u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+              u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+              u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+              u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(op + g * 8) = u;
+              if (flags & CCDM_EPI_SUMSQ_OUT) {
+                const float a0 = bf16_lo(u.x), a1 = bf16_hi(u.x), a2 = bf16_lo(u.y), a3 = bf16_hi(u.y);
+                const float a4 = bf16_lo(u.z), a5 = bf16_hi(u.z), a6 = bf16_lo(u.w), a7 = bf16_hi(u.w);
+                out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+              }
+            }
+          }
+        }
+      }
+    }
+    if ((flags & CCDM_EPI_SUMSQ_OUT) && valid) p.out_rowss[pix] = out_ss;
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ============================================================================ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                      const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  CCDM_REQUIRE(enc != nullptr, CCDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_b, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CCDM_REQUIRE(r == CUDA_SUCCESS, CCDM_ERR_BAD_ARG,
+               "cuTensorMapEncodeTiled failed (%d): base=%p rank=%d dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu "
+               "box=%u,%u,%u,%u",
+               (int)r, base, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+               (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+               (unsigned long long)strides_b[0], (unsigned long long)(rank > 2 ? strides_b[1] : 0),
+               (unsigned long long)(rank > 3 ? strides_b[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0,
+               rank > 3 ? box[3] : 0);
+  return CCDM_OK;
+}
+
+static uint32_t pow2_cols(int n) {
+  uint32_t c = 32;
+  while (c < static_cast<uint32_t>(n)) c <<= 1;
+  return c;
+}
+
+}  // namespace ccdm
+
+using namespace ccdm;
+
+extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
+  CCDM_REQUIRE(a != nullptr, CCDM_ERR_BAD_ARG, "tapgemm: null args");
+  CCDM_REQUIRE(a->n_src >= 1 && a->n_src <= CCDM_MAX_SRC, CCDM_ERR_BAD_ARG, "tapgemm: n_src=%d", a->n_src);
+  CCDM_REQUIRE(a->tw > 0 && a->th > 0 && a->tb > 0 && a->tw * a->th * a->tb == kTileM && a->tw <= 256 &&
+                   a->th <= 256 && a->tb <= 256,
+               CCDM_ERR_BAD_ARG, "tapgemm: tile box %dx%dx%d must hold 128 positions", a->tw, a->th, a->tb);
+  CCDM_REQUIRE(a->nz >= 1 && a->nz <= CCDM_MAX_Z && a->nkb >= 1, CCDM_ERR_BAD_ARG, "tapgemm: nz=%d nkb=%d", a->nz,
+               a->nkb);
+  CCDM_REQUIRE(a->n_tile >= 32 && a->n_tile <= 512 && a->n_tile % 32 == 0, CCDM_ERR_UNSUPPORTED_SHAPE,
+               "tapgemm: n_tile=%d must be a multiple of 32 in [32,512]", a->n_tile);
+  CCDM_REQUIRE(a->N >= 1 && a->N % 8 == 0 && a->n_rows % a->n_tile == 0 && a->n_rows >= a->N,
+               CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: N=%d n_rows=%d n_tile=%d", a->N, a->n_rows, a->n_tile);
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_RMSNORM) || a->n_rows == a->n_tile, CCDM_ERR_UNSUPPORTED_SHAPE,
+               "tapgemm: the RMSNorm epilogue needs all %d channels in one tile (n_tile=%d)", a->N, a->n_tile);
+  CCDM_REQUIRE(a->sched && a->wpacked && a->out, CCDM_ERR_BAD_ARG, "tapgemm: null sched/wpacked/out");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_BIAS) || a->bias, CCDM_ERR_BAD_ARG, "tapgemm: bias flag without pointer");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_ROWSCALE) || a->rowss, CCDM_ERR_BAD_ARG, "tapgemm: rowscale without rowss");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_RMSNORM) || a->gain, CCDM_ERR_BAD_ARG, "tapgemm: rmsnorm without gain");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_SS) || (a->scale_shift && a->ss_off % 4 == 0 && a->ss_ld % 4 == 0 && a->N % 4 == 0),
+               CCDM_ERR_BAD_ARG, "tapgemm: scale/shift pointer or alignment");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_RESID) || a->resid, CCDM_ERR_BAD_ARG, "tapgemm: resid flag without pointer");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_SUMSQ_OUT) || (a->out_rowss && a->n_rows == a->n_tile), CCDM_ERR_BAD_ARG,
+               "tapgemm: sumsq output needs out_rowss and a single N tile");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_QSOFTMAX) || a->q_cols % 32 == 0, CCDM_ERR_BAD_ARG, "tapgemm: q_cols %% 32");
+  CCDM_REQUIRE(a->w_batch_rows == 0 || (a->tb == 1 && a->nz == 1 && a->w_batch_rows >= a->n_rows), CCDM_ERR_BAD_ARG,
+               "tapgemm: per-sample weights need tb == 1, nz == 1 and w_batch_rows >= n_rows");
+
+  TapGemmMaps maps;
+  std::memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < CCDM_MAX_SRC; ++i) {
+    const ccdm_view& v = a->src[i < a->n_src ? i : 0];
+    CCDM_REQUIRE(v.ptr && (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0, CCDM_ERR_BAD_ARG,
+                 "tapgemm: source %d pointer must be 16-byte aligned", i);
+    CCDM_REQUIRE(v.C > 0 && v.W > 0 && v.H > 0 && v.B > 0 && v.sW % 8 == 0 && v.sH % 8 == 0 && v.sB % 8 == 0,
+                 CCDM_ERR_BAD_ARG, "tapgemm: source %d extents/strides (strides must be multiples of 8 elements)", i);
+    cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.B};
+    cuuint64_t str[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sB * 2};
+    cuuint32_t box[4] = {kBlockK, (cuuint32_t)a->tw, (cuuint32_t)a->th, (cuuint32_t)a->tb};
+    int rc = encode_map(&maps.a[i], v.ptr, 4, dims, str, box);
+    if (rc != CCDM_OK) return rc;
+  }
+  const int nsub = a->n_tile > 256 ? 2 : 1;
+  const int n_sub = a->n_tile / nsub;
+  CCDM_REQUIRE(n_sub % 16 == 0 && n_sub <= 256, CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: n_sub=%d", n_sub);
+  {
+    const cuuint64_t ktot = (cuuint64_t)a->nkb * kBlockK;
+    cuuint64_t dims[2] = {ktot, a->w_batch_rows > 0 ? (cuuint64_t)a->w_batch_rows * a->gB
+                                                    : (cuuint64_t)a->n_rows * a->nz};
+    cuuint64_t str[1] = {ktot * 2};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)n_sub};
+    CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->wpacked) & 15) == 0, CCDM_ERR_BAD_ARG, "tapgemm: wpacked alignment");
+    int rc = encode_map(&maps.b, a->wpacked, 2, dims, str, box);
+    if (rc != CCDM_OK) return rc;
+  }
+
+  TapGemmDev p;
+  std::memset(&p, 0, sizeof(p));
+  p.gW = a->gW; p.gH = a->gH; p.gB = a->gB;
+  p.tw = a->tw; p.th = a->th; p.tb = a->tb;
+  p.tiles_w = (a->gW + a->tw - 1) / a->tw;
+  p.tiles_h = (a->gH + a->th - 1) / a->th;
+  const int tiles_b = (a->gB + a->tb - 1) / a->tb;
+  p.w_batch_rows = a->w_batch_rows;
+  p.nkb = a->nkb; p.n_rows = a->n_rows; p.N = a->N; p.n_tile = a->n_tile; p.n_sub = n_sub; p.nsub = nsub;
+  p.sched = reinterpret_cast<const int4*>(a->sched);
+  p.flags = a->flags;
+  p.tmem_cols = pow2_cols(a->n_tile);
+  p.bias = a->bias; p.rowss = a->rowss; p.gain = a->gain; p.ss = a->scale_shift;
+  p.ss_ld = a->ss_ld; p.ss_off = a->ss_off;
+  p.resid = reinterpret_cast<const __nv_bfloat16*>(a->resid);
+  p.rsW = a->rsW; p.rsH = a->rsH; p.rsB = a->rsB;
+  p.out = a->out; p.osW = a->osW; p.osH = a->osH; p.osB = a->osB;
+  for (int i = 0; i < CCDM_MAX_Z; ++i) p.ooff[i] = a->ooff[i];
+  p.out_rowss = a->out_rowss; p.q_scale = a->q_scale; p.q_cols = a->q_cols; p.gain_mul = a->gain_mul;
+
+  const uint32_t stage_bytes = kABytes + (uint32_t)a->n_tile * 128u;
+  const size_t aux_bytes = kAuxBarBytes + 2 * kAuxVecFloats * sizeof(float) + (size_t)a->nkb * sizeof(int4);
+  const size_t budget = (stage_bytes <= 32768 ? 110 * 1024 : 224 * 1024) - aux_bytes - 1024;  // small tiles: 2 CTAs / SM
+  int stages = (int)(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > a->nkb) stages = a->nkb;
+  CCDM_REQUIRE(stages >= 1, CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: K schedule of %d blocks does not fit shared memory",
+               a->nkb);
+  p.stages = stages;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + aux_bytes + 1024;
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "tapgemm: cudaFuncSetAttribute");
+
+  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_b), (unsigned)(a->n_rows / a->n_tile), (unsigned)a->nz);
+  tapgemm_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(maps, p);
+  return after_launch("tapgemm_kernel");
+}
+
+// ---------------------------------------------------------------------------- weight packing
+
+namespace ccdm {
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_total, int ntaps,
+                                    const int4* __restrict__ psched, int nkb, int n_rows,
+                                    const float* __restrict__ cin_gain, float gain_mul,
+                                    __nv_bfloat16* __restrict__ out, long long total) {
+  // one thread per packed element: idx = ((z*n_rows + n)*nkb + kb)*64 + j
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx & 63);
+    const long long t = idx >> 6;
+    const int kb = (int)(t % nkb);
+    const long long zn = t / nkb;
+    const int n = (int)(zn % n_rows);
+    const int z = (int)(zn / n_rows);
+    const int4 e = psched[z * nkb + kb];
+    float acc = 0.f;
+    if (n < cout && j < e.y) {
+      const int ci = e.x + j;
+      const float* wp = w + ((long long)n * cin_total + ci) * ntaps;
+      unsigned mask = (unsigned)e.z;
+      for (int tp = 0; tp < ntaps; ++tp)
+        if (mask & (1u << tp)) acc += wp[tp];
+      acc *= gain_mul * (cin_gain ? cin_gain[ci] : 1.f);
+    }
+    out[idx] = __float2bfloat16(acc);
+  }
+}
+}  // namespace ccdm
+
+extern "C" int ccdm_pack_weights(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
+                                 int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain, float gain_mul,
+                                 void* wpacked, void* stream) {
+  CCDM_REQUIRE(w && psched && wpacked, CCDM_ERR_BAD_ARG, "pack_weights: null pointer");
+  CCDM_REQUIRE(cout > 0 && cin_total > 0 && ntaps > 0 && ntaps <= 32 && nz > 0 && nkb > 0 && n_rows >= cout,
+               CCDM_ERR_BAD_ARG, "pack_weights: bad sizes cout=%d cin=%d taps=%d nz=%d nkb=%d n_rows=%d", cout,
+               cin_total, ntaps, nz, nkb, n_rows);
+  const long long total = (long long)nz * n_rows * nkb * 64;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weights_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin_total, ntaps, reinterpret_cast<const int4*>(psched), nkb, n_rows, cin_gain, gain_mul,
+      reinterpret_cast<__nv_bfloat16*>(wpacked), total);
+  return after_launch("pack_weights_kernel");
+}

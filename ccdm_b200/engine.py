@@ -1,0 +1,570 @@
+"""Execution engine of the B200 UNet: turns a :class:`ccdm_b200.unet.Unet` into a flat program of C-ABI calls.
+
+The program is built once per (batch, resolution, mode): every intermediate lives in a persistent bf16 NHWC
+buffer, every kernel argument struct is pre-filled, so a forward is a list of ``lib.fn(args, stream)`` calls with
+no allocation and no host sync -- which is what makes the whole denoising step CUDA-graph capturable.
+
+Layer -> kernel mapping (reference lines in CCDM_unified/models/unet.py):
+  Block            (:143-152)  one tap-GEMM: conv3x3 + bias + RMSNorm + [(1+scale),shift] + SiLU
+  ResnetBlock      (:167-187)  all tc_mlp Linear layers of the network as ONE row-GEMM, then block1, [res_conv],
+                               block2 with the residual add fused; torch.cat inputs become dual-source K loops
+  LinearAttention  (:202-216)  qkv tap-GEMM (PreNorm folded: g*sqrt(C) into the weights, 1/|x| per row; q softmax in
+                               the epilogue) -> context kernel -> fold context into to_out -> tap-GEMM over q with
+                               per-sample weights + bias + RMSNorm + residual
+  Attention        (:228-240)  qkv tap-GEMM -> small softmax-attention kernel -> to_out tap-GEMM + residual
+  Downsample       (:80-81)    4x4/s2 conv as 16 taps over four strided parity views (no im2col, no gather pass)
+  Upsample         (:74-78)    nearest-2x folded into the conv: four output-parity 2x2 convs with summed taps
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from .plan import ConvPlan, plan_conv, tile_box, n_tiling, KB
+
+
+# --------------------------------------------------------------------------------------------- records
+
+@dataclass
+class ViewRec:
+    base: torch.Tensor          # bf16 storage the view lives in
+    off: int                    # element offset of the first element
+    C: int
+    W: int
+    H: int
+    B: int
+    sW: int
+    sH: int
+    sB: int
+
+
+@dataclass
+class PackRec:
+    name: str
+    weight: torch.Tensor        # fp32 [Cout, Cin_total, taps...] parameter (or [out, in] linear weight)
+    plan: ConvPlan
+    n_rows: int
+    packed: torch.Tensor        # bf16 [nz*n_rows, nkb*64]
+    sched: torch.Tensor         # int32 device [nz*nkb, 4]
+    psched: torch.Tensor
+    cin_gain: Optional[torch.Tensor] = None
+    gain_mul: float = 1.0
+    row_off: int = 0            # first packed row this weight occupies (tc_mlp layers share one matrix)
+    rows_alloc: int = 0
+
+
+@dataclass
+class TapGemmRec:
+    name: str
+    plan: ConvPlan
+    views: List[ViewRec]
+    gW: int
+    gH: int
+    gB: int
+    tile: Tuple[int, int, int]
+    pack: Optional[PackRec]             # None when the weights are produced on the fly (linattn fold)
+    wpacked: torch.Tensor
+    sched: torch.Tensor
+    n_rows: int
+    N: int
+    n_tile: int
+    flags: int
+    out: torch.Tensor
+    out_strides: Tuple[int, int, int]   # (sW, sH, sB) elements
+    ooff: Tuple[int, int, int, int] = (0, 0, 0, 0)
+    bias: Optional[torch.Tensor] = None
+    rowss: Optional[torch.Tensor] = None
+    gain: Optional[torch.Tensor] = None
+    gain_mul: float = 1.0
+    ss: Optional[torch.Tensor] = None
+    ss_ld: int = 0
+    ss_off: int = 0
+    resid: Optional[torch.Tensor] = None
+    resid_strides: Tuple[int, int, int] = (0, 0, 0)
+    out_rowss: Optional[torch.Tensor] = None
+    q_scale: float = 0.0
+    q_cols: int = 0
+    w_batch_rows: int = 0
+
+
+@dataclass
+class KernelRec:
+    """Any non-tap-GEMM call: ``kind`` names the C entry point (without the ccdm_ prefix), ``a`` its operands."""
+    kind: str
+    a: dict
+
+
+# --------------------------------------------------------------------------------------------- helpers
+
+def nhwc_view(t: torch.Tensor, c_off: int = 0, C: Optional[int] = None) -> ViewRec:
+    b, h, w, ct = t.shape
+    return ViewRec(t, c_off, ct - c_off if C is None else C, w, h, b, ct, w * ct, h * w * ct)
+
+
+def parity_views(t: torch.Tensor) -> List[ViewRec]:
+    """x[:, pr::2, pq::2, :] for (pr, pq) in row-major order -- the four planes of a stride-2 conv."""
+    b, h, w, ct = t.shape
+    out = []
+    for pr in range(2):
+        for pq in range(2):
+            out.append(ViewRec(t, (pr * w + pq) * ct, ct, (w - pq + 1) // 2, (h - pr + 1) // 2, b,
+                               2 * ct, 2 * w * ct, h * w * ct))
+    return out
+
+
+class Program:
+    """A flat list of records plus their pre-filled ctypes argument structs."""
+
+    def __init__(self, device):
+        self.device = device
+        self.recs: List[object] = []
+        self.calls: List[tuple] = []        # (fn, args tuple without the stream)
+        self.bufs: Dict[str, torch.Tensor] = {}
+        self._keep: List[object] = []
+
+    def buf(self, name, shape, dtype):
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        assert name not in self.bufs, name
+        self.bufs[name] = t
+        return t
+
+    def finalize(self):
+        lib = L.lib()
+        self.calls = [_make_call(lib, r, self._keep) for r in self.recs]
+
+    def run(self, stream: int):
+        for fn, args, name in self.calls:
+            rc = fn(*args, stream)
+            if rc != 0:
+                L.check(rc, name)
+
+
+def _fill_tapgemm(r: TapGemmRec) -> L.TapGemmArgs:
+    a = L.TapGemmArgs()
+    a.n_src = len(r.views)
+    for i, v in enumerate(r.views):
+        a.src[i] = L.View(v.base.data_ptr() + 2 * v.off, v.C, v.W, v.H, v.B, v.sW, v.sH, v.sB)
+    a.gW, a.gH, a.gB = r.gW, r.gH, r.gB
+    a.tw, a.th, a.tb = r.tile
+    a.nz, a.nkb = r.plan.nz, r.plan.nkb
+    a.sched, a.wpacked = r.sched.data_ptr(), r.wpacked.data_ptr()
+    a.n_rows, a.w_batch_rows, a.N, a.n_tile, a.flags = r.n_rows, r.w_batch_rows, r.N, r.n_tile, r.flags
+    a.bias, a.rowss, a.gain, a.gain_mul = L.ptr(r.bias), L.ptr(r.rowss), L.ptr(r.gain), r.gain_mul
+    a.scale_shift, a.ss_ld, a.ss_off = L.ptr(r.ss), r.ss_ld, r.ss_off
+    a.resid = L.ptr(r.resid)
+    a.rsW, a.rsH, a.rsB = r.resid_strides
+    a.out = r.out.data_ptr()
+    a.osW, a.osH, a.osB = r.out_strides
+    for i in range(L.MAX_Z):
+        a.ooff[i] = r.ooff[i]
+    a.out_rowss, a.q_scale, a.q_cols = L.ptr(r.out_rowss), r.q_scale, r.q_cols
+    return a
+
+
+def _make_call(lib, r, keep):
+    import ctypes as C
+    if isinstance(r, TapGemmRec):
+        args = _fill_tapgemm(r)
+        keep.append(args)
+        return lib.ccdm_tapgemm, (C.byref(args),), r.name
+    if isinstance(r, PackRec):
+        w = r.weight
+        cout, cin_total = w.shape[0], w.shape[1]
+        ntaps = w.numel() // (cout * cin_total)
+        dst = r.packed.data_ptr() + 2 * r.row_off * r.plan.nkb * KB
+        return lib.ccdm_pack_weights, (w.data_ptr(), cout, cin_total, ntaps, r.psched.data_ptr(), r.plan.nz, r.plan.nkb,
+                                       r.n_rows, L.ptr(r.cin_gain), r.gain_mul, dst), "pack:" + r.name
+    k, a = r.kind, r.a
+    p = L.ptr
+    if k == "stem_conv7":
+        return lib.ccdm_stem_conv7, (p(a["x"]), a["x_batch"], p(a["w"]), p(a["bias"]), p(a["out"]), a["B"], a["Cin"],
+                                     a["H"], a["W"], a["Cout"], a["Cout"]), k
+    if k == "head_conv1":
+        return lib.ccdm_head_conv1, (p(a["x"]), p(a["w"]), p(a["bias"]), p(a["out"]), a["B"], a["H"], a["W"], a["Cin"],
+                                     a["Cout"]), k
+    if k == "linattn_context":
+        return lib.ccdm_linattn_context, (p(a["qkv"]), p(a["ctx"]), a["B"], a["n"], a["heads"]), k
+    if k == "linattn_fold":
+        return lib.ccdm_linattn_fold, (p(a["w_out"]), p(a["ctx"]), p(a["wfold"]), a["B"], a["C"], a["n_rows"],
+                                       a["heads"]), k
+    if k == "attention_small":
+        return lib.ccdm_attention_small, (p(a["qkv"]), p(a["out"]), a["B"], a["n"], a["heads"], a["dim_head"],
+                                          a["scale"]), k
+    if k == "linear_small":
+        bn = a.get("bn")
+        return lib.ccdm_linear_small, (p(a["x"]), a["B"], a["in_dim"], p(a["w"]), p(a["bias"]), a["out_dim"],
+                                       p(bn.weight) if bn else None, p(bn.bias) if bn else None,
+                                       p(bn.running_mean) if bn else None, p(bn.running_var) if bn else None,
+                                       int(a.get("bn_train", 0)), a["act"], p(a["y"]), a["out_dim"]), k
+    if k == "time_features":
+        return lib.ccdm_time_features, (p(a["t"]), a["B"], a["dim"], p(a["out"])), k
+    if k == "select_null":
+        return lib.ccdm_select_null, (p(a["c"]), p(a["keep"]), 0, p(a["null_emb"]), a["B"], a["dim"]), k
+    if k == "silu_concat_bf16":
+        return lib.ccdm_silu_concat_bf16, (p(a["t_emb"]), a["dt"], p(a["c_emb"]), a["dc"], a["B"], p(a["out"])), k
+    raise ValueError(k)
+
+
+# --------------------------------------------------------------------------------------------- weights
+
+class WeightStore:
+    """bf16 K-blocked copies of the conv / linear weights, re-derived whenever a parameter changes.
+
+    The fp32 ``nn.Parameter`` tensors stay the source of truth (optimizer, EMA ``lerp_``, ``load_state_dict`` all
+    write them in place and bump ``_version``), so the packed copies are a cache keyed on those versions."""
+
+    def __init__(self, device):
+        self.device = device
+        self.packs: Dict[str, PackRec] = {}
+        self.program = Program(device)
+        self._stamp = None
+        self._params: List[torch.Tensor] = []
+
+    def add(self, name, weight, plan: ConvPlan, n_rows, cin_gain=None, gain_mul=1.0, shared=None, row_off=0) -> PackRec:
+        if name in self.packs:
+            return self.packs[name]
+        dev = self.device
+        if shared is None:
+            packed = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
+        else:
+            packed = shared
+        sched = torch.tensor(plan.sched, dtype=torch.int32, device=dev).contiguous()
+        psched = torch.tensor(plan.psched, dtype=torch.int32, device=dev).contiguous()
+        rec = PackRec(name, weight, plan, n_rows, packed, sched, psched, cin_gain, gain_mul, row_off)
+        self.packs[name] = rec
+        self.program.recs.append(rec)
+        self._params.append(weight)
+        if cin_gain is not None:
+            self._params.append(cin_gain)
+        return rec
+
+    def stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in self._params)
+
+    def refresh(self, stream: int):
+        st = self.stamp()
+        if st != self._stamp:
+            if len(self.program.calls) != len(self.program.recs):
+                self.program.finalize()
+            self.program.run(stream)
+            self._stamp = st
+
+
+# --------------------------------------------------------------------------------------------- program builder
+
+class UnetEngine:
+    def __init__(self, net):
+        self.net = net
+        self.device = net.init_conv.weight.device
+        self.weights = WeightStore(self.device)
+        self.programs: Dict[tuple, "UnetProgram"] = {}
+        self._ptr_stamp = None
+
+    def _param_ptrs(self):
+        return tuple(p.data_ptr() for p in self.net.parameters())
+
+    def program(self, B, x_batch, H, W, training) -> "UnetProgram":
+        ptrs = self._param_ptrs()
+        if ptrs != self._ptr_stamp:        # parameters were re-allocated (.to(), load with assign): rebuild all
+            self.programs.clear()
+            self.weights = WeightStore(self.device)
+            self._ptr_stamp = ptrs
+        key = (B, x_batch, H, W, bool(training))
+        prog = self.programs.get(key)
+        if prog is None:
+            prog = UnetProgram(self.net, self.weights, B, x_batch, H, W, training)
+            self.programs[key] = prog
+        return prog
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _run(self, prog, x, t, emb_rows, keep_rows):
+        if x.device != self.device:
+            raise RuntimeError(f"input on {x.device}, model on {self.device}")
+        prog.x_in.copy_(x)
+        prog.t_in.copy_(t.reshape(-1))
+        prog.emb_in.copy_(emb_rows)
+        prog.keep.copy_(keep_rows)
+        stream = self._stream()
+        self.weights.refresh(stream)
+        prog.run(stream)
+        if self.net.training:
+            for bn in (self.net.cond_mlp_1[1], self.net.cond_mlp_2[1]):
+                bn.num_batches_tracked += 1
+        return prog.out
+
+    def forward(self, x, t, labels_emb, keep_mask):
+        """One UNet evaluation.  keep_mask: bool [B] (True = conditional row) or None for all-conditional."""
+        B, _, H, W = x.shape
+        prog = self.program(B, B, H, W, self.net.training)
+        keep = torch.ones(B, dtype=torch.uint8, device=self.device) if keep_mask is None else keep_mask.to(torch.uint8)
+        return self._run(prog, x, t, labels_emb, keep).clone()
+
+    def forward_pair(self, x, t, labels_emb):
+        """Conditional and unconditional evaluations as one 2B batch (eval mode only).  Returns views of the
+        persistent output buffer: (cond [B,...], null [B,...])."""
+        B, _, H, W = x.shape
+        prog = self.program(2 * B, B, H, W, False)
+        if prog.pair_keep is None:
+            prog.pair_keep = torch.cat([torch.ones(B, dtype=torch.uint8), torch.zeros(B, dtype=torch.uint8)]).to(self.device)
+        t2 = torch.cat([t.reshape(-1), t.reshape(-1)])
+        emb2 = torch.cat([labels_emb, labels_emb])
+        out = self._run(prog, x, t2, emb2, prog.pair_keep)
+        return out[:B], out[B:]
+
+    def cfg_combine(self, cond, null, cond_scale, rescaled_phi, remove_parallel=True, keep_parallel_frac=0.0):
+        B = cond.shape[0]
+        chw = cond[0].numel()
+        out = torch.empty_like(cond)
+        L.check(L.lib().ccdm_cfg_combine(cond.data_ptr(), null.data_ptr(), out.data_ptr(), B, chw, float(cond_scale),
+                                         float(rescaled_phi), int(bool(remove_parallel)), float(keep_parallel_frac),
+                                         self._stream()), "cfg_combine")
+        return out
+
+
+class UnetProgram(Program):
+    def __init__(self, net, weights: WeightStore, B, x_batch, H, W, training):
+        super().__init__(net.init_conv.weight.device)
+        self.net, self.weights = net, weights
+        self.B, self.x_batch, self.H, self.W, self.training = B, x_batch, H, W, training
+        self.pair_keep = None
+        self._uid = 0
+        self._build()
+        self.finalize()
+
+    # ------------------------------------------------------------------ small builders
+    def act(self, name, h, w, c):
+        return self.buf(name, (self.B, h, w, c), torch.bfloat16)
+
+    def kernel(self, kind, **a):
+        self.recs.append(KernelRec(kind, a))
+
+    def conv(self, name, kind, srcs: List[torch.Tensor], conv_mod, out: torch.Tensor, flags=0, *, gain=None,
+             ss_off=None, resid=None, out_rowss=None, rowss=None, cin_gain=None, cin_gain_mul=1.0, q=None,
+             views: Optional[List[ViewRec]] = None):
+        """Append one tap-GEMM over NHWC sources.  ``conv_mod`` owns .weight / .bias (nn.Conv2d)."""
+        cins = [s.shape[3] for s in srcs] if views is None else [v.C for v in views]
+        cout = conv_mod.weight.shape[0]
+        plan = plan_conv(kind, cins, cout)
+        full_row = bool(flags & (L.EPI_RMSNORM | L.EPI_SUMSQ_OUT))
+        n_rows, n_tile = n_tiling(cout, full_row)
+        pack = self.weights.add(name, conv_mod.weight, plan, n_rows, cin_gain, cin_gain_mul)
+        gh, gw = out.shape[1], out.shape[2]
+        if plan.out_parity:
+            gh, gw = gh // 2, gw // 2
+        if views is None:
+            views = []
+            for s in srcs:
+                views += parity_views(s) if plan.n_views == 4 else [nhwc_view(s)]
+        co = out.shape[3]
+        if plan.out_parity:
+            ostr = (2 * co, 2 * out.shape[2] * co, out.shape[1] * out.shape[2] * co)
+            ooff = tuple((pa * out.shape[2] + pb) * co for pa in range(2) for pb in range(2))
+        else:
+            ostr = (co, out.shape[2] * co, out.shape[1] * out.shape[2] * co)
+            ooff = (0, 0, 0, 0)
+        if conv_mod.bias is not None:
+            flags |= L.EPI_BIAS
+        rec = TapGemmRec(name, plan, views, gw, gh, self.B, tile_box(gw, gh), pack, pack.packed, pack.sched, n_rows,
+                         cout, n_tile, flags, out, ostr, ooff, bias=conv_mod.bias, rowss=rowss, gain=gain,
+                         gain_mul=math.sqrt(cout) if gain is not None else 1.0, out_rowss=out_rowss)
+        if ss_off is not None:
+            rec.ss, rec.ss_ld, rec.ss_off = self.bufs["ss_all"], self.bufs["ss_all"].shape[1], ss_off
+        if resid is not None:
+            rc = resid.shape[3]
+            rec.resid, rec.resid_strides = resid, (rc, resid.shape[2] * rc, resid.shape[1] * resid.shape[2] * rc)
+        if q is not None:
+            rec.q_scale, rec.q_cols = q
+        self.recs.append(rec)
+        return rec
+
+    # ------------------------------------------------------------------ network pieces
+    def resblock(self, name, mod, srcs, h, w, ss_off, want_rowss=False):
+        cout = mod.dim_out
+        h1 = self.act(name + ".h1", h, w, cout)
+        self.conv(name + ".block1.proj", "3x3", srcs, mod.block1.proj, h1,
+                  L.EPI_RMSNORM | L.EPI_SS | L.EPI_SILU, gain=mod.block1.norm.g, ss_off=ss_off)
+        if isinstance(mod.res_conv, torch.nn.Conv2d):
+            res = self.act(name + ".res", h, w, cout)
+            self.conv(name + ".res_conv", "1x1", srcs, mod.res_conv, res)
+        else:
+            assert len(srcs) == 1
+            res = srcs[0]
+        out = self.act(name + ".out", h, w, cout)
+        rowss = self.buf(name + ".rowss", (self.B * h * w,), torch.float32) if want_rowss else None
+        self.conv(name + ".block2.proj", "3x3", [h1], mod.block2.proj, out,
+                  L.EPI_RMSNORM | L.EPI_SILU | L.EPI_RESID | (L.EPI_SUMSQ_OUT if want_rowss else 0),
+                  gain=mod.block2.norm.g, resid=res, out_rowss=rowss)
+        return out, rowss
+
+    def linear_attention(self, name, mod, x, rowss, h, w):
+        """mod = Residual(PreNorm(LinearAttention)); x NHWC [B,h,w,C] with its per-pixel sum of squares."""
+        pre, att = mod.fn, mod.fn.fn
+        C = x.shape[3]
+        heads, hid = att.heads, att.heads * att.dim_head
+        assert att.dim_head == 32, "linear attention kernels are written for dim_head == 32 (unet.py:190)"
+        n = h * w
+        qkv = self.act(name + ".qkv", h, w, 3 * hid)
+        self.conv(name + ".to_qkv", "1x1", [x], att.to_qkv, qkv, L.EPI_ROWSCALE | L.EPI_QSOFTMAX, rowss=rowss,
+                  cin_gain=pre.norm.g, cin_gain_mul=math.sqrt(C), q=(att.scale, hid))
+        ctx = self.buf(name + ".ctx", (self.B, heads, 32, 32), torch.float32)
+        self.kernel("linattn_context", qkv=qkv, ctx=ctx, B=self.B, n=n, heads=heads)
+        conv_out, norm_out = att.to_out[0], att.to_out[1]
+        n_rows, n_tile = n_tiling(C, True)
+        wfold = self.buf(name + ".wfold", (self.B * n_rows, hid), torch.bfloat16)
+        self.kernel("linattn_fold", w_out=conv_out.weight, ctx=ctx, wfold=wfold, B=self.B, C=C, n_rows=n_rows,
+                    heads=heads)
+        out = self.act(name + ".out", h, w, C)
+        plan = plan_conv("1x1", [hid], C)
+        sched = torch.tensor(plan.sched, dtype=torch.int32, device=self.device)
+        qview = ViewRec(qkv, 0, hid, w, h, self.B, 3 * hid, w * 3 * hid, h * w * 3 * hid)
+        rec = TapGemmRec(name + ".to_out", plan, [qview], w, h, self.B, tile_box(w, h, force_tb1=True), None, wfold,
+                         sched, n_rows, C, n_tile, L.EPI_BIAS | L.EPI_RMSNORM | L.EPI_RESID, out,
+                         (C, w * C, h * w * C), bias=conv_out.bias, gain=norm_out.g, gain_mul=math.sqrt(C), resid=x,
+                         resid_strides=(C, w * C, h * w * C), w_batch_rows=n_rows)
+        self.recs.append(rec)
+        return out
+
+    def mid_attention(self, name, mod, x, rowss, h, w):
+        pre, att = mod.fn, mod.fn.fn
+        C = x.shape[3]
+        hid = att.heads * att.dim_head
+        qkv = self.act(name + ".qkv", h, w, 3 * hid)
+        self.conv(name + ".to_qkv", "1x1", [x], att.to_qkv, qkv, L.EPI_ROWSCALE, rowss=rowss, cin_gain=pre.norm.g,
+                  cin_gain_mul=math.sqrt(C))
+        ao = self.act(name + ".attn", h, w, hid)
+        self.kernel("attention_small", qkv=qkv, out=ao, B=self.B, n=h * w, heads=att.heads, dim_head=att.dim_head,
+                    scale=att.scale)
+        out = self.act(name + ".out", h, w, C)
+        self.conv(name + ".to_out", "1x1", [ao], att.to_out, out, L.EPI_RESID, resid=x)
+        return out
+
+    # ------------------------------------------------------------------ whole network
+    def _build(self):
+        net, B, H, W, dev = self.net, self.B, self.H, self.W, self.device
+        dim, emb = net.dim, net.dim * 4
+        self.x_in = self.buf("x_in", (self.x_batch, net.in_channels, H, W), torch.float32)
+        self.t_in = self.buf("t_in", (B,), torch.int64)
+        self.emb_in = self.buf("emb_in", (B, net.embed_input_dim), torch.float32)
+        self.keep = self.buf("keep", (B,), torch.uint8)
+        self.out = self.buf("out", (B, net.out_dim, H, W), torch.float32)
+
+        # ---- embeddings (unet.py:397-421)
+        bn1, bn2 = net.cond_mlp_1[1], net.cond_mlp_2[1]
+        c1 = self.buf("c1", (B, dim), torch.float32)
+        self.kernel("linear_small", x=self.emb_in, B=B, in_dim=net.embed_input_dim, w=net.cond_mlp_1[0].weight,
+                    bias=net.cond_mlp_1[0].bias, out_dim=dim, bn=bn1, bn_train=self.training, act=L.ACT_RELU, y=c1)
+        self.kernel("select_null", c=c1, keep=self.keep, null_emb=net.null_cond_emb, B=B, dim=dim)
+        cemb = self.buf("c_emb", (B, emb), torch.float32)
+        self.kernel("linear_small", x=c1, B=B, in_dim=dim, w=net.cond_mlp_2[0].weight, bias=net.cond_mlp_2[0].bias,
+                    out_dim=emb, bn=bn2, bn_train=self.training, act=L.ACT_RELU, y=cemb)
+        tf = self.buf("t_feat", (B, dim), torch.float32)
+        self.kernel("time_features", t=self.t_in, B=B, dim=dim, out=tf)
+        t1 = self.buf("t_hidden", (B, emb), torch.float32)
+        self.kernel("linear_small", x=tf, B=B, in_dim=dim, w=net.time_mlp[1].weight, bias=net.time_mlp[1].bias,
+                    out_dim=emb, act=L.ACT_GELU, y=t1)
+        temb = self.buf("t_emb", (B, emb), torch.float32)
+        self.kernel("linear_small", x=t1, B=B, in_dim=emb, w=net.time_mlp[3].weight, bias=net.time_mlp[3].bias,
+                    out_dim=emb, act=L.ACT_NONE, y=temb)
+        tc = self.buf("tc_silu", (1, 1, B, 2 * emb), torch.bfloat16)        # "image" of B pixels in one row
+        self.kernel("silu_concat_bf16", t_emb=temb, dt=emb, c_emb=cemb, dc=emb, B=B, out=tc)
+
+        # ---- every ResnetBlock's tc_mlp Linear as one row-GEMM into ss_all[B, sum 2*Cout]
+        blocks = self._resblocks()
+        ss_offs, tot = {}, 0
+        for nm, mod in blocks:
+            ss_offs[nm] = tot
+            tot += 2 * mod.dim_out
+        n_rows = (tot + 127) // 128 * 128
+        ss_all = self.buf("ss_all", (B, n_rows), torch.float32)
+        plan = plan_conv("1x1", [2 * emb], n_rows)
+        shared = self.weights.packs["tc_mlp.0"].packed if "tc_mlp.0" in self.weights.packs else torch.zeros(
+            n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
+        if "tc_bias" not in self.weights.__dict__:
+            self.weights.tc_bias = torch.zeros(n_rows, dtype=torch.float32, device=dev)
+        first = None
+        for i, (nm, mod) in enumerate(blocks):
+            lin = mod.tc_mlp[1]
+            rec = self.weights.add(f"tc_mlp.{i}", lin.weight, plan_conv("1x1", [2 * emb], 2 * mod.dim_out),
+                                   2 * mod.dim_out, shared=shared, row_off=ss_offs[nm])
+            first = first or rec
+        self._tc_bias_srcs = [(ss_offs[nm], mod.tc_mlp[1].bias) for nm, mod in blocks]
+        sched = torch.tensor(plan.sched, dtype=torch.int32, device=dev)
+        self.recs.append(TapGemmRec("tc_mlp", plan, [nhwc_view(tc)], B, 1, 1, (128, 1, 1), None, shared, sched, n_rows,
+                                    n_rows, 128, L.EPI_BIAS | L.EPI_OUT_F32, ss_all, (n_rows, 0, 0),
+                                    bias=self.weights.tc_bias))
+
+        # ---- stem (unet.py:418-419)
+        stem = self.act("stem", H, W, net.init_dim)
+        self.kernel("stem_conv7", x=self.x_in, x_batch=self.x_batch, w=net.init_conv.weight, bias=net.init_conv.bias,
+                    out=stem, B=B, Cin=net.in_channels, H=H, W=W, Cout=net.init_dim)
+
+        # ---- down path (unet.py:425-433)
+        x, h, w = stem, H, W
+        skips = []
+        nlev = len(net.downs)
+        for k, (b1, b2, attn, down) in enumerate(net.downs):
+            x, _ = self.resblock(f"downs.{k}.0", b1, [x], h, w, ss_offs[f"downs.{k}.0"])
+            skips.append(x)
+            x, rss = self.resblock(f"downs.{k}.1", b2, [x], h, w, ss_offs[f"downs.{k}.1"], want_rowss=True)
+            x = self.linear_attention(f"downs.{k}.2", attn, x, rss, h, w)
+            skips.append(x)
+            if k < nlev - 1:
+                h, w = h // 2, w // 2
+                y = self.act(f"downs.{k}.3.out", h, w, down.weight.shape[0])
+                self.conv(f"downs.{k}.3", "down4x4s2", [x], down, y)
+            else:
+                y = self.act(f"downs.{k}.3.out", h, w, down.weight.shape[0])
+                self.conv(f"downs.{k}.3", "3x3", [x], down, y)
+            x = y
+
+        # ---- bottleneck (unet.py:435-439)
+        x, rss = self.resblock("mid_block1", net.mid_block1, [x], h, w, ss_offs["mid_block1"], want_rowss=True)
+        x = self.mid_attention("mid_attn", net.mid_attn, x, rss, h, w)
+        x, _ = self.resblock("mid_block2", net.mid_block2, [x], h, w, ss_offs["mid_block2"])
+
+        # ---- up path (unet.py:441-449): torch.cat((x, skip)) == two K-loop sources
+        for k, (b1, b2, attn, up) in enumerate(net.ups):
+            x, _ = self.resblock(f"ups.{k}.0", b1, [x, skips.pop()], h, w, ss_offs[f"ups.{k}.0"])
+            x, rss = self.resblock(f"ups.{k}.1", b2, [x, skips.pop()], h, w, ss_offs[f"ups.{k}.1"], want_rowss=True)
+            x = self.linear_attention(f"ups.{k}.2", attn, x, rss, h, w)
+            if k < nlev - 1:
+                conv = up[1]
+                h, w = h * 2, w * 2
+                y = self.act(f"ups.{k}.3.out", h, w, conv.weight.shape[0])
+                self.conv(f"ups.{k}.3.1", "up2x3x3", [x], conv, y)
+            else:
+                y = self.act(f"ups.{k}.3.out", h, w, up.weight.shape[0])
+                self.conv(f"ups.{k}.3", "3x3", [x], up, y)
+            x = y
+
+        # ---- head (unet.py:451-455)
+        x, _ = self.resblock("final_res_block", net.final_res_block, [x, stem], h, w, ss_offs["final_res_block"])
+        self.kernel("head_conv1", x=x, w=net.final_conv.weight, bias=net.final_conv.bias, out=self.out, B=B, H=H, W=W,
+                    Cin=net.init_dim, Cout=net.out_dim)
+
+    def _resblocks(self):
+        net = self.net
+        out = []
+        for k, lvl in enumerate(net.downs):
+            out += [(f"downs.{k}.0", lvl[0]), (f"downs.{k}.1", lvl[1])]
+        out += [("mid_block1", net.mid_block1), ("mid_block2", net.mid_block2)]
+        for k, lvl in enumerate(net.ups):
+            out += [(f"ups.{k}.0", lvl[0]), (f"ups.{k}.1", lvl[1])]
+        out.append(("final_res_block", net.final_res_block))
+        return out
+
+    def run(self, stream: int):
+        # tc_mlp biases are gathered into one vector; cheap device copies, refreshed with the weights
+        st = tuple(b._version for _, b in self._tc_bias_srcs)
+        if getattr(self.weights, "_tc_bias_stamp", None) != st:
+            for off, b in self._tc_bias_srcs:
+                self.weights.tc_bias[off:off + b.numel()].copy_(b.detach())
+            self.weights._tc_bias_stamp = st
+        super().run(stream)

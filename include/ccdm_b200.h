@@ -1,0 +1,233 @@
+/* ccdm_b200 -- C ABI of the B200-native CCDM denoiser hot path (libccdm_b200.so).
+ *
+ * The reference (eric98040/CCDM, CCDM_unified/) is pure PyTorch and has no FFI of its own; every entry point
+ * below names the reference call site(s) it replaces.  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it is an args struct;
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it, no host sync, no allocation
+ *     that outlives the call -> every entry point is CUDA-graph capturable;
+ *   - return 0 on success, a negative CCDM_ERR_* otherwise; ccdm_last_error() gives a thread-local message;
+ *   - activations between kernels are bf16 NHWC ("pixel rows" of C channels); NCHW fp32 only at the stem / head.
+ * There is no CPU fallback: without a CUDA device every compute entry point returns CCDM_ERR_CUDA.
+ */
+#ifndef CCDM_B200_H
+#define CCDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCDM_OK 0
+#define CCDM_ERR_BAD_ARG (-1)
+#define CCDM_ERR_UNSUPPORTED_SHAPE (-2)
+#define CCDM_ERR_CUDA (-3)
+
+int ccdm_version(void);
+const char* ccdm_last_error(void);
+/* Number of kernels this library has launched on this process so far (bench.py's "gpu_launches"). */
+int64_t ccdm_launch_count(void);
+/* sizeof() of the args structs as this library was compiled: 0 tapgemm, 1 view, 2 step, 3 qsample, 4 loss.
+ * Lets a foreign-language binding verify its struct mirrors. */
+int ccdm_struct_size(int which);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tap-GEMM: the implicit-GEMM convolution / linear engine (tcgen05 + TMEM + TMA).
+ *
+ *   out[b,h,w,n] = epilogue( sum_kb  A_{src[kb]}[b, h+dh[kb], w+dw[kb], c0[kb] : c0[kb]+64] . Wp[n, kb*64 : kb*64+64] )
+ *
+ * Replaces nn.Conv2d (3x3, 1x1, 4x4/s2 Downsample, nearest-2x Upsample+3x3) and nn.Linear call sites of
+ * CCDM_unified/models/unet.py:77,81,139,160,165,195,198,225,226,326,341 together with the elementwise tail that
+ * follows them there: RMSNorm (:88-89), (scale+1)*x+shift (:147-149), SiLU (:151), residual adds (:72,:187), the
+ * PreNorm in front of the attention 1x1 (:97-99, folded as a per-row scale) and the q softmax (:207,:210).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define CCDM_MAX_SRC 4
+#define CCDM_MAX_Z 4
+
+#define CCDM_EPI_BIAS 0x1u       /* + bias[n] */
+#define CCDM_EPI_ROWSCALE 0x2u   /* acc *= 1/max(sqrt(rowss[pixel]),1e-12) before the bias (PreNorm fold) */
+#define CCDM_EPI_RMSNORM 0x4u    /* v *= gain[n]*gain_mul / max(||v||_2 over n, 1e-12); needs N <= n_tile <= 512 */
+#define CCDM_EPI_SS 0x8u         /* v = v*(1+scale[b,n]) + shift[b,n] */
+#define CCDM_EPI_SILU 0x10u
+#define CCDM_EPI_RESID 0x20u     /* v += resid[b,h,w,n] (bf16) */
+#define CCDM_EPI_QSOFTMAX 0x40u  /* columns < q_cols: softmax over aligned groups of 32, times q_scale */
+#define CCDM_EPI_SUMSQ_OUT 0x80u /* out_rowss[pixel] = sum_n (bf16-rounded out)^2 */
+#define CCDM_EPI_OUT_F32 0x100u  /* out is fp32 instead of bf16 */
+
+typedef struct ccdm_view {
+  const void* ptr;    /* bf16; first element of the view (already offset for channel slices / parity planes) */
+  int32_t C, W, H, B; /* extents seen by TMA; reads outside them return 0 (this is the conv zero padding) */
+  int64_t sW, sH, sB; /* strides in elements; the channel stride is 1 */
+} ccdm_view;
+
+typedef struct ccdm_tapgemm_args {
+  int32_t n_src;
+  ccdm_view src[CCDM_MAX_SRC];
+  int32_t gW, gH, gB; /* extents of the output-position grid the 128-row tiles walk over */
+  int32_t tw, th, tb; /* tile box, tw*th*tb == 128 */
+  int32_t nz, nkb;    /* sub-problems (output parity planes) and 64-wide K blocks per sub-problem */
+  const int32_t* sched; /* device [nz*nkb][4] = {src, dw, dh, c0} */
+  const void* wpacked;  /* device bf16 [nz*n_rows][nkb*64], K contiguous (see ccdm_pack_weights) */
+  int32_t n_rows;       /* packed rows per sub-problem; multiple of n_tile */
+  int32_t w_batch_rows; /* 0: one weight set.  >0: per-sample weights, sample b starts at row b*w_batch_rows
+                           (linear-attention output projection with the context folded in); needs tb == 1 */
+  int32_t N;            /* valid output channels */
+  int32_t n_tile;       /* output channels per CTA: multiple of 32, <= 512 */
+  uint32_t flags;       /* CCDM_EPI_* */
+  const float* bias;
+  const float* rowss;
+  const float* gain;    /* RMSNorm g[n]; the kernel multiplies it by gain_mul (= sqrt(C), unet.py:89) */
+  float gain_mul;
+  const float* scale_shift; /* scale at [b*ss_ld + ss_off + n], shift at [b*ss_ld + ss_off + N + n] */
+  int32_t ss_ld, ss_off;
+  const void* resid;
+  int64_t rsW, rsH, rsB;
+  void* out;
+  int64_t osW, osH, osB;
+  int64_t ooff[CCDM_MAX_Z]; /* element offset of sub-problem z inside out */
+  float* out_rowss;
+  float q_scale;
+  int32_t q_cols;
+} ccdm_tapgemm_args;
+
+int ccdm_tapgemm(const ccdm_tapgemm_args* args, void* stream);
+
+/* Pack fp32 conv / linear weights [Cout][Cin_total][kh*kw] into the bf16 K-blocked layout ccdm_tapgemm reads.
+ * psched: device [nz*nkb][4] = {cin0, nvalid, tapmask, 0}: block kb of sub-problem z holds, for j < nvalid,
+ *   sum over taps t in tapmask of W[n][cin0+j][t] * (cin_gain ? cin_gain[cin0+j] : 1) * gain_mul     and 0 for j >= nvalid
+ * (tap sums implement the nearest-2x upsample fold; cin_gain folds the PreNorm g of unet.py:97-99). */
+int ccdm_pack_weights(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
+                      int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain, float gain_mul, void* wpacked,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stem and head (NCHW fp32 <-> NHWC bf16 boundary).
+ *   stem: unet.py:271,418  nn.Conv2d(in_channels, dim, 7, padding=3)
+ *   head: unet.py:348,455  nn.Conv2d(dim, out_dim, 1)
+ * ------------------------------------------------------------------------------------------------------------ */
+/* x_batch: samples held in x_nchw; output sample b reads input sample b % x_batch (the guided sampler runs the
+ * conditional and unconditional halves as one 2B batch over the same x_t). */
+int ccdm_stem_conv7(const float* x_nchw, int32_t x_batch, const float* w, const float* bias, void* out_nhwc, int32_t B,
+                    int32_t Cin, int32_t H, int32_t W, int32_t Cout, int64_t out_pix_stride, void* stream);
+int ccdm_head_conv1(const void* x_nhwc, const float* w, const float* bias, float* out_nchw, int32_t B, int32_t H,
+                    int32_t W, int32_t Cin, int32_t Cout, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention cores.
+ *   linear attention, unet.py:202-216: qkv is bf16 [B][n][3*heads*32] with q already softmaxed*scale by the
+ *     tap-GEMM epilogue; context[b,h,d,e] = sum_n softmax_n(k)[d,n] v[e,n]  (fp32 [B][heads][32][32])
+ *   softmax attention at the bottleneck, unet.py:228-240 (n <= 64 tokens, dim_head <= 64)
+ * ------------------------------------------------------------------------------------------------------------ */
+int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads, void* stream);
+/* Fold the per-sample context into the output projection (unet.py:214-216 + to_out[0] at :198):
+ *   wfold[b][c][h*32+d] = sum_e w_out[c][h*32+e] * ctx[b][h][d][e]     bf16 [B][n_rows][heads*32], rows >= C zero
+ * so that to_out(context^T . q) becomes one tap-GEMM over q with per-sample weights (w_batch_rows = n_rows). */
+int ccdm_linattn_fold(const float* w_out, const float* ctx, void* wfold, int32_t B, int32_t C, int32_t n_rows,
+                      int32_t heads, void* stream);
+int ccdm_attention_small(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head,
+                         float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Embedding MLPs (unet.py:102-115 sinusoid, :289-312 time / label MLPs with BatchNorm1d, :397-414 null-label
+ * select, :158-161 SiLU in front of every tc_mlp).  fp32, batch-sized.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define CCDM_ACT_NONE 0
+#define CCDM_ACT_RELU 1
+#define CCDM_ACT_GELU 2
+#define CCDM_ACT_SILU 3
+/* y[b, :] = act( BN( x[b, :] . W^T + bias ) ); bn_* may be NULL.  In training mode (bn_train != 0) the batch
+ * statistics are used and running_mean / running_var are updated in place (momentum 0.1, unbiased variance). */
+int ccdm_linear_small(const float* x, int32_t B, int32_t in_dim, const float* w, const float* bias, int32_t out_dim,
+                      const float* bn_w, const float* bn_b, float* bn_mean, float* bn_var, int32_t bn_train,
+                      int32_t act, float* y, int64_t y_ld, void* stream);
+int ccdm_time_features(const int64_t* t, int32_t B, int32_t dim, float* out, void* stream);
+/* c[b,:] = keep[b] ? c[b,:] : null_emb[:]   (keep may be NULL with all_null != 0) */
+int ccdm_select_null(float* c, const uint8_t* keep, int32_t all_null, const float* null_emb, int32_t B, int32_t dim,
+                     void* stream);
+/* out_bf16[b, 0:dt] = silu(t_emb[b]),  out_bf16[b, dt:dt+dc] = silu(c_emb[b]) */
+int ccdm_silu_concat_bf16(const float* t_emb, int32_t dt, const float* c_emb, int32_t dc, int32_t B, void* out,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Guidance + sampler step (one kernel).
+ *   CFG combine: unet.py:51-62,365-380 (orthogonal update, std rescale)
+ *   model_predictions: diffusion.py:295-336;  DDIM update :454-464;  DDPM p_sample :338-374, q_posterior :284-293
+ * coef is a device table [n_steps][CCDM_STEP_NCOEF] indexed by *step_counter (device int32), which the kernel
+ * increments when `advance` != 0, so one captured graph replays for every step.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define CCDM_OBJ_PRED_NOISE 0
+#define CCDM_OBJ_PRED_X0 1
+#define CCDM_OBJ_PRED_V 2
+#define CCDM_STEP_NCOEF 12
+/* coef row: [0] sqrt_recip_acp  [1] sqrt_recipm1_acp  [2] sqrt_acp  [3] sqrt_1m_acp
+ *           [4] ddim sqrt(alpha_next)  [5] ddim c  [6] ddim sigma  [7] is_last (x = x0)
+ *           [8] ddpm posterior_mean_coef1  [9] coef2  [10] exp(0.5*posterior_log_variance) (0 at t==0)  [11] unused */
+typedef struct ccdm_step_args {
+  const float* out_cond; /* [B][C][H][W] fp32 network output, conditional half */
+  const float* out_null; /* unconditional half; NULL when cond_scale == 1 */
+  float* x;              /* in: x_t, out: x_{t-1}  (fp32 NCHW) */
+  const float* noise;    /* N(0,1) draw for this step (may be NULL when every sigma is 0) */
+  float* pred_noise;     /* optional outputs for parity traces (may be NULL) */
+  float* pred_x0;
+  int32_t B, chw;
+  float cond_scale, rescaled_phi, keep_parallel_frac;
+  int32_t remove_parallel, objective, clip_x0, cfg_plus_plus, sampler; /* sampler: 0 = DDIM, 1 = DDPM */
+  const float* coef;
+  int32_t* step_counter;
+  int32_t advance;
+} ccdm_step_args;
+int ccdm_sampler_step(const ccdm_step_args* args, void* stream);
+/* Guidance arithmetic alone (forward_with_cond_scale without the sampler): guided = f(cond, null). */
+int ccdm_cfg_combine(const float* cond, const float* null_out, float* guided, int32_t B, int32_t chw,
+                     float cond_scale, float rescaled_phi, int32_t remove_parallel, float keep_parallel_frac,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training-side elementwise kernels.
+ *   q_sample: diffusion.py:487-499 fused with img*2-1 (:755) and the Hy noise scaling (:550-557)
+ *   loss:     diffusion.py:570-594,597-730 (target select, MSE, /Hy, loss_weight[t], vicinal batch weights)
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct ccdm_qsample_args {
+  const float* img01;    /* [B][chw] images in [0,1] */
+  const float* noise;    /* [B][chw] N(0,1) */
+  const float* noise2;   /* [B][chw] second draw used for null rows under use_Hy (may be NULL) */
+  const float* cov;      /* [B][chw] exp(-y2cov) or NULL */
+  const uint8_t* keep;   /* [B] keep mask (1 = conditional row) */
+  const int64_t* t;      /* [B] */
+  const float* sqrt_acp; /* [T] */
+  const float* sqrt_1m_acp;
+  float* x0;             /* out: img*2-1 */
+  float* noise_out;      /* out: the noise actually mixed in (scaled by sqrt(cov) on conditional rows) */
+  float* x_t;            /* out */
+  int32_t B, chw;
+} ccdm_qsample_args;
+int ccdm_q_sample(const ccdm_qsample_args* args, void* stream);
+
+typedef struct ccdm_loss_args {
+  const float* model_out; /* [B][chw] */
+  const float* x0;
+  const float* noise;
+  const float* cov;       /* NULL unless use_Hy */
+  const uint8_t* keep;
+  const int64_t* t;
+  const float* sqrt_acp;
+  const float* sqrt_1m_acp;
+  const float* loss_weight; /* [T] */
+  const float* row_weight;  /* [B] vicinal batch weights (already 1 on null rows), or NULL for the plain mean */
+  float* per_sample;        /* out [B]: loss_weight[t] * sum_chw (out-target)^2 / cov */
+  float* loss;              /* out [1] */
+  float* grad_out;          /* out [B][chw]: d loss / d model_out (may be NULL) */
+  int32_t B, chw, objective;
+} ccdm_loss_args;
+int ccdm_vicinal_loss(const ccdm_loss_args* args, void* stream);
+/* In-batch vicinal weights, diffusion.py:669-727 ("traditional" branch) and :602-664 (sliced branch):
+ * proj is [B][P] (P = 1 and proj = labels for scalar labels; P = label_dim with `euclid` != 0 for the multi-
+ * dimensional l2 branch; P = num_projections of already-projected labels for the sliced branch, where the
+ * per-projection thresholds are thr[p]).  w[i] = (1/B) * (1/P or 1) * sum_j [ |d_ij| <= thr ]  or exp(-nu d_ij^2). */
+int ccdm_vicinal_weights(const float* proj, int32_t B, int32_t P, int32_t euclid, int32_t hard, const float* thr,
+                         float nu, const uint8_t* keep, float* w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCDM_B200_H */

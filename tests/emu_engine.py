@@ -1,0 +1,156 @@
+"""CPU interpreter for ccdm_b200.engine programs (test infrastructure).
+
+Executes the *records* of a UnetProgram with torch ops, mirroring the kernels' documented semantics (bf16
+storage, fp32 accumulation, zero fill outside views).  It validates the host-side wiring -- buffer connectivity,
+schedules, strides, epilogue flags, scale/shift offsets -- against the oracle without a GPU, and predicts the
+bf16 error the device path should show.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from ccdm_b200 import _lib as L
+from ccdm_b200.engine import TapGemmRec, PackRec, KernelRec, ViewRec
+from ccdm_b200.plan import KB
+from tests.emu import pack_weights_emu, shifted
+
+
+def _view_tensor(v: ViewRec):
+    flat = v.base.reshape(-1)
+    return torch.as_strided(flat, (v.B, v.H, v.W, v.C), (v.sB, v.sH, v.sW, 1), v.off).float()
+
+
+def run_pack(r: PackRec):
+    w = r.weight.detach().float()
+    w4 = w.reshape(w.shape[0], w.shape[1], -1, 1)
+    g = r.cin_gain.detach().reshape(-1).float() if r.cin_gain is not None else None
+    packed = pack_weights_emu(r.plan, w4, r.n_rows, g, r.gain_mul)          # [nz, n_rows, K]
+    K = r.plan.nkb * KB
+    dst = r.packed.reshape(-1, K)
+    for z in range(r.plan.nz):
+        dst[r.row_off + z * r.n_rows: r.row_off + (z + 1) * r.n_rows] = packed[z].to(torch.bfloat16)
+
+
+def run_tapgemm(r: TapGemmRec):
+    gB, gH, gW = r.gB, r.gH, r.gW
+    K = r.plan.nkb * KB
+    wp = r.wpacked.reshape(-1, K).float()
+    views = [_view_tensor(v) for v in r.views]
+    out_flat = r.out.reshape(-1)
+    for z in range(r.plan.nz):
+        acc = torch.zeros(gB, gH, gW, r.N)
+        for kb in range(r.plan.nkb):
+            src, dw, dh, c0 = r.plan.sched[z * r.plan.nkb + kb]
+            a = shifted(views[src], dh, dw, gH, gW, c0)                      # [vB, gH, gW, 64]
+            a = a[:gB]
+            if r.w_batch_rows:
+                wrows = torch.stack([wp[b * r.w_batch_rows: b * r.w_batch_rows + r.N, kb * KB:(kb + 1) * KB]
+                                     for b in range(gB)])                   # [B, N, 64]
+                acc += torch.einsum("bhwk,bnk->bhwn", a, wrows)
+            else:
+                acc += a @ wp[z * r.n_rows: z * r.n_rows + r.N, kb * KB:(kb + 1) * KB].t()
+        v = acc
+        if r.flags & L.EPI_ROWSCALE:
+            rs = 1.0 / r.rowss.reshape(gB, gH, gW, 1).sqrt().clamp_min(1e-12)
+            v = v * rs
+        if r.flags & L.EPI_BIAS:
+            v = v + r.bias.detach().float()[: r.N]
+        if r.flags & L.EPI_RMSNORM:
+            inv = 1.0 / v.pow(2).sum(-1, keepdim=True).sqrt().clamp_min(1e-12)
+            v = v * inv * (r.gain.detach().reshape(-1).float() * r.gain_mul)
+        if r.flags & L.EPI_SS:
+            ss = r.ss[:gB]
+            sc = ss[:, r.ss_off: r.ss_off + r.N].reshape(gB, 1, 1, r.N)
+            sh = ss[:, r.ss_off + r.N: r.ss_off + 2 * r.N].reshape(gB, 1, 1, r.N)
+            v = v * (1 + sc) + sh
+        if r.flags & L.EPI_SILU:
+            v = F.silu(v)
+        if r.flags & L.EPI_QSOFTMAX:
+            qc = r.q_cols
+            q = v[..., :qc].reshape(gB, gH, gW, qc // 32, 32).softmax(-1) * r.q_scale
+            v = torch.cat([q.reshape(gB, gH, gW, qc), v[..., qc:]], -1)
+        if r.flags & L.EPI_RESID:
+            rs_ = r.resid_strides
+            res = torch.as_strided(r.resid.reshape(-1), (gB, gH, gW, r.N), (rs_[2], rs_[1], rs_[0], 1), 0).float()
+            v = v + res
+        os_ = r.out_strides
+        dst = torch.as_strided(out_flat, (gB, gH, gW, r.N), (os_[2], os_[1], os_[0], 1), r.ooff[z])
+        dst.copy_(v.to(r.out.dtype))
+        if r.flags & L.EPI_SUMSQ_OUT:
+            r.out_rowss.copy_(dst.float().pow(2).sum(-1).reshape(-1))
+
+
+def run_kernel(r: KernelRec):
+    k, a = r.kind, r.a
+    if k == "stem_conv7":
+        x = a["x"]
+        idx = torch.arange(a["B"]) % a["x_batch"]
+        y = F.conv2d(x[idx], a["w"].detach(), a["bias"].detach(), padding=3)
+        a["out"].copy_(y.permute(0, 2, 3, 1).to(torch.bfloat16))
+    elif k == "head_conv1":
+        x = a["x"].float().permute(0, 3, 1, 2)
+        a["out"].copy_(F.conv2d(x, a["w"].detach(), a["bias"].detach()))
+    elif k == "linattn_context":
+        B, n, heads = a["B"], a["n"], a["heads"]
+        qkv = a["qkv"].float().reshape(B, n, 3, heads, 32)
+        kk, vv = qkv[:, :, 1], qkv[:, :, 2]                                  # [B, n, heads, 32]
+        p = kk.softmax(dim=1)
+        a["ctx"].copy_(torch.einsum("bnhd,bnhe->bhde", p, vv))
+    elif k == "linattn_fold":
+        B, C, heads = a["B"], a["C"], a["heads"]
+        w = a["w_out"].detach().reshape(C, heads, 32)                        # [c, h, e]
+        wf = torch.einsum("che,bhde->bchd", w, a["ctx"]).reshape(B, C, heads * 32)
+        dst = a["wfold"].reshape(B, a["n_rows"], heads * 32)
+        dst.zero_()
+        dst[:, :C] = wf.to(torch.bfloat16)
+    elif k == "attention_small":
+        B, n, heads, dh = a["B"], a["n"], a["heads"], a["dim_head"]
+        qkv = a["qkv"].float().reshape(B, n, 3, heads, dh)
+        q, kk, vv = qkv[:, :, 0] * a["scale"], qkv[:, :, 1], qkv[:, :, 2]
+        att = torch.einsum("bihd,bjhd->bhij", q, kk).softmax(-1)
+        o = torch.einsum("bhij,bjhd->bihd", att, vv).reshape(B, n, heads * dh)
+        a["out"].copy_(o.reshape(a["out"].shape).to(torch.bfloat16))
+    elif k == "linear_small":
+        y = F.linear(a["x"], a["w"].detach(), a["bias"].detach())
+        bn = a.get("bn")
+        if bn is not None:
+            if a.get("bn_train"):
+                mean, var = y.mean(0), y.var(0, unbiased=False)
+                n = y.shape[0]
+                bn.running_mean.mul_(0.9).add_(0.1 * mean)
+                bn.running_var.mul_(0.9).add_(0.1 * var * n / max(n - 1, 1))
+            else:
+                mean, var = bn.running_mean, bn.running_var
+            y = (y - mean) * torch.rsqrt(var + 1e-5) * bn.weight.detach() + bn.bias.detach()
+        act = a["act"]
+        y = {L.ACT_NONE: lambda v: v, L.ACT_RELU: F.relu, L.ACT_GELU: F.gelu, L.ACT_SILU: F.silu}[act](y)
+        a["y"].copy_(y)
+    elif k == "time_features":
+        dim = a["dim"]
+        half = dim // 2
+        kf = math.log(10000) / (half - 1)
+        ang = a["t"].float()[:, None] * torch.exp(torch.arange(half) * -kf)[None]
+        a["out"].copy_(torch.cat([ang.sin(), ang.cos()], -1))
+    elif k == "select_null":
+        c = a["c"]
+        c.copy_(torch.where(a["keep"].bool()[:, None], c, a["null_emb"].detach()[None].expand_as(c)))
+    elif k == "silu_concat_bf16":
+        v = F.silu(torch.cat([a["t_emb"], a["c_emb"]], 1))
+        a["out"].copy_(v.reshape(a["out"].shape).to(torch.bfloat16))
+    else:
+        raise ValueError(k)
+
+
+def run_program(prog, weights):
+    with torch.no_grad():
+        for r in weights.program.recs:
+            run_pack(r)
+        for off, b in prog._tc_bias_srcs:
+            weights.tc_bias[off:off + b.numel()].copy_(b.detach())
+        for r in prog.recs:
+            if isinstance(r, TapGemmRec):
+                run_tapgemm(r)
+            else:
+                run_kernel(r)
+    return prog.out

@@ -1,0 +1,83 @@
+"""Host planning logic (tile boxes, K schedules, packing rule) against torch convolutions -- CPU only."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ccdm_b200.plan import plan_conv, tile_box, n_tiling, TILE_M
+from tests.emu import tapgemm_emu, assemble_parity
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("g", [(64, 64), (32, 32), (16, 16), (8, 8), (4, 4), (128, 128), (192, 192), (96, 96),
+                               (48, 48), (24, 24), (12, 12), (6, 6), (3, 3), (2, 2), (1, 1)])
+@pytest.mark.parametrize("tb1", [False, True])
+def test_tile_box(g, tb1):
+    tw, th, tb = tile_box(g[0], g[1], force_tb1=tb1)
+    assert tw * th * tb == TILE_M and max(tw, th, tb) <= 256
+    if tb1:
+        assert tb == 1
+    # exact cover for the power-of-two grids the shipped configs use
+    if g[0] in (64, 32, 16, 8, 4) and not tb1:
+        assert g[0] % tw == 0 and g[1] % th == 0
+
+
+@pytest.mark.parametrize("cins,cout", [((64,), 64), ((128, 64), 64), ((32,), 96), ((72,), 72), ((96, 32), 32)])
+def test_conv3x3(cins, cout):
+    torch.manual_seed(0)
+    xs = [torch.randn(2, c, 6, 5) for c in cins]
+    w = torch.randn(cout, sum(cins), 3, 3)
+    ref = nhwc(F.conv2d(torch.cat(xs, 1), w, padding=1))
+    out = tapgemm_emu(plan_conv("3x3", cins, cout), [nhwc(x) for x in xs], w, 6, 5)[0]
+    assert rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("cins,cout", [((64,), 384), ((128, 64), 64), ((40,), 8)])
+def test_conv1x1(cins, cout):
+    torch.manual_seed(1)
+    xs = [torch.randn(2, c, 4, 4) for c in cins]
+    w = torch.randn(cout, sum(cins), 1, 1)
+    ref = nhwc(F.conv2d(torch.cat(xs, 1), w))
+    g = torch.rand(sum(cins)) + 0.5
+    out = tapgemm_emu(plan_conv("1x1", cins, cout), [nhwc(x) for x in xs], w, 4, 4)[0]
+    assert rel(out, ref) < 1e-5
+    # cin_gain fold == scaling the input channels
+    ref_g = nhwc(F.conv2d(torch.cat(xs, 1) * g[None, :, None, None], w))
+    out_g = tapgemm_emu(plan_conv("1x1", cins, cout), [nhwc(x) for x in xs], w, 4, 4, cin_gain=g)[0]
+    assert rel(out_g, ref_g) < 1e-5
+
+
+@pytest.mark.parametrize("c,cout,hw", [(64, 128, (8, 8)), (32, 32, (6, 4)), (72, 144, (4, 4))])
+def test_down4x4s2(c, cout, hw):
+    torch.manual_seed(2)
+    x = torch.randn(2, c, *hw)
+    w = torch.randn(cout, c, 4, 4)
+    ref = nhwc(F.conv2d(x, w, stride=2, padding=1))
+    out = tapgemm_emu(plan_conv("down4x4s2", (c,), cout), [nhwc(x)], w, hw[0] // 2, hw[1] // 2)[0]
+    assert rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("c,cout,hw", [(64, 64, (4, 4)), (128, 64, (3, 5)), (32, 32, (1, 1))])
+def test_up2x3x3(c, cout, hw):
+    torch.manual_seed(3)
+    x = torch.randn(2, c, *hw)
+    w = torch.randn(cout, c, 3, 3)
+    ref = nhwc(F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1))
+    out4 = tapgemm_emu(plan_conv("up2x3x3", (c,), cout), [nhwc(x)], w, hw[0], hw[1])
+    assert rel(assemble_parity(out4), ref) < 1e-5
+
+
+def test_n_tiling():
+    assert n_tiling(64, True) == (64, 64)
+    assert n_tiling(512, True) == (512, 512)
+    assert n_tiling(72, True) == (96, 96)
+    assert n_tiling(384, False) == (384, 128)
+    assert n_tiling(9000, False)[1] == 128 and n_tiling(9000, False)[0] % 128 == 0
+    with pytest.raises(ValueError):
+        n_tiling(576, True)
