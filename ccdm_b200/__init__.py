@@ -1,0 +1,11 @@
+"""ccdm_b200 -- B200-native (sm_100a) implementation of the CCDM denoiser hot path.
+
+Public surface mirrors CCDM_unified: ``Unet`` (models/unet.py), ``GaussianDiffusion`` (diffusion.py),
+``LabelEmbed`` (label_embedding.py), ``Trainer`` / ``EMA`` (trainer.py, ema_pytorch.py).
+The arithmetic runs in libccdm_b200.so (include/ccdm_b200.h); there is no CPU or PyTorch fallback.
+"""
+from .unet import Unet  # noqa: F401
+from .diffusion import GaussianDiffusion, ModelPrediction  # noqa: F401
+from .label_embedding import LabelEmbed  # noqa: F401
+
+__all__ = ["Unet", "GaussianDiffusion", "ModelPrediction", "LabelEmbed"]

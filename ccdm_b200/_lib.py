@@ -42,14 +42,14 @@ class StepArgs(C.Structure):
         ("out_cond", vp), ("out_null", vp), ("x", vp), ("noise", vp), ("pred_noise", vp), ("pred_x0", vp),
         ("B", i32), ("chw", i32), ("cond_scale", f32), ("rescaled_phi", f32), ("keep_parallel_frac", f32),
         ("remove_parallel", i32), ("objective", i32), ("clip_x0", i32), ("cfg_plus_plus", i32), ("sampler", i32),
-        ("coef", vp), ("step_counter", vp), ("advance", i32),
+        ("coef", vp), ("step_counter", vp), ("advance", i32), ("t_rows", vp),
     ]
 
 
 class QSampleArgs(C.Structure):
     _fields_ = [
         ("img01", vp), ("noise", vp), ("noise2", vp), ("cov", vp), ("keep", vp), ("t", vp), ("sqrt_acp", vp),
-        ("sqrt_1m_acp", vp), ("x0", vp), ("noise_out", vp), ("x_t", vp), ("B", i32), ("chw", i32),
+        ("sqrt_1m_acp", vp), ("x0", vp), ("noise_out", vp), ("x_t", vp), ("B", i32), ("chw", i32), ("normalize", i32),
     ]
 
 
@@ -79,6 +79,7 @@ SIGNATURES = {
     "ccdm_select_null": (C.c_int, [vp, vp, i32, vp, i32, i32, vp]),
     "ccdm_silu_concat_bf16": (C.c_int, [vp, i32, vp, i32, i32, vp, vp]),
     "ccdm_sampler_step": (C.c_int, [C.POINTER(StepArgs), vp]),
+    "ccdm_broadcast_step_i64": (C.c_int, [vp, vp, vp, i32, vp]),
     "ccdm_cfg_combine": (C.c_int, [vp, vp, vp, i32, i32, f32, f32, i32, f32, vp]),
     "ccdm_q_sample": (C.c_int, [C.POINTER(QSampleArgs), vp]),
     "ccdm_vicinal_loss": (C.c_int, [C.POINTER(LossArgs), vp]),

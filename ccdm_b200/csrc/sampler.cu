@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args 
   const long long base = (long long)b * a.chw;
   const float* cond = a.out_cond + base;
   const float* nul = a.out_null ? a.out_null + base : nullptr;
-  const int step = a.step_counter ? *a.step_counter : 0;
-  const float* cf = a.x ? a.coef + (long long)step * CCDM_STEP_NCOEF : nullptr;
+  const long long step = a.t_rows ? a.t_rows[b] : (a.step_counter ? (long long)*a.step_counter : 0);
+  const float* cf = a.x ? a.coef + step * CCDM_STEP_NCOEF : nullptr;
 
   float a_cond = 1.f, a_null = 0.f, resc = 1.f;
   if (nul) {
@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args 
     }
     if (a.pred_noise) a.pred_noise[base + i] = eps;
     if (a.pred_x0) a.pred_x0[base + i] = x0;
+    if (a.sampler == 2) continue;  // predictions only
     float xn;
     if (a.sampler == 0) {  // DDIM, diffusion.py:450-464
       if (cf[7] != 0.f) {
@@ -149,6 +150,12 @@ __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args 
 // has read the old value (stream order) before it changes.
 __global__ void advance_counter_kernel(int* c) { *c += 1; }
 
+__global__ void broadcast_step_kernel(const long long* __restrict__ table, const int* __restrict__ counter,
+                                      long long* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = table[*counter];
+}
+
 // ---------------------------------------------------------------------------- q_sample
 __global__ void q_sample_kernel(const ccdm_qsample_args a) {
   const long long total = (long long)a.B * a.chw;
@@ -156,7 +163,7 @@ __global__ void q_sample_kernel(const ccdm_qsample_args a) {
        i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / a.chw);
     const long long t = a.t[b];
-    const float x0 = a.img01[i] * 2.f - 1.f;
+    const float x0 = a.normalize ? a.img01[i] * 2.f - 1.f : a.img01[i];
     float nz = a.noise[i];
     if (a.cov) {
       if (a.keep[b]) nz *= sqrtf(a.cov[i]);
@@ -254,8 +261,8 @@ using namespace ccdm;
 
 static int check_step(const ccdm_step_args* a) {
   CCDM_REQUIRE(a && a->out_cond && a->coef && a->B > 0 && a->chw > 1, CCDM_ERR_BAD_ARG, "sampler_step: bad args");
-  CCDM_REQUIRE(a->noise || a->sampler == 0, CCDM_ERR_BAD_ARG, "sampler_step: the DDPM update needs a noise draw");
-  CCDM_REQUIRE(a->objective >= 0 && a->objective <= 2 && (a->sampler == 0 || a->sampler == 1), CCDM_ERR_BAD_ARG,
+  CCDM_REQUIRE(a->noise || a->sampler != 1, CCDM_ERR_BAD_ARG, "sampler_step: the DDPM update needs a noise draw");
+  CCDM_REQUIRE(a->objective >= 0 && a->objective <= 2 && a->sampler >= 0 && a->sampler <= 2, CCDM_ERR_BAD_ARG,
                "sampler_step: objective=%d sampler=%d", a->objective, a->sampler);
   CCDM_REQUIRE(a->out_null || a->cond_scale == 1.f, CCDM_ERR_BAD_ARG,
                "sampler_step: cond_scale != 1 needs the unconditional output");
@@ -276,6 +283,14 @@ extern "C" int ccdm_sampler_step(const ccdm_step_args* a, void* stream) {
     rc = after_launch("advance_counter_kernel");
   }
   return rc;
+}
+
+extern "C" int ccdm_broadcast_step_i64(const int64_t* table, const int32_t* step_counter, int64_t* out, int32_t n,
+                                       void* stream) {
+  CCDM_REQUIRE(table && step_counter && out && n > 0, CCDM_ERR_BAD_ARG, "broadcast_step: bad args");
+  broadcast_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const long long*)table, step_counter,
+                                                                           (long long*)out, n);
+  return after_launch("broadcast_step_kernel");
 }
 
 extern "C" int ccdm_cfg_combine(const float* cond, const float* null_out, float* guided, int32_t B, int32_t chw,

@@ -142,6 +142,31 @@ class Program:
             if rc != 0:
                 L.check(rc, name)
 
+    def run_timed(self):
+        """Eager run on torch's current stream with a CUDA event between launches.
+        Returns [(record, milliseconds)] -- the per-kernel durations bench.py builds its roofline from."""
+        stream = torch.cuda.current_stream().cuda_stream
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.calls) + 1)]
+        evs[0].record()
+        for i, (fn, args, name) in enumerate(self.calls):
+            rc = fn(*args, stream)
+            if rc != 0:
+                L.check(rc, name)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        return [(self.recs[i], evs[i].elapsed_time(evs[i + 1])) for i in range(len(self.calls))]
+
+
+def tapgemm_flops(r: "TapGemmRec") -> float:
+    """Algorithmic FLOPs (2*MAC) of the reference convolution this record computes:
+    2 * B * Hout * Wout * Cout * Cin * kh * kw -- the nearest-2x fold and padded channels are NOT credited."""
+    cin = sum(r.plan.cins)
+    if r.plan.out_parity:
+        pos = r.gB * (2 * r.gH) * (2 * r.gW)
+    else:
+        pos = r.gB * r.gH * r.gW
+    return 2.0 * pos * r.N * cin * r.plan.ntaps
+
 
 def _fill_tapgemm(r: TapGemmRec) -> L.TapGemmArgs:
     a = L.TapGemmArgs()

@@ -171,12 +171,17 @@ typedef struct ccdm_step_args {
   float* pred_x0;
   int32_t B, chw;
   float cond_scale, rescaled_phi, keep_parallel_frac;
-  int32_t remove_parallel, objective, clip_x0, cfg_plus_plus, sampler; /* sampler: 0 = DDIM, 1 = DDPM */
+  int32_t remove_parallel, objective, clip_x0, cfg_plus_plus;
+  int32_t sampler;       /* 0 = DDIM update, 1 = DDPM update, 2 = predictions only (x is read, not written) */
   const float* coef;
-  int32_t* step_counter;
+  int32_t* step_counter; /* coef row = *step_counter (all samples), unless t_rows is given */
   int32_t advance;
+  const int64_t* t_rows; /* optional [B]: per-sample coef row (model_predictions with arbitrary timesteps) */
 } ccdm_step_args;
 int ccdm_sampler_step(const ccdm_step_args* args, void* stream);
+/* out[i] = table[*step_counter] for i < n  -- refreshes the timestep input of a captured step graph
+ * (torch.full((batch,), time), diffusion.py:440 / :363). */
+int ccdm_broadcast_step_i64(const int64_t* table, const int32_t* step_counter, int64_t* out, int32_t n, void* stream);
 /* Guidance arithmetic alone (forward_with_cond_scale without the sampler): guided = f(cond, null). */
 int ccdm_cfg_combine(const float* cond, const float* null_out, float* guided, int32_t B, int32_t chw,
                      float cond_scale, float rescaled_phi, int32_t remove_parallel, float keep_parallel_frac,
@@ -188,7 +193,7 @@ int ccdm_cfg_combine(const float* cond, const float* null_out, float* guided, in
  *   loss:     diffusion.py:570-594,597-730 (target select, MSE, /Hy, loss_weight[t], vicinal batch weights)
  * ------------------------------------------------------------------------------------------------------------ */
 typedef struct ccdm_qsample_args {
-  const float* img01;    /* [B][chw] images in [0,1] */
+  const float* img01;    /* [B][chw] images; in [0,1] when normalize != 0, already in [-1,1] otherwise */
   const float* noise;    /* [B][chw] N(0,1) */
   const float* noise2;   /* [B][chw] second draw used for null rows under use_Hy (may be NULL) */
   const float* cov;      /* [B][chw] exp(-y2cov) or NULL */
@@ -196,10 +201,11 @@ typedef struct ccdm_qsample_args {
   const int64_t* t;      /* [B] */
   const float* sqrt_acp; /* [T] */
   const float* sqrt_1m_acp;
-  float* x0;             /* out: img*2-1 */
+  float* x0;             /* out: img*2-1 (normalize != 0) or a copy of img */
   float* noise_out;      /* out: the noise actually mixed in (scaled by sqrt(cov) on conditional rows) */
   float* x_t;            /* out */
   int32_t B, chw;
+  int32_t normalize;
 } ccdm_qsample_args;
 int ccdm_q_sample(const ccdm_qsample_args* args, void* stream);
 
