@@ -202,15 +202,20 @@ def test_rc64_ddim_vs_oracle(objective, use_Hy):
     x = torch.randn(shape, device="cuda")
     if use_Hy:
         x = x * torch.sqrt(cov)
-    worst = 0.0
+    worst, worst_derived = 0.0, 0.0
     for (tm, tn) in pairs[:: max(1, S // 5)]:
         tt = torch.full((B,), tm, device="cuda", dtype=torch.long)
-        eps_o, x0_o = oracle.model_predictions(sch, net_o, x, tt, emb, 1.5, 0.7, clip_x_start=True)
-        mp = gd.model_predictions(x, tt, emb, cond_scale=1.5, rescaled_phi=0.7, clip_x_start=True)
-        worst = max(worst, relerr(mp.pred_noise, eps_o), relerr(mp.pred_x_start, x0_o))
-        x = x0_o * 0.5 + 0.5 * x                                   # move to another plausible state
-    print(f"   teacher-forced worst rel err {worst:.3e}")
+        eps_o, x0_o = oracle.model_predictions(sch, net_o, x, tt, emb, 1.5, 0.7, clip_x_start=False)
+        mp = gd.model_predictions(x, tt, emb, cond_scale=1.5, rescaled_phi=0.7, clip_x_start=False)
+        # the network's own (guided) prediction carries the bf16 tolerance; the quantity derived from it through
+        # 1/sqrt(1/acp - 1) (eps from x0, or x0 from eps) amplifies that error at the ends of the schedule
+        native = (relerr(mp.pred_x_start, x0_o) if objective == "pred_x0" else relerr(mp.pred_noise, eps_o))
+        derived = (relerr(mp.pred_noise, eps_o) if objective == "pred_x0" else relerr(mp.pred_x_start, x0_o))
+        worst, worst_derived = max(worst, native), max(worst_derived, derived)
+        x = oracle.q_sample(sch, x0_o.clamp(-1, 1), torch.full((B,), max(tn, 0), device="cuda"), torch.randn_like(x))
+    print(f"   teacher-forced worst rel err: network prediction {worst:.3e}, derived {worst_derived:.3e}")
     assert worst < BF16_TOL
+    assert worst_derived < 5 * BF16_TOL
 
 
 def test_ddpm_vs_oracle():
