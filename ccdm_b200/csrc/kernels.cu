@@ -219,48 +219,53 @@ __global__ void linattn_fold_kernel(const float* __restrict__ w_out, const float
 }
 
 // ============================================================================ bottleneck softmax attention
-// unet.py:228-240.  One CTA per (sample, head), one thread per query token (n <= 64, dim_head <= 64).
+// unet.py:228-240.  grid = (sample*head, query blocks of 64); one thread per query token, keys / values staged
+// through shared memory 64 tokens at a time with a running (online) softmax.  The shipped configs have 9 or 16
+// tokens here; larger token counts just loop.
+template <int DH>
 __global__ void __launch_bounds__(64) attention_small_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                              __nv_bfloat16* __restrict__ out, int n, int heads,
-                                                             int dh, float scale) {
-  extern __shared__ float s_att[];
-  const int pitch = dh + 1;
-  float* sq = s_att;
-  float* sk = sq + n * pitch;
-  float* sv = sk + n * pitch;
+                                                             float scale) {
+  __shared__ float sk[64][DH + 1], sv[64][DH + 1];
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int hid = heads * dh, ld = 3 * hid;
-  const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * dh;
-  for (int i = threadIdx.x; i < n * dh; i += blockDim.x) {
-    const int tok = i / dh, dd = i % dh;
-    const __nv_bfloat16* p = base + (long long)tok * ld + dd;
-    sq[tok * pitch + dd] = __bfloat162float(p[0]) * scale;
-    sk[tok * pitch + dd] = __bfloat162float(p[hid]);
-    sv[tok * pitch + dd] = __bfloat162float(p[2 * hid]);
+  const int hid = heads * DH, ld = 3 * hid;
+  const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * DH;
+  const int i = blockIdx.y * 64 + threadIdx.x;
+  const bool active = i < n;
+  float q[DH], acc[DH];
+#pragma unroll
+  for (int dd = 0; dd < DH; ++dd) {
+    q[dd] = active ? __bfloat162float(base[(long long)i * ld + dd]) * scale : 0.f;
+    acc[dd] = 0.f;
   }
-  __syncthreads();
-  const int i = threadIdx.x;
-  if (i >= n) return;
-  float sim[64];
-  float mx = -FLT_MAX;
-  for (int j = 0; j < n; ++j) {
-    float s = 0.f;
-    for (int dd = 0; dd < dh; ++dd) s = fmaf(sq[i * pitch + dd], sk[j * pitch + dd], s);
-    sim[j] = s;
-    mx = fmaxf(mx, s);
+  float m_run = -FLT_MAX, l_run = 0.f;
+  for (int j0 = 0; j0 < n; j0 += 64) {
+    const int rows = min(64, n - j0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < rows * DH; e += 64) {
+      const int tok = e / DH, dd = e % DH;
+      const __nv_bfloat16* p = base + (long long)(j0 + tok) * ld + dd;
+      sk[tok][dd] = __bfloat162float(p[hid]);
+      sv[tok][dd] = __bfloat162float(p[2 * hid]);
+    }
+    __syncthreads();
+    for (int j = 0; j < rows; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < DH; ++dd) s = fmaf(q[dd], sk[j][dd], s);
+      const float m_new = fmaxf(m_run, s);
+      const float corr = __expf(m_run - m_new), p = __expf(s - m_new);
+      l_run = l_run * corr + p;
+#pragma unroll
+      for (int dd = 0; dd < DH; ++dd) acc[dd] = acc[dd] * corr + p * sv[j][dd];
+      m_run = m_new;
+    }
   }
-  float sum = 0.f;
-  for (int j = 0; j < n; ++j) {
-    sim[j] = __expf(sim[j] - mx);
-    sum += sim[j];
-  }
-  const float inv = 1.f / sum;
-  __nv_bfloat16* o = out + ((long long)b * n + i) * hid + h * dh;
-  for (int dd = 0; dd < dh; ++dd) {
-    float a = 0.f;
-    for (int j = 0; j < n; ++j) a = fmaf(sim[j], sv[j * pitch + dd], a);
-    o[dd] = __float2bfloat16(a * inv);
-  }
+  if (!active) return;
+  const float inv = 1.f / l_run;
+  __nv_bfloat16* o = out + ((long long)b * n + i) * hid + h * DH;
+#pragma unroll
+  for (int dd = 0; dd < DH; ++dd) o[dd] = __float2bfloat16(acc[dd] * inv);
 }
 
 // ============================================================================ embedding MLPs
@@ -406,15 +411,18 @@ extern "C" int ccdm_linattn_fold(const float* w_out, const float* ctx, void* wfo
 
 extern "C" int ccdm_attention_small(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head,
                                     float scale, void* stream) {
-  CCDM_REQUIRE(qkv && out && B > 0, CCDM_ERR_BAD_ARG, "attention_small: bad args");
-  CCDM_REQUIRE(n >= 1 && n <= 64 && dim_head >= 1 && dim_head <= 64, CCDM_ERR_UNSUPPORTED_SHAPE,
-               "attention_small: n=%d dim_head=%d (bottleneck attention handles <= 64 tokens of <= 64 dims)", n,
-               dim_head);
-  const size_t smem = (size_t)3 * n * (dim_head + 1) * sizeof(float);
-  CCDM_REQUIRE(smem <= 48 * 1024, CCDM_ERR_UNSUPPORTED_SHAPE, "attention_small: n=%d x dim_head=%d too large", n,
-               dim_head);
-  attention_small_kernel<<<B * heads, 64, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, n,
-                                                                     heads, dim_head, scale);
+  CCDM_REQUIRE(qkv && out && B > 0 && n >= 1 && heads >= 1, CCDM_ERR_BAD_ARG, "attention_small: bad args");
+  dim3 grid(B * heads, (n + 63) / 64);
+  const __nv_bfloat16* in = (const __nv_bfloat16*)qkv;
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dim_head) {
+    case 16: attention_small_kernel<16><<<grid, 64, 0, s>>>(in, o, n, heads, scale); break;
+    case 32: attention_small_kernel<32><<<grid, 64, 0, s>>>(in, o, n, heads, scale); break;
+    case 64: attention_small_kernel<64><<<grid, 64, 0, s>>>(in, o, n, heads, scale); break;
+    default:
+      CCDM_REQUIRE(false, CCDM_ERR_UNSUPPORTED_SHAPE, "attention_small: dim_head=%d (supported: 16, 32, 64)", dim_head);
+  }
   return after_launch("attention_small_kernel");
 }
 

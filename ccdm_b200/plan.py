@@ -1,10 +1,15 @@
-"""Host-side planning for the tap-GEMM engine: tile boxes, K-block schedules and weight-packing schedules.
+"""Host-side planning for the tap-GEMM engine: tile boxes, K schedules and weight-packing schedules.
 
 Pure Python (no CUDA), so the CPU test-suite can check every schedule against ``torch.nn.functional.conv2d``.
 
-A K block is (source view, dw, dh, c0): 64 input channels starting at ``c0`` of view ``src`` read at the output
-position shifted by (dh, dw).  The matching packing entry (cin0, nvalid, tapmask) says which slice of the fp32
-``[Cout][Cin_total][taps]`` weight lands in that block (``tapmask`` sums several filter taps: nearest-2x fold).
+The K loop of a convolution is a list of *load groups*.  A group (src, dw, dh0, c0) is ONE TMA box: 64 input
+channels starting at ``c0`` of view ``src``, read at the output tile shifted by (dh0, dw) and ``th + R - 1`` rows
+tall.  It feeds ``R`` vertically adjacent filter taps (dh = dh0 .. dh0+R-1): tap r simply starts ``r*tw`` rows
+further down the same shared-memory box, so the rows a 3x3 window shares vertically are fetched once instead of
+three times.  ``R`` is uniform per layer (3 for 3x3, 2 for the stride-2 and the nearest-2x convs, 1 for 1x1 or
+whenever a tile spans several samples).  The packed weight has one 64-wide K block per (group, r), in that order;
+the packing entry (cin0, nvalid, tapmask) says which slice of the fp32 ``[Cout][Cin_total][taps]`` weight lands
+there (``tapmask`` sums several filter taps: nearest-2x fold).
 
 Reference call sites: CCDM_unified/models/unet.py:74-81 (Upsample / Downsample), :139 (3x3), :165,195,198 (1x1).
 """
@@ -32,14 +37,16 @@ def _pow2_ceil(n: int) -> int:
     return p
 
 
-def tile_box(gw: int, gh: int, force_tb1: bool = False) -> Tuple[int, int, int]:
+def tile_box(gw: int, gh: int, force_tb1: bool = False, square: bool = False) -> Tuple[int, int, int]:
     """(tw, th, tb) with tw*th*tb == 128 for an output grid of gw x gh positions per sample.
 
     Prefers boxes that divide the grid exactly (no masked rows); falls back to the next power of two for odd
-    sizes (3x3, 6x6 bottlenecks of the 192-px model).  ``force_tb1`` keeps a tile inside one sample (per-sample
-    weights) at the price of masked rows on tiny grids.
+    sizes (3x3, 6x6 bottlenecks of the 192-px model).  ``square`` asks for a 16x8 box when the grid allows it:
+    with vertical tap reuse the halo overhead is (th+2)/th, so tall boxes fetch less.  ``force_tb1`` keeps a tile
+    inside one sample (per-sample weights) at the price of masked rows on tiny grids.
     """
-    tw = _pow2_floor_div(gw, 64)
+    cap_w = 16 if (square and gw % 16 == 0 and gh % 8 == 0) else 64
+    tw = _pow2_floor_div(gw, cap_w)
     if tw < 4 and tw < gw:
         tw = min(_pow2_ceil(gw), 64)
     cap_h = TILE_M // tw
@@ -53,6 +60,12 @@ def tile_box(gw: int, gh: int, force_tb1: bool = False) -> Tuple[int, int, int]:
     return tw, th, tb
 
 
+def can_reuse_rows(tile: Tuple[int, int, int]) -> bool:
+    """Vertical tap reuse needs one sample per tile and 8-row-aligned tap offsets inside the shared-memory box."""
+    tw, th, tb = tile
+    return tb == 1 and tw % 8 == 0
+
+
 @dataclass
 class ConvPlan:
     """Everything ccdm_tapgemm / ccdm_pack_weights need for one layer, except pointers."""
@@ -61,12 +74,17 @@ class ConvPlan:
     cout: int
     ntaps: int                            # kh*kw of the fp32 weight
     nz: int
-    nkb: int
-    sched: List[Tuple[int, int, int, int]] = field(default_factory=list)    # [nz*nkb] (src, dw, dh, c0)
+    ngroups: int                          # load groups per sub-problem
+    R: int                                # vertical taps served by one load group
+    sched: List[Tuple[int, int, int, int]] = field(default_factory=list)    # [nz*ngroups] (src, dw, dh0, c0)
     psched: List[Tuple[int, int, int, int]] = field(default_factory=list)   # [nz*nkb] (cin0, nvalid, tapmask, 0)
     n_views: int = 1                      # views per source tensor (4 parity planes for the stride-2 conv)
     out_parity: bool = False              # nz == 4 output parity planes (nearest-2x + 3x3)
     stride: int = 1
+
+    @property
+    def nkb(self) -> int:
+        return self.ngroups * self.R
 
     @property
     def n_src(self) -> int:
@@ -77,56 +95,65 @@ def _chunks(c: int):
     return [(c0, min(KB, c - c0)) for c0 in range(0, c, KB)]
 
 
-def plan_conv(kind: str, cins: Sequence[int], cout: int) -> ConvPlan:
-    """kind: '1x1' | '3x3' | 'down4x4s2' | 'up2x3x3'."""
+def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = False) -> ConvPlan:
+    """kind: '1x1' | '3x3' | 'down4x4s2' | 'up2x3x3'.  ``reuse_rows`` groups vertically adjacent taps (R > 1)."""
     cins = tuple(int(c) for c in cins)
     offs = [sum(cins[:i]) for i in range(len(cins))]
     sched, psched = [], []
+
+    def emit(src_view, s, dw, rows):
+        """rows: [(dh, tapmask)] vertically consecutive taps of one column offset dw for source s."""
+        for c0, nv in _chunks(cins[s]):
+            if reuse_rows:
+                assert all(rows[i + 1][0] == rows[i][0] + 1 for i in range(len(rows) - 1))
+                sched.append((src_view, dw, rows[0][0], c0))
+                for _, mask in rows:
+                    psched.append((offs[s] + c0, nv, mask, 0))
+            else:
+                for dh, mask in rows:
+                    sched.append((src_view, dw, dh, c0))
+                    psched.append((offs[s] + c0, nv, mask, 0))
+
     if kind == "1x1":
-        for s, c in enumerate(cins):
-            for c0, nv in _chunks(c):
-                sched.append((s, 0, 0, c0))
-                psched.append((offs[s] + c0, nv, 1, 0))
-        return ConvPlan(kind, cins, cout, 1, 1, len(sched), sched, psched)
+        for s in range(len(cins)):
+            emit(s, s, 0, [(0, 1)])
+        R = 1
+        return ConvPlan(kind, cins, cout, 1, 1, len(sched), 1, sched, psched)
     if kind == "3x3":
-        for r in range(3):
-            for q in range(3):
-                for s, c in enumerate(cins):
-                    for c0, nv in _chunks(c):
-                        sched.append((s, q - 1, r - 1, c0))
-                        psched.append((offs[s] + c0, nv, 1 << (r * 3 + q), 0))
-        return ConvPlan(kind, cins, cout, 9, 1, len(sched), sched, psched)
+        for q in range(3):
+            for s in range(len(cins)):
+                emit(s, s, q - 1, [(r - 1, 1 << (r * 3 + q)) for r in range(3)])
+        R = 3 if reuse_rows else 1
+        return ConvPlan(kind, cins, cout, 9, 1, len(sched), R, sched, psched)
     if kind == "down4x4s2":
         # out[ho,wo] = sum_{r,q} W[r,q] x[2ho-1+r, 2wo-1+q];  2ho-1+r = 2(ho+dr)+pr  with (dr,pr) below.
         # The 4 parity planes x[pr::2, pq::2] are separate strided TMA views: view index = src*4 + pr*2 + pq.
-        split = {0: (-1, 1), 1: (0, 0), 2: (0, 1), 3: (1, 0)}
-        for r in range(4):
-            for q in range(4):
-                dr, pr = split[r]
-                dq, pq = split[q]
-                for s, c in enumerate(cins):
-                    for c0, nv in _chunks(c):
-                        sched.append((s * 4 + pr * 2 + pq, dq, dr, c0))
-                        psched.append((offs[s] + c0, nv, 1 << (r * 4 + q), 0))
-        return ConvPlan(kind, cins, cout, 16, 1, len(sched), sched, psched, n_views=4, stride=2)
+        taps = {1: [(-1, 0), (0, 2)], 0: [(0, 1), (1, 3)]}       # parity -> [(shift, filter index)]
+        for pr in (1, 0):
+            for pq in (1, 0):
+                for dq, q in taps[pq]:
+                    for s in range(len(cins)):
+                        emit(s * 4 + pr * 2 + pq, s, dq, [(dr, 1 << (r * 4 + q)) for dr, r in taps[pr]])
+        R = 2 if reuse_rows else 1
+        return ConvPlan(kind, cins, cout, 16, 1, len(sched), R, sched, psched, n_views=4, stride=2)
     if kind == "up2x3x3":
         # nearest-2x then 3x3/p1: output (2a+pa, 2b+pb) sees a 2x2 window of the low-res input; taps that hit the
         # same low-res pixel are summed at packing time (9 -> 4 taps, 2.25x fewer MACs).
-        rows = {0: [(-1, (0,)), (0, (1, 2))], 1: [(0, (0, 1)), (1, (2,))]}
+        win = {0: [(-1, (0,)), (0, (1, 2))], 1: [(0, (0, 1)), (1, (2,))]}
         for pa in range(2):
             for pb in range(2):
-                for dh, rset in rows[pa]:
-                    for dw, qset in rows[pb]:
+                for dw, qset in win[pb]:
+                    rows = []
+                    for dh, rset in win[pa]:
                         mask = 0
                         for r in rset:
                             for q in qset:
                                 mask |= 1 << (r * 3 + q)
-                        for s, c in enumerate(cins):
-                            for c0, nv in _chunks(c):
-                                sched.append((s, dw, dh, c0))
-                                psched.append((offs[s] + c0, nv, mask, 0))
-        nkb = len(sched) // 4
-        return ConvPlan(kind, cins, cout, 9, 4, nkb, sched, psched, out_parity=True)
+                        rows.append((dh, mask))
+                    for s in range(len(cins)):
+                        emit(s, s, dw, rows)
+        R = 2 if reuse_rows else 1
+        return ConvPlan(kind, cins, cout, 9, 4, len(sched) // 4, R, sched, psched, out_parity=True)
     raise ValueError(kind)
 
 

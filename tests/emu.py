@@ -54,10 +54,12 @@ def tapgemm_emu(plan: ConvPlan, srcs, w, gh, gw, n_rows=None, cin_gain=None):
     outs = []
     for z in range(plan.nz):
         acc = 0
-        for kb in range(plan.nkb):
-            src, dw, dh, c0 = plan.sched[z * plan.nkb + kb]
-            a = shifted(views[src], dh, dw, gh, gw, c0)
-            acc = acc + a @ packed[z, :w.shape[0], kb * KB:(kb + 1) * KB].t()
+        for g in range(plan.ngroups):
+            src, dw, dh0, c0 = plan.sched[z * plan.ngroups + g]
+            for r in range(plan.R):
+                kb = g * plan.R + r
+                a = shifted(views[src], dh0 + r, dw, gh, gw, c0)
+                acc = acc + a @ packed[z, :w.shape[0], kb * KB:(kb + 1) * KB].t()
         outs.append(acc)
     return torch.stack(outs)
 

@@ -41,8 +41,9 @@ def run_tapgemm(r: TapGemmRec):
     for z in range(r.plan.nz):
         acc = torch.zeros(gB, gH, gW, r.N)
         for kb in range(r.plan.nkb):
-            src, dw, dh, c0 = r.plan.sched[z * r.plan.nkb + kb]
-            a = shifted(views[src], dh, dw, gH, gW, c0)                      # [vB, gH, gW, 64]
+            g, rr = divmod(kb, r.plan.R)
+            src, dw, dh0, c0 = r.plan.sched[z * r.plan.ngroups + g]
+            a = shifted(views[src], dh0 + rr, dw, gH, gW, c0)                # [vB, gH, gW, 64]
             a = a[:gB]
             if r.w_batch_rows:
                 wrows = torch.stack([wp[b * r.w_batch_rows: b * r.w_batch_rows + r.N, kb * KB:(kb + 1) * KB]

@@ -39,7 +39,7 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     a = _lib.TapGemmArgs()
     assert handle.ccdm_tapgemm(ctypes.byref(a), None) == -1          # CCDM_ERR_BAD_ARG
     assert b"n_src" in handle.ccdm_last_error()
-    assert handle.ccdm_attention_small(1, 1, 1, 4096, 4, 32, 1.0, None) == -2   # CCDM_ERR_UNSUPPORTED_SHAPE
+    assert handle.ccdm_attention_small(1, 1, 1, 16, 4, 24, 1.0, None) == -2     # CCDM_ERR_UNSUPPORTED_SHAPE
 
 
 def test_no_cpu_fallback():

@@ -28,13 +28,16 @@ def test_tile_box(g, tb1):
         assert g[0] % tw == 0 and g[1] % th == 0
 
 
+@pytest.mark.parametrize("reuse", [False, True])
 @pytest.mark.parametrize("cins,cout", [((64,), 64), ((128, 64), 64), ((32,), 96), ((72,), 72), ((96, 32), 32)])
-def test_conv3x3(cins, cout):
+def test_conv3x3(cins, cout, reuse):
     torch.manual_seed(0)
     xs = [torch.randn(2, c, 6, 5) for c in cins]
     w = torch.randn(cout, sum(cins), 3, 3)
     ref = nhwc(F.conv2d(torch.cat(xs, 1), w, padding=1))
-    out = tapgemm_emu(plan_conv("3x3", cins, cout), [nhwc(x) for x in xs], w, 6, 5)[0]
+    plan = plan_conv("3x3", cins, cout, reuse_rows=reuse)
+    assert plan.R == (3 if reuse else 1) and plan.nkb == 9 * sum((c + 63) // 64 for c in cins)
+    out = tapgemm_emu(plan, [nhwc(x) for x in xs], w, 6, 5)[0]
     assert rel(out, ref) < 1e-5
 
 
@@ -53,23 +56,29 @@ def test_conv1x1(cins, cout):
     assert rel(out_g, ref_g) < 1e-5
 
 
+@pytest.mark.parametrize("reuse", [False, True])
 @pytest.mark.parametrize("c,cout,hw", [(64, 128, (8, 8)), (32, 32, (6, 4)), (72, 144, (4, 4))])
-def test_down4x4s2(c, cout, hw):
+def test_down4x4s2(c, cout, hw, reuse):
     torch.manual_seed(2)
     x = torch.randn(2, c, *hw)
     w = torch.randn(cout, c, 4, 4)
     ref = nhwc(F.conv2d(x, w, stride=2, padding=1))
-    out = tapgemm_emu(plan_conv("down4x4s2", (c,), cout), [nhwc(x)], w, hw[0] // 2, hw[1] // 2)[0]
+    plan = plan_conv("down4x4s2", (c,), cout, reuse_rows=reuse)
+    assert plan.R == (2 if reuse else 1)
+    out = tapgemm_emu(plan, [nhwc(x)], w, hw[0] // 2, hw[1] // 2)[0]
     assert rel(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("reuse", [False, True])
 @pytest.mark.parametrize("c,cout,hw", [(64, 64, (4, 4)), (128, 64, (3, 5)), (32, 32, (1, 1))])
-def test_up2x3x3(c, cout, hw):
+def test_up2x3x3(c, cout, hw, reuse):
     torch.manual_seed(3)
     x = torch.randn(2, c, *hw)
     w = torch.randn(cout, c, 3, 3)
     ref = nhwc(F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1))
-    out4 = tapgemm_emu(plan_conv("up2x3x3", (c,), cout), [nhwc(x)], w, hw[0], hw[1])
+    plan = plan_conv("up2x3x3", (c,), cout, reuse_rows=reuse)
+    assert plan.R == (2 if reuse else 1) and plan.nz == 4
+    out4 = tapgemm_emu(plan, [nhwc(x)], w, hw[0], hw[1])
     assert rel(assemble_parity(out4), ref) < 1e-5
 
 
