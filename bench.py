@@ -268,7 +268,7 @@ def run_b200(args):
                 if isinstance(r, TapGemmRec):
                     fl = tapgemm_flops(r)
                     rows.append({"name": r.name, "kind": r.plan.kind, "grid": [r.gB, r.gH, r.gW], "cin": sum(r.plan.cins),
-                                 "N": r.N, "n_tile": r.n_tile, "nkb": r.plan.nkb, "ms": ms_, "tflops": fl / ms_ / 1e9})
+                                 "N": r.N, "n_tile": r.n_tile, "nkb": r.plan.nkb, "R": r.plan.R, "tile": list(r.tile), "ms": ms_, "tflops": fl / ms_ / 1e9})
                 else:
                     rows.append({"name": getattr(r, "kind", "?"), "ms": ms_})
             json.dump({"batch": 2 * B, "total_ms": all_ms, "rows": rows}, f, indent=1)

@@ -28,7 +28,7 @@ class TapGemmArgs(C.Structure):
     _fields_ = [
         ("n_src", i32), ("src", View * MAX_SRC),
         ("gW", i32), ("gH", i32), ("gB", i32), ("tw", i32), ("th", i32), ("tb", i32),
-        ("nz", i32), ("nkb", i32), ("sched", vp), ("wpacked", vp),
+        ("nz", i32), ("ngroups", i32), ("R", i32), ("sched", vp), ("wpacked", vp),
         ("n_rows", i32), ("w_batch_rows", i32), ("N", i32), ("n_tile", i32), ("flags", C.c_uint32),
         ("bias", vp), ("rowss", vp), ("gain", vp), ("gain_mul", f32), ("scale_shift", vp), ("ss_ld", i32), ("ss_off", i32),
         ("resid", vp), ("rsW", i64), ("rsH", i64), ("rsB", i64),

@@ -324,6 +324,29 @@ __global__ void __launch_bounds__(128) linear_small_kernel(const float* __restri
   }
 }
 
+// Eval-mode variant (running statistics or no BatchNorm): one lane per batch row, one warp per (output feature,
+// 32-row slab), so the batch dimension is parallel instead of a serial loop.
+__global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restrict__ x, int B, int in_dim,
+                                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                                          int out_dim, const float* __restrict__ bn_w,
+                                                          const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
+                                                          const float* __restrict__ bn_var, int act,
+                                                          float* __restrict__ y, long long y_ld) {
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.y * 32 + (threadIdx.x & 31);
+  if (o >= out_dim || b >= B) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)b * in_dim);
+  const float4* wr = reinterpret_cast<const float4*>(w + (long long)o * in_dim);
+  float acc = 0.f;
+  for (int k = 0; k < in_dim / 4; ++k) {
+    const float4 a = __ldg(xr + k), c = __ldg(wr + k);
+    acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
+  }
+  acc += bias ? bias[o] : 0.f;
+  if (bn_w) acc = (acc - bn_mean[o]) * rsqrtf(bn_var[o] + 1e-5f) * bn_w[o] + bn_b[o];
+  y[(long long)b * y_ld + o] = act_apply(acc, act);
+}
+
 // unet.py:107-115: sin | cos of t * exp(-log(1e4) * i / (half-1))
 __global__ void time_features_kernel(const long long* __restrict__ t, int B, int dim, float* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -432,6 +455,12 @@ extern "C" int ccdm_linear_small(const float* x, int32_t B, int32_t in_dim, cons
   CCDM_REQUIRE(x && w && y && B > 0 && in_dim > 0 && out_dim > 0 && y_ld >= out_dim, CCDM_ERR_BAD_ARG,
                "linear_small: bad args");
   CCDM_REQUIRE(!bn_w || (bn_b && bn_mean && bn_var), CCDM_ERR_BAD_ARG, "linear_small: incomplete BatchNorm pointers");
+  if (!(bn_w && bn_train) && in_dim % 4 == 0) {
+    dim3 grid((out_dim + 7) / 8, (B + 31) / 32);
+    linear_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, in_dim, w, bias, out_dim, bn_w, bn_b, bn_mean,
+                                                               bn_var, act, y, y_ld);
+    return after_launch("linear_rows_kernel");
+  }
   linear_small_kernel<<<(out_dim + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x, B, in_dim, w, bias, out_dim, bn_w, bn_b,
                                                                            bn_mean, bn_var, bn_train, act, y, y_ld);
   return after_launch("linear_small_kernel");

@@ -1,17 +1,22 @@
-// Tap-GEMM: implicit-GEMM convolution / linear engine for sm_100a.
+// Tap-GEMM: persistent implicit-GEMM convolution / linear engine for sm_100a (tcgen05 + TMEM + TMA).
 //
 //   D[128 pixels x n_tile] (fp32, TMEM)  +=  A[128 x 64] (bf16, smem via TMA)  .  B[n_tile x 64]^T (bf16, smem via TMA)
 //
-// One CTA owns one 128-row output tile (a tb x th x tw box of output positions) and n_tile output channels.
-// Warp 0 / lane 0 : TMA producer.  One K block = one (source view, filter tap, 64-channel chunk): a 4-D box
-//                   {64ch, tw, th, tb} read at the tap-shifted position; out-of-range coordinates are
-//                   zero-filled by TMA, which is the convolution's zero padding.  Rows land 128 B apart in the
-//                   canonical SWIZZLE_128B K-major layout that tcgen05.mma consumes directly.
-// Warp 1 / lane 0 : tcgen05.mma issuer (M=128, N<=256 per instruction, K=16; up to two N halves), accumulators in
-//                   TMEM; tcgen05.commit releases smem stages and finally signals the epilogue.
-// Warps 2..5      : epilogue.  tcgen05.ld 32x32b gives every thread one pixel row, so the channel RMSNorm, the
-//                   scale/shift, SiLU, q-softmax and residual add are per-thread loops with no shuffles; the row
-//                   is read from TMEM twice (norm pass, output pass) instead of being held in registers.
+// One persistent CTA per SM walks a static list of 128-row output tiles (tb x th x tw boxes of output positions) for
+// one (sub-problem z, channel tile n0) combination = blockIdx.y.
+//   warp 0 / lane 0  TMA producer.  A K "load group" is one 4-D box {64 ch, tw, th+R-1, tb} of a source view read at
+//                    the tap-shifted position; out-of-range coordinates are zero-filled by TMA (= conv zero padding).
+//                    The box feeds R vertically adjacent filter taps: tap r starts r*tw rows (a multiple of the
+//                    1024-byte swizzle atom) further down the same box, so those rows are fetched once, not R times.
+//                    Weights are loaded ONCE per CTA and stay resident in shared memory when they fit; otherwise the
+//                    R weight blocks of a group travel in the same pipeline stage as its box.
+//   warp 1 / lane 0  tcgen05.mma issuer (M=128, N<=256 per instruction, K=16; two N halves for n_tile > 256).
+//                    Accumulators live in TMEM, double-buffered (2 x n_tile columns) so tile i+1 is multiplied while
+//                    tile i is in the epilogue.  tcgen05.commit frees smem stages / publishes finished accumulators.
+//   warps 2..9       epilogue.  tcgen05.ld 32x32b hands every thread one pixel row: channel RMSNorm, scale/shift,
+//                    SiLU, q-softmax, residual add and the bf16 pack are per-thread loops without shuffles.  The two
+//                    warps that share a TMEM lane quarter split the output columns; the norm's sum of squares is
+//                    recomputed by both from TMEM (cheaper than exchanging it).
 //
 // Replaces the nn.Conv2d / nn.Linear call sites listed in include/ccdm_b200.h.
 #include <cstring>
@@ -24,9 +29,11 @@ namespace ccdm {
 
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
-constexpr uint32_t kABytes = kTileM * kBlockK * 2;  // 16 KiB
+constexpr int kMaxN = 512;
 
 struct TapGemmMaps {
   CUtensorMap a[CCDM_MAX_SRC];
@@ -34,8 +41,9 @@ struct TapGemmMaps {
 };
 
 struct TapGemmDev {
-  int gW, gH, gB, tw, th, tb, tiles_w, tiles_h;
-  int nkb, n_rows, N, n_tile, n_sub, nsub, stages, w_batch_rows;
+  int gW, gH, gB, tw, th, tb, tiles_w, tiles_h, tiles_m, n_tiles;
+  int ngroups, R, nkb, n_rows, N, n_tile, n_sub, nsub, stages, acc_stages, w_batch_rows, b_resident;
+  uint32_t a_bytes, stage_bytes, res_bytes;
   const int4* sched;
   uint32_t flags, tmem_cols;
   const float *bias, *rowss, *gain, *ss;
@@ -50,233 +58,301 @@ struct TapGemmDev {
   int q_cols;
 };
 
-// aux smem block (after the stage ring): barriers, tmem slot, bias, gain, schedule
-constexpr int kAuxBarBytes = 256;
-constexpr int kAuxVecFloats = 512;
+// aux shared-memory block (after the resident weights and the stage ring)
+struct __align__(16) TapGemmAux {
+  uint64_t a_full[kMaxStages], a_empty[kMaxStages], b_full, tmem_full[2], tmem_empty[2];
+  uint32_t tmem_slot, pad_[3];
+  float bias[kMaxN], gain[kMaxN];         // bias[n], g[n]*gain_mul (0 for padded channels)
+  float gs[2][kMaxN], sh[2][kMaxN];       // per-tile g*(1+scale[b]), shift[b] (tiles inside one sample)
+  float part[kTileM];                     // sum-of-squares exchange between the two column halves
+};
 
-__global__ void __launch_bounds__(kThreads) tapgemm_kernel(const __grid_constant__ TapGemmMaps maps,
-                                                           const TapGemmDev p) {
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+__device__ __forceinline__ float fast_silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+
+__global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmMaps maps,
+                                                              const TapGemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-
-  const uint32_t b_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
-  uint8_t* aux = smem + static_cast<size_t>(p.stages) * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
-  uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* accum_bar = empty_bar + kMaxStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(aux + kAuxBarBytes);
-  float* s_gain = s_bias + kAuxVecFloats;
-  int4* s_sched = reinterpret_cast<int4*>(s_gain + kAuxVecFloats);
+  uint8_t* res_b = smem;                                   // resident weights (may be empty)
+  uint8_t* ring = smem + p.res_bytes;                      // pipeline stages
+  TapGemmAux* aux = reinterpret_cast<TapGemmAux*>(ring + static_cast<size_t>(p.stages) * p.stage_bytes);
+  int4* s_sched = reinterpret_cast<int4*>(aux + 1);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-
-  const int tile = blockIdx.x;
-  const int w0 = (tile % p.tiles_w) * p.tw;
-  const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
-  const int b0 = (tile / (p.tiles_w * p.tiles_h)) * p.tb;
-  const int n0 = blockIdx.y * p.n_tile;
-  const int z = blockIdx.z;
+  const int z = blockIdx.y / p.n_tiles;
+  const int n0 = (blockIdx.y % p.n_tiles) * p.n_tile;
+  const int b_bytes = p.n_tile * 128;
 
   // ---------------------------------------------------------------- one-time setup
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.b);
     tma_prefetch_desc(&maps.a[0]);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 1) tmem_alloc(&aux->tmem_slot, p.tmem_cols);
   if (tid == 64) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&aux->a_full[s], 1);
+      mbar_init(&aux->a_empty[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    mbar_init(&aux->b_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&aux->tmem_full[s], 1);
+      mbar_init(&aux->tmem_empty[s], kEpiWarps);
+    }
     fence_mbar_init();
   }
   for (int i = tid; i < p.n_tile; i += kThreads) {
     const bool ok = (n0 + i) < p.N;
-    s_bias[i] = ((p.flags & CCDM_EPI_BIAS) && ok) ? p.bias[n0 + i] : 0.f;
-    s_gain[i] = ((p.flags & CCDM_EPI_RMSNORM) && ok) ? p.gain[n0 + i] * p.gain_mul : 0.f;
+    aux->bias[i] = ((p.flags & CCDM_EPI_BIAS) && ok) ? p.bias[n0 + i] : 0.f;
+    aux->gain[i] = ((p.flags & CCDM_EPI_RMSNORM) && ok) ? p.gain[n0 + i] * p.gain_mul : 0.f;
   }
-  for (int i = tid; i < p.nkb; i += kThreads) s_sched[i] = p.sched[z * p.nkb + i];
+  for (int i = tid; i < p.ngroups; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = aux->tmem_slot;
+  const int tiles_per_sample = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
     // ============================================================== TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        const int4 e = s_sched[kb];
-        uint8_t* st = smem + static_cast<size_t>(s) * stage_bytes;
-        tma_load_4d(&maps.a[e.x], &full_bar[s], st, e.w, w0 + e.y, h0 + e.z, b0);
-        for (int sub = 0; sub < p.nsub; ++sub)
-          tma_load_2d(&maps.b, &full_bar[s], st + kABytes + sub * p.n_sub * 128, kb * kBlockK,
-                      b0 * p.w_batch_rows + z * p.n_rows + n0 + sub * p.n_sub);
+      if (p.b_resident) {
+        mbar_arrive_expect_tx(&aux->b_full, static_cast<uint32_t>(p.nkb) * b_bytes);
+        for (int kb = 0; kb < p.nkb; ++kb)
+          for (int sub = 0; sub < p.nsub; ++sub)
+            tma_load_2d(&maps.b, &aux->b_full, res_b + static_cast<size_t>(kb) * b_bytes + sub * p.n_sub * 128,
+                        kb * kBlockK, z * p.n_rows + n0 + sub * p.n_sub);
+      }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x) {
+        const int w0 = (tile % p.tiles_w) * p.tw;
+        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
+        const int b0 = (tile / tiles_per_sample) * p.tb;
+        const int wrow = b0 * p.w_batch_rows + z * p.n_rows + n0;
+        for (int g = 0; g < p.ngroups; ++g, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&aux->a_empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&aux->a_full[s], p.stage_bytes);
+          const int4 e = s_sched[g];
+          uint8_t* st = ring + static_cast<size_t>(s) * p.stage_bytes;
+          tma_load_4d(&maps.a[e.x], &aux->a_full[s], st, e.w, w0 + e.y, h0 + e.z, b0);
+          if (!p.b_resident) {
+            for (int r = 0; r < p.R; ++r)
+              for (int sub = 0; sub < p.nsub; ++sub)
+                tma_load_2d(&maps.b, &aux->a_full[s], st + p.a_bytes + r * b_bytes + sub * p.n_sub * 128,
+                            (g * p.R + r) * kBlockK, wrow + sub * p.n_sub);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ============================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(kTileM, p.n_sub);
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      if (p.b_resident) {
+        mbar_wait(&aux->b_full, 0);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + static_cast<size_t>(s) * stage_bytes);
-        const uint32_t b_addr = a_addr + kABytes;
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t adesc = umma_desc_sw128(a_addr + k * 32);
-          for (int sub = 0; sub < p.nsub; ++sub) {
-            const uint64_t bdesc = umma_desc_sw128(b_addr + sub * p.n_sub * 128 + k * 32);
-            umma_bf16_ss(tmem_base + sub * p.n_sub, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
       }
-      umma_commit(accum_bar);  // accumulators complete
-    }
-  } else {
-    // ============================================================== epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int m = q * 32 + lane;
-    const int lw = m % p.tw;
-    const int lh = (m / p.tw) % p.th;
-    const int lb = m / (p.tw * p.th);
-    const int w = w0 + lw, h = h0 + lh, b = b0 + lb;
-    const bool valid = (w < p.gW) && (h < p.gH) && (b < p.gB);
-    const int bs = b < p.gB ? b : p.gB - 1;
-    const long long pix = (static_cast<long long>(bs) * p.gH + (h < p.gH ? h : 0)) * p.gW + (w < p.gW ? w : 0);
-    const uint32_t flags = p.flags;
-
-    float rs = 1.f;
-    if (flags & CCDM_EPI_ROWSCALE) rs = valid ? 1.f / fmaxf(sqrtf(p.rowss[pix]), 1e-12f) : 0.f;
-
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int nchunk = p.n_tile / 32;
-    uint32_t r[32];
-
-    float inv = 1.f;
-    if (flags & CCDM_EPI_RMSNORM) {
-      float ssq = 0.f;
-      for (int c = 0; c < nchunk; ++c) {
-        tmem_ld32(trow + c * 32, r);
-        tmem_ld_wait();
+      uint32_t it = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++lt) {
+        const int as = lt % p.acc_stages;
+        const uint32_t aph = (lt / p.acc_stages) & 1;
+        mbar_wait(&aux->tmem_empty[as], aph ^ 1u);         // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * p.n_tile;
+        for (int g = 0; g < p.ngroups; ++g, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&aux->a_full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(s) * p.stage_bytes);
+          for (int r = 0; r < p.R; ++r) {
+            const uint32_t a_tap = a_addr + r * p.tw * 128;      // tap r: r*tw rows further down the same box
+            const uint32_t b_addr = p.b_resident ? smem_u32(res_b) + (g * p.R + r) * b_bytes
+                                                 : a_addr + p.a_bytes + r * b_bytes;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(r[j]) * rs + s_bias[c * 32 + j];
-          ssq += v * v;
-        }
-      }
-      inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
-    }
-
-    const float* ssrow = (flags & CCDM_EPI_SS) ? p.ss + static_cast<long long>(bs) * p.ss_ld + p.ss_off + n0 : nullptr;
-    const long long ro = static_cast<long long>(bs) * p.rsB + static_cast<long long>(h) * p.rsH +
-                         static_cast<long long>(w) * p.rsW + n0;
-    const long long oo = p.ooff[z] + static_cast<long long>(bs) * p.osB + static_cast<long long>(h) * p.osH +
-                         static_cast<long long>(w) * p.osW + n0;
-    float out_ss = 0.f;
-
-    for (int c = 0; c < nchunk; ++c) {
-      tmem_ld32(trow + c * 32, r);
-      tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs + s_bias[c * 32 + j];
-      if (flags & CCDM_EPI_RMSNORM) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= inv * s_gain[c * 32 + j];
-      }
-      if (flags & CCDM_EPI_SS) {
-        const float4* sc = reinterpret_cast<const float4*>(ssrow + c * 32);
-        const float4* sh = reinterpret_cast<const float4*>(ssrow + p.N + c * 32);
-        const bool in_n = (n0 + c * 32 + 32) <= p.N;
-        if (in_n) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 a = __ldg(sc + j4), d = __ldg(sh + j4);
-            v[j4 * 4 + 0] = v[j4 * 4 + 0] * (1.f + a.x) + d.x;
-            v[j4 * 4 + 1] = v[j4 * 4 + 1] * (1.f + a.y) + d.y;
-            v[j4 * 4 + 2] = v[j4 * 4 + 2] * (1.f + a.z) + d.z;
-            v[j4 * 4 + 3] = v[j4 * 4 + 3] * (1.f + a.w) + d.w;
-          }
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c * 32 + j < p.N) v[j] = v[j] * (1.f + ssrow[c * 32 + j]) + ssrow[p.N + c * 32 + j];
-        }
-      }
-      if (flags & CCDM_EPI_SILU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-      }
-      if ((flags & CCDM_EPI_QSOFTMAX) && (n0 + c * 32 < p.q_cols)) {
-        float mx = v[0];
-#pragma unroll
-        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __expf(v[j] - mx);
-          sum += v[j];
-        }
-        const float k = p.q_scale / sum;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= k;
-      }
-      if (valid) {
-        if (flags & CCDM_EPI_RESID) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + c * 32);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (n0 + c * 32 + g * 8 < p.N) {
-              const uint4 u = __ldg(rp + g);
-              v[g * 8 + 0] += bf16_lo(u.x); v[g * 8 + 1] += bf16_hi(u.x);
-              v[g * 8 + 2] += bf16_lo(u.y); v[g * 8 + 3] += bf16_hi(u.y);
-              v[g * 8 + 4] += bf16_lo(u.z); v[g * 8 + 5] += bf16_hi(u.z);
-              v[g * 8 + 6] += bf16_lo(u.w); v[g * 8 + 7] += bf16_hi(u.w);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t adesc = umma_desc_sw128(a_tap + k * 32);
+              for (int sub = 0; sub < p.nsub; ++sub) {
+                const uint64_t bdesc = umma_desc_sw128(b_addr + sub * p.n_sub * 128 + k * 32);
+                umma_bf16_ss(d_tmem + sub * p.n_sub, adesc, bdesc, idesc, (g | r | k) != 0 ? 1u : 0u);
+              }
             }
           }
+          umma_commit(&aux->a_empty[s]);                   // stage reusable once these MMAs have read it
         }
-        if (flags & CCDM_EPI_OUT_F32) {
-          float* op = reinterpret_cast<float*>(p.out) + oo + c * 32;
+        umma_commit(&aux->tmem_full[as]);                  // accumulators of this tile complete
+      }
+    }
+  } else {
+    // ============================================================== epilogue (warps 2..9)
+    const int ew = warp - 2;
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                              // which half of the columns this warp writes
+    const int et = ew * 32 + lane;                         // 0..255 among the epilogue threads
+    const int m = q * 32 + lane;
+    const int lw = m % p.tw, lh = (m / p.tw) % p.th, lb = m / (p.tw * p.th);
+    const uint32_t flags = p.flags;
+    const int nchunk = p.n_tile / 32;
+    const int per_half = (nchunk + 1) >> 1;
+    const int c_lo = half * per_half, c_hi = min(nchunk, c_lo + per_half);
+    const bool tile_ss = (flags & CCDM_EPI_SS) && p.tb == 1;   // scale/shift uniform over the tile
+    const uint32_t trow_lane = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t r[32];
+
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++lt) {
+      const int as = lt % p.acc_stages;
+      const uint32_t aph = (lt / p.acc_stages) & 1;
+      const int w0 = (tile % p.tiles_w) * p.tw;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
+      const int b0 = (tile / tiles_per_sample) * p.tb;
+      const int w = w0 + lw, h = h0 + lh, b = b0 + lb;
+      const bool valid = (w < p.gW) && (h < p.gH) && (b < p.gB);
+      const int bs = b < p.gB ? b : p.gB - 1;
+      const long long pix = (static_cast<long long>(bs) * p.gH + (h < p.gH ? h : 0)) * p.gW + (w < p.gW ? w : 0);
+      const int sb = lt & 1;                               // per-tile scale/shift buffer
+
+      if (tile_ss) {
+        const float* ssrow = p.ss + static_cast<long long>(b0) * p.ss_ld + p.ss_off + n0;
+        for (int c = et; c < p.n_tile; c += kEpiThreads) {
+          const bool ok = (n0 + c) < p.N;
+          aux->gs[sb][c] = ok ? aux->gain[c] * (1.f + ssrow[c]) : 0.f;
+          aux->sh[sb][c] = ok ? ssrow[p.N + c] : 0.f;
+        }
+        epi_bar();
+      }
+      float rs = 1.f;
+      if (flags & CCDM_EPI_ROWSCALE) rs = valid ? 1.f / fmaxf(sqrtf(p.rowss[pix]), 1e-12f) : 0.f;
+
+      mbar_wait(&aux->tmem_full[as], aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + trow_lane + as * p.n_tile;
+
+      float inv = 1.f;
+      if (flags & CCDM_EPI_RMSNORM) {
+        float ssq = 0.f;
+        for (int c = 0; c < nchunk; ++c) {
+          tmem_ld32(trow + c * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            if (n0 + c * 32 + g * 4 < p.N)
-              *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + oo + c * 32;
+          for (int j = 0; j < 32; ++j) {
+            const float v = fmaf(__uint_as_float(r[j]), rs, aux->bias[c * 32 + j]);
+            ssq = fmaf(v, v, ssq);
+          }
+        }
+        inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
+      }
+
+      const float* ssrow = ((flags & CCDM_EPI_SS) && !tile_ss)
+                               ? p.ss + static_cast<long long>(bs) * p.ss_ld + p.ss_off + n0 : nullptr;
+      const long long ro = static_cast<long long>(bs) * p.rsB + static_cast<long long>(h) * p.rsH +
+                           static_cast<long long>(w) * p.rsW + n0;
+      const long long oo = p.ooff[z] + static_cast<long long>(bs) * p.osB + static_cast<long long>(h) * p.osH +
+                           static_cast<long long>(w) * p.osW + n0;
+      float out_ss = 0.f;
+
+      for (int c = c_lo; c < c_hi; ++c) {
+        tmem_ld32(trow + c * 32, r);
+        tmem_ld_wait();
+        if (c == c_hi - 1) {                               // last TMEM read of this tile by this warp: release
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&aux->tmem_empty[as]);
+        }
+        float v[32];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (n0 + c * 32 + g * 8 < p.N) {
-              uint4 u;
-              u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-              u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-              u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-              u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-              *reinterpret_cast<uint4*>(op + g * 8) = u;
-              if (flags & CCDM_EPI_SUMSQ_OUT) {
-                const float a0 = bf16_lo(u.x), a1 = bf16_hi(u.x), a2 = bf16_lo(u.y), a3 = bf16_hi(u.y);
-                const float a4 = bf16_lo(u.z), a5 = bf16_hi(u.z), a6 = bf16_lo(u.w), a7 = bf16_hi(u.w);
-                out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), rs, aux->bias[c * 32 + j]);
+        if (flags & CCDM_EPI_RMSNORM) {
+          if (tile_ss) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j] * inv, aux->gs[sb][c * 32 + j], aux->sh[sb][c * 32 + j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= inv * aux->gain[c * 32 + j];
+          }
+        }
+        if (ssrow) {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c * 32 + j < p.N) v[j] = fmaf(v[j], 1.f + __ldg(ssrow + c * 32 + j), __ldg(ssrow + p.N + c * 32 + j));
+        }
+        if (flags & CCDM_EPI_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[j]);
+        }
+        if ((flags & CCDM_EPI_QSOFTMAX) && (n0 + c * 32 < p.q_cols)) {
+          float mx = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __expf(v[j] - mx);
+            sum += v[j];
+          }
+          const float k = __fdividef(p.q_scale, sum);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= k;
+        }
+        if (valid) {
+          if (flags & CCDM_EPI_RESID) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + c * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (n0 + c * 32 + g * 8 < p.N) {
+                const uint4 u = __ldg(rp + g);
+                v[g * 8 + 0] += bf16_lo(u.x); v[g * 8 + 1] += bf16_hi(u.x);
+                v[g * 8 + 2] += bf16_lo(u.y); v[g * 8 + 3] += bf16_hi(u.y);
+                v[g * 8 + 4] += bf16_lo(u.z); v[g * 8 + 5] += bf16_hi(u.z);
+                v[g * 8 + 6] += bf16_lo(u.w); v[g * 8 + 7] += bf16_hi(u.w);
+              }
+            }
+          }
+          if (flags & CCDM_EPI_OUT_F32) {
+            float* op = reinterpret_cast<float*>(p.out) + oo + c * 32;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if (n0 + c * 32 + g * 4 < p.N)
+                *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + oo + c * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (n0 + c * 32 + g * 8 < p.N) {
+                uint4 u;
+                u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                *reinterpret_cast<uint4*>(op + g * 8) = u;
+                if (flags & CCDM_EPI_SUMSQ_OUT) {
+                  const float a0 = bf16_lo(u.x), a1 = bf16_hi(u.x), a2 = bf16_lo(u.y), a3 = bf16_hi(u.y);
+                  const float a4 = bf16_lo(u.z), a5 = bf16_hi(u.z), a6 = bf16_lo(u.w), a7 = bf16_hi(u.w);
+                  out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+                }
               }
             }
           }
         }
       }
+      if (c_lo >= c_hi) {                                  // this warp owns no columns (n_tile == 32): still release
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aux->tmem_empty[as]);
+      }
+      if (flags & CCDM_EPI_SUMSQ_OUT) {                    // combine the two column halves of every row
+        if (half == 1) aux->part[m] = out_ss;
+        epi_bar();
+        if (half == 0 && valid) p.out_rowss[pix] = out_ss + aux->part[m];
+        epi_bar();
+      }
     }
-    if ((flags & CCDM_EPI_SUMSQ_OUT) && valid) p.out_rowss[pix] = out_ss;
   }
 
   // ---------------------------------------------------------------- teardown
@@ -307,8 +383,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                      const cuuint32_t* box) {
+int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                    const cuuint32_t* box) {
   EncodeTiledFn enc = get_encode();
   CCDM_REQUIRE(enc != nullptr, CCDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -339,12 +415,14 @@ using namespace ccdm;
 extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   CCDM_REQUIRE(a != nullptr, CCDM_ERR_BAD_ARG, "tapgemm: null args");
   CCDM_REQUIRE(a->n_src >= 1 && a->n_src <= CCDM_MAX_SRC, CCDM_ERR_BAD_ARG, "tapgemm: n_src=%d", a->n_src);
-  CCDM_REQUIRE(a->tw > 0 && a->th > 0 && a->tb > 0 && a->tw * a->th * a->tb == kTileM && a->tw <= 256 &&
-                   a->th <= 256 && a->tb <= 256,
-               CCDM_ERR_BAD_ARG, "tapgemm: tile box %dx%dx%d must hold 128 positions", a->tw, a->th, a->tb);
-  CCDM_REQUIRE(a->nz >= 1 && a->nz <= CCDM_MAX_Z && a->nkb >= 1, CCDM_ERR_BAD_ARG, "tapgemm: nz=%d nkb=%d", a->nz,
-               a->nkb);
-  CCDM_REQUIRE(a->n_tile >= 32 && a->n_tile <= 512 && a->n_tile % 32 == 0, CCDM_ERR_UNSUPPORTED_SHAPE,
+  CCDM_REQUIRE(a->tw > 0 && a->th > 0 && a->tb > 0 && a->tw * a->th * a->tb == kTileM, CCDM_ERR_BAD_ARG,
+               "tapgemm: tile box %dx%dx%d must hold 128 positions", a->tw, a->th, a->tb);
+  CCDM_REQUIRE(a->nz >= 1 && a->nz <= CCDM_MAX_Z && a->ngroups >= 1 && a->R >= 1 && a->R <= 4, CCDM_ERR_BAD_ARG,
+               "tapgemm: nz=%d ngroups=%d R=%d", a->nz, a->ngroups, a->R);
+  CCDM_REQUIRE(a->R == 1 || (a->tb == 1 && a->tw % 8 == 0), CCDM_ERR_BAD_ARG,
+               "tapgemm: vertical tap reuse (R=%d) needs tb == 1 and tw %% 8 == 0 (tile %dx%dx%d)", a->R, a->tw, a->th,
+               a->tb);
+  CCDM_REQUIRE(a->n_tile >= 32 && a->n_tile <= kMaxN && a->n_tile % 32 == 0, CCDM_ERR_UNSUPPORTED_SHAPE,
                "tapgemm: n_tile=%d must be a multiple of 32 in [32,512]", a->n_tile);
   CCDM_REQUIRE(a->N >= 1 && a->N % 8 == 0 && a->n_rows % a->n_tile == 0 && a->n_rows >= a->N,
                CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: N=%d n_rows=%d n_tile=%d", a->N, a->n_rows, a->n_tile);
@@ -354,8 +432,8 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_BIAS) || a->bias, CCDM_ERR_BAD_ARG, "tapgemm: bias flag without pointer");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_ROWSCALE) || a->rowss, CCDM_ERR_BAD_ARG, "tapgemm: rowscale without rowss");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_RMSNORM) || a->gain, CCDM_ERR_BAD_ARG, "tapgemm: rmsnorm without gain");
-  CCDM_REQUIRE(!(a->flags & CCDM_EPI_SS) || (a->scale_shift && a->ss_off % 4 == 0 && a->ss_ld % 4 == 0 && a->N % 4 == 0),
-               CCDM_ERR_BAD_ARG, "tapgemm: scale/shift pointer or alignment");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_SS) || (a->scale_shift && (a->flags & CCDM_EPI_RMSNORM)), CCDM_ERR_BAD_ARG,
+               "tapgemm: scale/shift needs its pointer and the RMSNorm epilogue (unet.py:145-149)");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_RESID) || a->resid, CCDM_ERR_BAD_ARG, "tapgemm: resid flag without pointer");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_SUMSQ_OUT) || (a->out_rowss && a->n_rows == a->n_tile), CCDM_ERR_BAD_ARG,
                "tapgemm: sumsq output needs out_rowss and a single N tile");
@@ -363,6 +441,8 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   CCDM_REQUIRE(a->w_batch_rows == 0 || (a->tb == 1 && a->nz == 1 && a->w_batch_rows >= a->n_rows), CCDM_ERR_BAD_ARG,
                "tapgemm: per-sample weights need tb == 1, nz == 1 and w_batch_rows >= n_rows");
 
+  const int box_h = a->th + a->R - 1;
+  CCDM_REQUIRE(a->tw <= 256 && box_h <= 256 && a->tb <= 256, CCDM_ERR_BAD_ARG, "tapgemm: TMA box too large");
   TapGemmMaps maps;
   std::memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < CCDM_MAX_SRC; ++i) {
@@ -373,21 +453,22 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
                  CCDM_ERR_BAD_ARG, "tapgemm: source %d extents/strides (strides must be multiples of 8 elements)", i);
     cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.B};
     cuuint64_t str[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sB * 2};
-    cuuint32_t box[4] = {kBlockK, (cuuint32_t)a->tw, (cuuint32_t)a->th, (cuuint32_t)a->tb};
-    int rc = encode_map(&maps.a[i], v.ptr, 4, dims, str, box);
+    cuuint32_t box[4] = {kBlockK, (cuuint32_t)a->tw, (cuuint32_t)box_h, (cuuint32_t)a->tb};
+    int rc = encode_map_bf16(&maps.a[i], v.ptr, 4, dims, str, box);
     if (rc != CCDM_OK) return rc;
   }
   const int nsub = a->n_tile > 256 ? 2 : 1;
   const int n_sub = a->n_tile / nsub;
+  const int nkb = a->ngroups * a->R;
   CCDM_REQUIRE(n_sub % 16 == 0 && n_sub <= 256, CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: n_sub=%d", n_sub);
   {
-    const cuuint64_t ktot = (cuuint64_t)a->nkb * kBlockK;
+    const cuuint64_t ktot = (cuuint64_t)nkb * kBlockK;
     cuuint64_t dims[2] = {ktot, a->w_batch_rows > 0 ? (cuuint64_t)a->w_batch_rows * a->gB
                                                     : (cuuint64_t)a->n_rows * a->nz};
     cuuint64_t str[1] = {ktot * 2};
     cuuint32_t box[2] = {kBlockK, (cuuint32_t)n_sub};
     CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->wpacked) & 15) == 0, CCDM_ERR_BAD_ARG, "tapgemm: wpacked alignment");
-    int rc = encode_map(&maps.b, a->wpacked, 2, dims, str, box);
+    int rc = encode_map_bf16(&maps.b, a->wpacked, 2, dims, str, box);
     if (rc != CCDM_OK) return rc;
   }
 
@@ -398,11 +479,15 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   p.tiles_w = (a->gW + a->tw - 1) / a->tw;
   p.tiles_h = (a->gH + a->th - 1) / a->th;
   const int tiles_b = (a->gB + a->tb - 1) / a->tb;
+  p.tiles_m = p.tiles_w * p.tiles_h * tiles_b;
+  p.n_tiles = a->n_rows / a->n_tile;
+  p.ngroups = a->ngroups; p.R = a->R; p.nkb = nkb;
   p.w_batch_rows = a->w_batch_rows;
-  p.nkb = a->nkb; p.n_rows = a->n_rows; p.N = a->N; p.n_tile = a->n_tile; p.n_sub = n_sub; p.nsub = nsub;
+  p.n_rows = a->n_rows; p.N = a->N; p.n_tile = a->n_tile; p.n_sub = n_sub; p.nsub = nsub;
   p.sched = reinterpret_cast<const int4*>(a->sched);
   p.flags = a->flags;
-  p.tmem_cols = pow2_cols(a->n_tile);
+  p.acc_stages = a->n_tile <= 256 ? 2 : 1;
+  p.tmem_cols = pow2_cols(a->n_tile * p.acc_stages);
   p.bias = a->bias; p.rowss = a->rowss; p.gain = a->gain; p.ss = a->scale_shift;
   p.ss_ld = a->ss_ld; p.ss_off = a->ss_off;
   p.resid = reinterpret_cast<const __nv_bfloat16*>(a->resid);
@@ -411,16 +496,32 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   for (int i = 0; i < CCDM_MAX_Z; ++i) p.ooff[i] = a->ooff[i];
   p.out_rowss = a->out_rowss; p.q_scale = a->q_scale; p.q_cols = a->q_cols; p.gain_mul = a->gain_mul;
 
-  const uint32_t stage_bytes = kABytes + (uint32_t)a->n_tile * 128u;
-  const size_t aux_bytes = kAuxBarBytes + 2 * kAuxVecFloats * sizeof(float) + (size_t)a->nkb * sizeof(int4);
-  const size_t budget = (stage_bytes <= 32768 ? 110 * 1024 : 224 * 1024) - aux_bytes - 1024;  // small tiles: 2 CTAs / SM
-  int stages = (int)(budget / stage_bytes);
+  // ---- launch geometry: persistent CTAs, one (z, n-tile) combination per blockIdx.y
+  const int combos = p.n_tiles * a->nz;
+  const int sms = num_sms();
+  int gx = (sms + combos - 1) / combos;
+  if (gx > p.tiles_m) gx = p.tiles_m;
+  if (gx < 1) gx = 1;
+  const int tiles_per_cta = (p.tiles_m + gx - 1) / gx;
+
+  // ---- shared-memory plan
+  const uint32_t b_bytes = (uint32_t)a->n_tile * 128u;
+  p.a_bytes = (uint32_t)(box_h * a->tw * a->tb) * 128u;
+  const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)a->ngroups * sizeof(int4);
+  const size_t budget = 226 * 1024 - aux_bytes - 1024;
+  const size_t res_all = (size_t)nkb * b_bytes;
+  p.b_resident = (a->w_batch_rows == 0 && tiles_per_cta >= 2 && res_all + 3 * (size_t)p.a_bytes <= budget) ? 1 : 0;
+  p.res_bytes = p.b_resident ? (uint32_t)res_all : 0;
+  p.stage_bytes = p.a_bytes + (p.b_resident ? 0 : (uint32_t)a->R * b_bytes);
+  int stages = (int)((budget - p.res_bytes) / p.stage_bytes);
+  int useful = a->ngroups * (tiles_per_cta > 1 ? 2 : 1);           // about two tiles of lookahead ...
+  if (tiles_per_cta > 1 && useful < 4) useful = 4;                 // ... but never fewer than 4 boxes in flight
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > a->nkb) stages = a->nkb;
-  CCDM_REQUIRE(stages >= 1, CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: K schedule of %d blocks does not fit shared memory",
-               a->nkb);
+  if (stages > useful) stages = useful;
+  CCDM_REQUIRE(stages >= 1, CCDM_ERR_UNSUPPORTED_SHAPE,
+               "tapgemm: one pipeline stage (%u bytes) does not fit shared memory", p.stage_bytes);
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + aux_bytes + 1024;
+  const size_t smem_bytes = p.res_bytes + (size_t)stages * p.stage_bytes + aux_bytes + 1024;
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
@@ -429,7 +530,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "tapgemm: cudaFuncSetAttribute");
 
-  dim3 grid((unsigned)(p.tiles_w * p.tiles_h * tiles_b), (unsigned)(a->n_rows / a->n_tile), (unsigned)a->nz);
+  dim3 grid((unsigned)gx, (unsigned)combos, 1);
   tapgemm_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(maps, p);
   return after_launch("tapgemm_kernel");
 }

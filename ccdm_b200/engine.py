@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _lib as L
-from .plan import ConvPlan, plan_conv, tile_box, n_tiling, KB
+from .plan import ConvPlan, plan_conv, tile_box, can_reuse_rows, n_tiling, KB
 
 
 # --------------------------------------------------------------------------------------------- records
@@ -175,7 +175,7 @@ def _fill_tapgemm(r: TapGemmRec) -> L.TapGemmArgs:
         a.src[i] = L.View(v.base.data_ptr() + 2 * v.off, v.C, v.W, v.H, v.B, v.sW, v.sH, v.sB)
     a.gW, a.gH, a.gB = r.gW, r.gH, r.gB
     a.tw, a.th, a.tb = r.tile
-    a.nz, a.nkb = r.plan.nz, r.plan.nkb
+    a.nz, a.ngroups, a.R = r.plan.nz, r.plan.ngroups, r.plan.R
     a.sched, a.wpacked = r.sched.data_ptr(), r.wpacked.data_ptr()
     a.n_rows, a.w_batch_rows, a.N, a.n_tile, a.flags = r.n_rows, r.w_batch_rows, r.N, r.n_tile, r.flags
     a.bias, a.rowss, a.gain, a.gain_mul = L.ptr(r.bias), L.ptr(r.rowss), L.ptr(r.gain), r.gain_mul
@@ -376,13 +376,15 @@ class UnetProgram(Program):
         """Append one tap-GEMM over NHWC sources.  ``conv_mod`` owns .weight / .bias (nn.Conv2d)."""
         cins = [s.shape[3] for s in srcs] if views is None else [v.C for v in views]
         cout = conv_mod.weight.shape[0]
-        plan = plan_conv(kind, cins, cout)
+        gh, gw = out.shape[1], out.shape[2]
+        if kind == "up2x3x3":
+            gh, gw = gh // 2, gw // 2
+        tile = tile_box(gw, gh, square=(kind != "1x1"))
+        reuse = kind != "1x1" and can_reuse_rows(tile)
+        plan = plan_conv(kind, cins, cout, reuse_rows=reuse)
         full_row = bool(flags & (L.EPI_RMSNORM | L.EPI_SUMSQ_OUT))
         n_rows, n_tile = n_tiling(cout, full_row)
-        pack = self.weights.add(name, conv_mod.weight, plan, n_rows, cin_gain, cin_gain_mul)
-        gh, gw = out.shape[1], out.shape[2]
-        if plan.out_parity:
-            gh, gw = gh // 2, gw // 2
+        pack = self.weights.add(f"{name}/R{plan.R}", conv_mod.weight, plan, n_rows, cin_gain, cin_gain_mul)
         if views is None:
             views = []
             for s in srcs:
@@ -396,7 +398,7 @@ class UnetProgram(Program):
             ooff = (0, 0, 0, 0)
         if conv_mod.bias is not None:
             flags |= L.EPI_BIAS
-        rec = TapGemmRec(name, plan, views, gw, gh, self.B, tile_box(gw, gh), pack, pack.packed, pack.sched, n_rows,
+        rec = TapGemmRec(name, plan, views, gw, gh, self.B, tile, pack, pack.packed, pack.sched, n_rows,
                          cout, n_tile, flags, out, ostr, ooff, bias=conv_mod.bias, rowss=rowss, gain=gain,
                          gain_mul=math.sqrt(cout) if gain is not None else 1.0, out_rowss=out_rowss)
         if ss_off is not None:

@@ -34,7 +34,7 @@ int ccdm_struct_size(int which);
 /* ------------------------------------------------------------------------------------------------------------
  * Tap-GEMM: the implicit-GEMM convolution / linear engine (tcgen05 + TMEM + TMA).
  *
- *   out[b,h,w,n] = epilogue( sum_kb  A_{src[kb]}[b, h+dh[kb], w+dw[kb], c0[kb] : c0[kb]+64] . Wp[n, kb*64 : kb*64+64] )
+ *   out[b,h,w,n] = epilogue( sum_{g,r}  A_{src[g]}[b, h+dh0[g]+r, w+dw[g], c0[g] : c0[g]+64] . Wp[n, (g*R+r)*64 : +64] )
  *
  * Replaces nn.Conv2d (3x3, 1x1, 4x4/s2 Downsample, nearest-2x Upsample+3x3) and nn.Linear call sites of
  * CCDM_unified/models/unet.py:77,81,139,160,165,195,198,225,226,326,341 together with the elementwise tail that
@@ -65,9 +65,11 @@ typedef struct ccdm_tapgemm_args {
   ccdm_view src[CCDM_MAX_SRC];
   int32_t gW, gH, gB; /* extents of the output-position grid the 128-row tiles walk over */
   int32_t tw, th, tb; /* tile box, tw*th*tb == 128 */
-  int32_t nz, nkb;    /* sub-problems (output parity planes) and 64-wide K blocks per sub-problem */
-  const int32_t* sched; /* device [nz*nkb][4] = {src, dw, dh, c0} */
-  const void* wpacked;  /* device bf16 [nz*n_rows][nkb*64], K contiguous (see ccdm_pack_weights) */
+  int32_t nz;         /* sub-problems (output parity planes of the nearest-2x conv) */
+  int32_t ngroups, R; /* K loop: ngroups TMA boxes per sub-problem, each th+R-1 rows tall and feeding R vertically
+                         adjacent filter taps (tap r starts r*tw rows into the box); R > 1 needs tb == 1, tw % 8 == 0 */
+  const int32_t* sched; /* device [nz*ngroups][4] = {src, dw, dh0, c0} */
+  const void* wpacked;  /* device bf16 [nz*n_rows][ngroups*R*64], K contiguous, block (g*R + r) = group g, tap r */
   int32_t n_rows;       /* packed rows per sub-problem; multiple of n_tile */
   int32_t w_batch_rows; /* 0: one weight set.  >0: per-sample weights, sample b starts at row b*w_batch_rows
                            (linear-attention output projection with the context folded in); needs tb == 1 */

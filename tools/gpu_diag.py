@@ -28,7 +28,7 @@ def case_gemm(which):
     import torch.nn.functional as F
     from ccdm_b200 import _lib as L
     from ccdm_b200.engine import Program, TapGemmRec, WeightStore, nhwc_view, parity_views
-    from ccdm_b200.plan import plan_conv, tile_box, n_tiling
+    from ccdm_b200.plan import plan_conv, tile_box, n_tiling, can_reuse_rows
     dev = torch.device("cuda")
     torch.manual_seed(0)
     shapes = []
@@ -46,12 +46,13 @@ def case_gemm(which):
         conv = torch.nn.Conv2d(sum(cins), cout, k).to(dev)
         ws = WeightStore(dev)
         prog = Program(dev)
-        plan = plan_conv(kind, cins, cout)
+        oh, ow = (H // 2, W // 2) if kind == "down4x4s2" else ((2 * H, 2 * W) if kind == "up2x3x3" else (H, W))
+        gh, gw = (H, W) if kind == "up2x3x3" else (oh, ow)
+        tile = tile_box(gw, gh, square=(kind != "1x1"))
+        plan = plan_conv(kind, cins, cout, reuse_rows=(kind != "1x1" and can_reuse_rows(tile)))
         n_rows, n_tile = n_tiling(cout, False)
         pack = ws.add("w", conv.weight, plan, n_rows)
-        oh, ow = (H // 2, W // 2) if kind == "down4x4s2" else ((2 * H, 2 * W) if kind == "up2x3x3" else (H, W))
         out = torch.zeros(B, oh, ow, cout, device=dev, dtype=torch.bfloat16)
-        gh, gw = (H, W) if kind == "up2x3x3" else (oh, ow)
         views = []
         for x in xs:
             views += parity_views(x) if plan.n_views == 4 else [nhwc_view(x)]
@@ -60,7 +61,7 @@ def case_gemm(which):
             ooff = tuple((pa * ow + pb) * cout for pa in range(2) for pb in range(2))
         else:
             ostr, ooff = (cout, ow * cout, oh * ow * cout), (0, 0, 0, 0)
-        rec = TapGemmRec("t", plan, views, gw, gh, B, tile_box(gw, gh), pack, pack.packed, pack.sched, n_rows, cout,
+        rec = TapGemmRec("t", plan, views, gw, gh, B, tile, pack, pack.packed, pack.sched, n_rows, cout,
                          n_tile, L.EPI_BIAS, out, ostr, ooff, bias=conv.bias)
         prog.recs.append(rec)
         prog.finalize()
@@ -78,7 +79,7 @@ def case_gemm(which):
             ref = F.conv2d(xin, wq, conv.bias, padding=k // 2)
         ref = ref.permute(0, 2, 3, 1)
         r, m = rel(out, ref)
-        print(f"{kind:10s} B={B} {H}x{W} cins={cins} cout={cout} tile={rec.tile} n_tile={n_tile}: rel={r:.3e} max={m:.3e}",
+        print(f"{kind:10s} B={B} {H}x{W} cins={cins} cout={cout} tile={rec.tile} R={plan.R} n_tile={n_tile}: rel={r:.3e} max={m:.3e}",
               "OK" if r < 1e-2 else "FAIL", flush=True)
         if r >= 1e-2:
             d = (out.float() - ref).abs()
