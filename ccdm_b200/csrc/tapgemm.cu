@@ -38,12 +38,14 @@ constexpr int kMaxN = 512;
 struct TapGemmMaps {
   CUtensorMap a[CCDM_MAX_SRC];
   CUtensorMap b;
+  CUtensorMap o[CCDM_MAX_Z];              // bf16 output views (one per sub-problem) for the TMA-store epilogue
 };
 
 struct TapGemmDev {
   int gW, gH, gB, tw, th, tb, tiles_w, tiles_h, tiles_m, n_tiles;
   int ngroups, R, nkb, n_rows, N, n_tile, n_sub, nsub, stages, acc_stages, w_batch_rows, b_resident;
-  uint32_t a_bytes, stage_bytes, res_bytes;
+  uint32_t a_bytes, stage_bytes, res_bytes, out_bytes;
+  int tiles_per_cta, out_bufs, store_tma;
   const int4* sched;
   uint32_t flags, tmem_cols;
   const float *bias, *rowss, *gain, *ss;
@@ -64,7 +66,7 @@ struct __align__(16) TapGemmAux {
   uint32_t tmem_slot, pad_[3];
   float bias[kMaxN], gain[kMaxN];         // bias[n], g[n]*gain_mul (0 for padded channels)
   float gs[2][kMaxN], sh[2][kMaxN];       // per-tile g*(1+scale[b]), shift[b] (tiles inside one sample)
-  float part[kTileM];                     // sum-of-squares exchange between the two column halves
+  float part[2][kTileM];                  // sum-of-squares exchange between the two column halves (tile parity)
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
@@ -77,7 +79,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* res_b = smem;                                   // resident weights (may be empty)
   uint8_t* ring = smem + p.res_bytes;                      // pipeline stages
-  TapGemmAux* aux = reinterpret_cast<TapGemmAux*>(ring + static_cast<size_t>(p.stages) * p.stage_bytes);
+  uint8_t* stg = ring + static_cast<size_t>(p.stages) * p.stage_bytes;   // output staging (TMA-store epilogue)
+  TapGemmAux* aux = reinterpret_cast<TapGemmAux*>(stg + static_cast<size_t>(p.out_bufs) * p.out_bytes);
   int4* s_sched = reinterpret_cast<int4*>(aux + 1);
 
   const int tid = threadIdx.x;
@@ -116,27 +119,31 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = aux->tmem_slot;
   const int tiles_per_sample = p.tiles_w * p.tiles_h;
+  // contiguous tile range per CTA: neighbouring tiles share halos in L2 and (mostly) the sample's scale/shift
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  const int t_end = min(p.tiles_m, t_begin + p.tiles_per_cta);
 
   if (warp == 0) {
-    // ============================================================== TMA producer
-    if (lane == 0) {
-      if (p.b_resident) {
-        mbar_arrive_expect_tx(&aux->b_full, static_cast<uint32_t>(p.nkb) * b_bytes);
-        for (int kb = 0; kb < p.nkb; ++kb)
-          for (int sub = 0; sub < p.nsub; ++sub)
-            tma_load_2d(&maps.b, &aux->b_full, res_b + static_cast<size_t>(kb) * b_bytes + sub * p.n_sub * 128,
-                        kb * kBlockK, z * p.n_rows + n0 + sub * p.n_sub);
-      }
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x) {
-        const int w0 = (tile % p.tiles_w) * p.tw;
-        const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
-        const int b0 = (tile / tiles_per_sample) * p.tb;
-        const int wrow = b0 * p.w_batch_rows + z * p.n_rows + n0;
-        for (int g = 0; g < p.ngroups; ++g, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&aux->a_empty[s], ph ^ 1u);
+    // ============================================================== TMA producer (warp-uniform loops, one lane issues)
+    if (p.b_resident && elect_one()) {
+      mbar_arrive_expect_tx(&aux->b_full, static_cast<uint32_t>(p.nkb) * b_bytes);
+      for (int kb = 0; kb < p.nkb; ++kb)
+        for (int sub = 0; sub < p.nsub; ++sub)
+          tma_load_2d(&maps.b, &aux->b_full, res_b + static_cast<size_t>(kb) * b_bytes + sub * p.n_sub * 128,
+                      kb * kBlockK, z * p.n_rows + n0 + sub * p.n_sub);
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int w0 = (tile % p.tiles_w) * p.tw;
+      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
+      const int b0 = (tile / tiles_per_sample) * p.tb;
+      const int wrow = b0 * p.w_batch_rows + z * p.n_rows + n0;
+      for (int g = 0; g < p.ngroups; ++g, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&aux->a_empty[s], ph ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&aux->a_full[s], p.stage_bytes);
           const int4 e = s_sched[g];
           uint8_t* st = ring + static_cast<size_t>(s) * p.stage_bytes;
@@ -148,47 +155,58 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                             (g * p.R + r) * kBlockK, wrow + sub * p.n_sub);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ============================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kTileM, p.n_sub);
-      if (p.b_resident) {
-        mbar_wait(&aux->b_full, 0);
+    // ============================================================== MMA issuer (warp-uniform loops, one lane issues)
+    const uint32_t idesc = umma_idesc_bf16(kTileM, p.n_sub);
+    const uint32_t ring16 = (smem_u32(ring) & 0x3FFFF) >> 4;       // descriptor address fields, in 16-byte units
+    const uint32_t res16 = (smem_u32(res_b) & 0x3FFFF) >> 4;
+    const uint32_t stage16 = p.stage_bytes >> 4, abytes16 = p.a_bytes >> 4, b16 = static_cast<uint32_t>(b_bytes) >> 4;
+    const uint32_t tap16 = static_cast<uint32_t>(p.tw) * 8;         // r*tw rows * 128 B / 16
+    const uint32_t sub16 = static_cast<uint32_t>(p.n_sub) * 8;
+    if (p.b_resident) {
+      mbar_wait(&aux->b_full, 0);
+      tc_fence_after();
+    }
+    uint32_t it = 0;
+    int lt = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+      const int as = lt % p.acc_stages;
+      const uint32_t aph = (lt / p.acc_stages) & 1;
+      mbar_wait(&aux->tmem_empty[as], aph ^ 1u);           // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * p.n_tile;
+      for (int g = 0; g < p.ngroups; ++g, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&aux->a_full[s], ph);
         tc_fence_after();
-      }
-      uint32_t it = 0;
-      int lt = 0;
-      for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++lt) {
-        const int as = lt % p.acc_stages;
-        const uint32_t aph = (lt / p.acc_stages) & 1;
-        mbar_wait(&aux->tmem_empty[as], aph ^ 1u);         // epilogue has drained this accumulator stage
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.n_tile;
-        for (int g = 0; g < p.ngroups; ++g, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&aux->a_full[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(s) * p.stage_bytes);
+        const uint32_t a16 = ring16 + s * stage16;
+        if (elect_one()) {
           for (int r = 0; r < p.R; ++r) {
-            const uint32_t a_tap = a_addr + r * p.tw * 128;      // tap r: r*tw rows further down the same box
-            const uint32_t b_addr = p.b_resident ? smem_u32(res_b) + (g * p.R + r) * b_bytes
-                                                 : a_addr + p.a_bytes + r * b_bytes;
+            const uint32_t at = a16 + r * tap16;                   // tap r: r*tw rows further down the same box
+            const uint32_t bt = p.b_resident ? res16 + (g * p.R + r) * b16 : a16 + abytes16 + r * b16;
+            if (p.nsub == 1) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint64_t adesc = umma_desc_sw128(a_tap + k * 32);
-              for (int sub = 0; sub < p.nsub; ++sub) {
-                const uint64_t bdesc = umma_desc_sw128(b_addr + sub * p.n_sub * 128 + k * 32);
-                umma_bf16_ss(d_tmem + sub * p.n_sub, adesc, bdesc, idesc, (g | r | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16_ss(d_tmem, umma_desc_sw128_a16(at + 2 * k), umma_desc_sw128_a16(bt + 2 * k), idesc,
+                             (g | r | k) != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                for (int sub = 0; sub < 2; ++sub)
+                  umma_bf16_ss(d_tmem + sub * p.n_sub, umma_desc_sw128_a16(at + 2 * k),
+                               umma_desc_sw128_a16(bt + sub * sub16 + 2 * k), idesc, (g | r | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&aux->a_empty[s]);                   // stage reusable once these MMAs have read it
         }
-        umma_commit(&aux->tmem_full[as]);                  // accumulators of this tile complete
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&aux->tmem_full[as]);   // accumulators of this tile complete
+      __syncwarp();
     }
   } else {
     // ============================================================== epilogue (warps 2..9)
@@ -205,9 +223,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const bool tile_ss = (flags & CCDM_EPI_SS) && p.tb == 1;   // scale/shift uniform over the tile
     const uint32_t trow_lane = static_cast<uint32_t>(q * 32) << 16;
     uint32_t r[32];
+    int ss_b = -1;                                         // sample whose scale/shift currently sits in aux->gs/sh
+    if (p.store_tma && ew == 0 && lane == 0) {
+      for (int i = 0; i < CCDM_MAX_Z; ++i) tma_prefetch_desc(&maps.o[i]);
+    }
 
     int lt = 0;
-    for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++lt) {
+    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
       const int as = lt % p.acc_stages;
       const uint32_t aph = (lt / p.acc_stages) & 1;
       const int w0 = (tile % p.tiles_w) * p.tw;
@@ -217,9 +239,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       const bool valid = (w < p.gW) && (h < p.gH) && (b < p.gB);
       const int bs = b < p.gB ? b : p.gB - 1;
       const long long pix = (static_cast<long long>(bs) * p.gH + (h < p.gH ? h : 0)) * p.gW + (w < p.gW ? w : 0);
-      const int sb = lt & 1;                               // per-tile scale/shift buffer
-
-      if (tile_ss) {
+      constexpr int sb = 0;
+      if (tile_ss && b0 != ss_b) {                         // new sample (uniform over the epilogue threads): refresh
+        epi_bar();                                         // everyone is done with the previous sample's vectors
         const float* ssrow = p.ss + static_cast<long long>(b0) * p.ss_ld + p.ss_off + n0;
         for (int c = et; c < p.n_tile; c += kEpiThreads) {
           const bool ok = (n0 + c) < p.N;
@@ -227,13 +249,33 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
           aux->sh[sb][c] = ok ? ssrow[p.N + c] : 0.f;
         }
         epi_bar();
+        ss_b = b0;
       }
-      float rs = 1.f;
-      if (flags & CCDM_EPI_ROWSCALE) rs = valid ? 1.f / fmaxf(sqrtf(p.rowss[pix]), 1e-12f) : 0.f;
+      // global operands of this tile are requested BEFORE waiting for the accumulators, so their latency overlaps
+      // the MMAs: the A-row sum of squares (PreNorm fold) and, when it fits in registers, the residual rows
+      float rss_raw = 1.f;
+      if ((flags & CCDM_EPI_ROWSCALE) && valid) rss_raw = __ldg(p.rowss + pix);
+      const long long ro = static_cast<long long>(bs) * p.rsB + static_cast<long long>(h) * p.rsH +
+                           static_cast<long long>(w) * p.rsW + n0;
+      const bool pre_res = (flags & CCDM_EPI_RESID) && valid && (c_hi - c_lo) <= 2;
+      uint4 rpre[2][4];
+      if (pre_res) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          if (c_lo + cc < c_hi) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + (c_lo + cc) * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              rpre[cc][g] = (n0 + (c_lo + cc) * 32 + g * 8 < p.N) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
 
       mbar_wait(&aux->tmem_full[as], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + trow_lane + as * p.n_tile;
+      float rs = 1.f;
+      if (flags & CCDM_EPI_ROWSCALE) rs = valid ? 1.f / fmaxf(sqrtf(rss_raw), 1e-12f) : 0.f;
 
       float inv = 1.f;
       if (flags & CCDM_EPI_RMSNORM) {
@@ -252,8 +294,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 
       const float* ssrow = ((flags & CCDM_EPI_SS) && !tile_ss)
                                ? p.ss + static_cast<long long>(bs) * p.ss_ld + p.ss_off + n0 : nullptr;
-      const long long ro = static_cast<long long>(bs) * p.rsB + static_cast<long long>(h) * p.rsH +
-                           static_cast<long long>(w) * p.rsW + n0;
       const long long oo = p.ooff[z] + static_cast<long long>(bs) * p.osB + static_cast<long long>(h) * p.osH +
                            static_cast<long long>(w) * p.osW + n0;
       float out_ss = 0.f;
@@ -300,13 +340,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= k;
         }
-        if (valid) {
-          if (flags & CCDM_EPI_RESID) {
+        if (valid || p.store_tma) {
+          if ((flags & CCDM_EPI_RESID) && valid) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + c * 32);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (n0 + c * 32 + g * 8 < p.N) {
-                const uint4 u = __ldg(rp + g);
+                const uint4 u = pre_res ? rpre[(c - c_lo) & 1][g] : __ldg(rp + g);
                 v[g * 8 + 0] += bf16_lo(u.x); v[g * 8 + 1] += bf16_hi(u.x);
                 v[g * 8 + 2] += bf16_lo(u.y); v[g * 8 + 3] += bf16_hi(u.y);
                 v[g * 8 + 4] += bf16_lo(u.z); v[g * 8 + 5] += bf16_hi(u.z);
@@ -322,15 +362,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                 *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
           } else {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + oo + c * 32;
+            // TMA-store path: the row goes to the swizzled staging panel (64 channels = 128 B per row per panel)
+            uint8_t* srow = stg + static_cast<size_t>(lt % p.out_bufs) * p.out_bytes + (c >> 1) * 16384 + m * 128;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              if (n0 + c * 32 + g * 8 < p.N) {
+              if (p.store_tma || n0 + c * 32 + g * 8 < p.N) {
                 uint4 u;
                 u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
                 u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
                 u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
                 u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                *reinterpret_cast<uint4*>(op + g * 8) = u;
+                if (p.store_tma)
+                  *reinterpret_cast<uint4*>(srow + ((((c & 1) * 4 + g) ^ (m & 7)) << 4)) = u;
+                else
+                  *reinterpret_cast<uint4*>(op + g * 8) = u;
                 if (flags & CCDM_EPI_SUMSQ_OUT) {
                   const float a0 = bf16_lo(u.x), a1 = bf16_hi(u.x), a2 = bf16_lo(u.y), a3 = bf16_hi(u.y);
                   const float a4 = bf16_lo(u.z), a5 = bf16_hi(u.z), a6 = bf16_lo(u.w), a7 = bf16_hi(u.w);
@@ -347,15 +392,31 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         if (lane == 0) mbar_arrive(&aux->tmem_empty[as]);
       }
       if (flags & CCDM_EPI_SUMSQ_OUT) {                    // combine the two column halves of every row
-        if (half == 1) aux->part[m] = out_ss;
+        if (half == 1) aux->part[lt & 1][m] = out_ss;
+      }
+      if (p.store_tma) {
+        // staging complete -> one thread hands the tile to the TMA unit.  Before the barrier it makes sure the
+        // PREVIOUS tile's bulk stores have finished reading their buffer, which the next tile will overwrite.
+        fence_proxy_async_smem();
+        if (et == 0) tma_store_wait_read0();
         epi_bar();
-        if (half == 0 && valid) p.out_rowss[pix] = out_ss + aux->part[m];
+        if (et == 0) {
+          const uint8_t* sbuf = stg + static_cast<size_t>(lt % p.out_bufs) * p.out_bytes;
+          for (int pn = 0; pn < (p.n_tile + 63) / 64; ++pn)
+            if (n0 + pn * 64 < p.N) tma_store_4d(&maps.o[z], sbuf + pn * 16384, n0 + pn * 64, w0, h0, b0);
+          tma_store_commit();
+          if (p.out_bufs == 1) tma_store_wait_read0();
+        }
+        if (p.out_bufs == 1) epi_bar();
+      } else if (flags & CCDM_EPI_SUMSQ_OUT) {
         epi_bar();
       }
+      if ((flags & CCDM_EPI_SUMSQ_OUT) && half == 0 && valid) p.out_rowss[pix] = out_ss + aux->part[lt & 1][m];
     }
   }
 
   // ---------------------------------------------------------------- teardown
+  if (p.store_tma && tid == 64) tma_store_wait_all();      // et == 0: the thread that issued the bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -503,12 +564,20 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   if (gx > p.tiles_m) gx = p.tiles_m;
   if (gx < 1) gx = 1;
   const int tiles_per_cta = (p.tiles_m + gx - 1) / gx;
+  gx = (p.tiles_m + tiles_per_cta - 1) / tiles_per_cta;            // contiguous ranges: no CTA without work
+  p.tiles_per_cta = tiles_per_cta;
 
   // ---- shared-memory plan
   const uint32_t b_bytes = (uint32_t)a->n_tile * 128u;
   p.a_bytes = (uint32_t)(box_h * a->tw * a->tb) * 128u;
   const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)a->ngroups * sizeof(int4);
-  const size_t budget = 226 * 1024 - aux_bytes - 1024;
+  size_t budget = 226 * 1024 - aux_bytes - 1024;
+  // bf16 outputs up to 256 channels per CTA leave through shared memory and TMA bulk stores (coalesced, clipped at the
+  // tensor edges); wider tiles (4x4 bottleneck layers) and fp32 outputs keep per-thread stores
+  p.store_tma = (!(a->flags & CCDM_EPI_OUT_F32) && a->n_tile <= 256) ? 1 : 0;
+  p.out_bytes = p.store_tma ? (uint32_t)((a->n_tile + 63) / 64) * 16384u : 0;
+  p.out_bufs = p.store_tma ? ((tiles_per_cta > 1 && p.out_bytes <= 32768) ? 2 : 1) : 0;
+  budget -= (size_t)p.out_bufs * p.out_bytes;
   const size_t res_all = (size_t)nkb * b_bytes;
   p.b_resident = (a->w_batch_rows == 0 && tiles_per_cta >= 2 && res_all + 3 * (size_t)p.a_bytes <= budget) ? 1 : 0;
   p.res_bytes = p.b_resident ? (uint32_t)res_all : 0;
@@ -521,7 +590,20 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   CCDM_REQUIRE(stages >= 1, CCDM_ERR_UNSUPPORTED_SHAPE,
                "tapgemm: one pipeline stage (%u bytes) does not fit shared memory", p.stage_bytes);
   p.stages = stages;
-  const size_t smem_bytes = p.res_bytes + (size_t)stages * p.stage_bytes + aux_bytes + 1024;
+  const size_t smem_bytes = p.res_bytes + (size_t)stages * p.stage_bytes + (size_t)p.out_bufs * p.out_bytes + aux_bytes + 1024;
+  if (p.store_tma) {
+    CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->osW % 8 == 0 && a->osH % 8 == 0 && a->osB % 8 == 0,
+                 CCDM_ERR_BAD_ARG, "tapgemm: output view must be 16-byte aligned with strides in multiples of 8");
+    for (int zz = 0; zz < CCDM_MAX_Z; ++zz) {
+      const int zi = zz < a->nz ? zz : 0;
+      CCDM_REQUIRE(a->ooff[zi] % 8 == 0, CCDM_ERR_BAD_ARG, "tapgemm: ooff[%d] must be a multiple of 8 elements", zi);
+      cuuint64_t dims[4] = {(cuuint64_t)a->N, (cuuint64_t)a->gW, (cuuint64_t)a->gH, (cuuint64_t)a->gB};
+      cuuint64_t str[3] = {(cuuint64_t)a->osW * 2, (cuuint64_t)a->osH * 2, (cuuint64_t)a->osB * 2};
+      cuuint32_t box[4] = {kBlockK, (cuuint32_t)a->tw, (cuuint32_t)a->th, (cuuint32_t)a->tb};
+      int rc = encode_map_bf16(&maps.o[zz], reinterpret_cast<const __nv_bfloat16*>(a->out) + a->ooff[zi], 4, dims, str, box);
+      if (rc != CCDM_OK) return rc;
+    }
+  }
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
