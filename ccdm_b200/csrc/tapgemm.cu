@@ -221,40 +221,61 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const int per_half = (nchunk + 1) >> 1;
     const int c_lo = half * per_half, c_hi = min(nchunk, c_lo + per_half);
     const bool tile_ss = (flags & CCDM_EPI_SS) && p.tb == 1;   // scale/shift uniform over the tile
+    const bool use_rs = (flags & CCDM_EPI_ROWSCALE) != 0;
     const uint32_t trow_lane = static_cast<uint32_t>(q * 32) << 16;
+    const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages >> 1;     // acc_stages is 1 or 2
+    const int ob_mask = p.out_bufs > 1 ? 1 : 0;
+    const int npanels = (p.n_tile + 63) / 64;
     uint32_t r[32];
     int ss_b = -1;                                         // sample whose scale/shift currently sits in aux->gs/sh
-    if (p.store_tma && ew == 0 && lane == 0) {
+    if (p.store_tma && et == 0) {
       for (int i = 0; i < CCDM_MAX_Z; ++i) tma_prefetch_desc(&maps.o[i]);
+    }
+    // tile coordinates advance incrementally (the CTA's tiles are contiguous): no divisions in the loop
+    int twi = t_begin % p.tiles_w, thi = (t_begin / p.tiles_w) % p.tiles_h, tbi = t_begin / tiles_per_sample;
+
+    auto row_of = [&](int w0, int h0, int b0, bool& valid, int& bs, long long& pix) {
+      const int w = w0 + lw, h = h0 + lh, b = b0 + lb;
+      valid = (w < p.gW) && (h < p.gH) && (b < p.gB);
+      bs = b < p.gB ? b : p.gB - 1;
+      pix = (static_cast<long long>(bs) * p.gH + (h < p.gH ? h : 0)) * p.gW + (w < p.gW ? w : 0);
+    };
+    float rss_next = 1.f;                                  // A-row sum of squares, fetched one tile ahead
+    if (use_rs && t_begin < t_end) {
+      bool v0; int b_; long long px;
+      row_of(twi * p.tw, thi * p.th, tbi * p.tb, v0, b_, px);
+      if (v0) rss_next = __ldg(p.rowss + px);
     }
 
     int lt = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
-      const int as = lt % p.acc_stages;
-      const uint32_t aph = (lt / p.acc_stages) & 1;
-      const int w0 = (tile % p.tiles_w) * p.tw;
-      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
-      const int b0 = (tile / tiles_per_sample) * p.tb;
-      const int w = w0 + lw, h = h0 + lh, b = b0 + lb;
-      const bool valid = (w < p.gW) && (h < p.gH) && (b < p.gB);
-      const int bs = b < p.gB ? b : p.gB - 1;
-      const long long pix = (static_cast<long long>(bs) * p.gH + (h < p.gH ? h : 0)) * p.gW + (w < p.gW ? w : 0);
-      constexpr int sb = 0;
+      const int as = lt & acc_mask;
+      const uint32_t aph = (lt >> acc_shift) & 1;
+      const int w0 = twi * p.tw, h0 = thi * p.th, b0 = tbi * p.tb;
+      if (++twi == p.tiles_w) { twi = 0; if (++thi == p.tiles_h) { thi = 0; ++tbi; } }
+      bool valid; int bs; long long pix;
+      row_of(w0, h0, b0, valid, bs, pix);
+      const int w = w0 + lw, h = h0 + lh;
+
       if (tile_ss && b0 != ss_b) {                         // new sample (uniform over the epilogue threads): refresh
         epi_bar();                                         // everyone is done with the previous sample's vectors
         const float* ssrow = p.ss + static_cast<long long>(b0) * p.ss_ld + p.ss_off + n0;
         for (int c = et; c < p.n_tile; c += kEpiThreads) {
           const bool ok = (n0 + c) < p.N;
-          aux->gs[sb][c] = ok ? aux->gain[c] * (1.f + ssrow[c]) : 0.f;
-          aux->sh[sb][c] = ok ? ssrow[p.N + c] : 0.f;
+          aux->gs[0][c] = ok ? aux->gain[c] * (1.f + ssrow[c]) : 0.f;
+          aux->sh[0][c] = ok ? ssrow[p.N + c] : 0.f;
         }
         epi_bar();
         ss_b = b0;
       }
-      // global operands of this tile are requested BEFORE waiting for the accumulators, so their latency overlaps
-      // the MMAs: the A-row sum of squares (PreNorm fold) and, when it fits in registers, the residual rows
-      float rss_raw = 1.f;
-      if ((flags & CCDM_EPI_ROWSCALE) && valid) rss_raw = __ldg(p.rowss + pix);
+      // global operands are requested BEFORE waiting for the accumulators so their latency overlaps the MMAs:
+      // next tile's A-row sum of squares and, when it fits in registers, this tile's residual rows
+      const float rss_raw = rss_next;
+      if (use_rs && tile + 1 < t_end) {
+        bool v1; int b_; long long px;
+        row_of(twi * p.tw, thi * p.th, tbi * p.tb, v1, b_, px);
+        rss_next = v1 ? __ldg(p.rowss + px) : 1.f;
+      }
       const long long ro = static_cast<long long>(bs) * p.rsB + static_cast<long long>(h) * p.rsH +
                            static_cast<long long>(w) * p.rsW + n0;
       const bool pre_res = (flags & CCDM_EPI_RESID) && valid && (c_hi - c_lo) <= 2;
@@ -274,28 +295,32 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       mbar_wait(&aux->tmem_full[as], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + trow_lane + as * p.n_tile;
-      float rs = 1.f;
-      if (flags & CCDM_EPI_ROWSCALE) rs = valid ? 1.f / fmaxf(sqrtf(rss_raw), 1e-12f) : 0.f;
+      const float rs = use_rs ? (valid ? 1.f / fmaxf(sqrtf(rss_raw), 1e-12f) : 0.f) : 1.f;
+      const float2 rs2 = make_float2(rs, rs);
 
       float inv = 1.f;
       if (flags & CCDM_EPI_RMSNORM) {
-        float ssq = 0.f;
+        float2 sq = make_float2(0.f, 0.f);
         for (int c = 0; c < nchunk; ++c) {
           tmem_ld32(trow + c * 32, r);
           tmem_ld_wait();
+          const float2* b2 = reinterpret_cast<const float2*>(aux->bias + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = fmaf(__uint_as_float(r[j]), rs, aux->bias[c * 32 + j]);
-            ssq = fmaf(v, v, ssq);
+          for (int i = 0; i < 16; ++i) {
+            const float2 a = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            const float2 v = use_rs ? __ffma2_rn(a, rs2, b2[i]) : __fadd2_rn(a, b2[i]);
+            sq = __ffma2_rn(v, v, sq);
           }
         }
-        inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
+        inv = 1.f / fmaxf(sqrtf(sq.x + sq.y), 1e-12f);
       }
+      const float2 inv2 = make_float2(inv, inv);
 
       const float* ssrow = ((flags & CCDM_EPI_SS) && !tile_ss)
                                ? p.ss + static_cast<long long>(bs) * p.ss_ld + p.ss_off + n0 : nullptr;
       const long long oo = p.ooff[z] + static_cast<long long>(bs) * p.osB + static_cast<long long>(h) * p.osH +
                            static_cast<long long>(w) * p.osW + n0;
+      uint8_t* const stg_row = stg + static_cast<size_t>(lt & ob_mask) * p.out_bytes + m * 128;
       float out_ss = 0.f;
 
       for (int c = c_lo; c < c_hi; ++c) {
@@ -306,82 +331,107 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&aux->tmem_empty[as]);
         }
-        float v[32];
+        float2 v[16];
+        {
+          const float2* b2 = reinterpret_cast<const float2*>(aux->bias + c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), rs, aux->bias[c * 32 + j]);
+          for (int i = 0; i < 16; ++i) {
+            const float2 a = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            v[i] = use_rs ? __ffma2_rn(a, rs2, b2[i]) : __fadd2_rn(a, b2[i]);
+          }
+        }
         if (flags & CCDM_EPI_RMSNORM) {
           if (tile_ss) {
+            const float2* g2 = reinterpret_cast<const float2*>(aux->gs[0] + c * 32);
+            const float2* s2 = reinterpret_cast<const float2*>(aux->sh[0] + c * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j] * inv, aux->gs[sb][c * 32 + j], aux->sh[sb][c * 32 + j]);
+            for (int i = 0; i < 16; ++i) v[i] = __ffma2_rn(__fmul2_rn(v[i], inv2), g2[i], s2[i]);
           } else {
+            const float2* g2 = reinterpret_cast<const float2*>(aux->gain + c * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= inv * aux->gain[c * 32 + j];
+            for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(__fmul2_rn(v[i], inv2), g2[i]);
           }
         }
-        if (ssrow) {
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c * 32 + j < p.N) v[j] = fmaf(v[j], 1.f + __ldg(ssrow + c * 32 + j), __ldg(ssrow + p.N + c * 32 + j));
-        }
-        if (flags & CCDM_EPI_SILU) {
+        if (ssrow) {                                       // tiles spanning several samples: per-row scale/shift
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[j]);
-        }
-        if ((flags & CCDM_EPI_QSOFTMAX) && (n0 + c * 32 < p.q_cols)) {
-          float mx = v[0];
-#pragma unroll
-          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-          float sum = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = __expf(v[j] - mx);
-            sum += v[j];
-          }
-          const float k = __fdividef(p.q_scale, sum);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= k;
-        }
-        if (valid || p.store_tma) {
-          if ((flags & CCDM_EPI_RESID) && valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + c * 32);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (n0 + c * 32 + g * 8 < p.N) {
-                const uint4 u = pre_res ? rpre[(c - c_lo) & 1][g] : __ldg(rp + g);
-                v[g * 8 + 0] += bf16_lo(u.x); v[g * 8 + 1] += bf16_hi(u.x);
-                v[g * 8 + 2] += bf16_lo(u.y); v[g * 8 + 3] += bf16_hi(u.y);
-                v[g * 8 + 4] += bf16_lo(u.z); v[g * 8 + 5] += bf16_hi(u.z);
-                v[g * 8 + 6] += bf16_lo(u.w); v[g * 8 + 7] += bf16_hi(u.w);
-              }
+          for (int i = 0; i < 16; ++i) {
+            if (n0 + c * 32 + 2 * i < p.N) {               // N is a multiple of 8: pairs are all-in or all-out
+              const float2 sc = __ldg(reinterpret_cast<const float2*>(ssrow + c * 32) + i);
+              const float2 sf = __ldg(reinterpret_cast<const float2*>(ssrow + p.N + c * 32) + i);
+              v[i] = __ffma2_rn(v[i], make_float2(1.f + sc.x, 1.f + sc.y), sf);
             }
           }
-          if (flags & CCDM_EPI_OUT_F32) {
+        }
+        if (flags & CCDM_EPI_SILU) {                       // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU per element
+          const float2 half2 = make_float2(0.5f, 0.5f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 hx = __fmul2_rn(v[i], half2);
+            float2 t;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(hx.x));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(hx.y));
+            v[i] = __ffma2_rn(hx, t, hx);
+          }
+        }
+        if ((flags & CCDM_EPI_QSOFTMAX) && (n0 + c * 32 < p.q_cols)) {
+          float mx = fmaxf(v[0].x, v[0].y);
+#pragma unroll
+          for (int i = 1; i < 16; ++i) mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
+          const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+          const float2 nmx = make_float2(-mx * 1.4426950408889634f, -mx * 1.4426950408889634f);
+          float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 e = __ffma2_rn(v[i], l2e, nmx);
+            v[i].x = exp2f(e.x);
+            v[i].y = exp2f(e.y);
+            sum2 = __fadd2_rn(sum2, v[i]);
+          }
+          const float k = __fdividef(p.q_scale, sum2.x + sum2.y);
+          const float2 k2 = make_float2(k, k);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], k2);
+        }
+        if ((flags & CCDM_EPI_RESID) && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + c * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (n0 + c * 32 + g * 8 < p.N) {
+              const uint4 u = pre_res ? (((c - c_lo) & 1) ? rpre[1][g] : rpre[0][g]) : __ldg(rp + g);
+              v[g * 4 + 0] = __fadd2_rn(v[g * 4 + 0], make_float2(bf16_lo(u.x), bf16_hi(u.x)));
+              v[g * 4 + 1] = __fadd2_rn(v[g * 4 + 1], make_float2(bf16_lo(u.y), bf16_hi(u.y)));
+              v[g * 4 + 2] = __fadd2_rn(v[g * 4 + 2], make_float2(bf16_lo(u.z), bf16_hi(u.z)));
+              v[g * 4 + 3] = __fadd2_rn(v[g * 4 + 3], make_float2(bf16_lo(u.w), bf16_hi(u.w)));
+            }
+          }
+        }
+        if (flags & CCDM_EPI_OUT_F32) {
+          if (valid) {
             float* op = reinterpret_cast<float*>(p.out) + oo + c * 32;
 #pragma unroll
             for (int g = 0; g < 8; ++g)
               if (n0 + c * 32 + g * 4 < p.N)
-                *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + oo + c * 32;
-            // TMA-store path: the row goes to the swizzled staging panel (64 channels = 128 B per row per panel)
-            uint8_t* srow = stg + static_cast<size_t>(lt % p.out_bufs) * p.out_bytes + (c >> 1) * 16384 + m * 128;
+                *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[2 * g].x, v[2 * g].y, v[2 * g + 1].x, v[2 * g + 1].y);
+          }
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + oo + c * 32;
+          uint8_t* const srow = stg_row + (c >> 1) * 16384;                // 64-channel staging panel of this chunk
+          const int j0 = (c & 1) * 4;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (p.store_tma || n0 + c * 32 + g * 8 < p.N) {
-                uint4 u;
-                u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                if (p.store_tma)
-                  *reinterpret_cast<uint4*>(srow + ((((c & 1) * 4 + g) ^ (m & 7)) << 4)) = u;
-                else
-                  *reinterpret_cast<uint4*>(op + g * 8) = u;
-                if (flags & CCDM_EPI_SUMSQ_OUT) {
-                  const float a0 = bf16_lo(u.x), a1 = bf16_hi(u.x), a2 = bf16_lo(u.y), a3 = bf16_hi(u.y);
-                  const float a4 = bf16_lo(u.z), a5 = bf16_hi(u.z), a6 = bf16_lo(u.w), a7 = bf16_hi(u.w);
-                  out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
-                }
-              }
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16(v[g * 4 + 0].x, v[g * 4 + 0].y);
+            u.y = pack_bf16(v[g * 4 + 1].x, v[g * 4 + 1].y);
+            u.z = pack_bf16(v[g * 4 + 2].x, v[g * 4 + 2].y);
+            u.w = pack_bf16(v[g * 4 + 3].x, v[g * 4 + 3].y);
+            if (p.store_tma)                                               // swizzled like a TMA SWIZZLE_128B box
+              *reinterpret_cast<uint4*>(srow + (((j0 + g) ^ (m & 7)) << 4)) = u;
+            else if (valid && n0 + c * 32 + g * 8 < p.N)
+              *reinterpret_cast<uint4*>(op + g * 8) = u;
+            if ((flags & CCDM_EPI_SUMSQ_OUT) && n0 + c * 32 + g * 8 < p.N) {
+              const float a0 = bf16_lo(u.x), a1 = bf16_hi(u.x), a2 = bf16_lo(u.y), a3 = bf16_hi(u.y);
+              const float a4 = bf16_lo(u.z), a5 = bf16_hi(u.z), a6 = bf16_lo(u.w), a7 = bf16_hi(u.w);
+              out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
             }
           }
         }
@@ -391,9 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&aux->tmem_empty[as]);
       }
-      if (flags & CCDM_EPI_SUMSQ_OUT) {                    // combine the two column halves of every row
-        if (half == 1) aux->part[lt & 1][m] = out_ss;
-      }
+      if ((flags & CCDM_EPI_SUMSQ_OUT) && half == 1) aux->part[lt & 1][m] = out_ss;   // combine the two column halves
       if (p.store_tma) {
         // staging complete -> one thread hands the tile to the TMA unit.  Before the barrier it makes sure the
         // PREVIOUS tile's bulk stores have finished reading their buffer, which the next tile will overwrite.
@@ -401,8 +449,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         if (et == 0) tma_store_wait_read0();
         epi_bar();
         if (et == 0) {
-          const uint8_t* sbuf = stg + static_cast<size_t>(lt % p.out_bufs) * p.out_bytes;
-          for (int pn = 0; pn < (p.n_tile + 63) / 64; ++pn)
+          const uint8_t* sbuf = stg + static_cast<size_t>(lt & ob_mask) * p.out_bytes;
+          for (int pn = 0; pn < npanels; ++pn)
             if (n0 + pn * 64 < p.N) tma_store_4d(&maps.o[z], sbuf + pn * 16384, n0 + pn * 64, w0, h0, b0);
           tma_store_commit();
           if (p.out_bufs == 1) tma_store_wait_read0();
@@ -560,7 +608,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   // ---- launch geometry: persistent CTAs, one (z, n-tile) combination per blockIdx.y
   const int combos = p.n_tiles * a->nz;
   const int sms = num_sms();
-  int gx = (sms + combos - 1) / combos;
+  int gx = sms / combos;                                           // never more CTAs than SMs: no second wave
   if (gx > p.tiles_m) gx = p.tiles_m;
   if (gx < 1) gx = 1;
   const int tiles_per_cta = (p.tiles_m + gx - 1) / gx;
