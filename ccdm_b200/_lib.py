@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libccdm_b200.so")
 MAX_SRC, MAX_Z, STEP_NCOEF = 4, 4, 12
 
 EPI_BIAS, EPI_ROWSCALE, EPI_RMSNORM, EPI_SS = 0x1, 0x2, 0x4, 0x8
-EPI_SILU, EPI_RESID, EPI_QSOFTMAX, EPI_SUMSQ_OUT, EPI_OUT_F32 = 0x10, 0x20, 0x40, 0x80, 0x100
+EPI_SILU, EPI_RESID, EPI_QSOFTMAX, EPI_SUMSQ_OUT, EPI_OUT_F32, EPI_KEXP = 0x10, 0x20, 0x40, 0x80, 0x100, 0x200
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU = 0, 1, 2, 3
 OBJ = {"pred_noise": 0, "pred_x0": 1, "pred_v": 2}
 
@@ -72,6 +72,7 @@ SIGNATURES = {
     "ccdm_stem_conv7": (C.c_int, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp]),
     "ccdm_head_conv1": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "ccdm_linattn_context": (C.c_int, [vp, vp, i32, i32, i32, vp]),
+    "ccdm_kexp_bound": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
     "ccdm_linattn_fold": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "ccdm_attention_small": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp]),
     "ccdm_linear_small": (C.c_int, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, i64, vp]),

@@ -116,75 +116,6 @@ __global__ void __launch_bounds__(256) head_conv1_kernel(const __nv_bfloat16* __
   for (int o = 0; o < Cout; ++o) out[(b * Cout + o) * HW + hw] = acc[o];
 }
 
-// ============================================================================ linear attention: context
-// unet.py:208,212.  One CTA per (sample, head): streaming softmax over the n tokens of k (running max, rescaled
-// sums) fused with the 32x32 context accumulation.  128 threads; thread (d, eg) owns context[d][8*eg .. 8*eg+8).
-constexpr int kCtxRows = 64;
-
-__global__ void __launch_bounds__(128) linattn_context_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                              float* __restrict__ ctx, int n, int heads) {
-  __shared__ float ks[kCtxRows][33];
-  __shared__ __align__(16) float vs[kCtxRows][32];
-  const int t = threadIdx.x;
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int ld = 3 * heads * 32;
-  const __nv_bfloat16* kbase = qkv + (long long)b * n * ld + heads * 32 + h * 32;
-  const __nv_bfloat16* vbase = kbase + heads * 32;
-  const int d = t >> 2, eg = t & 3;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  float ssum = 0.f, m_run = -FLT_MAX;
-
-  for (int r0 = 0; r0 < n; r0 += kCtxRows) {
-    const int rows = min(kCtxRows, n - r0);
-#pragma unroll
-    for (int i = 0; i < kCtxRows / 16; ++i) {
-      const int row = (t >> 3) + 16 * i, c4 = (t & 7) * 4;
-      float k4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX}, v4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (row < rows) {
-        const uint2 ku = __ldg(reinterpret_cast<const uint2*>(kbase + (long long)(r0 + row) * ld + c4));
-        const uint2 vu = __ldg(reinterpret_cast<const uint2*>(vbase + (long long)(r0 + row) * ld + c4));
-        k4[0] = bf16_lo(ku.x); k4[1] = bf16_hi(ku.x); k4[2] = bf16_lo(ku.y); k4[3] = bf16_hi(ku.y);
-        v4[0] = bf16_lo(vu.x); v4[1] = bf16_hi(vu.x); v4[2] = bf16_lo(vu.y); v4[3] = bf16_hi(vu.y);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        ks[row][c4 + j] = k4[j];
-        vs[row][c4 + j] = v4[j];
-      }
-    }
-    __syncthreads();
-    float mx = -FLT_MAX;
-    for (int row = eg; row < rows; row += 4) mx = fmaxf(mx, ks[row][d]);
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    const float m_new = fmaxf(m_run, mx);
-    const float sc = __expf(m_run - m_new);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] *= sc;
-    ssum *= sc;
-    m_run = m_new;
-    for (int row = eg; row < rows; row += 4) ks[row][d] = __expf(ks[row][d] - m_new);
-    __syncthreads();
-    for (int row = 0; row < rows; ++row) {
-      const float pk = ks[row][d];
-      const float4 va = *reinterpret_cast<const float4*>(&vs[row][eg * 8]);
-      const float4 vb = *reinterpret_cast<const float4*>(&vs[row][eg * 8 + 4]);
-      acc[0] = fmaf(pk, va.x, acc[0]); acc[1] = fmaf(pk, va.y, acc[1]);
-      acc[2] = fmaf(pk, va.z, acc[2]); acc[3] = fmaf(pk, va.w, acc[3]);
-      acc[4] = fmaf(pk, vb.x, acc[4]); acc[5] = fmaf(pk, vb.y, acc[5]);
-      acc[6] = fmaf(pk, vb.z, acc[6]); acc[7] = fmaf(pk, vb.w, acc[7]);
-      ssum += pk;
-    }
-    __syncthreads();
-  }
-  const float inv = 1.f / ssum;
-  float* o = ctx + ((long long)blockIdx.x * 32 + d) * 32 + eg * 8;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = acc[j] * inv;
-}
-
 // ============================================================================ linear attention: fold context into W_out
 // wfold[b][c][h*32+d] = sum_e w_out[c][h*32+e] * ctx[b][h][d][e].  One CTA per (sample, 32-row slab of c).
 __global__ void linattn_fold_kernel(const float* __restrict__ w_out, const float* __restrict__ ctx,
@@ -413,12 +344,6 @@ extern "C" int ccdm_head_conv1(const void* x, const float* w, const float* bias,
   head_conv1_kernel<<<(unsigned)((npix + 255) / 256), 256, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, w, bias, out, npix, H * W, Cin, Cout);
   return after_launch("head_conv1_kernel");
-}
-
-extern "C" int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads, void* stream) {
-  CCDM_REQUIRE(qkv && ctx && B > 0 && n > 0 && heads > 0, CCDM_ERR_BAD_ARG, "linattn_context: bad args");
-  linattn_context_kernel<<<B * heads, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, ctx, n, heads);
-  return after_launch("linattn_context_kernel");
 }
 
 extern "C" int ccdm_linattn_fold(const float* w_out, const float* ctx, void* wfold, int32_t B, int32_t C,

@@ -392,6 +392,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], k2);
         }
+        if ((flags & CCDM_EPI_KEXP) && (n0 + c * 32 >= p.q_cols) && (n0 + c * 32 < 2 * p.q_cols)) {
+          const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 e = __fmul2_rn(v[i], l2e);
+            v[i].x = exp2f(e.x);
+            v[i].y = exp2f(e.y);
+          }
+        }
         if ((flags & CCDM_EPI_RESID) && valid) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + c * 32);
 #pragma unroll
@@ -546,7 +555,8 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_RESID) || a->resid, CCDM_ERR_BAD_ARG, "tapgemm: resid flag without pointer");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_SUMSQ_OUT) || (a->out_rowss && a->n_rows == a->n_tile), CCDM_ERR_BAD_ARG,
                "tapgemm: sumsq output needs out_rowss and a single N tile");
-  CCDM_REQUIRE(!(a->flags & CCDM_EPI_QSOFTMAX) || a->q_cols % 32 == 0, CCDM_ERR_BAD_ARG, "tapgemm: q_cols %% 32");
+  CCDM_REQUIRE(!(a->flags & (CCDM_EPI_QSOFTMAX | CCDM_EPI_KEXP)) || (a->q_cols > 0 && a->q_cols % 32 == 0),
+               CCDM_ERR_BAD_ARG, "tapgemm: q_cols must be a positive multiple of 32");
   CCDM_REQUIRE(a->w_batch_rows == 0 || (a->tb == 1 && a->nz == 1 && a->w_batch_rows >= a->n_rows), CCDM_ERR_BAD_ARG,
                "tapgemm: per-sample weights need tb == 1, nz == 1 and w_batch_rows >= n_rows");
 

@@ -211,6 +211,8 @@ def _make_call(lib, r, keep):
     if k == "head_conv1":
         return lib.ccdm_head_conv1, (p(a["x"]), p(a["w"]), p(a["bias"]), p(a["out"]), a["B"], a["H"], a["W"], a["Cin"],
                                      a["Cout"]), k
+    if k == "kexp_bound":
+        return lib.ccdm_kexp_bound, (p(a["wpacked"]), a["n_rows"], a["K"], a["lo"], a["hi"], p(a["bias"])), k
     if k == "linattn_context":
         return lib.ccdm_linattn_context, (p(a["qkv"]), p(a["ctx"]), a["B"], a["n"], a["heads"]), k
     if k == "linattn_fold":
@@ -266,6 +268,17 @@ class WeightStore:
         if cin_gain is not None:
             self._params.append(cin_gain)
         return rec
+
+    def kexp_bias(self, pack: PackRec, lo: int, hi: int) -> torch.Tensor:
+        """Bias vector holding the softmax shift of the k columns of a to_qkv weight (refreshed with the pack)."""
+        key = "kexp:" + pack.name
+        if key not in self.packs:
+            bias = torch.zeros(pack.n_rows, dtype=torch.float32, device=self.device)
+            rec = KernelRec("kexp_bound", dict(wpacked=pack.packed, n_rows=pack.n_rows, K=pack.plan.nkb * KB, lo=lo,
+                                               hi=hi, bias=bias))
+            self.packs[key] = rec
+            self.program.recs.append(rec)
+        return self.packs[key].a["bias"]
 
     def stamp(self):
         return tuple((p.data_ptr(), p._version) for p in self._params)
@@ -438,8 +451,11 @@ class UnetProgram(Program):
         assert att.dim_head == 32, "linear attention kernels are written for dim_head == 32 (unet.py:190)"
         n = h * w
         qkv = self.act(name + ".qkv", h, w, 3 * hid)
-        self.conv(name + ".to_qkv", "1x1", [x], att.to_qkv, qkv, L.EPI_ROWSCALE | L.EPI_QSOFTMAX, rowss=rowss,
-                  cin_gain=pre.norm.g, cin_gain_mul=math.sqrt(C), q=(att.scale, hid))
+        rec = self.conv(name + ".to_qkv", "1x1", [x], att.to_qkv, qkv, L.EPI_ROWSCALE | L.EPI_QSOFTMAX | L.EPI_KEXP,
+                        rowss=rowss, cin_gain=pre.norm.g, cin_gain_mul=math.sqrt(C), q=(att.scale, hid))
+        # k columns: p = exp(k - bound), bound = ||W'_d|| from the packed weights (no max pass over the tokens)
+        rec.bias = self.weights.kexp_bias(rec.pack, hid, 2 * hid)
+        rec.flags |= L.EPI_BIAS
         ctx = self.buf(name + ".ctx", (self.B, heads, 32, 32), torch.float32)
         self.kernel("linattn_context", qkv=qkv, ctx=ctx, B=self.B, n=n, heads=heads)
         conv_out, norm_out = att.to_out[0], att.to_out[1]

@@ -53,6 +53,8 @@ int ccdm_struct_size(int which);
 #define CCDM_EPI_QSOFTMAX 0x40u  /* columns < q_cols: softmax over aligned groups of 32, times q_scale */
 #define CCDM_EPI_SUMSQ_OUT 0x80u /* out_rowss[pixel] = sum_n (bf16-rounded out)^2 */
 #define CCDM_EPI_OUT_F32 0x100u  /* out is fp32 instead of bf16 */
+#define CCDM_EPI_KEXP 0x200u     /* columns in [q_cols, 2*q_cols): v = exp(v) (the k softmax numerator; bias carries
+                                    the -bound shift from ccdm_kexp_bound, so v <= ~1 and nothing overflows) */
 
 typedef struct ccdm_view {
   const void* ptr;    /* bf16; first element of the view (already offset for channel slices / parity planes) */
@@ -116,11 +118,16 @@ int ccdm_head_conv1(const void* x_nhwc, const float* w, const float* bias, float
 
 /* ------------------------------------------------------------------------------------------------------------
  * Attention cores.
- *   linear attention, unet.py:202-216: qkv is bf16 [B][n][3*heads*32] with q already softmaxed*scale by the
- *     tap-GEMM epilogue; context[b,h,d,e] = sum_n softmax_n(k)[d,n] v[e,n]  (fp32 [B][heads][32][32])
+ *   linear attention, unet.py:202-216: qkv is bf16 [B][n][3*heads*32]; the tap-GEMM epilogue has already turned
+ *     q into softmax_d(q)*scale and k into p = exp(k - bound_d); context[b,h,d,e] = sum_n p[d,n] v[e,n] / sum_n p[d,n]
+ *     (fp32 [B][heads][32][32]) runs on tcgen05 for heads == 4 (both operands token-major = MN-major UMMA)
  *   softmax attention at the bottleneck, unet.py:228-240 (n <= 64 tokens, dim_head <= 64)
  * ------------------------------------------------------------------------------------------------------------ */
 int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads, void* stream);
+/* bias[n] = -1.01*||wpacked[n,:]||_2 - 1e-3 for n in [row_lo,row_hi), 0 elsewhere.  The PreNorm'd input rows have unit
+ * length, so |k[n,d]| <= ||W'_d||: using this bound as the softmax shift needs no max pass over the tokens. */
+int ccdm_kexp_bound(const void* wpacked, int32_t n_rows, int32_t K, int32_t row_lo, int32_t row_hi, float* bias,
+                    void* stream);
 /* Fold the per-sample context into the output projection (unet.py:214-216 + to_out[0] at :198):
  *   wfold[b][c][h*32+d] = sum_e w_out[c][h*32+e] * ctx[b][h][d][e]     bf16 [B][n_rows][heads*32], rows >= C zero
  * so that to_out(context^T . q) becomes one tap-GEMM over q with per-sample weights (w_batch_rows = n_rows). */

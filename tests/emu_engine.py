@@ -71,6 +71,9 @@ def run_tapgemm(r: TapGemmRec):
             qc = r.q_cols
             q = v[..., :qc].reshape(gB, gH, gW, qc // 32, 32).softmax(-1) * r.q_scale
             v = torch.cat([q.reshape(gB, gH, gW, qc), v[..., qc:]], -1)
+        if r.flags & L.EPI_KEXP:
+            qc = r.q_cols
+            v = torch.cat([v[..., :qc], v[..., qc:2 * qc].exp(), v[..., 2 * qc:]], -1)
         if r.flags & L.EPI_RESID:
             rs_ = r.resid_strides
             res = torch.as_strided(r.resid.reshape(-1), (gB, gH, gW, r.N), (rs_[2], rs_[1], rs_[0], 1), 0).float()
@@ -95,9 +98,13 @@ def run_kernel(r: KernelRec):
     elif k == "linattn_context":
         B, n, heads = a["B"], a["n"], a["heads"]
         qkv = a["qkv"].float().reshape(B, n, 3, heads, 32)
-        kk, vv = qkv[:, :, 1], qkv[:, :, 2]                                  # [B, n, heads, 32]
-        p = kk.softmax(dim=1)
-        a["ctx"].copy_(torch.einsum("bnhd,bnhe->bhde", p, vv))
+        pp, vv = qkv[:, :, 1], qkv[:, :, 2]                                  # [B, n, heads, 32]; pp = exp(k - bound)
+        a["ctx"].copy_(torch.einsum("bnhd,bnhe->bhde", pp, vv) / pp.sum(1).permute(0, 1, 2)[..., None])
+    elif k == "kexp_bound":
+        w = a["wpacked"].float().reshape(a["n_rows"], a["K"])
+        bias = a["bias"]
+        bias.zero_()
+        bias[a["lo"]:a["hi"]] = -1.01 * w[a["lo"]:a["hi"]].norm(dim=1) - 1e-3
     elif k == "linattn_fold":
         B, C, heads = a["B"], a["C"], a["heads"]
         w = a["w_out"].detach().reshape(C, heads, 32)                        # [c, h, e]
@@ -146,7 +153,10 @@ def run_kernel(r: KernelRec):
 def run_program(prog, weights):
     with torch.no_grad():
         for r in weights.program.recs:
-            run_pack(r)
+            if isinstance(r, PackRec):
+                run_pack(r)
+            else:
+                run_kernel(r)
         for off, b in prog._tc_bias_srcs:
             weights.tc_bias[off:off + b.numel()].copy_(b.detach())
         for r in prog.recs:
