@@ -7,5 +7,7 @@ The arithmetic runs in libccdm_b200.so (include/ccdm_b200.h); there is no CPU or
 from .unet import Unet  # noqa: F401
 from .diffusion import GaussianDiffusion, ModelPrediction  # noqa: F401
 from .label_embedding import LabelEmbed  # noqa: F401
+from .ema import EMA  # noqa: F401
+from .trainer import Trainer  # noqa: F401
 
-__all__ = ["Unet", "GaussianDiffusion", "ModelPrediction", "LabelEmbed"]
+__all__ = ["Unet", "GaussianDiffusion", "ModelPrediction", "LabelEmbed", "EMA", "Trainer"]

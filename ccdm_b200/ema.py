@@ -1,0 +1,65 @@
+"""Exponential moving average of a model, with the interface Trainer uses (CCDM_unified/ema_pytorch.py:18-181):
+``EMA(model, beta, update_after_step, update_every)``, ``.ema_model``, ``.update()``, ``state_dict()``.
+
+The copy/lerp over all tensors runs as multi-tensor ``torch._foreach`` ops (HBM-bound, every ``update_every``
+steps); fusing it with the optimizer step is a "next" row."""
+import copy
+
+import torch
+from torch import nn
+
+
+class EMA(nn.Module):
+    def __init__(self, model, ema_model=None, beta=0.9999, update_after_step=100, update_every=10, inv_gamma=1.0,
+                 power=2 / 3, min_value=0.0):
+        super().__init__()
+        self.beta = beta
+        self.online_model = model
+        self.ema_model = ema_model if ema_model is not None else copy.deepcopy(model)
+        self.ema_model.requires_grad_(False)
+        self.update_every, self.update_after_step = update_every, update_after_step
+        self.inv_gamma, self.power, self.min_value = inv_gamma, power, min_value
+        self.register_buffer("initted", torch.tensor([False]))
+        self.register_buffer("step", torch.tensor([0]))
+
+    def _pairs(self):
+        on = dict(self.online_model.named_parameters())
+        return [(p, on[n]) for n, p in self.ema_model.named_parameters() if p.dtype.is_floating_point]
+
+    def _buffer_pairs(self):
+        on = dict(self.online_model.named_buffers())
+        return [(b, on[n]) for n, b in self.ema_model.named_buffers()]
+
+    def copy_params_from_model_to_ema(self):
+        with torch.no_grad():
+            for e, o in self._pairs() + self._buffer_pairs():
+                e.copy_(o)
+
+    def get_current_decay(self):                     # ema_pytorch.py:124-131
+        epoch = max(int(self.step.item()) - self.update_after_step - 1, 0)
+        value = 1 - (1 + epoch / self.inv_gamma) ** -self.power
+        return 0.0 if epoch <= 0 else min(max(value, self.min_value), self.beta)
+
+    @torch.no_grad()
+    def update(self):                                # ema_pytorch.py:133-178
+        step = int(self.step.item())
+        self.step += 1
+        if (step % self.update_every) != 0:
+            return
+        if step <= self.update_after_step:
+            self.copy_params_from_model_to_ema()
+            return
+        if not bool(self.initted.item()):
+            self.copy_params_from_model_to_ema()
+            self.initted.fill_(True)
+        w = 1.0 - self.get_current_decay()
+        pairs = self._pairs()
+        torch._foreach_lerp_([e for e, _ in pairs], [o for _, o in pairs], w)
+        for e, o in self._buffer_pairs():
+            if e.dtype.is_floating_point:
+                e.lerp_(o.to(e.dtype), w)
+            else:
+                e.copy_(o)
+
+    def forward(self, *args, **kwargs):
+        return self.ema_model(*args, **kwargs)

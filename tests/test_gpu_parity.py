@@ -300,3 +300,25 @@ def test_backward_fails_loudly():
               vicinity_type="hv", kappa=0.1)
     with pytest.raises(NotImplementedError):
         loss.backward()
+
+
+def test_trainer_sample_given_labels_matches_direct_call():
+    """Hot caller (trainer.py:782-869): uint8 images for given labels through the EMA copy."""
+    import numpy as np
+    import ccdm_b200
+    spec = SPECS["rc_small"]
+    net, _ = make_net(spec, 4)
+    gd = ccdm_b200.GaussianDiffusion(net, image_size=16, timesteps=1000, sampling_timesteps=5, objective="pred_x0").cuda()
+    tr = ccdm_b200.Trainer("RC-49", gd, train_images=None, train_labels=None,
+                           vicinal_params={"kernel_sigma": 0.05, "kappa": 0.02, "nonzero_soft_weight_threshold": 1e-3},
+                           train_batch_size=16, results_folder="/tmp/ccdm_b200_results", ema_update_after_step=0)
+    fn_y2h = ccdm_b200.LabelEmbed(y2h_type="sinusoidal", h_dim=128, device=torch.device("cuda")).fn_y2h
+    labels = np.linspace(0, 1, 6).astype(np.float32)
+    torch.manual_seed(1)
+    imgs, lab = tr.sample_given_labels(labels, fn_y2h, batch_size=3, sampler="ddim", cond_scale=1.5)
+    assert imgs.shape == (6, 3, 16, 16) and imgs.dtype == np.uint8 and lab is labels
+    torch.manual_seed(1)
+    tr.ema.ema_model.eval()
+    y = torch.from_numpy(labels[:3]).cuda()
+    direct = tr.ema.ema_model.ddim_sample(labels_emb=fn_y2h(y), labels=y, shape=(3, 3, 16, 16), cond_scale=1.5)
+    assert np.array_equal(imgs[:3], (direct.clip(0, 1) * 255.0).type(torch.uint8).cpu().numpy())
