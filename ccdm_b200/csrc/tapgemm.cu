@@ -73,10 +73,15 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 
 __device__ __forceinline__ float fast_silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
+constexpr uint32_t kRuntimeFlags = 0x80000000u;            // template value: epilogue flags are read from the params
+
+// kFlags: the CCDM_EPI_* set compiled into the epilogue (dead branches vanish), or kRuntimeFlags.
+// kStoreTma: bf16 output through the shared-memory staging tile + TMA bulk store.
+template <uint32_t kFlags, bool kStoreTma>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmMaps maps,
                                                               const TapGemmDev p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];        // 1024-byte aligned: SWIZZLE_128B atoms
+  const uint32_t kflags = (kFlags == kRuntimeFlags) ? p.flags : kFlags;
   uint8_t* res_b = smem;                                   // resident weights (may be empty)
   uint8_t* ring = smem + p.res_bytes;                      // pipeline stages
   uint8_t* stg = ring + static_cast<size_t>(p.stages) * p.stage_bytes;   // output staging (TMA-store epilogue)
@@ -110,8 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   }
   for (int i = tid; i < p.n_tile; i += kThreads) {
     const bool ok = (n0 + i) < p.N;
-    aux->bias[i] = ((p.flags & CCDM_EPI_BIAS) && ok) ? p.bias[n0 + i] : 0.f;
-    aux->gain[i] = ((p.flags & CCDM_EPI_RMSNORM) && ok) ? p.gain[n0 + i] * p.gain_mul : 0.f;
+    aux->bias[i] = ((kflags & CCDM_EPI_BIAS) && ok) ? p.bias[n0 + i] : 0.f;
+    aux->gain[i] = ((kflags & CCDM_EPI_RMSNORM) && ok) ? p.gain[n0 + i] * p.gain_mul : 0.f;
   }
   for (int i = tid; i < p.ngroups; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
   tc_fence_before();
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const int et = ew * 32 + lane;                         // 0..255 among the epilogue threads
     const int m = q * 32 + lane;
     const int lw = m % p.tw, lh = (m / p.tw) % p.th, lb = m / (p.tw * p.th);
-    const uint32_t flags = p.flags;
+    const uint32_t flags = kflags;
     const int nchunk = p.n_tile / 32;
     const int per_half = (nchunk + 1) >> 1;
     const int c_lo = half * per_half, c_hi = min(nchunk, c_lo + per_half);
@@ -228,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const int npanels = (p.n_tile + 63) / 64;
     uint32_t r[32];
     int ss_b = -1;                                         // sample whose scale/shift currently sits in aux->gs/sh
-    if (p.store_tma && et == 0) {
+    if (kStoreTma && et == 0) {
       for (int i = 0; i < CCDM_MAX_Z; ++i) tma_prefetch_desc(&maps.o[i]);
     }
     // tile coordinates advance incrementally (the CTA's tiles are contiguous): no divisions in the loop
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             u.y = pack_bf16(v[g * 4 + 1].x, v[g * 4 + 1].y);
             u.z = pack_bf16(v[g * 4 + 2].x, v[g * 4 + 2].y);
             u.w = pack_bf16(v[g * 4 + 3].x, v[g * 4 + 3].y);
-            if (p.store_tma)                                               // swizzled like a TMA SWIZZLE_128B box
+            if (kStoreTma)                                               // swizzled like a TMA SWIZZLE_128B box
               *reinterpret_cast<uint4*>(srow + (((j0 + g) ^ (m & 7)) << 4)) = u;
             else if (valid && n0 + c * 32 + g * 8 < p.N)
               *reinterpret_cast<uint4*>(op + g * 8) = u;
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         if (lane == 0) mbar_arrive(&aux->tmem_empty[as]);
       }
       if ((flags & CCDM_EPI_SUMSQ_OUT) && half == 1) aux->part[lt & 1][m] = out_ss;   // combine the two column halves
-      if (p.store_tma) {
+      if (kStoreTma) {
         // staging complete -> one thread hands the tile to the TMA unit.  Before the barrier it makes sure the
         // PREVIOUS tile's bulk stores have finished reading their buffer, which the next tile will overwrite.
         fence_proxy_async_smem();
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   }
 
   // ---------------------------------------------------------------- teardown
-  if (p.store_tma && tid == 64) tma_store_wait_all();      // et == 0: the thread that issued the bulk stores
+  if (kStoreTma && tid == 64) tma_store_wait_all();      // et == 0: the thread that issued the bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -524,6 +529,45 @@ static uint32_t pow2_cols(int n) {
   uint32_t c = 32;
   while (c < static_cast<uint32_t>(n)) c <<= 1;
   return c;
+}
+
+template <uint32_t kFlags, bool kStoreTma>
+static int launch_one(dim3 grid, size_t smem_bytes, cudaStream_t stream, const TapGemmMaps& maps, const TapGemmDev& p) {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(tapgemm_kernel<kFlags, kStoreTma>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024);
+  });
+  if (err != cudaSuccess) return cuda_fail(err, "tapgemm: cudaFuncSetAttribute");
+  tapgemm_kernel<kFlags, kStoreTma><<<grid, kThreads, smem_bytes, stream>>>(maps, p);
+  return after_launch("tapgemm_kernel");
+}
+
+// The epilogue flag sets the UNet actually uses are compiled as separate instantiations; anything else takes the
+// runtime-flag instantiation (same code, branches kept).
+static int launch_variant(uint32_t flags, bool tma, dim3 grid, size_t smem_bytes, cudaStream_t stream,
+                          const TapGemmMaps& maps, const TapGemmDev& p) {
+#define CCDM_VARIANT(F)                                                                        \
+  case F:                                                                                      \
+    return tma ? launch_one<F, true>(grid, smem_bytes, stream, maps, p)                        \
+               : launch_one<F, false>(grid, smem_bytes, stream, maps, p);
+  switch (flags) {
+    CCDM_VARIANT(0x1Du)   // bias | rmsnorm | scale-shift | silu            (Block 1 of a ResnetBlock)
+    CCDM_VARIANT(0x35u)   // bias | rmsnorm | silu | resid                  (Block 2 + residual)
+    CCDM_VARIANT(0xB5u)   //   ... + sum of squares for the next PreNorm
+    CCDM_VARIANT(0x01u)   // bias                                           (res_conv, down / up sampling convs)
+    CCDM_VARIANT(0x243u)  // bias | rowscale | q-softmax | k-exp            (linear-attention qkv)
+    CCDM_VARIANT(0x02u)   // rowscale                                       (bottleneck-attention qkv)
+    CCDM_VARIANT(0x25u)   // bias | rmsnorm | resid                         (linear-attention to_out)
+    CCDM_VARIANT(0x21u)   // bias | resid                                   (bottleneck-attention to_out)
+    default:
+      break;
+  }
+#undef CCDM_VARIANT
+  if (flags == 0x101u) return launch_one<0x101u, false>(grid, smem_bytes, stream, maps, p);   // tc_mlp row-GEMM, fp32 out
+  return tma ? launch_one<kRuntimeFlags, true>(grid, smem_bytes, stream, maps, p)
+             : launch_one<kRuntimeFlags, false>(grid, smem_bytes, stream, maps, p);
 }
 
 }  // namespace ccdm
@@ -663,16 +707,8 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
     }
   }
 
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "tapgemm: cudaFuncSetAttribute");
-
   dim3 grid((unsigned)gx, (unsigned)combos, 1);
-  tapgemm_kernel<<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(maps, p);
-  return after_launch("tapgemm_kernel");
+  return launch_variant(a->flags, p.store_tma != 0, grid, smem_bytes, static_cast<cudaStream_t>(stream), maps, p);
 }
 
 // ---------------------------------------------------------------------------- weight packing

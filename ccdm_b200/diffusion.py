@@ -210,7 +210,8 @@ class GaussianDiffusion(nn.Module):
         tab = getattr(self, "_coef_t", None)
         if tab is None or tab.device != self.device:
             T = self.num_timesteps
-            tab = torch.zeros(T, L.STEP_NCOEF, dtype=torch.float32, device=self.device)
+            with torch.inference_mode(False):
+                tab = torch.zeros(T, L.STEP_NCOEF, dtype=torch.float32, device=self.device)
             tab[:, 0] = self.sqrt_recip_alphas_cumprod
             tab[:, 1] = self.sqrt_recipm1_alphas_cumprod
             tab[:, 2] = self.sqrt_alphas_cumprod
@@ -304,7 +305,9 @@ class GaussianDiffusion(nn.Module):
                bool(self.use_cfg_plus_plus), trace is not None)
         st = self._samplers.get(key)
         if st is None:
-            st = _SamplerState(self, prog, kind, B, C * H * W, cond_scale, rescaled_phi, clip_denoised, trace is not None)
+            with torch.inference_mode(False):      # persistent buffers must be normal tensors (reused outside)
+                st = _SamplerState(self, prog, kind, B, C * H * W, cond_scale, rescaled_phi, clip_denoised,
+                                   trace is not None)
             self._samplers[key] = st
 
         if kind == "ddim":

@@ -314,7 +314,8 @@ class UnetEngine:
         key = (B, x_batch, H, W, bool(training))
         prog = self.programs.get(key)
         if prog is None:
-            prog = UnetProgram(self.net, self.weights, B, x_batch, H, W, training)
+            with torch.inference_mode(False):      # persistent buffers must be normal tensors (reused outside)
+                prog = UnetProgram(self.net, self.weights, B, x_batch, H, W, training)
             self.programs[key] = prog
         return prog
 
@@ -350,7 +351,9 @@ class UnetEngine:
         B, _, H, W = x.shape
         prog = self.program(2 * B, B, H, W, False)
         if prog.pair_keep is None:
-            prog.pair_keep = torch.cat([torch.ones(B, dtype=torch.uint8), torch.zeros(B, dtype=torch.uint8)]).to(self.device)
+            with torch.inference_mode(False):
+                prog.pair_keep = torch.cat([torch.ones(B, dtype=torch.uint8),
+                                            torch.zeros(B, dtype=torch.uint8)]).to(self.device)
         t2 = torch.cat([t.reshape(-1), t.reshape(-1)])
         emb2 = torch.cat([labels_emb, labels_emb])
         out = self._run(prog, x, t2, emb2, prog.pair_keep)
