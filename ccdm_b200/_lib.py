@@ -70,8 +70,10 @@ SIGNATURES = {
     "ccdm_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), vp]),
     "ccdm_pack_weights": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, vp, vp]),
     "ccdm_stem_conv7": (C.c_int, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp]),
+    "ccdm_stem_im2row": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "ccdm_stem_pack": (C.c_int, [vp, vp, i32, i32, i32, vp]),
     "ccdm_head_conv1": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
-    "ccdm_linattn_context": (C.c_int, [vp, vp, i32, i32, i32, vp]),
+    "ccdm_linattn_context": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, i32, i32, vp]),
     "ccdm_kexp_bound": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
     "ccdm_linattn_fold": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "ccdm_attention_small": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp]),

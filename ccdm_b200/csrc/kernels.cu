@@ -83,6 +83,54 @@ __global__ void __launch_bounds__(256) stem_conv7_kernel(const float* __restrict
   }
 }
 
+// ============================================================================ stem on tensor cores: im2row + weight packing
+// The 7x7 stem becomes a 4-tap tap-GEMM over a bf16 NHWC "im2row" tensor whose 64 channels hold a 2-row x 7-column
+// window of the input:  rowimg[b,j,w, dr*7*Cin + s*Cin + c] = x[b,c,j-1+dr,w+s-3]  for j = 0..H (H+1 rows; dr in {0,1};
+// zero outside the image and for the unused channels).  Vertical tap pair g reads rowimg at row offset 2g-2; the
+// extra leading row keeps the pair (x[-1], x[0]) that straddles the top edge.
+__global__ void __launch_bounds__(256) stem_im2row_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                          int Cin, int H, int W, long long npix_total) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= npix_total) return;
+  const int w = (int)(p % W), h = (int)((p / W) % (H + 1)) - 1;       // h = j - 1
+  const long long b = p / ((long long)W * (H + 1));
+  const int nval = 14 * Cin;
+  uint4* orow = reinterpret_cast<uint4*>(out + p * 64);
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      float val = 0.f;
+      if (ch < nval) {
+        const int dr = ch / (7 * Cin), rem = ch % (7 * Cin), sx = rem / Cin, c = rem % Cin;
+        const int yy = h + dr, xx = w + sx - 3;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(x + ((b * Cin + c) * H + yy) * W + xx);
+      }
+      v[j] = val;
+    }
+    uint4 u;
+    u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+    orow[g] = u;
+  }
+}
+
+// packed[n][g*64 + dr*7*Cin + s*Cin + c] = w[n][c][2g+dr][s]  (0 for row 7 and for the unused channels)
+__global__ void stem_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+                                 int n_rows) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rows * 256) return;
+  const int n = idx / 256, k = idx % 256, g = k / 64, ch = k % 64;
+  float val = 0.f;
+  if (n < Cout && ch < 14 * Cin) {
+    const int dr = ch / (7 * Cin), rem = ch % (7 * Cin), sx = rem / Cin, c = rem % Cin;
+    const int r = 2 * g + dr;
+    if (r < 7) val = w[((n * Cin + c) * 7 + r) * 7 + sx];
+  }
+  out[idx] = __float2bfloat16(val);
+}
+
 // ============================================================================ head: 1x1 conv, NHWC bf16 -> NCHW fp32
 // unet.py:348,455.  One pixel per thread; reads the pixel row once, writes Cout planes coalesced.
 __global__ void __launch_bounds__(256) head_conv1_kernel(const __nv_bfloat16* __restrict__ x,
@@ -332,6 +380,23 @@ extern "C" int ccdm_stem_conv7(const float* x, int32_t x_batch, const float* w, 
   stem_conv7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (__nv_bfloat16*)out, Cin, H, W, Cout, cpad,
                                                                out_pix_stride, x_batch);
   return after_launch("stem_conv7_kernel");
+}
+
+extern "C" int ccdm_stem_im2row(const float* x, void* rowimg, int32_t B, int32_t Cin, int32_t H, int32_t W,
+                                void* stream) {
+  CCDM_REQUIRE(x && rowimg && B > 0 && Cin >= 1 && Cin <= 4 && H > 0 && W > 0, CCDM_ERR_BAD_ARG,
+               "stem_im2row: B=%d Cin=%d H=%d W=%d", B, Cin, H, W);
+  const long long npix = (long long)B * (H + 1) * W;
+  stem_im2row_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)rowimg, Cin, H,
+                                                                                       W, npix);
+  return after_launch("stem_im2row_kernel");
+}
+
+extern "C" int ccdm_stem_pack(const float* w, void* wpacked, int32_t Cout, int32_t Cin, int32_t n_rows, void* stream) {
+  CCDM_REQUIRE(w && wpacked && Cout > 0 && Cin >= 1 && Cin <= 4 && n_rows >= Cout, CCDM_ERR_BAD_ARG, "stem_pack: bad args");
+  const int total = n_rows * 256;
+  stem_pack_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wpacked, Cout, Cin, n_rows);
+  return after_launch("stem_pack_kernel");
 }
 
 extern "C" int ccdm_head_conv1(const void* x, const float* w, const float* bias, float* out, int32_t B, int32_t H,

@@ -48,7 +48,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(uint32_t M, uint32_t N
 }
 
 __global__ void __launch_bounds__(kCtxThreads, 1) linattn_context_mma_kernel(const __grid_constant__ CUtensorMap qkv_map,
-                                                                             float* __restrict__ ctx, int B, int n) {
+                                                                             float* __restrict__ ctx, int B, int n,
+                                                                             const float* __restrict__ w_out,
+                                                                             __nv_bfloat16* __restrict__ wfold, int C,
+                                                                             int n_rows) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
@@ -145,11 +148,34 @@ __global__ void __launch_bounds__(kCtxThreads, 1) linattn_context_mma_kernel(con
       __syncwarp();
       if (lane == 0) mbar_arrive(&aux->acc_empty);
       const float inv = 1.f / __uint_as_float(sum[0]);
-      float4* o = reinterpret_cast<float4*>(ctx + ((static_cast<long long>(b) * 4 + h) * 32 + d) * 32);
+      float cr[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = make_float4(__uint_as_float(r[4 * j]) * inv, __uint_as_float(r[4 * j + 1]) * inv,
-                           __uint_as_float(r[4 * j + 2]) * inv, __uint_as_float(r[4 * j + 3]) * inv);
+      for (int j = 0; j < 32; ++j) cr[j] = __uint_as_float(r[j]) * inv;
+      if (ctx) {
+        float4* o = reinterpret_cast<float4*>(ctx + ((static_cast<long long>(b) * 4 + h) * 32 + d) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = make_float4(cr[4 * j], cr[4 * j + 1], cr[4 * j + 2], cr[4 * j + 3]);
+      }
+      if (wfold) {
+        // fold the context into the output projection (unet.py:214-216 + to_out[0]):
+        //   wfold[b][c][h*32+d] = sum_e w_out[c][h*32+e] * ctx[b][h][d][e];  all lanes of a warp read the same w_out row
+        __nv_bfloat16* wf = wfold + static_cast<long long>(b) * n_rows * 128 + h * 32 + d;
+        for (int c = 0; c < n_rows; ++c) {
+          float acc = 0.f;
+          if (c < C) {
+            const float4* wr = reinterpret_cast<const float4*>(w_out + static_cast<long long>(c) * 128 + h * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 wv = __ldg(wr + j);
+              acc = fmaf(wv.x, cr[4 * j], acc);
+              acc = fmaf(wv.y, cr[4 * j + 1], acc);
+              acc = fmaf(wv.z, cr[4 * j + 2], acc);
+              acc = fmaf(wv.w, cr[4 * j + 3], acc);
+            }
+          }
+          wf[static_cast<long long>(c) * 128] = __float2bfloat16(acc);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -228,12 +254,20 @@ __global__ void kexp_bound_kernel(const __nv_bfloat16* __restrict__ wp, int n_ro
 
 using namespace ccdm;
 
-extern "C" int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads, void* stream) {
-  CCDM_REQUIRE(qkv && ctx && B > 0 && n > 0 && heads > 0, CCDM_ERR_BAD_ARG, "linattn_context: bad args");
+extern "C" int ccdm_linattn_fold(const float* w_out, const float* ctx, void* wfold, int32_t B, int32_t C,
+                                 int32_t n_rows, int32_t heads, void* stream);
+
+extern "C" int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads,
+                                    const float* w_out, void* wfold, int32_t C, int32_t n_rows, void* stream) {
+  CCDM_REQUIRE(qkv && (ctx || wfold) && B > 0 && n > 0 && heads > 0, CCDM_ERR_BAD_ARG, "linattn_context: bad args");
+  CCDM_REQUIRE(!wfold || (w_out && C > 0 && n_rows >= C), CCDM_ERR_BAD_ARG, "linattn_context: fold needs w_out, C, n_rows");
   cudaStream_t s = (cudaStream_t)stream;
   if (heads != 4) {
+    CCDM_REQUIRE(ctx, CCDM_ERR_BAD_ARG, "linattn_context: heads != 4 needs the ctx buffer");
     linattn_context_simt_kernel<<<B * heads, 128, 0, s>>>((const __nv_bfloat16*)qkv, ctx, n, heads);
-    return after_launch("linattn_context_simt_kernel");
+    int rc = after_launch("linattn_context_simt_kernel");
+    if (rc != CCDM_OK || !wfold) return rc;
+    return ccdm_linattn_fold(w_out, ctx, wfold, B, C, n_rows, heads, stream);
   }
   CUtensorMap map;
   cuuint64_t dims[3] = {384, (cuuint64_t)n, (cuuint64_t)B};
@@ -251,7 +285,7 @@ extern "C" int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int3
   }
   int grid = num_sms();
   if (grid > B) grid = B;
-  linattn_context_mma_kernel<<<grid, kCtxThreads, smem, s>>>(map, ctx, B, n);
+  linattn_context_mma_kernel<<<grid, kCtxThreads, smem, s>>>(map, ctx, B, n, w_out, (__nv_bfloat16*)wfold, C, n_rows);
   return after_launch("linattn_context_mma_kernel");
 }
 

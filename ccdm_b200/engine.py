@@ -208,13 +208,18 @@ def _make_call(lib, r, keep):
     if k == "stem_conv7":
         return lib.ccdm_stem_conv7, (p(a["x"]), a["x_batch"], p(a["w"]), p(a["bias"]), p(a["out"]), a["B"], a["Cin"],
                                      a["H"], a["W"], a["Cout"], a["Cout"]), k
+    if k == "stem_im2row":
+        return lib.ccdm_stem_im2row, (p(a["x"]), p(a["out"]), a["B"], a["Cin"], a["H"], a["W"]), k
+    if k == "stem_pack":
+        return lib.ccdm_stem_pack, (p(a["w"]), p(a["wpacked"]), a["Cout"], a["Cin"], a["n_rows"]), k
     if k == "head_conv1":
         return lib.ccdm_head_conv1, (p(a["x"]), p(a["w"]), p(a["bias"]), p(a["out"]), a["B"], a["H"], a["W"], a["Cin"],
                                      a["Cout"]), k
     if k == "kexp_bound":
         return lib.ccdm_kexp_bound, (p(a["wpacked"]), a["n_rows"], a["K"], a["lo"], a["hi"], p(a["bias"])), k
     if k == "linattn_context":
-        return lib.ccdm_linattn_context, (p(a["qkv"]), p(a["ctx"]), a["B"], a["n"], a["heads"]), k
+        return lib.ccdm_linattn_context, (p(a["qkv"]), p(a["ctx"]), a["B"], a["n"], a["heads"], p(a["w_out"]),
+                                          p(a["wfold"]), a["C"], a["n_rows"]), k
     if k == "linattn_fold":
         return lib.ccdm_linattn_fold, (p(a["w_out"]), p(a["ctx"]), p(a["wfold"]), a["B"], a["C"], a["n_rows"],
                                        a["heads"]), k
@@ -279,6 +284,18 @@ class WeightStore:
             self.packs[key] = rec
             self.program.recs.append(rec)
         return self.packs[key].a["bias"]
+
+    def stem_pack(self, weight: torch.Tensor, n_rows: int) -> torch.Tensor:
+        """bf16 [n_rows][256] packing of the 7x7 stem weight for the im2row formulation (ccdm_stem_pack)."""
+        key = "stem_pack"
+        if key not in self.packs:
+            packed = torch.zeros(n_rows, 256, dtype=torch.bfloat16, device=self.device)
+            rec = KernelRec("stem_pack", dict(w=weight, wpacked=packed, Cout=weight.shape[0], Cin=weight.shape[1],
+                                              n_rows=n_rows))
+            self.packs[key] = rec
+            self.program.recs.append(rec)
+            self._params.append(weight)
+        return self.packs[key].a["wpacked"]
 
     def stamp(self):
         return tuple((p.data_ptr(), p._version) for p in self._params)
@@ -460,12 +477,12 @@ class UnetProgram(Program):
         rec.bias = self.weights.kexp_bias(rec.pack, hid, 2 * hid)
         rec.flags |= L.EPI_BIAS
         ctx = self.buf(name + ".ctx", (self.B, heads, 32, 32), torch.float32)
-        self.kernel("linattn_context", qkv=qkv, ctx=ctx, B=self.B, n=n, heads=heads)
         conv_out, norm_out = att.to_out[0], att.to_out[1]
         n_rows, n_tile = n_tiling(C, True)
         wfold = self.buf(name + ".wfold", (self.B * n_rows, hid), torch.bfloat16)
-        self.kernel("linattn_fold", w_out=conv_out.weight, ctx=ctx, wfold=wfold, B=self.B, C=C, n_rows=n_rows,
-                    heads=heads)
+        # context + fold of the context into to_out's weights in one kernel
+        self.kernel("linattn_context", qkv=qkv, ctx=ctx, B=self.B, n=n, heads=heads, w_out=conv_out.weight,
+                    wfold=wfold, C=C, n_rows=n_rows)
         out = self.act(name + ".out", h, w, C)
         plan = plan_conv("1x1", [hid], C)
         sched = torch.tensor(plan.sched, dtype=torch.int32, device=self.device)
@@ -546,10 +563,21 @@ class UnetProgram(Program):
                                     n_rows, 128, L.EPI_BIAS | L.EPI_OUT_F32, ss_all, (n_rows, 0, 0),
                                     bias=self.weights.tc_bias))
 
-        # ---- stem (unet.py:418-419)
+        # ---- stem (unet.py:418-419): 7x7 conv as a 4-tap tap-GEMM over a 64-channel im2row tensor.  The stem sees no
+        # conditioning, so the cond / null halves of a 2B batch share it: computed per x_batch slab.
         stem = self.act("stem", H, W, net.init_dim)
-        self.kernel("stem_conv7", x=self.x_in, x_batch=self.x_batch, w=net.init_conv.weight, bias=net.init_conv.bias,
-                    out=stem, B=B, Cin=net.in_channels, H=H, W=W, Cout=net.init_dim)
+        xb = self.x_batch
+        rowimg = self.buf("stem_rows", (xb, H + 1, W, 64), torch.bfloat16)
+        self.kernel("stem_im2row", x=self.x_in, out=rowimg, B=xb, Cin=net.in_channels, H=H, W=W)
+        splan = plan_conv("stem7", [64], net.init_dim)
+        s_rows, s_tile = n_tiling(net.init_dim, False)
+        spack = self.weights.stem_pack(net.init_conv.weight, s_rows)
+        s_sched = torch.tensor(splan.sched, dtype=torch.int32, device=dev)
+        co = net.init_dim
+        for rep in range(B // xb):
+            self.recs.append(TapGemmRec(f"init_conv.{rep}", splan, [nhwc_view(rowimg)], W, H, xb, tile_box(W, H), None,
+                                        spack, s_sched, s_rows, co, s_tile, L.EPI_BIAS, stem[rep * xb:(rep + 1) * xb],
+                                        (co, W * co, H * W * co), bias=net.init_conv.bias))
 
         # ---- down path (unet.py:425-433)
         x, h, w = stem, H, W

@@ -114,6 +114,11 @@ def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = Fals
                     sched.append((src_view, dw, dh, c0))
                     psched.append((offs[s] + c0, nv, mask, 0))
 
+    if kind == "stem7":
+        # 7x7 stem over the 64-channel im2row tensor (ccdm_stem_im2row, H+1 rows): vertical tap pair g sits at row
+        # offset 2g-2.  Weights come from ccdm_stem_pack, so there is no packing schedule.
+        sched = [(0, 0, 2 * g - 2, 0) for g in range(4)]
+        return ConvPlan(kind, cins, cout, 49, 1, 4, 1, sched, [])
     if kind == "1x1":
         for s in range(len(cins)):
             emit(s, s, 0, [(0, 1)])

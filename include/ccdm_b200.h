@@ -113,6 +113,11 @@ int ccdm_pack_weights(const float* w, int32_t cout, int32_t cin_total, int32_t n
  * conditional and unconditional halves as one 2B batch over the same x_t). */
 int ccdm_stem_conv7(const float* x_nchw, int32_t x_batch, const float* w, const float* bias, void* out_nhwc, int32_t B,
                     int32_t Cin, int32_t H, int32_t W, int32_t Cout, int64_t out_pix_stride, void* stream);
+/* Tensor-core stem: the 7x7 conv as a 4-tap ccdm_tapgemm (schedule {src 0, dw 0, dh0 2g-2, c0 0}, g = 0..3) over
+ *   rowimg[b,j,w, dr*7*Cin + s*Cin + c] = x[b,c,j-1+dr,w+s-3], j = 0..H   (bf16 [B][H+1][W][64], zero outside the image)
+ * with weights packed[n][g*64 + dr*7*Cin + s*Cin + c] = w[n][c][2g+dr][s]. */
+int ccdm_stem_im2row(const float* x_nchw, void* rowimg, int32_t B, int32_t Cin, int32_t H, int32_t W, void* stream);
+int ccdm_stem_pack(const float* w, void* wpacked, int32_t Cout, int32_t Cin, int32_t n_rows, void* stream);
 int ccdm_head_conv1(const void* x_nhwc, const float* w, const float* bias, float* out_nchw, int32_t B, int32_t H,
                     int32_t W, int32_t Cin, int32_t Cout, void* stream);
 
@@ -123,7 +128,9 @@ int ccdm_head_conv1(const void* x_nhwc, const float* w, const float* bias, float
  *     (fp32 [B][heads][32][32]) runs on tcgen05 for heads == 4 (both operands token-major = MN-major UMMA)
  *   softmax attention at the bottleneck, unet.py:228-240 (n <= 64 tokens, dim_head <= 64)
  * ------------------------------------------------------------------------------------------------------------ */
-int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads, void* stream);
+/* When wfold != NULL the fold below is fused into the same kernel (ctx may then be NULL). */
+int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads, const float* w_out,
+                         void* wfold, int32_t C, int32_t n_rows, void* stream);
 /* bias[n] = -1.01*||wpacked[n,:]||_2 - 1e-3 for n in [row_lo,row_hi), 0 elsewhere.  The PreNorm'd input rows have unit
  * length, so |k[n,d]| <= ||W'_d||: using this bound as the softmax shift needs no max pass over the tokens. */
 int ccdm_kexp_bound(const void* wpacked, int32_t n_rows, int32_t K, int32_t row_lo, int32_t row_hi, float* bias,

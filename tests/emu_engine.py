@@ -79,7 +79,8 @@ def run_tapgemm(r: TapGemmRec):
             res = torch.as_strided(r.resid.reshape(-1), (gB, gH, gW, r.N), (rs_[2], rs_[1], rs_[0], 1), 0).float()
             v = v + res
         os_ = r.out_strides
-        dst = torch.as_strided(out_flat, (gB, gH, gW, r.N), (os_[2], os_[1], os_[0], 1), r.ooff[z])
+        dst = torch.as_strided(out_flat, (gB, gH, gW, r.N), (os_[2], os_[1], os_[0], 1),
+                               out_flat.storage_offset() + r.ooff[z])
         dst.copy_(v.to(r.out.dtype))
         if r.flags & L.EPI_SUMSQ_OUT:
             r.out_rowss.copy_(dst.float().pow(2).sum(-1).reshape(-1))
@@ -92,6 +93,26 @@ def run_kernel(r: KernelRec):
         idx = torch.arange(a["B"]) % a["x_batch"]
         y = F.conv2d(x[idx], a["w"].detach(), a["bias"].detach(), padding=3)
         a["out"].copy_(y.permute(0, 2, 3, 1).to(torch.bfloat16))
+    elif k == "stem_im2row":
+        x, Cin, H, W = a["x"], a["Cin"], a["H"], a["W"]
+        out = torch.zeros(a["B"], H + 1, W, 64)
+        xp = F.pad(x[: a["B"]], (3, 3, 1, 1))                                # cols -3..W+2, rows -1..H
+        for dr in range(2):
+            for sx in range(7):
+                for c in range(Cin):
+                    out[..., dr * 7 * Cin + sx * Cin + c] = xp[:, c, dr:dr + H + 1, sx:sx + W]
+        a["out"].copy_(out.to(torch.bfloat16))
+    elif k == "stem_pack":
+        w, Cin, Cout = a["w"].detach(), a["Cin"], a["Cout"]
+        packed = torch.zeros(a["n_rows"], 4, 64)
+        for g in range(4):
+            for dr in range(2):
+                r = 2 * g + dr
+                if r < 7:
+                    for sx in range(7):
+                        for c in range(Cin):
+                            packed[:Cout, g, dr * 7 * Cin + sx * Cin + c] = w[:, c, r, sx]
+        a["wpacked"].copy_(packed.reshape(a["n_rows"], 256).to(torch.bfloat16))
     elif k == "head_conv1":
         x = a["x"].float().permute(0, 3, 1, 2)
         a["out"].copy_(F.conv2d(x, a["w"].detach(), a["bias"].detach()))
@@ -100,6 +121,9 @@ def run_kernel(r: KernelRec):
         qkv = a["qkv"].float().reshape(B, n, 3, heads, 32)
         pp, vv = qkv[:, :, 1], qkv[:, :, 2]                                  # [B, n, heads, 32]; pp = exp(k - bound)
         a["ctx"].copy_(torch.einsum("bnhd,bnhe->bhde", pp, vv) / pp.sum(1).permute(0, 1, 2)[..., None])
+        if a.get("wfold") is not None:
+            run_kernel(KernelRec("linattn_fold", dict(w_out=a["w_out"], ctx=a["ctx"], wfold=a["wfold"], B=B, C=a["C"],
+                                                     n_rows=a["n_rows"], heads=heads)))
     elif k == "kexp_bound":
         w = a["wpacked"].float().reshape(a["n_rows"], a["K"])
         bias = a["bias"]
