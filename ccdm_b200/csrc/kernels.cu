@@ -197,6 +197,77 @@ __global__ void linattn_fold_kernel(const float* __restrict__ w_out, const float
   }
 }
 
+// ============================================================================ standalone channel RMSNorm (+ tail)
+// unet.py:88-89,145-151 for layers whose channel count does not fit one tap-GEMM tile (Cout > 512: the 576-wide
+// bottleneck of the dim-72 UTKFace-64 model) or whose tiny pixel count wants the GEMM split over output channels
+// (4x4 levels): z = conv + bias (bf16) in, out = [silu]( z/|z| * g*sqrt(C) * (1+scale) + shift ) [+ resid].
+// One warp per pixel row, 16-byte loads; HBM-bound (reads z [+ resid], writes out).
+__global__ void __launch_bounds__(256) rmsnorm_act_kernel(const __nv_bfloat16* __restrict__ z,
+                                                          __nv_bfloat16* __restrict__ out, long long rows, int C,
+                                                          int rows_per_sample, const float* __restrict__ gain,
+                                                          float gain_mul, const float* __restrict__ ss, int ss_ld,
+                                                          int ss_off, const __nv_bfloat16* __restrict__ resid,
+                                                          float* __restrict__ out_rowss, uint32_t flags) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = C >> 3;                                   // 8 channels per 16-byte vector
+  const uint4* zr = reinterpret_cast<const uint4*>(z + row * C);
+  constexpr int kMaxVec = 3;                                 // C <= 768
+  float v[kMaxVec][8];
+  float ssq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 u = __ldg(zr + vi);
+      v[i][0] = bf16_lo(u.x); v[i][1] = bf16_hi(u.x); v[i][2] = bf16_lo(u.y); v[i][3] = bf16_hi(u.y);
+      v[i][4] = bf16_lo(u.z); v[i][5] = bf16_hi(u.z); v[i][6] = bf16_lo(u.w); v[i][7] = bf16_hi(u.w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ssq = fmaf(v[i][j], v[i][j], ssq);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, off);
+  const float inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
+  const long long b = row / rows_per_sample;
+  const float* ssrow = (flags & CCDM_EPI_SS) ? ss + b * ss_ld + ss_off : nullptr;
+  float out_ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = vi * 8 + j;
+        float t = v[i][j] * inv * (gain[c] * gain_mul);
+        if (ssrow) t = fmaf(t, 1.f + ssrow[c], ssrow[C + c]);
+        if (flags & CCDM_EPI_SILU) t = t / (1.f + __expf(-t));
+        o[j] = t;
+      }
+      if (flags & CCDM_EPI_RESID) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(resid + row * C) + vi);
+        o[0] += bf16_lo(u.x); o[1] += bf16_hi(u.x); o[2] += bf16_lo(u.y); o[3] += bf16_hi(u.y);
+        o[4] += bf16_lo(u.z); o[5] += bf16_hi(u.z); o[6] += bf16_lo(u.w); o[7] += bf16_hi(u.w);
+      }
+      uint4 w;
+      w.x = pack_bf16(o[0], o[1]); w.y = pack_bf16(o[2], o[3]); w.z = pack_bf16(o[4], o[5]); w.w = pack_bf16(o[6], o[7]);
+      reinterpret_cast<uint4*>(out + row * C)[vi] = w;
+      if (flags & CCDM_EPI_SUMSQ_OUT) {
+        const float a0 = bf16_lo(w.x), a1 = bf16_hi(w.x), a2 = bf16_lo(w.y), a3 = bf16_hi(w.y);
+        const float a4 = bf16_lo(w.z), a5 = bf16_hi(w.z), a6 = bf16_lo(w.w), a7 = bf16_hi(w.w);
+        out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+      }
+    }
+  }
+  if (flags & CCDM_EPI_SUMSQ_OUT) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) out_ss += __shfl_xor_sync(0xffffffffu, out_ss, off);
+    if (lane == 0) out_rowss[row] = out_ss;
+  }
+}
+
 // ============================================================================ bottleneck softmax attention
 // unet.py:228-240.  grid = (sample*head, query blocks of 64); one thread per query token, keys / values staged
 // through shared memory 64 tokens at a time with a running (online) softmax.  The shipped configs have 9 or 16
@@ -420,6 +491,20 @@ extern "C" int ccdm_linattn_fold(const float* w_out, const float* ctx, void* wfo
   linattn_fold_kernel<<<grid, hid, (size_t)32 * hid * sizeof(float), (cudaStream_t)stream>>>(
       w_out, ctx, (__nv_bfloat16*)wfold, C, n_rows, heads);
   return after_launch("linattn_fold_kernel");
+}
+
+extern "C" int ccdm_rmsnorm_act(const void* z, void* out, int64_t rows, int32_t C, int32_t rows_per_sample,
+                                const float* gain, float gain_mul, const float* scale_shift, int32_t ss_ld,
+                                int32_t ss_off, const void* resid, float* out_rowss, uint32_t flags, void* stream) {
+  CCDM_REQUIRE(z && out && gain && rows > 0 && rows_per_sample > 0, CCDM_ERR_BAD_ARG, "rmsnorm_act: bad args");
+  CCDM_REQUIRE(C % 8 == 0 && C <= 768, CCDM_ERR_UNSUPPORTED_SHAPE, "rmsnorm_act: C=%d (multiple of 8, <= 768)", C);
+  CCDM_REQUIRE(!(flags & CCDM_EPI_SS) || scale_shift, CCDM_ERR_BAD_ARG, "rmsnorm_act: scale/shift pointer");
+  CCDM_REQUIRE(!(flags & CCDM_EPI_RESID) || resid, CCDM_ERR_BAD_ARG, "rmsnorm_act: resid pointer");
+  CCDM_REQUIRE(!(flags & CCDM_EPI_SUMSQ_OUT) || out_rowss, CCDM_ERR_BAD_ARG, "rmsnorm_act: out_rowss pointer");
+  rmsnorm_act_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)z, (__nv_bfloat16*)out, rows, C, rows_per_sample, gain, gain_mul, scale_shift, ss_ld, ss_off,
+      (const __nv_bfloat16*)resid, out_rowss, flags);
+  return after_launch("rmsnorm_act_kernel");
 }
 
 extern "C" int ccdm_attention_small(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head,

@@ -212,6 +212,10 @@ def _make_call(lib, r, keep):
         return lib.ccdm_stem_im2row, (p(a["x"]), p(a["out"]), a["B"], a["Cin"], a["H"], a["W"]), k
     if k == "stem_pack":
         return lib.ccdm_stem_pack, (p(a["w"]), p(a["wpacked"]), a["Cout"], a["Cin"], a["n_rows"]), k
+    if k == "rmsnorm_act":
+        return lib.ccdm_rmsnorm_act, (p(a["z"]), p(a["out"]), a["rows"], a["C"], a["rows_per_sample"], p(a["gain"]),
+                                      a["gain_mul"], p(a.get("ss")), a.get("ss_ld", 0), a.get("ss_off", 0),
+                                      p(a.get("resid")), p(a.get("out_rowss")), a["flags"]), k
     if k == "head_conv1":
         return lib.ccdm_head_conv1, (p(a["x"]), p(a["w"]), p(a["bias"]), p(a["out"]), a["B"], a["H"], a["W"], a["Cin"],
                                      a["Cout"]), k
@@ -416,6 +420,14 @@ class UnetProgram(Program):
         reuse = kind != "1x1" and can_reuse_rows(tile)
         plan = plan_conv(kind, cins, cout, reuse_rows=reuse)
         full_row = bool(flags & (L.EPI_RMSNORM | L.EPI_SUMSQ_OUT))
+        # A fused channel norm needs the whole row in one CTA (<= 512 TMEM columns).  Wider layers (dim-72 models:
+        # 576) and layers with too few pixel tiles to fill the GPU (4x4 / 8x8 levels) run the GEMM split over output
+        # channels with a plain bias epilogue and finish with the standalone norm kernel.
+        m_tiles = ((gw + tile[0] - 1) // tile[0]) * ((gh + tile[1] - 1) // tile[1]) * ((self.B + tile[2] - 1) // tile[2])
+        split = full_row and (cout > 512 or (cout >= 256 and m_tiles < 100))
+        if split:
+            return self._conv_split(name, kind, plan, tile, srcs, views, conv_mod, out, flags, gain, ss_off, resid,
+                                    out_rowss, gw, gh)
         n_rows, n_tile = n_tiling(cout, full_row)
         pack = self.weights.add(f"{name}/R{plan.R}", conv_mod.weight, plan, n_rows, cin_gain, cin_gain_mul)
         if views is None:
@@ -443,6 +455,32 @@ class UnetProgram(Program):
             rec.q_scale, rec.q_cols = q
         self.recs.append(rec)
         return rec
+
+    def _conv_split(self, name, kind, plan, tile, srcs, views, conv_mod, out, flags, gain, ss_off, resid, out_rowss,
+                    gw, gh):
+        """conv + bias as a channel-split tap-GEMM into a bf16 scratch, then ccdm_rmsnorm_act for the tail."""
+        cout = conv_mod.weight.shape[0]
+        n_rows, n_tile = n_tiling(cout, False)
+        pack = self.weights.add(f"{name}/R{plan.R}/split", conv_mod.weight, plan, n_rows)
+        if views is None:
+            views = []
+            for s_ in srcs:
+                views += parity_views(s_) if plan.n_views == 4 else [nhwc_view(s_)]
+        z = self.buf(name + ".z", tuple(out.shape), torch.bfloat16)
+        ostr = (cout, out.shape[2] * cout, out.shape[1] * out.shape[2] * cout)
+        self.recs.append(TapGemmRec(name, plan, views, gw, gh, self.B, tile, pack, pack.packed, pack.sched, n_rows,
+                                    cout, n_tile, L.EPI_BIAS if conv_mod.bias is not None else 0, z, ostr,
+                                    bias=conv_mod.bias))
+        a = dict(z=z, out=out, rows=self.B * gh * gw, C=cout, rows_per_sample=gh * gw, gain=gain,
+                 gain_mul=math.sqrt(cout), flags=flags & (L.EPI_SS | L.EPI_SILU | L.EPI_RESID | L.EPI_SUMSQ_OUT))
+        if ss_off is not None:
+            a.update(ss=self.bufs["ss_all"], ss_ld=self.bufs["ss_all"].shape[1], ss_off=ss_off)
+        if resid is not None:
+            a["resid"] = resid
+        if out_rowss is not None:
+            a["out_rowss"] = out_rowss
+        self.kernel("rmsnorm_act", **a)
+        return None
 
     # ------------------------------------------------------------------ network pieces
     def resblock(self, name, mod, srcs, h, w, ss_off, want_rowss=False):
@@ -478,20 +516,33 @@ class UnetProgram(Program):
         rec.flags |= L.EPI_BIAS
         ctx = self.buf(name + ".ctx", (self.B, heads, 32, 32), torch.float32)
         conv_out, norm_out = att.to_out[0], att.to_out[1]
-        n_rows, n_tile = n_tiling(C, True)
+        wide = C > 512                                      # norm cannot be fused: split channels + standalone norm
+        n_rows, n_tile = n_tiling(C, not wide)
         wfold = self.buf(name + ".wfold", (self.B * n_rows, hid), torch.bfloat16)
-        # context + fold of the context into to_out's weights in one kernel
+        # context, then its fold into to_out's weights: fused into the context kernel's epilogue while that is cheap
+        # (C <= 64), a separate whole-GPU launch for the wider levels
+        fuse = C <= 64 and heads == 4
         self.kernel("linattn_context", qkv=qkv, ctx=ctx, B=self.B, n=n, heads=heads, w_out=conv_out.weight,
-                    wfold=wfold, C=C, n_rows=n_rows)
+                    wfold=wfold if fuse else None, C=C, n_rows=n_rows)
+        if not fuse:
+            self.kernel("linattn_fold", w_out=conv_out.weight, ctx=ctx, wfold=wfold, B=self.B, C=C, n_rows=n_rows,
+                        heads=heads)
         out = self.act(name + ".out", h, w, C)
         plan = plan_conv("1x1", [hid], C)
         sched = torch.tensor(plan.sched, dtype=torch.int32, device=self.device)
         qview = ViewRec(qkv, 0, hid, w, h, self.B, 3 * hid, w * 3 * hid, h * w * 3 * hid)
+        dst = self.act(name + ".z", h, w, C) if wide else out
+        flags = L.EPI_BIAS if wide else (L.EPI_BIAS | L.EPI_RMSNORM | L.EPI_RESID)
         rec = TapGemmRec(name + ".to_out", plan, [qview], w, h, self.B, tile_box(w, h, force_tb1=True), None, wfold,
-                         sched, n_rows, C, n_tile, L.EPI_BIAS | L.EPI_RMSNORM | L.EPI_RESID, out,
-                         (C, w * C, h * w * C), bias=conv_out.bias, gain=norm_out.g, gain_mul=math.sqrt(C), resid=x,
-                         resid_strides=(C, w * C, h * w * C), w_batch_rows=n_rows)
+                         sched, n_rows, C, n_tile, flags, dst, (C, w * C, h * w * C), bias=conv_out.bias,
+                         w_batch_rows=n_rows)
+        if not wide:
+            rec.gain, rec.gain_mul = norm_out.g, math.sqrt(C)
+            rec.resid, rec.resid_strides = x, (C, w * C, h * w * C)
         self.recs.append(rec)
+        if wide:
+            self.kernel("rmsnorm_act", z=dst, out=out, rows=self.B * h * w, C=C, rows_per_sample=h * w,
+                        gain=norm_out.g, gain_mul=math.sqrt(C), resid=x, flags=L.EPI_RESID)
         return out
 
     def mid_attention(self, name, mod, x, rowss, h, w):

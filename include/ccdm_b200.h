@@ -104,6 +104,14 @@ int ccdm_pack_weights(const float* w, int32_t cout, int32_t cin_total, int32_t n
                       int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain, float gain_mul, void* wpacked,
                       void* stream);
 
+/* Standalone channel RMSNorm + tail for rows of C contiguous bf16 channels (unet.py:88-89,145-151), used when a
+ * layer's channels do not fit one tap-GEMM tile (C > 512) or its GEMM is split over output channels:
+ *   out = [silu]( z/max(|z|,1e-12) * gain*gain_mul * (1+scale[b]) + shift[b] ) [+ resid];  flags: CCDM_EPI_SS | SILU |
+ *   RESID | SUMSQ_OUT.  z already contains the conv bias.  Sample of a row = row / rows_per_sample. */
+int ccdm_rmsnorm_act(const void* z, void* out, int64_t rows, int32_t C, int32_t rows_per_sample, const float* gain,
+                     float gain_mul, const float* scale_shift, int32_t ss_ld, int32_t ss_off, const void* resid,
+                     float* out_rowss, uint32_t flags, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Stem and head (NCHW fp32 <-> NHWC bf16 boundary).
  *   stem: unet.py:271,418  nn.Conv2d(in_channels, dim, 7, padding=3)

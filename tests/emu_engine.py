@@ -113,6 +113,23 @@ def run_kernel(r: KernelRec):
                         for c in range(Cin):
                             packed[:Cout, g, dr * 7 * Cin + sx * Cin + c] = w[:, c, r, sx]
         a["wpacked"].copy_(packed.reshape(a["n_rows"], 256).to(torch.bfloat16))
+    elif k == "rmsnorm_act":
+        C, rps = a["C"], a["rows_per_sample"]
+        z = a["z"].float().reshape(-1, C)
+        v = z / z.pow(2).sum(-1, keepdim=True).sqrt().clamp_min(1e-12) * (a["gain"].detach().reshape(-1).float() * a["gain_mul"])
+        fl = a["flags"]
+        if fl & L.EPI_SS:
+            b = torch.arange(z.shape[0]) // rps
+            ss = a["ss"][b]
+            v = v * (1 + ss[:, a["ss_off"]: a["ss_off"] + C]) + ss[:, a["ss_off"] + C: a["ss_off"] + 2 * C]
+        if fl & L.EPI_SILU:
+            v = F.silu(v)
+        if fl & L.EPI_RESID:
+            v = v + a["resid"].float().reshape(-1, C)
+        o = v.to(torch.bfloat16)
+        a["out"].copy_(o.reshape(a["out"].shape))
+        if fl & L.EPI_SUMSQ_OUT:
+            a["out_rowss"].copy_(o.float().pow(2).sum(-1))
     elif k == "head_conv1":
         x = a["x"].float().permute(0, 3, 1, 2)
         a["out"].copy_(F.conv2d(x, a["w"].detach(), a["bias"].detach()))

@@ -11,8 +11,13 @@ SPECS = {
     # channel counts that are multiples of 64, as the sm_100a path wants them (RC-49 widths, shallow)
     "rc_small": UnetSpec(dim=64, dim_mults=(1, 2), in_channels=3, embed_input_dim=128, attn_dim_head=32, attn_heads=4),
 }
-SIZES = {"tiny": 16, "cell": 8, "rc_small": 16}
-BATCH = {"tiny": 3, "cell": 4, "rc_small": 2}
+# not in the golden tables (oracle-only comparisons): 256-wide bottleneck -> channel-split GEMM + standalone norm;
+# dim 72 = the UTKFace-64 widths (72 / 144 / 288 / 576: not multiples of 64, deepest level wider than 512)
+SPECS["wide"] = UnetSpec(dim=32, dim_mults=(1, 2, 8), in_channels=3, embed_input_dim=128, attn_dim_head=32, attn_heads=4)
+SPECS["uk64"] = UnetSpec(dim=72, dim_mults=(1, 2, 4, 4, 8), in_channels=3, embed_input_dim=128, attn_dim_head=32,
+                         attn_heads=4)
+SIZES = {"tiny": 16, "cell": 8, "rc_small": 16, "wide": 16, "uk64": 32}
+BATCH = {"tiny": 3, "cell": 4, "rc_small": 2, "wide": 2, "uk64": 2}
 
 
 def _gen(seed):

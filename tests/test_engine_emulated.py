@@ -20,7 +20,8 @@ def build(spec_name, seed):
 
 
 @pytest.mark.parametrize("spec_name,mode,keep_kind", [("tiny", "eval", "cond"), ("tiny", "eval", "mixed"),
-                                                      ("cell", "train", "null"), ("rc_small", "eval", "cond")])
+                                                      ("cell", "train", "null"), ("rc_small", "eval", "cond"),
+                                                      ("wide", "eval", "mixed")])
 def test_program_matches_oracle(spec_name, mode, keep_kind):
     spec, net, sd = build(spec_name, 5)
     net.train(mode == "train")

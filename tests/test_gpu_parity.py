@@ -102,6 +102,23 @@ def test_other_widths_vs_oracle(spec):
     assert relerr(y, ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("spec_name", ["wide", "uk64"])
+def test_split_norm_path_vs_oracle(spec_name):
+    """Channel-split GEMM + standalone norm: 256-wide bottleneck on few pixels, and the UTKFace-64 widths (dim 72:
+    channel counts that are not multiples of 64 and a 576-wide level that exceeds one TMEM tile)."""
+    spec = SPECS[spec_name]
+    net, sd = make_net(spec, 11)
+    net.eval()
+    x, t, emb = (v.cuda() for v in unet_inputs(spec_name))
+    for p in (0.0, 1.0):
+        y = net(x, t, emb, cond_drop_prob=p)
+        with torch.no_grad():
+            ref = unet_forward(sd, spec, x, t, emb, cond_drop_prob=p)
+        e = relerr(y, ref)
+        print(f"{spec_name} p={p}: rel err {e:.3e}")
+        assert e < BF16_TOL
+
+
 def test_mixed_mask_same_rng_stream():
     """0 < p < 1: the in-UNet Bernoulli mask is drawn like the reference (uniform_ < 1-p) from the CUDA stream."""
     spec = SPECS["rc_small"]
