@@ -253,8 +253,15 @@ def run_b200(args):
         pass
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved = g_fl / (g_ms / 1e3) / 1e12
+    traffic = None                      # dram read+write bytes per launch (avg) from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_tapgemm_traffic.json")))
+        if B == 200 and size == 64:
+            traffic = tr["traffic_bytes_per_launch_avg"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "tapgemm_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                 "launches_per_forward": n_g, "avg_launch_us": 1e3 * g_ms / max(n_g, 1),
                 "flops_per_launch_avg": g_fl / max(n_g, 1), "share_of_unet_time": g_ms / all_ms,
