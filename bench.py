@@ -27,7 +27,7 @@ import torch  # noqa: E402
 
 METRIC = "ddim_images_per_sec"
 UNIT = "images/s"
-WORKLOAD = "RC-49 64x64 CCDM UNet (dim 64, mults 1-2-2-4-8), random-init, DDIM-250 guided sampling (cond_scale 1.5)"
+WORKLOAD = "RC-49 {size}x{size} CCDM UNet (dim 64, mults 1-2-2-4-8), random-init, DDIM-{steps} guided sampling (cond_scale 1.5)"
 
 
 def parse():
@@ -44,7 +44,7 @@ def parse():
 
 
 def config(args, world):
-    return {"workload": WORKLOAD, "image_size": args.size, "ddim_steps": args.ddim_steps, "cond_scale": 1.5,
+    return {"workload": WORKLOAD.format(size=args.size, steps=args.ddim_steps), "image_size": args.size, "ddim_steps": args.ddim_steps, "cond_scale": 1.5,
             "rescaled_phi": 0.7, "objective": "pred_x0", "batch_per_gpu": args.batch,
             "global_batch": args.batch * world, "parallelism": f"sample-sharded x{world}, no data-path collective",
             "l2": "per-step activations (GBs) exceed the 126 MB L2; no flush needed"}

@@ -339,3 +339,55 @@ def test_trainer_sample_given_labels_matches_direct_call():
     y = torch.from_numpy(labels[:3]).cuda()
     direct = tr.ema.ema_model.ddim_sample(labels_emb=fn_y2h(y), labels=y, shape=(3, 3, 16, 16), cond_scale=1.5)
     assert np.array_equal(imgs[:3], (direct.clip(0, 1) * 255.0).type(torch.uint8).cpu().numpy())
+
+
+# ----------------------------------------------------------------------------- full-size, size-independent properties
+
+def test_full_size_sampling_is_batch_shard_invariant():
+    """BASELINE workload shape (RC-49 64x64, batch 200 per GPU): samples are independent of how the batch is split,
+    which is what the multi-GPU sharding (no data-path collective) relies on.  Few DDIM steps keep it short."""
+    B, S = 200, 3
+    gd, _ = _diffusion(RC64, 7, 64, timesteps=1000, sampling_timesteps=S, objective="pred_x0")
+    labels = torch.linspace(0, 1, B, device="cuda")
+    emb = oracle.y2h_sinusoidal(labels, 128)
+    torch.manual_seed(21)
+    x_init = torch.randn(B, 3, 64, 64, device="cuda")
+    full = gd.ddim_sample(labels_emb=emb, labels=labels, shape=(B, 3, 64, 64), cond_scale=1.5, x_init=x_init)
+    parts = [gd.ddim_sample(labels_emb=emb[lo:lo + 100], labels=labels[lo:lo + 100], shape=(100, 3, 64, 64),
+                            cond_scale=1.5, x_init=x_init[lo:lo + 100]) for lo in (0, 100)]
+    assert torch.equal(full, torch.cat(parts))                      # bit-identical: every sample is its own problem
+    assert full.min() >= 0.0 and full.max() <= 1.0 and torch.isfinite(full).all()
+
+
+def test_pair_batch_equals_two_forwards_on_device():
+    """The guided sampler evaluates cond + null as ONE 2B batch; in eval mode that must equal two forwards."""
+    net, _ = make_net(RC64, 7)
+    net.eval()
+    B = 6
+    torch.manual_seed(4)
+    x = torch.randn(B, 3, 64, 64, device="cuda")
+    t = torch.randint(0, 1000, (B,), device="cuda")
+    emb = oracle.y2h_sinusoidal(torch.rand(B, device="cuda"), 128)
+    cond = net(x, t, emb, cond_drop_prob=0.0)
+    null = net(x, t, emb, cond_drop_prob=1.0)
+    c2, n2 = net.engine().forward_pair(x, t, emb)
+    assert torch.equal(cond, c2) and torch.equal(null, n2)
+
+
+@pytest.mark.parametrize("name,spec,size", [
+    ("SA128", UnetSpec(dim=64, dim_mults=(1, 2, 2, 4, 4, 8)), 128),          # BASELINE config 4 widths
+    ("UK192", UnetSpec(dim=64, dim_mults=(1, 2, 2, 4, 4, 8, 8)), 192),       # BASELINE config 5 widths (3x3 bottleneck)
+])
+def test_large_configs_vs_oracle(name, spec, size):
+    torch.manual_seed(2)
+    net, sd = make_net(spec, 9)
+    net.eval()
+    x = torch.randn(1, 3, size, size, device="cuda")
+    t = torch.tensor([400], device="cuda")
+    emb = oracle.y2h_sinusoidal(torch.tensor([0.5], device="cuda"), 128)
+    y = net(x, t, emb, cond_drop_prob=0.0)
+    with torch.no_grad():
+        ref = unet_forward(sd, spec, x, t, emb, cond_drop_prob=0.0)
+    e = relerr(y, ref)
+    print(f"{name} {size}x{size}: rel err {e:.3e}")
+    assert e < BF16_TOL
