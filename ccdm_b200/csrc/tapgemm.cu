@@ -44,6 +44,7 @@ struct TapGemmMaps {
 struct TapGemmDev {
   int gW, gH, gB, tw, th, tb, tiles_w, tiles_h, tiles_m, n_tiles;
   int ngroups, R, nkb, n_rows, N, n_tile, n_sub, nsub, stages, acc_stages, w_batch_rows, b_resident;
+  int n_inner;                            // channel tiles walked by the SAME CTA per pixel tile (1: one per blockIdx.y)
   uint32_t a_bytes, stage_bytes, res_bytes, out_bytes;
   int tiles_per_cta, out_bufs, store_tma;
   const int4* sched;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int z = blockIdx.y / p.n_tiles;
-  const int n0 = (blockIdx.y % p.n_tiles) * p.n_tile;
+  const int n_base = (blockIdx.y % p.n_tiles) * p.n_tile;       // first output channel of this CTA
   const int b_bytes = p.n_tile * 128;
 
   // ---------------------------------------------------------------- one-time setup
@@ -113,10 +114,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     }
     fence_mbar_init();
   }
-  for (int i = tid; i < p.n_tile; i += kThreads) {
-    const bool ok = (n0 + i) < p.N;
-    aux->bias[i] = ((kflags & CCDM_EPI_BIAS) && ok) ? p.bias[n0 + i] : 0.f;
-    aux->gain[i] = ((kflags & CCDM_EPI_RMSNORM) && ok) ? p.gain[n0 + i] * p.gain_mul : 0.f;
+  for (int i = tid; i < p.n_tile * p.n_inner; i += kThreads) {
+    const bool ok = (n_base + i) < p.N;
+    aux->bias[i] = ((kflags & CCDM_EPI_BIAS) && ok) ? p.bias[n_base + i] : 0.f;
+    aux->gain[i] = ((kflags & CCDM_EPI_RMSNORM) && ok) ? p.gain[n_base + i] * p.gain_mul : 0.f;
   }
   for (int i = tid; i < p.ngroups; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
   tc_fence_before();
@@ -131,11 +132,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   if (warp == 0) {
     // ============================================================== TMA producer (warp-uniform loops, one lane issues)
     if (p.b_resident && elect_one()) {
-      mbar_arrive_expect_tx(&aux->b_full, static_cast<uint32_t>(p.nkb) * b_bytes);
-      for (int kb = 0; kb < p.nkb; ++kb)
-        for (int sub = 0; sub < p.nsub; ++sub)
-          tma_load_2d(&maps.b, &aux->b_full, res_b + static_cast<size_t>(kb) * b_bytes + sub * p.n_sub * 128,
-                      kb * kBlockK, z * p.n_rows + n0 + sub * p.n_sub);
+      mbar_arrive_expect_tx(&aux->b_full, static_cast<uint32_t>(p.nkb * p.n_inner) * b_bytes);
+      for (int nt = 0; nt < p.n_inner; ++nt)
+        for (int kb = 0; kb < p.nkb; ++kb)
+          for (int sub = 0; sub < p.nsub; ++sub)
+            tma_load_2d(&maps.b, &aux->b_full,
+                        res_b + static_cast<size_t>(nt * p.nkb + kb) * b_bytes + sub * p.n_sub * 128, kb * kBlockK,
+                        z * p.n_rows + n_base + nt * p.n_tile + sub * p.n_sub);
     }
     __syncwarp();
     uint32_t it = 0;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       const int w0 = (tile % p.tiles_w) * p.tw;
       const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
       const int b0 = (tile / tiles_per_sample) * p.tb;
-      const int wrow = b0 * p.w_batch_rows + z * p.n_rows + n0;
+      const int wrow = b0 * p.w_batch_rows + z * p.n_rows + n_base;
       for (int g = 0; g < p.ngroups; ++g, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
@@ -175,43 +178,47 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       mbar_wait(&aux->b_full, 0);
       tc_fence_after();
     }
-    uint32_t it = 0;
-    int lt = 0;
-    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
-      const int as = lt % p.acc_stages;
-      const uint32_t aph = (lt / p.acc_stages) & 1;
-      mbar_wait(&aux->tmem_empty[as], aph ^ 1u);           // epilogue has drained this accumulator stage
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * p.n_tile;
-      for (int g = 0; g < p.ngroups; ++g, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&aux->a_full[s], ph);
+    uint32_t it0 = 0;                                      // stage counter of the tile's first load group
+    uint32_t item = 0;                                     // (pixel tile, channel tile) pairs = accumulator uses
+    for (int tile = t_begin; tile < t_end; ++tile, it0 += p.ngroups) {
+      for (int nt = 0; nt < p.n_inner; ++nt, ++item) {
+        const int as = item & (p.acc_stages - 1);
+        const uint32_t aph = (item >> (p.acc_stages >> 1)) & 1;
+        mbar_wait(&aux->tmem_empty[as], aph ^ 1u);         // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a16 = ring16 + s * stage16;
-        if (elect_one()) {
-          for (int r = 0; r < p.R; ++r) {
-            const uint32_t at = a16 + r * tap16;                   // tap r: r*tw rows further down the same box
-            const uint32_t bt = p.b_resident ? res16 + (g * p.R + r) * b16 : a16 + abytes16 + r * b16;
-            if (p.nsub == 1) {
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_bf16_ss(d_tmem, umma_desc_sw128_a16(at + 2 * k), umma_desc_sw128_a16(bt + 2 * k), idesc,
-                             (g | r | k) != 0 ? 1u : 0u);
-            } else {
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                for (int sub = 0; sub < 2; ++sub)
-                  umma_bf16_ss(d_tmem + sub * p.n_sub, umma_desc_sw128_a16(at + 2 * k),
-                               umma_desc_sw128_a16(bt + sub * sub16 + 2 * k), idesc, (g | r | k) != 0 ? 1u : 0u);
-            }
+        const uint32_t d_tmem = tmem_base + as * p.n_tile;
+        for (int g = 0; g < p.ngroups; ++g) {
+          const uint32_t it = it0 + g;
+          const int s = it % p.stages;
+          if (nt == 0) {                                   // the boxes of a tile stay resident for all its channel tiles
+            mbar_wait(&aux->a_full[s], (it / p.stages) & 1);
+            tc_fence_after();
           }
-          umma_commit(&aux->a_empty[s]);                   // stage reusable once these MMAs have read it
+          const uint32_t a16 = ring16 + s * stage16;
+          if (elect_one()) {
+            for (int r = 0; r < p.R; ++r) {
+              const uint32_t at = a16 + r * tap16;                 // tap r: r*tw rows further down the same box
+              const uint32_t bt = p.b_resident ? res16 + ((nt * p.nkb) + g * p.R + r) * b16 : a16 + abytes16 + r * b16;
+              if (p.nsub == 1) {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_bf16_ss(d_tmem, umma_desc_sw128_a16(at + 2 * k), umma_desc_sw128_a16(bt + 2 * k), idesc,
+                               (g | r | k) != 0 ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  for (int sub = 0; sub < 2; ++sub)
+                    umma_bf16_ss(d_tmem + sub * p.n_sub, umma_desc_sw128_a16(at + 2 * k),
+                                 umma_desc_sw128_a16(bt + sub * sub16 + 2 * k), idesc, (g | r | k) != 0 ? 1u : 0u);
+              }
+            }
+            if (nt == p.n_inner - 1) umma_commit(&aux->a_empty[s]);   // box reusable once the last MMAs have read it
+          }
+          __syncwarp();
         }
+        if (elect_one()) umma_commit(&aux->tmem_full[as]);   // accumulators of this (tile, channel tile) complete
         __syncwarp();
       }
-      if (elect_one()) umma_commit(&aux->tmem_full[as]);   // accumulators of this tile complete
-      __syncwarp();
     }
   } else {
     // ============================================================== epilogue (warps 2..9)
@@ -252,10 +259,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       if (v0) rss_next = __ldg(p.rowss + px);
     }
 
-    int lt = 0;
-    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
-      const int as = lt & acc_mask;
-      const uint32_t aph = (lt >> acc_shift) & 1;
+    int lt = -1;                                           // accumulator-use counter: (pixel tile, channel tile) pairs
+    for (int tile = t_begin; tile < t_end; ++tile) {
       const int w0 = twi * p.tw, h0 = thi * p.th, b0 = tbi * p.tb;
       if (++twi == p.tiles_w) { twi = 0; if (++thi == p.tiles_h) { thi = 0; ++tbi; } }
       bool valid; int bs; long long pix;
@@ -264,9 +269,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 
       if (tile_ss && b0 != ss_b) {                         // new sample (uniform over the epilogue threads): refresh
         epi_bar();                                         // everyone is done with the previous sample's vectors
-        const float* ssrow = p.ss + static_cast<long long>(b0) * p.ss_ld + p.ss_off + n0;
+        const float* ssrow = p.ss + static_cast<long long>(b0) * p.ss_ld + p.ss_off + n_base;
         for (int c = et; c < p.n_tile; c += kEpiThreads) {
-          const bool ok = (n0 + c) < p.N;
+          const bool ok = (n_base + c) < p.N;
           aux->gs[0][c] = ok ? aux->gain[c] * (1.f + ssrow[c]) : 0.f;
           aux->sh[0][c] = ok ? ssrow[p.N + c] : 0.f;
         }
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         rss_next = v1 ? __ldg(p.rowss + px) : 1.f;
       }
       const long long ro = static_cast<long long>(bs) * p.rsB + static_cast<long long>(h) * p.rsH +
-                           static_cast<long long>(w) * p.rsW + n0;
+                           static_cast<long long>(w) * p.rsW + n_base;
       const bool pre_res = (flags & CCDM_EPI_RESID) && valid && (c_hi - c_lo) <= 2;
       uint4 rpre[2][4];
       if (pre_res) {
@@ -292,11 +297,17 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + (c_lo + cc) * 32);
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-              rpre[cc][g] = (n0 + (c_lo + cc) * 32 + g * 8 < p.N) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
+              rpre[cc][g] = (n_base + (c_lo + cc) * 32 + g * 8 < p.N) ? __ldg(rp + g) : make_uint4(0, 0, 0, 0);
           }
         }
       }
 
+      for (int nt = 0; nt < p.n_inner; ++nt) {
+      ++lt;
+      const int as = lt & acc_mask;
+      const uint32_t aph = (lt >> acc_shift) & 1;
+      const int n0 = n_base + nt * p.n_tile;               // first output channel of this item
+      const float* const s_bias = aux->bias + nt * p.n_tile;
       mbar_wait(&aux->tmem_full[as], aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + trow_lane + as * p.n_tile;
@@ -309,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         for (int c = 0; c < nchunk; ++c) {
           tmem_ld32(trow + c * 32, r);
           tmem_ld_wait();
-          const float2* b2 = reinterpret_cast<const float2*>(aux->bias + c * 32);
+          const float2* b2 = reinterpret_cast<const float2*>(s_bias + c * 32);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 a = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         }
         float2 v[16];
         {
-          const float2* b2 = reinterpret_cast<const float2*>(aux->bias + c * 32);
+          const float2* b2 = reinterpret_cast<const float2*>(s_bias + c * 32);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 a = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
@@ -474,6 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         epi_bar();
       }
       if ((flags & CCDM_EPI_SUMSQ_OUT) && half == 0 && valid) p.out_rowss[pix] = out_ss + aux->part[lt & 1][m];
+      }  // channel tiles of this pixel tile
     }
   }
 
@@ -644,6 +656,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   const int tiles_b = (a->gB + a->tb - 1) / a->tb;
   p.tiles_m = p.tiles_w * p.tiles_h * tiles_b;
   p.n_tiles = a->n_rows / a->n_tile;
+  p.n_inner = 1;
   p.ngroups = a->ngroups; p.R = a->R; p.nkb = nkb;
   p.w_batch_rows = a->w_batch_rows;
   p.n_rows = a->n_rows; p.N = a->N; p.n_tile = a->n_tile; p.n_sub = n_sub; p.nsub = nsub;
@@ -659,6 +672,18 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   for (int i = 0; i < CCDM_MAX_Z; ++i) p.ooff[i] = a->ooff[i];
   p.out_rowss = a->out_rowss; p.q_scale = a->q_scale; p.q_cols = a->q_cols; p.gain_mul = a->gain_mul;
 
+  // ---- channel tiles: by default one (z, n-tile) combination per blockIdx.y.  When the layer has several channel
+  // tiles with very different epilogue costs (linear-attention qkv: softmax | exp | copy) and all their weights fit in
+  // shared memory, every CTA walks ALL channel tiles of its pixel tiles instead: balanced, and A is fetched once.
+  {
+    const size_t all_b = (size_t)a->n_rows * nkb * 128;
+    const bool plain_epi = !(a->flags & (CCDM_EPI_RMSNORM | CCDM_EPI_SS | CCDM_EPI_RESID | CCDM_EPI_SUMSQ_OUT));
+    if (p.n_tiles > 1 && a->nz == 1 && a->w_batch_rows == 0 && plain_epi && a->n_rows <= kMaxN &&
+        all_b <= 64 * 1024 && a->ngroups <= 2 && a->n_tile <= 256) {
+      p.n_inner = p.n_tiles;
+      p.n_tiles = 1;
+    }
+  }
   // ---- launch geometry: persistent CTAs, one (z, n-tile) combination per blockIdx.y
   const int combos = p.n_tiles * a->nz;
   const int sms = num_sms();
@@ -680,8 +705,14 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   p.out_bytes = p.store_tma ? (uint32_t)((a->n_tile + 63) / 64) * 16384u : 0;
   p.out_bufs = p.store_tma ? ((tiles_per_cta > 1 && p.out_bytes <= 32768) ? 2 : 1) : 0;
   budget -= (size_t)p.out_bufs * p.out_bytes;
-  const size_t res_all = (size_t)nkb * b_bytes;
-  p.b_resident = (a->w_batch_rows == 0 && tiles_per_cta >= 2 && res_all + 3 * (size_t)p.a_bytes <= budget) ? 1 : 0;
+  const size_t res_all = (size_t)nkb * b_bytes * p.n_inner;
+  p.b_resident = (a->w_batch_rows == 0 && (tiles_per_cta >= 2 || p.n_inner > 1) &&
+                  res_all + 3 * (size_t)p.a_bytes <= budget) ? 1 : 0;
+  if (p.n_inner > 1 && !p.b_resident) {           // cannot happen with the limits above; keep the simple mode if so
+    p.n_tiles = p.n_inner;
+    p.n_inner = 1;
+    CCDM_REQUIRE(false, CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: internal: inner channel loop without resident weights");
+  }
   p.res_bytes = p.b_resident ? (uint32_t)res_all : 0;
   p.stage_bytes = p.a_bytes + (p.b_resident ? 0 : (uint32_t)a->R * b_bytes);
   int stages = (int)((budget - p.res_bytes) / p.stage_bytes);
@@ -689,6 +720,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   if (tiles_per_cta > 1 && useful < 4) useful = 4;                 // ... but never fewer than 4 boxes in flight
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > useful) stages = useful;
+  if (p.n_inner > 1 && stages < 2 * a->ngroups) stages = 2 * a->ngroups <= kMaxStages ? 2 * a->ngroups : a->ngroups;
   CCDM_REQUIRE(stages >= 1, CCDM_ERR_UNSUPPORTED_SHAPE,
                "tapgemm: one pipeline stage (%u bytes) does not fit shared memory", p.stage_bytes);
   p.stages = stages;
