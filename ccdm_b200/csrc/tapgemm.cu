@@ -125,12 +125,17 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = aux->tmem_slot;
   const int tiles_per_sample = p.tiles_w * p.tiles_h;
+  // Launched with programmatic stream serialization: everything above (and the resident-weight loads below, which
+  // no kernel of the forward pass writes) overlaps the previous kernel's drain.  The next kernel may start its own
+  // prologue as soon as every CTA of this grid has passed this point.
+  griddep_launch_dependents();
   // contiguous tile range per CTA: neighbouring tiles share halos in L2 and (mostly) the sample's scale/shift
   const int t_begin = blockIdx.x * p.tiles_per_cta;
   const int t_end = min(p.tiles_m, t_begin + p.tiles_per_cta);
 
   if (warp == 0) {
     // ============================================================== TMA producer (warp-uniform loops, one lane issues)
+    if (p.w_batch_rows != 0) griddep_wait();               // per-sample weights come from the previous kernel
     if (p.b_resident && elect_one()) {
       mbar_arrive_expect_tx(&aux->b_full, static_cast<uint32_t>(p.nkb * p.n_inner) * b_bytes);
       for (int nt = 0; nt < p.n_inner; ++nt)
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                         z * p.n_rows + n_base + nt * p.n_tile + sub * p.n_sub);
     }
     __syncwarp();
+    griddep_wait();                                        // activations below are the previous kernels' outputs
     uint32_t it = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int w0 = (tile % p.tiles_w) * p.tw;
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const int ob_mask = p.out_bufs > 1 ? 1 : 0;
     const int npanels = (p.n_tile + 63) / 64;
     uint32_t r[32];
+    griddep_wait();                                        // rowss / scale-shift / residual reads and all stores below
     int ss_b = -1;                                         // sample whose scale/shift currently sits in aux->gs/sh
     if (kStoreTma && et == 0) {
       for (int i = 0; i < CCDM_MAX_Z; ++i) tma_prefetch_desc(&maps.o[i]);
@@ -552,8 +559,21 @@ static int launch_one(dim3 grid, size_t smem_bytes, cudaStream_t stream, const T
                                227 * 1024);
   });
   if (err != cudaSuccess) return cuda_fail(err, "tapgemm: cudaFuncSetAttribute");
-  tapgemm_kernel<kFlags, kStoreTma><<<grid, kThreads, smem_bytes, stream>>>(maps, p);
-  return after_launch("tapgemm_kernel");
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_kernel<kFlags, kStoreTma>, maps, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return cuda_fail(e, "tapgemm_kernel launch");
+  return CCDM_OK;
 }
 
 // The epilogue flag sets the UNet actually uses are compiled as separate instantiations; anything else takes the
