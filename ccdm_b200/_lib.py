@@ -70,7 +70,6 @@ SIGNATURES = {
     "ccdm_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), vp]),
     "ccdm_pack_weights": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, vp, vp]),
     "ccdm_rmsnorm_act": (C.c_int, [vp, vp, i64, i32, i32, vp, f32, vp, i32, i32, vp, vp, C.c_uint32, vp]),
-    "ccdm_stem_conv7": (C.c_int, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp]),
     "ccdm_stem_im2row": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "ccdm_stem_pack": (C.c_int, [vp, vp, i32, i32, i32, vp]),
     "ccdm_head_conv1": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -7,82 +7,6 @@
 
 namespace ccdm {
 
-// ============================================================================ stem: 7x7 conv, NCHW fp32 -> NHWC bf16
-// unet.py:271,418.  Cin is 1 or 3: too thin for a TMA im2col, so this is a direct convolution on CUDA cores.
-// Block = 16x16 output pixels, one pixel per thread, 32 output channels per pass; weights [tap][cin][cout] and the
-// 22x22 input halo patch live in shared memory, weight reads are warp-wide broadcasts.
-constexpr int kStemTile = 16;
-constexpr int kStemHalo = kStemTile + 6;
-
-__global__ void __launch_bounds__(256) stem_conv7_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                         const float* __restrict__ bias,
-                                                         __nv_bfloat16* __restrict__ out, int Cin, int H, int W,
-                                                         int Cout, int CoutPad, long long out_pix_stride,
-                                                         int x_batch) {
-  extern __shared__ float s_stem[];
-  float* sw = s_stem;                                   // [49*Cin][CoutPad]
-  float* sx = s_stem + 49 * Cin * CoutPad;              // [Cin][22][23]
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  const int b = blockIdx.z;
-  const int w0 = blockIdx.x * kStemTile, h0 = blockIdx.y * kStemTile;
-
-  for (int i = tid; i < 49 * Cin * CoutPad; i += 256) {
-    const int co = i % CoutPad;
-    const int tc = i / CoutPad;       // tap*Cin + ci
-    const int ci = tc % Cin, tap = tc / Cin;
-    sw[i] = co < Cout ? w[(co * Cin + ci) * 49 + tap] : 0.f;
-  }
-  for (int i = tid; i < Cin * kStemHalo * kStemHalo; i += 256) {
-    const int xx = i % kStemHalo, yy = (i / kStemHalo) % kStemHalo, ci = i / (kStemHalo * kStemHalo);
-    const int gx = w0 + xx - 3, gy = h0 + yy - 3;
-    float v = 0.f;
-    if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = x[((long long)((b % x_batch) * Cin + ci) * H + gy) * W + gx];
-    sx[(ci * kStemHalo + yy) * (kStemHalo + 1) + xx] = v;
-  }
-  __syncthreads();
-
-  const int ox = w0 + tx, oy = h0 + ty;
-  const bool valid = ox < W && oy < H;
-  __nv_bfloat16* orow = out + ((long long)(b * H + (valid ? oy : 0)) * W + (valid ? ox : 0)) * out_pix_stride;
-
-  for (int cg = 0; cg < CoutPad; cg += 32) {
-    float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = (cg + j < Cout) ? bias[cg + j] : 0.f;
-    for (int ci = 0; ci < Cin; ++ci) {
-      for (int r = 0; r < 7; ++r) {
-#pragma unroll
-        for (int s = 0; s < 7; ++s) {
-          const float xv = sx[(ci * kStemHalo + ty + r) * (kStemHalo + 1) + tx + s];
-          const float4* wp = reinterpret_cast<const float4*>(sw + ((r * 7 + s) * Cin + ci) * CoutPad + cg);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 wv = wp[j4];
-            acc[j4 * 4 + 0] = fmaf(xv, wv.x, acc[j4 * 4 + 0]);
-            acc[j4 * 4 + 1] = fmaf(xv, wv.y, acc[j4 * 4 + 1]);
-            acc[j4 * 4 + 2] = fmaf(xv, wv.z, acc[j4 * 4 + 2]);
-            acc[j4 * 4 + 3] = fmaf(xv, wv.w, acc[j4 * 4 + 3]);
-          }
-        }
-      }
-    }
-    if (valid) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (cg + g * 8 < Cout) {
-          uint4 u;
-          u.x = pack_bf16(acc[g * 8 + 0], acc[g * 8 + 1]);
-          u.y = pack_bf16(acc[g * 8 + 2], acc[g * 8 + 3]);
-          u.z = pack_bf16(acc[g * 8 + 4], acc[g * 8 + 5]);
-          u.w = pack_bf16(acc[g * 8 + 6], acc[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(orow + cg + g * 8) = u;
-        }
-      }
-    }
-  }
-}
-
 // ============================================================================ stem on tensor cores: im2row + weight packing
 // The 7x7 stem becomes a 4-tap tap-GEMM over a bf16 NHWC "im2row" tensor whose 64 channels hold a 2-row x 7-column
 // window of the input:  rowimg[b,j,w, dr*7*Cin + s*Cin + c] = x[b,c,j-1+dr,w+s-3]  for j = 0..H (H+1 rows; dr in {0,1};
@@ -432,26 +356,6 @@ __global__ void silu_concat_kernel(const float* __restrict__ t_emb, int dt, cons
 using namespace ccdm;
 
 // ---------------------------------------------------------------------------- C ABI
-
-extern "C" int ccdm_stem_conv7(const float* x, int32_t x_batch, const float* w, const float* bias, void* out, int32_t B,
-                               int32_t Cin, int32_t H, int32_t W, int32_t Cout, int64_t out_pix_stride, void* stream) {
-  CCDM_REQUIRE(x && w && bias && out && x_batch > 0, CCDM_ERR_BAD_ARG, "stem_conv7: null pointer");
-  CCDM_REQUIRE(B > 0 && Cin > 0 && Cin <= 4 && H > 0 && W > 0 && Cout % 8 == 0 && out_pix_stride % 8 == 0,
-               CCDM_ERR_UNSUPPORTED_SHAPE, "stem_conv7: B=%d Cin=%d H=%d W=%d Cout=%d", B, Cin, H, W, Cout);
-  const int cpad = (Cout + 31) / 32 * 32;
-  const size_t smem = (size_t)(49 * Cin * cpad + Cin * kStemHalo * (kStemHalo + 1)) * sizeof(float);
-  CCDM_REQUIRE(smem <= 200 * 1024, CCDM_ERR_UNSUPPORTED_SHAPE, "stem_conv7: Cout=%d too wide", Cout);
-  static size_t max_set = 48 * 1024;
-  if (smem > max_set) {
-    cudaError_t e = cudaFuncSetAttribute(stem_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return cuda_fail(e, "stem_conv7: cudaFuncSetAttribute");
-    max_set = 200 * 1024;
-  }
-  dim3 grid((W + kStemTile - 1) / kStemTile, (H + kStemTile - 1) / kStemTile, B);
-  stem_conv7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (__nv_bfloat16*)out, Cin, H, W, Cout, cpad,
-                                                               out_pix_stride, x_batch);
-  return after_launch("stem_conv7_kernel");
-}
 
 extern "C" int ccdm_stem_im2row(const float* x, void* rowimg, int32_t B, int32_t Cin, int32_t H, int32_t W,
                                 void* stream) {

@@ -205,9 +205,6 @@ def _make_call(lib, r, keep):
                                        r.n_rows, L.ptr(r.cin_gain), r.gain_mul, dst), "pack:" + r.name
     k, a = r.kind, r.a
     p = L.ptr
-    if k == "stem_conv7":
-        return lib.ccdm_stem_conv7, (p(a["x"]), a["x_batch"], p(a["w"]), p(a["bias"]), p(a["out"]), a["B"], a["Cin"],
-                                     a["H"], a["W"], a["Cout"], a["Cout"]), k
     if k == "stem_im2row":
         return lib.ccdm_stem_im2row, (p(a["x"]), p(a["out"]), a["B"], a["Cin"], a["H"], a["W"]), k
     if k == "stem_pack":

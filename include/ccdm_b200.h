@@ -114,13 +114,9 @@ int ccdm_rmsnorm_act(const void* z, void* out, int64_t rows, int32_t C, int32_t 
 
 /* ------------------------------------------------------------------------------------------------------------
  * Stem and head (NCHW fp32 <-> NHWC bf16 boundary).
- *   stem: unet.py:271,418  nn.Conv2d(in_channels, dim, 7, padding=3)
+ *   stem: unet.py:271,418  nn.Conv2d(in_channels, dim, 7, padding=3)  -> im2row + ccdm_tapgemm (below)
  *   head: unet.py:348,455  nn.Conv2d(dim, out_dim, 1)
  * ------------------------------------------------------------------------------------------------------------ */
-/* x_batch: samples held in x_nchw; output sample b reads input sample b % x_batch (the guided sampler runs the
- * conditional and unconditional halves as one 2B batch over the same x_t). */
-int ccdm_stem_conv7(const float* x_nchw, int32_t x_batch, const float* w, const float* bias, void* out_nhwc, int32_t B,
-                    int32_t Cin, int32_t H, int32_t W, int32_t Cout, int64_t out_pix_stride, void* stream);
 /* Tensor-core stem: the 7x7 conv as a 4-tap ccdm_tapgemm (schedule {src 0, dw 0, dh0 2g-2, c0 0}, g = 0..3) over
  *   rowimg[b,j,w, dr*7*Cin + s*Cin + c] = x[b,c,j-1+dr,w+s-3], j = 0..H   (bf16 [B][H+1][W][64], zero outside the image)
  * with weights packed[n][g*64 + dr*7*Cin + s*Cin + c] = w[n][c][2g+dr][s]. */

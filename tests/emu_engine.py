@@ -88,12 +88,7 @@ def run_tapgemm(r: TapGemmRec):
 
 def run_kernel(r: KernelRec):
     k, a = r.kind, r.a
-    if k == "stem_conv7":
-        x = a["x"]
-        idx = torch.arange(a["B"]) % a["x_batch"]
-        y = F.conv2d(x[idx], a["w"].detach(), a["bias"].detach(), padding=3)
-        a["out"].copy_(y.permute(0, 2, 3, 1).to(torch.bfloat16))
-    elif k == "stem_im2row":
+    if k == "stem_im2row":
         x, Cin, H, W = a["x"], a["Cin"], a["H"], a["W"]
         out = torch.zeros(a["B"], H + 1, W, 64)
         xp = F.pad(x[: a["B"]], (3, 3, 1, 1))                                # cols -3..W+2, rows -1..H
