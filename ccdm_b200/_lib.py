@@ -61,6 +61,15 @@ class LossArgs(C.Structure):
     ]
 
 
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("n_src", i32), ("src", View * MAX_SRC), ("dz", vp), ("dsW", i64), ("dsH", i64), ("dsB", i64),
+        ("doff", i64 * MAX_Z), ("gW", i32), ("gH", i32), ("gB", i32), ("tw", i32), ("th", i32), ("tb", i32),
+        ("nz", i32), ("ngroups", i32), ("R", i32), ("sched", vp), ("N", i32), ("n_rows", i32), ("wgrad_packed", vp),
+        ("ksplit", i32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/ccdm_b200.h declares
 SIGNATURES = {
     "ccdm_version": (C.c_int, []),
@@ -87,6 +96,11 @@ SIGNATURES = {
     "ccdm_q_sample": (C.c_int, [C.POINTER(QSampleArgs), vp]),
     "ccdm_vicinal_loss": (C.c_int, [C.POINTER(LossArgs), vp]),
     "ccdm_vicinal_weights": (C.c_int, [vp, i32, i32, i32, i32, vp, f32, vp, vp, vp]),
+    "ccdm_pack_weights_t": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "ccdm_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), vp]),
+    "ccdm_unpack_wgrad": (C.c_int, [vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, i32, vp]),
+    "ccdm_block_bwd": (C.c_int, [vp, vp, vp, i64, i32, i32, vp, f32, vp, i32, i32, vp, C.c_uint32, vp]),
+    "ccdm_block_bwd_finish": (C.c_int, [vp, i32, i32, vp, f32, vp, i32, i32, vp, vp, vp, vp]),
 }
 
 _lib = None
@@ -103,7 +117,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the header and the library disagree
             fn.restype, fn.argtypes = res, args
-        for which, struct in enumerate((TapGemmArgs, View, StepArgs, QSampleArgs, LossArgs)):
+        for which, struct in enumerate((TapGemmArgs, View, StepArgs, QSampleArgs, LossArgs, WgradArgs)):
             if handle.ccdm_struct_size(which) != C.sizeof(struct):
                 raise RuntimeError(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes here, "
                                    f"{handle.ccdm_struct_size(which)} in {LIB_PATH}")

@@ -1,0 +1,214 @@
+"""Backward building blocks of the training step, over NHWC bf16 activations (autograd of the conv / Block call
+sites of CCDM_unified/models/unet.py:77-89,139-165,195-226,326-341; the reference reaches them through
+``loss.backward()`` in trainer.py).
+
+Three kernels carry ~all of the backward FLOPs and bytes:
+
+* data gradient   ``conv_dgrad``   = ``ccdm_tapgemm`` over dY with weights packed by ``ccdm_pack_weights_t``
+  (flipped filter; the 4x4/stride-2 and nearest-2x+3x3 convolutions trade schedules, see plan.py ``*_dgrad``);
+* weight gradient ``conv_wgrad``   = ``ccdm_conv_wgrad`` (tcgen05, positions as the K axis, split-K) +
+  ``ccdm_unpack_wgrad``;
+* Block tail      ``block_backward`` = ``ccdm_block_bwd`` (+ ``_finish``): RMSNorm / scale-shift / SiLU.
+
+These are eager, allocation-per-call wrappers used by the tests and by tools/prof_backward.py; the training program
+that chains them through the whole UNet is not built yet (``GaussianDiffusion.forward(...).backward()`` still raises).
+There is no fallback: every function runs the CUDA library or raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .plan import KB, ConvPlan, can_reuse_rows, n_tiling, plan_conv, tile_box
+
+_KIND_TAPS = {"1x1": 1, "3x3": 9, "down4x4s2": 16, "up2x3x3": 9}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _view(t: torch.Tensor, c_off: int = 0, c: Optional[int] = None) -> L.View:
+    b, h, w, ct = t.shape
+    return L.View(t.data_ptr() + 2 * c_off, ct - c_off if c is None else c, w, h, b, ct, w * ct, h * w * ct)
+
+
+def _parity_views(t: torch.Tensor) -> List[L.View]:
+    b, h, w, ct = t.shape
+    return [L.View(t.data_ptr() + 2 * (pr * w + pq) * ct, ct, (w - pq + 1) // 2, (h - pr + 1) // 2, b, 2 * ct,
+                   2 * w * ct, h * w * ct) for pr in range(2) for pq in range(2)]
+
+
+def _dev_i32(rows, device) -> torch.Tensor:
+    return torch.tensor(rows, dtype=torch.int32, device=device).contiguous()
+
+
+def _check(t: torch.Tensor, what: str):
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.dim() == 4):
+        raise ValueError(f"{what}: expected a contiguous CUDA bf16 [B,H,W,C] tensor, got {tuple(t.shape)} {t.dtype} {t.device}")
+
+
+def _plan_for(kind: str, cins: Sequence[int], cout: int, gw: int, gh: int) -> Tuple[ConvPlan, Tuple[int, int, int]]:
+    base = kind[:-6] if kind.endswith("_dgrad") else kind
+    tile = tile_box(gw, gh, square=(base != "1x1"))
+    reuse = base != "1x1" and can_reuse_rows(tile)
+    return plan_conv(kind, tuple(cins), cout, reuse_rows=reuse), tile
+
+
+def _launch_tapgemm(plan: ConvPlan, tile, views: List[L.View], gw, gh, gb, wpacked, sched, n_rows, n, n_tile, out,
+                    ostr, ooff, bias=None):
+    a = L.TapGemmArgs()
+    a.n_src = len(views)
+    for i, v in enumerate(views):
+        a.src[i] = v
+    a.gW, a.gH, a.gB = gw, gh, gb
+    a.tw, a.th, a.tb = tile
+    a.nz, a.ngroups, a.R = plan.nz, plan.ngroups, plan.R
+    a.sched, a.wpacked = sched.data_ptr(), wpacked.data_ptr()
+    a.n_rows, a.w_batch_rows, a.N, a.n_tile = n_rows, 0, n, n_tile
+    a.flags = L.EPI_BIAS if bias is not None else 0
+    a.bias = L.ptr(bias)
+    a.out = out.data_ptr()
+    a.osW, a.osH, a.osB = ostr
+    for i in range(L.MAX_Z):
+        a.ooff[i] = ooff[i]
+    L.check(L.lib().ccdm_tapgemm(C.byref(a), _stream()), f"tapgemm[{plan.kind}]")
+
+
+def _out_geometry(out: torch.Tensor, parity: bool):
+    _, h, w, co = out.shape
+    if parity:
+        return (2 * co, 2 * w * co, h * w * co), tuple((pa * w + pb) * co for pa in range(2) for pb in range(2))
+    return (co, w * co, h * w * co), (0, 0, 0, 0)
+
+
+def conv_forward(kind: str, srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    """z = conv(concat(srcs)) + bias with the plain epilogue (what a training forward keeps for the backward)."""
+    for s in srcs:
+        _check(s, "conv_forward source")
+    b, h, w, _ = srcs[0].shape
+    cout = weight.shape[0]
+    oh, ow = {"1x1": (h, w), "3x3": (h, w), "down4x4s2": (h // 2, w // 2), "up2x3x3": (2 * h, 2 * w)}[kind]
+    gh, gw = (h, w) if kind == "up2x3x3" else (oh, ow)
+    plan, tile = _plan_for(kind, [s.shape[3] for s in srcs], cout, gw, gh)
+    n_rows, n_tile = n_tiling(cout, False)
+    dev = weight.device
+    packed = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
+    sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
+    L.check(L.lib().ccdm_pack_weights(weight.data_ptr(), cout, weight.shape[1], _KIND_TAPS[kind], psched.data_ptr(),
+                                      plan.nz, plan.nkb, n_rows, None, 1.0, packed.data_ptr(), _stream()), "pack_weights")
+    views: List[L.View] = []
+    for s in srcs:
+        views += _parity_views(s) if plan.n_views == 4 else [_view(s)]
+    out = torch.empty(b, oh, ow, cout, dtype=torch.bfloat16, device=dev)
+    ostr, ooff = _out_geometry(out, plan.out_parity)
+    _launch_tapgemm(plan, tile, views, gw, gh, b, packed, sched, n_rows, cout, n_tile, out, ostr, ooff, bias)
+    return out
+
+
+def conv_dgrad(kind: str, dy: torch.Tensor, weight: torch.Tensor, cins: Sequence[int]) -> List[torch.Tensor]:
+    """Gradients w.r.t. each concatenated source of ``conv(kind)``: list of [B,H,W,cin_i] bf16 tensors."""
+    _check(dy, "conv_dgrad dy")
+    b, oh, ow, cout = dy.shape
+    if cout != weight.shape[0] or sum(cins) != weight.shape[1]:
+        raise ValueError(f"conv_dgrad: dy has {cout} channels, sources {tuple(cins)}, weight {tuple(weight.shape)}")
+    h, w = {"1x1": (oh, ow), "3x3": (oh, ow), "down4x4s2": (2 * oh, 2 * ow), "up2x3x3": (oh // 2, ow // 2)}[kind]
+    # the GEMM grid: positions of dx for stride-1 kinds and the upsampling conv, of dy (= one parity plane of dx) for
+    # the stride-2 conv
+    gh, gw = (oh, ow) if kind == "down4x4s2" else (h, w)
+    dev = weight.device
+    outs = []
+    n_off = 0
+    for cin in cins:
+        plan, tile = _plan_for(kind + "_dgrad", (cout,), cin, gw, gh)
+        n_rows, n_tile = n_tiling(cin, False)
+        packed = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
+        sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
+        L.check(L.lib().ccdm_pack_weights_t(weight.data_ptr(), cout, weight.shape[1], _KIND_TAPS[kind], psched.data_ptr(),
+                                            plan.nz, plan.nkb, n_rows, n_off, cin, packed.data_ptr(), _stream()),
+                "pack_weights_t")
+        views = _parity_views(dy) if plan.n_views == 4 else [_view(dy)]
+        dx = torch.empty(b, h, w, cin, dtype=torch.bfloat16, device=dev)
+        ostr, ooff = _out_geometry(dx, plan.out_parity)
+        _launch_tapgemm(plan, tile, views, gw, gh, b, packed, sched, n_rows, cin, n_tile, dx, ostr, ooff)
+        outs.append(dx)
+        n_off += cin
+    return outs
+
+
+def conv_wgrad(kind: str, srcs: Sequence[torch.Tensor], dz: torch.Tensor, ksplit: int = 0,
+               timing: Optional[list] = None) -> torch.Tensor:
+    """dW [Cout, sum(cins), kh, kw] fp32 of ``conv(kind)`` given its inputs and the gradient of its output."""
+    for s in srcs:
+        _check(s, "conv_wgrad source")
+    _check(dz, "conv_wgrad dz")
+    b, h, w, _ = srcs[0].shape
+    _, oh, ow, cout = dz.shape
+    gh, gw = (h, w) if kind == "up2x3x3" else (oh, ow)
+    cins = [s.shape[3] for s in srcs]
+    plan, tile = _plan_for(kind, cins, cout, gw, gh)
+    dev = dz.device
+    n_rows = (cout + 31) // 32 * 32
+    sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
+    gpacked = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.float32, device=dev)
+    a = L.WgradArgs()
+    views: List[L.View] = []
+    for s in srcs:
+        views += _parity_views(s) if plan.n_views == 4 else [_view(s)]
+    a.n_src = len(views)
+    for i, v in enumerate(views):
+        a.src[i] = v
+    a.dz = dz.data_ptr()
+    (a.dsW, a.dsH, a.dsB), ooff = _out_geometry(dz, plan.out_parity)
+    for i in range(L.MAX_Z):
+        a.doff[i] = ooff[i]
+    a.gW, a.gH, a.gB = gw, gh, b
+    a.tw, a.th, a.tb = tile
+    a.nz, a.ngroups, a.R = plan.nz, plan.ngroups, plan.R
+    a.sched = sched.data_ptr()
+    a.N, a.n_rows = cout, n_rows
+    a.wgrad_packed = gpacked.data_ptr()
+    a.ksplit = ksplit
+    if timing is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    L.check(L.lib().ccdm_conv_wgrad(C.byref(a), _stream()), f"conv_wgrad[{kind}]")
+    if timing is not None:
+        ev1.record()
+        timing.append((ev0, ev1))
+    k = int(math.isqrt(_KIND_TAPS[kind]))
+    dw = torch.empty(cout, sum(cins), k, k, dtype=torch.float32, device=dev)
+    L.check(L.lib().ccdm_unpack_wgrad(gpacked.data_ptr(), dw.data_ptr(), cout, sum(cins), _KIND_TAPS[kind],
+                                      psched.data_ptr(), plan.nz, plan.nkb, n_rows, None, 1.0, 0, _stream()),
+            "unpack_wgrad")
+    return dw
+
+
+def block_backward(dy: torch.Tensor, z: torch.Tensor, gain: torch.Tensor, scale_shift: Optional[torch.Tensor] = None,
+                   ss_off: int = 0, silu: bool = True):
+    """Backward of ``silu(rmsnorm(z) * (1+scale) + shift)`` (Block.forward, unet.py:143-152).
+
+    ``scale_shift`` is the fp32 [B, ld] buffer the forward read (scale at [ss_off, ss_off+C), shift right after).
+    Returns (dz bf16, d_scale_shift fp32 [B, ld] or None, dgain [C], dbias [C])."""
+    _check(dy, "block_backward dy")
+    _check(z, "block_backward z")
+    b, h, w, c = z.shape
+    dev = z.device
+    flags = (L.EPI_SILU if silu else 0) | (L.EPI_SS if scale_shift is not None else 0)
+    dz = torch.empty_like(z)
+    sums = torch.zeros(3, b, c, dtype=torch.float32, device=dev)
+    ld = scale_shift.shape[1] if scale_shift is not None else 0
+    gm = math.sqrt(c)
+    g = gain.reshape(-1)
+    L.check(L.lib().ccdm_block_bwd(dy.data_ptr(), z.data_ptr(), dz.data_ptr(), b * h * w, c, h * w, g.data_ptr(), gm,
+                                   L.ptr(scale_shift), ld, ss_off, sums.data_ptr(), flags, _stream()), "block_bwd")
+    d_ss = torch.zeros_like(scale_shift) if scale_shift is not None else None
+    dgain = torch.zeros(c, dtype=torch.float32, device=dev)
+    dbias = torch.zeros(c, dtype=torch.float32, device=dev)
+    L.check(L.lib().ccdm_block_bwd_finish(sums.data_ptr(), b, c, g.data_ptr(), gm, L.ptr(scale_shift), ld, ss_off,
+                                          L.ptr(d_ss), dgain.data_ptr(), dbias.data_ptr(), _stream()), "block_bwd_finish")
+    return dz, d_ss, dgain, dbias

@@ -25,6 +25,7 @@ extern "C" int ccdm_struct_size(int which) {
     case 2: return (int)sizeof(ccdm_step_args);
     case 3: return (int)sizeof(ccdm_qsample_args);
     case 4: return (int)sizeof(ccdm_loss_args);
+    case 5: return (int)sizeof(ccdm_wgrad_args);
     default: return -1;
   }
 }

@@ -1,0 +1,202 @@
+// Backward of the Block tail (RMSNorm -> (1+scale)*x+shift -> SiLU), CCDM_unified/models/unet.py:88-89,145-151.
+// HBM-bound row kernel: reads dY and Z once, writes dZ once, and leaves three per-(sample, channel) sums from which
+// the gradients of gain, bias, scale and shift follow (ccdm_block_bwd_finish).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ccdm {
+
+constexpr int kBwdThreads = 256;
+constexpr int kBwdMaxC = 1024;
+
+template <int kChunks, int kGroup>   // kGroup lanes share one row; each owns kChunks chunks of 8 channels
+__global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
+                                                                uint4* __restrict__ dz, int rows_per_sample,
+                                                                int rows_per_block, int C, const float* __restrict__ gain,
+                                                                float gain_mul, const float* __restrict__ ss, int ss_ld,
+                                                                int ss_off, float* __restrict__ sums, int B,
+                                                                uint32_t flags) {
+  __shared__ float acc_s[3][kBwdMaxC];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int nchunk = C >> 3;                                       // 8 channels (16 bytes) per chunk
+  constexpr int kRowsPerWarp = 32 / kGroup;
+  const int sub = lane / kGroup, gl = lane % kGroup;
+  for (int i = tid; i < 3 * kBwdMaxC; i += kBwdThreads) (&acc_s[0][0])[i] = 0.f;
+  __syncthreads();
+
+  float a[kChunks][8], sh[kChunks][8];
+  float s1[kChunks][8], s2[kChunks][8], s3[kChunks][8];
+#pragma unroll
+  for (int k = 0; k < kChunks; ++k) {
+    const int ch = gl + kGroup * k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = ch * 8 + j;
+      float sc = 0.f, sf = 0.f, g = 0.f;
+      if (ch < nchunk) {
+        g = gain[c] * gain_mul;
+        if (flags & CCDM_EPI_SS) {
+          sc = ss[(size_t)b * ss_ld + ss_off + c];
+          sf = ss[(size_t)b * ss_ld + ss_off + C + c];
+        }
+      }
+      a[k][j] = g * (1.f + sc);
+      sh[k][j] = sf;
+      s1[k][j] = s2[k][j] = s3[k][j] = 0.f;
+    }
+  }
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, rows_per_sample);
+  for (int rb = r0 + warp * kRowsPerWarp; rb < r1; rb += (kBwdThreads / 32) * kRowsPerWarp) {
+    const int r = rb + sub;
+    const bool live = r < r1;
+    const size_t rowoff = ((size_t)b * rows_per_sample + r) * nchunk;
+    float zf[kChunks][8], gy[kChunks][8];
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      const int ch = gl + kGroup * k;
+      uint4 zu = make_uint4(0, 0, 0, 0), du = make_uint4(0, 0, 0, 0);
+      if (live && ch < nchunk) {
+        zu = __ldg(z + rowoff + ch);
+        du = __ldg(dy + rowoff + ch);
+      }
+      const uint32_t zw[4] = {zu.x, zu.y, zu.z, zu.w}, dw[4] = {du.x, du.y, du.z, du.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        zf[k][2 * j] = bf16_lo(zw[j]);
+        zf[k][2 * j + 1] = bf16_hi(zw[j]);
+        gy[k][2 * j] = bf16_lo(dw[j]);
+        gy[k][2 * j + 1] = bf16_hi(dw[j]);
+        sq = fmaf(zf[k][2 * j], zf[k][2 * j], sq);
+        sq = fmaf(zf[k][2 * j + 1], zf[k][2 * j + 1], sq);
+      }
+    }
+#pragma unroll
+    for (int off = kGroup / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    const float inv = 1.f / fmaxf(sqrtf(sq), 1e-12f);
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float zh = zf[k][j] * inv;
+        float du = gy[k][j];
+        if (flags & CCDM_EPI_SILU) {
+          const float u = fmaf(zh, a[k][j], sh[k][j]);
+          const float sig = 1.f / (1.f + __expf(-u));
+          du *= sig * fmaf(u, 1.f - sig, 1.f);
+        }
+        s1[k][j] = fmaf(du, zh, s1[k][j]);
+        s2[k][j] += du;
+        const float dzh = du * a[k][j];
+        dot = fmaf(zh, dzh, dot);
+        zf[k][j] = zh;
+        gy[k][j] = dzh;
+      }
+    }
+#pragma unroll
+    for (int off = kGroup / 2; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      const int ch = gl + kGroup * k;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = (gy[k][j] - zf[k][j] * dot) * inv;
+        s3[k][j] += o[j];
+      }
+      if (live && ch < nchunk)
+        dz[rowoff + ch] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kChunks; ++k) {
+    const int ch = gl + kGroup * k;
+    if (ch < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&acc_s[0][ch * 8 + j], s1[k][j]);
+        atomicAdd(&acc_s[1][ch * 8 + j], s2[k][j]);
+        atomicAdd(&acc_s[2][ch * 8 + j], s3[k][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * C; i += kBwdThreads) {
+    const int w = i / C, c = i - w * C;
+    atomicAdd(&sums[((size_t)w * B + b) * C + c], acc_s[w][c]);
+  }
+}
+
+__global__ void block_bwd_finish_kernel(const float* __restrict__ sums, int B, int C, const float* __restrict__ gain,
+                                        float gain_mul, const float* __restrict__ ss, int ss_ld, int ss_off,
+                                        float* __restrict__ d_ss, float* __restrict__ dgain, float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float g = gain[c] * gain_mul;
+  float dg = 0.f, db = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float s0 = sums[((size_t)0 * B + b) * C + c];
+    const float s1 = sums[((size_t)1 * B + b) * C + c];
+    db += sums[((size_t)2 * B + b) * C + c];
+    const float sc = ss ? ss[(size_t)b * ss_ld + ss_off + c] : 0.f;
+    dg = fmaf(1.f + sc, s0, dg);
+    if (d_ss) {
+      d_ss[(size_t)b * ss_ld + ss_off + c] = g * s0;
+      d_ss[(size_t)b * ss_ld + ss_off + C + c] = s1;
+    }
+  }
+  if (dgain) dgain[c] += gain_mul * dg;
+  if (dbias) dbias[c] += db;
+}
+
+}  // namespace ccdm
+
+using namespace ccdm;
+
+extern "C" int ccdm_block_bwd(const void* dy, const void* z, void* dz, int64_t rows, int32_t C, int32_t rows_per_sample,
+                              const float* gain, float gain_mul, const float* scale_shift, int32_t ss_ld, int32_t ss_off,
+                              float* sums, uint32_t flags, void* stream) {
+  CCDM_REQUIRE(dy && z && dz && gain && sums, CCDM_ERR_BAD_ARG, "block_bwd: null pointer");
+  CCDM_REQUIRE(rows > 0 && rows_per_sample > 0 && rows % rows_per_sample == 0, CCDM_ERR_BAD_ARG,
+               "block_bwd: rows=%lld rows_per_sample=%d", (long long)rows, rows_per_sample);
+  CCDM_REQUIRE(C > 0 && C % 8 == 0 && C <= kBwdMaxC, CCDM_ERR_UNSUPPORTED_SHAPE,
+               "block_bwd: C=%d must be a multiple of 8 up to %d", C, kBwdMaxC);
+  CCDM_REQUIRE(!(flags & CCDM_EPI_SS) || scale_shift, CCDM_ERR_BAD_ARG, "block_bwd: scale/shift flag without pointer");
+  CCDM_REQUIRE((flags & ~(CCDM_EPI_SS | CCDM_EPI_SILU)) == 0, CCDM_ERR_BAD_ARG, "block_bwd: flags 0x%x", flags);
+  const int B = (int)(rows / rows_per_sample);
+  CCDM_REQUIRE(B <= 65535, CCDM_ERR_UNSUPPORTED_SHAPE, "block_bwd: %d samples", B);
+  // enough CTAs for a few waves, at least 8 rows per warp
+  int per_sample = (num_sms() * 6 + B - 1) / B;
+  const int max_split = (rows_per_sample + 63) / 64;
+  if (per_sample > max_split) per_sample = max_split;
+  if (per_sample < 1) per_sample = 1;
+  const int rows_per_block = (rows_per_sample + per_sample - 1) / per_sample;
+  per_sample = (rows_per_sample + rows_per_block - 1) / rows_per_block;
+  dim3 grid((unsigned)per_sample, (unsigned)B);
+  cudaStream_t s = (cudaStream_t)stream;
+#define CCDM_BWD(K, G)                                                                                                  \
+  block_bwd_kernel<K, G><<<grid, kBwdThreads, 0, s>>>((const uint4*)dy, (const uint4*)z, (uint4*)dz, rows_per_sample,   \
+                                                      rows_per_block, C, gain, gain_mul, scale_shift, ss_ld, ss_off,   \
+                                                      sums, B, flags)
+  if (C <= 32) CCDM_BWD(1, 4);
+  else if (C <= 64) CCDM_BWD(1, 8);
+  else if (C <= 128) CCDM_BWD(1, 16);
+  else if (C <= 256) CCDM_BWD(1, 32);
+  else if (C <= 512) CCDM_BWD(2, 32);
+  else CCDM_BWD(4, 32);
+#undef CCDM_BWD
+  return after_launch("block_bwd_kernel");
+}
+
+extern "C" int ccdm_block_bwd_finish(const float* sums, int32_t B, int32_t C, const float* gain, float gain_mul,
+                                     const float* scale_shift, int32_t ss_ld, int32_t ss_off, float* d_ss, float* dgain,
+                                     float* dbias, void* stream) {
+  CCDM_REQUIRE(sums && gain && B > 0 && C > 0, CCDM_ERR_BAD_ARG, "block_bwd_finish: bad args");
+  CCDM_REQUIRE(!d_ss || scale_shift, CCDM_ERR_BAD_ARG, "block_bwd_finish: d_ss without scale_shift");
+  block_bwd_finish_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, B, C, gain, gain_mul, scale_shift, ss_ld,
+                                                                            ss_off, d_ss, dgain, dbias);
+  return after_launch("block_bwd_finish_kernel");
+}

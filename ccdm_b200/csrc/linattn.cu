@@ -33,20 +33,6 @@ struct CtxAux {
   uint32_t tmem_slot;
 };
 
-// MN-major SWIZZLE_128B operand: LBO = stride between 64-element MN blocks, SBO = stride between 8-row K groups.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-
 __global__ void __launch_bounds__(kCtxThreads, 1) linattn_context_mma_kernel(const __grid_constant__ CUtensorMap qkv_map,
                                                                              float* __restrict__ ctx, int B, int n,
                                                                              const float* __restrict__ w_out,

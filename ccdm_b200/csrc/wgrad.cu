@@ -1,0 +1,324 @@
+// Weight gradient of the tap-GEMM convolutions on tensor cores (tcgen05), the backward of every nn.Conv2d of
+// CCDM_unified/models/unet.py (autograd of :77,81,139,160,165,195,198,225,226,326,341):
+//
+//   dW[co][ci][tap] = sum over output positions p of dZ[p][co] * X[p + shift(tap)][ci]
+//
+// Per load group of the FORWARD schedule (source view, dw, dh0, 64-channel slice c0; R vertically adjacent taps) this
+// is R GEMMs over the position axis that share their operands:
+//
+//   D_r[128 co x 64 ci] = dZ^T[128 co x 128 pos] . X_r[128 pos x 64 ci]          r = 0..R-1
+//
+// Activations are position-major (channels contiguous), so both operands are "MN-major" for UMMA: a TMA box of
+// {64 channels, tw, th, tb} lands as one 128-byte row per position in the SWIZZLE_128B layout.  The X box carries
+// R-1 extra rows, exactly like the forward kernel: tap r starts r*tw rows (r*tw*128 bytes) into it, i.e. the K offset
+// of the B descriptor.  Out-of-image positions are zero-filled by TMA (= the convolution's zero padding), out-of-range
+// channels likewise (so M is always 128, which costs the same tensor-core time as 64).
+//
+// Work split: blockIdx.y = (z, group, 128-channel output tile), blockIdx.x = slice of the position tiles (split-K).
+// Each CTA accumulates its slice in TMEM and adds it into the fp32 gradient with vector reductions.  The gradient is
+// produced in the PACKED layout of the forward weights ([z][row][kb*64 + j], kb = group*R + r); ccdm_unpack_wgrad
+// maps it back to [Cout][Cin][kh*kw] (summing the folded taps of the nearest-2x upsampling convolution).
+#include <cstring>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ccdm {
+
+int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                    const cuuint32_t* box);
+
+constexpr int kWgThreads = 192;
+constexpr int kWgMaxStages = 4;
+constexpr uint32_t kWgABlock = 128 * 128;        // one {64 ch x 128 pos} box of dZ
+
+struct WgAux {
+  uint64_t full[kWgMaxStages], empty[kWgMaxStages], acc_full;
+  uint32_t tmem_slot;
+};
+
+struct WgMaps {
+  CUtensorMap src[CCDM_MAX_SRC];
+  CUtensorMap dz[CCDM_MAX_Z];
+};
+
+struct WgDev {
+  const int4* sched;
+  float* out;
+  int ngroups, R, nkb, m_tiles, n_rows;
+  int tw, th, tb, tiles_w, tiles_h, tiles_m, tiles_per_cta;
+  int stages;
+  uint32_t b_bytes, stage_bytes, tx_bytes;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgDev p) {
+  extern __shared__ __align__(1024) uint8_t wg_smem[];
+  uint8_t* ring = wg_smem;
+  WgAux* aux = reinterpret_cast<WgAux*>(ring + (size_t)p.stages * p.stage_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const int unit = blockIdx.y;
+  const int mt = unit % p.m_tiles;
+  const int g = (unit / p.m_tiles) % p.ngroups;
+  const int z = unit / (p.m_tiles * p.ngroups);
+  const int4 e = __ldg(&p.sched[z * p.ngroups + g]);               // {source view, dw, dh0, c0}
+  const int t0 = blockIdx.x * p.tiles_per_cta;
+  const int t1 = min(t0 + p.tiles_per_cta, p.tiles_m);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.src[e.x]);
+    tma_prefetch_desc(&maps.dz[z]);
+  }
+  if (warp == 1) tmem_alloc(&aux->tmem_slot, 256);
+  if (tid == 64) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&aux->full[s], 1);
+      mbar_init(&aux->empty[s], 1);
+    }
+    mbar_init(&aux->acc_full, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = aux->tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    uint32_t it = 0;
+    for (int t = t0; t < t1; ++t, ++it) {
+      const int s = it % p.stages;
+      mbar_wait(&aux->empty[s], ((it / p.stages) & 1) ^ 1u);
+      if (elect_one()) {
+        const int tx = t % p.tiles_w;
+        const int ty = (t / p.tiles_w) % p.tiles_h;
+        const int tz = t / (p.tiles_w * p.tiles_h);
+        uint8_t* st = ring + (size_t)s * p.stage_bytes;
+        mbar_arrive_expect_tx(&aux->full[s], p.tx_bytes);
+        tma_load_4d(&maps.dz[z], &aux->full[s], st, mt * 128, tx * p.tw, ty * p.th, tz * p.tb);
+        tma_load_4d(&maps.dz[z], &aux->full[s], st + kWgABlock, mt * 128 + 64, tx * p.tw, ty * p.th, tz * p.tb);
+        tma_load_4d(&maps.src[e.x], &aux->full[s], st + 2 * kWgABlock, e.w, tx * p.tw + e.y, ty * p.th + e.z,
+                    tz * p.tb);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one elected lane)
+    const uint32_t idesc = umma_idesc_bf16_mn(128, 64);
+    uint32_t it = 0;
+    for (int t = t0; t < t1; ++t, ++it) {
+      const int s = it % p.stages;
+      mbar_wait(&aux->full[s], (it / p.stages) & 1);
+      tc_fence_after();
+      const uint32_t base = smem_u32(ring + (size_t)s * p.stage_bytes);
+      if (elect_one()) {
+        for (int r = 0; r < p.R; ++r) {
+          const uint32_t bbase = base + 2 * kWgABlock + (uint32_t)(r * p.tw) * 128u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t adesc = umma_desc_mn_sw128(base + k * 2048, kWgABlock);
+            const uint64_t bdesc = umma_desc_mn_sw128(bbase + k * 2048, kWgABlock);
+            umma_bf16_ss(tmem_base + r * 64, adesc, bdesc, idesc, (it | (uint32_t)k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&aux->empty[s]);
+      }
+      __syncwarp();
+    }
+    if (t1 > t0) {
+      if (elect_one()) umma_commit(&aux->acc_full);
+      __syncwarp();
+    }
+  } else if (t1 > t0) {
+    // ---------------------------------------------------------------- epilogue: row co = TMEM lane
+    const int q = warp & 3;
+    const int row = mt * 128 + q * 32 + lane;
+    mbar_wait(&aux->acc_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float* orow = p.out + ((size_t)z * p.n_rows + row) * ((size_t)p.nkb * 64) + (size_t)g * p.R * 64;
+    for (int r = 0; r < p.R; ++r) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(trow + r * 64 + half * 32, v);
+        tmem_ld_wait();
+        if (row < p.n_rows) {
+          float* o = orow + r * 64 + half * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(o + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// dW[n][ci][t] (+)= gain(ci) * sum over packed blocks that hold (ci, t) of packed[z][n][kb*64 + ci - cin0]
+__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ dw, int cout, int cin_total,
+                                    int ntaps, const int4* __restrict__ psched, int nz, int nkb, int n_rows,
+                                    const float* __restrict__ cin_gain, float gain_mul, int accumulate, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % ntaps);
+    const long long r = idx / ntaps;
+    const int ci = (int)(r % cin_total);
+    const int n = (int)(r / cin_total);
+    float acc = 0.f;
+    for (int zk = 0; zk < nz * nkb; ++zk) {
+      const int4 e = __ldg(&psched[zk]);
+      if (ci >= e.x && ci < e.x + e.y && ((unsigned)e.z >> t & 1u)) {
+        const int zz = zk / nkb, kb = zk - zz * nkb;
+        acc += packed[((size_t)zz * n_rows + n) * ((size_t)nkb * 64) + (size_t)kb * 64 + (ci - e.x)];
+      }
+    }
+    acc *= gain_mul * (cin_gain ? cin_gain[ci] : 1.f);
+    dw[idx] = accumulate ? dw[idx] + acc : acc;
+  }
+}
+
+// transposed packing for the data gradient: block kb of sub-problem z holds, for j < nvalid and n < n_count,
+//   sum over taps t in tapmask of W[cin0 + j][n_off + n][t]      (W is the forward [Cout][Cin_total][taps] tensor)
+__global__ void pack_weights_t_kernel(const float* __restrict__ w, int cin_total, int ntaps,
+                                      const int4* __restrict__ psched, int nkb, int n_rows, int n_off, int n_count,
+                                      __nv_bfloat16* __restrict__ out, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx & 63);
+    const long long t = idx >> 6;
+    const int kb = (int)(t % nkb);
+    const long long zn = t / nkb;
+    const int n = (int)(zn % n_rows);
+    const int z = (int)(zn / n_rows);
+    const int4 e = psched[z * nkb + kb];
+    float acc = 0.f;
+    if (n < n_count && j < e.y) {
+      const float* wp = w + ((long long)(e.x + j) * cin_total + (n_off + n)) * ntaps;
+      const unsigned mask = (unsigned)e.z;
+      for (int tp = 0; tp < ntaps; ++tp)
+        if (mask & (1u << tp)) acc += wp[tp];
+    }
+    out[idx] = __float2bfloat16(acc);
+  }
+}
+
+}  // namespace ccdm
+
+using namespace ccdm;
+
+extern "C" int ccdm_conv_wgrad(const ccdm_wgrad_args* a, void* stream) {
+  CCDM_REQUIRE(a != nullptr, CCDM_ERR_BAD_ARG, "conv_wgrad: null args");
+  CCDM_REQUIRE(a->n_src >= 1 && a->n_src <= CCDM_MAX_SRC, CCDM_ERR_BAD_ARG, "conv_wgrad: n_src=%d", a->n_src);
+  CCDM_REQUIRE(a->tw > 0 && a->th > 0 && a->tb > 0 && a->tw * a->th * a->tb == 128, CCDM_ERR_BAD_ARG,
+               "conv_wgrad: tile box %dx%dx%d must hold 128 positions", a->tw, a->th, a->tb);
+  CCDM_REQUIRE(a->nz >= 1 && a->nz <= CCDM_MAX_Z && a->ngroups >= 1 && a->R >= 1 && a->R <= 3, CCDM_ERR_BAD_ARG,
+               "conv_wgrad: nz=%d ngroups=%d R=%d", a->nz, a->ngroups, a->R);
+  CCDM_REQUIRE(a->R == 1 || (a->tb == 1 && a->tw % 8 == 0), CCDM_ERR_BAD_ARG,
+               "conv_wgrad: vertical tap reuse (R=%d) needs tb == 1 and tw %% 8 == 0", a->R);
+  CCDM_REQUIRE(a->sched && a->dz && a->wgrad_packed, CCDM_ERR_BAD_ARG, "conv_wgrad: null sched/dz/wgrad_packed");
+  CCDM_REQUIRE(a->N >= 1 && a->N % 8 == 0 && a->n_rows >= a->N, CCDM_ERR_UNSUPPORTED_SHAPE, "conv_wgrad: N=%d n_rows=%d",
+               a->N, a->n_rows);
+  CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->wgrad_packed) & 15) == 0, CCDM_ERR_BAD_ARG, "conv_wgrad: output alignment");
+  const int box_h = a->th + a->R - 1;
+  WgMaps maps;
+  std::memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < CCDM_MAX_SRC; ++i) {
+    const ccdm_view& v = a->src[i < a->n_src ? i : 0];
+    CCDM_REQUIRE(v.ptr && (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0, CCDM_ERR_BAD_ARG,
+                 "conv_wgrad: source %d pointer must be 16-byte aligned", i);
+    CCDM_REQUIRE(v.C > 0 && v.W > 0 && v.H > 0 && v.B > 0 && v.sW % 8 == 0 && v.sH % 8 == 0 && v.sB % 8 == 0,
+                 CCDM_ERR_BAD_ARG, "conv_wgrad: source %d extents/strides", i);
+    cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.B};
+    cuuint64_t str[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sB * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)a->tw, (cuuint32_t)box_h, (cuuint32_t)a->tb};
+    int rc = encode_map_bf16(&maps.src[i], v.ptr, 4, dims, str, box);
+    if (rc != CCDM_OK) return rc;
+  }
+  CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->dz) & 15) == 0 && a->dsW % 8 == 0 && a->dsH % 8 == 0 && a->dsB % 8 == 0,
+               CCDM_ERR_BAD_ARG, "conv_wgrad: dz view must be 16-byte aligned with strides in multiples of 8");
+  for (int zz = 0; zz < CCDM_MAX_Z; ++zz) {
+    const int zi = zz < a->nz ? zz : 0;
+    CCDM_REQUIRE(a->doff[zi] % 8 == 0, CCDM_ERR_BAD_ARG, "conv_wgrad: doff[%d] must be a multiple of 8 elements", zi);
+    cuuint64_t dims[4] = {(cuuint64_t)a->N, (cuuint64_t)a->gW, (cuuint64_t)a->gH, (cuuint64_t)a->gB};
+    cuuint64_t str[3] = {(cuuint64_t)a->dsW * 2, (cuuint64_t)a->dsH * 2, (cuuint64_t)a->dsB * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)a->tw, (cuuint32_t)a->th, (cuuint32_t)a->tb};
+    int rc = encode_map_bf16(&maps.dz[zz], reinterpret_cast<const __nv_bfloat16*>(a->dz) + a->doff[zi], 4, dims, str, box);
+    if (rc != CCDM_OK) return rc;
+  }
+  WgDev p;
+  std::memset(&p, 0, sizeof(p));
+  p.sched = reinterpret_cast<const int4*>(a->sched);
+  p.out = a->wgrad_packed;
+  p.ngroups = a->ngroups; p.R = a->R; p.nkb = a->ngroups * a->R;
+  p.m_tiles = (a->N + 127) / 128;
+  p.n_rows = a->n_rows;
+  p.tw = a->tw; p.th = a->th; p.tb = a->tb;
+  p.tiles_w = (a->gW + a->tw - 1) / a->tw;
+  p.tiles_h = (a->gH + a->th - 1) / a->th;
+  p.tiles_m = p.tiles_w * p.tiles_h * ((a->gB + a->tb - 1) / a->tb);
+  const int units = a->nz * a->ngroups * p.m_tiles;
+  int ksplit = a->ksplit > 0 ? a->ksplit : num_sms() / units;      // split-K so that about one wave of CTAs runs
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > p.tiles_m) ksplit = p.tiles_m;
+  p.tiles_per_cta = (p.tiles_m + ksplit - 1) / ksplit;
+  ksplit = (p.tiles_m + p.tiles_per_cta - 1) / p.tiles_per_cta;    // no CTA without work
+  p.b_bytes = (uint32_t)(box_h * a->tw * a->tb) * 128u;
+  p.tx_bytes = 2 * kWgABlock + p.b_bytes;
+  p.stage_bytes = p.tx_bytes;
+  p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
+  p.stages = p.tiles_per_cta < kWgMaxStages ? (p.tiles_per_cta < 2 ? 2 : p.tiles_per_cta) : kWgMaxStages;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + sizeof(WgAux) + 1024;
+  CCDM_REQUIRE(smem <= 227 * 1024, CCDM_ERR_UNSUPPORTED_SHAPE, "conv_wgrad: %zu bytes of shared memory", smem);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_wgrad: cudaFuncSetAttribute");
+    attr_smem = smem;
+  }
+  conv_wgrad_kernel<<<dim3((unsigned)ksplit, (unsigned)units), kWgThreads, smem, (cudaStream_t)stream>>>(maps, p);
+  return after_launch("conv_wgrad_kernel");
+}
+
+extern "C" int ccdm_unpack_wgrad(const float* packed, float* dw, int32_t cout, int32_t cin_total, int32_t ntaps,
+                                 const int32_t* psched, int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain,
+                                 float gain_mul, int32_t accumulate, void* stream) {
+  CCDM_REQUIRE(packed && dw && psched, CCDM_ERR_BAD_ARG, "unpack_wgrad: null pointer");
+  CCDM_REQUIRE(cout > 0 && cin_total > 0 && ntaps > 0 && ntaps <= 32 && nz > 0 && nkb > 0 && n_rows >= cout,
+               CCDM_ERR_BAD_ARG, "unpack_wgrad: bad sizes");
+  const long long total = (long long)cout * cin_total * ntaps;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpack_wgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(packed, dw, cout, cin_total, ntaps,
+                                                                         reinterpret_cast<const int4*>(psched), nz, nkb,
+                                                                         n_rows, cin_gain, gain_mul, accumulate, total);
+  return after_launch("unpack_wgrad_kernel");
+}
+
+extern "C" int ccdm_pack_weights_t(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
+                                   int32_t nz, int32_t nkb, int32_t n_rows, int32_t n_off, int32_t n_count, void* wpacked,
+                                   void* stream) {
+  CCDM_REQUIRE(w && psched && wpacked, CCDM_ERR_BAD_ARG, "pack_weights_t: null pointer");
+  CCDM_REQUIRE(cout > 0 && cin_total > 0 && ntaps > 0 && ntaps <= 32 && nz > 0 && nkb > 0 && n_off >= 0 && n_count > 0 &&
+                   n_off + n_count <= cin_total && n_rows >= n_count,
+               CCDM_ERR_BAD_ARG, "pack_weights_t: bad sizes cout=%d cin=%d taps=%d n_off=%d n_count=%d n_rows=%d", cout,
+               cin_total, ntaps, n_off, n_count, n_rows);
+  const long long total = (long long)nz * n_rows * nkb * 64;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weights_t_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      w, cin_total, ntaps, reinterpret_cast<const int4*>(psched), nkb, n_rows, n_off, n_count,
+      reinterpret_cast<__nv_bfloat16*>(wpacked), total);
+  return after_launch("pack_weights_t_kernel");
+}

@@ -68,7 +68,11 @@ def can_reuse_rows(tile: Tuple[int, int, int]) -> bool:
 
 @dataclass
 class ConvPlan:
-    """Everything ccdm_tapgemm / ccdm_pack_weights need for one layer, except pointers."""
+    """Everything ccdm_tapgemm / ccdm_pack_weights need for one layer, except pointers.
+
+    For the data-gradient plans (``*_dgrad``) the roles swap: the GEMM's input channels are the forward layer's
+    OUTPUT channels (``cins`` = (Cout,)), its output channels the forward layer's input channels, and packing entries
+    index the forward weight as W[k_channel][n_channel][tap] (``transposed``)."""
     kind: str
     cins: Tuple[int, ...]                 # channels of each concatenated source
     cout: int
@@ -81,6 +85,7 @@ class ConvPlan:
     n_views: int = 1                      # views per source tensor (4 parity planes for the stride-2 conv)
     out_parity: bool = False              # nz == 4 output parity planes (nearest-2x + 3x3)
     stride: int = 1
+    transposed: bool = False              # data-gradient plan: pack W with input/output channel roles swapped
 
     @property
     def nkb(self) -> int:
@@ -159,7 +164,54 @@ def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = Fals
                         emit(s, s, dw, rows)
         R = 2 if reuse_rows else 1
         return ConvPlan(kind, cins, cout, 9, 4, len(sched) // 4, R, sched, psched, out_parity=True)
+    if kind.endswith("_dgrad"):
+        return _plan_dgrad(kind[:-6], cins, cout, reuse_rows, emit, sched, psched)
     raise ValueError(kind)
+
+
+def _plan_dgrad(fwd_kind, cins, cout, reuse_rows, emit, sched, psched):
+    """dX = conv^T(dY): `cins` = (forward Cout,) are the channels of dY, `cout` the forward input channels produced.
+
+    3x3 / 1x1:  dx[h,w] = sum_{r,q} dy[h+1-r, w+1-q] W[r,q]           -> same taps with the filter flipped
+    4x4 / s2:   dx[2a+ph, 2b+pw] = sum over the two filter rows r = ph+1 (mod 2): a 2x2 conv of dy per input parity
+                plane (exactly the structure of the nearest-2x forward, without tap sums)
+    up2x + 3x3: dx[a,b] = sum over the four output parity planes of dy of 2x2 convs with the folded weights
+                (exactly the structure of the stride-2 forward: four strided views of dy)"""
+    assert len(cins) == 1
+    if fwd_kind == "1x1":
+        emit(0, 0, 0, [(0, 1)])
+        return ConvPlan("1x1_dgrad", cins, cout, 1, 1, len(sched), 1, sched, psched, transposed=True)
+    if fwd_kind == "3x3":
+        for q in range(3):
+            emit(0, 0, q - 1, [(r - 1, 1 << ((2 - r) * 3 + (2 - q))) for r in range(3)])
+        return ConvPlan("3x3_dgrad", cins, cout, 9, 1, len(sched), 3 if reuse_rows else 1, sched, psched,
+                        transposed=True)
+    if fwd_kind == "down4x4s2":
+        # parity p of the input row: [(shift of dy row, filter row)] in increasing shift
+        rows = {0: [(-1, 3), (0, 1)], 1: [(0, 2), (1, 0)]}
+        for ph in range(2):
+            for pw in range(2):
+                for dq, q in rows[pw]:
+                    emit(0, 0, dq, [(dr, 1 << (r * 4 + q)) for dr, r in rows[ph]])
+        return ConvPlan("down4x4s2_dgrad", cins, cout, 16, 4, len(sched) // 4, 2 if reuse_rows else 1, sched, psched,
+                        out_parity=True, transposed=True)
+    if fwd_kind == "up2x3x3":
+        # forward window of parity p: [(dh, filter rows)]; the gradient reads dy plane p at the negated shift
+        win = {0: [(-1, (0,)), (0, (1, 2))], 1: [(0, (0, 1)), (1, (2,))]}
+        for pa in range(2):
+            for pb in range(2):
+                for dw, qset in sorted((-dw_, qs) for dw_, qs in win[pb]):
+                    rows = []
+                    for dh, rset in sorted((-dh_, rs) for dh_, rs in win[pa]):
+                        mask = 0
+                        for r in rset:
+                            for q in qset:
+                                mask |= 1 << (r * 3 + q)
+                        rows.append((dh, mask))
+                    emit(pa * 2 + pb, 0, dw, rows)
+        return ConvPlan("up2x3x3_dgrad", cins, cout, 9, 1, len(sched), 2 if reuse_rows else 1, sched, psched,
+                        n_views=4, transposed=True)
+    raise ValueError(fwd_kind)
 
 
 def n_tiling(cout: int, full_row: bool) -> Tuple[int, int]:

@@ -27,7 +27,7 @@ int ccdm_version(void);
 const char* ccdm_last_error(void);
 /* Number of kernels this library has launched on this process so far (bench.py's "gpu_launches"). */
 int64_t ccdm_launch_count(void);
-/* sizeof() of the args structs as this library was compiled: 0 tapgemm, 1 view, 2 step, 3 qsample, 4 loss.
+/* sizeof() of the args structs as this library was compiled: 0 tapgemm, 1 view, 2 step, 3 qsample, 4 loss, 5 wgrad.
  * Lets a foreign-language binding verify its struct mirrors. */
 int ccdm_struct_size(int which);
 
@@ -252,6 +252,59 @@ int ccdm_vicinal_loss(const ccdm_loss_args* args, void* stream);
  * per-projection thresholds are thr[p]).  w[i] = (1/B) * (1/P or 1) * sum_j [ |d_ij| <= thr ]  or exp(-nu d_ij^2). */
 int ccdm_vicinal_weights(const float* proj, int32_t B, int32_t P, int32_t euclid, int32_t hard, const float* thr,
                          float nu, const uint8_t* keep, float* w, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Backward building blocks of the training step (autograd of the call sites above; trainer.py:560-640 drives
+ * loss.backward() through them in the reference).  The data gradient of every convolution is ccdm_tapgemm itself,
+ * run over dY with weights packed by ccdm_pack_weights_t (filter flipped / channel roles swapped; the stride-2 and
+ * nearest-2x convolutions trade places: see ccdm_b200/plan.py "*_dgrad").
+ * ------------------------------------------------------------------------------------------------------------ */
+/* Transposed packing: block kb of sub-problem z holds, for j < nvalid and n < n_count,
+ *   sum over taps t in tapmask of W[cin0+j][n_off+n][t],   W = the forward [cout][cin_total][ntaps] tensor
+ * (n_off / n_count select the input-channel window of one source of a concatenated forward input). */
+int ccdm_pack_weights_t(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
+                        int32_t nz, int32_t nkb, int32_t n_rows, int32_t n_off, int32_t n_count, void* wpacked,
+                        void* stream);
+
+/* Weight gradient of one tap-GEMM layer (tcgen05, positions as the K axis), accumulated (+=, fp32) in the PACKED
+ * layout of the forward weights:  wgrad_packed[z][n][(g*R+r)*64 + j] += sum_p dZ_z[p][n] * src[g][p + tap(g,r)][c0[g]+j].
+ * src / gW..tb / nz / ngroups / R / sched are the forward layer's; dz is the gradient w.r.t. the conv output (bias
+ * included, before any norm), bf16, addressed like the forward `out` (strides dsW/dsH/dsB, plane offsets doff[z]).
+ * ksplit = number of position slices (CTAs per (z, group, 128-row tile)); 0 = fill the GPU once. */
+typedef struct ccdm_wgrad_args {
+  int32_t n_src;
+  ccdm_view src[CCDM_MAX_SRC];
+  const void* dz;
+  int64_t dsW, dsH, dsB;
+  int64_t doff[CCDM_MAX_Z];
+  int32_t gW, gH, gB;
+  int32_t tw, th, tb;
+  int32_t nz, ngroups, R;
+  const int32_t* sched;
+  int32_t N, n_rows;
+  float* wgrad_packed;
+  int32_t ksplit;
+} ccdm_wgrad_args;
+int ccdm_conv_wgrad(const ccdm_wgrad_args* args, void* stream);
+/* Packed gradient -> dW[cout][cin_total][ntaps] (= or +=): every (ci, t) gathers the packed blocks that hold it
+ * (the folded taps of the nearest-2x convolution sum), times cin_gain[ci]*gain_mul when the forward packed with them. */
+int ccdm_unpack_wgrad(const float* packed, float* dw, int32_t cout, int32_t cin_total, int32_t ntaps,
+                      const int32_t* psched, int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain,
+                      float gain_mul, int32_t accumulate, void* stream);
+
+/* Backward of the Block tail (unet.py:88-89,145-151): with zh = z/max(|z|,1e-12), n = zh*gain*gain_mul,
+ * u = n*(1+scale[b]) + shift[b], y = silu(u):
+ *   du = dy * silu'(u)          dz = (gain*gain_mul*(1+scale)*du - zh * <zh, same>) / |z|        (bf16 out)
+ *   sums[0][b][c] += sum_rows du*zh      sums[1][b][c] += sum_rows du      sums[2][b][c] += sum_rows dz
+ * flags: CCDM_EPI_SS | CCDM_EPI_SILU as in the forward.  sums is fp32 [3][B][C], zeroed by the caller. */
+int ccdm_block_bwd(const void* dy, const void* z, void* dz, int64_t rows, int32_t C, int32_t rows_per_sample,
+                   const float* gain, float gain_mul, const float* scale_shift, int32_t ss_ld, int32_t ss_off,
+                   float* sums, uint32_t flags, void* stream);
+/* Finish: d_ss[b][ss_off+c] = gain*gain_mul*sums0, d_ss[b][ss_off+C+c] = sums1 (when d_ss != NULL);
+ * dgain[c] += gain_mul * sum_b (1+scale[b,c]) * sums0;  dbias[c] += sum_b sums2. */
+int ccdm_block_bwd_finish(const float* sums, int32_t B, int32_t C, const float* gain, float gain_mul,
+                          const float* scale_shift, int32_t ss_ld, int32_t ss_off, float* d_ss, float* dgain,
+                          float* dbias, void* stream);
 
 #ifdef __cplusplus
 }

@@ -6,10 +6,17 @@ import torch
 from ccdm_b200.plan import KB, ConvPlan
 
 
-def pack_weights_emu(plan: ConvPlan, w: torch.Tensor, n_rows: int, cin_gain=None, gain_mul: float = 1.0):
-    """w: [Cout, Cin_total, kh, kw] fp32 -> [nz, n_rows, nkb*64] fp32 (the kernel stores bf16)."""
-    cout, cin_total = w.shape[0], w.shape[1]
-    wt = w.reshape(cout, cin_total, -1)
+def pack_weights_emu(plan: ConvPlan, w: torch.Tensor, n_rows: int, cin_gain=None, gain_mul: float = 1.0, n_off: int = 0,
+                     n_count=None):
+    """w: [Cout, Cin_total, kh, kw] fp32 -> [nz, n_rows, nkb*64] fp32 (the kernel stores bf16).
+    Transposed plans (data gradient) read W[k_channel][n_off + n][tap] for n < n_count."""
+    if plan.transposed:
+        wt = w.reshape(w.shape[0], w.shape[1], -1).transpose(0, 1)          # [Cin_total(n), Cout(k), taps]
+        wt = wt[n_off:n_off + (n_count if n_count is not None else wt.shape[0] - n_off)]
+        cout, cin_total = wt.shape[0], wt.shape[1]
+    else:
+        cout, cin_total = w.shape[0], w.shape[1]
+        wt = w.reshape(cout, cin_total, -1)
     out = torch.zeros(plan.nz, n_rows, plan.nkb * KB)
     for z in range(plan.nz):
         for kb in range(plan.nkb):
@@ -46,10 +53,11 @@ def shifted(view, dh, dw, gh, gw, c0):
     return out
 
 
-def tapgemm_emu(plan: ConvPlan, srcs, w, gh, gw, n_rows=None, cin_gain=None):
-    """Returns [nz, B, gh, gw, Cout] fp32 accumulators (no epilogue)."""
-    n_rows = n_rows or w.shape[0]
-    packed = pack_weights_emu(plan, w, n_rows, cin_gain)
+def tapgemm_emu(plan: ConvPlan, srcs, w, gh, gw, n_rows=None, cin_gain=None, n_off=0, n_count=None):
+    """Returns [nz, B, gh, gw, N] fp32 accumulators (no epilogue)."""
+    nout = (n_count if n_count is not None else w.shape[1] - n_off) if plan.transposed else w.shape[0]
+    n_rows = n_rows or nout
+    packed = pack_weights_emu(plan, w, n_rows, cin_gain, n_off=n_off, n_count=n_count)
     views = make_views(plan, srcs)
     outs = []
     for z in range(plan.nz):
@@ -59,7 +67,7 @@ def tapgemm_emu(plan: ConvPlan, srcs, w, gh, gw, n_rows=None, cin_gain=None):
             for r in range(plan.R):
                 kb = g * plan.R + r
                 a = shifted(views[src], dh0 + r, dw, gh, gw, c0)
-                acc = acc + a @ packed[z, :w.shape[0], kb * KB:(kb + 1) * KB].t()
+                acc = acc + a @ packed[z, :nout, kb * KB:(kb + 1) * KB].t()
         outs.append(acc)
     return torch.stack(outs)
 
