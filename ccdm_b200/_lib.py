@@ -82,7 +82,7 @@ SIGNATURES = {
     "ccdm_stem_im2row": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "ccdm_stem_pack": (C.c_int, [vp, vp, i32, i32, i32, vp]),
     "ccdm_head_conv1": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
-    "ccdm_linattn_context": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, i32, i32, vp]),
+    "ccdm_linattn_context": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, vp, i32, i32, vp]),
     "ccdm_kexp_bound": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
     "ccdm_linattn_fold": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "ccdm_attention_small": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp]),
@@ -101,6 +101,15 @@ SIGNATURES = {
     "ccdm_unpack_wgrad": (C.c_int, [vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, i32, vp]),
     "ccdm_block_bwd": (C.c_int, [vp, vp, vp, i64, i32, i32, vp, f32, vp, i32, i32, vp, C.c_uint32, vp]),
     "ccdm_block_bwd_finish": (C.c_int, [vp, i32, i32, vp, f32, vp, i32, i32, vp, vp, vp, vp]),
+    "ccdm_colsum_bf16": (C.c_int, [vp, i64, i32, vp, vp]),
+    "ccdm_linattn_prep": (C.c_int, [vp, i32, i32, vp, f32, vp]),
+    "ccdm_linattn_pack_blockdiag": (C.c_int, [vp, vp, i32, vp, i32, vp]),
+    "ccdm_linattn_dcontext": (C.c_int, [vp, vp, vp, i32, i32, vp]),
+    "ccdm_linattn_bwd_rowdot": (C.c_int, [vp, vp, vp, vp, i32, vp]),
+    "ccdm_linattn_bwd_finish": (C.c_int, [vp, vp, i32, i32, vp, f32, vp]),
+    "ccdm_attention_small_bwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, f32, vp]),
+    "ccdm_head_conv1_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "ccdm_stem_unpack_wgrad": (C.c_int, [vp, vp, i32, i32, i32, vp]),
 }
 
 _lib = None

@@ -10,13 +10,13 @@ Three kernels carry ~all of the backward FLOPs and bytes:
   ``ccdm_unpack_wgrad``;
 * Block tail      ``block_backward`` = ``ccdm_block_bwd`` (+ ``_finish``): RMSNorm / scale-shift / SiLU.
 
-These are eager, allocation-per-call wrappers used by the tests and by tools/prof_backward.py; the training program
-that chains them through the whole UNet is not built yet (``GaussianDiffusion.forward(...).backward()`` still raises).
-There is no fallback: every function runs the CUDA library or raises.
+These are eager, allocation-per-call wrappers; ccdm_b200/train.py chains them (as torch.autograd.Function nodes) into
+the backward of the whole UNet.  There is no fallback: every function runs the CUDA library or raises.
 """
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 from typing import List, Optional, Sequence, Tuple
 
@@ -43,8 +43,18 @@ def _parity_views(t: torch.Tensor) -> List[L.View]:
                    2 * w * ct, h * w * ct) for pr in range(2) for pq in range(2)]
 
 
+_I32_CACHE: dict = {}
+
+
 def _dev_i32(rows, device) -> torch.Tensor:
-    return torch.tensor(rows, dtype=torch.int32, device=device).contiguous()
+    """Schedule tables are tiny and immutable: one device copy per (table, device)."""
+    key = (id(rows), str(device))
+    hit = _I32_CACHE.get(key)
+    if hit is None or hit[0] is not rows:
+        with torch.inference_mode(False):
+            hit = (rows, torch.tensor(rows, dtype=torch.int32, device=device).contiguous())
+        _I32_CACHE[key] = hit
+    return hit[1]
 
 
 def _check(t: torch.Tensor, what: str):
@@ -53,14 +63,19 @@ def _check(t: torch.Tensor, what: str):
 
 
 def _plan_for(kind: str, cins: Sequence[int], cout: int, gw: int, gh: int) -> Tuple[ConvPlan, Tuple[int, int, int]]:
+    return _plan_cached(kind, tuple(cins), cout, gw, gh)
+
+
+@functools.lru_cache(maxsize=None)
+def _plan_cached(kind, cins, cout, gw, gh):
     base = kind[:-6] if kind.endswith("_dgrad") else kind
     tile = tile_box(gw, gh, square=(base != "1x1"))
     reuse = base != "1x1" and can_reuse_rows(tile)
-    return plan_conv(kind, tuple(cins), cout, reuse_rows=reuse), tile
+    return plan_conv(kind, cins, cout, reuse_rows=reuse), tile
 
 
 def _launch_tapgemm(plan: ConvPlan, tile, views: List[L.View], gw, gh, gb, wpacked, sched, n_rows, n, n_tile, out,
-                    ostr, ooff, bias=None):
+                    ostr, ooff, bias=None, resid: Optional[torch.Tensor] = None, w_batch_rows: int = 0, out_c_off: int = 0):
     a = L.TapGemmArgs()
     a.n_src = len(views)
     for i, v in enumerate(views):
@@ -69,10 +84,14 @@ def _launch_tapgemm(plan: ConvPlan, tile, views: List[L.View], gw, gh, gb, wpack
     a.tw, a.th, a.tb = tile
     a.nz, a.ngroups, a.R = plan.nz, plan.ngroups, plan.R
     a.sched, a.wpacked = sched.data_ptr(), wpacked.data_ptr()
-    a.n_rows, a.w_batch_rows, a.N, a.n_tile = n_rows, 0, n, n_tile
-    a.flags = L.EPI_BIAS if bias is not None else 0
+    a.n_rows, a.w_batch_rows, a.N, a.n_tile = n_rows, w_batch_rows, n, n_tile
+    a.flags = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESID if resid is not None else 0)
     a.bias = L.ptr(bias)
-    a.out = out.data_ptr()
+    if resid is not None:
+        rc = resid.shape[3]
+        a.resid = resid.data_ptr()
+        a.rsW, a.rsH, a.rsB = rc, resid.shape[2] * rc, resid.shape[1] * resid.shape[2] * rc
+    a.out = out.data_ptr() + 2 * out_c_off
     a.osW, a.osH, a.osB = ostr
     for i in range(L.MAX_Z):
         a.ooff[i] = ooff[i]
@@ -86,8 +105,9 @@ def _out_geometry(out: torch.Tensor, parity: bool):
     return (co, w * co, h * w * co), (0, 0, 0, 0)
 
 
-def conv_forward(kind: str, srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor] = None):
-    """z = conv(concat(srcs)) + bias with the plain epilogue (what a training forward keeps for the backward)."""
+def conv_forward(kind: str, srcs: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 resid: Optional[torch.Tensor] = None):
+    """z = conv(concat(srcs)) + bias [+ resid] with the plain epilogue (what a training forward keeps for the backward)."""
     for s in srcs:
         _check(s, "conv_forward source")
     b, h, w, _ = srcs[0].shape
@@ -106,7 +126,41 @@ def conv_forward(kind: str, srcs: Sequence[torch.Tensor], weight: torch.Tensor, 
         views += _parity_views(s) if plan.n_views == 4 else [_view(s)]
     out = torch.empty(b, oh, ow, cout, dtype=torch.bfloat16, device=dev)
     ostr, ooff = _out_geometry(out, plan.out_parity)
-    _launch_tapgemm(plan, tile, views, gw, gh, b, packed, sched, n_rows, cout, n_tile, out, ostr, ooff, bias)
+    _launch_tapgemm(plan, tile, views, gw, gh, b, packed, sched, n_rows, cout, n_tile, out, ostr, ooff, bias, resid)
+    return out
+
+
+def per_sample_linear(src: torch.Tensor, c_off: int, w_batch: torch.Tensor, out: torch.Tensor, out_c_off: int):
+    """out[b,h,w,out_c_off:out_c_off+128] = W_b . src[b,h,w,c_off:c_off+128] with one 128x128 bf16 matrix per sample
+    (the block-diagonal context products of the linear attention, forward and backward)."""
+    b, h, w, _ = src.shape
+    plan, _ = _plan_for("1x1", (128,), 128, w, h)
+    tile = tile_box(w, h, force_tb1=True)
+    sched = _dev_i32(plan.sched, src.device)
+    co = out.shape[3]
+    _launch_tapgemm(plan, tile, [_view(src, c_off, 128)], w, h, b, w_batch, sched, 128, 128, 128, out,
+                    (co, w * co, h * w * co), (0, 0, 0, 0), w_batch_rows=128, out_c_off=out_c_off)
+    return out
+
+
+def rmsnorm_act(z: torch.Tensor, gain: torch.Tensor, scale_shift: Optional[torch.Tensor] = None, silu: bool = False,
+                resid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = [silu]( z/|z| * gain*sqrt(C) * (1+scale) + shift ) [+ resid]   (unet.py:88-89,145-151)"""
+    _check(z, "rmsnorm_act z")
+    b, h, w, c = z.shape
+    out = torch.empty_like(z)
+    flags = (L.EPI_SILU if silu else 0) | (L.EPI_SS if scale_shift is not None else 0) | (L.EPI_RESID if resid is not None else 0)
+    ld = scale_shift.shape[1] if scale_shift is not None else 0
+    L.check(L.lib().ccdm_rmsnorm_act(z.data_ptr(), out.data_ptr(), b * h * w, c, h * w, gain.data_ptr(), math.sqrt(c),
+                                     L.ptr(scale_shift), ld, 0, L.ptr(resid), None, flags, _stream()), "rmsnorm_act")
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [C] column sums of a bf16 [..., C] tensor (bias gradient of a plain convolution)."""
+    c = x.shape[-1]
+    out = torch.zeros(c, dtype=torch.float32, device=x.device)
+    L.check(L.lib().ccdm_colsum_bf16(x.data_ptr(), x.numel() // c, c, out.data_ptr(), _stream()), "colsum_bf16")
     return out
 
 
@@ -140,6 +194,41 @@ def conv_dgrad(kind: str, dy: torch.Tensor, weight: torch.Tensor, cins: Sequence
     return outs
 
 
+@functools.lru_cache(maxsize=None)
+def _plan_cached_stem(cout: int) -> ConvPlan:
+    return plan_conv("stem7", (64,), cout)
+
+
+def wgrad_packed(plan: ConvPlan, tile, views: List[L.View], dz: torch.Tensor, gw: int, gh: int, sched: torch.Tensor,
+                 cout: int, n_rows: int, ksplit: int = 0, timing: Optional[list] = None) -> torch.Tensor:
+    """fp32 [nz*n_rows, nkb*64] weight gradient in the packed layout of the forward weights (ccdm_conv_wgrad)."""
+    dev = dz.device
+    gpacked = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.float32, device=dev)
+    a = L.WgradArgs()
+    a.n_src = len(views)
+    for i, v in enumerate(views):
+        a.src[i] = v
+    a.dz = dz.data_ptr()
+    (a.dsW, a.dsH, a.dsB), ooff = _out_geometry(dz, plan.out_parity)
+    for i in range(L.MAX_Z):
+        a.doff[i] = ooff[i]
+    a.gW, a.gH, a.gB = gw, gh, dz.shape[0]
+    a.tw, a.th, a.tb = tile
+    a.nz, a.ngroups, a.R = plan.nz, plan.ngroups, plan.R
+    a.sched = sched.data_ptr()
+    a.N, a.n_rows = cout, n_rows
+    a.wgrad_packed = gpacked.data_ptr()
+    a.ksplit = ksplit
+    if timing is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    L.check(L.lib().ccdm_conv_wgrad(C.byref(a), _stream()), f"conv_wgrad[{plan.kind}]")
+    if timing is not None:
+        ev1.record()
+        timing.append((ev0, ev1))
+    return gpacked
+
+
 def conv_wgrad(kind: str, srcs: Sequence[torch.Tensor], dz: torch.Tensor, ksplit: int = 0,
                timing: Optional[list] = None) -> torch.Tensor:
     """dW [Cout, sum(cins), kh, kw] fp32 of ``conv(kind)`` given its inputs and the gradient of its output."""
@@ -154,32 +243,10 @@ def conv_wgrad(kind: str, srcs: Sequence[torch.Tensor], dz: torch.Tensor, ksplit
     dev = dz.device
     n_rows = (cout + 31) // 32 * 32
     sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
-    gpacked = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.float32, device=dev)
-    a = L.WgradArgs()
     views: List[L.View] = []
     for s in srcs:
         views += _parity_views(s) if plan.n_views == 4 else [_view(s)]
-    a.n_src = len(views)
-    for i, v in enumerate(views):
-        a.src[i] = v
-    a.dz = dz.data_ptr()
-    (a.dsW, a.dsH, a.dsB), ooff = _out_geometry(dz, plan.out_parity)
-    for i in range(L.MAX_Z):
-        a.doff[i] = ooff[i]
-    a.gW, a.gH, a.gB = gw, gh, b
-    a.tw, a.th, a.tb = tile
-    a.nz, a.ngroups, a.R = plan.nz, plan.ngroups, plan.R
-    a.sched = sched.data_ptr()
-    a.N, a.n_rows = cout, n_rows
-    a.wgrad_packed = gpacked.data_ptr()
-    a.ksplit = ksplit
-    if timing is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-    L.check(L.lib().ccdm_conv_wgrad(C.byref(a), _stream()), f"conv_wgrad[{kind}]")
-    if timing is not None:
-        ev1.record()
-        timing.append((ev0, ev1))
+    gpacked = wgrad_packed(plan, tile, views, dz, gw, gh, sched, cout, n_rows, ksplit, timing)
     k = int(math.isqrt(_KIND_TAPS[kind]))
     dw = torch.empty(cout, sum(cins), k, k, dtype=torch.float32, device=dev)
     L.check(L.lib().ccdm_unpack_wgrad(gpacked.data_ptr(), dw.data_ptr(), cout, sum(cins), _KIND_TAPS[kind],

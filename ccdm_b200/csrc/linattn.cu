@@ -33,8 +33,14 @@ struct CtxAux {
   uint32_t tmem_slot;
 };
 
-__global__ void __launch_bounds__(kCtxThreads, 1) linattn_context_mma_kernel(const __grid_constant__ CUtensorMap qkv_map,
-                                                                             float* __restrict__ ctx, int B, int n,
+// The same kernel computes the backward token-axis product dctx = Q^T . dOut (unet.py:214 transposed): the A operand
+// then comes from channels [a_ch0, a_ch0+128) of `a_map`, B from channels [b_ch0, b_ch0+128) of `b_map`, and the
+// result is left un-normalised (normalize == 0).  `sums_out` ([B][128]) receives the column sums of A.
+__global__ void __launch_bounds__(kCtxThreads, 1) linattn_context_mma_kernel(const __grid_constant__ CUtensorMap a_map,
+                                                                             const __grid_constant__ CUtensorMap b_map,
+                                                                             int a_ch0, int b_ch0, int normalize,
+                                                                             float* __restrict__ ctx,
+                                                                             float* __restrict__ sums_out, int B, int n,
                                                                              const float* __restrict__ w_out,
                                                                              __nv_bfloat16* __restrict__ wfold, int C,
                                                                              int n_rows) {
@@ -45,7 +51,10 @@ __global__ void __launch_bounds__(kCtxThreads, 1) linattn_context_mma_kernel(con
   CtxAux* aux = reinterpret_cast<CtxAux*>(ones + kCtxBlock);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&qkv_map);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a_map);
+    tma_prefetch_desc(&b_map);
+  }
   if (warp == 1) tmem_alloc(&aux->tmem_slot, 256);
   if (tid == 64) {
     for (int s = 0; s < kCtxStages; ++s) {
@@ -78,8 +87,8 @@ __global__ void __launch_bounds__(kCtxThreads, 1) linattn_context_mma_kernel(con
           for (int j = 0; j < 4; ++j)
             asm volatile(
                 "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                ::"r"(smem_u32(st + j * kCtxBlock)), "l"(reinterpret_cast<uint64_t>(&qkv_map)),
-                "r"(smem_u32(&aux->full[s])), "r"(128 + j * 64), "r"(kt * kCtxTok), "r"(b)
+                ::"r"(smem_u32(st + j * kCtxBlock)), "l"(reinterpret_cast<uint64_t>(j < 2 ? &a_map : &b_map)),
+                "r"(smem_u32(&aux->full[s])), "r"(j < 2 ? a_ch0 + j * 64 : b_ch0 + (j - 2) * 64), "r"(kt * kCtxTok), "r"(b)
                 : "memory");
         }
         __syncwarp();
@@ -133,7 +142,8 @@ __global__ void __launch_bounds__(kCtxThreads, 1) linattn_context_mma_kernel(con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&aux->acc_empty);
-      const float inv = 1.f / __uint_as_float(sum[0]);
+      const float inv = normalize ? 1.f / __uint_as_float(sum[0]) : 1.f;
+      if (sums_out) sums_out[static_cast<long long>(b) * 128 + h * 32 + d] = __uint_as_float(sum[0]);
       float cr[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) cr[j] = __uint_as_float(r[j]) * inv;
@@ -243,24 +253,23 @@ using namespace ccdm;
 extern "C" int ccdm_linattn_fold(const float* w_out, const float* ctx, void* wfold, int32_t B, int32_t C,
                                  int32_t n_rows, int32_t heads, void* stream);
 
-extern "C" int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads,
-                                    const float* w_out, void* wfold, int32_t C, int32_t n_rows, void* stream) {
-  CCDM_REQUIRE(qkv && (ctx || wfold) && B > 0 && n > 0 && heads > 0, CCDM_ERR_BAD_ARG, "linattn_context: bad args");
-  CCDM_REQUIRE(!wfold || (w_out && C > 0 && n_rows >= C), CCDM_ERR_BAD_ARG, "linattn_context: fold needs w_out, C, n_rows");
-  cudaStream_t s = (cudaStream_t)stream;
-  if (heads != 4) {
-    CCDM_REQUIRE(ctx, CCDM_ERR_BAD_ARG, "linattn_context: heads != 4 needs the ctx buffer");
-    linattn_context_simt_kernel<<<B * heads, 128, 0, s>>>((const __nv_bfloat16*)qkv, ctx, n, heads);
-    int rc = after_launch("linattn_context_simt_kernel");
-    if (rc != CCDM_OK || !wfold) return rc;
-    return ccdm_linattn_fold(w_out, ctx, wfold, B, C, n_rows, heads, stream);
-  }
-  CUtensorMap map;
-  cuuint64_t dims[3] = {384, (cuuint64_t)n, (cuuint64_t)B};
-  cuuint64_t str[2] = {384 * 2, (cuuint64_t)n * 384 * 2};
+static int launch_token_gemm(const void* a, int a_ld, int a_ch0, const void* bsrc, int b_ld, int b_ch0, int normalize,
+                             float* ctx, float* sums_out, int B, int n, const float* w_out, void* wfold, int C, int n_rows,
+                             cudaStream_t s) {
+  CUtensorMap amap, bmap;
   cuuint32_t box[3] = {64, kCtxTok, 1};
-  int rc = encode_map_bf16(&map, qkv, 3, dims, str, box);
-  if (rc != CCDM_OK) return rc;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a_ld, (cuuint64_t)n, (cuuint64_t)B};
+    cuuint64_t str[2] = {(cuuint64_t)a_ld * 2, (cuuint64_t)n * a_ld * 2};
+    int rc = encode_map_bf16(&amap, a, 3, dims, str, box);
+    if (rc != CCDM_OK) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)b_ld, (cuuint64_t)n, (cuuint64_t)B};
+    cuuint64_t str[2] = {(cuuint64_t)b_ld * 2, (cuuint64_t)n * b_ld * 2};
+    int rc = encode_map_bf16(&bmap, bsrc, 3, dims, str, box);
+    if (rc != CCDM_OK) return rc;
+  }
   const size_t smem = kCtxStages * kCtxStageBytes + kCtxBlock + sizeof(CtxAux) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -271,8 +280,29 @@ extern "C" int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int3
   }
   int grid = num_sms();
   if (grid > B) grid = B;
-  linattn_context_mma_kernel<<<grid, kCtxThreads, smem, s>>>(map, ctx, B, n, w_out, (__nv_bfloat16*)wfold, C, n_rows);
+  linattn_context_mma_kernel<<<grid, kCtxThreads, smem, s>>>(amap, bmap, a_ch0, b_ch0, normalize, ctx, sums_out, B, n, w_out,
+                                                             (__nv_bfloat16*)wfold, C, n_rows);
   return after_launch("linattn_context_mma_kernel");
+}
+
+extern "C" int ccdm_linattn_dcontext(const void* qkv, const void* dout, float* dctx, int32_t B, int32_t n, void* stream) {
+  CCDM_REQUIRE(qkv && dout && dctx && B > 0 && n > 0, CCDM_ERR_BAD_ARG, "linattn_dcontext: bad args");
+  return launch_token_gemm(qkv, 384, 0, dout, 128, 0, 0, dctx, nullptr, B, n, nullptr, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" int ccdm_linattn_context(const void* qkv, float* ctx, float* colsum, int32_t B, int32_t n, int32_t heads,
+                                    const float* w_out, void* wfold, int32_t C, int32_t n_rows, void* stream) {
+  CCDM_REQUIRE(qkv && (ctx || wfold) && B > 0 && n > 0 && heads > 0, CCDM_ERR_BAD_ARG, "linattn_context: bad args");
+  CCDM_REQUIRE(!wfold || (w_out && C > 0 && n_rows >= C), CCDM_ERR_BAD_ARG, "linattn_context: fold needs w_out, C, n_rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (heads != 4) {
+    CCDM_REQUIRE(ctx && !colsum, CCDM_ERR_BAD_ARG, "linattn_context: heads != 4 needs the ctx buffer and has no colsum output");
+    linattn_context_simt_kernel<<<B * heads, 128, 0, s>>>((const __nv_bfloat16*)qkv, ctx, n, heads);
+    int rc = after_launch("linattn_context_simt_kernel");
+    if (rc != CCDM_OK || !wfold) return rc;
+    return ccdm_linattn_fold(w_out, ctx, wfold, B, C, n_rows, heads, stream);
+  }
+  return launch_token_gemm(qkv, 384, 128, qkv, 384, 256, 1, ctx, colsum, B, n, w_out, wfold, C, n_rows, s);
 }
 
 extern "C" int ccdm_kexp_bound(const void* wpacked, int32_t n_rows, int32_t K, int32_t row_lo, int32_t row_hi,

@@ -530,6 +530,13 @@ int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   EncodeTiledFn enc = get_encode();
   CCDM_REQUIRE(enc != nullptr, CCDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // The driver entry point needs a current context on the calling thread.  Threads that have not made a runtime call
+  // yet (PyTorch's autograd workers run the backward nodes) bind the primary context here, once.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_b, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

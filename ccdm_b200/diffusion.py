@@ -66,18 +66,19 @@ def compute_projection(y, v):                                  # diffusion.py:96
     return torch.matmul(y, vn.t())
 
 
-class _NoBackward(torch.autograd.Function):
-    """Marks the loss as differentiable so that .backward() fails loudly instead of silently doing nothing."""
+class _LossGrad(torch.autograd.Function):
+    """Ties the scalar the loss kernel produced to the UNet output: d loss / d model_out comes from the same kernel
+    (ccdm_vicinal_loss, grad_out), so ``loss.backward()`` continues into ccdm_b200/train.py's graph."""
 
     @staticmethod
-    def forward(ctx, loss, anchor):
+    def forward(ctx, model_out, loss, grad_out):
+        ctx.save_for_backward(grad_out)
         return loss.clone()
 
     @staticmethod
     def backward(ctx, g):
-        raise NotImplementedError(
-            "ccdm_b200: the UNet backward (dgrad / wgrad tap-GEMMs, norm and attention backward) is not built yet; "
-            "the training loss is forward-only in this round (see DESIGN.md, 'What comes next')")
+        grad_out, = ctx.saved_tensors
+        return grad_out * g, None, None
 
 
 class GaussianDiffusion(nn.Module):
@@ -457,19 +458,22 @@ class GaussianDiffusion(nn.Module):
         per = torch.empty(b, dtype=torch.float32, device=dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         la = L.LossArgs()
+        model_out = model_out.contiguous()
         la.model_out, la.x0, la.noise = model_out.data_ptr(), x0.data_ptr(), noise_used.data_ptr()
         la.cov = cov.data_ptr() if self.use_Hy else None
         la.keep, la.t = keep_u8.data_ptr(), tt.data_ptr()
         la.sqrt_acp, la.sqrt_1m_acp = qa.sqrt_acp, qa.sqrt_1m_acp
         la.loss_weight, la.row_weight = self.loss_weight.data_ptr(), L.ptr(row_w)
-        la.per_sample, la.loss, la.grad_out = per.data_ptr(), loss.data_ptr(), None
+        want_grad = torch.is_grad_enabled() and model_out.requires_grad
+        grad_out = torch.empty(b, chw, dtype=torch.float32, device=dev) if want_grad else None
+        la.per_sample, la.loss, la.grad_out = per.data_ptr(), loss.data_ptr(), L.ptr(grad_out)
         la.B, la.chw, la.objective = b, chw, L.OBJ[self.objective]
         L.check(lib.ccdm_vicinal_loss(ctypes.byref(la), stream), "vicinal_loss")
         out = loss[0]
+        if want_grad:
+            out = _LossGrad.apply(model_out, out, grad_out.view_as(model_out))
         if scale_all is not None:
             out = out * scale_all
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.unet.parameters()):
-            out = _NoBackward.apply(out, self.unet.final_conv.bias)
         return out
 
     def forward(self, img, *args, **kwargs):

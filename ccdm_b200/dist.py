@@ -72,3 +72,46 @@ def gather_images_u8(img_u8: torch.Tensor, dst: int = 0):
     if dist.get_rank() != dst:
         return None
     return torch.cat([b[: int(s.item())] for b, s in zip(bufs, sizes)])
+
+
+# ------------------------------------------------------------------------------------------- data-parallel training
+# training shards by micro-batch; the one exchange step is the gradient all-reduce.  The reference
+# gets it from accelerate/DDP (trainer.py:121-128,724); here it is an explicit bucketed all-reduce over NCCL (NVLS
+# reduces inside the NVSwitch), issued after the backward of the last micro-batch.
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0):
+    """Make every replica start from rank ``src``'s parameters and buffers."""
+    if not dist.is_initialized():
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src)
+
+
+def all_reduce_gradients(params, bucket_bytes: int = 64 << 20):
+    """Average ``p.grad`` over the ranks in flat fp32 buckets (one collective per ~64 MiB instead of one per tensor)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    world = dist.get_world_size()
+    grads = [p.grad for p in params if p.grad is not None]
+    bucket, size = [], 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+        off = 0
+        for g in bucket:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+        bucket, size = [], 0
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()

@@ -219,7 +219,7 @@ def _make_call(lib, r, keep):
     if k == "kexp_bound":
         return lib.ccdm_kexp_bound, (p(a["wpacked"]), a["n_rows"], a["K"], a["lo"], a["hi"], p(a["bias"])), k
     if k == "linattn_context":
-        return lib.ccdm_linattn_context, (p(a["qkv"]), p(a["ctx"]), a["B"], a["n"], a["heads"], p(a["w_out"]),
+        return lib.ccdm_linattn_context, (p(a["qkv"]), p(a["ctx"]), None, a["B"], a["n"], a["heads"], p(a["w_out"]),
                                           p(a["wfold"]), a["C"], a["n_rows"]), k
     if k == "linattn_fold":
         return lib.ccdm_linattn_fold, (p(a["w_out"]), p(a["ctx"]), p(a["wfold"]), a["B"], a["C"], a["n_rows"],

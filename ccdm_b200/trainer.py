@@ -1,10 +1,10 @@
 """Trainer with the reference's surface (CCDM_unified/trainer.py:43-871): constructor keywords, ``train(fn_y2h)``,
 ``sample_given_labels(...)``, ``save`` / ``load``.  No ``accelerate``: one process per GPU (``ccdm_b200.dist``).
 
-``sample_given_labels`` is the hot caller and is complete.  ``train`` builds batches like the reference (vicinity
-search vectorised on the device instead of a per-sample Python loop with a ``.cpu()`` sync each) and evaluates the
-fused loss; the optimizer step needs the UNet backward kernels, which are not built yet, so ``loss.backward()``
-raises ``NotImplementedError``.
+``sample_given_labels`` is the hot sampling caller.  ``train`` builds batches like the reference (vicinity search
+vectorised on the device instead of a per-sample Python loop with a ``.cpu()`` sync each), evaluates the fused loss,
+back-propagates through the CUDA graph of ccdm_b200/train.py, averages gradients over the ranks when launched under
+torchrun (``ccdm_b200.dist.all_reduce_gradients``) and steps torch's Adam + the EMA like the reference.
 """
 from __future__ import annotations
 
@@ -15,6 +15,7 @@ import numpy as np
 import torch
 from torch.optim import Adam
 
+from . import dist as ccdm_dist
 from .ema import EMA
 from .diffusion import generate_random_vectors
 from .utils import divisible_by, exists
@@ -141,7 +142,8 @@ class Trainer(object):
                 loss = self.model(images, labels_emb=fn_y2h(labels), labels=labels, vicinal_weights=weights, **kw)
                 loss = loss / self.gradient_accumulate_every
                 total += loss.item()
-                loss.backward()                      # raises NotImplementedError until the backward kernels land
+                loss.backward()
+            ccdm_dist.all_reduce_gradients(list(self.model.parameters()))
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.max_grad_norm)
             if self.step % 500 == 0:
                 with open(log, "a") as f:

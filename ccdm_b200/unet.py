@@ -184,6 +184,10 @@ class Unet(nn.Module):
             else:
                 mask = torch.zeros((b,), device=x.device).float().uniform_(0, 1) < keep
             self.keep_mask = mask
+        if self.training and torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+            # training step: autograd graph over the CUDA kernels (ccdm_b200/train.py); BatchNorm1d uses batch statistics
+            from .train import unet_train_forward
+            return unet_train_forward(self, x, timesteps, labels_emb, mask)
         return self.engine().forward(x, timesteps, labels_emb, mask)
 
     def forward_with_cond_scale(self, *args, cond_scale=1.0, rescaled_phi=0.0, remove_parallel_component=True,

@@ -132,9 +132,10 @@ int ccdm_head_conv1(const void* x_nhwc, const float* w, const float* bias, float
  *     (fp32 [B][heads][32][32]) runs on tcgen05 for heads == 4 (both operands token-major = MN-major UMMA)
  *   softmax attention at the bottleneck, unet.py:228-240 (n <= 64 tokens, dim_head <= 64)
  * ------------------------------------------------------------------------------------------------------------ */
-/* When wfold != NULL the fold below is fused into the same kernel (ctx may then be NULL). */
-int ccdm_linattn_context(const void* qkv, float* ctx, int32_t B, int32_t n, int32_t heads, const float* w_out,
-                         void* wfold, int32_t C, int32_t n_rows, void* stream);
+/* When wfold != NULL the fold below is fused into the same kernel (ctx may then be NULL).  colsum (optional, heads == 4
+ * only) receives S[b][h*32+d] = sum_n p[d,n], which the backward needs. */
+int ccdm_linattn_context(const void* qkv, float* ctx, float* colsum, int32_t B, int32_t n, int32_t heads,
+                         const float* w_out, void* wfold, int32_t C, int32_t n_rows, void* stream);
 /* bias[n] = -1.01*||wpacked[n,:]||_2 - 1e-3 for n in [row_lo,row_hi), 0 elsewhere.  The PreNorm'd input rows have unit
  * length, so |k[n,d]| <= ||W'_d||: using this bound as the softmax shift needs no max pass over the tokens. */
 int ccdm_kexp_bound(const void* wpacked, int32_t n_rows, int32_t K, int32_t row_lo, int32_t row_hi, float* bias,
@@ -305,6 +306,31 @@ int ccdm_block_bwd(const void* dy, const void* z, void* dz, int64_t rows, int32_
 int ccdm_block_bwd_finish(const float* sums, int32_t B, int32_t C, const float* gain, float gain_mul,
                           const float* scale_shift, int32_t ss_ld, int32_t ss_off, float* d_ss, float* dgain,
                           float* dbias, void* stream);
+
+/* ---- training-only pieces (autograd of unet.py:202-216, :228-240, :271, :348); heads = 4, dim_head = 32 for the
+ * linear attention, as in the reference (never overridden, unet.py:190,325,340) ---- */
+/* out[c] += sum over rows of x[row][c] (bf16 [rows][C]): bias gradients of plain convolutions. */
+int ccdm_colsum_bf16(const void* x, int64_t rows, int32_t C, float* out, void* stream);
+/* In place on the raw qkv [B][n][384] of the to_qkv conv: q <- softmax over each head's channels * scale (:207,:210),
+ * k <- exp(k - kmax[b][c]) with kmax the per-sample maximum over tokens (written to kmax [B][128]). */
+int ccdm_linattn_prep(void* qkv, int32_t B, int32_t n, float* kmax, float scale, void* stream);
+/* Per-sample block-diagonal [B][128][128] bf16 weights for ccdm_tapgemm (w_batch_rows = 128) from m = fp32
+ * [B][4][32][32]: transpose == 0 -> w[b][h*32+e][h*32+d] = m[b][h][d][e] / row_div[b][h*32+d]; else rows/cols swapped. */
+int ccdm_linattn_pack_blockdiag(const float* m, const float* row_div, int32_t transpose, void* w, int32_t B, void* stream);
+/* dctx[b][h][d][e] = sum_n q_sm[b][n][h*32+d] * dout[b][n][h*32+e]  (tcgen05, same kernel as the context). */
+int ccdm_linattn_dcontext(const void* qkv, const void* dout, float* dctx, int32_t B, int32_t n, void* stream);
+/* c[b][h*32+d] = sum_e dctx*ctx / S  (the column-sum term of the token softmax backward). */
+int ccdm_linattn_bwd_rowdot(const float* ctx, const float* dctx, const float* S, float* c, int32_t B, void* stream);
+/* In place: dpre [B][n][384] = [dq_sm | dp_term | dv] -> gradient of the raw qkv, given qkv = [q_sm | p | v]. */
+int ccdm_linattn_bwd_finish(const void* qkv, void* dpre, int32_t B, int32_t n, const float* c, float scale, void* stream);
+/* Backward of ccdm_attention_small: dqkv [B][n][3*heads*dim_head] from the raw qkv and dout [B][n][heads*dim_head]. */
+int ccdm_attention_small_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t n, int32_t heads,
+                             int32_t dim_head, float scale, void* stream);
+/* Backward of ccdm_head_conv1: dh (bf16 NHWC), dw [Cout][Cin] += , db [Cout] += from dout (fp32 NCHW). */
+int ccdm_head_conv1_bwd(const float* dout_nchw, const void* h, const float* w, void* dh, float* dw, float* db, int32_t B,
+                        int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream);
+/* Inverse of ccdm_stem_pack for the gradient ccdm_conv_wgrad leaves over the im2row tensor: dW [Cout][Cin][7][7]. */
+int ccdm_stem_unpack_wgrad(const float* packed, float* dw, int32_t Cout, int32_t Cin, int32_t accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,16 @@ def _worker(rank, world, port, q):
     slowest = D.max_over_ranks(1.0 + r)                     # rank 1 is "slower"
     img = (mine * 255).to(torch.uint8).view(-1, 1, 1, 1).repeat(1, 3, 2, 2)
     allimg = D.gather_images_u8(img)
-    q.put((r, mine.tolist(), slowest, None if allimg is None else allimg[:, 0, 0, 0].tolist()))
+    # data-parallel training exchange: replicas start equal, gradients are averaged in flat buckets
+    torch.manual_seed(r)
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3))
+    D.broadcast_parameters(lin)
+    w0 = lin[0].weight.detach().clone()
+    for i, p in enumerate(lin.parameters()):
+        p.grad = torch.full_like(p, float(r + 1) * (i + 1))
+    D.all_reduce_gradients(list(lin.parameters()), bucket_bytes=64)      # tiny buckets: several collectives
+    gsum = [p.grad.flatten()[0].item() for p in lin.parameters()]
+    q.put((r, mine.tolist(), slowest, None if allimg is None else allimg[:, 0, 0, 0].tolist(), w0.sum().item(), gsum))
     torch.distributed.destroy_process_group()
 
 
@@ -55,3 +64,5 @@ def test_two_rank_gloo():
     assert res[0][1] + res[1][1] == labels.tolist()         # shards partition the batch in order
     assert res[0][2] == res[1][2] == 2.0                    # max over ranks
     assert res[0][3] == (labels * 255).to(torch.uint8).tolist() and res[1][3] is None
+    assert res[0][4] == res[1][4]                           # parameters broadcast from rank 0
+    assert res[0][5] == res[1][5] == [1.5 * (i + 1) for i in range(4)]   # mean of (1, 2) * (i + 1)

@@ -306,19 +306,6 @@ def test_loss_vs_oracle(name):
     assert e < BF16_TOL
 
 
-def test_backward_fails_loudly():
-    import ccdm_b200
-    spec = SPECS["rc_small"]
-    net, _ = make_net(spec, 4)
-    gd = ccdm_b200.GaussianDiffusion(net, image_size=16, timesteps=1000, objective="pred_x0").cuda().train()
-    img = torch.rand(4, 3, 16, 16, device="cuda")
-    labels = torch.rand(4, device="cuda")
-    loss = gd(img, labels_emb=oracle.y2h_sinusoidal(labels, 128), labels=labels, vicinal_weights=torch.ones(4, device="cuda"),
-              vicinity_type="hv", kappa=0.1)
-    with pytest.raises(NotImplementedError):
-        loss.backward()
-
-
 def test_trainer_sample_given_labels_matches_direct_call():
     """Hot caller (trainer.py:782-869): uint8 images for given labels through the EMA copy."""
     import numpy as np

@@ -1,0 +1,118 @@
+"""Times one optimizer step of the training path: q_sample -> UNet forward ->
+vicinal loss -> backward through ccdm_b200/train.py -> Adam.  CUDA events, W warm-up steps, K timed steps, max over
+ranks; under torchrun it also averages gradients over the ranks (ccdm_b200.dist.all_reduce_gradients).
+
+  python tools/bench_train.py [--model uk64|rc64] [--batch 128] [--steps 5] [--warmup 3] [--breakdown]
+
+Prints one JSON line: ms/step, images/s, algorithmic TFLOP/s (3 x forward FLOPs per image, the usual fwd+dgrad+wgrad
+accounting) against MEASURED_PEAKS.json, and with --breakdown the forward / backward / optimizer split.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ccdm_b200  # noqa: E402
+from ccdm_b200 import dist as D  # noqa: E402
+
+MODELS = {
+    # forward GFLOP per image from SURVEY.md section 8d (conv + linear + bmm, 2*MAC)
+    "uk64": dict(dim=72, dim_mults=(1, 2, 4, 4, 8), size=64, gflop=16.25),
+    "rc64": dict(dim=64, dim_mults=(1, 2, 2, 4, 8), size=64, gflop=11.00),
+}
+
+
+def sinusoid(y, dim):
+    half = dim // 2
+    f = torch.exp(-math.log(10000) * torch.arange(half, device=y.device, dtype=torch.float32) / half)
+    a = y.reshape(-1)[:, None].float() * f[None]
+    return torch.cat([torch.cos(a), torch.sin(a)], -1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="uk64", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--breakdown", action="store_true")
+    a = ap.parse_args()
+    rank, local, world = D.env_world()
+    torch.cuda.set_device(local)
+    D.init("nccl")
+    m = MODELS[a.model]
+    torch.manual_seed(111)
+    net = ccdm_b200.Unet(dim=m["dim"], embed_input_dim=128, cond_drop_prob=0.1, dim_mults=m["dim_mults"], in_channels=3,
+                         attn_dim_head=32, attn_heads=4)
+    n_el = 3 * m["size"] ** 2
+    fn_y2cov = lambda y: (sinusoid(y, n_el) + 1) / 2                      # sinusoidal covariance embedding, cov_dim = C*H*W
+    gd = ccdm_b200.GaussianDiffusion(net, image_size=m["size"], objective="pred_x0", use_Hy=True, fn_y2cov=fn_y2cov,
+                                     cond_drop_prob=0.1, timesteps=1000, vicinity_type="hv").cuda().train()
+    D.broadcast_parameters(gd)
+    opt = torch.optim.Adam(gd.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    g = torch.Generator().manual_seed(rank)
+    B = a.batch
+    img = torch.rand(B, 3, m["size"], m["size"], generator=g).cuda()
+    labels = torch.rand(B, generator=g).cuda()
+    emb = sinusoid(labels, 128)
+    ones = torch.ones(B, device="cuda")
+    params = list(gd.parameters())
+    lib = ccdm_b200._lib.lib()
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        loss = gd(img, labels_emb=emb, labels=labels, vicinal_weights=ones, vicinity_type="hv", kappa=0.05)
+        if ev:
+            ev[1].record()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if ev:
+            ev[2].record()
+        D.all_reduce_gradients(params)
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        if ev:
+            ev[3].record()
+        return loss
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    D.barrier()
+    l0 = lib.ccdm_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(a.steps)]
+    e0.record()
+    for k in range(a.steps):
+        loss = step(evs[k] if a.breakdown else None)
+    e1.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1) / a.steps)
+    launches = (lib.ccdm_launch_count() - l0) // a.steps
+    if rank == 0:
+        peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
+        tflops = 3 * m["gflop"] * B * world / ms                         # GFLOP / ms = TFLOP/s
+        rec = dict(metric="train step", model=a.model, per_gpu_batch=B, n_gpus=world, ms_per_step=round(ms, 2),
+                   images_per_s=round(B * world / ms * 1e3, 1), algorithmic_tflops=round(tflops, 1),
+                   frac_of_sustained_bf16_peak=round(tflops / world / peaks["bf16_tflops_sustained"], 3),
+                   kernel_launches_per_step=int(launches), loss=round(loss.item(), 5),
+                   peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
+        if a.breakdown:
+            f = sum(e[0].elapsed_time(e[1]) for e in evs) / a.steps
+            b = sum(e[1].elapsed_time(e[2]) for e in evs) / a.steps
+            o = sum(e[2].elapsed_time(e[3]) for e in evs) / a.steps
+            rec.update(forward_ms=round(f, 2), backward_ms=round(b, 2), allreduce_clip_adam_ms=round(o, 2))
+        print(json.dumps(rec), flush=True)
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/bench_train.jsonl", "a") as fh:
+            fh.write(json.dumps(rec) + "\n")
+
+
+if __name__ == "__main__":
+    main()
