@@ -3,6 +3,8 @@
 Public surface mirrors CCDM_unified: ``Unet`` (models/unet.py), ``GaussianDiffusion`` (diffusion.py),
 ``LabelEmbed`` (label_embedding.py), ``Trainer`` / ``EMA`` (trainer.py, ema_pytorch.py).
 The arithmetic runs in libccdm_b200.so (include/ccdm_b200.h); there is no CPU or PyTorch fallback.
+Training: ``loss.backward()`` runs through ccdm_b200.train (autograd nodes over the kernels);
+``ccdm_b200.train_graph.GraphedTrainStep`` replays the whole optimizer step from one CUDA graph.
 """
 from .unet import Unet  # noqa: F401
 from .diffusion import GaussianDiffusion, ModelPrediction  # noqa: F401

@@ -117,7 +117,7 @@ def conv_forward(kind: str, srcs: Sequence[torch.Tensor], weight: torch.Tensor, 
     plan, tile = _plan_for(kind, [s.shape[3] for s in srcs], cout, gw, gh)
     n_rows, n_tile = n_tiling(cout, False)
     dev = weight.device
-    packed = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
+    packed = torch.empty(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
     sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
     L.check(L.lib().ccdm_pack_weights(weight.data_ptr(), cout, weight.shape[1], _KIND_TAPS[kind], psched.data_ptr(),
                                       plan.nz, plan.nkb, n_rows, None, 1.0, packed.data_ptr(), _stream()), "pack_weights")
@@ -180,7 +180,7 @@ def conv_dgrad(kind: str, dy: torch.Tensor, weight: torch.Tensor, cins: Sequence
     for cin in cins:
         plan, tile = _plan_for(kind + "_dgrad", (cout,), cin, gw, gh)
         n_rows, n_tile = n_tiling(cin, False)
-        packed = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
+        packed = torch.empty(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
         sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
         L.check(L.lib().ccdm_pack_weights_t(weight.data_ptr(), cout, weight.shape[1], _KIND_TAPS[kind], psched.data_ptr(),
                                             plan.nz, plan.nkb, n_rows, n_off, cin, packed.data_ptr(), _stream()),
@@ -267,15 +267,16 @@ def block_backward(dy: torch.Tensor, z: torch.Tensor, gain: torch.Tensor, scale_
     dev = z.device
     flags = (L.EPI_SILU if silu else 0) | (L.EPI_SS if scale_shift is not None else 0)
     dz = torch.empty_like(z)
-    sums = torch.zeros(3, b, c, dtype=torch.float32, device=dev)
+    zbuf = torch.zeros(3 * b * c + 2 * c, dtype=torch.float32, device=dev)          # one fill: sums | dgain | dbias
+    sums, dgain, dbias = zbuf[:3 * b * c], zbuf[3 * b * c:3 * b * c + c], zbuf[3 * b * c + c:]
     ld = scale_shift.shape[1] if scale_shift is not None else 0
     gm = math.sqrt(c)
     g = gain.reshape(-1)
     L.check(L.lib().ccdm_block_bwd(dy.data_ptr(), z.data_ptr(), dz.data_ptr(), b * h * w, c, h * w, g.data_ptr(), gm,
                                    L.ptr(scale_shift), ld, ss_off, sums.data_ptr(), flags, _stream()), "block_bwd")
-    d_ss = torch.zeros_like(scale_shift) if scale_shift is not None else None
-    dgain = torch.zeros(c, dtype=torch.float32, device=dev)
-    dbias = torch.zeros(c, dtype=torch.float32, device=dev)
+    d_ss = None
+    if scale_shift is not None:             # every element is written when the buffer is exactly [scale | shift]
+        d_ss = torch.empty_like(scale_shift) if (ss_off == 0 and ld == 2 * c) else torch.zeros_like(scale_shift)
     L.check(L.lib().ccdm_block_bwd_finish(sums.data_ptr(), b, c, g.data_ptr(), gm, L.ptr(scale_shift), ld, ss_off,
                                           L.ptr(d_ss), dgain.data_ptr(), dbias.data_ptr(), _stream()), "block_bwd_finish")
     return dz, d_ss, dgain, dbias

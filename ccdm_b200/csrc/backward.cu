@@ -9,19 +9,19 @@ namespace ccdm {
 constexpr int kBwdThreads = 256;
 constexpr int kBwdMaxC = 1024;
 
-template <int kChunks, int kGroup>   // kGroup lanes share one row; each owns kChunks chunks of 8 channels
+template <int kChunks>   // G lanes share one row; each owns kChunks chunks of 8 channels (see row_lane_plan)
 __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
                                                                 uint4* __restrict__ dz, int rows_per_sample,
                                                                 int rows_per_block, int C, const float* __restrict__ gain,
                                                                 float gain_mul, const float* __restrict__ ss, int ss_ld,
                                                                 int ss_off, float* __restrict__ sums, int B,
-                                                                uint32_t flags) {
+                                                                uint32_t flags, int G) {
   __shared__ float acc_s[3][kBwdMaxC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
   const int nchunk = C >> 3;                                       // 8 channels (16 bytes) per chunk
-  constexpr int kRowsPerWarp = 32 / kGroup;
-  const int sub = lane / kGroup, gl = lane % kGroup;
+  const int kRowsPerWarp = 32 / G;
+  const int sub = lane / G, gl = lane - sub * G;
   for (int i = tid; i < 3 * kBwdMaxC; i += kBwdThreads) (&acc_s[0][0])[i] = 0.f;
   __syncthreads();
 
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
   float s1[kChunks][8], s2[kChunks][8], s3[kChunks][8];
 #pragma unroll
   for (int k = 0; k < kChunks; ++k) {
-    const int ch = gl + kGroup * k;
+    const int ch = gl + G * k;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = ch * 8 + j;
@@ -48,20 +48,40 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
   }
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(r0 + rows_per_block, rows_per_sample);
-  for (int rb = r0 + warp * kRowsPerWarp; rb < r1; rb += (kBwdThreads / 32) * kRowsPerWarp) {
+  // software pipeline: the loads of the next row group are issued before the current one is processed
+  const int rstep = (kBwdThreads / 32) * kRowsPerWarp;
+  uint4 zn[kChunks], dn[kChunks];
+  auto fetch = [&](int rb) {
     const int r = rb + sub;
-    const bool live = r < r1;
+    const bool ok = sub < kRowsPerWarp && r < r1;
+    const size_t off = ((size_t)b * rows_per_sample + r) * nchunk;
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      const int ch = gl + G * k;
+      zn[k] = dn[k] = make_uint4(0, 0, 0, 0);
+      if (ok && ch < nchunk) {
+        zn[k] = __ldg(z + off + ch);
+        dn[k] = __ldg(dy + off + ch);
+      }
+    }
+  };
+  fetch(r0 + warp * kRowsPerWarp);
+  for (int rb = r0 + warp * kRowsPerWarp; rb < r1; rb += rstep) {
+    const int r = rb + sub;
+    const bool live = sub < kRowsPerWarp && r < r1;
     const size_t rowoff = ((size_t)b * rows_per_sample + r) * nchunk;
+    uint4 zc[kChunks], dc[kChunks];
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      zc[k] = zn[k];
+      dc[k] = dn[k];
+    }
+    if (rb + rstep < r1) fetch(rb + rstep);
     float zf[kChunks][8], gy[kChunks][8];
     float sq = 0.f;
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
-      const int ch = gl + kGroup * k;
-      uint4 zu = make_uint4(0, 0, 0, 0), du = make_uint4(0, 0, 0, 0);
-      if (live && ch < nchunk) {
-        zu = __ldg(z + rowoff + ch);
-        du = __ldg(dy + rowoff + ch);
-      }
+      const uint4 zu = zc[k], du = dc[k];
       const uint32_t zw[4] = {zu.x, zu.y, zu.z, zu.w}, dw[4] = {du.x, du.y, du.z, du.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -73,8 +93,7 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
         sq = fmaf(zf[k][2 * j + 1], zf[k][2 * j + 1], sq);
       }
     }
-#pragma unroll
-    for (int off = kGroup / 2; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    sq = seg_sum(sq, gl, G, lane);
     const float inv = 1.f / fmaxf(sqrtf(sq), 1e-12f);
     float dot = 0.f;
 #pragma unroll
@@ -96,11 +115,10 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
         gy[k][j] = dzh;
       }
     }
-#pragma unroll
-    for (int off = kGroup / 2; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    dot = seg_sum(dot, gl, G, lane);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
-      const int ch = gl + kGroup * k;
+      const int ch = gl + G * k;
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -113,7 +131,7 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
   }
 #pragma unroll
   for (int k = 0; k < kChunks; ++k) {
-    const int ch = gl + kGroup * k;
+    const int ch = gl + G * k;
     if (ch < nchunk) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -130,26 +148,42 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
   }
 }
 
-__global__ void block_bwd_finish_kernel(const float* __restrict__ sums, int B, int C, const float* __restrict__ gain,
-                                        float gain_mul, const float* __restrict__ ss, int ss_ld, int ss_off,
-                                        float* __restrict__ d_ss, float* __restrict__ dgain, float* __restrict__ dbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float g = gain[c] * gain_mul;
+__global__ void __launch_bounds__(256) block_bwd_finish_kernel(const float* __restrict__ sums, int B, int C,
+                                                               const float* __restrict__ gain, float gain_mul,
+                                                               const float* __restrict__ ss, int ss_ld, int ss_off,
+                                                               float* __restrict__ d_ss, float* __restrict__ dgain,
+                                                               float* __restrict__ dbias) {
+  // thread (b-lane, c): consecutive threads take consecutive channels (coalesced), 8 sample lanes per CTA
+  __shared__ float red[2][8][32];
+  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float dg = 0.f, db = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float s0 = sums[((size_t)0 * B + b) * C + c];
-    const float s1 = sums[((size_t)1 * B + b) * C + c];
-    db += sums[((size_t)2 * B + b) * C + c];
-    const float sc = ss ? ss[(size_t)b * ss_ld + ss_off + c] : 0.f;
-    dg = fmaf(1.f + sc, s0, dg);
-    if (d_ss) {
-      d_ss[(size_t)b * ss_ld + ss_off + c] = g * s0;
-      d_ss[(size_t)b * ss_ld + ss_off + C + c] = s1;
+  if (c < C) {
+    const float g = gain[c] * gain_mul;
+    for (int b = bl; b < B; b += 8) {
+      const float s0 = sums[((size_t)0 * B + b) * C + c];
+      const float s1 = sums[((size_t)1 * B + b) * C + c];
+      db += sums[((size_t)2 * B + b) * C + c];
+      const float sc = ss ? ss[(size_t)b * ss_ld + ss_off + c] : 0.f;
+      dg = fmaf(1.f + sc, s0, dg);
+      if (d_ss) {
+        d_ss[(size_t)b * ss_ld + ss_off + c] = g * s0;
+        d_ss[(size_t)b * ss_ld + ss_off + C + c] = s1;
+      }
     }
   }
-  if (dgain) dgain[c] += gain_mul * dg;
-  if (dbias) dbias[c] += db;
+  red[0][bl][cl] = dg;
+  red[1][bl][cl] = db;
+  __syncthreads();
+  if (bl == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      dg += red[0][i][cl];
+      db += red[1][i][cl];
+    }
+    if (dgain) dgain[c] += gain_mul * dg;
+    if (dbias) dbias[c] += db;
+  }
 }
 
 }  // namespace ccdm
@@ -177,16 +211,16 @@ extern "C" int ccdm_block_bwd(const void* dy, const void* z, void* dz, int64_t r
   per_sample = (rows_per_sample + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)per_sample, (unsigned)B);
   cudaStream_t s = (cudaStream_t)stream;
-#define CCDM_BWD(K, G)                                                                                                  \
-  block_bwd_kernel<K, G><<<grid, kBwdThreads, 0, s>>>((const uint4*)dy, (const uint4*)z, (uint4*)dz, rows_per_sample,   \
-                                                      rows_per_block, C, gain, gain_mul, scale_shift, ss_ld, ss_off,   \
-                                                      sums, B, flags)
-  if (C <= 32) CCDM_BWD(1, 4);
-  else if (C <= 64) CCDM_BWD(1, 8);
-  else if (C <= 128) CCDM_BWD(1, 16);
-  else if (C <= 256) CCDM_BWD(1, 32);
-  else if (C <= 512) CCDM_BWD(2, 32);
-  else CCDM_BWD(4, 32);
+  int kv, G;
+  row_lane_plan(C / 8, 4, &kv, &G);
+#define CCDM_BWD(K)                                                                                                   \
+  block_bwd_kernel<K><<<grid, kBwdThreads, 0, s>>>((const uint4*)dy, (const uint4*)z, (uint4*)dz, rows_per_sample,    \
+                                                   rows_per_block, C, gain, gain_mul, scale_shift, ss_ld, ss_off, sums, \
+                                                   B, flags, G)
+  if (kv == 1) CCDM_BWD(1);
+  else if (kv == 2) CCDM_BWD(2);
+  else if (kv == 3) CCDM_BWD(3);
+  else CCDM_BWD(4);
 #undef CCDM_BWD
   return after_launch("block_bwd_kernel");
 }
@@ -196,7 +230,7 @@ extern "C" int ccdm_block_bwd_finish(const float* sums, int32_t B, int32_t C, co
                                      float* dbias, void* stream) {
   CCDM_REQUIRE(sums && gain && B > 0 && C > 0, CCDM_ERR_BAD_ARG, "block_bwd_finish: bad args");
   CCDM_REQUIRE(!d_ss || scale_shift, CCDM_ERR_BAD_ARG, "block_bwd_finish: d_ss without scale_shift");
-  block_bwd_finish_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, B, C, gain, gain_mul, scale_shift, ss_ld,
+  block_bwd_finish_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(sums, B, C, gain, gain_mul, scale_shift, ss_ld,
                                                                             ss_off, d_ss, dgain, dbias);
   return after_launch("block_bwd_finish_kernel");
 }

@@ -126,69 +126,112 @@ __global__ void linattn_fold_kernel(const float* __restrict__ w_out, const float
 // bottleneck of the dim-72 UTKFace-64 model) or whose tiny pixel count wants the GEMM split over output channels
 // (4x4 levels): z = conv + bias (bf16) in, out = [silu]( z/|z| * g*sqrt(C) * (1+scale) + shift ) [+ resid].
 // One warp per pixel row, 16-byte loads; HBM-bound (reads z [+ resid], writes out).
-__global__ void __launch_bounds__(256) rmsnorm_act_kernel(const __nv_bfloat16* __restrict__ z,
-                                                          __nv_bfloat16* __restrict__ out, long long rows, int C,
-                                                          int rows_per_sample, const float* __restrict__ gain,
-                                                          float gain_mul, const float* __restrict__ ss, int ss_ld,
-                                                          int ss_off, const __nv_bfloat16* __restrict__ resid,
-                                                          float* __restrict__ out_rowss, uint32_t flags) {
-  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const int nvec = C >> 3;                                   // 8 channels per 16-byte vector
-  const uint4* zr = reinterpret_cast<const uint4*>(z + row * C);
-  constexpr int kMaxVec = 3;                                 // C <= 768
-  float v[kMaxVec][8];
-  float ssq = 0.f;
+// Lane mapping: a row of C channels is nchunk = C/8 16-byte vectors; G = ceil(nchunk / kV) lanes share a row, each
+// owning kV vectors, so a warp covers 32/G rows per iteration (C = 64 -> 4 rows, C = 72 -> 3 rows of 9 lanes).  All
+// rows of a CTA belong to one sample (blockIdx.y), so gain * (1 + scale) and shift live in registers.
+template <int kV>
+__global__ void __launch_bounds__(256) rmsnorm_act_kernel(const uint4* __restrict__ z, uint4* __restrict__ out,
+                                                          int rows_per_sample, int rows_per_block, int C, int G,
+                                                          const float* __restrict__ gain, float gain_mul,
+                                                          const float* __restrict__ ss, int ss_ld, int ss_off,
+                                                          const uint4* __restrict__ resid, float* __restrict__ out_rowss,
+                                                          uint32_t flags) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int nchunk = C >> 3;
+  const int rpw = 32 / G;                                          // rows per warp iteration
+  const int sub = lane / G, gl = lane - sub * G;
+  float a[kV][8], sh[kV][8];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const uint4 u = __ldg(zr + vi);
-      v[i][0] = bf16_lo(u.x); v[i][1] = bf16_hi(u.x); v[i][2] = bf16_lo(u.y); v[i][3] = bf16_hi(u.y);
-      v[i][4] = bf16_lo(u.z); v[i][5] = bf16_hi(u.z); v[i][6] = bf16_lo(u.w); v[i][7] = bf16_hi(u.w);
+  for (int k = 0; k < kV; ++k) {
+    const int ch = gl + G * k;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ssq = fmaf(v[i][j], v[i][j], ssq);
+    for (int j = 0; j < 8; ++j) {
+      const int c = ch * 8 + j;
+      float g = 0.f, sc = 0.f, sf = 0.f;
+      if (ch < nchunk) {
+        g = gain[c] * gain_mul;
+        if (flags & CCDM_EPI_SS) {
+          sc = ss[(size_t)b * ss_ld + ss_off + c];
+          sf = ss[(size_t)b * ss_ld + ss_off + C + c];
+        }
+      }
+      a[k][j] = g * (1.f + sc);
+      sh[k][j] = sf;
     }
   }
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, rows_per_sample);
+  // software pipeline: the loads of the next row group are issued before the current one is processed
+  const int rstep = 8 * rpw;
+  uint4 zn[kV], rn[kV];
+  auto fetch = [&](int rb) {
+    const int r = rb + sub;
+    const bool ok = sub < rpw && r < r1;
+    const size_t off = ((size_t)b * rows_per_sample + r) * nchunk;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, off);
-  const float inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
-  const long long b = row / rows_per_sample;
-  const float* ssrow = (flags & CCDM_EPI_SS) ? ss + b * ss_ld + ss_off : nullptr;
-  float out_ss = 0.f;
+    for (int k = 0; k < kV; ++k) {
+      const int ch = gl + G * k;
+      zn[k] = rn[k] = make_uint4(0, 0, 0, 0);
+      if (ok && ch < nchunk) {
+        zn[k] = __ldg(z + off + ch);
+        if (flags & CCDM_EPI_RESID) rn[k] = __ldg(resid + off + ch);
+      }
+    }
+  };
+  fetch(r0 + warp * rpw);
+  for (int rb = r0 + warp * rpw; rb < r1; rb += rstep) {
+    const int r = rb + sub;
+    const bool live = sub < rpw && r < r1;
+    const size_t rowoff = ((size_t)b * rows_per_sample + r) * nchunk;
+    float v[kV][8];
+    uint4 ru[kV], zc[kV];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+    for (int k = 0; k < kV; ++k) {
+      zc[k] = zn[k];
+      ru[k] = rn[k];
+    }
+    if (rb + rstep < r1) fetch(rb + rstep);
+    float ssq = 0.f;
+#pragma unroll
+    for (int k = 0; k < kV; ++k) {
+      const int ch = gl + G * k;
+      const uint4 u = zc[k];
+      v[k][0] = bf16_lo(u.x); v[k][1] = bf16_hi(u.x); v[k][2] = bf16_lo(u.y); v[k][3] = bf16_hi(u.y);
+      v[k][4] = bf16_lo(u.z); v[k][5] = bf16_hi(u.z); v[k][6] = bf16_lo(u.w); v[k][7] = bf16_hi(u.w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ssq = fmaf(v[k][j], v[k][j], ssq);
+    }
+    ssq = seg_sum(ssq, gl, G, lane);
+    const float inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
+    float out_ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kV; ++k) {
+      const int ch = gl + G * k;
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int c = vi * 8 + j;
-        float t = v[i][j] * inv * (gain[c] * gain_mul);
-        if (ssrow) t = fmaf(t, 1.f + ssrow[c], ssrow[C + c]);
+        float t = fmaf(v[k][j] * inv, a[k][j], sh[k][j]);
         if (flags & CCDM_EPI_SILU) t = t / (1.f + __expf(-t));
         o[j] = t;
       }
       if (flags & CCDM_EPI_RESID) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(resid + row * C) + vi);
-        o[0] += bf16_lo(u.x); o[1] += bf16_hi(u.x); o[2] += bf16_lo(u.y); o[3] += bf16_hi(u.y);
-        o[4] += bf16_lo(u.z); o[5] += bf16_hi(u.z); o[6] += bf16_lo(u.w); o[7] += bf16_hi(u.w);
+        o[0] += bf16_lo(ru[k].x); o[1] += bf16_hi(ru[k].x); o[2] += bf16_lo(ru[k].y); o[3] += bf16_hi(ru[k].y);
+        o[4] += bf16_lo(ru[k].z); o[5] += bf16_hi(ru[k].z); o[6] += bf16_lo(ru[k].w); o[7] += bf16_hi(ru[k].w);
       }
       uint4 w;
       w.x = pack_bf16(o[0], o[1]); w.y = pack_bf16(o[2], o[3]); w.z = pack_bf16(o[4], o[5]); w.w = pack_bf16(o[6], o[7]);
-      reinterpret_cast<uint4*>(out + row * C)[vi] = w;
+      if (live && ch < nchunk) out[rowoff + ch] = w;
       if (flags & CCDM_EPI_SUMSQ_OUT) {
         const float a0 = bf16_lo(w.x), a1 = bf16_hi(w.x), a2 = bf16_lo(w.y), a3 = bf16_hi(w.y);
         const float a4 = bf16_lo(w.z), a5 = bf16_hi(w.z), a6 = bf16_lo(w.w), a7 = bf16_hi(w.w);
-        out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+        if (ch < nchunk) out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
       }
     }
-  }
-  if (flags & CCDM_EPI_SUMSQ_OUT) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) out_ss += __shfl_xor_sync(0xffffffffu, out_ss, off);
-    if (lane == 0) out_rowss[row] = out_ss;
+    if (flags & CCDM_EPI_SUMSQ_OUT) {
+      out_ss = seg_sum(out_ss, gl, G, lane);
+      if (live && gl == 0) out_rowss[(size_t)b * rows_per_sample + r] = out_ss;
+    }
   }
 }
 
@@ -405,9 +448,27 @@ extern "C" int ccdm_rmsnorm_act(const void* z, void* out, int64_t rows, int32_t 
   CCDM_REQUIRE(!(flags & CCDM_EPI_SS) || scale_shift, CCDM_ERR_BAD_ARG, "rmsnorm_act: scale/shift pointer");
   CCDM_REQUIRE(!(flags & CCDM_EPI_RESID) || resid, CCDM_ERR_BAD_ARG, "rmsnorm_act: resid pointer");
   CCDM_REQUIRE(!(flags & CCDM_EPI_SUMSQ_OUT) || out_rowss, CCDM_ERR_BAD_ARG, "rmsnorm_act: out_rowss pointer");
-  rmsnorm_act_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)z, (__nv_bfloat16*)out, rows, C, rows_per_sample, gain, gain_mul, scale_shift, ss_ld, ss_off,
-      (const __nv_bfloat16*)resid, out_rowss, flags);
+  CCDM_REQUIRE(rows % rows_per_sample == 0, CCDM_ERR_BAD_ARG, "rmsnorm_act: rows=%lld rows_per_sample=%d",
+               (long long)rows, rows_per_sample);
+  const int B = (int)(rows / rows_per_sample);
+  CCDM_REQUIRE(B <= 65535, CCDM_ERR_UNSUPPORTED_SHAPE, "rmsnorm_act: %d samples", B);
+  int kv, G;
+  row_lane_plan(C / 8, 3, &kv, &G);
+  int per_sample = (num_sms() * 8 + B - 1) / B;                    // a few waves of CTAs, >= 32 rows each
+  const int max_split = (rows_per_sample + 31) / 32;
+  if (per_sample > max_split) per_sample = max_split;
+  if (per_sample < 1) per_sample = 1;
+  const int rows_per_block = (rows_per_sample + per_sample - 1) / per_sample;
+  per_sample = (rows_per_sample + rows_per_block - 1) / rows_per_block;
+  dim3 grid((unsigned)per_sample, (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CCDM_RMS(K)                                                                                                   \
+  rmsnorm_act_kernel<K><<<grid, 256, 0, st>>>((const uint4*)z, (uint4*)out, rows_per_sample, rows_per_block, C, G, gain, \
+                                              gain_mul, scale_shift, ss_ld, ss_off, (const uint4*)resid, out_rowss, flags)
+  if (kv == 1) CCDM_RMS(1);
+  else if (kv == 2) CCDM_RMS(2);
+  else CCDM_RMS(3);
+#undef CCDM_RMS
   return after_launch("rmsnorm_act_kernel");
 }
 

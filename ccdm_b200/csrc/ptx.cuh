@@ -181,6 +181,15 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
+__device__ __forceinline__ float seg_sum(float v, int gl, int G, int lane) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float o = __shfl_down_sync(0xffffffffu, v, off);
+    if (gl + off < G) v += o;
+  }
+  return __shfl_sync(0xffffffffu, v, lane - gl);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

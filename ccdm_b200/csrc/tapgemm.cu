@@ -600,6 +600,7 @@ static int launch_variant(uint32_t flags, bool tma, dim3 grid, size_t smem_bytes
     CCDM_VARIANT(0x02u)   // rowscale                                       (bottleneck-attention qkv)
     CCDM_VARIANT(0x25u)   // bias | rmsnorm | resid                         (linear-attention to_out)
     CCDM_VARIANT(0x21u)   // bias | resid                                   (bottleneck-attention to_out)
+    CCDM_VARIANT(0x00u)   // plain                                          (data gradients, per-sample context products)
     default:
       break;
   }

@@ -166,26 +166,31 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   }
 }
 
-// dW[n][ci][t] (+)= gain(ci) * sum over packed blocks that hold (ci, t) of packed[z][n][kb*64 + ci - cin0]
+// dW[n][cin0+j][t] += gain * packed[z][n][kb*64 + j] for every tap t in the block's tapmask (scatter; dW zeroed or
+// accumulated by the caller -- the folded taps of the nearest-2x convolution land on the same element from several
+// blocks, hence atomics)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ dw, int cout, int cin_total,
-                                    int ntaps, const int4* __restrict__ psched, int nz, int nkb, int n_rows,
-                                    const float* __restrict__ cin_gain, float gain_mul, int accumulate, long long total) {
+                                    int ntaps, const int4* __restrict__ psched, int nkb, int n_rows,
+                                    const float* __restrict__ cin_gain, float gain_mul, long long total) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(idx % ntaps);
-    const long long r = idx / ntaps;
-    const int ci = (int)(r % cin_total);
-    const int n = (int)(r / cin_total);
-    float acc = 0.f;
-    for (int zk = 0; zk < nz * nkb; ++zk) {
-      const int4 e = __ldg(&psched[zk]);
-      if (ci >= e.x && ci < e.x + e.y && ((unsigned)e.z >> t & 1u)) {
-        const int zz = zk / nkb, kb = zk - zz * nkb;
-        acc += packed[((size_t)zz * n_rows + n) * ((size_t)nkb * 64) + (size_t)kb * 64 + (ci - e.x)];
-      }
+    const int j = (int)(idx & 63);
+    const long long t = idx >> 6;
+    const int kb = (int)(t % nkb);
+    const long long zn = t / nkb;
+    const int n = (int)(zn % n_rows);
+    const int z = (int)(zn / n_rows);
+    const int4 e = __ldg(&psched[z * nkb + kb]);
+    if (n >= cout || j >= e.y) continue;
+    const int ci = e.x + j;
+    const float v = packed[idx] * gain_mul * (cin_gain ? cin_gain[ci] : 1.f);
+    float* dst = dw + ((long long)n * cin_total + ci) * ntaps;
+    unsigned mask = (unsigned)e.z;
+    while (mask) {
+      const int tp = __ffs(mask) - 1;
+      mask &= mask - 1;
+      atomicAdd(dst + tp, v);
     }
-    acc *= gain_mul * (cin_gain ? cin_gain[ci] : 1.f);
-    dw[idx] = accumulate ? dw[idx] + acc : acc;
   }
 }
 
@@ -297,12 +302,17 @@ extern "C" int ccdm_unpack_wgrad(const float* packed, float* dw, int32_t cout, i
   CCDM_REQUIRE(packed && dw && psched, CCDM_ERR_BAD_ARG, "unpack_wgrad: null pointer");
   CCDM_REQUIRE(cout > 0 && cin_total > 0 && ntaps > 0 && ntaps <= 32 && nz > 0 && nkb > 0 && n_rows >= cout,
                CCDM_ERR_BAD_ARG, "unpack_wgrad: bad sizes");
-  const long long total = (long long)cout * cin_total * ntaps;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)cout * cin_total * ntaps * sizeof(float), s);
+    if (e != cudaSuccess) return cuda_fail(e, "unpack_wgrad: cudaMemsetAsync");
+  }
+  const long long total = (long long)nz * n_rows * nkb * 64;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_wgrad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(packed, dw, cout, cin_total, ntaps,
-                                                                         reinterpret_cast<const int4*>(psched), nz, nkb,
-                                                                         n_rows, cin_gain, gain_mul, accumulate, total);
+  unpack_wgrad_kernel<<<(unsigned)blocks, 256, 0, s>>>(packed, dw, cout, cin_total, ntaps,
+                                                       reinterpret_cast<const int4*>(psched), nkb, n_rows, cin_gain,
+                                                       gain_mul, total);
   return after_launch("unpack_wgrad_kernel");
 }
 

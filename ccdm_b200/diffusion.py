@@ -422,10 +422,15 @@ class GaussianDiffusion(nn.Module):
             cov = self.convert_y_to_cov(labels).contiguous().float()
             if not given_noise:
                 noise = torch.randn_like(x_start)
-                null_idx = torch.where(keep == False)[0]                       # noqa: E712  (host sync, as in the reference)
-                if len(null_idx) > 0:
-                    noise2 = torch.empty_like(x_start)
-                    noise2[null_idx] = torch.randn_like(x_start[null_idx])
+                if getattr(self, "graph_safe_rng", False):
+                    # CUDA-graph capture (train_graph.py): no host round trip; null rows take their N(0,1) draw from a
+                    # full-batch tensor (same distribution, different RNG consumption than the reference)
+                    noise2 = torch.randn_like(x_start)
+                else:
+                    null_idx = torch.where(keep == False)[0]                   # noqa: E712  (host sync, as in the reference)
+                    if len(null_idx) > 0:
+                        noise2 = torch.empty_like(x_start)
+                        noise2[null_idx] = torch.randn_like(x_start[null_idx])
         elif not given_noise:
             noise = torch.randn_like(x_start)
         x0 = x_start.contiguous().float()

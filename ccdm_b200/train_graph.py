@@ -1,0 +1,76 @@
+"""One whole optimizer step -- q_sample, UNet forward, vicinal loss, backward, gradient all-reduce, clip, Adam --
+captured once into a CUDA graph and replayed (CCDM_unified/trainer.py:557-740 is the loop it replaces).
+
+The eager training path (ccdm_b200/train.py) issues ~1000 small launches per step from Python; at B200 speeds the step
+is then bound by the host.  Captured, the step costs one graph launch.  Requirements that make the capture legal:
+
+* static shapes: the batch is copied into fixed device buffers before every replay;
+* no host synchronisation inside the step: ``GaussianDiffusion.graph_safe_rng`` draws the null-row noise for the whole
+  batch instead of first asking the host how many null rows there are (diffusion.py:532-536 does a ``torch.where`` +
+  ``len``); the noise is then distributed identically but consumes the RNG stream differently from the reference;
+* the optimizer keeps its step count on the device (``capturable=True``).
+
+Random draws (timesteps, masks, noise) use PyTorch's graph-safe Philox generator, so every replay sees fresh numbers.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import dist as ccdm_dist
+
+
+class GraphedTrainStep:
+    def __init__(self, diffusion, optimizer: torch.optim.Optimizer, images: torch.Tensor, labels: torch.Tensor,
+                 labels_emb: torch.Tensor, *, loss_kwargs: Optional[dict] = None, max_grad_norm: Optional[float] = 1.0,
+                 warmup: int = 3):
+        """``images`` / ``labels`` / ``labels_emb`` are example batches (their shapes are frozen)."""
+        self.gd, self.opt = diffusion, optimizer
+        self.kw = dict(loss_kwargs or {})
+        self.max_grad_norm = max_grad_norm
+        self.params = [p for p in diffusion.parameters() if p.requires_grad]
+        for grp in optimizer.param_groups:
+            grp["capturable"] = True
+            if "foreach" in grp and grp["foreach"] is None:
+                grp["foreach"] = True
+        for st in optimizer.state.values():
+            if "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
+                st["step"] = st["step"].to(images.device)
+        self.images = images.detach().clone()
+        self.labels = labels.detach().clone()
+        self.labels_emb = labels_emb.detach().clone()
+        self.weights = torch.ones(images.shape[0], device=images.device)
+        self.loss = torch.zeros((), device=images.device)
+        self.graph = torch.cuda.CUDAGraph()
+        diffusion.graph_safe_rng = True
+        diffusion.train()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):      # allocator, schedule tables, optimizer state, autograd threads
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        torch.cuda.synchronize()
+
+    def _step(self):
+        loss = self.gd(self.images, labels_emb=self.labels_emb, labels=self.labels, vicinal_weights=self.weights, **self.kw)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        ccdm_dist.all_reduce_gradients(self.params)
+        if self.max_grad_norm is not None:
+            torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm)
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor, labels_emb: torch.Tensor) -> torch.Tensor:
+        """Runs one optimizer step on the given batch; returns the (device, 0-dim) loss of that step."""
+        self.images.copy_(images, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        self.labels_emb.copy_(labels_emb, non_blocking=True)
+        self.graph.replay()
+        return self.loss

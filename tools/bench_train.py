@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--breakdown", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="capture the whole step into a CUDA graph (train_graph.py)")
     a = ap.parse_args()
     rank, local, world = D.env_world()
     torch.cuda.set_device(local)
@@ -80,6 +81,10 @@ def main():
             ev[3].record()
         return loss
 
+    if a.graph:
+        from ccdm_b200.train_graph import GraphedTrainStep
+        gstep = GraphedTrainStep(gd, opt, img, labels, emb, loss_kwargs=dict(vicinity_type="hv", kappa=0.05))
+        step = lambda ev=None: gstep(img, labels, emb)
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
@@ -89,7 +94,7 @@ def main():
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(a.steps)]
     e0.record()
     for k in range(a.steps):
-        loss = step(evs[k] if a.breakdown else None)
+        loss = step(evs[k] if (a.breakdown and not a.graph) else None)
     e1.record()
     torch.cuda.synchronize()
     D.barrier()
@@ -98,12 +103,12 @@ def main():
     if rank == 0:
         peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
         tflops = 3 * m["gflop"] * B * world / ms                         # GFLOP / ms = TFLOP/s
-        rec = dict(metric="train step", model=a.model, per_gpu_batch=B, n_gpus=world, ms_per_step=round(ms, 2),
+        rec = dict(metric="train step", mode="cuda-graph" if a.graph else "eager", model=a.model, per_gpu_batch=B, n_gpus=world, ms_per_step=round(ms, 2),
                    images_per_s=round(B * world / ms * 1e3, 1), algorithmic_tflops=round(tflops, 1),
                    frac_of_sustained_bf16_peak=round(tflops / world / peaks["bf16_tflops_sustained"], 3),
                    kernel_launches_per_step=int(launches), loss=round(loss.item(), 5),
                    peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
-        if a.breakdown:
+        if a.breakdown and not a.graph:
             f = sum(e[0].elapsed_time(e[1]) for e in evs) / a.steps
             b = sum(e[1].elapsed_time(e[2]) for e in evs) / a.steps
             o = sum(e[2].elapsed_time(e[3]) for e in evs) / a.steps
