@@ -132,7 +132,7 @@ def _oracle_grads(spec, sd, x, t, emb, keep_mask, p_drop, dout):
     return y.detach(), {k: v.grad for k, v in sd_o.items() if isinstance(v, torch.Tensor) and v.requires_grad}
 
 
-@pytest.mark.parametrize("spec_name,seed", [("tiny", 1), ("rc_small", 4), ("cell", 3), ("wide", 5)])
+@pytest.mark.parametrize("spec_name,seed", [("tiny", 1), ("rc_small", 4), ("cell", 3), ("wide", 5), ("uk64", 6)])
 def test_unet_backward_vs_oracle(spec_name, seed):
     spec = SPECS[spec_name]
     net, sd = make_net(spec, seed, p_drop=0.3)

@@ -98,7 +98,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     D.barrier()
-    ms = D.max_over_ranks(e0.elapsed_time(e1) / a.steps)
+    ms = D.max_over_ranks(e0.elapsed_time(e1) / a.steps, device=torch.device("cuda", local))
     launches = (lib.ccdm_launch_count() - l0) // a.steps
     if rank == 0:
         peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
