@@ -110,6 +110,8 @@ SIGNATURES = {
     "ccdm_attention_small_bwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "ccdm_head_conv1_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "ccdm_stem_unpack_wgrad": (C.c_int, [vp, vp, i32, i32, i32, vp]),
+    "ccdm_fused_adam": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, f32, f32, vp]),
+    "ccdm_multi_lerp": (C.c_int, [vp, vp, vp, i32, vp, vp]),
 }
 
 _lib = None

@@ -18,11 +18,13 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
                                                                 uint32_t flags, int G) {
   __shared__ float acc_s[3][kBwdMaxC];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y;
   const int nchunk = C >> 3;                                       // 8 channels (16 bytes) per chunk
   const int kRowsPerWarp = 32 / G;
   const int sub = lane / G, gl = lane - sub * G;
-  for (int i = tid; i < 3 * kBwdMaxC; i += kBwdThreads) (&acc_s[0][0])[i] = 0.f;
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, rows_per_sample);
+  for (int i = tid; i < 3 * C; i += kBwdThreads) (&acc_s[0][0])[(i / C) * kBwdMaxC + (i % C)] = 0.f;
   __syncthreads();
 
   float a[kChunks][8], sh[kChunks][8];
@@ -30,27 +32,24 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
 #pragma unroll
   for (int k = 0; k < kChunks; ++k) {
     const int ch = gl + G * k;
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ch < nchunk) {
+      load8(gain + ch * 8, g);
+      if (flags & CCDM_EPI_SS) {
+        load8(ss + (size_t)b * ss_ld + ss_off + ch * 8, sc);
+        load8(ss + (size_t)b * ss_ld + ss_off + C + ch * 8, sf);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = ch * 8 + j;
-      float sc = 0.f, sf = 0.f, g = 0.f;
-      if (ch < nchunk) {
-        g = gain[c] * gain_mul;
-        if (flags & CCDM_EPI_SS) {
-          sc = ss[(size_t)b * ss_ld + ss_off + c];
-          sf = ss[(size_t)b * ss_ld + ss_off + C + c];
-        }
-      }
-      a[k][j] = g * (1.f + sc);
-      sh[k][j] = sf;
+      a[k][j] = g[j] * gain_mul * (1.f + sc[j]);
+      sh[k][j] = sf[j];
       s1[k][j] = s2[k][j] = s3[k][j] = 0.f;
     }
   }
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(r0 + rows_per_block, rows_per_sample);
   // software pipeline: the loads of the next row group are issued before the current one is processed
   const int rstep = (kBwdThreads / 32) * kRowsPerWarp;
-  uint4 zn[kChunks], dn[kChunks];
+  uint4 zn[kChunks], dn[kChunks];                                 // next row group, loaded one iteration ahead
   auto fetch = [&](int rb) {
     const int r = rb + sub;
     const bool ok = sub < kRowsPerWarp && r < r1;
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
       }
     }
     sq = seg_sum(sq, gl, G, lane);
-    const float inv = 1.f / fmaxf(sqrtf(sq), 1e-12f);
+    const float inv = rsqrtf(fmaxf(sq, 1e-24f));                   // 1 / max(|z|, 1e-12)
     float dot = 0.f;
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
@@ -104,7 +103,7 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
         float du = gy[k][j];
         if (flags & CCDM_EPI_SILU) {
           const float u = fmaf(zh, a[k][j], sh[k][j]);
-          const float sig = 1.f / (1.f + __expf(-u));
+          const float sig = sigmoid_fast(u);
           du *= sig * fmaf(u, 1.f - sig, 1.f);
         }
         s1[k][j] = fmaf(du, zh, s1[k][j]);
@@ -201,18 +200,18 @@ extern "C" int ccdm_block_bwd(const void* dy, const void* z, void* dz, int64_t r
   CCDM_REQUIRE(!(flags & CCDM_EPI_SS) || scale_shift, CCDM_ERR_BAD_ARG, "block_bwd: scale/shift flag without pointer");
   CCDM_REQUIRE((flags & ~(CCDM_EPI_SS | CCDM_EPI_SILU)) == 0, CCDM_ERR_BAD_ARG, "block_bwd: flags 0x%x", flags);
   const int B = (int)(rows / rows_per_sample);
+  cudaStream_t s = (cudaStream_t)stream;
+  int kv, G;
+  row_lane_plan(C / 8, 4, &kv, &G);
   CCDM_REQUIRE(B <= 65535, CCDM_ERR_UNSUPPORTED_SHAPE, "block_bwd: %d samples", B);
-  // enough CTAs for a few waves, at least 8 rows per warp
-  int per_sample = (num_sms() * 6 + B - 1) / B;
+  // a few CTAs per SM, slabs of >= 64 rows of one sample each
+  int per_sample = (num_sms() * 3 + B - 1) / B;
   const int max_split = (rows_per_sample + 63) / 64;
   if (per_sample > max_split) per_sample = max_split;
   if (per_sample < 1) per_sample = 1;
   const int rows_per_block = (rows_per_sample + per_sample - 1) / per_sample;
   per_sample = (rows_per_sample + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)per_sample, (unsigned)B);
-  cudaStream_t s = (cudaStream_t)stream;
-  int kv, G;
-  row_lane_plan(C / 8, 4, &kv, &G);
 #define CCDM_BWD(K)                                                                                                   \
   block_bwd_kernel<K><<<grid, kBwdThreads, 0, s>>>((const uint4*)dy, (const uint4*)z, (uint4*)dz, rows_per_sample,    \
                                                    rows_per_block, C, gain, gain_mul, scale_shift, ss_ld, ss_off, sums, \

@@ -131,106 +131,111 @@ __global__ void linattn_fold_kernel(const float* __restrict__ w_out, const float
 // rows of a CTA belong to one sample (blockIdx.y), so gain * (1 + scale) and shift live in registers.
 template <int kV>
 __global__ void __launch_bounds__(256) rmsnorm_act_kernel(const uint4* __restrict__ z, uint4* __restrict__ out,
-                                                          int rows_per_sample, int rows_per_block, int C, int G,
-                                                          const float* __restrict__ gain, float gain_mul,
-                                                          const float* __restrict__ ss, int ss_ld, int ss_off,
-                                                          const uint4* __restrict__ resid, float* __restrict__ out_rowss,
-                                                          uint32_t flags) {
+                                                          int rows_per_sample, int rows_per_item, int items_per_sample,
+                                                          int n_items, int C, int G, const float* __restrict__ gain,
+                                                          float gain_mul, const float* __restrict__ ss, int ss_ld,
+                                                          int ss_off, const uint4* __restrict__ resid,
+                                                          float* __restrict__ out_rowss, uint32_t flags) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y;
   const int nchunk = C >> 3;
   const int rpw = 32 / G;                                          // rows per warp iteration
   const int sub = lane / G, gl = lane - sub * G;
-  float a[kV][8], sh[kV][8];
+  const int rstep = 8 * rpw;
+  // persistent CTAs: work item = (sample, slab of rows); the grid is one resident wave
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = item / items_per_sample;
+    const int r0 = (item - b * items_per_sample) * rows_per_item;
+    const int r1 = min(r0 + rows_per_item, rows_per_sample);
+    float2 a[kV][4], sh[kV][4];
 #pragma unroll
-  for (int k = 0; k < kV; ++k) {
-    const int ch = gl + G * k;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = ch * 8 + j;
-      float g = 0.f, sc = 0.f, sf = 0.f;
+    for (int k = 0; k < kV; ++k) {
+      const int ch = gl + G * k;
+      float g[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       if (ch < nchunk) {
-        g = gain[c] * gain_mul;
+        load8(gain + ch * 8, g);
         if (flags & CCDM_EPI_SS) {
-          sc = ss[(size_t)b * ss_ld + ss_off + c];
-          sf = ss[(size_t)b * ss_ld + ss_off + C + c];
+          load8(ss + (size_t)b * ss_ld + ss_off + ch * 8, sc);
+          load8(ss + (size_t)b * ss_ld + ss_off + C + ch * 8, sf);
         }
       }
-      a[k][j] = g * (1.f + sc);
-      sh[k][j] = sf;
-    }
-  }
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(r0 + rows_per_block, rows_per_sample);
-  // software pipeline: the loads of the next row group are issued before the current one is processed
-  const int rstep = 8 * rpw;
-  uint4 zn[kV], rn[kV];
-  auto fetch = [&](int rb) {
-    const int r = rb + sub;
-    const bool ok = sub < rpw && r < r1;
-    const size_t off = ((size_t)b * rows_per_sample + r) * nchunk;
 #pragma unroll
-    for (int k = 0; k < kV; ++k) {
-      const int ch = gl + G * k;
-      zn[k] = rn[k] = make_uint4(0, 0, 0, 0);
-      if (ok && ch < nchunk) {
-        zn[k] = __ldg(z + off + ch);
-        if (flags & CCDM_EPI_RESID) rn[k] = __ldg(resid + off + ch);
+      for (int j = 0; j < 4; ++j) {
+        a[k][j] = make_float2(g[2 * j] * gain_mul * (1.f + sc[2 * j]), g[2 * j + 1] * gain_mul * (1.f + sc[2 * j + 1]));
+        sh[k][j] = make_float2(sf[2 * j], sf[2 * j + 1]);
       }
     }
-  };
-  fetch(r0 + warp * rpw);
-  for (int rb = r0 + warp * rpw; rb < r1; rb += rstep) {
-    const int r = rb + sub;
-    const bool live = sub < rpw && r < r1;
-    const size_t rowoff = ((size_t)b * rows_per_sample + r) * nchunk;
-    float v[kV][8];
-    uint4 ru[kV], zc[kV];
+    uint4 zn[kV], rn[kV];                                          // next row group, loaded one iteration ahead
+    auto fetch = [&](int rb) {
+      const int r = rb + sub;
+      const bool ok = sub < rpw && r < r1;
+      const size_t off = ((size_t)b * rows_per_sample + r) * nchunk;
 #pragma unroll
-    for (int k = 0; k < kV; ++k) {
-      zc[k] = zn[k];
-      ru[k] = rn[k];
-    }
-    if (rb + rstep < r1) fetch(rb + rstep);
-    float ssq = 0.f;
-#pragma unroll
-    for (int k = 0; k < kV; ++k) {
-      const int ch = gl + G * k;
-      const uint4 u = zc[k];
-      v[k][0] = bf16_lo(u.x); v[k][1] = bf16_hi(u.x); v[k][2] = bf16_lo(u.y); v[k][3] = bf16_hi(u.y);
-      v[k][4] = bf16_lo(u.z); v[k][5] = bf16_hi(u.z); v[k][6] = bf16_lo(u.w); v[k][7] = bf16_hi(u.w);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ssq = fmaf(v[k][j], v[k][j], ssq);
-    }
-    ssq = seg_sum(ssq, gl, G, lane);
-    const float inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
-    float out_ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < kV; ++k) {
-      const int ch = gl + G * k;
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = fmaf(v[k][j] * inv, a[k][j], sh[k][j]);
-        if (flags & CCDM_EPI_SILU) t = t / (1.f + __expf(-t));
-        o[j] = t;
+      for (int k = 0; k < kV; ++k) {
+        const int ch = gl + G * k;
+        zn[k] = rn[k] = make_uint4(0, 0, 0, 0);
+        if (ok && ch < nchunk) {
+          zn[k] = __ldg(z + off + ch);
+          if (flags & CCDM_EPI_RESID) rn[k] = __ldg(resid + off + ch);
+        }
       }
-      if (flags & CCDM_EPI_RESID) {
-        o[0] += bf16_lo(ru[k].x); o[1] += bf16_hi(ru[k].x); o[2] += bf16_lo(ru[k].y); o[3] += bf16_hi(ru[k].y);
-        o[4] += bf16_lo(ru[k].z); o[5] += bf16_hi(ru[k].z); o[6] += bf16_lo(ru[k].w); o[7] += bf16_hi(ru[k].w);
+    };
+    fetch(r0 + warp * rpw);
+    for (int rb = r0 + warp * rpw; rb < r1; rb += rstep) {
+      const int r = rb + sub;
+      const bool live = sub < rpw && r < r1;
+      const size_t rowoff = ((size_t)b * rows_per_sample + r) * nchunk;
+      float2 v[kV][4];
+      uint4 ru[kV];
+      float2 sq2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kV; ++k) {
+        const uint4 u = zn[k];
+        ru[k] = rn[k];
+        v[k][0] = make_float2(bf16_lo(u.x), bf16_hi(u.x));
+        v[k][1] = make_float2(bf16_lo(u.y), bf16_hi(u.y));
+        v[k][2] = make_float2(bf16_lo(u.z), bf16_hi(u.z));
+        v[k][3] = make_float2(bf16_lo(u.w), bf16_hi(u.w));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sq2 = __ffma2_rn(v[k][j], v[k][j], sq2);
       }
-      uint4 w;
-      w.x = pack_bf16(o[0], o[1]); w.y = pack_bf16(o[2], o[3]); w.z = pack_bf16(o[4], o[5]); w.w = pack_bf16(o[6], o[7]);
-      if (live && ch < nchunk) out[rowoff + ch] = w;
+      if (rb + rstep < r1) fetch(rb + rstep);
+      const float ssq = seg_sum(sq2.x + sq2.y, gl, G, lane);
+      const float inv = rsqrtf(fmaxf(ssq, 1e-24f));                // 1 / max(|z|, 1e-12)
+      const float2 inv2 = make_float2(inv, inv);
+      float out_ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < kV; ++k) {
+        const int ch = gl + G * k;
+        float2 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 t = __ffma2_rn(__fmul2_rn(v[k][j], inv2), a[k][j], sh[k][j]);
+          if (flags & CCDM_EPI_SILU) {                             // t * sigmoid(t) = h + h * tanh(h), h = t / 2
+            const float2 h = __fmul2_rn(t, make_float2(0.5f, 0.5f));
+            t = __ffma2_rn(h, make_float2(tanh_fast(h.x), tanh_fast(h.y)), h);
+          }
+          o[j] = t;
+        }
+        if (flags & CCDM_EPI_RESID) {
+          o[0] = __fadd2_rn(o[0], make_float2(bf16_lo(ru[k].x), bf16_hi(ru[k].x)));
+          o[1] = __fadd2_rn(o[1], make_float2(bf16_lo(ru[k].y), bf16_hi(ru[k].y)));
+          o[2] = __fadd2_rn(o[2], make_float2(bf16_lo(ru[k].z), bf16_hi(ru[k].z)));
+          o[3] = __fadd2_rn(o[3], make_float2(bf16_lo(ru[k].w), bf16_hi(ru[k].w)));
+        }
+        uint4 w;
+        w.x = pack_bf16(o[0].x, o[0].y); w.y = pack_bf16(o[1].x, o[1].y);
+        w.z = pack_bf16(o[2].x, o[2].y); w.w = pack_bf16(o[3].x, o[3].y);
+        if (live && ch < nchunk) out[rowoff + ch] = w;
+        if (flags & CCDM_EPI_SUMSQ_OUT) {
+          const float a0 = bf16_lo(w.x), a1 = bf16_hi(w.x), a2 = bf16_lo(w.y), a3 = bf16_hi(w.y);
+          const float a4 = bf16_lo(w.z), a5 = bf16_hi(w.z), a6 = bf16_lo(w.w), a7 = bf16_hi(w.w);
+          if (ch < nchunk) out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+        }
+      }
       if (flags & CCDM_EPI_SUMSQ_OUT) {
-        const float a0 = bf16_lo(w.x), a1 = bf16_hi(w.x), a2 = bf16_lo(w.y), a3 = bf16_hi(w.y);
-        const float a4 = bf16_lo(w.z), a5 = bf16_hi(w.z), a6 = bf16_lo(w.w), a7 = bf16_hi(w.w);
-        if (ch < nchunk) out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+        out_ss = seg_sum(out_ss, gl, G, lane);
+        if (live && gl == 0) out_rowss[(size_t)b * rows_per_sample + r] = out_ss;
       }
-    }
-    if (flags & CCDM_EPI_SUMSQ_OUT) {
-      out_ss = seg_sum(out_ss, gl, G, lane);
-      if (live && gl == 0) out_rowss[(size_t)b * rows_per_sample + r] = out_ss;
     }
   }
 }
@@ -451,20 +456,31 @@ extern "C" int ccdm_rmsnorm_act(const void* z, void* out, int64_t rows, int32_t 
   CCDM_REQUIRE(rows % rows_per_sample == 0, CCDM_ERR_BAD_ARG, "rmsnorm_act: rows=%lld rows_per_sample=%d",
                (long long)rows, rows_per_sample);
   const int B = (int)(rows / rows_per_sample);
-  CCDM_REQUIRE(B <= 65535, CCDM_ERR_UNSUPPORTED_SHAPE, "rmsnorm_act: %d samples", B);
   int kv, G;
   row_lane_plan(C / 8, 3, &kv, &G);
-  int per_sample = (num_sms() * 8 + B - 1) / B;                    // a few waves of CTAs, >= 32 rows each
-  const int max_split = (rows_per_sample + 31) / 32;
+  // persistent grid: one resident wave of CTAs; work items = (sample, slab of >= 64 rows), ~6 items per CTA
+  cudaStream_t st = (cudaStream_t)stream;
+  static int occ[4] = {0, 0, 0, 0};
+  if (!occ[kv]) {
+    int o = 1;
+    if (kv == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, rmsnorm_act_kernel<1>, 256, 0);
+    else if (kv == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, rmsnorm_act_kernel<2>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, rmsnorm_act_kernel<3>, 256, 0);
+    occ[kv] = o > 0 ? o : 1;
+  }
+  const int slots = num_sms() * occ[kv];
+  int per_sample = (slots * 6 + B - 1) / B;
+  const int max_split = (rows_per_sample + 63) / 64;
   if (per_sample > max_split) per_sample = max_split;
   if (per_sample < 1) per_sample = 1;
-  const int rows_per_block = (rows_per_sample + per_sample - 1) / per_sample;
-  per_sample = (rows_per_sample + rows_per_block - 1) / rows_per_block;
-  dim3 grid((unsigned)per_sample, (unsigned)B);
-  cudaStream_t st = (cudaStream_t)stream;
+  const int rows_per_item = (rows_per_sample + per_sample - 1) / per_sample;
+  per_sample = (rows_per_sample + rows_per_item - 1) / rows_per_item;
+  const int n_items = per_sample * B;
+  const int grid = n_items < slots ? n_items : slots;
 #define CCDM_RMS(K)                                                                                                   \
-  rmsnorm_act_kernel<K><<<grid, 256, 0, st>>>((const uint4*)z, (uint4*)out, rows_per_sample, rows_per_block, C, G, gain, \
-                                              gain_mul, scale_shift, ss_ld, ss_off, (const uint4*)resid, out_rowss, flags)
+  rmsnorm_act_kernel<K><<<grid, 256, 0, st>>>((const uint4*)z, (uint4*)out, rows_per_sample, rows_per_item, per_sample, \
+                                              n_items, C, G, gain, gain_mul, scale_shift, ss_ld, ss_off,               \
+                                              (const uint4*)resid, out_rowss, flags)
   if (kv == 1) CCDM_RMS(1);
   else if (kv == 2) CCDM_RMS(2);
   else CCDM_RMS(3);

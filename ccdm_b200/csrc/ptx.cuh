@@ -181,7 +181,32 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
+// 8 consecutive floats; vector loads when the address allows (scale/shift offsets are multiples of 8 floats in
+// practice), scalar otherwise
+__device__ __forceinline__ void load8(const float* p, float (&o)[8]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p)), y = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = y.x; o[5] = y.y; o[6] = y.z; o[7] = y.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __ldg(p + j);
+  }
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// sigmoid(x) = 0.5 + 0.5 tanh(x/2): one MUFU, no division
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+// Sum over the G lanes of a row segment, broadcast to all of them.  Power-of-two G: xor butterfly.
 __device__ __forceinline__ float seg_sum(float v, int gl, int G, int lane) {
+  if ((G & (G - 1)) == 0) {
+    for (int off = G >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+  }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     const float o = __shfl_down_sync(0xffffffffu, v, off);

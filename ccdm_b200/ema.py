@@ -1,8 +1,8 @@
 """Exponential moving average of a model, with the interface Trainer uses (CCDM_unified/ema_pytorch.py:18-181):
 ``EMA(model, beta, update_after_step, update_every)``, ``.ema_model``, ``.update()``, ``state_dict()``.
 
-The copy/lerp over all tensors runs as multi-tensor ``torch._foreach`` ops (HBM-bound, every ``update_every``
-steps); fusing it with the optimizer step is a "next" row."""
+The lerp over all parameters is one launch of ``ccdm_multi_lerp`` over a pointer table (HBM-bound, every
+``update_every`` steps); CPU models (tests) use ``torch._foreach_lerp_``."""
 import copy
 
 import torch
@@ -54,7 +54,18 @@ class EMA(nn.Module):
             self.initted.fill_(True)
         w = 1.0 - self.get_current_decay()
         pairs = self._pairs()
-        torch._foreach_lerp_([e for e, _ in pairs], [o for _, o in pairs], w)
+        if pairs and all(e.is_cuda and e.dtype == torch.float32 for e, _ in pairs):
+            # one launch over a pointer table (ccdm_multi_lerp); rebuilt only if a tensor moved
+            from .optim import MultiLerp
+            ml = getattr(self, "_ml", None)
+            ptrs = tuple(e.data_ptr() for e, _ in pairs) + tuple(o.data_ptr() for _, o in pairs)
+            if ml is None or self._ml_ptrs != ptrs:
+                ml = MultiLerp([e for e, _ in pairs], [o for _, o in pairs])
+                object.__setattr__(self, "_ml", ml)
+                object.__setattr__(self, "_ml_ptrs", ptrs)
+            ml(w)
+        else:
+            torch._foreach_lerp_([e for e, _ in pairs], [o for _, o in pairs], w)
         for e, o in self._buffer_pairs():
             if e.dtype.is_floating_point:
                 e.lerp_(o.to(e.dtype), w)

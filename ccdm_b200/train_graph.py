@@ -19,6 +19,7 @@ from typing import Optional
 import torch
 
 from . import dist as ccdm_dist
+from .optim import FusedAdam
 
 
 class GraphedTrainStep:
@@ -30,13 +31,17 @@ class GraphedTrainStep:
         self.kw = dict(loss_kwargs or {})
         self.max_grad_norm = max_grad_norm
         self.params = [p for p in diffusion.parameters() if p.requires_grad]
-        for grp in optimizer.param_groups:
-            grp["capturable"] = True
-            if "foreach" in grp and grp["foreach"] is None:
-                grp["foreach"] = True
-        for st in optimizer.state.values():
-            if "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
-                st["step"] = st["step"].to(images.device)
+        self.fused = isinstance(optimizer, FusedAdam)
+        if self.fused:
+            optimizer.max_grad_norm = max_grad_norm               # clipping is part of the fused step
+        else:
+            for grp in optimizer.param_groups:
+                grp["capturable"] = True
+                if "foreach" in grp and grp["foreach"] is None:
+                    grp["foreach"] = True
+            for st in optimizer.state.values():
+                if "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
+                    st["step"] = st["step"].to(images.device)
         self.images = images.detach().clone()
         self.labels = labels.detach().clone()
         self.labels_emb = labels_emb.detach().clone()
@@ -61,9 +66,12 @@ class GraphedTrainStep:
         loss = self.gd(self.images, labels_emb=self.labels_emb, labels=self.labels, vicinal_weights=self.weights, **self.kw)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
-        ccdm_dist.all_reduce_gradients(self.params)
-        if self.max_grad_norm is not None:
-            torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm)
+        if self.fused:
+            self.opt.all_reduce_gradients()
+        else:
+            ccdm_dist.all_reduce_gradients(self.params)
+            if self.max_grad_norm is not None:
+                torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm)
         self.opt.step()
         self.loss.copy_(loss.detach())
 

@@ -17,6 +17,7 @@ from torch.optim import Adam
 
 from . import dist as ccdm_dist
 from .ema import EMA
+from .optim import FusedAdam
 from .diffusion import generate_random_vectors
 from .utils import divisible_by, exists
 
@@ -46,7 +47,12 @@ class Trainer(object):
         assert (train_batch_size * gradient_accumulate_every) >= 16, \
             "your effective batch size (train_batch_size x gradient_accumulate_every) should be at least 16 or above"
         self.train_num_steps, self.max_grad_norm = train_num_steps, max_grad_norm
-        self.opt = Adam(diffusion_model.parameters(), lr=train_lr, betas=adam_betas)
+        params = list(diffusion_model.parameters())
+        if params and params[0].is_cuda:
+            # clip_grad_norm_ + Adam fused over flat buffers (ccdm_b200/optim.py); same arithmetic as torch's Adam
+            self.opt = FusedAdam(params, lr=train_lr, betas=adam_betas, max_grad_norm=max_grad_norm)
+        else:
+            self.opt = Adam(params, lr=train_lr, betas=adam_betas)
         self.ema = EMA(diffusion_model, update_after_step=ema_update_after_step, beta=ema_decay,
                        update_every=ema_update_every)
         self.ema.to(self.device)
@@ -143,8 +149,11 @@ class Trainer(object):
                 loss = loss / self.gradient_accumulate_every
                 total += loss.item()
                 loss.backward()
-            ccdm_dist.all_reduce_gradients(list(self.model.parameters()))
-            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.max_grad_norm)
+            if isinstance(self.opt, FusedAdam):
+                self.opt.all_reduce_gradients()                   # one collective over the flat gradient buffer; clip is fused
+            else:
+                ccdm_dist.all_reduce_gradients(list(self.model.parameters()))
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.max_grad_norm)
             if self.step % 500 == 0:
                 with open(log, "a") as f:
                     f.write(f"\r Step: {self.step}, Loss: {total:.4f}.")

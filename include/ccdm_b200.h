@@ -332,6 +332,21 @@ int ccdm_head_conv1_bwd(const float* dout_nchw, const void* h, const float* w, v
 /* Inverse of ccdm_stem_pack for the gradient ccdm_conv_wgrad leaves over the im2row tensor: dW [Cout][Cin][7][7]. */
 int ccdm_stem_unpack_wgrad(const float* packed, float* dw, int32_t Cout, int32_t Cin, int32_t accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimizer step: clip_grad_norm_ + Adam of trainer.py:137,724,733-734 in three launches
+ * over flat fp32 gradient / moment buffers, and the EMA lerp of ema_pytorch.py:150-178 in one.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* chunk i covers chunk_n[i] elements of one parameter tensor starting at chunk_param[i]; its gradient and Adam
+ * moments sit at g_flat / m_flat / v_flat + chunk_off[i].  step (device float) is incremented first (torch's
+ * bias-correction convention); sumsq != NULL enables clipping: g *= min(1, max_norm / (||g_flat||_2 + 1e-6)), with the
+ * squared norm left in sumsq[0] (device double).  n_flat = total elements of the flat buffers. */
+int ccdm_fused_adam(void* const* chunk_param, const int64_t* chunk_off, const int32_t* chunk_n, int32_t n_chunks,
+                    const float* g_flat, float* m_flat, float* v_flat, int64_t n_flat, float* step, double* sumsq,
+                    float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, void* stream);
+/* dst[i] += weight[0] * (src[i] - dst[i]) over n_chunks (pointer, pointer, count) triples. */
+int ccdm_multi_lerp(void* const* dst, const void* const* src, const int32_t* chunk_n, int32_t n_chunks,
+                    const float* weight, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,3 +285,84 @@ def test_graphed_train_step():
     assert len(set(round(v, 6) for v in losses[:5])) > 1          # new timesteps / noise on every replay
     assert sum(losses[-10:]) < 0.8 * sum(losses[:10])
     assert all(torch.isfinite(p).all() for p in gd.parameters())
+
+
+def test_fused_adam_matches_torch_adam():
+    """FusedAdam (clip + Adam over flat buffers) vs clip_grad_norm_ + torch.optim.Adam on identical gradients, 5 steps."""
+    from ccdm_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(64, 3, 7, 7), (64,), (1, 64, 1, 1), (128, 64, 3, 3), (7,), (300, 5)]
+    pa = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = FusedAdam(pa, lr=3e-3, betas=(0.9, 0.99), max_grad_norm=1.0)
+    ob = torch.optim.Adam(pb, lr=3e-3, betas=(0.9, 0.99))
+    for step in range(5):
+        gs = [torch.randn_like(p) * (10.0 if step % 2 == 0 else 0.01) for p in pa]      # clipped and unclipped steps
+        oa.zero_grad()
+        for p, g in zip(pa, gs):
+            p.grad.add_(g)                     # what autograd's AccumulateGrad does with an attached view
+        for p, g in zip(pb, gs):
+            p.grad = g.clone()
+        norm_b = torch.nn.utils.clip_grad_norm_(pb, 1.0)
+        oa.step()
+        ob.step()
+        assert abs(oa.grad_norm.item() - norm_b.item()) / norm_b.item() < 1e-5
+        for a, b in zip(pa, pb):
+            assert relerr(a.detach(), b.detach()) < 1e-6
+    sd = oa.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 5
+    assert relerr(sd["state"][3]["exp_avg"], ob.state_dict()["state"][3]["exp_avg"]) < 1e-6
+
+
+def test_ema_multi_lerp_matches_foreach():
+    import ccdm_b200
+    from ccdm_b200.ema import EMA
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(33, 17), torch.nn.Linear(17, 5)).cuda()
+    ema = EMA(net, beta=0.99, update_after_step=0, update_every=1)
+    ref = [p.detach().clone() for p in net.parameters()]
+    for step in range(6):
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(torch.randn_like(p) * 0.1)
+        s = int(ema.step.item())
+        ema.update()
+        if s == 0:
+            ref = [p.detach().clone() for p in net.parameters()]          # first call copies
+        else:
+            if s == 1:
+                ref = [p.detach().clone() for p in net.parameters()]      # initted copy, then lerp with itself
+            w = 1.0 - ema.get_current_decay()
+            ref = [r.lerp(p.detach(), w) for r, p in zip(ref, net.parameters())]
+    for e, r in zip(ema.ema_model.parameters(), ref):
+        assert relerr(e, r) < 1e-5
+
+
+def test_trainer_train_runs_optimizer_steps(tmp_path):
+    """Trainer.train (trainer.py:537-780): vicinal batch construction on the device, loss, backward through the CUDA
+    graph of autograd nodes, fused clip + Adam, EMA -- three optimizer steps on a toy data set."""
+    import numpy as np
+    import ccdm_b200
+    from ccdm_b200.optim import FusedAdam
+    spec = SPECS["rc_small"]
+    net, _ = make_net(spec, 4, p_drop=0.1)
+    gd = ccdm_b200.GaussianDiffusion(net, image_size=16, timesteps=1000, sampling_timesteps=5, objective="pred_x0",
+                                     cond_drop_prob=0.1, vicinity_type="hv").cuda()
+    rng = np.random.RandomState(0)
+    images = rng.randint(0, 256, size=(64, 3, 16, 16)).astype(np.uint8)
+    labels = rng.rand(64).astype(np.float32)
+    tr = ccdm_b200.Trainer("RC-49", gd, train_images=images, train_labels=labels,
+                           vicinal_params={"kernel_sigma": 0.05, "kappa": 0.1, "nonzero_soft_weight_threshold": 1e-3},
+                           train_batch_size=16, train_num_steps=3, results_folder=str(tmp_path), vicinity_type="hv",
+                           ema_update_after_step=0, ema_update_every=1)
+    assert isinstance(tr.opt, FusedAdam)
+    fn_y2h = ccdm_b200.LabelEmbed(y2h_type="sinusoidal", h_dim=128, device=torch.device("cuda")).fn_y2h
+    before = torch.cat([p.detach().flatten().clone() for p in gd.parameters()])
+    gd.train()
+    tr.train(fn_y2h)
+    after = torch.cat([p.detach().flatten() for p in gd.parameters()])
+    assert tr.step == 3
+    assert torch.isfinite(after).all() and (after - before).abs().max() > 0
+    assert float(tr.opt.step_count.item()) == 3.0
+    ema_p = torch.cat([p.detach().flatten() for p in tr.ema.ema_model.parameters()])
+    assert torch.isfinite(ema_p).all()

@@ -17,6 +17,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ccdm_b200  # noqa: E402
+import ccdm_b200.optim  # noqa: E402,F401
 from ccdm_b200 import dist as D  # noqa: E402
 
 MODELS = {
@@ -40,6 +41,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--breakdown", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam + clip_grad_norm_ instead of FusedAdam")
     ap.add_argument("--graph", action="store_true", help="capture the whole step into a CUDA graph (train_graph.py)")
     a = ap.parse_args()
     rank, local, world = D.env_world()
@@ -54,7 +56,10 @@ def main():
     gd = ccdm_b200.GaussianDiffusion(net, image_size=m["size"], objective="pred_x0", use_Hy=True, fn_y2cov=fn_y2cov,
                                      cond_drop_prob=0.1, timesteps=1000, vicinity_type="hv").cuda().train()
     D.broadcast_parameters(gd)
-    opt = torch.optim.Adam(gd.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    if a.torch_adam:
+        opt = torch.optim.Adam(gd.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    else:
+        opt = ccdm_b200.optim.FusedAdam(gd.parameters(), lr=1e-4, betas=(0.9, 0.99), max_grad_norm=1.0)
     g = torch.Generator().manual_seed(rank)
     B = a.batch
     img = torch.rand(B, 3, m["size"], m["size"], generator=g).cuda()
@@ -74,8 +79,11 @@ def main():
         loss.backward()
         if ev:
             ev[2].record()
-        D.all_reduce_gradients(params)
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        if a.torch_adam:
+            D.all_reduce_gradients(params)
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+        else:
+            opt.all_reduce_gradients()
         opt.step()
         if ev:
             ev[3].record()
@@ -103,7 +111,7 @@ def main():
     if rank == 0:
         peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
         tflops = 3 * m["gflop"] * B * world / ms                         # GFLOP / ms = TFLOP/s
-        rec = dict(metric="train step", mode="cuda-graph" if a.graph else "eager", model=a.model, per_gpu_batch=B, n_gpus=world, ms_per_step=round(ms, 2),
+        rec = dict(metric="train step", mode="cuda-graph" if a.graph else "eager", optimizer="torch" if a.torch_adam else "fused", model=a.model, per_gpu_batch=B, n_gpus=world, ms_per_step=round(ms, 2),
                    images_per_s=round(B * world / ms * 1e3, 1), algorithmic_tflops=round(tflops, 1),
                    frac_of_sustained_bf16_peak=round(tflops / world / peaks["bf16_tflops_sustained"], 3),
                    kernel_launches_per_step=int(launches), loss=round(loss.item(), 5),
