@@ -156,10 +156,11 @@ def rmsnorm_act(z: torch.Tensor, gain: torch.Tensor, scale_shift: Optional[torch
     return out
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
-    """fp32 [C] column sums of a bf16 [..., C] tensor (bias gradient of a plain convolution)."""
+def colsum(x: torch.Tensor, accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [C] column sums of a bf16 [..., C] tensor (bias gradient of a plain convolution); added to
+    ``accumulate_into`` when given."""
     c = x.shape[-1]
-    out = torch.zeros(c, dtype=torch.float32, device=x.device)
+    out = accumulate_into if accumulate_into is not None else torch.zeros(c, dtype=torch.float32, device=x.device)
     L.check(L.lib().ccdm_colsum_bf16(x.data_ptr(), x.numel() // c, c, out.data_ptr(), _stream()), "colsum_bf16")
     return out
 
@@ -230,8 +231,9 @@ def wgrad_packed(plan: ConvPlan, tile, views: List[L.View], dz: torch.Tensor, gw
 
 
 def conv_wgrad(kind: str, srcs: Sequence[torch.Tensor], dz: torch.Tensor, ksplit: int = 0,
-               timing: Optional[list] = None) -> torch.Tensor:
-    """dW [Cout, sum(cins), kh, kw] fp32 of ``conv(kind)`` given its inputs and the gradient of its output."""
+               timing: Optional[list] = None, accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW [Cout, sum(cins), kh, kw] fp32 of ``conv(kind)`` given its inputs and the gradient of its output.
+    With ``accumulate_into`` (a contiguous fp32 tensor of that shape, e.g. ``weight.grad``) the result is added there."""
     for s in srcs:
         _check(s, "conv_wgrad source")
     _check(dz, "conv_wgrad dz")
@@ -248,19 +250,21 @@ def conv_wgrad(kind: str, srcs: Sequence[torch.Tensor], dz: torch.Tensor, ksplit
         views += _parity_views(s) if plan.n_views == 4 else [_view(s)]
     gpacked = wgrad_packed(plan, tile, views, dz, gw, gh, sched, cout, n_rows, ksplit, timing)
     k = int(math.isqrt(_KIND_TAPS[kind]))
-    dw = torch.empty(cout, sum(cins), k, k, dtype=torch.float32, device=dev)
+    dw = accumulate_into if accumulate_into is not None else torch.empty(cout, sum(cins), k, k, dtype=torch.float32, device=dev)
     L.check(L.lib().ccdm_unpack_wgrad(gpacked.data_ptr(), dw.data_ptr(), cout, sum(cins), _KIND_TAPS[kind],
-                                      psched.data_ptr(), plan.nz, plan.nkb, n_rows, None, 1.0, 0, _stream()),
-            "unpack_wgrad")
+                                      psched.data_ptr(), plan.nz, plan.nkb, n_rows, None, 1.0,
+                                      1 if accumulate_into is not None else 0, _stream()), "unpack_wgrad")
     return dw
 
 
 def block_backward(dy: torch.Tensor, z: torch.Tensor, gain: torch.Tensor, scale_shift: Optional[torch.Tensor] = None,
-                   ss_off: int = 0, silu: bool = True):
+                   ss_off: int = 0, silu: bool = True, dgain_into: Optional[torch.Tensor] = None,
+                   dbias_into: Optional[torch.Tensor] = None):
     """Backward of ``silu(rmsnorm(z) * (1+scale) + shift)`` (Block.forward, unet.py:143-152).
 
     ``scale_shift`` is the fp32 [B, ld] buffer the forward read (scale at [ss_off, ss_off+C), shift right after).
-    Returns (dz bf16, d_scale_shift fp32 [B, ld] or None, dgain [C], dbias [C])."""
+    Returns (dz bf16, d_scale_shift fp32 [B, ld] or None, dgain [C], dbias [C]); ``dgain_into`` / ``dbias_into``
+    (fp32, C elements, e.g. the parameters' ``.grad``) receive ``+=`` instead and None is returned in their place."""
     _check(dy, "block_backward dy")
     _check(z, "block_backward z")
     b, h, w, c = z.shape
@@ -278,5 +282,7 @@ def block_backward(dy: torch.Tensor, z: torch.Tensor, gain: torch.Tensor, scale_
     if scale_shift is not None:             # every element is written when the buffer is exactly [scale | shift]
         d_ss = torch.empty_like(scale_shift) if (ss_off == 0 and ld == 2 * c) else torch.zeros_like(scale_shift)
     L.check(L.lib().ccdm_block_bwd_finish(sums.data_ptr(), b, c, g.data_ptr(), gm, L.ptr(scale_shift), ld, ss_off,
-                                          L.ptr(d_ss), dgain.data_ptr(), dbias.data_ptr(), _stream()), "block_bwd_finish")
-    return dz, d_ss, dgain, dbias
+                                          L.ptr(d_ss), (dgain_into if dgain_into is not None else dgain).data_ptr(),
+                                          (dbias_into if dbias_into is not None else dbias).data_ptr(), _stream()),
+            "block_bwd_finish")
+    return dz, d_ss, (None if dgain_into is not None else dgain), (None if dbias_into is not None else dbias)

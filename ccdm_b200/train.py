@@ -43,6 +43,18 @@ def _c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _grad_slot(p: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """``p.grad`` when a gradient buffer is already attached to the parameter (FusedAdam's flat-buffer views, or any
+    earlier accumulation): the kernels then add into it directly and the node returns None for that input, which saves
+    the temporary, its zero fill and autograd's accumulate kernel.  None otherwise (autograd gets the tensor)."""
+    if p is None or not isinstance(p, torch.nn.Parameter):
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device or g.numel() != p.numel():
+        return None
+    return g
+
+
 # ------------------------------------------------------------------------------------------------- nodes
 
 class ConvFn(Function):
@@ -52,6 +64,7 @@ class ConvFn(Function):
     def forward(ctx, kind, weight, bias, resid, *srcs):
         out = K.conv_forward(kind, srcs, weight, bias, resid)
         ctx.kind, ctx.has_bias, ctx.has_resid = kind, bias is not None, resid is not None
+        ctx.params = (weight, bias)
         ctx.save_for_backward(weight, *srcs)
         return out
 
@@ -59,12 +72,20 @@ class ConvFn(Function):
     def backward(ctx, dz):
         dz = _c(dz)
         weight, *srcs = ctx.saved_tensors
+        wparam, bparam = ctx.params
         cins = [s.shape[3] for s in srcs]
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
         if any(ctx.needs_input_grad[4:]):
             dsrcs = K.conv_dgrad(ctx.kind, dz, weight, cins)
-        dw = K.conv_wgrad(ctx.kind, srcs, dz) if ctx.needs_input_grad[1] else None
-        db = K.colsum(dz) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            slot = _grad_slot(wparam)
+            dw = K.conv_wgrad(ctx.kind, srcs, dz, accumulate_into=slot)
+            dw = None if slot is not None else dw
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            slot = _grad_slot(bparam)
+            db = K.colsum(dz, accumulate_into=slot)
+            db = None if slot is not None else db
         return (None, dw, db, dz if ctx.has_resid else None, *dsrcs)
 
 
@@ -80,6 +101,7 @@ class ConvBlockFn(Function):
         out = K.rmsnorm_act(z, g, ss, silu, resid)
         ctx.kind, ctx.silu, ctx.has_ss, ctx.has_resid = kind, silu, ss is not None, resid is not None
         ctx.gain_shape = gain.shape
+        ctx.params = (weight, bias, gain)
         ctx.save_for_backward(weight, g, z, *( [ss] if ss is not None else [] ), *srcs)
         return out
 
@@ -90,13 +112,16 @@ class ConvBlockFn(Function):
         weight, g, z = saved[:3]
         ss = saved[3] if ctx.has_ss else None
         srcs = saved[4:] if ctx.has_ss else saved[3:]
-        dz, d_ss, dgain, dbias = K.block_backward(dh, z, g, ss, 0, ctx.silu)
+        wparam, bparam, gparam = ctx.params
+        gslot, bslot, wslot = _grad_slot(gparam), _grad_slot(bparam), _grad_slot(wparam)
+        dz, d_ss, dgain, dbias = K.block_backward(dh, z, g, ss, 0, ctx.silu, dgain_into=gslot, dbias_into=bslot)
         cins = [s.shape[3] for s in srcs]
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
         if any(ctx.needs_input_grad[7:]):
             dsrcs = K.conv_dgrad(ctx.kind, dz, weight, cins)
-        dw = K.conv_wgrad(ctx.kind, srcs, dz)
-        return (None, None, dw, dbias, dgain.view(ctx.gain_shape), d_ss, dh if ctx.has_resid else None, *dsrcs)
+        dw = K.conv_wgrad(ctx.kind, srcs, dz, accumulate_into=wslot)
+        return (None, None, None if wslot is not None else dw, dbias,
+                dgain.view(ctx.gain_shape) if dgain is not None else None, d_ss, dh if ctx.has_resid else None, *dsrcs)
 
 
 class RmsNormFn(Function):
@@ -106,14 +131,16 @@ class RmsNormFn(Function):
     def forward(ctx, x, gain):
         g = gain.reshape(-1)
         ctx.gain_shape = gain.shape
+        ctx.params = (gain,)
         ctx.save_for_backward(x, g)
         return K.rmsnorm_act(x, g)
 
     @staticmethod
     def backward(ctx, dy):
         x, g = ctx.saved_tensors
-        dx, _, dgain, _ = K.block_backward(_c(dy), x, g, None, 0, False)
-        return dx, dgain.view(ctx.gain_shape)
+        gslot = _grad_slot(ctx.params[0])
+        dx, _, dgain, _ = K.block_backward(_c(dy), x, g, None, 0, False, dgain_into=gslot)
+        return dx, dgain.view(ctx.gain_shape) if dgain is not None else None
 
 
 class LinAttnCoreFn(Function):
