@@ -89,6 +89,7 @@ class TapGemmRec:
     q_scale: float = 0.0
     q_cols: int = 0
     w_batch_rows: int = 0
+    algo_flops: Optional[float] = None  # overrides tapgemm_flops (GEMMs that are not a reference convolution)
 
 
 @dataclass
@@ -160,6 +161,8 @@ class Program:
 def tapgemm_flops(r: "TapGemmRec") -> float:
     """Algorithmic FLOPs (2*MAC) of the reference convolution this record computes:
     2 * B * Hout * Wout * Cout * Cin * kh * kw -- the nearest-2x fold and padded channels are NOT credited."""
+    if r.algo_flops is not None:
+        return r.algo_flops
     cin = sum(r.plan.cins)
     if r.plan.out_parity:
         pos = r.gB * (2 * r.gH) * (2 * r.gW)
@@ -221,6 +224,8 @@ def _make_call(lib, r, keep):
     if k == "linattn_context":
         return lib.ccdm_linattn_context, (p(a["qkv"]), p(a["ctx"]), None, a["B"], a["n"], a["heads"], p(a["w_out"]),
                                           p(a["wfold"]), a["C"], a["n_rows"]), k
+    if k == "linattn_pack_blockdiag":
+        return lib.ccdm_linattn_pack_blockdiag, (p(a["m"]), p(a.get("row_div")), a["transpose"], p(a["w"]), a["B"]), k
     if k == "linattn_fold":
         return lib.ccdm_linattn_fold, (p(a["w_out"]), p(a["ctx"]), p(a["wfold"]), a["B"], a["C"], a["n_rows"],
                                        a["heads"]), k
@@ -516,12 +521,27 @@ class UnetProgram(Program):
         wide = C > 512                                      # norm cannot be fused: split channels + standalone norm
         n_rows, n_tile = n_tiling(C, not wide)
         wfold = self.buf(name + ".wfold", (self.B * n_rows, hid), torch.bfloat16)
+        wfold.zero_()                                       # rows [C, n_rows) are padding and must stay zero
         # context, then its fold into to_out's weights: fused into the context kernel's epilogue while that is cheap
         # (C <= 64), a separate whole-GPU launch for the wider levels
         fuse = C <= 64 and heads == 4
         self.kernel("linattn_context", qkv=qkv, ctx=ctx, B=self.B, n=n, heads=heads, w_out=conv_out.weight,
                     wfold=wfold if fuse else None, C=C, n_rows=n_rows)
-        if not fuse:
+        if not fuse and heads == 4:
+            # fold on tensor cores: wfold[b][c][hd] = sum_k Wout[c][k] * blockdiag(ctx_b)[hd][k] is a tap-GEMM whose
+            # "image" is the (packed, bf16) to_out weight itself -- C pixels x 128 channels, the same for every sample
+            # (batch stride 0) -- and whose per-sample weights are the block-diagonal contexts
+            wb = self.buf(name + ".ctx_bd", (self.B * 128, 128), torch.bfloat16)
+            self.kernel("linattn_pack_blockdiag", m=ctx, row_div=None, transpose=1, w=wb, B=self.B)
+            fplan = plan_conv("1x1", [hid], 128)
+            wpack = self.weights.add(name + ".to_out.w/R1", conv_out.weight, plan_conv("1x1", [hid], C),
+                                     n_tiling(C, False)[0])
+            wview = ViewRec(wpack.packed, 0, hid, C, 1, self.B, hid, C * hid, 0)
+            fsched = torch.tensor(fplan.sched, dtype=torch.int32, device=self.device)
+            self.recs.append(TapGemmRec(name + ".fold", fplan, [wview], C, 1, self.B, tile_box(C, 1, force_tb1=True),
+                                        None, wb, fsched, 128, 128, 128, 0, wfold, (hid, C * hid, n_rows * hid),
+                                        w_batch_rows=128, algo_flops=2.0 * self.B * C * hid * 32))
+        elif not fuse:
             self.kernel("linattn_fold", w_out=conv_out.weight, ctx=ctx, wfold=wfold, B=self.B, C=C, n_rows=n_rows,
                         heads=heads)
         out = self.act(name + ".out", h, w, C)

@@ -141,6 +141,16 @@ def run_kernel(r: KernelRec):
         bias = a["bias"]
         bias.zero_()
         bias[a["lo"]:a["hi"]] = -1.01 * w[a["lo"]:a["hi"]].norm(dim=1) - 1e-3
+    elif k == "linattn_pack_blockdiag":
+        B = a["B"]
+        m = a["m"].float().reshape(B, 4, 32, 32)                             # [b, h, d, e]
+        if a.get("row_div") is not None:
+            m = m / a["row_div"].reshape(B, 4, 32, 1)
+        w = torch.zeros(B, 128, 128)
+        for h in range(4):
+            blk = m[:, h] if a["transpose"] else m[:, h].transpose(1, 2)     # rows d (transpose) or rows e
+            w[:, h * 32:(h + 1) * 32, h * 32:(h + 1) * 32] = blk
+        a["w"].reshape(B, 128, 128).copy_(w.to(torch.bfloat16))
     elif k == "linattn_fold":
         B, C, heads = a["B"], a["C"], a["heads"]
         w = a["w_out"].detach().reshape(C, heads, 32)                        # [c, h, e]
