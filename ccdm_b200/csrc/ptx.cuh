@@ -193,6 +193,12 @@ __device__ __forceinline__ void load8(const float* p, float (&o)[8]) {
   }
 }
 
+// 2^x, one MUFU (exp2f without -use_fast_math expands to a range-handling sequence of ~6 instructions)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 e = __ffma2_rn(v[i], l2e, nmx);
-            v[i].x = exp2f(e.x);
-            v[i].y = exp2f(e.y);
+            v[i].x = ex2_fast(e.x);
+            v[i].y = ex2_fast(e.y);
             sum2 = __fadd2_rn(sum2, v[i]);
           }
           const float k = __fdividef(p.q_scale, sum2.x + sum2.y);
@@ -420,8 +420,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 e = __fmul2_rn(v[i], l2e);
-            v[i].x = exp2f(e.x);
-            v[i].y = exp2f(e.y);
+            v[i].x = ex2_fast(e.x);
+            v[i].y = ex2_fast(e.y);
           }
         }
         if ((flags & CCDM_EPI_RESID) && valid) {
