@@ -34,17 +34,30 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const uint4* __restric
 }
 
 // ---------------------------------------------------------------------------- LinearAttention forward pieces
-// kmax[b][c] = max over tokens of qkv[b][tok][128 + c], c < 128 (the softmax-over-tokens shift, unet.py:208)
-__global__ void __launch_bounds__(256) linattn_kmax_kernel(const __nv_bfloat16* __restrict__ qkv, int n,
+// kmax[b][c] = max over tokens of qkv[b][tok][128 + c], c < 128 (the softmax-over-tokens shift, unet.py:208).
+// grid = (token slabs, B): each CTA reduces its slab and merges with an ordered-int atomic max (kmax pre-filled with
+// -FLT_MAX by kmax_init_kernel).
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void kmax_init_kernel(float* __restrict__ kmax, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) kmax[i] = -FLT_MAX;
+}
+
+__global__ void __launch_bounds__(256) linattn_kmax_kernel(const __nv_bfloat16* __restrict__ qkv, int n, int slab,
                                                            float* __restrict__ kmax) {
   __shared__ float red[16][128];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.y, tid = threadIdx.x;
   const int ch = tid & 15, rl = tid >> 4;
   const uint4* base = reinterpret_cast<const uint4*>(qkv + (size_t)b * n * 384 + 128);
+  const int t0 = blockIdx.x * slab, t1 = min(t0 + slab, n);
   float m[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) m[j] = -FLT_MAX;
-  for (int t = rl; t < n; t += 16) {
+  for (int t = t0 + rl; t < t1; t += 16) {
     const uint4 u = __ldg(base + (size_t)t * 48 + ch);
     m[0] = fmaxf(m[0], bf16_lo(u.x)); m[1] = fmaxf(m[1], bf16_hi(u.x));
     m[2] = fmaxf(m[2], bf16_lo(u.y)); m[3] = fmaxf(m[3], bf16_hi(u.y));
@@ -58,7 +71,7 @@ __global__ void __launch_bounds__(256) linattn_kmax_kernel(const __nv_bfloat16* 
     float v = red[0][tid];
 #pragma unroll
     for (int r = 1; r < 16; ++r) v = fmaxf(v, red[r][tid]);
-    kmax[(size_t)b * 128 + tid] = v;
+    atomic_max_float(&kmax[(size_t)b * 128 + tid], v);
   }
 }
 
@@ -360,8 +373,16 @@ extern "C" int ccdm_colsum_bf16(const void* x, int64_t rows, int32_t C, float* o
 extern "C" int ccdm_linattn_prep(void* qkv, int32_t B, int32_t n, float* kmax, float scale, void* stream) {
   CCDM_REQUIRE(qkv && kmax && B > 0 && n > 0, CCDM_ERR_BAD_ARG, "linattn_prep: bad args");
   cudaStream_t s = (cudaStream_t)stream;
-  linattn_kmax_kernel<<<B, 256, 0, s>>>((const __nv_bfloat16*)qkv, n, kmax);
-  int rc = after_launch("linattn_kmax_kernel");
+  kmax_init_kernel<<<(B * 128 + 255) / 256, 256, 0, s>>>(kmax, B * 128);
+  int rc = after_launch("kmax_init_kernel");
+  if (rc != CCDM_OK) return rc;
+  int slabs = (num_sms() * 4 + B - 1) / B;                         // a few CTAs per SM, >= 64 tokens each
+  if (slabs > (n + 63) / 64) slabs = (n + 63) / 64;
+  if (slabs < 1) slabs = 1;
+  const int slab = (n + slabs - 1) / slabs;
+  slabs = (n + slab - 1) / slab;
+  linattn_kmax_kernel<<<dim3(slabs, B), 256, 0, s>>>((const __nv_bfloat16*)qkv, n, slab, kmax);
+  rc = after_launch("linattn_kmax_kernel");
   if (rc != CCDM_OK) return rc;
   const long long tokens = (long long)B * n;
   linattn_prep_kernel<<<(unsigned)((tokens + 7) / 8), 256, 0, s>>>((__nv_bfloat16*)qkv, tokens, n, kmax, scale);
