@@ -14,6 +14,7 @@ MAX_SRC, MAX_Z, STEP_NCOEF = 4, 4, 12
 
 EPI_BIAS, EPI_ROWSCALE, EPI_RMSNORM, EPI_SS = 0x1, 0x2, 0x4, 0x8
 EPI_SILU, EPI_RESID, EPI_QSOFTMAX, EPI_SUMSQ_OUT, EPI_OUT_F32, EPI_KEXP = 0x10, 0x20, 0x40, 0x80, 0x100, 0x200
+EPI_RELU, EPI_TANH = 0x400, 0x800
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU = 0, 1, 2, 3
 OBJ = {"pred_noise": 0, "pred_x0": 1, "pred_v": 2}
 
@@ -110,6 +111,8 @@ SIGNATURES = {
     "ccdm_attention_small_bwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "ccdm_head_conv1_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "ccdm_stem_unpack_wgrad": (C.c_int, [vp, vp, i32, i32, i32, vp]),
+    "ccdm_condbn_coef": (C.c_int, [vp, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp]),
+    "ccdm_affine_act": (C.c_int, [vp, vp, i64, i32, i32, vp, i32, i32, i32, vp]),
     "ccdm_fused_adam": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, f32, f32, vp]),
     "ccdm_multi_lerp": (C.c_int, [vp, vp, vp, i32, vp, vp]),
 }

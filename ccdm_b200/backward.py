@@ -75,7 +75,8 @@ def _plan_cached(kind, cins, cout, gw, gh):
 
 
 def _launch_tapgemm(plan: ConvPlan, tile, views: List[L.View], gw, gh, gb, wpacked, sched, n_rows, n, n_tile, out,
-                    ostr, ooff, bias=None, resid: Optional[torch.Tensor] = None, w_batch_rows: int = 0, out_c_off: int = 0):
+                    ostr, ooff, bias=None, resid: Optional[torch.Tensor] = None, w_batch_rows: int = 0, out_c_off: int = 0,
+                    flags: int = 0, ss: Optional[torch.Tensor] = None):
     a = L.TapGemmArgs()
     a.n_src = len(views)
     for i, v in enumerate(views):
@@ -85,13 +86,16 @@ def _launch_tapgemm(plan: ConvPlan, tile, views: List[L.View], gw, gh, gb, wpack
     a.nz, a.ngroups, a.R = plan.nz, plan.ngroups, plan.R
     a.sched, a.wpacked = sched.data_ptr(), wpacked.data_ptr()
     a.n_rows, a.w_batch_rows, a.N, a.n_tile = n_rows, w_batch_rows, n, n_tile
-    a.flags = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESID if resid is not None else 0)
+    a.flags = flags | (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESID if resid is not None else 0)
     a.bias = L.ptr(bias)
+    if ss is not None:
+        a.flags |= L.EPI_SS
+        a.scale_shift, a.ss_ld, a.ss_off = ss.data_ptr(), ss.shape[1], 0
     if resid is not None:
         rc = resid.shape[3]
         a.resid = resid.data_ptr()
         a.rsW, a.rsH, a.rsB = rc, resid.shape[2] * rc, resid.shape[1] * resid.shape[2] * rc
-    a.out = out.data_ptr() + 2 * out_c_off
+    a.out = out.data_ptr() + out.element_size() * out_c_off
     a.osW, a.osH, a.osB = ostr
     for i in range(L.MAX_Z):
         a.ooff[i] = ooff[i]

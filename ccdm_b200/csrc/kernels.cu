@@ -240,6 +240,42 @@ __global__ void __launch_bounds__(256) rmsnorm_act_kernel(const uint4* __restric
   }
 }
 
+// ============================================================================ generator helpers (models/sngan.py)
+__global__ void condbn_coef_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ weight, const float* __restrict__ bias,
+                                   const float* __restrict__ mean, const float* __restrict__ var, float eps, int B, int C,
+                                   float* __restrict__ ss) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const float r = rsqrtf(var[c] + eps);
+  const float a = r * (weight ? weight[c] : 1.f) * (1.f + (gamma ? gamma[i] : 0.f));
+  ss[(size_t)b * 2 * C + c] = a - 1.f;
+  ss[(size_t)b * 2 * C + C + c] = (beta ? beta[i] : 0.f) + (bias ? bias[c] : 0.f) - mean[c] * a;
+}
+
+// out = act(x * (1 + scale[b]) + shift[b]); one thread per 8-channel vector
+__global__ void __launch_bounds__(256) affine_act_kernel(const uint4* __restrict__ x, uint4* __restrict__ out,
+                                                         long long nvec, int nchunk, int rows_per_sample, int C,
+                                                         const float* __restrict__ ss, int ss_ld, int ss_off, int act) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / nchunk;
+    const int ch = (int)(i - row * nchunk);
+    const long long b = row / rows_per_sample;
+    float sc[8], sf[8];
+    load8(ss + b * ss_ld + ss_off + ch * 8, sc);
+    load8(ss + b * ss_ld + ss_off + C + ch * 8, sf);
+    const uint4 u = __ldg(x + i);
+    float v[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = fmaf(v[j], 1.f + sc[j], sf[j]);
+      if (act == 1) v[j] = fmaxf(v[j], 0.f);
+    }
+    out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
 // ============================================================================ bottleneck softmax attention
 // unet.py:228-240.  grid = (sample*head, query blocks of 64); one thread per query token, keys / values staged
 // through shared memory 64 tokens at a time with a running (online) softmax.  The shipped configs have 9 or 16
@@ -486,6 +522,28 @@ extern "C" int ccdm_rmsnorm_act(const void* z, void* out, int64_t rows, int32_t 
   else CCDM_RMS(3);
 #undef CCDM_RMS
   return after_launch("rmsnorm_act_kernel");
+}
+
+extern "C" int ccdm_condbn_coef(const float* gamma, const float* beta, const float* weight, const float* bias,
+                                const float* mean, const float* var, float eps, int32_t B, int32_t C, float* ss,
+                                void* stream) {
+  CCDM_REQUIRE(mean && var && ss && B > 0 && C > 0, CCDM_ERR_BAD_ARG, "condbn_coef: bad args");
+  const int n = B * C;
+  condbn_coef_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gamma, beta, weight, bias, mean, var, eps, B, C, ss);
+  return after_launch("condbn_coef_kernel");
+}
+
+extern "C" int ccdm_affine_act(const void* x, void* out, int64_t rows, int32_t C, int32_t rows_per_sample,
+                               const float* scale_shift, int32_t ss_ld, int32_t ss_off, int32_t act, void* stream) {
+  CCDM_REQUIRE(x && out && scale_shift && rows > 0 && rows_per_sample > 0 && rows % rows_per_sample == 0, CCDM_ERR_BAD_ARG,
+               "affine_act: bad args");
+  CCDM_REQUIRE(C > 0 && C % 8 == 0 && (act == 0 || act == 1), CCDM_ERR_UNSUPPORTED_SHAPE, "affine_act: C=%d act=%d", C, act);
+  const long long nvec = rows * (C / 8);
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  affine_act_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, nvec, C / 8,
+                                                                        rows_per_sample, C, scale_shift, ss_ld, ss_off, act);
+  return after_launch("affine_act_kernel");
 }
 
 extern "C" int ccdm_attention_small(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head,

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         const float* ssrow = p.ss + static_cast<long long>(b0) * p.ss_ld + p.ss_off + n_base;
         for (int c = et; c < p.n_tile; c += kEpiThreads) {
           const bool ok = (n_base + c) < p.N;
-          aux->gs[0][c] = ok ? aux->gain[c] * (1.f + ssrow[c]) : 0.f;
+          aux->gs[0][c] = ok ? ((flags & CCDM_EPI_RMSNORM) ? aux->gain[c] : 1.f) * (1.f + ssrow[c]) : 0.f;
           aux->sh[0][c] = ok ? ssrow[p.N + c] : 0.f;
         }
         epi_bar();
@@ -375,6 +375,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(__fmul2_rn(v[i], inv2), g2[i]);
           }
         }
+        if (!(flags & CCDM_EPI_RMSNORM) && tile_ss) {      // conditional batch norm: per-(sample, channel) affine map
+          const float2* g2 = reinterpret_cast<const float2*>(aux->gs[0] + c * 32);
+          const float2* s2 = reinterpret_cast<const float2*>(aux->sh[0] + c * 32);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __ffma2_rn(v[i], g2[i], s2[i]);
+        }
         if (ssrow) {                                       // tiles spanning several samples: per-row scale/shift
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -395,6 +401,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(hx.y));
             v[i] = __ffma2_rn(hx, t, hx);
           }
+        }
+        if (flags & CCDM_EPI_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
+        }
+        if (flags & CCDM_EPI_TANH) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = make_float2(tanh_fast(v[i].x), tanh_fast(v[i].y));
         }
         if ((flags & CCDM_EPI_QSOFTMAX) && (n0 + c * 32 < p.q_cols)) {
           float mx = fmaxf(v[0].x, v[0].y);
@@ -601,11 +615,13 @@ static int launch_variant(uint32_t flags, bool tma, dim3 grid, size_t smem_bytes
     CCDM_VARIANT(0x25u)   // bias | rmsnorm | resid                         (linear-attention to_out)
     CCDM_VARIANT(0x21u)   // bias | resid                                   (bottleneck-attention to_out)
     CCDM_VARIANT(0x00u)   // plain                                          (data gradients, per-sample context products)
+    CCDM_VARIANT(0x409u)  // bias | scale-shift | relu                      (generator conv1 + CondBN + ReLU)
     default:
       break;
   }
 #undef CCDM_VARIANT
   if (flags == 0x101u) return launch_one<0x101u, false>(grid, smem_bytes, stream, maps, p);   // tc_mlp row-GEMM, fp32 out
+  if (flags == 0x901u) return launch_one<0x901u, false>(grid, smem_bytes, stream, maps, p);   // generator output: tanh, fp32
   return tma ? launch_one<kRuntimeFlags, true>(grid, smem_bytes, stream, maps, p)
              : launch_one<kRuntimeFlags, false>(grid, smem_bytes, stream, maps, p);
 }
@@ -634,8 +650,8 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_BIAS) || a->bias, CCDM_ERR_BAD_ARG, "tapgemm: bias flag without pointer");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_ROWSCALE) || a->rowss, CCDM_ERR_BAD_ARG, "tapgemm: rowscale without rowss");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_RMSNORM) || a->gain, CCDM_ERR_BAD_ARG, "tapgemm: rmsnorm without gain");
-  CCDM_REQUIRE(!(a->flags & CCDM_EPI_SS) || (a->scale_shift && (a->flags & CCDM_EPI_RMSNORM)), CCDM_ERR_BAD_ARG,
-               "tapgemm: scale/shift needs its pointer and the RMSNorm epilogue (unet.py:145-149)");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_SS) || a->scale_shift, CCDM_ERR_BAD_ARG,
+               "tapgemm: scale/shift flag without pointer (unet.py:145-149, sngan.py:28-36)");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_RESID) || a->resid, CCDM_ERR_BAD_ARG, "tapgemm: resid flag without pointer");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_SUMSQ_OUT) || (a->out_rowss && a->n_rows == a->n_tile), CCDM_ERR_BAD_ARG,
                "tapgemm: sumsq output needs out_rowss and a single N tile");

@@ -101,7 +101,7 @@ def _chunks(c: int):
 
 
 def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = False) -> ConvPlan:
-    """kind: '1x1' | '3x3' | 'down4x4s2' | 'up2x3x3'.  ``reuse_rows`` groups vertically adjacent taps (R > 1)."""
+    """kind: '1x1' | '3x3' | 'down4x4s2' | 'up2x3x3' | 'up2x1x1' | 'stem7' | '<kind>_dgrad'.  ``reuse_rows`` groups vertically adjacent taps (R > 1)."""
     cins = tuple(int(c) for c in cins)
     offs = [sum(cins[:i]) for i in range(len(cins))]
     sched, psched = [], []
@@ -164,6 +164,12 @@ def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = Fals
                         emit(s, s, dw, rows)
         R = 2 if reuse_rows else 1
         return ConvPlan(kind, cins, cout, 9, 4, len(sched) // 4, R, sched, psched, out_parity=True)
+    if kind == "up2x1x1":
+        # nearest-2x then 1x1 (the generator's bypass, sngan.py:66-70): every output parity plane is the same 1x1 conv
+        for _ in range(4):
+            for s in range(len(cins)):
+                emit(s, s, 0, [(0, 1)])
+        return ConvPlan(kind, cins, cout, 1, 4, len(sched) // 4, 1, sched, psched, out_parity=True)
     if kind.endswith("_dgrad"):
         return _plan_dgrad(kind[:-6], cins, cout, reuse_rows, emit, sched, psched)
     raise ValueError(kind)

@@ -47,7 +47,7 @@ int ccdm_struct_size(int which);
 #define CCDM_EPI_BIAS 0x1u       /* + bias[n] */
 #define CCDM_EPI_ROWSCALE 0x2u   /* acc *= 1/max(sqrt(rowss[pixel]),1e-12) before the bias (PreNorm fold) */
 #define CCDM_EPI_RMSNORM 0x4u    /* v *= gain[n]*gain_mul / max(||v||_2 over n, 1e-12); needs N <= n_tile <= 512 */
-#define CCDM_EPI_SS 0x8u         /* v = v*(1+scale[b,n]) + shift[b,n] */
+#define CCDM_EPI_SS 0x8u         /* v = v*(1+scale[b,n]) + shift[b,n]; without CCDM_EPI_RMSNORM it needs tb == 1 */
 #define CCDM_EPI_SILU 0x10u
 #define CCDM_EPI_RESID 0x20u     /* v += resid[b,h,w,n] (bf16) */
 #define CCDM_EPI_QSOFTMAX 0x40u  /* columns < q_cols: softmax over aligned groups of 32, times q_scale */
@@ -55,6 +55,8 @@ int ccdm_struct_size(int which);
 #define CCDM_EPI_OUT_F32 0x100u  /* out is fp32 instead of bf16 */
 #define CCDM_EPI_KEXP 0x200u     /* columns in [q_cols, 2*q_cols): v = exp(v) (the k softmax numerator; bias carries
                                     the -bound shift from ccdm_kexp_bound, so v <= ~1 and nothing overflows) */
+#define CCDM_EPI_RELU 0x400u     /* v = max(v, 0)   (generator blocks, models/sngan.py:76-80) */
+#define CCDM_EPI_TANH 0x800u     /* v = tanh(v)     (generator output, models/sngan.py:128) */
 
 typedef struct ccdm_view {
   const void* ptr;    /* bf16; first element of the view (already offset for channel slices / parity planes) */
@@ -346,6 +348,21 @@ int ccdm_fused_adam(void* const* chunk_param, const int64_t* chunk_off, const in
 /* dst[i] += weight[0] * (src[i] - dst[i]) over n_chunks (pointer, pointer, count) triples. */
 int ccdm_multi_lerp(void* const* dst, const void* const* src, const int32_t* chunk_n, int32_t n_chunks,
                     const float* weight, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * One-step generator: models/sngan.py:19-139 in eval mode.  The convolutions are
+ * ccdm_tapgemm ("up2x3x3" for Upsample+conv1, "up2x1x1" for the bypass, epilogues CCDM_EPI_SS | CCDM_EPI_RELU for
+ * ConditionalBatchNorm2d + ReLU and CCDM_EPI_TANH for the output); the two helpers below supply the rest.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* (Conditional) BatchNorm2d with running statistics as a per-(sample, channel) affine map in the scale/shift layout
+ * of ccdm_tapgemm (sngan.py:28-36): with r = rsqrt(var+eps), a = r * (weight ? weight[c] : 1) * (1 + (gamma ? gamma[b,c] : 0)):
+ *   ss[b][c] = a - 1,   ss[b][C+c] = (beta ? beta[b,c] : 0) + (bias ? bias[c] : 0) - mean[c]*a        (ss is [B][2C]) */
+int ccdm_condbn_coef(const float* gamma, const float* beta, const float* weight, const float* bias, const float* mean,
+                     const float* var, float eps, int32_t B, int32_t C, float* ss, void* stream);
+/* out = act(x*(1+scale[b]) + shift[b]) over bf16 rows of C channels (pre-activation CondBN + ReLU in front of a conv);
+ * act: 0 none, 1 ReLU. */
+int ccdm_affine_act(const void* x, void* out, int64_t rows, int32_t C, int32_t rows_per_sample, const float* scale_shift,
+                    int32_t ss_ld, int32_t ss_off, int32_t act, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,3 +112,20 @@ def test_loss_and_grads(name):
         close(sd[k].grad, gold["grad_" + k.replace(".", "_")], tol=2e-3)
     sq = sum(float((v.grad.double() ** 2).sum()) for v in sd.values() if getattr(v, "grad", None) is not None)
     assert abs(sq - gold["grad_sqnorm"]) / gold["grad_sqnorm"] < 2e-3
+
+
+# ----------------------------------------------------------------------------- one-step generator (sngan.py)
+
+@pytest.mark.parametrize("name", ["g64", "g128", "g192_mono"])
+def test_generator_oracle_vs_reference_golden(name):
+    from oracle.sngan_ref import generator_forward, make_state_dict, state_dict_shapes
+    from tests.golden.sngan_cases import GEN_CASES, GEN_SPECS, gen_inputs
+    sname, seed, batch = GEN_CASES[name]
+    spec = GEN_SPECS[sname]
+    gold = torch.load(os.path.join(G, "sngan.pt"), weights_only=True)[name]
+    assert list(state_dict_shapes(spec).keys()) == gold["keys"]          # names and registration order of the reference
+    z, y = gen_inputs(spec, batch)
+    with torch.no_grad():
+        out = generator_forward(make_state_dict(spec, seed), spec, z, y)
+    assert out.shape == gold["out"].shape
+    assert ((out - gold["out"]).norm() / gold["out"].norm()).item() < 1e-5
