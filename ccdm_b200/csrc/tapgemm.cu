@@ -74,6 +74,59 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 
 __device__ __forceinline__ float fast_silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
+// Descriptor from a low word that already holds (address >> 4) | LBO bit; the high word is constant.
+__device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) {
+  return (kUmmaDescSw128 & 0xFFFFFFFF00000000ull) | lo;
+}
+
+// kR vertically adjacent taps x 4 K-steps of one load group, fully unrolled (tap r: r*tw rows further down the box).
+template <int kR>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t tap16, uint32_t b16,
+                                           uint32_t idesc, bool first_group) {
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16_ss(d_tmem, umma_desc_lo(a_lo + r * tap16 + 2 * k), umma_desc_lo(b_lo + r * b16 + 2 * k), idesc,
+                   (r | k) != 0 ? 1u : (first_group ? 0u : 1u));
+  }
+}
+
+// MMA-issuer loop of the common case (weights resident in shared memory, one N sub-tile, one channel tile per CTA),
+// specialised on the number of vertically adjacent taps: no per-group branching, barrier addresses as plain integers.
+template <int kR>
+__device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_groups, int n_stages, uint32_t a_lo0,
+                                                  uint32_t stage16, uint32_t b_lo0, uint32_t tap16, uint32_t b16,
+                                                  uint32_t idesc, uint32_t tmem_base, uint32_t n_tile, int acc_mask,
+                                                  int acc_shift, uint32_t full_bar, uint32_t empty_bar,
+                                                  uint32_t tfull_bar, uint32_t tempty_bar) {
+  int s = 0;
+  uint32_t ph = 0;
+  uint32_t a_lo = a_lo0;
+  uint32_t item = 0;
+  for (int tile = t_begin; tile < t_end; ++tile, ++item) {
+    const int as = item & acc_mask;
+    mbar_wait_a(tempty_bar + 8 * as, ((item >> acc_shift) & 1) ^ 1u);    // epilogue has drained this accumulator stage
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + as * n_tile;
+    uint32_t b_lo = b_lo0;
+    for (int g = 0; g < n_groups; ++g) {
+      mbar_wait_a(full_bar + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_taps<kR>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
+        umma_commit_a(empty_bar + 8 * s);
+      }
+      __syncwarp();
+      b_lo += kR * b16;
+      a_lo += stage16;
+      if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+    }
+    if (elect_one()) umma_commit_a(tfull_bar + 8 * as);
+    __syncwarp();
+  }
+}
+
 constexpr uint32_t kRuntimeFlags = 0x80000000u;            // template value: epilogue flags are read from the params
 
 // kFlags: the CCDM_EPI_* set compiled into the epilogue (dead branches vanish), or kRuntimeFlags.
@@ -147,22 +200,25 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     }
     __syncwarp();
     griddep_wait();                                        // activations below are the previous kernels' outputs
-    uint32_t it = 0;
+    // No divisions in the loop: the single producer lane is latency-bound, every instruction counts.
+    int twi = t_begin % p.tiles_w, thi = (t_begin / p.tiles_w) % p.tiles_h, tbi = t_begin / tiles_per_sample;
+    const int n_stages = p.stages, n_groups = p.ngroups;
+    const uint32_t stage_bytes = p.stage_bytes;
+    const bool b_res = p.b_resident != 0;
+    int s = 0;                                             // ring slot of the next load group
+    uint32_t ph = 0;                                       // ... and how many times the ring has wrapped (mod 2)
     for (int tile = t_begin; tile < t_end; ++tile) {
-      const int w0 = (tile % p.tiles_w) * p.tw;
-      const int h0 = ((tile / p.tiles_w) % p.tiles_h) * p.th;
-      const int b0 = (tile / tiles_per_sample) * p.tb;
+      const int w0 = twi * p.tw, h0 = thi * p.th, b0 = tbi * p.tb;
+      if (++twi == p.tiles_w) { twi = 0; if (++thi == p.tiles_h) { thi = 0; ++tbi; } }
       const int wrow = b0 * p.w_batch_rows + z * p.n_rows + n_base;
-      for (int g = 0; g < p.ngroups; ++g, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
+      for (int g = 0; g < n_groups; ++g) {
         mbar_wait(&aux->a_empty[s], ph ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&aux->a_full[s], p.stage_bytes);
+          mbar_arrive_expect_tx(&aux->a_full[s], stage_bytes);
           const int4 e = s_sched[g];
-          uint8_t* st = ring + static_cast<size_t>(s) * p.stage_bytes;
+          uint8_t* st = ring + static_cast<size_t>(s) * stage_bytes;
           tma_load_4d(&maps.a[e.x], &aux->a_full[s], st, e.w, w0 + e.y, h0 + e.z, b0);
-          if (!p.b_resident) {
+          if (!b_res) {
             for (int r = 0; r < p.R; ++r)
               for (int sub = 0; sub < p.nsub; ++sub)
                 tma_load_2d(&maps.b, &aux->a_full[s], st + p.a_bytes + r * b_bytes + sub * p.n_sub * 128,
@@ -170,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
           }
         }
         __syncwarp();
+        if (++s == n_stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -184,48 +241,76 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       mbar_wait(&aux->b_full, 0);
       tc_fence_after();
     }
-    uint32_t it0 = 0;                                      // stage counter of the tile's first load group
+    // The issuing lane is latency-bound (a serial chain of uniform-datapath instructions), so the loop carries running
+    // ring / phase counters instead of dividing, keeps the loop invariants in registers and unrolls the taps with
+    // compile-time offsets.  Descriptor low words already contain the constant LBO bit: advancing is one add.
+    const uint32_t desc_lo = static_cast<uint32_t>(kUmmaDescSw128);          // 1 << 16
+    const uint32_t a_lo0 = ring16 | desc_lo, b_res_lo = res16 | desc_lo;
+    const int n_stages = p.stages, n_groups = p.ngroups, n_inner = p.n_inner, R = p.R;
+    const bool b_res = p.b_resident != 0, one_sub = p.nsub == 1;
+    const uint32_t n_tile = p.n_tile, nkb_b16 = static_cast<uint32_t>(p.nkb) * b16, rb16 = static_cast<uint32_t>(R) * b16;
+    const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages >> 1;
+    if (b_res && one_sub && n_inner == 1 && R <= 3) {
+      const uint32_t full_bar = smem_u32(&aux->a_full[0]), empty_bar = smem_u32(&aux->a_empty[0]);
+      const uint32_t tfull_bar = smem_u32(&aux->tmem_full[0]), tempty_bar = smem_u32(&aux->tmem_empty[0]);
+      if (R == 3)
+        mma_loop_resident<3>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+                             n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+      else if (R == 2)
+        mma_loop_resident<2>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+                             n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+      else
+        mma_loop_resident<1>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+                             n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+    } else {
+    int s = 0;                                             // ring slot of the tile's next load group
+    uint32_t ph = 0;
     uint32_t item = 0;                                     // (pixel tile, channel tile) pairs = accumulator uses
-    for (int tile = t_begin; tile < t_end; ++tile, it0 += p.ngroups) {
-      for (int nt = 0; nt < p.n_inner; ++nt, ++item) {
-        const int as = item & (p.acc_stages - 1);
-        const uint32_t aph = (item >> (p.acc_stages >> 1)) & 1;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int s_tile = s;
+      const uint32_t ph_tile = ph;
+      for (int nt = 0; nt < n_inner; ++nt, ++item) {
+        const int as = item & acc_mask;
+        const uint32_t aph = (item >> acc_shift) & 1;
         mbar_wait(&aux->tmem_empty[as], aph ^ 1u);         // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * p.n_tile;
-        for (int g = 0; g < p.ngroups; ++g) {
-          const uint32_t it = it0 + g;
-          const int s = it % p.stages;
-          if (nt == 0) {                                   // the boxes of a tile stay resident for all its channel tiles
-            mbar_wait(&aux->a_full[s], (it / p.stages) & 1);
+        const uint32_t d_tmem = tmem_base + as * n_tile;
+        s = s_tile;                                        // the boxes of a tile stay resident for all its channel tiles
+        ph = ph_tile;
+        uint32_t b_lo = b_res_lo + nt * nkb_b16;
+        for (int g = 0; g < n_groups; ++g) {
+          if (nt == 0) {
+            mbar_wait(&aux->a_full[s], ph);
             tc_fence_after();
           }
-          const uint32_t a16 = ring16 + s * stage16;
+          const uint32_t a_lo = a_lo0 + s * stage16;
+          if (!b_res) b_lo = a_lo + abytes16;
           if (elect_one()) {
-            for (int r = 0; r < p.R; ++r) {
-              const uint32_t at = a16 + r * tap16;                 // tap r: r*tw rows further down the same box
-              const uint32_t bt = p.b_resident ? res16 + ((nt * p.nkb) + g * p.R + r) * b16 : a16 + abytes16 + r * b16;
-              if (p.nsub == 1) {
-#pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k)
-                  umma_bf16_ss(d_tmem, umma_desc_sw128_a16(at + 2 * k), umma_desc_sw128_a16(bt + 2 * k), idesc,
-                               (g | r | k) != 0 ? 1u : 0u);
-              } else {
+            if (one_sub) {
+              if (R == 3) issue_taps<3>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
+              else if (R == 1) issue_taps<1>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
+              else if (R == 2) issue_taps<2>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
+              else issue_taps<4>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
+            } else {
+              for (int r = 0; r < R; ++r) {
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k)
                   for (int sub = 0; sub < 2; ++sub)
-                    umma_bf16_ss(d_tmem + sub * p.n_sub, umma_desc_sw128_a16(at + 2 * k),
-                                 umma_desc_sw128_a16(bt + sub * sub16 + 2 * k), idesc, (g | r | k) != 0 ? 1u : 0u);
+                    umma_bf16_ss(d_tmem + sub * p.n_sub, umma_desc_lo(a_lo + r * tap16 + 2 * k),
+                                 umma_desc_lo(b_lo + r * b16 + sub * sub16 + 2 * k), idesc, (g | r | k) != 0 ? 1u : 0u);
               }
             }
-            if (nt == p.n_inner - 1) umma_commit(&aux->a_empty[s]);   // box reusable once the last MMAs have read it
+            if (nt == n_inner - 1) umma_commit(&aux->a_empty[s]);   // box reusable once the last MMAs have read it
           }
           __syncwarp();
+          b_lo += rb16;
+          if (++s == n_stages) { s = 0; ph ^= 1u; }
         }
         if (elect_one()) umma_commit(&aux->tmem_full[as]);   // accumulators of this (tile, channel tile) complete
         __syncwarp();
       }
     }
+    }  // generic path
   } else {
     // ============================================================== epilogue (warps 2..9)
     const int ew = warp - 2;
