@@ -85,6 +85,17 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
       : "memory");
   if (!ok) mbar_wait_slow(bar_addr, parity);
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(const CUtensorMap* m, uint32_t bar_addr, uint32_t dst_addr, int c0, int c1,
+                                              int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];"
+      ::"r"(dst_addr), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }

@@ -127,6 +127,58 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
   }
 }
 
+// MMA-issuer loop (one N sub-tile), specialised on the number of vertically adjacent taps and on whether the weights
+// are resident in shared memory or ride in the stage behind the A box: no per-group branching, barrier addresses as
+// plain integers.  n_inner > 1: every CTA walks several channel tiles of the same boxes (qkv), which stay in the ring
+// until the last channel tile has read them.
+template <int kR, bool kRes, bool kMultiN>
+__device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_groups, int n_stages, int n_inner_rt,
+                                              uint32_t a_lo0, uint32_t stage16, uint32_t abytes16, uint32_t b_lo0,
+                                              uint32_t nkb_b16, uint32_t tap16, uint32_t b16, uint32_t idesc,
+                                              uint32_t tmem_base, uint32_t n_tile, int acc_mask, int acc_shift,
+                                              uint32_t full_bar, uint32_t empty_bar, uint32_t tfull_bar,
+                                              uint32_t tempty_bar) {
+  const int n_inner = kMultiN ? n_inner_rt : 1;             // compile-time 1 for the common case: no restore code
+  int s = 0;
+  uint32_t ph = 0;
+  uint32_t a_lo = a_lo0;
+  uint32_t item = 0;
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int s_tile = s;
+    const uint32_t ph_tile = ph, a_tile = a_lo;
+    uint32_t b_nt = b_lo0;
+    for (int nt = 0; nt < n_inner; ++nt, ++item, b_nt += nkb_b16) {
+      const int as = item & acc_mask;
+      mbar_wait_a(tempty_bar + 8 * as, ((item >> acc_shift) & 1) ^ 1u);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * n_tile;
+      if (kMultiN) {
+        s = s_tile;
+        ph = ph_tile;
+        a_lo = a_tile;
+      }
+      uint32_t b_lo = b_nt;
+      const bool last_nt = !kMultiN || nt == n_inner - 1;
+      for (int g = 0; g < n_groups; ++g) {
+        if (!kMultiN || nt == 0) {
+          mbar_wait_a(full_bar + 8 * s, ph);
+          tc_fence_after();
+        }
+        if (elect_one()) {
+          issue_taps<kR>(d_tmem, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0);
+          if (last_nt) umma_commit_a(empty_bar + 8 * s);   // box reusable once the last MMAs have read it
+        }
+        __syncwarp();
+        b_lo += kR * b16;
+        a_lo += stage16;
+        if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+      }
+      if (elect_one()) umma_commit_a(tfull_bar + 8 * as);
+      __syncwarp();
+    }
+  }
+}
+
 constexpr uint32_t kRuntimeFlags = 0x80000000u;            // template value: epilogue flags are read from the params
 
 // kFlags: the CCDM_EPI_* set compiled into the epilogue (dead branches vanish), or kRuntimeFlags.
@@ -250,18 +302,31 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const bool b_res = p.b_resident != 0, one_sub = p.nsub == 1;
     const uint32_t n_tile = p.n_tile, nkb_b16 = static_cast<uint32_t>(p.nkb) * b16, rb16 = static_cast<uint32_t>(R) * b16;
     const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages >> 1;
-    if (b_res && one_sub && n_inner == 1 && R <= 3) {
+    if (one_sub && R <= 3 && (n_inner == 1 || (R == 1 && b_res))) {
       const uint32_t full_bar = smem_u32(&aux->a_full[0]), empty_bar = smem_u32(&aux->a_empty[0]);
       const uint32_t tfull_bar = smem_u32(&aux->tmem_full[0]), tempty_bar = smem_u32(&aux->tmem_empty[0]);
-      if (R == 3)
-        mma_loop_resident<3>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                             n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
-      else if (R == 2)
-        mma_loop_resident<2>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                             n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
-      else
-        mma_loop_resident<1>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                             n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+#define CCDM_MMA_LOOP(KR, RES, MULTI)                                                                                  \
+  mma_loop_fast<KR, RES, MULTI>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo, nkb_b16, \
+                                tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, \
+                                tempty_bar)
+      if (n_inner > 1) {                                   // several channel tiles per box (qkv): weights always resident
+        CCDM_MMA_LOOP(1, true, true);
+      } else if (b_res) {
+        if (R == 3)
+          mma_loop_resident<3>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+        else if (R == 2)
+          mma_loop_resident<2>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+        else
+          mma_loop_resident<1>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+      } else {
+        if (R == 3) CCDM_MMA_LOOP(3, false, false);
+        else if (R == 2) CCDM_MMA_LOOP(2, false, false);
+        else CCDM_MMA_LOOP(1, false, false);
+      }
+#undef CCDM_MMA_LOOP
     } else {
     int s = 0;                                             // ring slot of the tile's next load group
     uint32_t ph = 0;
