@@ -55,6 +55,21 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// R taps x 8 K-steps (16 positions each) of one position tile; descriptor low words hold (address >> 4) | LBO.
+template <int kR>
+__device__ __forceinline__ void wgrad_taps(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo, uint32_t tap16,
+                                           uint32_t idesc, uint32_t acc_first) {
+  constexpr uint64_t hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                          (static_cast<uint64_t>(2) << 61);
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      umma_bf16_ss(tmem_base + r * 64, hi | (a_lo + k * 128), hi | (b_lo + r * tap16 + k * 128), idesc,
+                   k != 0 ? 1u : acc_first);
+  }
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgMaps maps, const WgDev p) {
   extern __shared__ __align__(1024) uint8_t wg_smem[];
   uint8_t* ring = wg_smem;
@@ -88,46 +103,57 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   const uint32_t tmem_base = aux->tmem_slot;
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
-    uint32_t it = 0;
-    for (int t = t0; t < t1; ++t, ++it) {
-      const int s = it % p.stages;
-      mbar_wait(&aux->empty[s], ((it / p.stages) & 1) ^ 1u);
+    // ---------------------------------------------------------------- TMA producer (single lane: no divisions, running
+    // ring / phase counters, integer shared-memory addresses)
+    int tx = t0 % p.tiles_w, ty = (t0 / p.tiles_w) % p.tiles_h, tz = t0 / (p.tiles_w * p.tiles_h);
+    const uint32_t full_bar = smem_u32(&aux->full[0]), empty_bar = smem_u32(&aux->empty[0]);
+    const uint32_t ring_a = smem_u32(ring);
+    const int n_stages = p.stages;
+    const CUtensorMap* const dzm = &maps.dz[z];
+    const CUtensorMap* const srm = &maps.src[e.x];
+    int s = 0;
+    uint32_t ph = 0, st_a = ring_a;
+    for (int t = t0; t < t1; ++t) {
+      mbar_wait_a(empty_bar + 8 * s, ph ^ 1u);
       if (elect_one()) {
-        const int tx = t % p.tiles_w;
-        const int ty = (t / p.tiles_w) % p.tiles_h;
-        const int tz = t / (p.tiles_w * p.tiles_h);
-        uint8_t* st = ring + (size_t)s * p.stage_bytes;
-        mbar_arrive_expect_tx(&aux->full[s], p.tx_bytes);
-        tma_load_4d(&maps.dz[z], &aux->full[s], st, mt * 128, tx * p.tw, ty * p.th, tz * p.tb);
-        tma_load_4d(&maps.dz[z], &aux->full[s], st + kWgABlock, mt * 128 + 64, tx * p.tw, ty * p.th, tz * p.tb);
-        tma_load_4d(&maps.src[e.x], &aux->full[s], st + 2 * kWgABlock, e.w, tx * p.tw + e.y, ty * p.th + e.z,
-                    tz * p.tb);
+        const int cw = tx * p.tw, chh = ty * p.th, cb = tz * p.tb;
+        mbar_arrive_expect_tx_a(full_bar + 8 * s, p.tx_bytes);
+        tma_load_4d_a(dzm, full_bar + 8 * s, st_a, mt * 128, cw, chh, cb);
+        tma_load_4d_a(dzm, full_bar + 8 * s, st_a + kWgABlock, mt * 128 + 64, cw, chh, cb);
+        tma_load_4d_a(srm, full_bar + 8 * s, st_a + 2 * kWgABlock, e.w, cw + e.y, chh + e.z, cb);
       }
       __syncwarp();
+      if (++tx == p.tiles_w) { tx = 0; if (++ty == p.tiles_h) { ty = 0; ++tz; } }
+      st_a += p.stage_bytes;
+      if (++s == n_stages) { s = 0; ph ^= 1u; st_a = ring_a; }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one elected lane)
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one elected lane).
+    // The lane is latency-bound: descriptors advance by integer adds on a precomputed low word (address >> 4 | LBO),
+    // the taps are unrolled per R, barriers are addressed as integers.
     const uint32_t idesc = umma_idesc_bf16_mn(128, 64);
-    uint32_t it = 0;
-    for (int t = t0; t < t1; ++t, ++it) {
-      const int s = it % p.stages;
-      mbar_wait(&aux->full[s], (it / p.stages) & 1);
+    const uint32_t full_bar = smem_u32(&aux->full[0]), empty_bar = smem_u32(&aux->empty[0]);
+    const uint32_t lo_flags = static_cast<uint32_t>((kWgABlock >> 4) & 0x3FFF) << 16;       // LBO = 16 KiB block stride
+    const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFF) >> 4) | lo_flags;
+    const uint32_t stage16 = p.stage_bytes >> 4, tap16 = static_cast<uint32_t>(p.tw) * 8;
+    const int n_stages = p.stages;
+    int s = 0;
+    uint32_t ph = 0, a_lo = a_lo0;
+    uint32_t first = 0;                                    // 0 for the first position tile: overwrite the accumulators
+    for (int t = t0; t < t1; ++t) {
+      mbar_wait_a(full_bar + 8 * s, ph);
       tc_fence_after();
-      const uint32_t base = smem_u32(ring + (size_t)s * p.stage_bytes);
       if (elect_one()) {
-        for (int r = 0; r < p.R; ++r) {
-          const uint32_t bbase = base + 2 * kWgABlock + (uint32_t)(r * p.tw) * 128u;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t adesc = umma_desc_mn_sw128(base + k * 2048, kWgABlock);
-            const uint64_t bdesc = umma_desc_mn_sw128(bbase + k * 2048, kWgABlock);
-            umma_bf16_ss(tmem_base + r * 64, adesc, bdesc, idesc, (it | (uint32_t)k) != 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(&aux->empty[s]);
+        const uint32_t b_lo = a_lo + ((2 * kWgABlock) >> 4);
+        if (p.R == 3) wgrad_taps<3>(tmem_base, a_lo, b_lo, tap16, idesc, first);
+        else if (p.R == 2) wgrad_taps<2>(tmem_base, a_lo, b_lo, tap16, idesc, first);
+        else wgrad_taps<1>(tmem_base, a_lo, b_lo, tap16, idesc, first);
+        umma_commit_a(empty_bar + 8 * s);
       }
       __syncwarp();
+      first = 1;
+      a_lo += stage16;
+      if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
     }
     if (t1 > t0) {
       if (elect_one()) umma_commit(&aux->acc_full);
