@@ -59,6 +59,7 @@ struct TapGemmDev {
   float* out_rowss;
   float q_scale, gain_mul;
   int q_cols;
+  int epi_alt;                            // the two epilogue warp groups take alternate tiles (n_tile <= 64)
 };
 
 // aux shared-memory block (after the resident weights and the stage ring)
@@ -71,6 +72,11 @@ struct __align__(16) TapGemmAux {
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+// alternate-tile mode: each group of four epilogue warps synchronises on its own named barrier (ids 1 and 2)
+__device__ __forceinline__ void epi_bar_g(bool alt, int grp) {
+  if (alt) asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+  else epi_bar();
+}
 
 __device__ __forceinline__ float fast_silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     mbar_init(&aux->b_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&aux->tmem_full[s], 1);
-      mbar_init(&aux->tmem_empty[s], kEpiWarps);
+      mbar_init(&aux->tmem_empty[s], p.epi_alt ? kEpiWarps / 2 : kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -387,7 +393,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const uint32_t flags = kflags;
     const int nchunk = p.n_tile / 32;
     const int per_half = (nchunk + 1) >> 1;
-    const int c_lo = half * per_half, c_hi = min(nchunk, c_lo + per_half);
+    // Two ways to split the epilogue between the two groups of four warps: by column halves of the same tile, or
+    // (narrow tiles) by tile parity -- each group then owns whole rows of every other tile, the two tiles' epilogues
+    // overlap, the row's sum of squares needs no exchange and every barrier is group-local.
+    const bool alt = p.epi_alt != 0;
+    const int gi = alt ? half : 0;                         // this group's slot in the per-group shared-memory vectors
+    const int et_g = alt ? (et & 127) : et;                // thread index inside the synchronising group
+    const int g_threads = alt ? 128 : kEpiThreads;
+    const int t_step = alt ? 2 : 1;
+    const int c_lo = alt ? 0 : half * per_half, c_hi = alt ? nchunk : min(nchunk, c_lo + per_half);
     const bool tile_ss = (flags & CCDM_EPI_SS) && p.tb == 1;   // scale/shift uniform over the tile
     const bool use_rs = (flags & CCDM_EPI_ROWSCALE) != 0;
     const uint32_t trow_lane = static_cast<uint32_t>(q * 32) << 16;
@@ -397,11 +411,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     uint32_t r[32];
     griddep_wait();                                        // rowss / scale-shift / residual reads and all stores below
     int ss_b = -1;                                         // sample whose scale/shift currently sits in aux->gs/sh
-    if (kStoreTma && et == 0) {
+    if (kStoreTma && et_g == 0) {
       for (int i = 0; i < CCDM_MAX_Z; ++i) tma_prefetch_desc(&maps.o[i]);
     }
     // tile coordinates advance incrementally (the CTA's tiles are contiguous): no divisions in the loop
-    int twi = t_begin % p.tiles_w, thi = (t_begin / p.tiles_w) % p.tiles_h, tbi = t_begin / tiles_per_sample;
+    const int t_first = t_begin + (alt ? half : 0);
+    int twi = t_first % p.tiles_w, thi = (t_first / p.tiles_w) % p.tiles_h, tbi = t_first / tiles_per_sample;
+    auto advance = [&]() { if (++twi == p.tiles_w) { twi = 0; if (++thi == p.tiles_h) { thi = 0; ++tbi; } } };
 
     auto row_of = [&](int w0, int h0, int b0, bool& valid, int& bs, long long& pix) {
       const int w = w0 + lw, h = h0 + lh, b = b0 + lb;
@@ -410,35 +426,36 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       pix = (static_cast<long long>(bs) * p.gH + (h < p.gH ? h : 0)) * p.gW + (w < p.gW ? w : 0);
     };
     float rss_next = 1.f;                                  // A-row sum of squares, fetched one tile ahead
-    if (use_rs && t_begin < t_end) {
+    if (use_rs && t_first < t_end) {
       bool v0; int b_; long long px;
       row_of(twi * p.tw, thi * p.th, tbi * p.tb, v0, b_, px);
       if (v0) rss_next = __ldg(p.rowss + px);
     }
 
-    int lt = -1;                                           // accumulator-use counter: (pixel tile, channel tile) pairs
-    for (int tile = t_begin; tile < t_end; ++tile) {
+    int lt = alt ? half - 2 : -1;                          // accumulator-use counter: (pixel tile, channel tile) pairs
+    for (int tile = t_first; tile < t_end; tile += t_step) {
       const int w0 = twi * p.tw, h0 = thi * p.th, b0 = tbi * p.tb;
-      if (++twi == p.tiles_w) { twi = 0; if (++thi == p.tiles_h) { thi = 0; ++tbi; } }
+      advance();
+      if (alt) advance();                                  // (twi, thi, tbi) now name this group's next tile
       bool valid; int bs; long long pix;
       row_of(w0, h0, b0, valid, bs, pix);
       const int w = w0 + lw, h = h0 + lh;
 
-      if (tile_ss && b0 != ss_b) {                         // new sample (uniform over the epilogue threads): refresh
-        epi_bar();                                         // everyone is done with the previous sample's vectors
+      if (tile_ss && b0 != ss_b) {                         // new sample (uniform over the group's threads): refresh
+        epi_bar_g(alt, half);                              // everyone is done with the previous sample's vectors
         const float* ssrow = p.ss + static_cast<long long>(b0) * p.ss_ld + p.ss_off + n_base;
-        for (int c = et; c < p.n_tile; c += kEpiThreads) {
+        for (int c = et_g; c < p.n_tile; c += g_threads) {
           const bool ok = (n_base + c) < p.N;
-          aux->gs[0][c] = ok ? ((flags & CCDM_EPI_RMSNORM) ? aux->gain[c] : 1.f) * (1.f + ssrow[c]) : 0.f;
-          aux->sh[0][c] = ok ? ssrow[p.N + c] : 0.f;
+          aux->gs[gi][c] = ok ? ((flags & CCDM_EPI_RMSNORM) ? aux->gain[c] : 1.f) * (1.f + ssrow[c]) : 0.f;
+          aux->sh[gi][c] = ok ? ssrow[p.N + c] : 0.f;
         }
-        epi_bar();
+        epi_bar_g(alt, half);
         ss_b = b0;
       }
       // global operands are requested BEFORE waiting for the accumulators so their latency overlaps the MMAs:
       // next tile's A-row sum of squares and, when it fits in registers, this tile's residual rows
       const float rss_raw = rss_next;
-      if (use_rs && tile + 1 < t_end) {
+      if (use_rs && tile + t_step < t_end) {
         bool v1; int b_; long long px;
         row_of(twi * p.tw, thi * p.th, tbi * p.tb, v1, b_, px);
         rss_next = v1 ? __ldg(p.rowss + px) : 1.f;
@@ -460,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       }
 
       for (int nt = 0; nt < p.n_inner; ++nt) {
-      ++lt;
+      lt += t_step;
       const int as = lt & acc_mask;
       const uint32_t aph = (lt >> acc_shift) & 1;
       const int n0 = n_base + nt * p.n_tile;               // first output channel of this item
@@ -494,7 +511,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       const long long oo = p.ooff[z] + static_cast<long long>(bs) * p.osB + static_cast<long long>(h) * p.osH +
                            static_cast<long long>(w) * p.osW + n0;
       uint8_t* const stg_row = stg + static_cast<size_t>(lt & ob_mask) * p.out_bytes + m * 128;
-      float out_ss = 0.f;
+      float out_ss = 0.f, out_ss_hi = 0.f;                 // alternate-tile mode keeps the two column halves apart so that
+                                                           // the sum rounds exactly as in the split mode (batch-shard invariance)
+      if (kStoreTma && alt) {
+        // A group re-uses its ONE staging buffer for every tile it owns: the bulk store of its previous tile must have
+        // finished reading the buffer before anyone overwrites it (in split mode the two buffers alternate instead).
+        if (et_g == 0) tma_store_wait_read0();
+        epi_bar_g(true, half);
+      }
 
       for (int c = c_lo; c < c_hi; ++c) {
         tmem_ld32(trow + c * 32, r);
@@ -515,8 +539,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         }
         if (flags & CCDM_EPI_RMSNORM) {
           if (tile_ss) {
-            const float2* g2 = reinterpret_cast<const float2*>(aux->gs[0] + c * 32);
-            const float2* s2 = reinterpret_cast<const float2*>(aux->sh[0] + c * 32);
+            const float2* g2 = reinterpret_cast<const float2*>(aux->gs[gi] + c * 32);
+            const float2* s2 = reinterpret_cast<const float2*>(aux->sh[gi] + c * 32);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __ffma2_rn(__fmul2_rn(v[i], inv2), g2[i], s2[i]);
           } else {
@@ -526,8 +550,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
           }
         }
         if (!(flags & CCDM_EPI_RMSNORM) && tile_ss) {      // conditional batch norm: per-(sample, channel) affine map
-          const float2* g2 = reinterpret_cast<const float2*>(aux->gs[0] + c * 32);
-          const float2* s2 = reinterpret_cast<const float2*>(aux->sh[0] + c * 32);
+          const float2* g2 = reinterpret_cast<const float2*>(aux->gs[gi] + c * 32);
+          const float2* s2 = reinterpret_cast<const float2*>(aux->sh[gi] + c * 32);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __ffma2_rn(v[i], g2[i], s2[i]);
         }
@@ -627,7 +651,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             if ((flags & CCDM_EPI_SUMSQ_OUT) && n0 + c * 32 + g * 8 < p.N) {
               const float a0 = bf16_lo(u.x), a1 = bf16_hi(u.x), a2 = bf16_lo(u.y), a3 = bf16_hi(u.y);
               const float a4 = bf16_lo(u.z), a5 = bf16_hi(u.z), a6 = bf16_lo(u.w), a7 = bf16_hi(u.w);
-              out_ss += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+              const float sq8 = a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+              if (alt && c >= per_half) out_ss_hi += sq8;
+              else out_ss += sq8;
             }
           }
         }
@@ -637,31 +663,34 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&aux->tmem_empty[as]);
       }
-      if ((flags & CCDM_EPI_SUMSQ_OUT) && half == 1) aux->part[lt & 1][m] = out_ss;   // combine the two column halves
+      if ((flags & CCDM_EPI_SUMSQ_OUT) && !alt && half == 1) aux->part[lt & 1][m] = out_ss;   // combine the column halves
       if (kStoreTma) {
         // staging complete -> one thread hands the tile to the TMA unit.  Before the barrier it makes sure the
         // PREVIOUS tile's bulk stores have finished reading their buffer, which the next tile will overwrite.
         fence_proxy_async_smem();
-        if (et == 0) tma_store_wait_read0();
-        epi_bar();
-        if (et == 0) {
+        if (et_g == 0) tma_store_wait_read0();
+        epi_bar_g(alt, half);
+        if (et_g == 0) {
           const uint8_t* sbuf = stg + static_cast<size_t>(lt & ob_mask) * p.out_bytes;
           for (int pn = 0; pn < npanels; ++pn)
             if (n0 + pn * 64 < p.N) tma_store_4d(&maps.o[z], sbuf + pn * 16384, n0 + pn * 64, w0, h0, b0);
           tma_store_commit();
           if (p.out_bufs == 1) tma_store_wait_read0();
         }
-        if (p.out_bufs == 1) epi_bar();
-      } else if (flags & CCDM_EPI_SUMSQ_OUT) {
+        if (p.out_bufs == 1) epi_bar_g(alt, half);
+      } else if ((flags & CCDM_EPI_SUMSQ_OUT) && !alt) {
         epi_bar();
       }
-      if ((flags & CCDM_EPI_SUMSQ_OUT) && half == 0 && valid) p.out_rowss[pix] = out_ss + aux->part[lt & 1][m];
+      if ((flags & CCDM_EPI_SUMSQ_OUT) && valid) {
+        if (alt) p.out_rowss[pix] = out_ss + out_ss_hi;
+        else if (half == 0) p.out_rowss[pix] = out_ss + aux->part[lt & 1][m];
+      }
       }  // channel tiles of this pixel tile
     }
   }
 
   // ---------------------------------------------------------------- teardown
-  if (kStoreTma && tid == 64) tma_store_wait_all();      // et == 0: the thread that issued the bulk stores
+  if (kStoreTma && (tid == 64 || (p.epi_alt && tid == 64 + 128))) tma_store_wait_all();   // the threads that issued bulk stores
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -915,6 +944,10 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > useful) stages = useful;
   if (p.n_inner > 1 && stages < 2 * a->ngroups) stages = 2 * a->ngroups <= kMaxStages ? 2 * a->ngroups : a->ngroups;
+  // narrow tiles: the two epilogue warp groups take alternate tiles (needs both accumulator stages and both staging
+  // buffers, one channel tile per CTA and more than one tile per CTA)
+  p.epi_alt = (a->n_tile <= 64 && p.n_inner == 1 && p.acc_stages == 2 && tiles_per_cta >= 2 &&
+               (!p.store_tma || p.out_bufs == 2)) ? 1 : 0;
   CCDM_REQUIRE(stages >= 1, CCDM_ERR_UNSUPPORTED_SHAPE,
                "tapgemm: one pipeline stage (%u bytes) does not fit shared memory", p.stage_bytes);
   p.stages = stages;
