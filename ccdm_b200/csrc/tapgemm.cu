@@ -946,7 +946,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   if (p.n_inner > 1 && stages < 2 * a->ngroups) stages = 2 * a->ngroups <= kMaxStages ? 2 * a->ngroups : a->ngroups;
   // narrow tiles: the two epilogue warp groups take alternate tiles (needs both accumulator stages and both staging
   // buffers, one channel tile per CTA and more than one tile per CTA)
-  p.epi_alt = (a->n_tile <= 64 && p.n_inner == 1 && p.acc_stages == 2 && tiles_per_cta >= 2 &&
+  p.epi_alt = (a->n_tile <= 128 && p.n_inner == 1 && p.acc_stages == 2 && tiles_per_cta >= 2 &&
                (!p.store_tma || p.out_bufs == 2)) ? 1 : 0;
   CCDM_REQUIRE(stages >= 1, CCDM_ERR_UNSUPPORTED_SHAPE,
                "tapgemm: one pipeline stage (%u bytes) does not fit shared memory", p.stage_bytes);
