@@ -20,6 +20,7 @@
 //
 // Replaces the nn.Conv2d / nn.Linear call sites listed in include/ccdm_b200.h.
 #include <cstring>
+#include <type_traits>
 #include <mutex>
 
 #include "common.cuh"
@@ -520,7 +521,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         epi_bar_g(true, half);
       }
 
-      for (int c = c_lo; c < c_hi; ++c) {
+      // The chunk body is instantiated per column class (0 plain, 1 q-softmax, 2 k-exp) so that the branches do not
+      // merge with 32 live values (the merge cost one register move per value and chunk).
+      auto chunk_body = [&](const int c, auto cmode_tag) {
+        constexpr int kCMode = decltype(cmode_tag)::value;
         tmem_ld32(trow + c * 32, r);
         tmem_ld_wait();
         if (c == c_hi - 1) {                               // last TMEM read of this tile by this warp: release
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = make_float2(tanh_fast(v[i].x), tanh_fast(v[i].y));
         }
-        if ((flags & CCDM_EPI_QSOFTMAX) && (n0 + c * 32 < p.q_cols)) {
+        if constexpr (kCMode == 1) {
           float mx = fmaxf(v[0].x, v[0].y);
 #pragma unroll
           for (int i = 1; i < 16; ++i) mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], k2);
         }
-        if ((flags & CCDM_EPI_KEXP) && (n0 + c * 32 >= p.q_cols) && (n0 + c * 32 < 2 * p.q_cols)) {
+        if constexpr (kCMode == 2) {
           const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -657,6 +661,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             }
           }
         }
+      };
+      for (int c = c_lo; c < c_hi; ++c) {
+        const int col = n0 + c * 32;
+        if ((flags & CCDM_EPI_QSOFTMAX) && col < p.q_cols) chunk_body(c, std::integral_constant<int, 1>{});
+        else if ((flags & CCDM_EPI_KEXP) && col >= p.q_cols && col < 2 * p.q_cols) chunk_body(c, std::integral_constant<int, 2>{});
+        else chunk_body(c, std::integral_constant<int, 0>{});
       }
       if (c_lo >= c_hi) {                                  // this warp owns no columns (n_tile == 32): still release
         tc_fence_before();
