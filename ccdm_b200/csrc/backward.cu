@@ -76,56 +76,66 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
       dc[k] = dn[k];
     }
     if (rb + rstep < r1) fetch(rb + rstep);
-    float zf[kChunks][8], gy[kChunks][8];
-    float sq = 0.f;
+    // packed fp32x2 arithmetic throughout (FFMA2 / FMUL2 / FADD2): the kernel is issue-bound, not DRAM-bound
+    float2 zf[kChunks][4], gy[kChunks][4];
+    float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
       const uint4 zu = zc[k], du = dc[k];
-      const uint32_t zw[4] = {zu.x, zu.y, zu.z, zu.w}, dw[4] = {du.x, du.y, du.z, du.w};
+      zf[k][0] = make_float2(bf16_lo(zu.x), bf16_hi(zu.x));
+      zf[k][1] = make_float2(bf16_lo(zu.y), bf16_hi(zu.y));
+      zf[k][2] = make_float2(bf16_lo(zu.z), bf16_hi(zu.z));
+      zf[k][3] = make_float2(bf16_lo(zu.w), bf16_hi(zu.w));
+      gy[k][0] = make_float2(bf16_lo(du.x), bf16_hi(du.x));
+      gy[k][1] = make_float2(bf16_lo(du.y), bf16_hi(du.y));
+      gy[k][2] = make_float2(bf16_lo(du.z), bf16_hi(du.z));
+      gy[k][3] = make_float2(bf16_lo(du.w), bf16_hi(du.w));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        zf[k][2 * j] = bf16_lo(zw[j]);
-        zf[k][2 * j + 1] = bf16_hi(zw[j]);
-        gy[k][2 * j] = bf16_lo(dw[j]);
-        gy[k][2 * j + 1] = bf16_hi(dw[j]);
-        sq = fmaf(zf[k][2 * j], zf[k][2 * j], sq);
-        sq = fmaf(zf[k][2 * j + 1], zf[k][2 * j + 1], sq);
-      }
+      for (int j = 0; j < 4; ++j) sq2 = __ffma2_rn(zf[k][j], zf[k][j], sq2);
     }
-    sq = seg_sum(sq, gl, G, lane);
+    const float sq = seg_sum(sq2.x + sq2.y, gl, G, lane);
     const float inv = rsqrtf(fmaxf(sq, 1e-24f));                   // 1 / max(|z|, 1e-12)
-    float dot = 0.f;
+    const float2 inv2 = make_float2(inv, inv);
+    const float2 one2 = make_float2(1.f, 1.f), half2 = make_float2(0.5f, 0.5f);
+    float2 dot2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float zh = zf[k][j] * inv;
-        float du = gy[k][j];
+      for (int j = 0; j < 4; ++j) {
+        const float2 aj = make_float2(a[k][2 * j], a[k][2 * j + 1]);
+        const float2 zh = __fmul2_rn(zf[k][j], inv2);
+        float2 du = gy[k][j];
         if (flags & CCDM_EPI_SILU) {
-          const float u = fmaf(zh, a[k][j], sh[k][j]);
-          const float sig = sigmoid_fast(u);
-          du *= sig * fmaf(u, 1.f - sig, 1.f);
+          // silu'(u) = sig * (1 + u * (1 - sig)),  sig = 0.5 + 0.5 tanh(u / 2)
+          const float2 u = __ffma2_rn(zh, aj, make_float2(sh[k][2 * j], sh[k][2 * j + 1]));
+          const float2 hu = __fmul2_rn(u, half2);
+          const float2 sig = __ffma2_rn(make_float2(tanh_fast(hu.x), tanh_fast(hu.y)), half2, half2);
+          const float2 t = __ffma2_rn(u, make_float2(1.f - sig.x, 1.f - sig.y), one2);
+          du = __fmul2_rn(du, __fmul2_rn(sig, t));
         }
-        s1[k][j] = fmaf(du, zh, s1[k][j]);
-        s2[k][j] += du;
-        const float dzh = du * a[k][j];
-        dot = fmaf(zh, dzh, dot);
+        const float2 s1v = __ffma2_rn(du, zh, make_float2(s1[k][2 * j], s1[k][2 * j + 1]));
+        s1[k][2 * j] = s1v.x; s1[k][2 * j + 1] = s1v.y;
+        s2[k][2 * j] += du.x; s2[k][2 * j + 1] += du.y;
+        const float2 dzh = __fmul2_rn(du, aj);
+        dot2 = __ffma2_rn(zh, dzh, dot2);
         zf[k][j] = zh;
         gy[k][j] = dzh;
       }
     }
-    dot = seg_sum(dot, gl, G, lane);
+    const float dot = seg_sum(dot2.x + dot2.y, gl, G, lane);
+    const float2 ndot2 = make_float2(-dot, -dot);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
       const int ch = gl + G * k;
-      float o[8];
+      float2 o[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o[j] = (gy[k][j] - zf[k][j] * dot) * inv;
-        s3[k][j] += o[j];
+      for (int j = 0; j < 4; ++j) {
+        o[j] = __fmul2_rn(__ffma2_rn(zf[k][j], ndot2, gy[k][j]), inv2);
+        s3[k][2 * j] += o[j].x; s3[k][2 * j + 1] += o[j].y;
       }
       if (live && ch < nchunk)
-        dz[rowoff + ch] = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        dz[rowoff + ch] = make_uint4(pack_bf16(o[0].x, o[0].y), pack_bf16(o[1].x, o[1].y), pack_bf16(o[2].x, o[2].y),
+                                     pack_bf16(o[3].x, o[3].y));
     }
   }
 #pragma unroll
