@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib as L
-from .utils import default, identity, normalize_to_neg_one_to_one, unnormalize_to_zero_to_one, prob_mask_like
+from .utils import default, normalize_to_neg_one_to_one, unnormalize_to_zero_to_one, prob_mask_like
 
 ModelPrediction = namedtuple("ModelPrediction", ["pred_noise", "pred_x_start"])
 

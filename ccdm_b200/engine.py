@@ -18,7 +18,7 @@ Layer -> kernel mapping (reference lines in CCDM_unified/models/unet.py):
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch

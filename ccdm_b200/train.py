@@ -36,7 +36,7 @@ from torch.autograd import Function
 
 from . import _lib as L
 from . import backward as K
-from .plan import n_tiling, plan_conv, tile_box
+from .plan import n_tiling, tile_box
 
 
 def _c(t: torch.Tensor) -> torch.Tensor:

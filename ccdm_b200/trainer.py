@@ -19,7 +19,7 @@ from . import dist as ccdm_dist
 from .ema import EMA
 from .optim import FusedAdam
 from .diffusion import generate_random_vectors
-from .utils import divisible_by, exists
+from .utils import divisible_by
 
 
 class Trainer(object):

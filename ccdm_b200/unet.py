@@ -8,8 +8,6 @@ calling the model on a CPU tensor raises.
 """
 from __future__ import annotations
 
-import math
-
 import torch
 from torch import nn
 
