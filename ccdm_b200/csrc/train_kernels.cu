@@ -110,12 +110,20 @@ __global__ void __launch_bounds__(256) linattn_prep_kernel(__nv_bfloat16* __rest
 // matrices m[b][h][d][e]:   transpose == 0: w[b][h*32+e][h*32+d] = m[b][h][d][e] * rs(d)     (out = m^T . in)
 //                           transpose != 0: w[b][h*32+d][h*32+e] = m[b][h][d][e] * rs(d)     (out = m   . in)
 // rs(d) = 1 / row_div[b][h*32+d] when row_div is given.
+// diag_only: write just the four 32x32 diagonal blocks (idx enumerates [b][row][32 columns of the row's head]); the
+// off-diagonal zeros of a persistent buffer are written once by the caller.
 __global__ void __launch_bounds__(256) linattn_pack_blockdiag_kernel(const float* __restrict__ m,
                                                                      const float* __restrict__ row_div,
                                                                      int transpose, __nv_bfloat16* __restrict__ w,
-                                                                     long long total) {
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+                                                                     long long total, int diag_only) {
+  long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
+  if (diag_only) {                                                 // idx = (b*128 + row)*32 + j  ->  full index
+    const int j = (int)(idx & 31);
+    const long long br = idx >> 5;
+    const int row_ = (int)(br & 127);
+    idx = (br << 7) + (row_ & ~31) + j;
+  }
   const int col = (int)(idx & 127), row = (int)((idx >> 7) & 127);
   const long long b = idx >> 14;
   float v = 0.f;
@@ -392,9 +400,10 @@ extern "C" int ccdm_linattn_prep(void* qkv, int32_t B, int32_t n, float* kmax, f
 extern "C" int ccdm_linattn_pack_blockdiag(const float* m, const float* row_div, int32_t transpose, void* w, int32_t B,
                                            void* stream) {
   CCDM_REQUIRE(m && w && B > 0, CCDM_ERR_BAD_ARG, "linattn_pack_blockdiag: bad args");
-  const long long total = (long long)B * 128 * 128;
+  const int diag_only = (transpose & 2) ? 1 : 0;                   // bit 1 of `transpose`: diagonal blocks only
+  const long long total = (long long)B * 128 * (diag_only ? 32 : 128);
   linattn_pack_blockdiag_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      m, row_div, transpose, (__nv_bfloat16*)w, total);
+      m, row_div, transpose & 1, (__nv_bfloat16*)w, total, diag_only);
   return after_launch("linattn_pack_blockdiag_kernel");
 }
 

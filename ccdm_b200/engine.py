@@ -532,7 +532,8 @@ class UnetProgram(Program):
             # "image" is the (packed, bf16) to_out weight itself -- C pixels x 128 channels, the same for every sample
             # (batch stride 0) -- and whose per-sample weights are the block-diagonal contexts
             wb = self.buf(name + ".ctx_bd", (self.B * 128, 128), torch.bfloat16)
-            self.kernel("linattn_pack_blockdiag", m=ctx, row_div=None, transpose=1, w=wb, B=self.B)
+            wb.zero_()                                      # off-diagonal blocks stay zero: only the diagonal is rewritten
+            self.kernel("linattn_pack_blockdiag", m=ctx, row_div=None, transpose=1 | 2, w=wb, B=self.B)
             fplan = plan_conv("1x1", [hid], 128)
             wpack = self.weights.add(name + ".to_out.w/R1", conv_out.weight, plan_conv("1x1", [hid], C),
                                      n_tiling(C, False)[0])

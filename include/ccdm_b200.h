@@ -317,7 +317,8 @@ int ccdm_colsum_bf16(const void* x, int64_t rows, int32_t C, float* out, void* s
  * k <- exp(k - kmax[b][c]) with kmax the per-sample maximum over tokens (written to kmax [B][128]). */
 int ccdm_linattn_prep(void* qkv, int32_t B, int32_t n, float* kmax, float scale, void* stream);
 /* Per-sample block-diagonal [B][128][128] bf16 weights for ccdm_tapgemm (w_batch_rows = 128) from m = fp32
- * [B][4][32][32]: transpose == 0 -> w[b][h*32+e][h*32+d] = m[b][h][d][e] / row_div[b][h*32+d]; else rows/cols swapped. */
+ * [B][4][32][32]: (transpose & 1) == 0 -> w[b][h*32+e][h*32+d] = m[b][h][d][e] / row_div[b][h*32+d]; else rows/cols
+ * swapped.  transpose & 2: write only the four diagonal 32x32 blocks (the caller zeroed the buffer once). */
 int ccdm_linattn_pack_blockdiag(const float* m, const float* row_div, int32_t transpose, void* w, int32_t B, void* stream);
 /* dctx[b][h][d][e] = sum_n q_sm[b][n][h*32+d] * dout[b][n][h*32+e]  (tcgen05, same kernel as the context). */
 int ccdm_linattn_dcontext(const void* qkv, const void* dout, float* dctx, int32_t B, int32_t n, void* stream);

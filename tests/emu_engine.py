@@ -148,7 +148,7 @@ def run_kernel(r: KernelRec):
             m = m / a["row_div"].reshape(B, 4, 32, 1)
         w = torch.zeros(B, 128, 128)
         for h in range(4):
-            blk = m[:, h] if a["transpose"] else m[:, h].transpose(1, 2)     # rows d (transpose) or rows e
+            blk = m[:, h] if (a["transpose"] & 1) else m[:, h].transpose(1, 2)   # rows d (transpose) or rows e
             w[:, h * 32:(h + 1) * 32, h * 32:(h + 1) * 32] = blk
         a["w"].reshape(B, 128, 128).copy_(w.to(torch.bfloat16))
     elif k == "linattn_fold":
