@@ -63,6 +63,7 @@ class FusedAdam(torch.optim.Optimizer):
             self.step_count = torch.zeros(1, dtype=torch.float32, device=dev)
             self.grad_sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
             self._tab = _chunk_tables(ps, self._offsets, dev)
+        self._ptrs = [p.data_ptr() for p in ps]
         self._attach()
 
     # ------------------------------------------------------------------ gradient views
@@ -99,6 +100,14 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        ptrs = [p.data_ptr() for p in self._ps]
+        if ptrs != self._ptrs:                                     # a parameter's storage moved (.to(), load with assign)
+            for p in self._ps:
+                if not (p.is_cuda and p.device == self.flat_grad.device and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise RuntimeError("FusedAdam: a parameter left the device / dtype the optimizer was built for")
+            with torch.inference_mode(False):
+                self._tab = _chunk_tables(self._ps, self._offsets, self.flat_grad.device)
+            self._ptrs = ptrs
         self._attach()
         g = self.param_groups[0]
         ptrs, offs, ns = self._tab
