@@ -83,7 +83,10 @@ class CpuReference:
         return time.perf_counter() - t0
 
 
-def cpu_baseline(args, budget_s=15.0, batch=2):
+CPU_BATCH = 16      # the reference's own CPU-runnable case (BASELINE configs[0]: batch 16); measured 2x the img/s of batch 2
+
+
+def cpu_baseline(args, budget_s=15.0, batch=CPU_BATCH):
     """Bounded sample: as many guided DDIM steps of `batch` images as fit in ~budget_s (at least one)."""
     ref = CpuReference(args.size)
     t_one = ref.denoise_steps(batch, 1)                      # also the warm-up
@@ -102,7 +105,7 @@ def run_reference(args):
     if rank != 0:
         return
     ref = CpuReference(args.size)
-    batch, n = 2, 1                                          # one bench step = a bounded sample: 1 of 250 DDIM steps
+    batch, n = CPU_BATCH, 1                                  # one bench step = a bounded sample: 1 of 250 DDIM steps
     for _ in range(args.warmup):
         ref.denoise_steps(batch, n)
     t0 = time.perf_counter()
