@@ -1,0 +1,43 @@
+"""Vanilla (GroupNorm) UNet cases shared by tests/golden/make_golden_vanilla.py (reference side) and the tests."""
+import torch
+
+from oracle.vanilla_unet_ref import VanillaSpec
+
+V_SPECS = {
+    # group boundaries straddle the two concatenated sources in the up path (96 channels / 4 groups = 24)
+    "v_tiny": VanillaSpec(model_channels=32, channel_mult=(1, 2), num_res_blocks=1, attention_resolutions=(2,),
+                          num_heads=2, num_groups=4, embed_input_dim=16),
+    # attention at every level: 256 / 64 / 16 tokens, head widths 16 / 32 / 32
+    "v_attn": VanillaSpec(model_channels=32, channel_mult=(1, 2, 2), num_res_blocks=1, attention_resolutions=(1, 2, 4),
+                          num_heads=2, num_groups=8, embed_input_dim=32),
+    # the RC-49 64x64 script configuration (V/scripts/run_train_ccdm.sh): attention only in the middle block
+    # (64 tokens, 4 heads of 128)
+    "v_rc": VanillaSpec(model_channels=64, channel_mult=(1, 2, 4, 8), num_res_blocks=2, attention_resolutions=(16, 32),
+                        num_heads=4, num_groups=8, embed_input_dim=128),
+}
+V_SIZES = {"v_tiny": 16, "v_attn": 16, "v_rc": 64}
+V_BATCH = {"v_tiny": 3, "v_attn": 4, "v_rc": 2}
+# name -> (spec, weight seed, mode, keep mask kind)
+V_CASES = {
+    "v_tiny_eval_mixed": ("v_tiny", 1, "eval", "mixed"),
+    "v_tiny_train_cond": ("v_tiny", 2, "train", "cond"),
+    "v_attn_eval_mixed": ("v_attn", 3, "eval", "mixed"),
+    "v_attn_eval_null": ("v_attn", 3, "eval", "null"),
+    "v_rc_eval_mixed": ("v_rc", 4, "eval", "mixed"),
+}
+# name -> (spec, weight seed, cond_scale, rescaled_phi)
+V_CFG_CASES = {"v_tiny_cfg": ("v_tiny", 1, 1.5, 0.7), "v_attn_cfg_plain": ("v_attn", 3, 2.0, 0.0)}
+
+
+def keep_mask(kind, b):
+    return {"cond": torch.ones(b, dtype=torch.bool), "null": torch.zeros(b, dtype=torch.bool),
+            "mixed": torch.tensor([True, False, True, False, True, True][:b])}[kind]
+
+
+def vanilla_inputs(spec_name, seed=70):
+    spec, size, b = V_SPECS[spec_name], V_SIZES[spec_name], V_BATCH[spec_name]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, spec.in_channels, size, size, generator=g)
+    t = torch.randint(0, 1000, (b,), generator=g)
+    classes = torch.rand(b, spec.embed_input_dim, generator=g)
+    return x, t, classes
