@@ -1,0 +1,204 @@
+// Vanilla (ADM-style) UNet pieces that the unified UNet does not have:
+//   GroupNorm statistics + the per-(sample, channel) affine map that GroupNorm [+ (1+scale), shift] reduces to
+//   (CCDM_vanilla/.../models/unet.py:88-90 norm_layer; call sites :99 conv1, :111 + :146 conv2, :160 attention, :323 out),
+//   and the softmax attention over all H*W tokens with the reference's per-head [q|k|v] channel split (:165-175).
+// GroupNorm needs a reduction over every pixel of a sample, so it cannot live in one conv tile's epilogue: the statistics
+// are one HBM-bound read of the tensor, the apply step (ccdm_affine_act, SiLU) one read + one write in front of the conv.
+#include <cfloat>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ccdm {
+
+// sums[b][0][c_off + c] += sum over the sample's pixels of x,  sums[b][1][c_off + c] += sum of x^2.
+// x: bf16 [B][rows_per_sample][C] contiguous, C % 8 == 0, C <= 2048; sums: fp32 [B][2][ld].  grid = (slabs, B).
+__global__ void __launch_bounds__(256) channel_stats_kernel(const uint4* __restrict__ x, int rows_per_sample, int C,
+                                                            int slab, float* __restrict__ sums, int ld, int c_off) {
+  __shared__ float acc_s[2 * 2048];
+  const int nchunk = C >> 3;
+  const int lanes = 256 / nchunk;                                  // row lanes per block
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int i = tid; i < 2 * C; i += 256) acc_s[i] = 0.f;
+  __syncthreads();
+  const int ch = tid % nchunk, rl = tid / nchunk;
+  if (rl < lanes) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint4* base = x + (long long)b * rows_per_sample * nchunk;
+    const int r0 = blockIdx.x * slab, r1 = min(r0 + slab, rows_per_sample);
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      const uint4 u = __ldg(base + (long long)r * nchunk + ch);
+      const float v[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                          bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        q[j] = fmaf(v[j], v[j], q[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&acc_s[ch * 8 + j], s[j]);
+      atomicAdd(&acc_s[C + ch * 8 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  float* dst = sums + (long long)b * 2 * ld + c_off;
+  for (int i = tid; i < C; i += 256) {
+    atomicAdd(dst + i, acc_s[i]);
+    atomicAdd(dst + ld + i, acc_s[C + i]);
+  }
+}
+
+// One thread per (sample, channel) of the concatenated channel axis.  GroupNorm(x)*gamma + beta, optionally followed by
+// *(1+scale) + shift, is the affine map x*a + t with
+//   a = rstd_g * gamma_c * (1 + scale_bc),   t = (beta_c - mean_g * rstd_g * gamma_c) * (1 + scale_bc) + shift_bc.
+// Written per SOURCE in the [a-1 | t] layout ccdm_affine_act / ccdm_tapgemm read: channels [0,C0) -> coef[b][0..2*C0),
+// channels [C0,Ctot) -> coef[b][2*C0 .. 2*Ctot).  A group may straddle the two sources (it is defined on the concatenation).
+__global__ void groupnorm_coef_kernel(const float* __restrict__ sums, int Ctot, int G, float inv_count, float eps,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ ss_in, int ss_ld, int ss_off, int C0,
+                                      float* __restrict__ coef, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Ctot) return;
+  const int b = i / Ctot, c = i - b * Ctot;
+  const int cg = Ctot / G, g0 = (c / cg) * cg;
+  const float* s = sums + (long long)b * 2 * Ctot;
+  float sum = 0.f, sq = 0.f;
+  for (int k = 0; k < cg; ++k) {
+    sum += s[g0 + k];
+    sq += s[Ctot + g0 + k];
+  }
+  const float mean = sum * inv_count;
+  const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  float a = rstd * gamma[c];
+  float t = beta[c] - mean * a;
+  if (ss_in) {
+    const float sc = 1.f + ss_in[(long long)b * ss_ld + ss_off + c];
+    a *= sc;
+    t = fmaf(t, sc, ss_in[(long long)b * ss_ld + ss_off + Ctot + c]);
+  }
+  float* row = coef + (long long)b * 2 * Ctot;
+  if (c < C0) {
+    row[c] = a - 1.f;
+    row[C0 + c] = t;
+  } else {
+    const int c1 = c - C0, C1 = Ctot - C0;
+    row[2 * C0 + c1] = a - 1.f;
+    row[2 * C0 + C1 + c1] = t;
+  }
+}
+
+// softmax(q k^T * scale) v over n tokens for one (sample, head); grid = (B*heads, query blocks of 64), 128 threads:
+// two threads per query, each owning the even / odd half of the head's DH dimensions (dot products are completed with one
+// shuffle); keys / values are staged through shared memory 32 tokens at a time with a running (online) softmax.
+// Channel layout of qkv [B][n][3*heads*DH]: head h starts at h*hs; q, k, v at +qo, +ko, +vo.
+template <int DH>
+__global__ void __launch_bounds__(128) attention_tokens_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                               __nv_bfloat16* __restrict__ out, int n, int heads,
+                                                               float scale, int hs, int qo, int ko, int vo) {
+  constexpr int HD = DH / 2, KT = 32;
+  __shared__ float sk[KT][DH], sv[KT][DH];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int hid = heads * DH, ld = 3 * hid;
+  const __nv_bfloat16* base = qkv + (long long)b * n * ld + h * hs;
+  const int tid = threadIdx.x, half = tid & 1;
+  const int i = blockIdx.y * 64 + (tid >> 1);
+  const bool active = i < n;
+  float q[HD], acc[HD];
+#pragma unroll
+  for (int dd = 0; dd < HD; ++dd) {
+    q[dd] = active ? __bfloat162float(base[(long long)i * ld + qo + 2 * dd + half]) * scale : 0.f;
+    acc[dd] = 0.f;
+  }
+  float m_run = -FLT_MAX, l_run = 0.f;
+  for (int j0 = 0; j0 < n; j0 += KT) {
+    const int rows = min(KT, n - j0);
+    __syncthreads();
+    for (int e = tid; e < rows * DH; e += 128) {
+      const int tok = e / DH, dd = e % DH;
+      const __nv_bfloat16* p = base + (long long)(j0 + tok) * ld + dd;
+      sk[tok][dd] = __bfloat162float(p[ko]);
+      sv[tok][dd] = __bfloat162float(p[vo]);
+    }
+    __syncthreads();
+    for (int j = 0; j < rows; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) s = fmaf(q[dd], sk[j][2 * dd + half], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      const float m_new = fmaxf(m_run, s);
+      const float corr = __expf(m_run - m_new), p = __expf(s - m_new);
+      l_run = l_run * corr + p;
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) acc[dd] = fmaf(acc[dd], corr, p * sv[j][2 * dd + half]);
+      m_run = m_new;
+    }
+  }
+  if (!active) return;
+  const float inv = 1.f / l_run;
+  __nv_bfloat16* o = out + ((long long)b * n + i) * hid + h * DH;
+#pragma unroll
+  for (int dd = 0; dd < HD; ++dd) o[2 * dd + half] = __float2bfloat16(acc[dd] * inv);
+}
+
+}  // namespace ccdm
+
+using namespace ccdm;
+
+extern "C" int ccdm_channel_stats(const void* x, int32_t B, int32_t rows_per_sample, int32_t C, float* sums, int32_t ld,
+                                  int32_t c_off, int32_t zero_first, void* stream) {
+  CCDM_REQUIRE(x && sums && B > 0 && rows_per_sample > 0 && c_off >= 0 && ld >= c_off + C, CCDM_ERR_BAD_ARG,
+               "channel_stats: bad args");
+  CCDM_REQUIRE(C > 0 && C % 8 == 0 && C <= 2048, CCDM_ERR_UNSUPPORTED_SHAPE, "channel_stats: C=%d (multiple of 8, <= 2048)", C);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)B * 2 * ld * sizeof(float), s);
+    if (e != cudaSuccess) return cuda_fail(e, "channel_stats: memset");
+  }
+  const int lanes = 256 / (C / 8);
+  int slabs = (num_sms() * 4 + B - 1) / B;                         // a few CTAs per SM over the whole batch
+  const int max_slabs = (rows_per_sample + lanes * 4 - 1) / (lanes * 4);   // >= 4 rows per lane
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  const int slab = (rows_per_sample + slabs - 1) / slabs;
+  slabs = (rows_per_sample + slab - 1) / slab;
+  channel_stats_kernel<<<dim3(slabs, B), 256, 0, s>>>((const uint4*)x, rows_per_sample, C, slab, sums, ld, c_off);
+  return after_launch("channel_stats_kernel");
+}
+
+extern "C" int ccdm_groupnorm_coef(const float* sums, int32_t B, int32_t Ctot, int32_t groups, int64_t rows_per_sample,
+                                   float eps, const float* gamma, const float* beta, const float* scale_shift,
+                                   int32_t ss_ld, int32_t ss_off, int32_t C0, float* coef, void* stream) {
+  CCDM_REQUIRE(sums && gamma && beta && coef && B > 0 && Ctot > 0 && rows_per_sample > 0, CCDM_ERR_BAD_ARG,
+               "groupnorm_coef: bad args");
+  CCDM_REQUIRE(groups > 0 && Ctot % groups == 0 && C0 > 0 && C0 <= Ctot, CCDM_ERR_BAD_ARG,
+               "groupnorm_coef: Ctot=%d groups=%d C0=%d", Ctot, groups, C0);
+  const int n = B * Ctot;
+  const float inv_count = 1.f / ((float)rows_per_sample * (float)(Ctot / groups));
+  groupnorm_coef_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, Ctot, groups, inv_count, eps, gamma, beta,
+                                                                           scale_shift, ss_ld, ss_off, C0, coef, B);
+  return after_launch("groupnorm_coef_kernel");
+}
+
+extern "C" int ccdm_attention_tokens(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head,
+                                     float scale, int32_t head_major, void* stream) {
+  CCDM_REQUIRE(qkv && out && B > 0 && n >= 1 && heads >= 1, CCDM_ERR_BAD_ARG, "attention_tokens: bad args");
+  const int hid = heads * dim_head;
+  const int hs = head_major ? 3 * dim_head : dim_head;
+  const int qo = 0, ko = head_major ? dim_head : hid, vo = head_major ? 2 * dim_head : 2 * hid;
+  dim3 grid(B * heads, (n + 63) / 64);
+  const __nv_bfloat16* in = (const __nv_bfloat16*)qkv;
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dim_head) {
+    case 16: attention_tokens_kernel<16><<<grid, 128, 0, s>>>(in, o, n, heads, scale, hs, qo, ko, vo); break;
+    case 32: attention_tokens_kernel<32><<<grid, 128, 0, s>>>(in, o, n, heads, scale, hs, qo, ko, vo); break;
+    case 64: attention_tokens_kernel<64><<<grid, 128, 0, s>>>(in, o, n, heads, scale, hs, qo, ko, vo); break;
+    case 128: attention_tokens_kernel<128><<<grid, 128, 0, s>>>(in, o, n, heads, scale, hs, qo, ko, vo); break;
+    default:
+      CCDM_REQUIRE(false, CCDM_ERR_UNSUPPORTED_SHAPE, "attention_tokens: dim_head=%d (supported: 16, 32, 64, 128)", dim_head);
+  }
+  return after_launch("attention_tokens_kernel");
+}

@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const uint4* __restrict
     for (int j = 0; j < 8; ++j) {
       v[j] = fmaf(v[j], 1.f + sc[j], sf[j]);
       if (act == 1) v[j] = fmaxf(v[j], 0.f);
+      else if (act == 2) v[j] = silu_f(v[j]);
     }
     out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
@@ -537,7 +538,7 @@ extern "C" int ccdm_affine_act(const void* x, void* out, int64_t rows, int32_t C
                                const float* scale_shift, int32_t ss_ld, int32_t ss_off, int32_t act, void* stream) {
   CCDM_REQUIRE(x && out && scale_shift && rows > 0 && rows_per_sample > 0 && rows % rows_per_sample == 0, CCDM_ERR_BAD_ARG,
                "affine_act: bad args");
-  CCDM_REQUIRE(C > 0 && C % 8 == 0 && (act == 0 || act == 1), CCDM_ERR_UNSUPPORTED_SHAPE, "affine_act: C=%d act=%d", C, act);
+  CCDM_REQUIRE(C > 0 && C % 8 == 0 && act >= 0 && act <= 2, CCDM_ERR_UNSUPPORTED_SHAPE, "affine_act: C=%d act=%d", C, act);
   const long long nvec = rows * (C / 8);
   long long blocks = (nvec + 255) / 256;
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;

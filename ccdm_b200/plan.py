@@ -101,7 +101,7 @@ def _chunks(c: int):
 
 
 def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = False) -> ConvPlan:
-    """kind: '1x1' | '3x3' | 'down4x4s2' | 'up2x3x3' | 'up2x1x1' | 'stem7' | '<kind>_dgrad'.  ``reuse_rows`` groups vertically adjacent taps (R > 1)."""
+    """kind: '1x1' | '3x3' | 'down4x4s2' | 'down3x3s2' | 'up2x3x3' | 'up2x1x1' | 'stem7' | '<kind>_dgrad'.  ``reuse_rows`` groups vertically adjacent taps (R > 1)."""
     cins = tuple(int(c) for c in cins)
     offs = [sum(cins[:i]) for i in range(len(cins))]
     sched, psched = [], []
@@ -146,6 +146,21 @@ def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = Fals
                         emit(s * 4 + pr * 2 + pq, s, dq, [(dr, 1 << (r * 4 + q)) for dr, r in taps[pr]])
         R = 2 if reuse_rows else 1
         return ConvPlan(kind, cins, cout, 16, 1, len(sched), R, sched, psched, n_views=4, stride=2)
+    if kind == "down3x3s2":
+        # the vanilla UNet's Downsample (CCDM_vanilla/.../models/unet.py:193-198): 3x3, stride 2, padding 1.
+        # out[ho,wo] = sum_{r,q} W[r,q] x[2ho-1+r, 2wo-1+q]; row r lives on parity plane (r+1)%2 at shift -1 (r = 0) or 0.
+        # With vertical reuse R must be uniform, so the even plane's single row is paired with a zero-weight row.
+        taps = {1: [(-1, 0), (0, 2)], 0: [(0, 1)]}               # parity -> [(shift, filter index)]
+        for pr in (1, 0):
+            for pq in (1, 0):
+                for dq, q in taps[pq]:
+                    rows = [(dr, 1 << (r * 3 + q)) for dr, r in taps[pr]]
+                    if reuse_rows and len(rows) == 1:
+                        rows.append((rows[0][0] + 1, 0))
+                    for s in range(len(cins)):
+                        emit(s * 4 + pr * 2 + pq, s, dq, rows)
+        R = 2 if reuse_rows else 1
+        return ConvPlan(kind, cins, cout, 9, 1, len(sched), R, sched, psched, n_views=4, stride=2)
     if kind == "up2x3x3":
         # nearest-2x then 3x3/p1: output (2a+pa, 2b+pb) sees a 2x2 window of the low-res input; taps that hit the
         # same low-res pixel are summed at packing time (9 -> 4 taps, 2.25x fewer MACs).

@@ -361,9 +361,35 @@ int ccdm_multi_lerp(void* const* dst, const void* const* src, const int32_t* chu
 int ccdm_condbn_coef(const float* gamma, const float* beta, const float* weight, const float* bias, const float* mean,
                      const float* var, float eps, int32_t B, int32_t C, float* ss, void* stream);
 /* out = act(x*(1+scale[b]) + shift[b]) over bf16 rows of C channels (pre-activation CondBN + ReLU in front of a conv);
- * act: 0 none, 1 ReLU. */
+ * act: 0 none, 1 ReLU, 2 SiLU (the vanilla UNet's GroupNorm -> SiLU pre-activation). */
 int ccdm_affine_act(const void* x, void* out, int64_t rows, int32_t C, int32_t rows_per_sample, const float* scale_shift,
                     int32_t ss_ld, int32_t ss_off, int32_t act, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Vanilla (ADM-style) UNet, SURVEY.md section 8f rank 4: CCDM_vanilla/RC-49/RC-49_64x64/CCGM/CCDM/models/unet.py.
+ * Its convolutions are ccdm_tapgemm (3x3, 1x1 shortcut over the concatenated sources, "down3x3s2" for Downsample :193-198,
+ * "up2x3x3" for Upsample :178-190); nn.GroupNorm (:88-90; call sites :99, :111 + :146, :160, :323) is
+ * ccdm_channel_stats -> ccdm_groupnorm_coef -> ccdm_affine_act (act 2 = SiLU) in front of the conv.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* sums[b][0][c_off+c] += sum_pixels x[b][p][c],  sums[b][1][c_off+c] += sum_pixels x^2;  x bf16 [B][rows_per_sample][C]
+ * (contiguous, C % 8 == 0, C <= 2048), sums fp32 [B][2][ld].  zero_first != 0 clears the whole sums buffer first
+ * (a memset node on the stream); a concatenated input calls this once per source with its channel offset. */
+int ccdm_channel_stats(const void* x, int32_t B, int32_t rows_per_sample, int32_t C, float* sums, int32_t ld,
+                       int32_t c_off, int32_t zero_first, void* stream);
+/* GroupNorm(groups, Ctot)(x)*gamma + beta [then *(1+scale[b]) + shift[b], unet.py:146] as a per-(sample, channel)
+ * affine map in the [a-1 | t] scale/shift layout of ccdm_affine_act / ccdm_tapgemm, from sums [B][2][Ctot]:
+ *   mean_g, var_g over rows_per_sample * Ctot/groups elements (biased variance, eps inside the sqrt);
+ *   a = rstd_g*gamma[c]*(1+scale),  t = (beta[c] - mean_g*rstd_g*gamma[c])*(1+scale) + shift
+ * scale_shift (may be NULL): fp32 [B][ss_ld], scale at ss_off + c, shift at ss_off + Ctot + c.
+ * coef: fp32 [B][2*Ctot], one [a-1 | t] segment per source: channels [0,C0) at 0, channels [C0,Ctot) at 2*C0. */
+int ccdm_groupnorm_coef(const float* sums, int32_t B, int32_t Ctot, int32_t groups, int64_t rows_per_sample, float eps,
+                        const float* gamma, const float* beta, const float* scale_shift, int32_t ss_ld, int32_t ss_off,
+                        int32_t C0, float* coef, void* stream);
+/* AttentionBlock core (unet.py:165-175): out[b][t][h*dh+d] = softmax_s(q_t . k_s * scale) v_s over all n tokens;
+ * qkv bf16 [B][n][3*heads*dh].  head_major != 0: the reference's split (head h owns channels [3*dh*h, 3*dh*(h+1)) as
+ * q | k | v); head_major == 0: [q heads | k heads | v heads] (the unified UNet's split).  dim_head in {16,32,64,128}. */
+int ccdm_attention_tokens(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head, float scale,
+                          int32_t head_major, void* stream);
 
 #ifdef __cplusplus
 }

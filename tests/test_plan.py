@@ -70,6 +70,21 @@ def test_down4x4s2(c, cout, hw, reuse):
 
 
 @pytest.mark.parametrize("reuse", [False, True])
+@pytest.mark.parametrize("cins,cout,hw", [((64,), 64, (8, 8)), ((32,), 48, (6, 4)), ((128,), 128, (16, 16)),
+                                          ((72, 24), 40, (4, 4))])
+def test_down3x3s2(cins, cout, hw, reuse):
+    """The vanilla UNet's Downsample: 3x3 / stride 2 / padding 1 over four parity planes."""
+    torch.manual_seed(12)
+    xs = [torch.randn(2, c, *hw) for c in cins]
+    w = torch.randn(cout, sum(cins), 3, 3)
+    ref = nhwc(F.conv2d(torch.cat(xs, 1), w, stride=2, padding=1))
+    plan = plan_conv("down3x3s2", cins, cout, reuse_rows=reuse)
+    assert plan.R == (2 if reuse else 1) and plan.n_views == 4
+    out = tapgemm_emu(plan, [nhwc(x) for x in xs], w, hw[0] // 2, hw[1] // 2)[0]
+    assert rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("reuse", [False, True])
 @pytest.mark.parametrize("c,cout,hw", [(64, 64, (4, 4)), (128, 64, (3, 5)), (32, 32, (1, 1))])
 def test_up2x3x3(c, cout, hw, reuse):
     torch.manual_seed(3)
