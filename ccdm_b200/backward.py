@@ -25,7 +25,7 @@ import torch
 from . import _lib as L
 from .plan import KB, ConvPlan, can_reuse_rows, n_tiling, plan_conv, tile_box
 
-_KIND_TAPS = {"1x1": 1, "3x3": 9, "down4x4s2": 16, "up2x3x3": 9}
+_KIND_TAPS = {"1x1": 1, "3x3": 9, "down4x4s2": 16, "down3x3s2": 9, "up2x3x3": 9}
 
 
 def _stream() -> int:
@@ -116,7 +116,8 @@ def conv_forward(kind: str, srcs: Sequence[torch.Tensor], weight: torch.Tensor, 
         _check(s, "conv_forward source")
     b, h, w, _ = srcs[0].shape
     cout = weight.shape[0]
-    oh, ow = {"1x1": (h, w), "3x3": (h, w), "down4x4s2": (h // 2, w // 2), "up2x3x3": (2 * h, 2 * w)}[kind]
+    oh, ow = {"1x1": (h, w), "3x3": (h, w), "down4x4s2": (h // 2, w // 2), "down3x3s2": ((h + 1) // 2, (w + 1) // 2),
+              "up2x3x3": (2 * h, 2 * w)}[kind]
     gh, gw = (h, w) if kind == "up2x3x3" else (oh, ow)
     plan, tile = _plan_for(kind, [s.shape[3] for s in srcs], cout, gw, gh)
     n_rows, n_tile = n_tiling(cout, False)

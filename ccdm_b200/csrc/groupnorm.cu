@@ -90,6 +90,20 @@ __global__ void groupnorm_coef_kernel(const float* __restrict__ sums, int Ctot, 
   }
 }
 
+// timestep_embedding (V/models/unet.py:40-57): out[b] = [cos(t*f_j) | sin(t*f_j)], f_j = exp(-ln(max_period)*j/half).
+// (The unified UNet's SinusoidalPosEmb is sin | cos with the exponent divided by half-1: ccdm_time_features.)
+__global__ void time_features_adm_kernel(const long long* __restrict__ t, int B, int dim, float log_period,
+                                         float* __restrict__ out) {
+  const int half = dim >> 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, j = i - b * half;
+  const float f = expf(-log_period * (float)j / (float)half);
+  const float a = (float)t[b] * f;
+  out[(long long)b * dim + j] = cosf(a);
+  out[(long long)b * dim + half + j] = sinf(a);
+}
+
 // softmax(q k^T * scale) v over n tokens for one (sample, head); grid = (B*heads, query blocks of 64), 128 threads:
 // two threads per query, each owning the even / odd half of the head's DH dimensions (dot products are completed with one
 // shuffle); keys / values are staged through shared memory 32 tokens at a time with a running (online) softmax.
@@ -180,6 +194,16 @@ extern "C" int ccdm_groupnorm_coef(const float* sums, int32_t B, int32_t Ctot, i
   groupnorm_coef_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, Ctot, groups, inv_count, eps, gamma, beta,
                                                                            scale_shift, ss_ld, ss_off, C0, coef, B);
   return after_launch("groupnorm_coef_kernel");
+}
+
+extern "C" int ccdm_time_features_adm(const int64_t* t, int32_t B, int32_t dim, float max_period, float* out,
+                                      void* stream) {
+  CCDM_REQUIRE(t && out && B > 0 && dim >= 2 && dim % 2 == 0 && max_period > 1.f, CCDM_ERR_BAD_ARG,
+               "time_features_adm: bad args");
+  const int n = B * (dim / 2);
+  time_features_adm_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const long long*)t, B, dim,
+                                                                              logf(max_period), out);
+  return after_launch("time_features_adm_kernel");
 }
 
 extern "C" int ccdm_attention_tokens(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head,

@@ -244,6 +244,22 @@ def _make_call(lib, r, keep):
         return lib.ccdm_select_null, (p(a["c"]), p(a["keep"]), 0, p(a["null_emb"]), a["B"], a["dim"]), k
     if k == "silu_concat_bf16":
         return lib.ccdm_silu_concat_bf16, (p(a["t_emb"]), a["dt"], p(a["c_emb"]), a["dc"], a["B"], p(a["out"])), k
+    # ---- vanilla (GroupNorm) UNet, ccdm_b200/vanilla_unet.py
+    if k == "channel_stats":
+        return lib.ccdm_channel_stats, (p(a["x"]), a["B"], a["rows"], a["C"], p(a["sums"]), a["ld"], a["c_off"],
+                                        a["zero_first"]), k
+    if k == "groupnorm_coef":
+        return lib.ccdm_groupnorm_coef, (p(a["sums"]), a["B"], a["Ctot"], a["groups"], a["rows"], a["eps"], p(a["gamma"]),
+                                         p(a["beta"]), p(a.get("ss")), a.get("ss_ld", 0), a.get("ss_off", 0), a["C0"],
+                                         p(a["coef"])), k
+    if k == "affine_act":
+        return lib.ccdm_affine_act, (p(a["x"]), p(a["out"]), a["rows"], a["C"], a["rows_per_sample"], p(a["ss"]),
+                                     a["ss_ld"], a["ss_off"], a["act"]), k
+    if k == "attention_tokens":
+        return lib.ccdm_attention_tokens, (p(a["qkv"]), p(a["out"]), a["B"], a["n"], a["heads"], a["dim_head"],
+                                           a["scale"], a["head_major"]), k
+    if k == "time_features_adm":
+        return lib.ccdm_time_features_adm, (p(a["t"]), a["B"], a["dim"], a["max_period"], p(a["out"])), k
     raise ValueError(k)
 
 

@@ -385,6 +385,8 @@ int ccdm_channel_stats(const void* x, int32_t B, int32_t rows_per_sample, int32_
 int ccdm_groupnorm_coef(const float* sums, int32_t B, int32_t Ctot, int32_t groups, int64_t rows_per_sample, float eps,
                         const float* gamma, const float* beta, const float* scale_shift, int32_t ss_ld, int32_t ss_off,
                         int32_t C0, float* coef, void* stream);
+/* timestep_embedding (unet.py:40-57): out fp32 [B][dim] = [cos(t*f_j) | sin(t*f_j)], f_j = max_period^(-j/(dim/2)); dim even. */
+int ccdm_time_features_adm(const int64_t* t, int32_t B, int32_t dim, float max_period, float* out, void* stream);
 /* AttentionBlock core (unet.py:165-175): out[b][t][h*dh+d] = softmax_s(q_t . k_s * scale) v_s over all n tokens;
  * qkv bf16 [B][n][3*heads*dh].  head_major != 0: the reference's split (head h owns channels [3*dh*h, 3*dh*(h+1)) as
  * q | k | v); head_major == 0: [q heads | k heads | v heads] (the unified UNet's split).  dim_head in {16,32,64,128}. */

@@ -192,6 +192,56 @@ def run_kernel(r: KernelRec):
     elif k == "silu_concat_bf16":
         v = F.silu(torch.cat([a["t_emb"], a["c_emb"]], 1))
         a["out"].copy_(v.reshape(a["out"].shape).to(torch.bfloat16))
+    elif k == "channel_stats":
+        x = a["x"].float().reshape(a["B"], a["rows"], a["C"])
+        sums = a["sums"]                                                     # [B, 2, ld]
+        if a["zero_first"]:
+            sums.zero_()
+        sums[:, 0, a["c_off"]: a["c_off"] + a["C"]] += x.sum(1)
+        sums[:, 1, a["c_off"]: a["c_off"] + a["C"]] += x.pow(2).sum(1)
+    elif k == "groupnorm_coef":
+        B, Ctot, G, C0 = a["B"], a["Ctot"], a["groups"], a["C0"]
+        cg = Ctot // G
+        cnt = a["rows"] * cg
+        s = a["sums"].reshape(B, 2, G, cg).sum(-1)                           # [B, 2, G]
+        mean = s[:, 0] / cnt
+        var = (s[:, 1] / cnt - mean * mean).clamp_min(0)
+        rstd = torch.rsqrt(var + a["eps"])
+        mean_c, rstd_c = mean.repeat_interleave(cg, 1), rstd.repeat_interleave(cg, 1)
+        aa = rstd_c * a["gamma"].detach()[None]
+        tt = a["beta"].detach()[None] - mean_c * aa
+        if a.get("ss") is not None:
+            ss, off = a["ss"][:B], a["ss_off"]
+            sc = 1 + ss[:, off: off + Ctot]
+            aa, tt = aa * sc, tt * sc + ss[:, off + Ctot: off + 2 * Ctot]
+        coef = a["coef"]
+        coef[:, :C0], coef[:, C0: 2 * C0] = aa[:, :C0] - 1, tt[:, :C0]
+        if C0 < Ctot:
+            C1 = Ctot - C0
+            coef[:, 2 * C0: 2 * C0 + C1], coef[:, 2 * C0 + C1:] = aa[:, C0:] - 1, tt[:, C0:]
+    elif k == "affine_act":
+        C, rps = a["C"], a["rows_per_sample"]
+        x = a["x"].float().reshape(-1, rps, C)
+        ss, off = a["ss"], a["ss_off"]
+        v = x * (1 + ss[: x.shape[0], None, off: off + C]) + ss[: x.shape[0], None, off + C: off + 2 * C]
+        v = {0: lambda u: u, 1: F.relu, 2: F.silu}[a["act"]](v)
+        a["out"].copy_(v.reshape(a["out"].shape).to(torch.bfloat16))
+    elif k == "attention_tokens":
+        B, n, heads, dh = a["B"], a["n"], a["heads"], a["dim_head"]
+        flat = a["qkv"].float().reshape(B, n, 3 * heads * dh)
+        if a["head_major"]:
+            qkv = flat.reshape(B, n, heads, 3, dh).permute(0, 1, 3, 2, 4)     # -> [B, n, 3, heads, dh]
+        else:
+            qkv = flat.reshape(B, n, 3, heads, dh)
+        q, kk, vv = qkv[:, :, 0] * a["scale"], qkv[:, :, 1], qkv[:, :, 2]
+        att = torch.einsum("bihd,bjhd->bhij", q, kk).softmax(-1)
+        o = torch.einsum("bhij,bjhd->bihd", att, vv).reshape(B, n, heads * dh)
+        a["out"].copy_(o.reshape(a["out"].shape).to(torch.bfloat16))
+    elif k == "time_features_adm":
+        half = a["dim"] // 2
+        f = torch.exp(-math.log(a["max_period"]) * torch.arange(half, dtype=torch.float32) / half)
+        ang = a["t"].float()[:, None] * f[None]
+        a["out"].copy_(torch.cat([ang.cos(), ang.sin()], -1))
     else:
         raise ValueError(k)
 
@@ -205,9 +255,11 @@ def run_program(prog, weights):
                 run_kernel(r)
         for off, b in prog._tc_bias_srcs:
             weights.tc_bias[off:off + b.numel()].copy_(b.detach())
+        if hasattr(prog, "_head_bias_src"):                                  # VanillaProgram: padded bias of the output conv
+            weights.head_bias[: prog._head_bias_src.numel()].copy_(prog._head_bias_src.detach())
         for r in prog.recs:
             if isinstance(r, TapGemmRec):
                 run_tapgemm(r)
             else:
                 run_kernel(r)
-    return prog.out
+    return prog.result() if hasattr(prog, "result") else prog.out

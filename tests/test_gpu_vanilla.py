@@ -1,0 +1,180 @@
+"""GPU parity of the vanilla (GroupNorm) UNet path against the oracle and the reference's
+own outputs (tests/golden/vanilla_unet.pt), through the C ABI.
+
+GATED: the GroupNorm / token-attention kernels were written in a session that had no GPU minutes left, so they have
+compiled for sm_100a and their host program is CPU-verified (tests/test_vanilla_emulated.py), but they have never run
+on a device.  Until their first GPU run they are opt-in (CCDM_RUN_UNVERIFIED=1) so that an unverified kernel cannot take
+down the verified suite; remove the gate once green.
+"""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("CCDM_RUN_UNVERIFIED") != "1",
+                                 reason="vanilla-UNet kernels not yet run on a GPU: set CCDM_RUN_UNVERIFIED=1")]
+
+GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vanilla_unet.pt"))
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("cs,groups,hw,with_ss", [((64,), 8, (16, 16), False), ((64, 32), 4, (8, 8), True),
+                                                  ((128, 64), 8, (32, 32), True), ((512,), 8, (8, 8), False),
+                                                  ((256, 512), 8, (4, 4), True), ((72,), 8, (6, 10), True)])
+def test_groupnorm_chain_matches_torch(cs, groups, hw, with_ss):
+    """channel_stats -> groupnorm_coef -> affine_act(SiLU) == silu(group_norm(cat(x)) [*(1+scale)+shift]), per source;
+    96- and 768-channel concatenations have groups that straddle the two sources."""
+    from ccdm_b200 import _lib as L
+    lib = L.lib()
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, (h, w), ctot = 3, hw, sum(cs)
+    xs = [(torch.randn(B, h, w, c, generator=g) * 1.5 + 0.3).to(dev).to(torch.bfloat16).contiguous() for c in cs]
+    gamma = (1 + 0.2 * torch.randn(ctot, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(ctot, generator=g)).to(dev)
+    ss = (0.3 * torch.randn(B, 40 + 2 * ctot, generator=g)).to(dev) if with_ss else None
+    sums = torch.full((B, 2, ctot), 7.0, device=dev)            # stale contents: zero_first must clear them
+    off = 0
+    for i, x in enumerate(xs):
+        L.check(lib.ccdm_channel_stats(x.data_ptr(), B, h * w, x.shape[3], sums.data_ptr(), ctot, off, int(i == 0), _stream()))
+        off += x.shape[3]
+    coef = torch.empty(B, 2 * ctot, device=dev)
+    L.check(lib.ccdm_groupnorm_coef(sums.data_ptr(), B, ctot, groups, h * w, 1e-5, gamma.data_ptr(), beta.data_ptr(),
+                                    L.ptr(ss), ss.shape[1] if with_ss else 0, 40, cs[0], coef.data_ptr(), _stream()))
+    outs, off = [], 0
+    for x in xs:
+        o = torch.empty_like(x)
+        L.check(lib.ccdm_affine_act(x.data_ptr(), o.data_ptr(), B * h * w, x.shape[3], h * w, coef.data_ptr(),
+                                    coef.shape[1], off, 2, _stream()))
+        outs.append(o)
+        off += 2 * x.shape[3]
+    torch.cuda.synchronize()
+    cat = torch.cat([x.float() for x in xs], -1)
+    want_sums = torch.stack([cat.sum((1, 2)), cat.pow(2).sum((1, 2))], 1)
+    assert rel(sums, want_sums) < 1e-4
+    y = F.group_norm(cat.permute(0, 3, 1, 2), groups, gamma, beta, eps=1e-5)
+    if with_ss:
+        y = y * (1 + ss[:, 40:40 + ctot, None, None]) + ss[:, 40 + ctot:40 + 2 * ctot, None, None]
+    want = F.silu(y).permute(0, 2, 3, 1)
+    got = torch.cat([o.float() for o in outs], -1)
+    assert rel(got, want) < 6e-3, rel(got, want)
+
+
+@pytest.mark.parametrize("dh", [16, 32, 64, 128])
+@pytest.mark.parametrize("n", [16, 64, 100, 256])
+@pytest.mark.parametrize("head_major", [0, 1])
+def test_attention_tokens_matches_torch(dh, n, head_major):
+    from ccdm_b200 import _lib as L
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(n + dh)
+    B, heads = 3, 2
+    hid = heads * dh
+    qkv = torch.randn(B, n, 3 * hid, generator=g).to(dev).to(torch.bfloat16).contiguous()
+    out = torch.empty(B, n, hid, dtype=torch.bfloat16, device=dev)
+    scale = 1.0 / math.sqrt(dh)
+    L.check(L.lib().ccdm_attention_tokens(qkv.data_ptr(), out.data_ptr(), B, n, heads, dh, scale, head_major, _stream()))
+    torch.cuda.synchronize()
+    f = qkv.float()
+    v5 = f.reshape(B, n, heads, 3, dh).permute(0, 1, 3, 2, 4) if head_major else f.reshape(B, n, 3, heads, dh)
+    q, k, v = v5[:, :, 0] * scale, v5[:, :, 1], v5[:, :, 2]
+    att = torch.einsum("bihd,bjhd->bhij", q, k).softmax(-1)
+    want = torch.einsum("bhij,bjhd->bihd", att, v).reshape(B, n, hid)
+    assert rel(out, want) < 1e-2
+
+
+def test_time_features_adm():
+    from ccdm_b200 import _lib as L
+    from oracle.vanilla_unet_ref import timestep_embedding
+    dev = torch.device("cuda")
+    t = torch.tensor([0, 1, 17, 500, 999], device=dev)
+    for dim in (32, 64, 128):
+        out = torch.empty(5, dim, device=dev)
+        L.check(L.lib().ccdm_time_features_adm(t.data_ptr(), 5, dim, 10000.0, out.data_ptr(), _stream()))
+        torch.cuda.synchronize()
+        assert (out - timestep_embedding(t, dim)).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 64, (64, 64)), (128, 128, (32, 32)), (256, 256, (16, 16)), (32, 48, (8, 8))])
+def test_down3x3s2_matches_conv2d(cin, cout, hw):
+    from ccdm_b200.backward import conv_forward
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(4, hw[0], hw[1], cin, generator=g).to(dev).to(torch.bfloat16).contiguous()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(dev)
+    b = (0.1 * torch.randn(cout, generator=g)).to(dev)
+    got = conv_forward("down3x3s2", [x], w, b)
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert rel(got, want) < 6e-3
+
+
+def _build(sname, seed, dev):
+    from ccdm_b200.vanilla_unet import VanillaUnet
+    from oracle.vanilla_unet_ref import make_state_dict
+    from tests.golden.vanilla_cases import V_SPECS
+    s = V_SPECS[sname]
+    net = VanillaUnet(embed_input_dim=s.embed_input_dim, cond_drop_prob=0.5, in_channels=s.in_channels,
+                      model_channels=s.model_channels, num_res_blocks=s.num_res_blocks,
+                      attention_resolutions=s.attention_resolutions, channel_mult=s.channel_mult, num_heads=s.num_heads,
+                      num_groups=s.num_groups)
+    sd = make_state_dict(s, seed)
+    net.load_state_dict(sd, strict=True)
+    return s, net.to(dev), sd
+
+
+def test_forward_matches_reference_outputs():
+    """Whole network through VanillaEngine vs the reference's own outputs (golden) -- bf16 tolerance 2e-2 (BASELINE.json)."""
+    from tests.golden.vanilla_cases import V_BATCH, V_CASES, keep_mask, vanilla_inputs
+    dev = torch.device("cuda")
+    for name, (sname, seed, mode, kind) in V_CASES.items():
+        spec, net, _ = _build(sname, seed, dev)
+        net.train(mode == "train")
+        x, t, classes = (v.to(dev) for v in vanilla_inputs(sname))
+        keep = keep_mask(kind, V_BATCH[sname]).to(dev)
+        with torch.no_grad():
+            out = net.engine().forward(x, t, classes, keep)
+        err = rel(out.cpu(), GOLD[name]["out"])
+        print(f"{name}: rel L2 err vs the reference's output {err:.3e}")
+        assert err < 2e-2, (name, err)
+
+
+def test_guidance_matches_reference_outputs():
+    from tests.golden.vanilla_cases import V_CFG_CASES, vanilla_inputs
+    dev = torch.device("cuda")
+    for name, (sname, seed, cs, phi) in V_CFG_CASES.items():
+        _, net, _ = _build(sname, seed, dev)
+        net.eval()
+        x, t, classes = (v.to(dev) for v in vanilla_inputs(sname))
+        with torch.no_grad():
+            out = net.forward_with_cond_scale(x, t, classes, cond_scale=cs, rescaled_phi=phi)
+        err = rel(out.cpu(), GOLD[name]["out"])
+        assert err < 3e-2, (name, err)
+
+
+def test_rc49_config_pair_batch_and_oracle():
+    """RC-49 64x64 script configuration at batch 8: the 2B pair batch equals two forwards, and both match the oracle."""
+    from oracle.vanilla_unet_ref import vanilla_unet_forward
+    dev = torch.device("cuda")
+    spec, net, sd = _build("v_rc", 9, dev)
+    net.eval()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(8, 3, 64, 64, generator=g).to(dev)
+    t = torch.randint(0, 1000, (8,), generator=g).to(dev)
+    classes = torch.rand(8, 128, generator=g).to(dev)
+    with torch.no_grad():
+        cond, null = net.engine().forward_pair(x, t, classes)
+        c1 = net.engine().forward(x, t, classes, None)
+        sd_d = {k: v.to(dev) for k, v in sd.items()}
+        ref_c = vanilla_unet_forward(sd_d, spec, x, t, classes, torch.ones(8, dtype=torch.bool, device=dev))
+        ref_n = vanilla_unet_forward(sd_d, spec, x, t, classes, torch.zeros(8, dtype=torch.bool, device=dev))
+    assert rel(cond, c1) < 5e-3        # not bit-equal: the statistics are accumulated with atomics (order varies)
+    assert rel(cond, ref_c) < 2e-2 and rel(null, ref_n) < 2e-2
