@@ -264,7 +264,8 @@ class GaussianDiffusion(nn.Module):
         a.out_cond, a.out_null, a.x = cond.data_ptr(), L.ptr(null), xs.data_ptr()
         a.pred_noise, a.pred_x0 = eps.data_ptr(), x0.data_ptr()
         a.B, a.chw = B, xs[0].numel()
-        a.cond_scale, a.rescaled_phi, a.keep_parallel_frac, a.remove_parallel = cond_scale, rescaled_phi, 0.0, 1
+        a.cond_scale, a.rescaled_phi, a.keep_parallel_frac = cond_scale, rescaled_phi, 0.0
+        a.remove_parallel = int(getattr(unet, "cfg_remove_parallel", True))      # False: the vanilla UNet's plain CFG
         a.objective, a.clip_x0, a.cfg_plus_plus, a.sampler = L.OBJ[self.objective], int(clip_x_start), int(self.use_cfg_plus_plus), 2
         a.coef = self._coef_by_t().data_ptr()
         tt = t.to(torch.int64).contiguous()
@@ -303,7 +304,7 @@ class GaussianDiffusion(nn.Module):
         stream = self._stream()
 
         key = (id(prog), kind, float(cond_scale), float(rescaled_phi), bool(clip_denoised), self.objective,
-               bool(self.use_cfg_plus_plus), trace is not None)
+               bool(self.use_cfg_plus_plus), trace is not None, int(self.sampling_timesteps))
         st = self._samplers.get(key)
         if st is None:
             with torch.inference_mode(False):      # persistent buffers must be normal tensors (reused outside)
@@ -510,7 +511,8 @@ class _SamplerState:
         a.x, a.noise = prog.x_in.data_ptr(), self.noise.data_ptr()
         a.pred_noise, a.pred_x0 = L.ptr(self.pred_noise), L.ptr(self.pred_x0)
         a.B, a.chw = B, chw
-        a.cond_scale, a.rescaled_phi, a.keep_parallel_frac, a.remove_parallel = cond_scale, rescaled_phi, 0.0, 1
+        a.cond_scale, a.rescaled_phi, a.keep_parallel_frac = cond_scale, rescaled_phi, 0.0
+        a.remove_parallel = int(getattr(gd.unet, "cfg_remove_parallel", True))
         a.objective, a.cfg_plus_plus = L.OBJ[gd.objective], int(gd.use_cfg_plus_plus)
         a.clip_x0 = int(clip_denoised) if kind == "ddim" else 0       # p_mean_variance clamps separately (:344-345)
         a.sampler = 0 if kind == "ddim" else 1

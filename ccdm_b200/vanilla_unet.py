@@ -19,8 +19,12 @@ program of C-ABI calls (same machinery as :mod:`ccdm_b200.engine`):
 Boundary glue in PyTorch (layout only): NCHW fp32 -> the first 3 of 64 bf16 NHWC channels for the 3x3 stem, and the
 8-channel fp32 NHWC output of the last conv -> NCHW.  There is no CPU / PyTorch fallback for the arithmetic.
 
-STATUS: host program checked on CPU against the oracle through the record interpreter (tests/test_vanilla_emulated.py);
-the GroupNorm / attention kernels compile for sm_100a but have not run on a GPU yet (tests/test_gpu_vanilla.py).
+The program exposes the same ``x_in / t_in / emb_in / keep / out / run(stream)`` surface as the unified UNet's, so
+:class:`ccdm_b200.VanillaGaussianDiffusion` drives it from the same CUDA-graph sampling loop.
+
+STATUS: host program checked on CPU against the oracle AND the reference's own outputs through the record interpreter
+(tests/test_vanilla_emulated.py: 0.8-1.0 % relative error, the bf16 storage level); the GroupNorm / attention kernels
+compile for sm_100a but have not run on a GPU yet (tests/test_gpu_vanilla.py, opt-in until their first device run).
 """
 from __future__ import annotations
 
@@ -113,6 +117,10 @@ class VanillaUnet(nn.Module):
         self.num_res_blocks, self.attention_resolutions = num_res_blocks, tuple(attention_resolutions)
         self.dropout, self.channel_mult, self.conv_resample = dropout, tuple(channel_mult), conv_resample
         self.num_heads, self.num_groups = num_heads, num_groups
+        # what ccdm_b200.GaussianDiffusion reads from a denoiser: output width, time-embedding kind, guidance flavour
+        self.out_dim = self.out_channels
+        self.random_or_learned_sinusoidal_cond = False
+        self.cfg_remove_parallel = False           # plain CFG (V/diffusion.py:34-56): no orthogonal-update projection
         mc = model_channels
         e = mc * 4
         self.time_mlp = nn.Sequential(nn.Linear(mc, e), nn.SiLU(), nn.Linear(e, e))
@@ -230,17 +238,18 @@ class VanillaEngine:
         self.programs: Dict[tuple, "VanillaProgram"] = {}
         self._ptr_stamp = None
 
-    def program(self, B, H, W, training) -> "VanillaProgram":
+    def program(self, B, x_batch, H, W, training) -> "VanillaProgram":
+        """Same signature as UnetEngine.program: ``x_batch`` < B (= B/2) means the cond / null halves share one input."""
         ptrs = tuple(p.data_ptr() for p in self.net.parameters())
         if ptrs != self._ptr_stamp:               # parameters were re-allocated: rebuild everything
             self.programs.clear()
             self.weights = WeightStore(self.device)
             self._ptr_stamp = ptrs
-        key = (B, H, W, bool(training))
+        key = (B, x_batch, H, W, bool(training))
         prog = self.programs.get(key)
         if prog is None:
             with torch.inference_mode(False):
-                prog = VanillaProgram(self.net, self.weights, B, H, W, training)
+                prog = VanillaProgram(self.net, self.weights, B, x_batch, H, W, training)
             self.programs[key] = prog
         return prog
 
@@ -253,21 +262,23 @@ class VanillaEngine:
         prog.run(stream)
         if self.net.training:
             self.net.classes_emb[1].num_batches_tracked += 1
-        return prog.result()
+        return prog.out
 
     def forward(self, x, t, classes, keep_mask):
         B, _, H, W = x.shape
-        prog = self.program(B, H, W, self.net.training)
+        prog = self.program(B, B, H, W, self.net.training)
         keep = torch.ones(B, dtype=torch.uint8, device=self.device) if keep_mask is None else keep_mask.to(torch.uint8)
-        return self._run(prog, x, t, classes, keep)
+        return self._run(prog, x, t, classes, keep).clone()
 
     def forward_pair(self, x, t, classes):
         """Conditional and unconditional evaluations as one 2B batch (eval mode: BatchNorm1d uses running statistics and
-        GroupNorm is per sample, so this equals two forwards)."""
+        GroupNorm is per sample, so this equals two forwards).  Returns views of the persistent output buffer."""
         B, _, H, W = x.shape
-        prog = self.program(2 * B, H, W, False)
-        keep = torch.cat([torch.ones(B, dtype=torch.uint8), torch.zeros(B, dtype=torch.uint8)]).to(self.device)
-        out = self._run(prog, torch.cat([x, x]), torch.cat([t.reshape(-1), t.reshape(-1)]), torch.cat([classes, classes]), keep)
+        prog = self.program(2 * B, B, H, W, False)
+        if prog.pair_keep is None:
+            with torch.inference_mode(False):
+                prog.pair_keep = torch.cat([torch.ones(B, dtype=torch.uint8), torch.zeros(B, dtype=torch.uint8)]).to(self.device)
+        out = self._run(prog, x, torch.cat([t.reshape(-1), t.reshape(-1)]), torch.cat([classes, classes]), prog.pair_keep)
         return out[:B], out[B:]
 
 
@@ -283,12 +294,13 @@ def partial_k_plan(k_total: int, k_valid: int, cout: int):
 class VanillaProgram(UnetProgram):
     """Flat C-ABI program of one VanillaUnet evaluation at a fixed (batch, resolution, mode)."""
 
-    def __init__(self, net: VanillaUnet, weights: WeightStore, B, H, W, training):
+    def __init__(self, net: VanillaUnet, weights: WeightStore, B, x_batch, H, W, training):
         # (UnetProgram.__init__ reads the unified UNet's attributes, so the base Program is initialised directly)
         from .engine import Program
         Program.__init__(self, net.null_classes_emb.device)
         self.net, self.weights = net, weights
-        self.B, self.x_batch, self.H, self.W, self.training = B, B, H, W, training
+        assert B % x_batch == 0
+        self.B, self.x_batch, self.H, self.W, self.training = B, x_batch, H, W, training
         self.pair_keep = None
         down = 2 ** (len(net.channel_mult) - 1)
         if H % down or W % down:
@@ -298,13 +310,21 @@ class VanillaProgram(UnetProgram):
 
     # ------------------------------------------------------------------ boundary
     def load_inputs(self, x, t, classes, keep_rows):
-        self.x_pad[..., : self.net.in_channels].copy_(x.permute(0, 2, 3, 1))     # layout glue: NCHW fp32 -> NHWC bf16
+        self.x_in.copy_(x)
         self.t_in.copy_(t.reshape(-1))
         self.emb_in.copy_(classes.reshape(self.B, -1))
         self.keep.copy_(keep_rows)
 
-    def result(self):
-        return self.out8[..., : self.net.out_channels].permute(0, 3, 1, 2).contiguous()
+    def glue_in(self):
+        """Layout glue, NCHW fp32 ``x_in`` -> the first channels of the NHWC bf16 stem input (every x_batch slab)."""
+        xb, cin = self.x_batch, self.net.in_channels
+        src = self.x_in.permute(0, 2, 3, 1)
+        for rep in range(self.B // xb):
+            self.x_pad[rep * xb:(rep + 1) * xb, ..., :cin].copy_(src)
+
+    def glue_out(self):
+        """Layout glue, 8-channel fp32 NHWC output of the last conv -> NCHW fp32 ``out``."""
+        self.out.copy_(self.out8[..., : self.net.out_channels].permute(0, 3, 1, 2))
 
     # ------------------------------------------------------------------ GroupNorm
     def gn_coef(self, name, srcs: List[torch.Tensor], gn: nn.GroupNorm, ss_off: Optional[int] = None):
@@ -404,6 +424,8 @@ class VanillaProgram(UnetProgram):
     def _build(self):
         net, B, H, W, dev = self.net, self.B, self.H, self.W, self.device
         mc, e = net.model_channels, net.model_channels * 4
+        self.x_in = self.buf("x_in", (self.x_batch, net.in_channels, H, W), torch.float32)
+        self.out = self.buf("out", (B, net.out_channels, H, W), torch.float32)
         self.x_pad = self.buf("x_pad", (B, H, W, KB), torch.bfloat16)
         self.x_pad.zero_()                              # channels >= in_channels stay zero (and meet zero weights)
         self.t_in = self.buf("t_in", (B,), torch.int64)
@@ -504,8 +526,14 @@ class VanillaProgram(UnetProgram):
                                     algo_flops=2.0 * self.B * gh * gw * cout * src.shape[3] * 9))
 
     def run(self, stream: int):
+        """``stream`` must be torch's current stream: the two layout copies at the boundary are torch kernels (they are
+        captured with the rest when the sampler records its CUDA graph)."""
+        if stream != torch.cuda.current_stream().cuda_stream:
+            raise RuntimeError("VanillaProgram.run: launch on torch's current stream")
         b = self._head_bias_src
         if getattr(self.weights, "_head_bias_stamp", None) != (b.data_ptr(), b._version):
             self.weights.head_bias[: b.numel()].copy_(b.detach())
             self.weights._head_bias_stamp = (b.data_ptr(), b._version)
+        self.glue_in()
         super().run(stream)
+        self.glue_out()

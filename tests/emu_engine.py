@@ -248,6 +248,8 @@ def run_kernel(r: KernelRec):
 
 def run_program(prog, weights):
     with torch.no_grad():
+        if hasattr(prog, "glue_in"):                                         # VanillaProgram: boundary layout copies
+            prog.glue_in()
         for r in weights.program.recs:
             if isinstance(r, PackRec):
                 run_pack(r)
@@ -262,4 +264,6 @@ def run_program(prog, weights):
                 run_tapgemm(r)
             else:
                 run_kernel(r)
-    return prog.result() if hasattr(prog, "result") else prog.out
+    if hasattr(prog, "glue_out"):
+        prog.glue_out()
+    return prog.out

@@ -20,7 +20,8 @@ import importlib.util  # noqa: E402
 import torch  # noqa: E402
 
 from oracle.vanilla_unet_ref import make_state_dict  # noqa: E402
-from tests.golden.vanilla_cases import V_CASES, V_CFG_CASES, V_SPECS, V_BATCH, keep_mask, vanilla_inputs  # noqa: E402
+from tests.golden.vanilla_cases import (V_CASES, V_CFG_CASES, V_SAMPLER_CASES, V_SIZES, V_SPECS, V_BATCH, keep_mask,  # noqa: E402
+                                        sampler_classes, vanilla_inputs)
 
 VREF = "/root/reference/CCDM_vanilla/RC-49/RC-49_64x64/CCGM/CCDM"
 
@@ -75,6 +76,33 @@ def main():
         out[name] = {"out": y.clone()}
         print(name, tuple(y.shape), float(y.abs().mean()))
     torch.save(out, os.path.join(HERE, "vanilla_unet.pt"))
+
+    # ---- sampling loops through the reference's own GaussianDiffusion (needs utils.py -> accelerate / ema_pytorch stubs)
+    for m in ("accelerate",):
+        stub = types.ModuleType(m)
+        stub.Accelerator = object
+        sys.modules.setdefault(m, stub)
+    sys.path.insert(0, VREF)
+    ref_diff = load(os.path.join(VREF, "diffusion.py"), "ref_vanilla_diffusion")
+    samp = {}
+    for name, c in V_SAMPLER_CASES.items():
+        s = V_SPECS[c["spec"]]
+        net = build(ref_pm, s, c["seed"]).eval()
+        size = V_SIZES[c["spec"]]
+        gd = ref_diff.GaussianDiffusion(torch.nn.DataParallel(net), image_size=size, timesteps=c["T"],
+                                        sampling_timesteps=c["S"], objective=c["objective"],
+                                        ddim_sampling_eta=c["eta"]).eval()
+        classes = sampler_classes(c)
+        torch.manual_seed(c["rng"])
+        with torch.no_grad():
+            if c["kind"] == "ddim":
+                img = gd.ddim_sample(classes, (c["B"], s.in_channels, size, size), cond_scale=c["scale"],
+                                     rescaled_phi=c["phi"])
+            else:
+                img = gd.sample(classes, cond_scale=c["scale"], rescaled_phi=c["phi"], preset_sampling_timesteps=c["S"])
+        samp[name] = {"img": img.clone()}
+        print(name, tuple(img.shape), float(img.mean()))
+    torch.save(samp, os.path.join(HERE, "vanilla_sampler.pt"))
 
 
 if __name__ == "__main__":

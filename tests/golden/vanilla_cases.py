@@ -41,3 +41,22 @@ def vanilla_inputs(spec_name, seed=70):
     t = torch.randint(0, 1000, (b,), generator=g)
     classes = torch.rand(b, spec.embed_input_dim, generator=g)
     return x, t, classes
+
+# sampling through the reference's own GaussianDiffusion (V/diffusion.py); name -> settings
+V_SAMPLER_CASES = {
+    "v_ddim_x0": dict(kind="ddim", spec="v_tiny", seed=1, B=2, T=1000, S=5, objective="pred_x0", eta=0.0, scale=1.5,
+                      phi=0.3, rng=41),          # phi is ignored by the reference's ddim_sample (V:335)
+    "v_ddim_eps_eta": dict(kind="ddim", spec="v_tiny", seed=1, B=3, T=1000, S=4, objective="pred_noise", eta=1.0,
+                           scale=2.0, phi=0.7, rng=42),
+    "v_ddim_v_attn": dict(kind="ddim", spec="v_attn", seed=3, B=2, T=200, S=3, objective="pred_v", eta=0.5, scale=1.5,
+                          phi=0.7, rng=43),
+    "v_ddpm_x0": dict(kind="ddpm", spec="v_tiny", seed=1, B=2, T=1000, S=4, objective="pred_x0", eta=1.0, scale=1.5,
+                      phi=0.4, rng=44),
+    "v_ddpm_eps_unguided": dict(kind="ddpm", spec="v_attn", seed=3, B=2, T=1000, S=3, objective="pred_noise", eta=1.0,
+                                scale=1.0, phi=0.7, rng=45),
+}
+
+
+def sampler_classes(c):
+    g = torch.Generator().manual_seed(c["rng"] + 1000)
+    return torch.rand(c["B"], V_SPECS[c["spec"]].embed_input_dim, generator=g)

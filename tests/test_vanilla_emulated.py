@@ -32,7 +32,7 @@ def test_program_matches_oracle_and_reference(name):
     x, t, classes = vanilla_inputs(sname)
     B, size = V_BATCH[sname], V_SIZES[sname]
     ws = WeightStore(torch.device("cpu"))
-    prog = VanillaProgram(net, ws, B, size, size, mode == "train")
+    prog = VanillaProgram(net, ws, B, B, size, size, mode == "train")
     keep = keep_mask(kind, B)
     prog.load_inputs(x, t, classes, keep.to(torch.uint8))
     out = run_program(prog, ws)
@@ -57,3 +57,22 @@ def test_no_cpu_fallback():
     _, net = build("v_tiny", 0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         net.eval()(torch.zeros(2, 3, 16, 16), torch.zeros(2, dtype=torch.long), torch.zeros(2, 16), cond_drop_prob=0.0)
+
+
+def test_pair_batch_shares_the_input():
+    """2B program with x_batch = B (what the guided sampler runs): halves == conditional / unconditional forwards."""
+    spec, net = build("v_tiny", 1)
+    net.eval()
+    x, t, classes = vanilla_inputs("v_tiny")
+    B, size = V_BATCH["v_tiny"], V_SIZES["v_tiny"]
+    ws = WeightStore(torch.device("cpu"))
+    prog = VanillaProgram(net, ws, 2 * B, B, size, size, False)
+    keep = torch.cat([torch.ones(B), torch.zeros(B)]).to(torch.uint8)
+    prog.load_inputs(x, torch.cat([t, t]), torch.cat([classes, classes]), keep)
+    out = run_program(prog, ws)
+    sd = make_state_dict(spec, 1)
+    with torch.no_grad():
+        c = vanilla_unet_forward(sd, spec, x, t, classes, torch.ones(B, dtype=torch.bool))
+        n = vanilla_unet_forward(sd, spec, x, t, classes, torch.zeros(B, dtype=torch.bool))
+    assert ((out[:B] - c).norm() / c.norm()).item() < 2e-2
+    assert ((out[B:] - n).norm() / n.norm()).item() < 2e-2
