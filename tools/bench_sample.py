@@ -1,6 +1,7 @@
 """Guided sampling throughput of the other BASELINE.json sampling configurations (the headline RC-49 64x64 line is
 bench.py):  --model sa128  SteeringAngle 128x128 CCDM, DDIM-250, covariance-embedded labels (use_Hy), cond_scale 1.5
             --model uk128  UTKFace 128x128 CcDPM, DDPM-1000 (`.sample`), pred_noise, cond_scale 2.0
+            --model vrc64  vanilla (GroupNorm) RC-49 64x64 UNet, DDIM-250, cond_scale 1.5 (V/scripts/run_train_ccdm.sh)
 CUDA-event timed, W warm-up + K timed samplings, max over ranks under torchrun; one JSON line.
 
   python tools/bench_sample.py --model sa128 [--batch 64] [--steps 2] [--warmup 1]
@@ -22,6 +23,8 @@ MODELS = {   # forward GFLOP per image from SURVEY.md section 8d
                   use_Hy=True, scale=1.5),
     "uk128": dict(dim=64, dim_mults=(1, 2, 4, 4, 8, 8), size=128, gflop=52.08, sampler="ddpm", S=1000,
                   objective="pred_noise", use_Hy=False, scale=2.0),
+    # vanilla tree (CCDM_vanilla/RC-49/RC-49_64x64/CCGM/CCDM/scripts/run_train_ccdm.sh); 21.8 GFLOP / image
+    "vrc64": dict(vanilla=True, size=64, gflop=21.8, sampler="ddim", S=250, objective="pred_x0", use_Hy=False, scale=1.5),
 }
 
 
@@ -47,18 +50,26 @@ def main():
     m = MODELS[a.model]
     S = a.sampling_steps or m["S"]
     torch.manual_seed(111)
-    net = ccdm_b200.Unet(dim=m["dim"], embed_input_dim=128, cond_drop_prob=0.1, dim_mults=m["dim_mults"], in_channels=3,
-                         attn_dim_head=32, attn_heads=4)
     n_el = 3 * m["size"] ** 2
-    gd = ccdm_b200.GaussianDiffusion(net, image_size=m["size"], objective=m["objective"], use_Hy=m["use_Hy"],
-                                     fn_y2cov=(lambda y: (sinusoid(y, n_el) + 1) / 2) if m["use_Hy"] else None,
-                                     cond_drop_prob=0.1, timesteps=1000, sampling_timesteps=S).to(dev).eval()
+    if m.get("vanilla"):
+        net = ccdm_b200.VanillaUnet(embed_input_dim=128, cond_drop_prob=0.1, model_channels=64, num_res_blocks=2,
+                                    attention_resolutions=(16, 32), channel_mult=(1, 2, 4, 8), num_heads=4, num_groups=8)
+        gd = ccdm_b200.VanillaGaussianDiffusion(net, image_size=m["size"], objective=m["objective"], timesteps=1000,
+                                                sampling_timesteps=S, ddim_sampling_eta=0.0).to(dev).eval()
+    else:
+        net = ccdm_b200.Unet(dim=m["dim"], embed_input_dim=128, cond_drop_prob=0.1, dim_mults=m["dim_mults"], in_channels=3,
+                             attn_dim_head=32, attn_heads=4)
+        gd = ccdm_b200.GaussianDiffusion(net, image_size=m["size"], objective=m["objective"], use_Hy=m["use_Hy"],
+                                         fn_y2cov=(lambda y: (sinusoid(y, n_el) + 1) / 2) if m["use_Hy"] else None,
+                                         cond_drop_prob=0.1, timesteps=1000, sampling_timesteps=S).to(dev).eval()
     B = a.batch
     labels = torch.linspace(0, 1, B * world, device=dev)[rank * B:(rank + 1) * B]
     emb = sinusoid(labels, 128)
     shape = (B, 3, m["size"], m["size"])
 
     def run():
+        if m.get("vanilla"):
+            return gd.ddim_sample(emb, shape, cond_scale=m["scale"])
         if m["sampler"] == "ddim":
             return gd.ddim_sample(labels_emb=emb, labels=labels, shape=shape, cond_scale=m["scale"])
         return gd.sample(labels_emb=emb, labels=labels, cond_scale=m["scale"])
