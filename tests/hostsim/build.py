@@ -1,0 +1,39 @@
+"""TEST INFRASTRUCTURE: compile the CUDA-core kernels of a ccdm_b200/csrc/*.cu file for the HOST (g++, C++20) through
+tests/hostsim/cuda_host_shim.h, so that the kernel source itself -- not a restatement of it -- runs on the CPU.
+
+The .cu text is used verbatim except for (1) its two project includes, which the shim replaces, and (2) the
+``kernel<<<grid, block, 0, stream>>>(args);`` launch syntax, rewritten to ``LAUNCH(kernel, (grid), (block), args);``.
+"""
+import hashlib
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LAUNCH_RE = re.compile(r"([A-Za-z_]\w*(?:<\d+>)?)<<<(.*?),\s*(\w+),\s*0,\s*([^>]*?)>>>\((.*?)\);", re.S)
+
+
+def host_source(cu_path: str) -> str:
+    src = open(cu_path).read()
+    src = src.replace('#include "common.cuh"', "").replace('#include "ptx.cuh"', "")
+    src, n = LAUNCH_RE.subn(lambda m: f"LAUNCH({m.group(1)}, ({m.group(2)}), ({m.group(3)}), {m.group(5)});", src)
+    assert n > 0 and "<<<" not in src, "unconverted kernel launch"
+    return '#include "cuda_host_shim.h"\n' + src
+
+
+def build(cu_name: str) -> str:
+    """Returns the path of the host-compiled shared library for ccdm_b200/csrc/<cu_name> (rebuilt when the source changes)."""
+    cu_path = os.path.join(ROOT, "ccdm_b200", "csrc", cu_name)
+    text = host_source(cu_path) + open(os.path.join(HERE, "cuda_host_shim.h")).read()
+    tag = hashlib.sha1(text.encode()).hexdigest()[:12]
+    out_dir = os.path.join(HERE, "build")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, f"{os.path.splitext(cu_name)[0]}_host_{tag}.so")
+    if not os.path.exists(so):
+        cpp = so[:-3] + ".cpp"
+        with open(cpp, "w") as f:
+            f.write(host_source(cu_path))
+        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-I", HERE,
+                        "-I", os.path.join(ROOT, "include"), cpp, "-o", so], check=True)
+    return so

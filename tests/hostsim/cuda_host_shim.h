@@ -1,0 +1,128 @@
+// TEST INFRASTRUCTURE: a minimal CUDA-on-host shim so that the CUDA-core kernels of a .cu file can be compiled by g++ and
+// executed on the CPU exactly as written (index math, shared-memory staging, barriers, shuffles, atomics), one thread
+// block at a time with one OS thread per CUDA thread.  Used by tests/test_kernels_hostsim.py to check kernels in a
+// container without a GPU; it is NOT a fallback and nothing under ccdm_b200/ uses it.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <barrier>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include "ccdm_b200.h"
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct uint4 { uint32_t x, y, z, w; };
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+static const int cudaSuccess = 0;
+
+static thread_local dim3 threadIdx, blockIdx;
+static dim3 blockDim, gridDim;
+static std::unique_ptr<std::barrier<>> g_bar;
+static std::vector<float> g_shfl;
+
+#define __global__ static
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static              // blocks run one at a time, so one static copy per kernel == per-block storage
+
+static inline void __syncthreads() { g_bar->arrive_and_wait(); }
+static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+// every thread of the block must take part (true for the kernels tested: uniform trip counts)
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  const unsigned t = threadIdx.x;
+  g_shfl[t] = v;
+  g_bar->arrive_and_wait();
+  const float r = g_shfl[(t & ~31u) | ((t ^ (unsigned)lane_mask) & 31u)];
+  g_bar->arrive_and_wait();
+  return r;
+}
+#define __expf(x) expf(x)
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+using std::max;
+using std::min;
+
+struct __nv_bfloat16 { uint16_t v; };
+static inline float __bfloat162float(__nv_bfloat16 h) {
+  uint32_t u = (uint32_t)h.v << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline __nv_bfloat16 __float2bfloat16(float f) {          // round to nearest even, as the device intrinsic
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  __nv_bfloat16 h;
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) { h.v = 0x7FFF; return h; }
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  h.v = (uint16_t)(u >> 16);
+  return h;
+}
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
+
+// ---- what the kernels use from common.cuh / ptx.cuh
+namespace ccdm {
+static char g_err[512];
+static inline void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+static inline int cuda_fail(cudaError_t, const char* what) { set_error("%s", what); return CCDM_ERR_CUDA; }
+static inline int after_launch(const char*) { return CCDM_OK; }
+static inline int num_sms() { return 148; }
+static inline float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+static inline float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+}  // namespace ccdm
+#define CCDM_REQUIRE(cond, code, ...)  \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::ccdm::set_error(__VA_ARGS__);  \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+static inline void launch_blocks(dim3 grid, dim3 block, const std::function<void()>& body) {
+  gridDim = grid;
+  blockDim = block;
+  g_shfl.assign(block.x, 0.f);
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        g_bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)block.x);
+        std::vector<std::thread> ts;
+        ts.reserve(block.x);
+        for (unsigned t = 0; t < block.x; ++t)
+          ts.emplace_back([&, t] {
+            threadIdx = dim3(t, 0, 0);
+            blockIdx = dim3(bx, by, bz);
+            body();
+            g_bar->arrive_and_drop();          // a thread that returned early must not block later barriers
+          });
+        for (auto& th : ts) th.join();
+      }
+}
+#define LAUNCH(kernel, grid, block, ...) launch_blocks(dim3 grid, dim3 block, [&] { kernel(__VA_ARGS__); })
+
+extern "C" const char* hostsim_last_error() { return ccdm::g_err; }
