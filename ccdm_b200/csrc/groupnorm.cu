@@ -90,6 +90,155 @@ __global__ void groupnorm_coef_kernel(const float* __restrict__ sums, int Ctot, 
   }
 }
 
+// ---------------------------------------------------------------------------- backward of norm -> affine -> activation
+// Forward (per source): u = x*(1+s_bc) + t_bc, y = act(u), with (s, t) the forward coefficients of groupnorm_coef_kernel.
+// d act(u)/du recomputed from x: act 0 none, 1 ReLU, 2 SiLU.
+__device__ __forceinline__ float act_grad(float u, int act) {
+  if (act == 1) return u > 0.f ? 1.f : 0.f;
+  if (act == 2) {
+    const float sg = 1.f / (1.f + __expf(-u));
+    return sg * (1.f + u * (1.f - sg));
+  }
+  return 1.f;
+}
+
+// bsums[b][0][c_off+c] += sum_p du,  bsums[b][1][c_off+c] += sum_p du*x,  du = dy * act'(x*(1+s)+t).
+// Same decomposition as channel_stats_kernel; dy, x: bf16 [B][rows_per_sample][C].  grid = (slabs, B).
+__global__ void __launch_bounds__(256) norm_bwd_stats_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                                             int rows_per_sample, int C, int slab,
+                                                             const float* __restrict__ coef, int coef_ld, int coef_off,
+                                                             int act, float* __restrict__ bsums, int ld, int c_off) {
+  __shared__ float acc_s[2 * 2048];
+  const int nchunk = C >> 3;
+  const int lanes = 256 / nchunk;
+  const int tid = threadIdx.x, b = blockIdx.y;
+  for (int i = tid; i < 2 * C; i += 256) acc_s[i] = 0.f;
+  __syncthreads();
+  const int ch = tid % nchunk, rl = tid / nchunk;
+  if (rl < lanes) {
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sc[8], sh[8];
+    const float* crow = coef + (long long)b * coef_ld + coef_off;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = 1.f + crow[ch * 8 + j];
+      sh[j] = crow[C + ch * 8 + j];
+    }
+    const long long base = (long long)b * rows_per_sample * nchunk;
+    const int r0 = blockIdx.x * slab, r1 = min(r0 + slab, rows_per_sample);
+    for (int r = r0 + rl; r < r1; r += lanes) {
+      const uint4 ux = __ldg(x + base + (long long)r * nchunk + ch);
+      const uint4 ud = __ldg(dy + base + (long long)r * nchunk + ch);
+      const float xv[8] = {bf16_lo(ux.x), bf16_hi(ux.x), bf16_lo(ux.y), bf16_hi(ux.y),
+                           bf16_lo(ux.z), bf16_hi(ux.z), bf16_lo(ux.w), bf16_hi(ux.w)};
+      const float dv[8] = {bf16_lo(ud.x), bf16_hi(ud.x), bf16_lo(ud.y), bf16_hi(ud.y),
+                           bf16_lo(ud.z), bf16_hi(ud.z), bf16_lo(ud.w), bf16_hi(ud.w)};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float du = dv[j] * act_grad(fmaf(xv[j], sc[j], sh[j]), act);
+        s1[j] += du;
+        s2[j] = fmaf(du, xv[j], s2[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&acc_s[ch * 8 + j], s1[j]);
+      atomicAdd(&acc_s[C + ch * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  float* dst = bsums + (long long)b * 2 * ld + c_off;
+  for (int i = tid; i < C; i += 256) {
+    atomicAdd(dst + i, acc_s[i]);
+    atomicAdd(dst + ld + i, acc_s[C + i]);
+  }
+}
+
+// One thread per (sample, channel) of the concatenated axis.  With x^ = (x-mu_g) r_g, m = 1+scale_bc, S1 = sum_p du,
+// S2 = sum_p du*x, Sx = sum_p du*x^ = r (S2 - mu S1), and the group means M1 = sum_{c in g} gamma_c m S1 / cnt,
+// M2 = sum_{c in g} gamma_c m Sx / cnt:
+//   dx = A*du + Bc*x + Cc,   A = r gamma m (the forward coefficient),  Bc = -r^2 M2,  Cc = r^2 M2 mu - r M1
+//   dgamma_c += m Sx,  dbeta_c += m S1,  dscale_bc = gamma Sx + beta S1,  dshift_bc = S1.
+// bcoef: per source [A | Bc | Cc] segments (source 0 at 0, source 1 at 3*C0); d_ss: [B][2*Ctot] = [dscale | dshift].
+__global__ void groupnorm_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ bsums, int Ctot, int G,
+                                          float inv_count, float eps, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, const float* __restrict__ ss_in, int ss_ld,
+                                          int ss_off, int C0, float* __restrict__ bcoef, float* __restrict__ dgamma,
+                                          float* __restrict__ dbeta, float* __restrict__ d_ss, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Ctot) return;
+  const int b = i / Ctot, c = i - b * Ctot;
+  const int cg = Ctot / G, g0 = (c / cg) * cg;
+  const float* s = sums + (long long)b * 2 * Ctot;
+  const float* bs = bsums + (long long)b * 2 * Ctot;
+  float sum = 0.f, sq = 0.f;
+  for (int k = 0; k < cg; ++k) {
+    sum += s[g0 + k];
+    sq += s[Ctot + g0 + k];
+  }
+  const float mean = sum * inv_count;
+  const float var = fmaxf(sq * inv_count - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  float m1 = 0.f, m2 = 0.f;
+  for (int k = 0; k < cg; ++k) {
+    const int ck = g0 + k;
+    const float mk = ss_in ? 1.f + ss_in[(long long)b * ss_ld + ss_off + ck] : 1.f;
+    const float gm = gamma[ck] * mk;
+    m1 = fmaf(gm, bs[ck], m1);
+    m2 = fmaf(gm, rstd * (bs[Ctot + ck] - mean * bs[ck]), m2);
+  }
+  m1 *= inv_count;
+  m2 *= inv_count;
+  const float m = ss_in ? 1.f + ss_in[(long long)b * ss_ld + ss_off + c] : 1.f;
+  const float S1 = bs[c], Sx = rstd * (bs[Ctot + c] - mean * S1);
+  const float A = rstd * gamma[c] * m;
+  const float Bc = -rstd * rstd * m2;
+  const float Cc = rstd * rstd * m2 * mean - rstd * m1;
+  float* row = bcoef + (long long)b * 3 * Ctot;
+  if (c < C0) {
+    row[c] = A;
+    row[C0 + c] = Bc;
+    row[2 * C0 + c] = Cc;
+  } else {
+    const int c1 = c - C0, C1 = Ctot - C0;
+    row[3 * C0 + c1] = A;
+    row[3 * C0 + C1 + c1] = Bc;
+    row[3 * C0 + 2 * C1 + c1] = Cc;
+  }
+  if (dgamma) atomicAdd(dgamma + c, m * Sx);
+  if (dbeta) atomicAdd(dbeta + c, m * S1);
+  if (d_ss) {
+    d_ss[(long long)b * 2 * Ctot + c] = fmaf(gamma[c], Sx, beta[c] * S1);
+    d_ss[(long long)b * 2 * Ctot + Ctot + c] = S1;
+  }
+}
+
+// dx = A*du + Bc*x + Cc per element, du = dy * act'(x*(1+s)+t); one thread per 8-channel vector.
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                                             uint4* __restrict__ dx, long long nvec, int nchunk,
+                                                             int rows_per_sample, int C, const float* __restrict__ coef,
+                                                             int coef_ld, int coef_off, const float* __restrict__ bcoef,
+                                                             int bcoef_ld, int bcoef_off, int act) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / nchunk;
+    const int ch = (int)(i - row * nchunk);
+    const long long b = row / rows_per_sample;
+    const float* crow = coef + b * coef_ld + coef_off + ch * 8;
+    const float* brow = bcoef + b * bcoef_ld + bcoef_off + ch * 8;
+    const uint4 ux = __ldg(x + i), ud = __ldg(dy + i);
+    const float xv[8] = {bf16_lo(ux.x), bf16_hi(ux.x), bf16_lo(ux.y), bf16_hi(ux.y),
+                         bf16_lo(ux.z), bf16_hi(ux.z), bf16_lo(ux.w), bf16_hi(ux.w)};
+    const float dv[8] = {bf16_lo(ud.x), bf16_hi(ud.x), bf16_lo(ud.y), bf16_hi(ud.y),
+                         bf16_lo(ud.z), bf16_hi(ud.z), bf16_lo(ud.w), bf16_hi(ud.w)};
+    alignas(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float du = dv[j] * act_grad(fmaf(xv[j], 1.f + crow[j], crow[C + j]), act);
+      o[j] = __float2bfloat16(fmaf(brow[j], du, fmaf(brow[C + j], xv[j], brow[2 * C + j])));
+    }
+    dx[i] = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
 // timestep_embedding (V/models/unet.py:40-57): out[b] = [cos(t*f_j) | sin(t*f_j)], f_j = exp(-ln(max_period)*j/half).
 // (The unified UNet's SinusoidalPosEmb is sin | cos with the exponent divided by half-1: ccdm_time_features.)
 __global__ void time_features_adm_kernel(const long long* __restrict__ t, int B, int dim, float log_period,
@@ -194,6 +343,62 @@ extern "C" int ccdm_groupnorm_coef(const float* sums, int32_t B, int32_t Ctot, i
   groupnorm_coef_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, Ctot, groups, inv_count, eps, gamma, beta,
                                                                            scale_shift, ss_ld, ss_off, C0, coef, B);
   return after_launch("groupnorm_coef_kernel");
+}
+
+extern "C" int ccdm_norm_bwd_stats(const void* dy, const void* x, int32_t B, int32_t rows_per_sample, int32_t C,
+                                   const float* coef, int32_t coef_ld, int32_t coef_off, int32_t act, float* bsums,
+                                   int32_t ld, int32_t c_off, int32_t zero_first, void* stream) {
+  CCDM_REQUIRE(dy && x && coef && bsums && B > 0 && rows_per_sample > 0 && c_off >= 0 && ld >= c_off + C &&
+                   coef_ld >= coef_off + 2 * C && act >= 0 && act <= 2,
+               CCDM_ERR_BAD_ARG, "norm_bwd_stats: bad args");
+  CCDM_REQUIRE(C > 0 && C % 8 == 0 && C <= 2048, CCDM_ERR_UNSUPPORTED_SHAPE, "norm_bwd_stats: C=%d (multiple of 8, <= 2048)", C);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(bsums, 0, (size_t)B * 2 * ld * sizeof(float), s);
+    if (e != cudaSuccess) return cuda_fail(e, "norm_bwd_stats: memset");
+  }
+  const int lanes = 256 / (C / 8);
+  int slabs = (num_sms() * 4 + B - 1) / B;
+  const int max_slabs = (rows_per_sample + lanes * 4 - 1) / (lanes * 4);
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  const int slab = (rows_per_sample + slabs - 1) / slabs;
+  slabs = (rows_per_sample + slab - 1) / slab;
+  norm_bwd_stats_kernel<<<dim3(slabs, B), 256, 0, s>>>((const uint4*)dy, (const uint4*)x, rows_per_sample, C, slab, coef,
+                                                       coef_ld, coef_off, act, bsums, ld, c_off);
+  return after_launch("norm_bwd_stats_kernel");
+}
+
+extern "C" int ccdm_groupnorm_bwd_coef(const float* sums, const float* bsums, int32_t B, int32_t Ctot, int32_t groups,
+                                       int64_t rows_per_sample, float eps, const float* gamma, const float* beta,
+                                       const float* scale_shift, int32_t ss_ld, int32_t ss_off, int32_t C0, float* bcoef,
+                                       float* dgamma, float* dbeta, float* d_ss, void* stream) {
+  CCDM_REQUIRE(sums && bsums && gamma && beta && bcoef && B > 0 && Ctot > 0 && rows_per_sample > 0, CCDM_ERR_BAD_ARG,
+               "groupnorm_bwd_coef: bad args");
+  CCDM_REQUIRE(groups > 0 && Ctot % groups == 0 && C0 > 0 && C0 <= Ctot, CCDM_ERR_BAD_ARG,
+               "groupnorm_bwd_coef: Ctot=%d groups=%d C0=%d", Ctot, groups, C0);
+  const int n = B * Ctot;
+  const float inv_count = 1.f / ((float)rows_per_sample * (float)(Ctot / groups));
+  groupnorm_bwd_coef_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, bsums, Ctot, groups, inv_count, eps,
+                                                                               gamma, beta, scale_shift, ss_ld, ss_off, C0,
+                                                                               bcoef, dgamma, dbeta, d_ss, B);
+  return after_launch("groupnorm_bwd_coef_kernel");
+}
+
+extern "C" int ccdm_norm_bwd_apply(const void* dy, const void* x, void* dx, int64_t rows, int32_t C, int32_t rows_per_sample,
+                                   const float* coef, int32_t coef_ld, int32_t coef_off, const float* bcoef,
+                                   int32_t bcoef_ld, int32_t bcoef_off, int32_t act, void* stream) {
+  CCDM_REQUIRE(dy && x && dx && coef && bcoef && rows > 0 && rows_per_sample > 0 && rows % rows_per_sample == 0 &&
+                   act >= 0 && act <= 2,
+               CCDM_ERR_BAD_ARG, "norm_bwd_apply: bad args");
+  CCDM_REQUIRE(C > 0 && C % 8 == 0, CCDM_ERR_UNSUPPORTED_SHAPE, "norm_bwd_apply: C=%d", C);
+  const long long nvec = rows * (C / 8);
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  norm_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)x, (uint4*)dx,
+                                                                            nvec, C / 8, rows_per_sample, C, coef, coef_ld,
+                                                                            coef_off, bcoef, bcoef_ld, bcoef_off, act);
+  return after_launch("norm_bwd_apply_kernel");
 }
 
 extern "C" int ccdm_time_features_adm(const int64_t* t, int32_t B, int32_t dim, float max_period, float* out,

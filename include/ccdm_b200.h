@@ -385,6 +385,24 @@ int ccdm_channel_stats(const void* x, int32_t B, int32_t rows_per_sample, int32_
 int ccdm_groupnorm_coef(const float* sums, int32_t B, int32_t Ctot, int32_t groups, int64_t rows_per_sample, float eps,
                         const float* gamma, const float* beta, const float* scale_shift, int32_t ss_ld, int32_t ss_off,
                         int32_t C0, float* coef, void* stream);
+/* Backward of [GroupNorm ->] x*(1+s)+t -> act (autograd of unet.py:99,111,146 reached from loss.backward()), three steps:
+ *  1. ccdm_norm_bwd_stats:   bsums[b][0][c_off+c] += sum_p du, bsums[b][1][c_off+c] += sum_p du*x with du = dy*act'(x*(1+s)+t);
+ *                            dy, x bf16 [B][rows_per_sample][C]; coef = the forward [s | t] segment of this source
+ *                            (fp32 [B][coef_ld] at coef_off); act 0 none / 1 ReLU / 2 SiLU; bsums fp32 [B][2][ld].
+ *  2. ccdm_groupnorm_bwd_coef: from the forward sums and bsums (both [B][2][Ctot]): per source [A | Bc | Cc] segments of
+ *                            bcoef fp32 [B][3*Ctot] (source 0 at 0, source 1 at 3*C0) such that dx = A*du + Bc*x + Cc;
+ *                            dgamma[c] += , dbeta[c] += (may be NULL); d_ss [B][2*Ctot] = [dscale | dshift] (may be NULL).
+ *  3. ccdm_norm_bwd_apply:   dx (bf16) = A*du + Bc*x + Cc per element, du recomputed as in step 1. */
+int ccdm_norm_bwd_stats(const void* dy, const void* x, int32_t B, int32_t rows_per_sample, int32_t C, const float* coef,
+                        int32_t coef_ld, int32_t coef_off, int32_t act, float* bsums, int32_t ld, int32_t c_off,
+                        int32_t zero_first, void* stream);
+int ccdm_groupnorm_bwd_coef(const float* sums, const float* bsums, int32_t B, int32_t Ctot, int32_t groups,
+                            int64_t rows_per_sample, float eps, const float* gamma, const float* beta,
+                            const float* scale_shift, int32_t ss_ld, int32_t ss_off, int32_t C0, float* bcoef,
+                            float* dgamma, float* dbeta, float* d_ss, void* stream);
+int ccdm_norm_bwd_apply(const void* dy, const void* x, void* dx, int64_t rows, int32_t C, int32_t rows_per_sample,
+                        const float* coef, int32_t coef_ld, int32_t coef_off, const float* bcoef, int32_t bcoef_ld,
+                        int32_t bcoef_off, int32_t act, void* stream);
 /* timestep_embedding (unet.py:40-57): out fp32 [B][dim] = [cos(t*f_j) | sin(t*f_j)], f_j = max_period^(-j/(dim/2)); dim even. */
 int ccdm_time_features_adm(const int64_t* t, int32_t B, int32_t dim, float max_period, float* out, void* stream);
 /* AttentionBlock core (unet.py:165-175): out[b][t][h*dh+d] = softmax_s(q_t . k_s * scale) v_s over all n tokens;

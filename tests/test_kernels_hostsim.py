@@ -101,3 +101,69 @@ def test_time_features_adm(lib):
         out = torch.empty(5, dim)
         assert lib.ccdm_time_features_adm(t.data_ptr(), 5, dim, 10000.0, out.data_ptr(), None) == 0
         assert (out - timestep_embedding(t, dim)).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("cs,groups,hw,with_ss,act", [((64,), 8, (8, 8), False, 2), ((64, 32), 4, (6, 5), True, 2),
+                                                      ((72,), 8, (4, 7), True, 2), ((16, 8), 3, (5, 5), True, 0),
+                                                      ((32,), 4, (4, 4), False, 1)])
+def test_groupnorm_backward_chain_matches_autograd(lib, cs, groups, hw, with_ss, act):
+    """norm_bwd_stats -> groupnorm_bwd_coef -> norm_bwd_apply == autograd of act(group_norm(cat(x)) [*(1+scale)+shift])
+    w.r.t. x, gamma, beta, scale, shift -- with groups that straddle the two concatenated sources."""
+    lib.ccdm_norm_bwd_stats.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, i32, i32, i32, vp]
+    lib.ccdm_groupnorm_bwd_coef.argtypes = [vp, vp, i32, i32, i32, i64, f32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.ccdm_norm_bwd_apply.argtypes = [vp, vp, vp, i64, i32, i32, vp, i32, i32, vp, i32, i32, i32, vp]
+    g = torch.Generator().manual_seed(17)
+    B, (h, w), ctot = 3, hw, sum(cs)
+    xs = [(torch.randn(B, h, w, c, generator=g) * 1.5 + 0.3).to(torch.bfloat16).contiguous() for c in cs]
+    dys = [torch.randn(B, h, w, c, generator=g).to(torch.bfloat16).contiguous() for c in cs]
+    gamma = 1 + 0.2 * torch.randn(ctot, generator=g)
+    beta = 0.1 * torch.randn(ctot, generator=g)
+    SS_OFF = 24
+    ss = 0.3 * torch.randn(B, SS_OFF + 2 * ctot, generator=g) if with_ss else None
+    ssp = ss.data_ptr() if with_ss else None
+    ss_ld = ss.shape[1] if with_ss else 0
+    # ---- forward statistics and coefficients (kernels under test in the forward tests above)
+    sums = torch.zeros(B, 2, ctot)
+    off = 0
+    for i, x in enumerate(xs):
+        assert lib.ccdm_channel_stats(x.data_ptr(), B, h * w, x.shape[3], sums.data_ptr(), ctot, off, int(i == 0), None) == 0
+        off += x.shape[3]
+    coef = torch.empty(B, 2 * ctot)
+    assert lib.ccdm_groupnorm_coef(sums.data_ptr(), B, ctot, groups, h * w, 1e-5, gamma.data_ptr(), beta.data_ptr(), ssp,
+                                   ss_ld, SS_OFF, cs[0], coef.data_ptr(), None) == 0
+    # ---- backward
+    bsums = torch.full((B, 2, ctot), 3.0)
+    off = coff = 0
+    for i, (x, dy) in enumerate(zip(xs, dys)):
+        c = x.shape[3]
+        assert lib.ccdm_norm_bwd_stats(dy.data_ptr(), x.data_ptr(), B, h * w, c, coef.data_ptr(), 2 * ctot, coff, act,
+                                       bsums.data_ptr(), ctot, off, int(i == 0), None) == 0, lib.hostsim_last_error()
+        off, coff = off + c, coff + 2 * c
+    bcoef = torch.empty(B, 3 * ctot)
+    dgamma, dbeta = torch.full((ctot,), 0.5), torch.full((ctot,), -0.25)      # accumulate semantics
+    d_ss = torch.empty(B, 2 * ctot)
+    assert lib.ccdm_groupnorm_bwd_coef(sums.data_ptr(), bsums.data_ptr(), B, ctot, groups, h * w, 1e-5, gamma.data_ptr(),
+                                       beta.data_ptr(), ssp, ss_ld, SS_OFF, cs[0], bcoef.data_ptr(), dgamma.data_ptr(),
+                                       dbeta.data_ptr(), d_ss.data_ptr(), None) == 0, lib.hostsim_last_error()
+    dxs, coff, boff = [], 0, 0
+    for x, dy in zip(xs, dys):
+        c = x.shape[3]
+        dx = torch.empty_like(x)
+        assert lib.ccdm_norm_bwd_apply(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), B * h * w, c, h * w, coef.data_ptr(),
+                                       2 * ctot, coff, bcoef.data_ptr(), 3 * ctot, boff, act, None) == 0
+        dxs.append(dx)
+        coff, boff = coff + 2 * c, boff + 3 * c
+    # ---- autograd reference on the same (bf16-rounded) inputs
+    xr = torch.cat([x.float() for x in xs], -1).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.group_norm(xr.permute(0, 3, 1, 2), groups, gr, br, eps=1e-5)
+    if with_ss:
+        sc = ss[:, SS_OFF:SS_OFF + ctot].clone().requires_grad_(True)
+        sh = ss[:, SS_OFF + ctot:SS_OFF + 2 * ctot].clone().requires_grad_(True)
+        y = y * (1 + sc[:, :, None, None]) + sh[:, :, None, None]
+    y = {0: lambda v: v, 1: F.relu, 2: F.silu}[act](y)
+    y.backward(torch.cat([d.float() for d in dys], -1).permute(0, 3, 1, 2))
+    assert rel(torch.cat([d.float() for d in dxs], -1), xr.grad) < 6e-3          # bf16 output rounding
+    assert rel(dgamma - 0.5, gr.grad) < 1e-4 and rel(dbeta + 0.25, br.grad) < 1e-4
+    if with_ss:
+        assert rel(d_ss[:, :ctot], sc.grad) < 1e-4 and rel(d_ss[:, ctot:], sh.grad) < 1e-4
