@@ -118,6 +118,7 @@ SIGNATURES = {
     "ccdm_norm_bwd_stats": (C.c_int, [vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, i32, i32, i32, vp]),
     "ccdm_groupnorm_bwd_coef": (C.c_int, [vp, vp, i32, i32, i32, i64, f32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "ccdm_norm_bwd_apply": (C.c_int, [vp, vp, vp, i64, i32, i32, vp, i32, i32, vp, i32, i32, i32, vp]),
+    "ccdm_attention_tokens_bwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
     "ccdm_time_features_adm": (C.c_int, [vp, i32, i32, f32, vp, vp]),
     "ccdm_attention_tokens": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, i32, vp]),
     "ccdm_fused_adam": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, f32, f32, vp]),

@@ -306,6 +306,149 @@ __global__ void __launch_bounds__(128) attention_tokens_kernel(const __nv_bfloat
   for (int dd = 0; dd < HD; ++dd) o[2 * dd + half] = __float2bfloat16(acc[dd] * inv);
 }
 
+// Backward of attention_tokens_kernel.  One CTA per (sample, head); shared memory holds q, k, v, dO of the head as fp32
+// [n][DH] plus per-query (max, 1/sum, D = <dO, O>).  SPLIT threads share one token, thread `part` owning the head
+// dimensions d = SPLIT*dd + part (dot products are completed with xor shuffles).  Phase A (token = query): softmax
+// statistics and dq.  Phase B (token = key): dk, dv.  Same channel layout parameters as the forward.
+template <int DH, int SPLIT>
+__global__ void __launch_bounds__(128) attention_tokens_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                   const __nv_bfloat16* __restrict__ dout,
+                                                                   __nv_bfloat16* __restrict__ dqkv, int n, int heads,
+                                                                   float scale, int hs, int qo, int ko, int vo) {
+  constexpr int HD = DH / SPLIT, TOK = 128 / SPLIT;
+  extern __shared__ float att_smem[];
+  float* sq = att_smem;
+  float* sk = sq + (size_t)n * DH;
+  float* sv = sk + (size_t)n * DH;
+  float* sd = sv + (size_t)n * DH;
+  float* st = sd + (size_t)n * DH;                                 // [n][3]
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int hid = heads * DH, ld = 3 * hid;
+  const __nv_bfloat16* base = qkv + (size_t)b * n * ld + h * hs;
+  const __nv_bfloat16* dob = dout + (size_t)b * n * hid + h * DH;
+  __nv_bfloat16* gbase = dqkv + (size_t)b * n * ld + h * hs;
+  const int tid = threadIdx.x, part = tid % SPLIT, slot = tid / SPLIT;
+  for (int e = tid; e < n * DH; e += 128) {
+    const int tok = e / DH, dd = e % DH;
+    const __nv_bfloat16* p = base + (size_t)tok * ld + dd;
+    sq[e] = __bfloat162float(p[qo]) * scale;                       // q arrives pre-scaled in shared memory
+    sk[e] = __bfloat162float(p[ko]);
+    sv[e] = __bfloat162float(p[vo]);
+    sd[e] = __bfloat162float(dob[(size_t)tok * hid + dd]);
+  }
+  __syncthreads();
+  // ---- phase A: per query i
+  for (int i0 = 0; i0 < n; i0 += TOK) {
+    const int i = i0 + slot;
+    const bool active = i < n;
+    const int ir = active ? i : 0;
+    float q[HD], g[HD], dq[HD];
+#pragma unroll
+    for (int dd = 0; dd < HD; ++dd) {
+      q[dd] = sq[ir * DH + SPLIT * dd + part];
+      g[dd] = sd[ir * DH + SPLIT * dd + part];
+      dq[dd] = 0.f;
+    }
+    float m = -FLT_MAX;
+    for (int j = 0; j < n; ++j) {
+      float sc = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) sc = fmaf(q[dd], sk[j * DH + SPLIT * dd + part], sc);
+#pragma unroll
+      for (int off = 1; off < SPLIT; off <<= 1) sc += __shfl_xor_sync(0xffffffffu, sc, off);
+      m = fmaxf(m, sc);
+    }
+    float l = 0.f, dsum = 0.f;                                      // dsum = sum_j e_ij * <dO_i, v_j>
+    for (int j = 0; j < n; ++j) {
+      float sc = 0.f, gv = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) {
+        sc = fmaf(q[dd], sk[j * DH + SPLIT * dd + part], sc);
+        gv = fmaf(g[dd], sv[j * DH + SPLIT * dd + part], gv);
+      }
+#pragma unroll
+      for (int off = 1; off < SPLIT; off <<= 1) {
+        sc += __shfl_xor_sync(0xffffffffu, sc, off);
+        gv += __shfl_xor_sync(0xffffffffu, gv, off);
+      }
+      const float e = __expf(sc - m);
+      l += e;
+      dsum = fmaf(e, gv, dsum);
+    }
+    const float inv = 1.f / l;
+    const float D = dsum * inv;                                     // <dO_i, O_i>
+    for (int j = 0; j < n; ++j) {
+      float sc = 0.f, gv = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) {
+        sc = fmaf(q[dd], sk[j * DH + SPLIT * dd + part], sc);
+        gv = fmaf(g[dd], sv[j * DH + SPLIT * dd + part], gv);
+      }
+#pragma unroll
+      for (int off = 1; off < SPLIT; off <<= 1) {
+        sc += __shfl_xor_sync(0xffffffffu, sc, off);
+        gv += __shfl_xor_sync(0xffffffffu, gv, off);
+      }
+      const float ds = __expf(sc - m) * inv * (gv - D);
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) dq[dd] = fmaf(ds, sk[j * DH + SPLIT * dd + part], dq[dd]);
+    }
+    if (active) {
+      if (part == 0) {
+        st[i * 3] = m;
+        st[i * 3 + 1] = inv;
+        st[i * 3 + 2] = D;
+      }
+      __nv_bfloat16* o = gbase + (size_t)i * ld + qo;
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) o[SPLIT * dd + part] = __float2bfloat16(dq[dd] * scale);
+    }
+  }
+  __syncthreads();
+  // ---- phase B: per key j
+  for (int j0 = 0; j0 < n; j0 += TOK) {
+    const int j = j0 + slot;
+    const bool active = j < n;
+    const int jr = active ? j : 0;
+    float kk[HD], vv[HD], dk[HD], dv[HD];
+#pragma unroll
+    for (int dd = 0; dd < HD; ++dd) {
+      kk[dd] = sk[jr * DH + SPLIT * dd + part];
+      vv[dd] = sv[jr * DH + SPLIT * dd + part];
+      dk[dd] = 0.f;
+      dv[dd] = 0.f;
+    }
+    for (int i = 0; i < n; ++i) {
+      float sc = 0.f, gv = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) {
+        sc = fmaf(sq[i * DH + SPLIT * dd + part], kk[dd], sc);
+        gv = fmaf(sd[i * DH + SPLIT * dd + part], vv[dd], gv);
+      }
+#pragma unroll
+      for (int off = 1; off < SPLIT; off <<= 1) {
+        sc += __shfl_xor_sync(0xffffffffu, sc, off);
+        gv += __shfl_xor_sync(0xffffffffu, gv, off);
+      }
+      const float pr = __expf(sc - st[i * 3]) * st[i * 3 + 1];
+      const float ds = pr * (gv - st[i * 3 + 2]);
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) {
+        dk[dd] = fmaf(ds, sq[i * DH + SPLIT * dd + part], dk[dd]);   // q in shared memory already carries `scale`
+        dv[dd] = fmaf(pr, sd[i * DH + SPLIT * dd + part], dv[dd]);
+      }
+    }
+    if (active) {
+      __nv_bfloat16* o = gbase + (size_t)j * ld;
+#pragma unroll
+      for (int dd = 0; dd < HD; ++dd) {
+        o[ko + SPLIT * dd + part] = __float2bfloat16(dk[dd]);
+        o[vo + SPLIT * dd + part] = __float2bfloat16(dv[dd]);
+      }
+    }
+  }
+}
+
 }  // namespace ccdm
 
 using namespace ccdm;
@@ -430,4 +573,45 @@ extern "C" int ccdm_attention_tokens(const void* qkv, void* out, int32_t B, int3
       CCDM_REQUIRE(false, CCDM_ERR_UNSUPPORTED_SHAPE, "attention_tokens: dim_head=%d (supported: 16, 32, 64, 128)", dim_head);
   }
   return after_launch("attention_tokens_kernel");
+}
+
+extern "C" int ccdm_attention_tokens_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t n, int32_t heads,
+                                         int32_t dim_head, float scale, int32_t head_major, void* stream) {
+  CCDM_REQUIRE(qkv && dout && dqkv && B > 0 && n >= 1 && heads >= 1, CCDM_ERR_BAD_ARG, "attention_tokens_bwd: bad args");
+  const size_t smem = ((size_t)4 * n * dim_head + (size_t)3 * n) * sizeof(float);
+  CCDM_REQUIRE(smem <= 200 * 1024, CCDM_ERR_UNSUPPORTED_SHAPE,
+               "attention_tokens_bwd: %d tokens x %d do not fit shared memory", n, dim_head);
+  const int hid = heads * dim_head;
+  const int hs = head_major ? 3 * dim_head : dim_head;
+  const int qo = 0, ko = head_major ? dim_head : hid, vo = head_major ? 2 * dim_head : 2 * hid;
+  cudaStream_t s = (cudaStream_t)stream;
+  const __nv_bfloat16* in = (const __nv_bfloat16*)qkv;
+  const __nv_bfloat16* dob = (const __nv_bfloat16*)dout;
+  __nv_bfloat16* o = (__nv_bfloat16*)dqkv;
+  cudaError_t e = cudaSuccess;
+  switch (dim_head) {
+    case 16:
+      e = cudaFuncSetAttribute(attention_tokens_bwd_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "attention_tokens_bwd: cudaFuncSetAttribute");
+      attention_tokens_bwd_kernel<16, 2><<<B * heads, 128, smem, s>>>(in, dob, o, n, heads, scale, hs, qo, ko, vo);
+      break;
+    case 32:
+      e = cudaFuncSetAttribute(attention_tokens_bwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "attention_tokens_bwd: cudaFuncSetAttribute");
+      attention_tokens_bwd_kernel<32, 2><<<B * heads, 128, smem, s>>>(in, dob, o, n, heads, scale, hs, qo, ko, vo);
+      break;
+    case 64:
+      e = cudaFuncSetAttribute(attention_tokens_bwd_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "attention_tokens_bwd: cudaFuncSetAttribute");
+      attention_tokens_bwd_kernel<64, 2><<<B * heads, 128, smem, s>>>(in, dob, o, n, heads, scale, hs, qo, ko, vo);
+      break;
+    case 128:
+      e = cudaFuncSetAttribute(attention_tokens_bwd_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "attention_tokens_bwd: cudaFuncSetAttribute");
+      attention_tokens_bwd_kernel<128, 4><<<B * heads, 128, smem, s>>>(in, dob, o, n, heads, scale, hs, qo, ko, vo);
+      break;
+    default:
+      CCDM_REQUIRE(false, CCDM_ERR_UNSUPPORTED_SHAPE, "attention_tokens_bwd: dim_head=%d (supported: 16, 32, 64, 128)", dim_head);
+  }
+  return after_launch("attention_tokens_bwd_kernel");
 }

@@ -411,6 +411,11 @@ int ccdm_time_features_adm(const int64_t* t, int32_t B, int32_t dim, float max_p
 int ccdm_attention_tokens(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head, float scale,
                           int32_t head_major, void* stream);
 
+/* Backward of ccdm_attention_tokens: dqkv (same layout as qkv) from the raw qkv and dout [B][n][heads*dim_head].  One CTA
+ * per (sample, head) with the head's q, k, v, dO in shared memory: n * dim_head <= ~12 k elements. */
+int ccdm_attention_tokens_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t n, int32_t heads,
+                              int32_t dim_head, float scale, int32_t head_major, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,7 +2,8 @@
 tests/hostsim/cuda_host_shim.h, so that the kernel source itself -- not a restatement of it -- runs on the CPU.
 
 The .cu text is used verbatim except for (1) its two project includes, which the shim replaces, and (2) the
-``kernel<<<grid, block, 0, stream>>>(args);`` launch syntax, rewritten to ``LAUNCH(kernel, (grid), (block), args);``.
+``kernel<<<grid, block, 0, stream>>>(args);`` launch syntax, rewritten to ``LAUNCH(kernel, (grid), (block), args);``, and (3) ``extern __shared__ float name[];``, which becomes a pointer to the shim's
+dynamic-shared-memory buffer.
 """
 import hashlib
 import os
@@ -11,13 +12,15 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LAUNCH_RE = re.compile(r"([A-Za-z_]\w*(?:<\d+>)?)<<<(.*?),\s*(\w+),\s*0,\s*([^>]*?)>>>\((.*?)\);", re.S)
+LAUNCH_RE = re.compile(r"([A-Za-z_]\w*(?:<[\d, ]+>)?)<<<(.*?),\s*(\w+),\s*\w+,\s*([^>]*?)>>>\((.*?)\);", re.S)
+DYN_SMEM_RE = re.compile(r"extern\s+__shared__\s+float\s+(\w+)\[\];")
 
 
 def host_source(cu_path: str) -> str:
     src = open(cu_path).read()
     src = src.replace('#include "common.cuh"', "").replace('#include "ptx.cuh"', "")
-    src, n = LAUNCH_RE.subn(lambda m: f"LAUNCH({m.group(1)}, ({m.group(2)}), ({m.group(3)}), {m.group(5)});", src)
+    src = DYN_SMEM_RE.sub(r"float* \1 = g_dyn_smem;", src)          # dynamic shared memory: one 256 KB host buffer
+    src, n = LAUNCH_RE.subn(lambda m: f"LAUNCH(({m.group(1)}), ({m.group(2)}), ({m.group(3)}), {m.group(5)});", src)
     assert n > 0 and "<<<" not in src, "unconverted kernel launch"
     return '#include "cuda_host_shim.h"\n' + src
 

@@ -78,6 +78,9 @@ static inline __nv_bfloat16 __float2bfloat16(float f) {          // round to nea
 }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
+static float g_dyn_smem[64 * 1024];                                  // 256 KB of "dynamic shared memory"
+static const int cudaFuncAttributeMaxDynamicSharedMemorySize = 8;
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 
 // ---- what the kernels use from common.cuh / ptx.cuh

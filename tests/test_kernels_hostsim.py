@@ -167,3 +167,23 @@ def test_groupnorm_backward_chain_matches_autograd(lib, cs, groups, hw, with_ss,
     assert rel(dgamma - 0.5, gr.grad) < 1e-4 and rel(dbeta + 0.25, br.grad) < 1e-4
     if with_ss:
         assert rel(d_ss[:, :ctot], sc.grad) < 1e-4 and rel(d_ss[:, ctot:], sh.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dh,n,head_major", [(16, 16, 0), (16, 70, 1), (32, 40, 1), (64, 33, 0), (128, 64, 1), (128, 9, 0)])
+def test_attention_tokens_backward_matches_autograd(lib, dh, n, head_major):
+    lib.ccdm_attention_tokens_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]
+    g = torch.Generator().manual_seed(3 * n + dh)
+    B, heads = 2, 2
+    hid = heads * dh
+    qkv = torch.randn(B, n, 3 * hid, generator=g).to(torch.bfloat16).contiguous()
+    dout = torch.randn(B, n, hid, generator=g).to(torch.bfloat16).contiguous()
+    dqkv = torch.zeros_like(qkv)
+    scale = 1.0 / math.sqrt(dh)
+    assert lib.ccdm_attention_tokens_bwd(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, n, heads, dh, scale, head_major,
+                                         None) == 0, lib.hostsim_last_error()
+    f = qkv.float().requires_grad_(True)
+    v5 = f.reshape(B, n, heads, 3, dh).permute(0, 1, 3, 2, 4) if head_major else f.reshape(B, n, 3, heads, dh)
+    att = torch.einsum("bihd,bjhd->bhij", v5[:, :, 0] * scale, v5[:, :, 1]).softmax(-1)
+    o = torch.einsum("bhij,bjhd->bihd", att, v5[:, :, 2]).reshape(B, n, hid)
+    o.backward(dout.float())
+    assert rel(dqkv, f.grad) < 6e-3          # bf16 output rounding
