@@ -176,10 +176,11 @@ def conv_dgrad(kind: str, dy: torch.Tensor, weight: torch.Tensor, cins: Sequence
     b, oh, ow, cout = dy.shape
     if cout != weight.shape[0] or sum(cins) != weight.shape[1]:
         raise ValueError(f"conv_dgrad: dy has {cout} channels, sources {tuple(cins)}, weight {tuple(weight.shape)}")
-    h, w = {"1x1": (oh, ow), "3x3": (oh, ow), "down4x4s2": (2 * oh, 2 * ow), "up2x3x3": (oh // 2, ow // 2)}[kind]
+    h, w = {"1x1": (oh, ow), "3x3": (oh, ow), "down4x4s2": (2 * oh, 2 * ow), "down3x3s2": (2 * oh, 2 * ow),
+            "up2x3x3": (oh // 2, ow // 2)}[kind]
     # the GEMM grid: positions of dx for stride-1 kinds and the upsampling conv, of dy (= one parity plane of dx) for
     # the stride-2 conv
-    gh, gw = (oh, ow) if kind == "down4x4s2" else (h, w)
+    gh, gw = (oh, ow) if kind in ("down4x4s2", "down3x3s2") else (h, w)
     dev = weight.device
     outs = []
     n_off = 0

@@ -216,6 +216,17 @@ def _plan_dgrad(fwd_kind, cins, cout, reuse_rows, emit, sched, psched):
                     emit(0, 0, dq, [(dr, 1 << (r * 4 + q)) for dr, r in rows[ph]])
         return ConvPlan("down4x4s2_dgrad", cins, cout, 16, 4, len(sched) // 4, 2 if reuse_rows else 1, sched, psched,
                         out_parity=True, transposed=True)
+    if fwd_kind == "down3x3s2":
+        # x row 2a+ph receives filter row r where 2a+ph = 2ho-1+r: ph = 0 -> r = 1 (ho = a); ph = 1 -> r = 2 (ho = a) and
+        # r = 0 (ho = a+1).  Parity-0 rows / columns are padded with a zero-weight tap so that every parity plane has the
+        # same 2x2 tap structure (uniform ngroups and R, as the kernel requires).
+        rows = {0: [(0, 1), (1, None)], 1: [(0, 2), (1, 0)]}
+        for ph in range(2):
+            for pw in range(2):
+                for dq, q in rows[pw]:
+                    emit(0, 0, dq, [(dr, 0 if (r is None or q is None) else 1 << (r * 3 + q)) for dr, r in rows[ph]])
+        return ConvPlan("down3x3s2_dgrad", cins, cout, 9, 4, len(sched) // 4, 2 if reuse_rows else 1, sched, psched,
+                        out_parity=True, transposed=True)
     if fwd_kind == "up2x3x3":
         # forward window of parity p: [(dh, filter rows)]; the gradient reads dy plane p at the negated shift
         win = {0: [(-1, (0,)), (0, (1, 2))], 1: [(0, (0, 1)), (1, (2,))]}

@@ -119,19 +119,21 @@ def _dgrad_ref(fn, x, w):
 
 @pytest.mark.parametrize("reuse", [False, True])
 @pytest.mark.parametrize("kind,cin,cout,hw", [("3x3", 64, 32, (6, 5)), ("3x3", 96, 64, (4, 4)), ("1x1", 40, 72, (3, 3)),
-                                             ("down4x4s2", 32, 64, (8, 6)), ("up2x3x3", 64, 32, (3, 4))])
+                                             ("down4x4s2", 32, 64, (8, 6)), ("up2x3x3", 64, 32, (3, 4)),
+                                             ("down3x3s2", 32, 64, (8, 6)), ("down3x3s2", 72, 40, (4, 4))])
 def test_dgrad_plans(kind, cin, cout, hw, reuse):
     torch.manual_seed(5)
     x = torch.randn(2, cin, *hw)
-    k = {"3x3": 3, "1x1": 1, "down4x4s2": 4, "up2x3x3": 3}[kind]
+    k = {"3x3": 3, "1x1": 1, "down4x4s2": 4, "up2x3x3": 3, "down3x3s2": 3}[kind]
     w = torch.randn(cout, cin, k, k)
     fwd = {"3x3": lambda a, b: F.conv2d(a, b, padding=1), "1x1": lambda a, b: F.conv2d(a, b),
            "down4x4s2": lambda a, b: F.conv2d(a, b, stride=2, padding=1),
+           "down3x3s2": lambda a, b: F.conv2d(a, b, stride=2, padding=1),
            "up2x3x3": lambda a, b: F.conv2d(F.interpolate(a, scale_factor=2, mode="nearest"), b, padding=1)}[kind]
     dy, dx = _dgrad_ref(fwd, x, w)
     plan = plan_conv(kind + "_dgrad", (cout,), cin, reuse_rows=reuse)
     assert plan.transposed
-    if kind == "down4x4s2":                       # four output parity planes of dx, each the size of dy
+    if kind in ("down4x4s2", "down3x3s2"):        # four output parity planes of dx, each the size of dy
         out4 = tapgemm_emu(plan, [nhwc(dy)], w, dy.shape[2], dy.shape[3])
         got = assemble_parity(out4)
     else:
