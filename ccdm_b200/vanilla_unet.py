@@ -204,9 +204,13 @@ class VanillaUnet(nn.Module):
                 mask = torch.zeros((b,), device=x.device).float().uniform_(0, 1) < keep
             self.keep_mask = mask
         if self.training and torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
-            raise NotImplementedError("ccdm_b200.VanillaUnet: the backward of the GroupNorm UNet is not built; "
-                                      "run the forward under torch.no_grad()")
-        out = self.engine().forward(x, timesteps, classes, mask)
+            # training step: autograd graph over the CUDA kernels (ccdm_b200/vanilla_train.py); BatchNorm1d uses batch statistics
+            if not x.is_cuda:
+                raise RuntimeError("ccdm_b200.VanillaUnet runs on sm_100a only (there is no CPU fallback)")
+            from .vanilla_train import vanilla_train_forward
+            out = vanilla_train_forward(self, x, timesteps, classes, mask)
+        else:
+            out = self.engine().forward(x, timesteps, classes, mask)
         if return_null_indx:
             return out, torch.where(self.keep_mask == False)[0]      # noqa: E712  (V:375)
         return out
