@@ -46,6 +46,19 @@ def _holder_forward(self, *a, **k):
     raise RuntimeError(f"{type(self).__name__} only holds parameters; run the whole ccdm_b200.VanillaUnet instead")
 
 
+def prob_mask_like(shape, prob, device):          # V:31-37
+    if prob == 1:
+        return torch.ones(shape, device=device, dtype=torch.bool)
+    if prob == 0:
+        return torch.zeros(shape, device=device, dtype=torch.bool)
+    return torch.zeros(shape, device=device).float().uniform_(0, 1) < prob
+
+
+def _require_cuda(x):
+    if not x.is_cuda:
+        raise RuntimeError("ccdm_b200.VanillaUnet runs on sm_100a only (there is no CPU fallback)")
+
+
 class TimestepEmbedSequential(nn.Sequential):     # V:72-84
     forward = _holder_forward
 
@@ -195,18 +208,11 @@ class VanillaUnet(nn.Module):
         b = x.shape[0]
         mask = None
         if p > 0:
-            keep = 1 - p
-            if keep == 1:
-                mask = torch.ones(b, device=x.device, dtype=torch.bool)
-            elif keep == 0:
-                mask = torch.zeros(b, device=x.device, dtype=torch.bool)
-            else:
-                mask = torch.zeros((b,), device=x.device).float().uniform_(0, 1) < keep
+            mask = prob_mask_like((b,), 1 - p, x.device)
             self.keep_mask = mask
         if self.training and torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
             # training step: autograd graph over the CUDA kernels (ccdm_b200/vanilla_train.py); BatchNorm1d uses batch statistics
-            if not x.is_cuda:
-                raise RuntimeError("ccdm_b200.VanillaUnet runs on sm_100a only (there is no CPU fallback)")
+            _require_cuda(x)
             from .vanilla_train import vanilla_train_forward
             out = vanilla_train_forward(self, x, timesteps, classes, mask)
         else:

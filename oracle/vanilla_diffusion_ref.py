@@ -68,3 +68,27 @@ def v_ddpm_sample(sch: Schedule, guided: Guided, classes, shape, *, steps: Optio
         noise = torch.randn_like(img) if t > 0 else 0.0
         img = mean + (0.5 * logvar).exp() * noise
     return (img + 1) * 0.5
+
+
+def v_p_losses(sch: Schedule, net_train: Callable[[Tensor, Tensor, Tensor], Tensor], x0: Tensor, t: Tensor, *, classes: Tensor,
+               noise: Tensor, keep: Tensor, vicinal_weights: Optional[Tensor] = None) -> Tensor:
+    """V/diffusion.py:388-424 (without the auxiliary-regressor penalty).  ``net_train(x, t, classes)`` is the training-mode
+    UNet evaluated with the label-drop mask ``keep`` (bool [B]) it would have drawn; rows with keep == False get vicinal
+    weight 1 (V:398-399).  The squared error is NOT averaged per sample first: einops ``reduce(loss, 'b ... -> b (...)',
+    'mean')`` with the same axes on both sides only flattens (V:414)."""
+    from .diffusion_ref import q_sample
+    b, c, h, w = x0.shape
+    out = net_train(q_sample(sch, x0, t, noise), t, classes)
+    if sch.objective == "pred_noise":
+        target = noise
+    elif sch.objective == "pred_x0":
+        target = x0
+    else:
+        target = _at(sch.sqrt_alphas_cumprod, t, x0) * noise - _at(sch.sqrt_one_minus_alphas_cumprod, t, x0) * x0
+    loss = ((out - target) ** 2).flatten(1)
+    loss = loss * _at(sch.loss_weight, t, loss)
+    if vicinal_weights is None:
+        return loss.mean()
+    wts = vicinal_weights.clone().to(loss.dtype)
+    wts[~keep] = 1.0
+    return torch.sum(wts * loss.sum(1)) / (b * c * h * w)

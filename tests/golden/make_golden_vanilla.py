@@ -20,8 +20,8 @@ import importlib.util  # noqa: E402
 import torch  # noqa: E402
 
 from oracle.vanilla_unet_ref import make_state_dict  # noqa: E402
-from tests.golden.vanilla_cases import (V_CASES, V_CFG_CASES, V_SAMPLER_CASES, V_SIZES, V_SPECS, V_BATCH, keep_mask,  # noqa: E402
-                                        sampler_classes, vanilla_inputs)
+from tests.golden.vanilla_cases import (V_CASES, V_CFG_CASES, V_LOSS_CASES, V_LOSS_GRAD_KEYS, V_SAMPLER_CASES, V_SIZES, V_SPECS, V_BATCH, keep_mask,  # noqa: E402
+                                        loss_inputs, sampler_classes, vanilla_inputs)
 
 VREF = "/root/reference/CCDM_vanilla/RC-49/RC-49_64x64/CCGM/CCDM"
 
@@ -103,6 +103,25 @@ def main():
         samp[name] = {"img": img.clone()}
         print(name, tuple(img.shape), float(img.mean()))
     torch.save(samp, os.path.join(HERE, "vanilla_sampler.pt"))
+
+    # ---- training loss + gradients through the reference's own p_losses (label-drop mask injected, noise / t given)
+    loss = {}
+    for name, c in V_LOSS_CASES.items():
+        s = V_SPECS[c["spec"]]
+        net = build(ref, s, c["seed"]).train()
+        mask = keep_mask(c["kind"], V_BATCH[c["spec"]])
+        ref.prob_mask_like = lambda shape, prob, device, _m=mask: _m.clone()
+        gd = ref_diff.GaussianDiffusion(torch.nn.DataParallel(net), image_size=V_SIZES[c["spec"]], timesteps=1000,
+                                        objective=c["objective"]).train()
+        x0, t, classes, noise, weights = loss_inputs(c)
+        val = gd.p_losses(x0, t, classes=classes, noise=noise, vicinal_weights=None if weights is None else weights.clone())
+        val.backward()
+        g = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+        loss[name] = {"loss": val.detach().clone(),
+                      "grad_sqnorm": sum(float((v.double() ** 2).sum()) for v in g.values()),
+                      **{"grad_" + k: g[k] for k in V_LOSS_GRAD_KEYS}}
+        print(name, float(val), loss[name]["grad_sqnorm"])
+    torch.save(loss, os.path.join(HERE, "vanilla_loss.pt"))
 
 
 if __name__ == "__main__":

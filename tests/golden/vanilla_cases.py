@@ -60,3 +60,22 @@ V_SAMPLER_CASES = {
 def sampler_classes(c):
     g = torch.Generator().manual_seed(c["rng"] + 1000)
     return torch.rand(c["B"], V_SPECS[c["spec"]].embed_input_dim, generator=g)
+
+# training loss through the reference's own GaussianDiffusion.p_losses + backward; name -> settings
+V_LOSS_CASES = {
+    "v_loss_x0_vic": dict(spec="v_tiny", seed=2, objective="pred_x0", vic=True, kind="mixed", rng=51),
+    "v_loss_eps_plain": dict(spec="v_tiny", seed=2, objective="pred_noise", vic=False, kind="cond", rng=52),
+    "v_loss_v_vic_attn": dict(spec="v_attn", seed=3, objective="pred_v", vic=True, kind="mixed", rng=53),
+}
+V_LOSS_GRAD_KEYS = ("out.2.bias", "down_blocks.0.0.weight", "middle_block.0.tc_mlp.1.weight", "out.0.weight")
+
+
+def loss_inputs(c):
+    spec, size, b = V_SPECS[c["spec"]], V_SIZES[c["spec"]], V_BATCH[c["spec"]]
+    g = torch.Generator().manual_seed(c["rng"])
+    x0 = torch.rand(b, spec.in_channels, size, size, generator=g) * 2 - 1
+    t = torch.randint(0, 1000, (b,), generator=g)
+    classes = torch.rand(b, spec.embed_input_dim, generator=g)
+    noise = torch.randn(b, spec.in_channels, size, size, generator=g)
+    weights = (0.2 + torch.rand(b, generator=g)) if c["vic"] else None
+    return x0, t, classes, noise, weights

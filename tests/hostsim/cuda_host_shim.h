@@ -33,7 +33,7 @@ static const int cudaSuccess = 0;
 static thread_local dim3 threadIdx, blockIdx;
 static dim3 blockDim, gridDim;
 static std::unique_ptr<std::barrier<>> g_bar;
-static std::vector<float> g_shfl;
+static std::vector<double> g_shfl;      // one 8-byte slot per thread (float and double shuffles)
 
 #define __global__ static
 #define __device__
@@ -47,11 +47,14 @@ static inline void __syncthreads() { g_bar->arrive_and_wait(); }
 static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 // every thread of the block must take part (true for the kernels tested: uniform trip counts)
-static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  static_assert(sizeof(T) <= sizeof(double), "shuffle payload");
   const unsigned t = threadIdx.x;
-  g_shfl[t] = v;
+  memcpy(&g_shfl[t], &v, sizeof(T));
   g_bar->arrive_and_wait();
-  const float r = g_shfl[(t & ~31u) | ((t ^ (unsigned)lane_mask) & 31u)];
+  T r;
+  memcpy(&r, &g_shfl[(t & ~31u) | ((t ^ (unsigned)lane_mask) & 31u)], sizeof(T));
   g_bar->arrive_and_wait();
   return r;
 }
@@ -109,7 +112,7 @@ static inline float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u
 static inline void launch_blocks(dim3 grid, dim3 block, const std::function<void()>& body) {
   gridDim = grid;
   blockDim = block;
-  g_shfl.assign(block.x, 0.f);
+  g_shfl.assign(block.x, 0.0);
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {

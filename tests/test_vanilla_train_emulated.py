@@ -5,6 +5,7 @@
 and the parameter gradients compared with autograd of the oracle.  Checks saved tensors, coefficient layouts, the
 concatenated-source handling, the scale/shift gradient path into the tc_mlp Linears and the padded stem / head weights."""
 import ctypes as C
+import os
 
 import pytest
 import torch
@@ -30,15 +31,21 @@ def _f32(ptr, n):
     return torch.frombuffer((C.c_float * n).from_address(ptr), dtype=torch.float32)
 
 
+SAMPLER_SYMBOLS = ["ccdm_q_sample", "ccdm_vicinal_loss"]
+
+
 class HostLib:
-    """libccdm_b200.so stand-in for CPU tensors: host builds of the CUDA-core kernels + a restatement of ccdm_affine_act."""
+    """libccdm_b200.so stand-in for CPU tensors: host builds of the CUDA-core kernels (groupnorm.cu, sampler.cu) + a
+    restatement of ccdm_affine_act."""
 
     def __init__(self):
         h = C.CDLL(build("groupnorm.cu"))
-        for name in HOST_SYMBOLS:
-            fn = getattr(h, name)
-            fn.restype, fn.argtypes = L.SIGNATURES[name]
-            setattr(self, name, fn)
+        hs = C.CDLL(build("sampler.cu"))
+        for handle, names in ((h, HOST_SYMBOLS), (hs, SAMPLER_SYMBOLS)):
+            for name in names:
+                fn = getattr(handle, name)
+                fn.restype, fn.argtypes = L.SIGNATURES[name]
+                setattr(self, name, fn)
         h.hostsim_last_error.restype = C.c_char_p
         self.ccdm_last_error = h.hostsim_last_error
 
@@ -147,3 +154,47 @@ def test_training_step_gradients_match_oracle_autograd(host_path, sname, kind):
               "classes_emb.0.weight", "time_mlp.0.weight"):
         g, w = net.get_parameter(n).grad, sd_g[n].grad
         assert ((g - w).norm() / w.norm().clamp_min(1e-12)).item() < 6e-2, n
+
+
+@pytest.mark.parametrize("name", ["v_loss_x0_vic", "v_loss_eps_plain", pytest.param(
+    "v_loss_v_vic_attn", marks=pytest.mark.skipif(not os.environ.get("CCDM_SLOW_TESTS"),
+                                                  reason="256-token attention under the thread-per-CUDA-thread simulation "
+                                                         "takes ~3 min: set CCDM_SLOW_TESTS=1 (passes)"))])
+def test_p_losses_and_backward_match_the_reference(host_path, monkeypatch, name):
+    """Product code end to end -- VanillaGaussianDiffusion.p_losses (ccdm_q_sample, VanillaUnet autograd nodes,
+    ccdm_vicinal_loss from their own source) + loss.backward() -- against the loss and gradients the reference's own
+    GaussianDiffusion.p_losses produced (tests/golden/vanilla_loss.pt), label-drop mask injected as in the generator."""
+    import os
+    import ccdm_b200
+    import ccdm_b200.vanilla_unet as VU
+    from ccdm_b200.diffusion import GaussianDiffusion
+    from tests.golden.vanilla_cases import V_LOSS_CASES, V_LOSS_GRAD_KEYS, V_SIZES, loss_inputs
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vanilla_loss.pt"))[name]
+    c = V_LOSS_CASES[name]
+    spec = V_SPECS[c["spec"]]
+    net = VanillaUnet(embed_input_dim=spec.embed_input_dim, cond_drop_prob=0.5, in_channels=spec.in_channels,
+                      model_channels=spec.model_channels, num_res_blocks=spec.num_res_blocks,
+                      attention_resolutions=spec.attention_resolutions, channel_mult=spec.channel_mult,
+                      num_heads=spec.num_heads, num_groups=spec.num_groups)
+    net.load_state_dict(make_state_dict(spec, c["seed"]), strict=True)
+    net.train()
+    mask = keep_mask(c["kind"], V_BATCH[c["spec"]])
+    monkeypatch.setattr(VU, "prob_mask_like", lambda shape, prob, device: mask.clone())
+    monkeypatch.setattr(VU, "_require_cuda", lambda x: None)
+    monkeypatch.setattr(GaussianDiffusion, "_stream", staticmethod(lambda: None))
+    gd = ccdm_b200.VanillaGaussianDiffusion(torch.nn.DataParallel(net), image_size=V_SIZES[c["spec"]], timesteps=1000,
+                                            objective=c["objective"]).train()
+    x0, t, classes, noise, weights = loss_inputs(c)
+    w_in = None if weights is None else weights.clone()
+    val = gd.p_losses(x0, t, classes=classes, noise=noise, vicinal_weights=w_in)
+    val.backward()
+    assert abs(val.item() - gold["loss"].item()) < 2e-2 * abs(gold["loss"].item()), (val.item(), gold["loss"].item())
+    if w_in is not None:                                   # rows whose label was dropped were set to 1 in place (V:399)
+        assert torch.equal(w_in[~mask], torch.ones_like(w_in[~mask])) and torch.equal(w_in[mask], weights[mask])
+    sq = sum(float((p.grad.double() ** 2).sum()) for p in net.parameters() if p.grad is not None)
+    print(f"{name}: loss {val.item():.5f} (reference {gold['loss'].item():.5f}), |grad|^2 {sq:.4f} (reference {gold['grad_sqnorm']:.4f})")
+    assert abs(sq - gold["grad_sqnorm"]) < 8e-2 * gold["grad_sqnorm"]
+    for k in V_LOSS_GRAD_KEYS:
+        g, w = net.get_parameter(k).grad, gold["grad_" + k]
+        cos = (g.flatten().double() @ w.flatten().double() / (g.norm().double() * w.norm().double())).item()
+        assert cos > 0.995, (k, cos)
