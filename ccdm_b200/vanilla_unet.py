@@ -25,6 +25,7 @@ The program exposes the same ``x_in / t_in / emb_in / keep / out / run(stream)``
 STATUS: host program checked on CPU against the oracle AND the reference's own outputs through the record interpreter
 (tests/test_vanilla_emulated.py: 0.8-1.0 % relative error, the bf16 storage level); the GroupNorm / attention kernels
 compile for sm_100a but have not run on a GPU yet (tests/test_gpu_vanilla.py, opt-in until their first device run).
+Training (``loss.backward()``) runs through ccdm_b200/vanilla_train.py.
 """
 from __future__ import annotations
 

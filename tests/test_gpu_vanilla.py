@@ -216,3 +216,127 @@ def test_sampling_loops_match_reference_outputs():
         print(f"{name}: PSNR vs the oracle (same seed, same device) {psnr:.1f} dB")
         # eps objective + random-init weights: in-tolerance per-step error is amplified by sqrt(1/acp - 1)
         assert psnr >= (30.0 if c["objective"] == "pred_noise" else 40.0), (name, psnr)
+
+
+# ------------------------------------------------------------------------------------------------- training step
+
+@pytest.mark.parametrize("cs,groups,hw,with_ss,act", [((64,), 8, (16, 16), False, 2), ((64, 32), 4, (8, 8), True, 2),
+                                                      ((128, 64), 8, (32, 32), True, 2), ((512,), 8, (8, 8), False, 0),
+                                                      ((256, 512), 8, (4, 4), True, 2)])
+def test_groupnorm_node_backward_matches_autograd(cs, groups, hw, with_ss, act):
+    from ccdm_b200.vanilla_train import GroupNormActFn
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(21)
+    B, (h, w), ctot = 3, hw, sum(cs)
+    xs = [(torch.randn(B, h, w, c, generator=g) * 1.5 + 0.3).to(dev).to(torch.bfloat16).requires_grad_(True) for c in cs]
+    dys = [torch.randn(B, h, w, c, generator=g).to(dev).to(torch.bfloat16) for c in cs]
+    gamma = (1 + 0.2 * torch.randn(ctot, generator=g)).to(dev).requires_grad_(True)
+    beta = (0.1 * torch.randn(ctot, generator=g)).to(dev).requires_grad_(True)
+    ss = (0.3 * torch.randn(B, 2 * ctot, generator=g)).to(dev).requires_grad_(True) if with_ss else None
+    outs = GroupNormActFn.apply(groups, 1e-5, act, gamma, beta, ss, *xs)
+    torch.autograd.backward(outs, dys)
+    xr = torch.cat([x.detach().float() for x in xs], -1).requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    y = F.group_norm(xr.permute(0, 3, 1, 2), groups, gr, br, eps=1e-5)
+    if with_ss:
+        sr = ss.detach().clone().requires_grad_(True)
+        y = y * (1 + sr[:, :ctot, None, None]) + sr[:, ctot:, None, None]
+    y = {0: lambda v: v, 2: F.silu}[act](y)
+    y.backward(torch.cat([d.float() for d in dys], -1).permute(0, 3, 1, 2))
+    assert rel(torch.cat([o.float() for o in outs], -1), y.permute(0, 2, 3, 1)) < 6e-3
+    assert rel(torch.cat([x.grad.float() for x in xs], -1), xr.grad) < 1e-2
+    assert rel(gamma.grad, gr.grad) < 2e-3 and rel(beta.grad, br.grad) < 2e-3
+    if with_ss:
+        assert rel(ss.grad, sr.grad) < 2e-3
+
+
+@pytest.mark.parametrize("dh,n", [(16, 64), (32, 256), (64, 100), (128, 64), (128, 16)])
+def test_attention_tokens_backward_matches_autograd(dh, n):
+    from ccdm_b200.vanilla_train import AttnTokensFn
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(n + dh)
+    B, heads = 3, 4
+    hid = heads * dh
+    qkv = torch.randn(B, 1, n, 3 * hid, generator=g).to(dev).to(torch.bfloat16).requires_grad_(True)
+    dout = torch.randn(B, 1, n, hid, generator=g).to(dev).to(torch.bfloat16)
+    out = AttnTokensFn.apply(qkv, heads)
+    out.backward(dout)
+    f = qkv.detach().float().reshape(B, n, 3 * hid).requires_grad_(True)
+    v5 = f.reshape(B, n, heads, 3, dh).permute(0, 1, 3, 2, 4)
+    att = torch.einsum("bihd,bjhd->bhij", v5[:, :, 0] / math.sqrt(dh), v5[:, :, 1]).softmax(-1)
+    o = torch.einsum("bhij,bjhd->bihd", att, v5[:, :, 2]).reshape(B, n, hid)
+    o.backward(dout.float().reshape(B, n, hid))
+    assert rel(out.reshape(B, n, hid), o) < 1e-2
+    assert rel(qkv.grad.reshape(B, n, 3 * hid), f.grad) < 1.5e-2
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(64, 64, (32, 32)), (128, 128, (16, 16)), (32, 48, (8, 8))])
+def test_down3x3s2_gradients_match_autograd(cin, cout, hw):
+    from ccdm_b200.train import ConvFn
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(cin)
+    x = torch.randn(4, hw[0], hw[1], cin, generator=g).to(dev).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(dev).requires_grad_(True)
+    b = (0.1 * torch.randn(cout, generator=g)).to(dev).requires_grad_(True)
+    dy = torch.randn(4, hw[0] // 2, hw[1] // 2, cout, generator=g).to(dev).to(torch.bfloat16)
+    ConvFn.apply("down3x3s2", w, b, None, x).backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = w.detach().to(torch.bfloat16).float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    F.conv2d(xr, wr, br, stride=2, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    assert rel(x.grad.float().permute(0, 3, 1, 2), xr.grad) < 1e-2
+    assert rel(w.grad, wr.grad) < 1e-2 and rel(b.grad, br.grad) < 2e-3
+
+
+def test_training_step_gradients_match_oracle_autograd():
+    """Whole vanilla UNet: forward + backward through the CUDA nodes vs fp32 autograd of the oracle (on the GPU)."""
+    from ccdm_b200.vanilla_train import vanilla_train_forward
+    from oracle.vanilla_unet_ref import vanilla_unet_forward
+    from tests.golden.vanilla_cases import V_BATCH, keep_mask, vanilla_inputs
+    dev = torch.device("cuda")
+    for sname, kind, seed in (("v_tiny", "mixed", 7), ("v_attn", "cond", 8), ("v_rc", "mixed", 9)):
+        spec, net, sd = _build(sname, seed, dev)
+        net.train()
+        x, t, classes = (v.to(dev) for v in vanilla_inputs(sname))
+        keep = keep_mask(kind, V_BATCH[sname]).to(dev)
+        dout = torch.randn(x.shape, generator=torch.Generator().manual_seed(9)).to(dev)
+        out = vanilla_train_forward(net, x, t, classes, keep)
+        out.backward(dout)
+        sd_g = {k: (v.to(dev).clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k and
+                    k != "null_classes_emb" else v.to(dev).clone()) for k, v in sd.items()}
+        ref = vanilla_unet_forward(sd_g, spec, x, t, classes, keep, training=True)
+        ref.backward(dout)
+        names = [n for n, p in net.named_parameters() if p.requires_grad]
+        got = torch.cat([net.get_parameter(n).grad.flatten() for n in names]).double()
+        want = torch.cat([sd_g[n].grad.flatten() for n in names]).double()
+        cos = (got @ want / (got.norm() * want.norm())).item()
+        print(f"{sname}: output rel err {rel(out, ref):.3e}, gradient cosine {cos:.5f}")
+        assert rel(out, ref) < 2e-2 and cos > 0.999, (sname, cos)
+
+
+def test_p_losses_match_reference_outputs():
+    """VanillaGaussianDiffusion.p_losses + backward vs the loss / gradients of the reference's own p_losses (golden)."""
+    import ccdm_b200
+    import ccdm_b200.vanilla_unet as VU
+    from tests.golden.vanilla_cases import V_BATCH, V_LOSS_CASES, V_LOSS_GRAD_KEYS, V_SIZES, keep_mask, loss_inputs
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vanilla_loss.pt"))
+    dev = torch.device("cuda")
+    saved = VU.prob_mask_like
+    try:
+        for name, c in V_LOSS_CASES.items():
+            spec, net, _ = _build(c["spec"], c["seed"], dev)
+            net.train()
+            mask = keep_mask(c["kind"], V_BATCH[c["spec"]]).to(dev)
+            VU.prob_mask_like = lambda shape, prob, device, _m=mask: _m.clone()
+            gd = ccdm_b200.VanillaGaussianDiffusion(net, image_size=V_SIZES[c["spec"]], timesteps=1000,
+                                                    objective=c["objective"]).to(dev).train()
+            x0, t, classes, noise, weights = (v.to(dev) if v is not None else None for v in loss_inputs(c))
+            val = gd.p_losses(x0, t, classes=classes, noise=noise, vicinal_weights=weights)
+            val.backward()
+            ref = gold[name]
+            assert abs(val.item() - ref["loss"].item()) < 2e-2 * abs(ref["loss"].item()), name
+            for k in V_LOSS_GRAD_KEYS:
+                gg, ww = net.get_parameter(k).grad.cpu(), ref["grad_" + k]
+                cos = (gg.flatten().double() @ ww.flatten().double() / (gg.norm().double() * ww.norm().double())).item()
+                assert cos > 0.995, (name, k, cos)
+    finally:
+        VU.prob_mask_like = saved
