@@ -12,7 +12,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LAUNCH_RE = re.compile(r"([A-Za-z_]\w*(?:<[\d, ]+>)?)<<<(.*?),\s*(\w+),\s*\w+,\s*([^>]*?)>>>\((.*?)\);", re.S)
+LAUNCH_RE = re.compile(r"([A-Za-z_]\w*(?:<[\w, ]+>)?)<<<(.*?),\s*([^,]+?),\s*([^,]+?),\s*([^,>]*?)>>>\((.*?)\);", re.S)
 DYN_SMEM_RE = re.compile(r"extern\s+__shared__\s+float\s+(\w+)\[\];")
 
 
@@ -20,9 +20,12 @@ def host_source(cu_path: str) -> str:
     src = open(cu_path).read()
     src = src.replace('#include "common.cuh"', "").replace('#include "ptx.cuh"', "")
     src = DYN_SMEM_RE.sub(r"float* \1 = g_dyn_smem;", src)          # dynamic shared memory: one 256 KB host buffer
-    src, n = LAUNCH_RE.subn(lambda m: f"LAUNCH(({m.group(1)}), ({m.group(2)}), ({m.group(3)}), {m.group(5)});", src)
+    src, n = LAUNCH_RE.subn(lambda m: f"LAUNCH(({m.group(1)}), ({m.group(2)}), ({m.group(3)}), {m.group(6)});", src)
     assert n > 0 and "<<<" not in src, "unconverted kernel launch"
-    return '#include "cuda_host_shim.h"\n' + src
+    common = open(os.path.join(ROOT, "ccdm_b200", "csrc", "common.cuh")).read()
+    i = common.index("inline void row_lane_plan")
+    plan_fn = common[i:common.index("\n}\n", i) + 3]                     # the host helper, verbatim from common.cuh
+    return '#include "cuda_host_shim.h"\nnamespace ccdm {\n' + plan_fn + "}\n" + src
 
 
 def build(cu_name: str) -> str:
