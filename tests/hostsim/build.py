@@ -12,7 +12,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-LAUNCH_RE = re.compile(r"([A-Za-z_]\w*(?:<[\w, ]+>)?)<<<(.*?),\s*([^,]+?),\s*([^,]+?),\s*([^,>]*?)>>>\((.*?)\);", re.S)
+LAUNCH_RE = re.compile(r"([A-Za-z_]\w*(?:<[\w, ]+>)?)<<<(.*?),\s*([^,]+?),\s*([^,]+?),\s*([^,]*?)>>>\((.*?)\);", re.S)
 DYN_SMEM_RE = re.compile(r"extern\s+__shared__\s+float\s+(\w+)\[\];")
 
 
@@ -28,18 +28,53 @@ def host_source(cu_path: str) -> str:
     return '#include "cuda_host_shim.h"\nnamespace ccdm {\n' + plan_fn + "}\n" + src
 
 
-def build(cu_name: str) -> str:
-    """Returns the path of the host-compiled shared library for ccdm_b200/csrc/<cu_name> (rebuilt when the source changes)."""
+def _definition(src: str, header_re: str) -> str:
+    """Text of the function whose header matches ``header_re`` (from the start of that line to the matching brace)."""
+    m = re.search(header_re, src)
+    assert m, header_re
+    start = src.rfind("\n", 0, m.start()) + 1
+    i = src.index("{", m.end())
+    depth = 0
+    while True:
+        depth += {"{": 1, "}": -1}.get(src[i], 0)
+        i += 1
+        if depth == 0:
+            return src[start:i] + "\n"
+
+
+def extract_source(cu_path: str, kernels, entries) -> str:
+    """A .cu file that also holds tcgen05 / TMA code cannot be compiled for the host as a whole: take only the named
+    CUDA-core kernels and C entry points (verbatim) out of it."""
+    src = open(cu_path).read()
+    body = "namespace ccdm {\n" + "".join(_definition(src, r"__global__ void (?:__launch_bounds__\(\w+\) )?" + k + r"\(")
+                                          for k in kernels) + "}\nusing namespace ccdm;\n"
+    body += "".join(_definition(src, r'extern "C" int ' + e + r"\(") for e in entries)
+    body, n = LAUNCH_RE.subn(lambda m: f"LAUNCH(({m.group(1)}), ({m.group(2)}), ({m.group(3)}), {m.group(6)});", body)
+    assert n > 0 and "<<<" not in body
+    return '#include "cuda_host_shim.h"\n' + body
+
+
+def build_extract(cu_name: str, kernels, entries) -> str:
     cu_path = os.path.join(ROOT, "ccdm_b200", "csrc", cu_name)
-    text = host_source(cu_path) + open(os.path.join(HERE, "cuda_host_shim.h")).read()
-    tag = hashlib.sha1(text.encode()).hexdigest()[:12]
+    text = extract_source(cu_path, kernels, entries)
+    return _compile(text, os.path.splitext(cu_name)[0] + "_part")
+
+
+def _compile(text: str, stem: str) -> str:
+    tag = hashlib.sha1((text + open(os.path.join(HERE, "cuda_host_shim.h")).read()).encode()).hexdigest()[:12]
     out_dir = os.path.join(HERE, "build")
     os.makedirs(out_dir, exist_ok=True)
-    so = os.path.join(out_dir, f"{os.path.splitext(cu_name)[0]}_host_{tag}.so")
+    so = os.path.join(out_dir, f"{stem}_host_{tag}.so")
     if not os.path.exists(so):
         cpp = so[:-3] + ".cpp"
         with open(cpp, "w") as f:
-            f.write(host_source(cu_path))
+            f.write(text)
         subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-I", HERE,
                         "-I", os.path.join(ROOT, "include"), cpp, "-o", so], check=True)
     return so
+
+
+def build(cu_name: str) -> str:
+    """Returns the path of the host-compiled shared library for ccdm_b200/csrc/<cu_name> (rebuilt when the source changes)."""
+    cu_path = os.path.join(ROOT, "ccdm_b200", "csrc", cu_name)
+    return _compile(host_source(cu_path), os.path.splitext(cu_name)[0])

@@ -23,6 +23,7 @@ struct dim3 {
   unsigned x, y, z;
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
+struct int4 { int x, y, z, w; };
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 struct float2 { float x, y; };

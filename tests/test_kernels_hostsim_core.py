@@ -415,3 +415,78 @@ def test_multi_lerp(opt):
     assert opt.ccdm_multi_lerp(dp.data_ptr(), sp.data_ptr(), ns.data_ptr(), 2, w.data_ptr(), None) == 0
     for d, x in zip(dst, want):
         assert rel(d, x) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------- weight packing (tapgemm.cu / wgrad.cu)
+
+@pytest.fixture(scope="module")
+def packlib():
+    from tests.hostsim.build import build_extract
+    a = C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights"]))
+    b = C.CDLL(build_extract("wgrad.cu", ["unpack_wgrad_kernel", "pack_weights_t_kernel"],
+                             ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"]))
+    for h, names in ((a, ["ccdm_pack_weights"]), (b, ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"])):
+        for n in names:
+            fn = getattr(h, n)
+            fn.restype, fn.argtypes = L.SIGNATURES[n]
+    return a, b
+
+
+def _i32(rows):
+    return torch.tensor(rows, dtype=torch.int32).contiguous()
+
+
+@pytest.mark.parametrize("kind,cins,cout,reuse", [("3x3", (40, 24), 24, False), ("down3x3s2", (64,), 32, True),
+                                                  ("up2x3x3", (32,), 32, True), ("1x1", (72,), 32, False)])
+def test_pack_and_unpack_kernels_match_the_emulator(packlib, kind, cins, cout, reuse):
+    """The real pack / unpack kernels (source extracted from tapgemm.cu / wgrad.cu) against tests/emu.py's packing rule,
+    including the zero-weight padding taps of the vanilla UNet's stride-2 conv (tapmask 0)."""
+    from ccdm_b200.plan import KB, plan_conv
+    from tests.emu import pack_weights_emu
+    pk, wg = packlib
+    taps = {"3x3": 9, "1x1": 1, "down3x3s2": 9, "up2x3x3": 9, "down4x4s2": 16}[kind]
+    k = int(math.isqrt(taps))
+    g = torch.Generator().manual_seed(15)
+    w = torch.randn(cout, sum(cins), k, k, generator=g)
+    plan = plan_conv(kind, cins, cout, reuse_rows=reuse)
+    n_rows = (cout + 31) // 32 * 32
+    packed = torch.full((plan.nz * n_rows, plan.nkb * KB), 7.0).to(torch.bfloat16)
+    ps = _i32(plan.psched)
+    assert pk.ccdm_pack_weights(w.data_ptr(), cout, sum(cins), taps, ps.data_ptr(), plan.nz, plan.nkb, n_rows, None, 1.0,
+                                packed.data_ptr(), None) == 0
+    want = pack_weights_emu(plan, w, n_rows).reshape(plan.nz * n_rows, -1)
+    assert torch.equal(packed, want.to(torch.bfloat16))
+    # unpack(pack(w)) scatters every packed block back to its taps: folded taps receive the same value several times
+    dw = torch.empty_like(w)
+    assert wg.ccdm_unpack_wgrad(want.contiguous().data_ptr(), dw.data_ptr(), cout, sum(cins), taps, ps.data_ptr(), plan.nz,
+                                plan.nkb, n_rows, None, 1.0, 0, None) == 0
+    mult = torch.zeros(taps)
+    cnt = torch.zeros(taps)
+    for z in range(plan.nz):
+        for kb in range(plan.nkb):
+            c0, nv, mask, _ = plan.psched[z * plan.nkb + kb]
+            if c0 == 0 and nv > 0:
+                ts = [t for t in range(taps) if mask >> t & 1]
+                for t in ts:
+                    cnt[t] += 1
+    assert (cnt > 0).all()                                  # every filter tap is covered by some block
+    if kind != "up2x3x3":                                   # no tap folding: exact round trip
+        assert rel(dw, w) < 1e-6
+
+
+@pytest.mark.parametrize("kind,cin,cout,reuse", [("3x3", 32, 32, True), ("down3x3s2", 32, 32, True), ("down3x3s2", 40, 24, False)])
+def test_transposed_pack_kernel_matches_the_emulator(packlib, kind, cin, cout, reuse):
+    from ccdm_b200.plan import KB, plan_conv
+    from tests.emu import pack_weights_emu
+    _, wg = packlib
+    taps = 9
+    g = torch.Generator().manual_seed(16)
+    w = torch.randn(cout, cin, 3, 3, generator=g)
+    plan = plan_conv(kind + "_dgrad", (cout,), cin, reuse_rows=reuse)
+    n_rows = (cin + 31) // 32 * 32
+    packed = torch.full((plan.nz * n_rows, plan.nkb * KB), 7.0).to(torch.bfloat16)
+    ps = _i32(plan.psched)
+    assert wg.ccdm_pack_weights_t(w.data_ptr(), cout, cin, taps, ps.data_ptr(), plan.nz, plan.nkb, n_rows, 0, cin,
+                                  packed.data_ptr(), None) == 0
+    want = pack_weights_emu(plan, w, n_rows).reshape(plan.nz * n_rows, -1)
+    assert torch.equal(packed, want.to(torch.bfloat16))
