@@ -37,7 +37,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from .engine import KernelRec, TapGemmRec, UnetProgram, ViewRec, WeightStore, nhwc_view
+from .engine import TapGemmRec, UnetProgram, WeightStore, nhwc_view
 from .plan import KB, can_reuse_rows, n_tiling, plan_conv, tile_box
 
 ACT_AFFINE_NONE, ACT_AFFINE_SILU = 0, 2          # ccdm_affine_act codes
