@@ -2,7 +2,7 @@
 vicinal loss -> backward through ccdm_b200/train.py -> Adam.  CUDA events, W warm-up steps, K timed steps, max over
 ranks; under torchrun it also averages gradients over the ranks (ccdm_b200.dist.all_reduce_gradients).
 
-  python tools/bench_train.py [--model uk64|rc64] [--batch 128] [--steps 5] [--warmup 3] [--breakdown]
+  python tools/bench_train.py [--model uk64|rc64|vrc64] [--batch 128] [--steps 5] [--warmup 3] [--breakdown]
 
 Prints one JSON line: ms/step, images/s, algorithmic TFLOP/s (3 x forward FLOPs per image, the usual fwd+dgrad+wgrad
 accounting) against MEASURED_PEAKS.json, and with --breakdown the forward / backward / optimizer split.
@@ -24,6 +24,8 @@ MODELS = {
     # forward GFLOP per image from SURVEY.md section 8d (conv + linear + bmm, 2*MAC)
     "uk64": dict(dim=72, dim_mults=(1, 2, 4, 4, 8), size=64, gflop=16.25),
     "rc64": dict(dim=64, dim_mults=(1, 2, 2, 4, 8), size=64, gflop=11.00),
+    # vanilla (GroupNorm) tree, RC-49 64x64 script configuration (V/scripts/run_train_ccdm.sh: batch 128, pred_x0); eager only
+    "vrc64": dict(vanilla=True, size=64, gflop=21.8),
 }
 
 
@@ -49,12 +51,19 @@ def main():
     D.init("nccl")
     m = MODELS[a.model]
     torch.manual_seed(111)
-    net = ccdm_b200.Unet(dim=m["dim"], embed_input_dim=128, cond_drop_prob=0.1, dim_mults=m["dim_mults"], in_channels=3,
-                         attn_dim_head=32, attn_heads=4)
     n_el = 3 * m["size"] ** 2
-    fn_y2cov = lambda y: (sinusoid(y, n_el) + 1) / 2                      # sinusoidal covariance embedding, cov_dim = C*H*W
-    gd = ccdm_b200.GaussianDiffusion(net, image_size=m["size"], objective="pred_x0", use_Hy=True, fn_y2cov=fn_y2cov,
-                                     cond_drop_prob=0.1, timesteps=1000, vicinity_type="hv").cuda().train()
+    if m.get("vanilla"):
+        if a.graph:
+            raise SystemExit("--graph is not wired for the vanilla model (its UNet draws the label-drop mask itself)")
+        net = ccdm_b200.VanillaUnet(embed_input_dim=128, cond_drop_prob=0.1, model_channels=64, num_res_blocks=2,
+                                    attention_resolutions=(16, 32), channel_mult=(1, 2, 4, 8), num_heads=4, num_groups=8)
+        gd = ccdm_b200.VanillaGaussianDiffusion(net, image_size=m["size"], objective="pred_x0", timesteps=1000).cuda().train()
+    else:
+        net = ccdm_b200.Unet(dim=m["dim"], embed_input_dim=128, cond_drop_prob=0.1, dim_mults=m["dim_mults"], in_channels=3,
+                             attn_dim_head=32, attn_heads=4)
+        fn_y2cov = lambda y: (sinusoid(y, n_el) + 1) / 2                  # sinusoidal covariance embedding, cov_dim = C*H*W
+        gd = ccdm_b200.GaussianDiffusion(net, image_size=m["size"], objective="pred_x0", use_Hy=True, fn_y2cov=fn_y2cov,
+                                         cond_drop_prob=0.1, timesteps=1000, vicinity_type="hv").cuda().train()
     D.broadcast_parameters(gd)
     if a.torch_adam:
         opt = torch.optim.Adam(gd.parameters(), lr=1e-4, betas=(0.9, 0.99))
@@ -72,7 +81,10 @@ def main():
     def step(ev=None):
         if ev:
             ev[0].record()
-        loss = gd(img, labels_emb=emb, labels=labels, vicinal_weights=ones, vicinity_type="hv", kappa=0.05)
+        if m.get("vanilla"):
+            loss = gd(img, classes=emb, vicinal_weights=ones.clone())      # the trainer's per-sample weights (V/trainer.py)
+        else:
+            loss = gd(img, labels_emb=emb, labels=labels, vicinal_weights=ones, vicinity_type="hv", kappa=0.05)
         if ev:
             ev[1].record()
         opt.zero_grad(set_to_none=True)

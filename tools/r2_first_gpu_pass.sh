@@ -9,10 +9,12 @@ CCDM_RUN_UNVERIFIED=1 timeout 900 python -m pytest tests/test_gpu_vanilla.py -x 
 echo "vanilla tests exit $?" | tee -a gpurun_out/vanilla_tests.log
 timeout 600 python tools/bench_sample.py --model vrc64 --batch 200 --steps 1 --warmup 1 > gpurun_out/vanilla_bench.log 2>&1
 echo "vanilla bench exit $?" | tee -a gpurun_out/vanilla_bench.log
+timeout 600 python tools/bench_train.py --model vrc64 --batch 128 --steps 3 --warmup 2 --breakdown > gpurun_out/vanilla_train_bench.log 2>&1
+echo "vanilla train bench exit $?" | tee -a gpurun_out/vanilla_train_bench.log
 timeout 300 python tools/prof_groupnorm.py > gpurun_out/prof_groupnorm.log 2>&1
 echo "prof_groupnorm exit $?" | tee -a gpurun_out/prof_groupnorm.log
 timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests.log 2>&1
 echo "gpu tests exit $?" | tee -a gpurun_out/gpu_tests.log
 timeout 600 python bench.py > gpurun_out/bench_r2_first.json 2> gpurun_out/bench_r2_first.err
-tail -3 gpurun_out/vanilla_tests.log gpurun_out/vanilla_bench.log gpurun_out/prof_groupnorm.log gpurun_out/gpu_tests.log
+tail -3 gpurun_out/vanilla_tests.log gpurun_out/vanilla_bench.log gpurun_out/vanilla_train_bench.log gpurun_out/prof_groupnorm.log gpurun_out/gpu_tests.log
 cat gpurun_out/bench_r2_first.json
