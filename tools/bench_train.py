@@ -66,16 +66,17 @@ def main():
                                          cond_drop_prob=0.1, timesteps=1000, vicinity_type="hv").cuda().train()
     D.broadcast_parameters(gd)
     if a.torch_adam:
-        opt = torch.optim.Adam(gd.parameters(), lr=1e-4, betas=(0.9, 0.99))
+        opt = torch.optim.Adam([p for p in gd.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99))
     else:
-        opt = ccdm_b200.optim.FusedAdam(gd.parameters(), lr=1e-4, betas=(0.9, 0.99), max_grad_norm=1.0)
+        opt = ccdm_b200.optim.FusedAdam([p for p in gd.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99),
+                                        max_grad_norm=1.0)
     g = torch.Generator().manual_seed(rank)
     B = a.batch
     img = torch.rand(B, 3, m["size"], m["size"], generator=g).cuda()
     labels = torch.rand(B, generator=g).cuda()
     emb = sinusoid(labels, 128)
     ones = torch.ones(B, device="cuda")
-    params = list(gd.parameters())
+    params = [p for p in gd.parameters() if p.requires_grad]
     lib = ccdm_b200._lib.lib()
 
     def step(ev=None):
