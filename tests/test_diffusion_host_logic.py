@@ -116,3 +116,126 @@ def test_p_losses_host_logic_matches_oracle(host_sampler, name):
     assert abs(val.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item())), (val.item(), ref.item())
     for k, p in net.named_parameters():
         assert ((got[k] - p.grad).norm() / p.grad.norm().clamp_min(1e-12)).item() < 1e-4, k
+
+
+# ------------------------------------------------------------------------------------------------- sampling loops
+
+class _StubProgram:
+    """The surface _loop / _SamplerState use of an engine program: x_in / t_in / emb_in / keep / out / run(stream)."""
+
+    def __init__(self, net, B, x_batch, H, W):
+        c = net.in_channels
+        self.net, self.B, self.x_batch = net, B, x_batch
+        self.x_in = torch.zeros(x_batch, c, H, W)
+        self.t_in = torch.zeros(B, dtype=torch.int64)
+        self.emb_in = torch.zeros(B, net.emb.in_features)
+        self.keep = torch.zeros(B, dtype=torch.uint8)
+        self.out = torch.zeros(B, c, H, W)
+
+    def run(self, stream):
+        x = self.x_in.repeat(self.B // self.x_batch, 1, 1, 1)
+        with torch.no_grad():
+            self.out.copy_(self.net(x, self.t_in, self.emb_in, keep_mask=self.keep.bool()))
+
+
+class _StubEngine:
+    def __init__(self, net):
+        self.net, self.progs = net, {}
+        self.weights = type("W", (), {"refresh": staticmethod(lambda stream: None)})()
+
+    def program(self, B, x_batch, H, W, training):
+        return self.progs.setdefault((B, x_batch, H, W), _StubProgram(self.net, B, x_batch, H, W))
+
+
+@pytest.fixture()
+def host_loop(monkeypatch, host_sampler):
+    import ccdm_b200.diffusion as DM
+    lib = L.lib()
+    h = C.CDLL(build("sampler.cu"))
+    for name in ("ccdm_sampler_step", "ccdm_broadcast_step_i64"):
+        fn = getattr(h, name)
+        fn.restype, fn.argtypes = L.SIGNATURES[name]
+        setattr(lib, name, fn)
+    # no CUDA graph on the CPU: every step launches the same three calls eagerly
+    monkeypatch.setattr(DM._SamplerState, "step", lambda self: self._launch(None))
+
+
+@pytest.mark.parametrize("kind,objective,eta,use_Hy,scale", [("ddim", "pred_x0", 0.0, False, 1.5), ("ddim", "pred_noise", 0.5, False, 1.5),
+                                                             ("ddim", "pred_x0", 0.0, True, 1.5), ("ddim", "pred_v", 0.0, False, 2.0),
+                                                             ("ddpm", "pred_noise", 0.0, False, 2.0), ("ddpm", "pred_x0", 0.0, True, 1.5),
+                                                             ("ddim", "pred_x0", 0.3, False, 1.0)])
+def test_sampling_loop_host_logic_matches_oracle(host_loop, kind, objective, eta, use_Hy, scale):
+    """_loop + _SamplerState (coefficient tables, device step counter, noise draws, Hy initial scaling, guided 2B batch) with
+    ccdm_broadcast_step_i64 / ccdm_sampler_step run from source, against oracle.ddim_sample / ddpm_sample with the same
+    stand-in network and torch seed."""
+    B, ch, size, emb_dim, S = 3, 3, 8, 16, 5
+    le = ccdm_b200.LabelEmbed(y2h_type="sinusoidal", y2cov_type="sinusoidal", h_dim=emb_dim, cov_dim=ch * size * size,
+                              device=torch.device("cpu"))
+    labels = torch.linspace(0.1, 0.9, B)
+    emb = le.fn_y2h(labels)
+    torch.manual_seed(6)
+    net = StubDenoiser(ch, emb_dim).eval()
+    net.engine = lambda _e=_StubEngine(net): _e
+    gd = GaussianDiffusion(net, image_size=size, use_Hy=use_Hy, fn_y2cov=le.fn_y2cov if use_Hy else None, timesteps=1000,
+                           sampling_timesteps=S, objective=objective, ddim_sampling_eta=eta).eval()
+    shape = (B, ch, size, size)
+    torch.manual_seed(321)
+    if kind == "ddim":
+        img = gd.ddim_sample(labels_emb=emb, labels=labels, shape=shape, cond_scale=scale)
+    else:
+        img = gd.sample(labels_emb=emb, labels=labels, cond_scale=scale)
+    sch = oracle.make_schedule(1000, "cosine", objective)
+
+    def onet(x, t, e, p):
+        keep = torch.ones(x.shape[0], dtype=torch.bool) if p == 0.0 else torch.zeros(x.shape[0], dtype=torch.bool)
+        with torch.no_grad():
+            return net(x, t, e, keep_mask=keep)
+
+    cov = torch.exp(-le.fn_y2cov(labels).view(shape)) if use_Hy else None
+    torch.manual_seed(321)
+    if kind == "ddim":
+        ref = oracle.ddim_sample(sch, onet, emb, shape, sampling_timesteps=S, cond_scale=scale, eta=eta, init_cov=cov)
+    else:
+        ref = oracle.ddpm_sample(sch, onet, emb, shape, sampling_timesteps=S, cond_scale=scale, init_cov=cov)
+    assert (img - ref).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("kind,objective,eta,phi", [("ddim", "pred_x0", 0.0, 0.2), ("ddim", "pred_noise", 1.0, 0.7), ("ddpm", "pred_x0", 1.0, 0.4)])
+def test_vanilla_sampling_wrapper_matches_oracle(host_loop, kind, objective, eta, phi):
+    """VanillaGaussianDiffusion's call-site details on CPU: plain CFG (cfg_remove_parallel = False), ddim_sample ignoring its
+    rescaled_phi (always 0.7), DDPM over preset_sampling_timesteps -- against oracle.vanilla_diffusion_ref."""
+    from oracle.vanilla_diffusion_ref import v_ddim_sample, v_ddpm_sample
+    B, ch, size, emb_dim, S, scale = 3, 3, 8, 16, 4, 1.5
+    g = torch.Generator().manual_seed(8)
+    classes = torch.rand(B, emb_dim, generator=g)
+    torch.manual_seed(6)
+    net = StubDenoiser(ch, emb_dim).eval()
+    net.cfg_remove_parallel = False
+    net.engine = lambda _e=_StubEngine(net): _e
+    gd = ccdm_b200.VanillaGaussianDiffusion(net, image_size=size, timesteps=1000, sampling_timesteps=S, objective=objective,
+                                            ddim_sampling_eta=eta).eval()
+    shape = (B, ch, size, size)
+    torch.manual_seed(11)
+    if kind == "ddim":
+        img = gd.ddim_sample(classes, shape, cond_scale=scale, rescaled_phi=phi)
+    else:
+        img = gd.sample(classes, cond_scale=scale, rescaled_phi=phi, preset_sampling_timesteps=S)
+
+    def guided(x, t, cl, cs, ph):                          # V/diffusion.py:34-56 over the stand-in network
+        with torch.no_grad():
+            cond = net(x, t, cl, keep_mask=torch.ones(B, dtype=torch.bool))
+            null = net(x, t, cl, keep_mask=torch.zeros(B, dtype=torch.bool))
+        s = null + (cond - null) * cs
+        if ph == 0:
+            return s
+        dims = (1, 2, 3)
+        return s * (cond.std(dim=dims, keepdim=True) / s.std(dim=dims, keepdim=True)) * ph + s * (1 - ph)
+
+    sch = oracle.make_schedule(1000, "cosine", objective)
+    torch.manual_seed(11)
+    if kind == "ddim":
+        ref = v_ddim_sample(sch, guided, classes, shape, sampling_timesteps=S, cond_scale=scale, eta=eta)
+    else:
+        ref = v_ddpm_sample(sch, guided, classes, shape, steps=S, cond_scale=scale, rescaled_phi=phi)
+    assert (img - ref).abs().max().item() < 2e-4
+    assert gd.sampling_timesteps == S and gd.ddim_sampling_eta == eta        # the preset overrides were restored
