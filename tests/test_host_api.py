@@ -57,3 +57,46 @@ def test_unet_deepcopy_and_dataparallel_wrapper():
     assert twin.unet is not gd.unet and twin.unet._engine is None
     assert set(twin.state_dict()) == set(gd.state_dict())
     assert any(k.startswith("model.module.") for k in gd.state_dict())      # reference checkpoint key layout
+
+
+def _cpu_trainer(labels, vicinity_type, kappa, tmp_path, **kw):
+    import numpy as np
+    net = ccdm_b200.Unet(dim=32, dim_mults=(1, 2))
+    gd = ccdm_b200.GaussianDiffusion(net, image_size=8, timesteps=100)
+    n = len(labels)
+    images = (np.random.RandomState(0).rand(n, 3, 8, 8) * 255).astype("float32")
+    return ccdm_b200.Trainer("RC-49", gd, train_images=images, train_labels=np.asarray(labels, dtype="float32"),
+                             vicinal_params=dict(kernel_sigma=0.05, kappa=kappa, nonzero_soft_weight_threshold=1e-3),
+                             train_batch_size=16, results_folder=str(tmp_path), vicinity_type=vicinity_type, **kw)
+
+
+def test_trainer_batch_construction_hard_vicinity(tmp_path):
+    """Trainer.sample_real_indices (vectorised restatement of trainer.py:317-459): every pick lies in the hard vicinity
+    of its target label, all vicinity members are reachable, and an empty vicinity falls back to the nearest label."""
+    torch.manual_seed(0)
+    labels = torch.linspace(0, 1, 101)
+    tr = _cpu_trainer(labels.numpy(), "hv", 0.021, tmp_path)
+    targets = torch.tensor([0.5, 0.1, 0.9, 0.333]).repeat(200)
+    idx = tr.sample_real_indices(targets)
+    assert ((labels[idx] - targets).abs() <= 0.021 + 1e-6).all()
+    picked_for_half = set(idx[0::4].tolist())
+    assert picked_for_half == {48, 49, 50, 51, 52}                  # uniform over the whole vicinity of 0.5
+    # empty vicinity -> nearest neighbour (trainer.py:405-417)
+    sparse = _cpu_trainer([0.0, 0.4, 1.0], "hv", 0.01, tmp_path)
+    assert sparse.sample_real_indices(torch.tensor([0.3, 0.75, 0.05])).tolist() == [1, 2, 0]
+
+
+def test_trainer_batch_construction_sliced_vicinity(tmp_path, monkeypatch):
+    """Sliced hard vicinity with vector labels: the pick's projection on (one of) the random directions is within
+    kappa * |v| of the target's (trainer.py:344-400)."""
+    import ccdm_b200.trainer as T
+    torch.manual_seed(1)
+    labels = torch.rand(300, 3)
+    v = torch.tensor([[0.6, -0.2, 1.1], [0.1, 0.9, -0.4]])
+    monkeypatch.setattr(T, "generate_random_vectors", lambda kind, dim, n, device: v.to(device))
+    tr = _cpu_trainer(labels.numpy(), "shv", 0.05, tmp_path, label_dim=3, num_projections=2)
+    targets = torch.rand(64, 3)
+    idx = tr.sample_real_indices(targets)
+    vn = torch.nn.functional.normalize(v, dim=1)
+    d = ((targets @ vn.t()) - (labels[idx] @ vn.t())).abs()         # [B, P]
+    assert (d <= 0.05 * v.norm(dim=1)[None] + 1e-6).any(1).all()
