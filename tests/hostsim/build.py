@@ -16,11 +16,26 @@ LAUNCH_RE = re.compile(r"([A-Za-z_]\w*(?:<[\w, ]+>)?)<<<(.*?),\s*([^,]+?),\s*([^
 DYN_SMEM_RE = re.compile(r"extern\s+__shared__\s+float\s+(\w+)\[\];")
 
 
+SYNC_RE = re.compile(r"__syncthreads|__shfl|__syncwarp|block_sum|warp_sum|seg_sum")
+
+
+def _launch_sub(src: str):
+    """Rewrites the launches of ``src``.  A kernel whose body uses no barrier / shuffle (directly or through the project's
+    reduction helpers) does not need concurrent threads: its CUDA threads run one after the other in the calling thread
+    (LAUNCH_SEQ), which is orders of magnitude faster than one OS thread each."""
+    def repl(m):
+        base = m.group(1).split("<")[0]
+        body = _definition(src, r"__global__ void (?:__launch_bounds__\([\w, ]+\) )?" + base + r"\(")
+        macro = "LAUNCH" if SYNC_RE.search(body) else "LAUNCH_SEQ"
+        return f"{macro}(({m.group(1)}), ({m.group(2)}), ({m.group(3)}), {m.group(6)});"
+    return LAUNCH_RE.subn(repl, src)
+
+
 def host_source(cu_path: str) -> str:
     src = open(cu_path).read()
     src = src.replace('#include "common.cuh"', "").replace('#include "ptx.cuh"', "")
     src = DYN_SMEM_RE.sub(r"float* \1 = g_dyn_smem;", src)          # dynamic shared memory: one 256 KB host buffer
-    src, n = LAUNCH_RE.subn(lambda m: f"LAUNCH(({m.group(1)}), ({m.group(2)}), ({m.group(3)}), {m.group(6)});", src)
+    src, n = _launch_sub(src)
     assert n > 0 and "<<<" not in src, "unconverted kernel launch"
     common = open(os.path.join(ROOT, "ccdm_b200", "csrc", "common.cuh")).read()
     i = common.index("inline void row_lane_plan")
@@ -49,7 +64,7 @@ def extract_source(cu_path: str, kernels, entries) -> str:
     body = "namespace ccdm {\n" + "".join(_definition(src, r"__global__ void (?:__launch_bounds__\(\w+\) )?" + k + r"\(")
                                           for k in kernels) + "}\nusing namespace ccdm;\n"
     body += "".join(_definition(src, r'extern "C" int ' + e + r"\(") for e in entries)
-    body, n = LAUNCH_RE.subn(lambda m: f"LAUNCH(({m.group(1)}), ({m.group(2)}), ({m.group(3)}), {m.group(6)});", body)
+    body, n = _launch_sub(body)
     assert n > 0 and "<<<" not in body
     return '#include "cuda_host_shim.h"\n' + body
 

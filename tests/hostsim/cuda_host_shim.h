@@ -192,6 +192,20 @@ static inline void launch_blocks(dim3 grid, dim3 block, const std::function<void
         for (auto& th : ts) th.join();
       }
 }
+// kernels without barriers / shuffles: the CUDA threads of every block run one after the other in the calling thread
+static inline void launch_blocks_seq(dim3 grid, dim3 block, const std::function<void()>& body) {
+  gridDim = grid;
+  blockDim = block;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx)
+        for (unsigned t = 0; t < block.x; ++t) {
+          threadIdx = dim3(t, 0, 0);
+          blockIdx = dim3(bx, by, bz);
+          body();
+        }
+}
+#define LAUNCH_SEQ(kernel, grid, block, ...) launch_blocks_seq(dim3 grid, dim3 block, [&] { kernel(__VA_ARGS__); })
 #define LAUNCH(kernel, grid, block, ...) launch_blocks(dim3 grid, dim3 block, [&] { kernel(__VA_ARGS__); })
 
 extern "C" const char* hostsim_last_error() { return ccdm::g_err; }
