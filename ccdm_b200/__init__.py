@@ -16,6 +16,7 @@ from .trainer import Trainer  # noqa: F401
 from .sngan import sngan_generator  # noqa: F401
 from .vanilla_unet import VanillaUnet  # noqa: F401
 from .vanilla_diffusion import VanillaGaussianDiffusion  # noqa: F401
+from .vanilla_trainer import VanillaTrainer  # noqa: F401
 
 __all__ = ["Unet", "GaussianDiffusion", "ModelPrediction", "LabelEmbed", "EMA", "Trainer", "sngan_generator", "VanillaUnet",
-           "VanillaGaussianDiffusion"]
+           "VanillaGaussianDiffusion", "VanillaTrainer"]
