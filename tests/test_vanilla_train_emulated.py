@@ -242,23 +242,23 @@ def test_vanilla_trainer_batch_construction(tmp_path):
     assert targets is None and w is None and idx.shape == (32,)
 
 
-def test_vanilla_trainer_two_steps_end_to_end(host_path, monkeypatch, tmp_path):
-    """VanillaTrainer.train for two optimizer steps on CPU (kernels from source, convs restated): the loss is finite, the
+def test_vanilla_trainer_step_end_to_end(host_path, monkeypatch, tmp_path):
+    """VanillaTrainer.train for one optimizer step on CPU (kernels from source, convs restated): the loss is finite, the
     parameters move, the EMA and the checkpoint round trip work."""
     import ccdm_b200.vanilla_unet as VU
     from ccdm_b200.diffusion import GaussianDiffusion
     monkeypatch.setattr(VU, "_require_cuda", lambda x: None)
     monkeypatch.setattr(GaussianDiffusion, "_stream", staticmethod(lambda: None))
     torch.manual_seed(3)
-    tr, net = _trainer(tmp_path, torch.linspace(0, 1, 40).numpy(), "soft", 500.0, batch=16, steps=2)
+    tr, net = _trainer(tmp_path, torch.linspace(0, 1, 40).numpy(), "soft", 500.0, batch=16, steps=1)
     w0 = net.out[2].weight.detach().clone()
     fn_y2h = lambda y: torch.stack([torch.sin((k + 1) * y) for k in range(16)], 1)        # noqa: E731  (any callable works)
     tr.train(fn_y2h)
-    assert tr.step == 2 and not torch.equal(net.out[2].weight, w0)
+    assert tr.step == 1 and not torch.equal(net.out[2].weight, w0)
     assert all(torch.isfinite(p).all() for p in net.parameters())
-    assert (tmp_path / "model-2.pt").exists()
-    log = (tmp_path / "log_loss_niters2.txt").read_text()
+    assert (tmp_path / "model-1.pt").exists()
+    log = (tmp_path / "log_loss_niters1.txt").read_text()
     assert "Step: 0, Loss:" in log and "nan" not in log.lower()
-    tr2, net2 = _trainer(tmp_path, torch.linspace(0, 1, 40).numpy(), "soft", 500.0, batch=16, steps=2)
-    tr2.load(2)
-    assert tr2.step == 2 and torch.equal(net2.out[2].weight, net.out[2].weight)
+    tr2, net2 = _trainer(tmp_path, torch.linspace(0, 1, 40).numpy(), "soft", 500.0, batch=16, steps=1)
+    tr2.load(1)
+    assert tr2.step == 1 and torch.equal(net2.out[2].weight, net.out[2].weight)
