@@ -22,7 +22,7 @@ SYNC_RE = re.compile(r"__syncthreads|__shfl|__syncwarp|block_sum|warp_sum|seg_su
 def _launch_sub(src: str):
     """Rewrites the launches of ``src``.  A kernel whose body uses no barrier / shuffle (directly or through the project's
     reduction helpers) does not need concurrent threads: its CUDA threads run one after the other in the calling thread
-    (LAUNCH_SEQ), which is orders of magnitude faster than one OS thread each."""
+    (LAUNCH_SEQ), which is much faster than a fiber each."""
     def repl(m):
         base = m.group(1).split("<")[0]
         body = _definition(src, r"__global__ void (?:__launch_bounds__\([\w, ]+\) )?" + base + r"\(")
@@ -84,7 +84,7 @@ def _compile(text: str, stem: str) -> str:
         cpp = so[:-3] + ".cpp"
         with open(cpp, "w") as f:
             f.write(text)
-        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-I", HERE,
+        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-I", HERE,
                         "-I", os.path.join(ROOT, "include"), cpp, "-o", so], check=True)
     return so
 

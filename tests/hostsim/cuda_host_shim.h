@@ -1,11 +1,12 @@
 // TEST INFRASTRUCTURE: a minimal CUDA-on-host shim so that the CUDA-core kernels of a .cu file can be compiled by g++ and
 // executed on the CPU exactly as written (index math, shared-memory staging, barriers, shuffles, atomics), one thread
-// block at a time with one OS thread per CUDA thread.  Used by tests/test_kernels_hostsim.py to check kernels in a
-// container without a GPU; it is NOT a fallback and nothing under ccdm_b200/ uses it.
+// block at a time.  Every CUDA thread of the block is a cooperative fiber (ucontext) that runs until its next barrier or
+// shuffle, so execution is deterministic and needs no OS threads; kernels without barriers run their threads in a plain
+// loop.  Used by tests/test_kernels_hostsim*.py and tests/hostpath.py to check kernels in a container without a GPU; it is
+// NOT a fallback and nothing under ccdm_b200/ uses it.
 #pragma once
 #include <algorithm>
 #include <atomic>
-#include <barrier>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -14,7 +15,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
-#include <thread>
+#include <ucontext.h>
 #include <vector>
 
 #include "ccdm_b200.h"
@@ -39,10 +40,25 @@ typedef void* cudaStream_t;
 typedef int cudaError_t;
 static const int cudaSuccess = 0;
 
-static thread_local dim3 threadIdx, blockIdx;
-static dim3 blockDim, gridDim;
-static std::unique_ptr<std::barrier<>> g_bar;
+static dim3 threadIdx, blockIdx, blockDim, gridDim;
 static std::vector<double> g_shfl;      // one 8-byte slot per thread (float and double shuffles)
+
+// ---- cooperative fibers: one per CUDA thread of the running block
+enum { WAIT_NONE = 0, WAIT_BLOCK = 1, WAIT_WARP = 2 };
+struct Fiber {
+  ucontext_t ctx;
+  std::vector<char> stack;
+  bool done = false;
+  int wait = WAIT_NONE;
+};
+static std::vector<Fiber> g_fib;
+static ucontext_t g_sched;
+static unsigned g_cur = 0;
+static const std::function<void()>* g_body = nullptr;
+static inline void fiber_wait(int scope) {       // park the current fiber at a barrier of the given scope
+  g_fib[g_cur].wait = scope;
+  swapcontext(&g_fib[g_cur].ctx, &g_sched);
+}
 
 #define __global__ static
 #define __device__
@@ -52,24 +68,23 @@ static std::vector<double> g_shfl;      // one 8-byte slot per thread (float and
 #define __launch_bounds__(...)
 #define __shared__ static              // blocks run one at a time, so one static copy per kernel == per-block storage
 
-static inline void __syncthreads() { g_bar->arrive_and_wait(); }
-static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
-static inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v, std::memory_order_relaxed); }
-static inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_relaxed); }
+static inline void __syncthreads() { fiber_wait(WAIT_BLOCK); }
+static inline float atomicAdd(float* p, float v) { const float o = *p; *p = o + v; return o; }
+static inline double atomicAdd(double* p, double v) { const double o = *p; *p = o + v; return o; }
+static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 // warp-scoped: the 32 (or fewer, in a trailing partial warp) threads of a warp must all take part, as on the device
-static std::vector<std::unique_ptr<std::barrier<>>> g_warp_bar;
 template <typename T>
 static inline T shfl_from(T v, unsigned src_lane) {
   static_assert(sizeof(T) <= sizeof(double), "shuffle payload");
-  const unsigned t = threadIdx.x, w = t >> 5;
+  const unsigned t = threadIdx.x;
   memcpy(&g_shfl[t], &v, sizeof(T));
-  g_warp_bar[w]->arrive_and_wait();
+  fiber_wait(WAIT_WARP);
   unsigned src = (t & ~31u) | (src_lane & 31u);
   if (src >= blockDim.x) src = t;
   T r;
   memcpy(&r, &g_shfl[src], sizeof(T));
-  g_warp_bar[w]->arrive_and_wait();
+  fiber_wait(WAIT_WARP);
   return r;
 }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return shfl_from(v, (threadIdx.x ^ (unsigned)lane_mask) & 31u); }
@@ -78,7 +93,7 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d
   return shfl_from(v, lane + delta > 31u ? lane : lane + delta);
 }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src_lane) { return shfl_from(v, (unsigned)src_lane); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { g_warp_bar[threadIdx.x >> 5]->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { fiber_wait(WAIT_WARP); }
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline float __fdividef(float a, float b) { return a / b; }
 #define __expf(x) expf(x)
@@ -110,18 +125,8 @@ template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int
 template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 4; return 0; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
-static inline int atomicMax(int* p, int v) {
-  std::atomic_ref<int> a(*p);
-  int old = a.load();
-  while (old < v && !a.compare_exchange_weak(old, v)) {}
-  return old;
-}
-static inline unsigned atomicMin(unsigned* p, unsigned v) {
-  std::atomic_ref<unsigned> a(*p);
-  unsigned old = a.load();
-  while (old > v && !a.compare_exchange_weak(old, v)) {}
-  return old;
-}
+static inline int atomicMax(int* p, int v) { const int o = *p; if (o < v) *p = v; return o; }
+static inline unsigned atomicMin(unsigned* p, unsigned v) { const unsigned o = *p; if (o > v) *p = v; return o; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 
 // ---- what the kernels use from common.cuh / ptx.cuh
@@ -167,29 +172,76 @@ static inline void griddep_launch_dependents() {}
     }                                  \
   } while (0)
 
+static void fiber_entry() {
+  (*g_body)();
+  g_fib[g_cur].done = true;
+  swapcontext(&g_fib[g_cur].ctx, &g_sched);
+}
+// Round-robin scheduler: every runnable fiber runs until its next barrier / shuffle (or to the end); a barrier opens when all
+// live fibers of its scope (block, or one warp) are parked at it.  A block that can neither run nor open a barrier is a
+// deadlock in the kernel (divergent barrier) and aborts.
 static inline void launch_blocks(dim3 grid, dim3 block, const std::function<void()>& body) {
+  constexpr size_t kStack = 256 * 1024;
   gridDim = grid;
   blockDim = block;
+  g_body = &body;
   g_shfl.assign(block.x, 0.0);
-  const unsigned n_warps = (block.x + 31) / 32;
+  if (g_fib.size() < block.x) g_fib.resize(block.x);
+  const unsigned n = block.x, n_warps = (n + 31) / 32;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
-        g_bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)block.x);
-        g_warp_bar.clear();
-        for (unsigned w = 0; w < n_warps; ++w)
-          g_warp_bar.push_back(std::make_unique<std::barrier<>>((std::ptrdiff_t)std::min(32u, block.x - 32 * w)));
-        std::vector<std::thread> ts;
-        ts.reserve(block.x);
-        for (unsigned t = 0; t < block.x; ++t)
-          ts.emplace_back([&, t] {
+        blockIdx = dim3(bx, by, bz);
+        for (unsigned t = 0; t < n; ++t) {
+          Fiber& f = g_fib[t];
+          if (f.stack.size() != kStack) f.stack.resize(kStack);
+          f.done = false;
+          f.wait = WAIT_NONE;
+          getcontext(&f.ctx);
+          f.ctx.uc_stack.ss_sp = f.stack.data();
+          f.ctx.uc_stack.ss_size = kStack;
+          f.ctx.uc_link = &g_sched;
+          makecontext(&f.ctx, fiber_entry, 0);
+        }
+        unsigned live = n;
+        while (live) {
+          bool progressed = false;
+          for (unsigned t = 0; t < n; ++t) {
+            Fiber& f = g_fib[t];
+            if (f.done || f.wait != WAIT_NONE) continue;
+            g_cur = t;
             threadIdx = dim3(t, 0, 0);
-            blockIdx = dim3(bx, by, bz);
-            body();
-            g_bar->arrive_and_drop();          // a thread that returned early must not block later barriers
-            g_warp_bar[t >> 5]->arrive_and_drop();
-          });
-        for (auto& th : ts) th.join();
+            swapcontext(&g_sched, &f.ctx);
+            progressed = true;
+            if (f.done) --live;
+          }
+          // open the barriers whose every live participant has arrived
+          bool all_block = live > 0;
+          for (unsigned t = 0; t < n && all_block; ++t)
+            if (!g_fib[t].done && g_fib[t].wait != WAIT_BLOCK) all_block = false;
+          if (all_block) {
+            for (unsigned t = 0; t < n; ++t) g_fib[t].wait = WAIT_NONE;
+            progressed = true;
+          }
+          for (unsigned w = 0; w < n_warps; ++w) {
+            const unsigned lo = 32 * w, hi = std::min(n, lo + 32);
+            bool all = false, any = false;
+            for (unsigned t = lo; t < hi; ++t)
+              if (!g_fib[t].done) {
+                if (!any) all = true;
+                any = true;
+                if (g_fib[t].wait != WAIT_WARP) all = false;
+              }
+            if (any && all) {
+              for (unsigned t = lo; t < hi; ++t) g_fib[t].wait = WAIT_NONE;
+              progressed = true;
+            }
+          }
+          if (!progressed) {
+            fprintf(stderr, "hostsim: deadlock in block (%u,%u,%u): divergent barrier\n", bx, by, bz);
+            abort();
+          }
+        }
       }
 }
 // kernels without barriers / shuffles: the CUDA threads of every block run one after the other in the calling thread
@@ -205,7 +257,28 @@ static inline void launch_blocks_seq(dim3 grid, dim3 block, const std::function<
           body();
         }
 }
-#define LAUNCH_SEQ(kernel, grid, block, ...) launch_blocks_seq(dim3 grid, dim3 block, [&] { kernel(__VA_ARGS__); })
-#define LAUNCH(kernel, grid, block, ...) launch_blocks(dim3 grid, dim3 block, [&] { kernel(__VA_ARGS__); })
+// HOSTSIM_PROFILE=1: per-kernel launch counts and wall time, printed when the library is unloaded
+#include <chrono>
+#include <map>
+#include <string>
+struct HostsimProfile {
+  std::map<std::string, std::pair<long, double>> rows;
+  ~HostsimProfile() {
+    if (!getenv("HOSTSIM_PROFILE")) return;
+    for (auto& r : rows) fprintf(stderr, "hostsim %-44s %6ld launches %9.3f s\n", r.first.c_str(), r.second.first, r.second.second);
+  }
+};
+static HostsimProfile g_profile;
+template <typename F>
+static inline void profiled(const char* name, F&& f) {
+  const auto t0 = std::chrono::steady_clock::now();
+  f();
+  auto& r = g_profile.rows[name];
+  r.first += 1;
+  r.second += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+#define LAUNCH_SEQ(kernel, grid, block, ...) \
+  profiled(#kernel, [&] { launch_blocks_seq(dim3 grid, dim3 block, [&] { kernel(__VA_ARGS__); }); })
+#define LAUNCH(kernel, grid, block, ...) profiled(#kernel, [&] { launch_blocks(dim3 grid, dim3 block, [&] { kernel(__VA_ARGS__); }); })
 
 extern "C" const char* hostsim_last_error() { return ccdm::g_err; }

@@ -1,5 +1,5 @@
 """The CUDA-core kernels of ccdm_b200/csrc/groupnorm.cu, compiled for the HOST from their own source
-(tests/hostsim: one OS thread per CUDA thread, real barriers / shuffles / atomics) and checked against torch.
+(tests/hostsim: every CUDA thread a cooperative fiber, real barriers / shuffles / atomics) and checked against torch.
 
 This exercises the kernels' index arithmetic, shared-memory staging, grid sizing and argument checks without a GPU.
 It says nothing about performance and is not a fallback: the product loads only libccdm_b200.so (sm_100a).
