@@ -1,122 +1,25 @@
 """Node wiring of the vanilla (GroupNorm) UNet's training step on CPU: ccdm_b200.vanilla_train runs unchanged, with
-  * the GroupNorm / attention kernels executed from their own CUDA source compiled for the host (tests/hostsim),
-  * ccdm_affine_act and the tap-GEMM based helpers (conv forward / data gradient / weight gradient / bias sums) replaced
-    by torch restatements with bf16 storage,
+  * every CUDA-core kernel executed from its own CUDA source compiled for the host (tests/hostsim),
+  * the tap-GEMM based helpers (conv forward / data gradient / weight gradient / bias sums) replaced by torch restatements
+    with bf16 storage (tests/hostpath.py),
 and the parameter gradients compared with autograd of the oracle.  Checks saved tensors, coefficient layouts, the
 concatenated-source handling, the scale/shift gradient path into the tc_mlp Linears and the padded stem / head weights."""
-import ctypes as C
 import math
 import os
 
 import pytest
 import torch
-import torch.nn.functional as F
 
-import ccdm_b200.backward as K
-from ccdm_b200 import _lib as L
 from ccdm_b200.vanilla_train import vanilla_train_forward
 from ccdm_b200.vanilla_unet import VanillaUnet
 from oracle.vanilla_unet_ref import make_state_dict, vanilla_unet_forward
+from tests import hostpath
 from tests.golden.vanilla_cases import V_BATCH, V_SPECS, keep_mask, vanilla_inputs
-from tests.hostsim.build import build
-
-HOST_SYMBOLS = ["ccdm_channel_stats", "ccdm_groupnorm_coef", "ccdm_norm_bwd_stats", "ccdm_groupnorm_bwd_coef",
-                "ccdm_norm_bwd_apply", "ccdm_attention_tokens", "ccdm_attention_tokens_bwd"]
-
-
-def _bf16(ptr, n):
-    return torch.frombuffer((C.c_uint16 * n).from_address(ptr), dtype=torch.bfloat16)
-
-
-def _f32(ptr, n):
-    return torch.frombuffer((C.c_float * n).from_address(ptr), dtype=torch.float32)
-
-
-SAMPLER_SYMBOLS = ["ccdm_q_sample", "ccdm_vicinal_loss"]
-
-
-class HostLib:
-    """libccdm_b200.so stand-in for CPU tensors: host builds of the CUDA-core kernels (groupnorm.cu, sampler.cu) + a
-    restatement of ccdm_affine_act."""
-
-    def __init__(self):
-        h = C.CDLL(build("groupnorm.cu"))
-        hs = C.CDLL(build("sampler.cu"))
-        for handle, names in ((h, HOST_SYMBOLS), (hs, SAMPLER_SYMBOLS)):
-            for name in names:
-                fn = getattr(handle, name)
-                fn.restype, fn.argtypes = L.SIGNATURES[name]
-                setattr(self, name, fn)
-        h.hostsim_last_error.restype = C.c_char_p
-        self.ccdm_last_error = h.hostsim_last_error
-
-    @staticmethod
-    def ccdm_affine_act(x, out, rows, c, rps, ss, ss_ld, ss_off, act, stream):
-        b = rows // rps
-        xv = _bf16(x, rows * c).float().reshape(b, rps, c)
-        s = _f32(ss, b * ss_ld).reshape(b, ss_ld)
-        v = xv * (1 + s[:, None, ss_off:ss_off + c]) + s[:, None, ss_off + c:ss_off + 2 * c]
-        v = {0: lambda u: u, 1: F.relu, 2: F.silu}[act](v)
-        _bf16(out, rows * c).copy_(v.reshape(-1).to(torch.bfloat16))
-        return 0
-
-
-def _conv(kind, x, w, b=None):
-    if kind == "up2x3x3":
-        x = F.interpolate(x, scale_factor=2, mode="nearest")
-    return F.conv2d(x, w, b, stride=2 if kind == "down3x3s2" else 1, padding=0 if kind == "1x1" else 1)
-
-
-def _nchw(t):
-    return t.float().permute(0, 3, 1, 2)
-
-
-def conv_forward(kind, srcs, weight, bias=None, resid=None):
-    y = _conv(kind, torch.cat([_nchw(s) for s in srcs], 1), weight.detach().to(torch.bfloat16).float(),
-              bias.detach() if bias is not None else None).permute(0, 2, 3, 1)
-    if resid is not None:
-        y = y + resid.float()
-    return y.to(torch.bfloat16).contiguous()
-
-
-def conv_dgrad(kind, dy, weight, cins):
-    b, oh, ow, _ = dy.shape
-    h, w = {"1x1": (oh, ow), "3x3": (oh, ow), "down3x3s2": (2 * oh, 2 * ow), "up2x3x3": (oh // 2, ow // 2)}[kind]
-    x = torch.zeros(b, sum(cins), h, w, requires_grad=True)
-    with torch.enable_grad():
-        y = _conv(kind, x, weight.detach().to(torch.bfloat16).float())
-    (dx,) = torch.autograd.grad(y, x, _nchw(dy))
-    return [t.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous() for t in dx.split(list(cins), 1)]
-
-
-def conv_wgrad(kind, srcs, dz, ksplit=0, timing=None, accumulate_into=None):
-    x = torch.cat([_nchw(s) for s in srcs], 1)
-    k = 1 if kind == "1x1" else 3
-    w = torch.zeros(dz.shape[3], x.shape[1], k, k, requires_grad=True)
-    with torch.enable_grad():
-        y = _conv(kind, x, w)
-    (dw,) = torch.autograd.grad(y, w, _nchw(dz))
-    if accumulate_into is not None:
-        accumulate_into.add_(dw)
-        return accumulate_into
-    return dw
-
-
-def colsum(x, accumulate_into=None):
-    s = x.float().reshape(-1, x.shape[-1]).sum(0)
-    if accumulate_into is not None:
-        accumulate_into.add_(s)
-        return accumulate_into
-    return s
 
 
 @pytest.fixture()
 def host_path(monkeypatch):
-    lib = HostLib()
-    monkeypatch.setattr(L, "lib", lambda: lib)
-    monkeypatch.setattr(K, "_stream", lambda: None)
-    for name, fn in (("conv_forward", conv_forward), ("conv_dgrad", conv_dgrad), ("conv_wgrad", conv_wgrad), ("colsum", colsum)):
-        monkeypatch.setattr(K, name, fn)
+    hostpath.install(monkeypatch)
 
 
 @pytest.mark.parametrize("sname,kind", [("v_tiny", "mixed"), ("v_attn", "cond")])
@@ -130,8 +33,8 @@ def test_training_step_gradients_match_oracle_autograd(host_path, sname, kind):
     net.load_state_dict(sd, strict=True)
     net.train()
     x, t, classes = vanilla_inputs(sname)
-    if sname == "v_attn":               # attention at every level: 8x8 input (64 / 16 / 4 tokens) keeps the thread-per-CUDA-
-        x = x[..., :8, :8].contiguous()  # thread simulation of the attention kernels to seconds
+    if sname == "v_attn":               # attention at every level: 8x8 input (64 / 16 / 4 tokens) keeps the fiber
+        x = x[..., :8, :8].contiguous()  # simulation of the attention kernels to seconds
     keep = keep_mask(kind, V_BATCH[sname])
     dout = torch.randn(x.shape, generator=torch.Generator().manual_seed(9))
     out = vanilla_train_forward(net, x, t, classes, keep)
