@@ -175,3 +175,106 @@ def install(monkeypatch):
     from ccdm_b200.diffusion import GaussianDiffusion
     monkeypatch.setattr(GaussianDiffusion, "_stream", staticmethod(lambda: None))
     return lib
+
+
+# ------------------------------------------------------------------------------------------------- C-ABI level ccdm_tapgemm
+
+class _Plan:
+    """The few ConvPlan fields tests.emu_engine.run_tapgemm reads, rebuilt from a ccdm_tapgemm_args struct."""
+
+    def __init__(self, a):
+        self.nz, self.ngroups, self.R = a.nz, a.ngroups, a.R
+        self.nkb = a.ngroups * a.R
+        n = a.nz * a.ngroups * 4
+        s = torch.frombuffer((C.c_int32 * n).from_address(a.sched), dtype=torch.int32).reshape(-1, 4).tolist()
+        self.sched = [tuple(r) for r in s]
+
+
+def _flat(ptr, n, dtype):
+    ctype, size = {torch.bfloat16: (C.c_uint16, 2), torch.float32: (C.c_float, 4)}[dtype]
+    return torch.frombuffer((ctype * n).from_address(ptr), dtype=dtype)
+
+
+def tapgemm_abi(argref, stream):
+    """ccdm_tapgemm(const ccdm_tapgemm_args*, stream) on host pointers: decodes the argument struct exactly as the library
+    would (views, strides, packed weights, epilogue operands) and evaluates it with the documented semantics."""
+    a = argref._obj if hasattr(argref, "_obj") else argref.contents
+    views = []
+    for i in range(a.n_src):
+        v = a.src[i]
+        span = (v.B - 1) * v.sB + (v.H - 1) * v.sH + (v.W - 1) * v.sW + v.C
+        views.append(ViewRec(_flat(v.ptr, span, torch.bfloat16), 0, v.C, v.W, v.H, v.B, v.sW, v.sH, v.sB))
+    plan = _Plan(a)
+    K_ = plan.nkb * KB
+    rows = (a.gB * a.w_batch_rows) if a.w_batch_rows else a.nz * a.n_rows
+    wpacked = _flat(a.wpacked, rows * K_, torch.bfloat16).reshape(rows, K_)
+    out_dtype = torch.float32 if a.flags & L.EPI_OUT_F32 else torch.bfloat16
+    ooff = tuple(a.ooff[i] for i in range(L.MAX_Z))
+    span = max(ooff[:a.nz]) + (a.gB - 1) * a.osB + (a.gH - 1) * a.osH + (a.gW - 1) * a.osW + a.N
+    out = _flat(a.out, span, out_dtype)
+    rec = TapGemmRec("abi", plan, views, a.gW, a.gH, a.gB, (a.tw, a.th, a.tb), None, wpacked, None, a.n_rows, a.N, a.n_tile,
+                     a.flags, out, (a.osW, a.osH, a.osB), ooff, gain_mul=a.gain_mul, ss_ld=a.ss_ld, ss_off=a.ss_off,
+                     q_scale=a.q_scale, q_cols=a.q_cols, w_batch_rows=a.w_batch_rows)
+    npix = a.gB * a.gH * a.gW
+    if a.bias:
+        rec.bias = _flat(a.bias, a.N, torch.float32)
+    if a.rowss:
+        rec.rowss = _flat(a.rowss, npix, torch.float32)
+    if a.gain:
+        rec.gain = _flat(a.gain, a.N, torch.float32)
+    if a.scale_shift:
+        rec.ss = _flat(a.scale_shift, a.gB * a.ss_ld, torch.float32).reshape(a.gB, a.ss_ld)
+    if a.resid:
+        rspan = (a.gB - 1) * a.rsB + (a.gH - 1) * a.rsH + (a.gW - 1) * a.rsW + a.N
+        rec.resid, rec.resid_strides = _flat(a.resid, rspan, torch.bfloat16), (a.rsW, a.rsH, a.rsB)
+    if a.out_rowss:
+        rec.out_rowss = _flat(a.out_rowss, npix, torch.float32)
+    with torch.no_grad():
+        run_tapgemm(rec)
+    return 0
+
+
+def linattn_context_abi(qkv, ctx, colsum, b, n, heads, w_out, wfold, c, n_rows, stream):
+    """ccdm_linattn_context incl. the fused fold into to_out's weights (linattn.cu)."""
+    q = _flat(qkv, b * n * 3 * heads * 32, torch.bfloat16).float().reshape(b, n, 3, heads, 32)
+    p, v = q[:, :, 1], q[:, :, 2]
+    s = p.sum(1)
+    cm = torch.einsum("bnhd,bnhe->bhde", p, v) / s[..., None]
+    if ctx:
+        _flat(ctx, b * heads * 32 * 32, torch.float32).copy_(cm.reshape(-1))
+    if colsum:
+        _flat(colsum, b * heads * 32, torch.float32).copy_(s.reshape(-1))
+    if wfold:
+        w = _flat(w_out, c * heads * 32, torch.float32).reshape(c, heads, 32)
+        wf = torch.einsum("che,bhde->bchd", w, cm).reshape(b, c, heads * 32)
+        dst = _flat(wfold, b * n_rows * heads * 32, torch.bfloat16).reshape(b, n_rows, heads * 32)
+        dst.zero_()
+        dst[:, :c] = wf.to(torch.bfloat16)
+    return 0
+
+
+def install_engine(monkeypatch):
+    """Everything `install` does, plus what the INFERENCE engine needs: ccdm_tapgemm / ccdm_linattn_context at the C-ABI
+    level, the weight-pack kernels from source, eager sampler steps instead of CUDA-graph capture, and CPU devices accepted."""
+    import ccdm_b200.diffusion as DM
+    import ccdm_b200.engine as E
+    import ccdm_b200.unet as U
+    lib = install(monkeypatch)
+    for cu, kernels, entries in (("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights"]),
+                                 ("linattn.cu", ["kexp_bound_kernel"], ["ccdm_kexp_bound"])):
+        h = C.CDLL(build_extract(cu, kernels, entries))
+        for name in entries:
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = L.SIGNATURES[name]
+            setattr(lib, name, fn)
+    lib.ccdm_tapgemm = tapgemm_abi
+    lib.ccdm_linattn_context = linattn_context_abi
+    monkeypatch.setattr(E.UnetEngine, "_stream", staticmethod(lambda: None))
+    monkeypatch.setattr(DM._SamplerState, "step", lambda self: self._launch(None))
+
+    def engine(self):
+        if self._engine is None:
+            self._engine = E.UnetEngine(self)
+        return self._engine
+    monkeypatch.setattr(U.Unet, "engine", engine)
+    return lib
