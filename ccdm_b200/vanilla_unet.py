@@ -55,6 +55,10 @@ def prob_mask_like(shape, prob, device):          # V:31-37
     return torch.zeros(shape, device=device).float().uniform_(0, 1) < prob
 
 
+def _current_stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
 def _require_cuda(x):
     if not x.is_cuda:
         raise RuntimeError("ccdm_b200.VanillaUnet runs on sm_100a only (there is no CPU fallback)")
@@ -235,7 +239,7 @@ class VanillaUnet(nn.Module):
         out = torch.empty_like(cond)
         L.check(L.lib().ccdm_cfg_combine(cond.data_ptr(), null.data_ptr(), out.data_ptr(), cond.shape[0], cond[0].numel(),
                                          float(cond_scale), float(rescaled_phi), 0, 0.0,
-                                         torch.cuda.current_stream().cuda_stream), "cfg_combine")
+                                         _current_stream()), "cfg_combine")
         return out
 
 
@@ -268,7 +272,7 @@ class VanillaEngine:
         if x.device != self.device:
             raise RuntimeError(f"input on {x.device}, model on {self.device}")
         prog.load_inputs(x, t, classes, keep_rows)
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = _current_stream()
         self.weights.refresh(stream)
         prog.run(stream)
         if self.net.training:
@@ -539,7 +543,7 @@ class VanillaProgram(UnetProgram):
     def run(self, stream: int):
         """``stream`` must be torch's current stream: the two layout copies at the boundary are torch kernels (they are
         captured with the rest when the sampler records its CUDA graph)."""
-        if stream != torch.cuda.current_stream().cuda_stream:
+        if stream != _current_stream():
             raise RuntimeError("VanillaProgram.run: launch on torch's current stream")
         b = self._head_bias_src
         if getattr(self.weights, "_head_bias_stamp", None) != (b.data_ptr(), b._version):

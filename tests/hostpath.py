@@ -277,4 +277,14 @@ def install_engine(monkeypatch):
             self._engine = E.UnetEngine(self)
         return self._engine
     monkeypatch.setattr(U.Unet, "engine", engine)
+
+    import ccdm_b200.vanilla_unet as VU
+
+    def v_engine(self):
+        if self._engine is None:
+            self._engine = VU.VanillaEngine(self)
+        return self._engine
+    monkeypatch.setattr(VU.VanillaUnet, "engine", v_engine)
+    monkeypatch.setattr(VU, "_current_stream", lambda: None)
+    monkeypatch.setattr(VU, "_require_cuda", lambda x: None)
     return lib

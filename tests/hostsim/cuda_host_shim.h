@@ -15,6 +15,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <setjmp.h>
 #include <ucontext.h>
 #include <vector>
 
@@ -45,19 +46,32 @@ static std::vector<double> g_shfl;      // one 8-byte slot per thread (float and
 
 // ---- cooperative fibers: one per CUDA thread of the running block
 enum { WAIT_NONE = 0, WAIT_BLOCK = 1, WAIT_WARP = 2 };
+// makecontext / setcontext start a fiber on its own stack; every later switch is _setjmp / _longjmp (no signal-mask system
+// call, ~50x cheaper than swapcontext).  Built with _FORTIFY_SOURCE off: the fortified longjmp rejects cross-stack jumps.
 struct Fiber {
   ucontext_t ctx;
+  jmp_buf jb;
   std::vector<char> stack;
-  bool done = false;
+  bool started = false, done = false;
   int wait = WAIT_NONE;
 };
 static std::vector<Fiber> g_fib;
-static ucontext_t g_sched;
+static jmp_buf g_sched_jb;
 static unsigned g_cur = 0;
 static const std::function<void()>* g_body = nullptr;
+static inline void fiber_yield() {               // back to the scheduler; returns when the scheduler resumes this fiber
+  if (!_setjmp(g_fib[g_cur].jb)) _longjmp(g_sched_jb, 1);
+}
 static inline void fiber_wait(int scope) {       // park the current fiber at a barrier of the given scope
   g_fib[g_cur].wait = scope;
-  swapcontext(&g_fib[g_cur].ctx, &g_sched);
+  fiber_yield();
+}
+static inline void fiber_resume(unsigned t) {    // scheduler side: run fiber t until it yields or finishes
+  if (_setjmp(g_sched_jb)) return;
+  Fiber& f = g_fib[t];
+  if (f.started) _longjmp(f.jb, 1);
+  f.started = true;
+  setcontext(&f.ctx);
 }
 
 #define __global__ static
@@ -175,7 +189,7 @@ static inline void griddep_launch_dependents() {}
 static void fiber_entry() {
   (*g_body)();
   g_fib[g_cur].done = true;
-  swapcontext(&g_fib[g_cur].ctx, &g_sched);
+  _longjmp(g_sched_jb, 1);
 }
 // Round-robin scheduler: every runnable fiber runs until its next barrier / shuffle (or to the end); a barrier opens when all
 // live fibers of its scope (block, or one warp) are parked at it.  A block that can neither run nor open a barrier is a
@@ -195,12 +209,12 @@ static inline void launch_blocks(dim3 grid, dim3 block, const std::function<void
         for (unsigned t = 0; t < n; ++t) {
           Fiber& f = g_fib[t];
           if (f.stack.size() != kStack) f.stack.resize(kStack);
-          f.done = false;
+          f.started = f.done = false;
           f.wait = WAIT_NONE;
           getcontext(&f.ctx);
           f.ctx.uc_stack.ss_sp = f.stack.data();
           f.ctx.uc_stack.ss_size = kStack;
-          f.ctx.uc_link = &g_sched;
+          f.ctx.uc_link = nullptr;
           makecontext(&f.ctx, fiber_entry, 0);
         }
         unsigned live = n;
@@ -211,7 +225,7 @@ static inline void launch_blocks(dim3 grid, dim3 block, const std::function<void
             if (f.done || f.wait != WAIT_NONE) continue;
             g_cur = t;
             threadIdx = dim3(t, 0, 0);
-            swapcontext(&g_sched, &f.ctx);
+            fiber_resume(t);
             progressed = true;
             if (f.done) --live;
           }

@@ -84,3 +84,69 @@ def test_sampling_matches_the_reference_samples(monkeypatch, name):
     # the eps objective additionally amplifies it by sqrt(1/acp - 1)
     floor = 40.0 if c["kind"] == "ddim" and c["objective"] != "pred_noise" else 30.0
     assert psnr >= floor, (name, psnr)
+
+
+# ------------------------------------------------------------------------------------------------- vanilla (GroupNorm) tree
+
+def _vnet(sname, seed):
+    from oracle.vanilla_unet_ref import make_state_dict as v_sd
+    from tests.golden.vanilla_cases import V_SPECS
+    s = V_SPECS[sname]
+    net = ccdm_b200.VanillaUnet(embed_input_dim=s.embed_input_dim, cond_drop_prob=0.5, in_channels=s.in_channels,
+                                model_channels=s.model_channels, num_res_blocks=s.num_res_blocks,
+                                attention_resolutions=s.attention_resolutions, channel_mult=s.channel_mult,
+                                num_heads=s.num_heads, num_groups=s.num_groups)
+    net.load_state_dict(v_sd(s, seed), strict=True)
+    return s, net
+
+
+VGOLD = {k: torch.load(os.path.join(os.path.dirname(__file__), "golden", f"vanilla_{k}.pt")) for k in ("unet", "sampler")}
+
+
+def test_vanilla_forward_and_guidance_match_the_reference(monkeypatch):
+    """VanillaUnet.forward (mask drawn by the product's prob_mask_like, injected) and forward_with_cond_scale on CPU vs the
+    outputs of the reference's own module."""
+    import ccdm_b200.vanilla_unet as VU
+    from tests.golden.vanilla_cases import V_BATCH, V_CASES, V_CFG_CASES, keep_mask, vanilla_inputs
+    hostpath.install_engine(monkeypatch)
+    for name, (sname, seed, mode, kind) in V_CASES.items():
+        if sname == "v_rc":                                # 64x64 script configuration: tests/test_vanilla_emulated.py
+            continue
+        _, net = _vnet(sname, seed)
+        net.train(mode == "train")
+        mask = keep_mask(kind, V_BATCH[sname])
+        monkeypatch.setattr(VU, "prob_mask_like", lambda shape, prob, device, _m=mask: _m.clone())
+        x, t, classes = vanilla_inputs(sname)
+        with torch.no_grad():
+            y = net(x, t, classes, cond_drop_prob=0.5)
+        assert rel(y, VGOLD["unet"][name]["out"]) < 2e-2, name
+    for name, (sname, seed, cs, phi) in V_CFG_CASES.items():
+        _, net = _vnet(sname, seed)
+        net.eval()
+        x, t, classes = vanilla_inputs(sname)
+        with torch.no_grad():
+            y = net.forward_with_cond_scale(x, t, classes, cond_scale=cs, rescaled_phi=phi)
+        assert rel(y, VGOLD["unet"][name]["out"]) < 3e-2, name
+
+
+def test_vanilla_sampling_matches_the_reference_samples(monkeypatch):
+    from tests.golden.vanilla_cases import V_SAMPLER_CASES, V_SIZES, sampler_classes
+    hostpath.install_engine(monkeypatch)
+    for name, c in V_SAMPLER_CASES.items():
+        s, net = _vnet(c["spec"], c["seed"])
+        net.eval()
+        size = V_SIZES[c["spec"]]
+        gd = ccdm_b200.VanillaGaussianDiffusion(torch.nn.DataParallel(net), image_size=size, timesteps=c["T"],
+                                                sampling_timesteps=c["S"], objective=c["objective"],
+                                                ddim_sampling_eta=c["eta"]).eval()
+        classes = sampler_classes(c)
+        torch.manual_seed(c["rng"])
+        if c["kind"] == "ddim":
+            img = gd.ddim_sample(classes, (c["B"], s.in_channels, size, size), cond_scale=c["scale"], rescaled_phi=c["phi"])
+        else:
+            img = gd.sample(classes, cond_scale=c["scale"], rescaled_phi=c["phi"], preset_sampling_timesteps=c["S"])
+        mse = ((img - VGOLD["sampler"][name]["img"]) ** 2).mean().item()
+        psnr = 10 * math.log10(1.0 / max(mse, 1e-20))
+        print(f"{name}: PSNR vs the reference's own samples {psnr:.1f} dB")
+        floor = 40.0 if c["kind"] == "ddim" and c["objective"] != "pred_noise" else 30.0
+        assert psnr >= floor, (name, psnr)

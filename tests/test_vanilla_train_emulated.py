@@ -60,10 +60,7 @@ def test_training_step_gradients_match_oracle_autograd(host_path, sname, kind):
         assert ((g - w).norm() / w.norm().clamp_min(1e-12)).item() < 6e-2, n
 
 
-@pytest.mark.parametrize("name", ["v_loss_x0_vic", "v_loss_eps_plain", pytest.param(
-    "v_loss_v_vic_attn", marks=pytest.mark.skipif(not os.environ.get("CCDM_SLOW_TESTS"),
-                                                  reason="256-token attention backward under the fiber simulation takes "
-                                                         "~45 s: set CCDM_SLOW_TESTS=1 (passes)"))])
+@pytest.mark.parametrize("name", ["v_loss_x0_vic", "v_loss_eps_plain", "v_loss_v_vic_attn"])
 def test_p_losses_and_backward_match_the_reference(host_path, monkeypatch, name):
     """Product code end to end -- VanillaGaussianDiffusion.p_losses (ccdm_q_sample, VanillaUnet autograd nodes,
     ccdm_vicinal_loss from their own source) + loss.backward() -- against the loss and gradients the reference's own
