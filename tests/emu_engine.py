@@ -67,6 +67,10 @@ def run_tapgemm(r: TapGemmRec):
             v = v * (1 + sc) + sh
         if r.flags & L.EPI_SILU:
             v = F.silu(v)
+        if r.flags & L.EPI_RELU:
+            v = F.relu(v)
+        if r.flags & L.EPI_TANH:
+            v = torch.tanh(v)
         if r.flags & L.EPI_QSOFTMAX:
             qc = r.q_cols
             q = v[..., :qc].reshape(gB, gH, gW, qc // 32, 32).softmax(-1) * r.q_scale

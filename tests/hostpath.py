@@ -1,15 +1,15 @@
-"""TEST INFRASTRUCTURE: run the PRODUCT training / loss code of ccdm_b200 on CPU tensors.
+"""TEST INFRASTRUCTURE: run the PRODUCT code of ccdm_b200 (inference engine, training nodes, losses) on CPU tensors.
 
   * every CUDA-core kernel comes from a host build of its own source (tests/hostsim);
-  * the tcgen05 pieces are restated in torch with bf16 storage: the tap-GEMM based helpers of ccdm_b200.backward
-    (conv forward / data gradient / weight gradient, per-sample 128x128 products, the stem's tap-GEMM and packed weight
-    gradient) and the two tensor-core linear-attention entry points (ccdm_linattn_context, ccdm_linattn_dcontext);
-  * ccdm_b200 itself is untouched: `install(monkeypatch)` swaps `_lib.lib`, a few `backward.*` functions and the stream getter.
+  * the tcgen05 entry points are evaluated at the C-ABI level from their decoded argument structs / pointers, in torch with
+    bf16 storage: ccdm_tapgemm (forward convs, data gradients, per-sample products, stem), ccdm_conv_wgrad, and the two
+    tensor-core linear-attention GEMMs (ccdm_linattn_context, ccdm_linattn_dcontext);
+  * ccdm_b200 itself is untouched -- its plans, weight packing and argument marshalling all run: `install(monkeypatch)` swaps
+    only `_lib.lib`, the "is this a CUDA tensor" check and the stream getters.
 """
 import ctypes as C
 
 import torch
-import torch.nn.functional as F
 
 import ccdm_b200.backward as K
 from ccdm_b200 import _lib as L
@@ -20,22 +20,21 @@ from tests.emu_engine import _view_tensor, run_tapgemm
 from tests.hostsim.build import build, build_extract
 
 
-def _bf16(ptr, n):
-    return torch.frombuffer((C.c_uint16 * n).from_address(ptr), dtype=torch.bfloat16)
-
-
-def _f32(ptr, n):
-    return torch.frombuffer((C.c_float * n).from_address(ptr), dtype=torch.float32)
+def _flat(ptr, n, dtype):
+    ctype = {torch.bfloat16: C.c_uint16, torch.float32: C.c_float}[dtype]
+    return torch.frombuffer((ctype * n).from_address(ptr), dtype=dtype)
 
 
 class HostLib:
-    """libccdm_b200.so stand-in for CPU tensors."""
+    """libccdm_b200.so stand-in for CPU tensors: host builds of every CUDA-core source file."""
 
     def __init__(self):
         handles = [C.CDLL(build(f)) for f in ("kernels.cu", "train_kernels.cu", "backward.cu", "sampler.cu", "groupnorm.cu",
                                               "optim.cu")]
         handles.append(C.CDLL(build_extract("wgrad.cu", ["unpack_wgrad_kernel", "pack_weights_t_kernel"],
                                             ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"])))
+        handles.append(C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights"])))
+        handles.append(C.CDLL(build_extract("linattn.cu", ["kexp_bound_kernel"], ["ccdm_kexp_bound"])))
         for name, (res, args) in L.SIGNATURES.items():
             for h in handles:
                 fn = getattr(h, name, None)
@@ -45,136 +44,10 @@ class HostLib:
                     break
         handles[0].hostsim_last_error.restype = C.c_char_p
         self.ccdm_last_error = handles[0].hostsim_last_error
-
-    # ---- tcgen05 entry points, restated (linattn.cu)
-    @staticmethod
-    def ccdm_linattn_context(qkv, ctx, colsum, b, n, heads, w_out, wfold, c, n_rows, stream):
-        """ctx[b,h,d,e] = sum_n p[n,hd] v[n,he] / S[hd],  S = sum_n p  (p = exp(k - max) written by ccdm_linattn_prep)."""
-        assert not w_out and not wfold
-        q = _bf16(qkv, b * n * 3 * heads * 32).float().reshape(b, n, 3, heads, 32)
-        p, v = q[:, :, 1], q[:, :, 2]
-        s = p.sum(1)                                                         # [b, heads, 32]
-        _f32(ctx, b * heads * 32 * 32).copy_((torch.einsum("bnhd,bnhe->bhde", p, v) / s[..., None]).reshape(-1))
-        if colsum:
-            _f32(colsum, b * heads * 32).copy_(s.reshape(-1))
-        return 0
-
-    @staticmethod
-    def ccdm_linattn_dcontext(qkv, dout, dctx, b, n, stream):
-        q = _bf16(qkv, b * n * 384).float().reshape(b, n, 3, 4, 32)[:, :, 0]
-        g = _bf16(dout, b * n * 128).float().reshape(b, n, 4, 32)
-        _f32(dctx, b * 4 * 32 * 32).copy_(torch.einsum("bnhd,bnhe->bhde", q, g).reshape(-1))
-        return 0
-
-    @staticmethod
-    def ccdm_affine_act(x, out, rows, c, rps, ss, ss_ld, ss_off, act, stream):      # kept for parity with older callers
-        raise AssertionError("ccdm_affine_act is provided by the host build of kernels.cu")
-
-
-# ------------------------------------------------------------------------------------------------- ccdm_b200.backward stand-ins
-
-def _conv(kind, x, w, b=None):
-    if kind == "up2x3x3":
-        x = F.interpolate(x, scale_factor=2, mode="nearest")
-    stride = 2 if kind in ("down3x3s2", "down4x4s2") else 1
-    return F.conv2d(x, w, b, stride=stride, padding=0 if kind == "1x1" else 1)
-
-
-def _nchw(t):
-    return t.float().permute(0, 3, 1, 2)
-
-
-def conv_forward(kind, srcs, weight, bias=None, resid=None):
-    y = _conv(kind, torch.cat([_nchw(s) for s in srcs], 1), weight.detach().to(torch.bfloat16).float(),
-              bias.detach() if bias is not None else None).permute(0, 2, 3, 1)
-    if resid is not None:
-        y = y + resid.float()
-    return y.to(torch.bfloat16).contiguous()
-
-
-def conv_dgrad(kind, dy, weight, cins):
-    b, oh, ow, _ = dy.shape
-    h, w = {"1x1": (oh, ow), "3x3": (oh, ow), "down3x3s2": (2 * oh, 2 * ow), "down4x4s2": (2 * oh, 2 * ow),
-            "up2x3x3": (oh // 2, ow // 2)}[kind]
-    x = torch.zeros(b, sum(cins), h, w, requires_grad=True)
-    with torch.enable_grad():
-        y = _conv(kind, x, weight.detach().to(torch.bfloat16).float())
-    (dx,) = torch.autograd.grad(y, x, _nchw(dy))
-    return [t.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous() for t in dx.split(list(cins), 1)]
-
-
-def conv_wgrad(kind, srcs, dz, ksplit=0, timing=None, accumulate_into=None):
-    x = torch.cat([_nchw(s) for s in srcs], 1)
-    k = {"1x1": 1, "down4x4s2": 4}.get(kind, 3)
-    w = torch.zeros(dz.shape[3], x.shape[1], k, k, requires_grad=True)
-    with torch.enable_grad():
-        y = _conv(kind, x, w)
-    (dw,) = torch.autograd.grad(y, w, _nchw(dz))
-    if accumulate_into is not None:
-        accumulate_into.add_(dw.view_as(accumulate_into))
-        return accumulate_into
-    return dw
-
-
-def colsum(x, accumulate_into=None):
-    s = x.float().reshape(-1, x.shape[-1]).sum(0)
-    if accumulate_into is not None:
-        accumulate_into.add_(s)
-        return accumulate_into
-    return s
-
-
-def per_sample_linear(src, c_off, w_batch, out, out_c_off):
-    b = src.shape[0]
-    x = src[..., c_off:c_off + 128].float()
-    w = w_batch.float().reshape(b, 128, 128)
-    out[..., out_c_off:out_c_off + 128] = torch.einsum("bhwk,bnk->bhwn", x, w).to(torch.bfloat16)
-    return out
-
-
-def _view(t, c_off=0, c=None):
-    b, h, w, ct = t.shape
-    return ViewRec(t, c_off, ct - c_off if c is None else c, w, h, b, ct, w * ct, h * w * ct)
-
-
-def _launch_tapgemm(plan, tile, views, gw, gh, gb, wpacked, sched, n_rows, n, n_tile, out, ostr, ooff, bias=None, resid=None,
-                    w_batch_rows=0, out_c_off=0, flags=0, ss=None):
-    assert out_c_off == 0 and ss is None
-    fl = flags | (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESID if resid is not None else 0)
-    rec = TapGemmRec("emu", plan, list(views), gw, gh, gb, tile, None, wpacked, sched, n_rows, n, n_tile, fl, out, ostr, ooff,
-                     bias=bias, w_batch_rows=w_batch_rows)
-    if resid is not None:
-        rc = resid.shape[3]
-        rec.resid, rec.resid_strides = resid, (rc, resid.shape[2] * rc, resid.shape[1] * resid.shape[2] * rc)
-    run_tapgemm(rec)
-
-
-def wgrad_packed(plan, tile, views, dz, gw, gh, sched, cout, n_rows, ksplit=0, timing=None):
-    """fp32 [nz*n_rows, nkb*64]: for K block (group g, tap r): dz^T . (source view shifted by the block's tap)."""
-    assert plan.nz == 1
-    g = torch.zeros(n_rows, plan.nkb * KB)
-    d = dz.float()
-    vt = [_view_tensor(v) for v in views]
-    for kb in range(plan.nkb):
-        grp, r = divmod(kb, plan.R)
-        src, dw, dh0, c0 = plan.sched[grp]
-        a = shifted(vt[src], dh0 + r, dw, gh, gw, c0)                        # [B, gh, gw, 64]
-        g[:cout, kb * KB:(kb + 1) * KB] = torch.einsum("bhwn,bhwk->nk", d, a)
-    return g
-
-
-def install(monkeypatch):
-    lib = HostLib()
-    monkeypatch.setattr(L, "lib", lambda: lib)
-    monkeypatch.setattr(K, "_stream", lambda: None)
-    monkeypatch.setattr(K, "_check", lambda t, what: None)
-    for name, fn in (("conv_forward", conv_forward), ("conv_dgrad", conv_dgrad), ("conv_wgrad", conv_wgrad), ("colsum", colsum),
-                     ("per_sample_linear", per_sample_linear), ("_view", _view), ("_launch_tapgemm", _launch_tapgemm),
-                     ("wgrad_packed", wgrad_packed)):
-        monkeypatch.setattr(K, name, fn)
-    from ccdm_b200.diffusion import GaussianDiffusion
-    monkeypatch.setattr(GaussianDiffusion, "_stream", staticmethod(lambda: None))
-    return lib
+        self.ccdm_tapgemm = tapgemm_abi
+        self.ccdm_conv_wgrad = wgrad_abi
+        self.ccdm_linattn_context = linattn_context_abi
+        self.ccdm_linattn_dcontext = linattn_dcontext_abi
 
 
 # ------------------------------------------------------------------------------------------------- C-ABI level ccdm_tapgemm
@@ -188,11 +61,6 @@ class _Plan:
         n = a.nz * a.ngroups * 4
         s = torch.frombuffer((C.c_int32 * n).from_address(a.sched), dtype=torch.int32).reshape(-1, 4).tolist()
         self.sched = [tuple(r) for r in s]
-
-
-def _flat(ptr, n, dtype):
-    ctype, size = {torch.bfloat16: (C.c_uint16, 2), torch.float32: (C.c_float, 4)}[dtype]
-    return torch.frombuffer((ctype * n).from_address(ptr), dtype=dtype)
 
 
 def tapgemm_abi(argref, stream):
@@ -253,22 +121,57 @@ def linattn_context_abi(qkv, ctx, colsum, b, n, heads, w_out, wfold, c, n_rows, 
     return 0
 
 
+def wgrad_abi(argref, stream):
+    """ccdm_conv_wgrad(const ccdm_wgrad_args*, stream): packed fp32 gradient += dz^T . (source view shifted by the block's tap)
+    for every K block (group g, tap r) of the FORWARD schedule, per sub-problem z."""
+    a = argref._obj if hasattr(argref, "_obj") else argref.contents
+    plan = _Plan(a)
+    views = []
+    for i in range(a.n_src):
+        v = a.src[i]
+        span = (v.B - 1) * v.sB + (v.H - 1) * v.sH + (v.W - 1) * v.sW + v.C
+        views.append(_view_tensor(ViewRec(_flat(v.ptr, span, torch.bfloat16), 0, v.C, v.W, v.H, v.B, v.sW, v.sH, v.sB)))
+    doff = [a.doff[i] for i in range(L.MAX_Z)]
+    span = max(doff[:a.nz]) + (a.gB - 1) * a.dsB + (a.gH - 1) * a.dsH + (a.gW - 1) * a.dsW + a.N
+    dz_flat = _flat(a.dz, span, torch.bfloat16)
+    g = _flat(a.wgrad_packed, a.nz * a.n_rows * plan.nkb * KB, torch.float32).reshape(a.nz * a.n_rows, plan.nkb * KB)
+    for z in range(a.nz):
+        d = torch.as_strided(dz_flat, (a.gB, a.gH, a.gW, a.N), (a.dsB, a.dsH, a.dsW, 1), doff[z]).float()
+        for kb in range(plan.nkb):
+            grp, r = divmod(kb, plan.R)
+            src, dw, dh0, c0 = plan.sched[z * plan.ngroups + grp]
+            x = shifted(views[src], dh0 + r, dw, a.gH, a.gW, c0)[: a.gB]
+            g[z * a.n_rows: z * a.n_rows + a.N, kb * KB:(kb + 1) * KB] += torch.einsum("bhwn,bhwk->nk", d, x)
+    return 0
+
+
+def linattn_dcontext_abi(qkv, dout, dctx, b, n, stream):
+    """ccdm_linattn_dcontext: dctx[b,h,d,e] = sum_n q_sm[n,hd] dout[n,he]  (tcgen05 in linattn.cu)."""
+    q = _flat(qkv, b * n * 384, torch.bfloat16).float().reshape(b, n, 3, 4, 32)[:, :, 0]
+    g = _flat(dout, b * n * 128, torch.bfloat16).float().reshape(b, n, 4, 32)
+    _flat(dctx, b * 4 * 32 * 32, torch.float32).copy_(torch.einsum("bnhd,bnhe->bhde", q, g).reshape(-1))
+    return 0
+
+
+def install(monkeypatch):
+    """ccdm_b200.backward / train / diffusion run UNCHANGED (plans, weight packing, argument structs); only the library handle is
+    swapped: CUDA-core kernels from source, the tcgen05 entry points at the C-ABI level."""
+    lib = HostLib()
+    monkeypatch.setattr(L, "lib", lambda: lib)
+    monkeypatch.setattr(K, "_stream", lambda: None)
+    monkeypatch.setattr(K, "_check", lambda t, what: None)             # "expected a CUDA tensor": host pointers are fine here
+    from ccdm_b200.diffusion import GaussianDiffusion
+    monkeypatch.setattr(GaussianDiffusion, "_stream", staticmethod(lambda: None))
+    return lib
+
+
 def install_engine(monkeypatch):
-    """Everything `install` does, plus what the INFERENCE engine needs: ccdm_tapgemm / ccdm_linattn_context at the C-ABI
-    level, the weight-pack kernels from source, eager sampler steps instead of CUDA-graph capture, and CPU devices accepted."""
+    """Everything `install` does, plus what the INFERENCE engine needs: eager sampler steps instead of CUDA-graph capture and
+    CPU devices accepted by the engines."""
     import ccdm_b200.diffusion as DM
     import ccdm_b200.engine as E
     import ccdm_b200.unet as U
     lib = install(monkeypatch)
-    for cu, kernels, entries in (("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights"]),
-                                 ("linattn.cu", ["kexp_bound_kernel"], ["ccdm_kexp_bound"])):
-        h = C.CDLL(build_extract(cu, kernels, entries))
-        for name in entries:
-            fn = getattr(h, name)
-            fn.restype, fn.argtypes = L.SIGNATURES[name]
-            setattr(lib, name, fn)
-    lib.ccdm_tapgemm = tapgemm_abi
-    lib.ccdm_linattn_context = linattn_context_abi
     monkeypatch.setattr(E.UnetEngine, "_stream", staticmethod(lambda: None))
     monkeypatch.setattr(DM._SamplerState, "step", lambda self: self._launch(None))
 
