@@ -60,6 +60,11 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _require_cuda(z):
+    if not z.is_cuda:
+        raise RuntimeError("ccdm_b200.sngan_generator runs on sm_100a only (there is no CPU fallback)")
+
+
 class sngan_generator(nn.Module):                   # noqa: N801  (the reference's class name)
     def __init__(self, dim_z=128, dim_embed=128, nc=3, img_size=64, gene_ch=32, ch_multi=None):
         super().__init__()
@@ -155,8 +160,7 @@ class sngan_generator(nn.Module):                   # noqa: N801  (the reference
         if self.training:
             raise NotImplementedError("ccdm_b200.sngan_generator: only the eval-mode forward (running BatchNorm statistics) "
                                       "runs on the CUDA path; training the generator is outside this round's scope")
-        if not z.is_cuda:
-            raise RuntimeError("ccdm_b200.sngan_generator runs on sm_100a only (there is no CPU fallback)")
+        _require_cuda(z)
         if y is None:
             raise NotImplementedError("the unconditional branch (sngan.py:84-85) is never taken by dmd.py")
         b = z.shape[0]

@@ -190,4 +190,8 @@ def install_engine(monkeypatch):
     monkeypatch.setattr(VU.VanillaUnet, "engine", v_engine)
     monkeypatch.setattr(VU, "_current_stream", lambda: None)
     monkeypatch.setattr(VU, "_require_cuda", lambda x: None)
+
+    import ccdm_b200.sngan as SG
+    monkeypatch.setattr(SG, "_require_cuda", lambda z: None)
+    monkeypatch.setattr(SG, "_stream", lambda: None)
     return lib

@@ -150,3 +150,24 @@ def test_vanilla_sampling_matches_the_reference_samples(monkeypatch):
         print(f"{name}: PSNR vs the reference's own samples {psnr:.1f} dB")
         floor = 40.0 if c["kind"] == "ddim" and c["objective"] != "pred_noise" else 30.0
         assert psnr >= floor, (name, psnr)
+
+
+# ------------------------------------------------------------------------------------------------- one-step generator
+
+@pytest.mark.parametrize("name", ["g64", "g192_mono"])
+def test_generator_forward_matches_the_reference(monkeypatch, name):
+    """ccdm_b200.sngan_generator.forward (eval mode) on CPU vs the output of the reference's own sngan_generator."""
+    from oracle.sngan_ref import make_state_dict as g_sd
+    from tests.golden.sngan_cases import GEN_CASES, GEN_SPECS, gen_inputs
+    hostpath.install_engine(monkeypatch)
+    sname, seed, batch = GEN_CASES[name]
+    s = GEN_SPECS[sname]
+    net = ccdm_b200.sngan_generator(dim_z=s.dim_z, dim_embed=s.dim_embed, nc=s.nc, img_size=s.img_size, gene_ch=s.gene_ch)
+    net.load_state_dict(g_sd(s, seed), strict=True)
+    net.eval()
+    z, y = gen_inputs(s, batch)
+    out = net(z, y)
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "sngan.pt"))[name]["out"]
+    err = rel(out, gold)
+    print(f"{name}: rel L2 err vs the reference's output {err:.3e}")
+    assert err < 2e-2
