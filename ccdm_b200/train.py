@@ -39,6 +39,11 @@ from . import backward as K
 from .plan import n_tiling, tile_box
 
 
+def _require_cuda(x: torch.Tensor):
+    if not x.is_cuda:
+        raise RuntimeError("ccdm_b200.Unet runs on sm_100a only (there is no CPU fallback)")
+
+
 def _c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
@@ -336,8 +341,7 @@ def unet_train_forward(net, x: torch.Tensor, t: torch.Tensor, labels_emb: torch.
     """Unet.forward in training mode with an autograd graph; returns the fp32 NCHW prediction.
 
     ``keep_mask`` is the Bernoulli mask ``Unet.forward`` drew (None when cond_drop_prob == 0)."""
-    if not x.is_cuda:
-        raise RuntimeError("ccdm_b200.Unet runs on sm_100a only (there is no CPU fallback)")
+    _require_cuda(x)
     b = x.shape[0]
     # conditioning (unet.py:397-414,421-423): tiny fp32 matrices, PyTorch library calls under autograd
     c = net.cond_mlp_1(labels_emb.float())

@@ -162,6 +162,10 @@ def install(monkeypatch):
     monkeypatch.setattr(K, "_check", lambda t, what: None)             # "expected a CUDA tensor": host pointers are fine here
     from ccdm_b200.diffusion import GaussianDiffusion
     monkeypatch.setattr(GaussianDiffusion, "_stream", staticmethod(lambda: None))
+    import ccdm_b200.train as T
+    import ccdm_b200.vanilla_unet as VU
+    monkeypatch.setattr(T, "_require_cuda", lambda x: None)             # the "no CPU fallback" guards of the training forwards
+    monkeypatch.setattr(VU, "_require_cuda", lambda x: None)
     return lib
 
 
