@@ -18,10 +18,26 @@ pytestmark = [pytest.mark.gpu,
                                  reason="vanilla-UNet kernels not yet run on a GPU: set CCDM_RUN_UNVERIFIED=1")]
 
 GOLD = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vanilla_unet.pt"))
+DEV = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+@pytest.fixture(autouse=True)
+def _host_stand_in(monkeypatch):
+    """Without a GPU (CCDM_RUN_UNVERIFIED=1 pytest tests/test_gpu_vanilla.py -m gpu in the build container) the same test
+    bodies run against the host builds of the kernels (tests/hostpath.py): a dry run of the TESTS themselves."""
+    if not torch.cuda.is_available():
+        from tests import hostpath
+        hostpath.install_engine(monkeypatch)
+    yield
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else None
+
+
+def _sync():
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
 
 
 def rel(a, b):
@@ -36,7 +52,7 @@ def test_groupnorm_chain_matches_torch(cs, groups, hw, with_ss):
     96- and 768-channel concatenations have groups that straddle the two sources."""
     from ccdm_b200 import _lib as L
     lib = L.lib()
-    dev = torch.device("cuda")
+    dev = DEV
     g = torch.Generator(device="cpu").manual_seed(5)
     B, (h, w), ctot = 3, hw, sum(cs)
     xs = [(torch.randn(B, h, w, c, generator=g) * 1.5 + 0.3).to(dev).to(torch.bfloat16).contiguous() for c in cs]
@@ -58,7 +74,7 @@ def test_groupnorm_chain_matches_torch(cs, groups, hw, with_ss):
                                     coef.shape[1], off, 2, _stream()))
         outs.append(o)
         off += 2 * x.shape[3]
-    torch.cuda.synchronize()
+    _sync()
     cat = torch.cat([x.float() for x in xs], -1)
     want_sums = torch.stack([cat.sum((1, 2)), cat.pow(2).sum((1, 2))], 1)
     assert rel(sums, want_sums) < 1e-4
@@ -75,7 +91,7 @@ def test_groupnorm_chain_matches_torch(cs, groups, hw, with_ss):
 @pytest.mark.parametrize("head_major", [0, 1])
 def test_attention_tokens_matches_torch(dh, n, head_major):
     from ccdm_b200 import _lib as L
-    dev = torch.device("cuda")
+    dev = DEV
     g = torch.Generator().manual_seed(n + dh)
     B, heads = 3, 2
     hid = heads * dh
@@ -83,7 +99,7 @@ def test_attention_tokens_matches_torch(dh, n, head_major):
     out = torch.empty(B, n, hid, dtype=torch.bfloat16, device=dev)
     scale = 1.0 / math.sqrt(dh)
     L.check(L.lib().ccdm_attention_tokens(qkv.data_ptr(), out.data_ptr(), B, n, heads, dh, scale, head_major, _stream()))
-    torch.cuda.synchronize()
+    _sync()
     f = qkv.float()
     v5 = f.reshape(B, n, heads, 3, dh).permute(0, 1, 3, 2, 4) if head_major else f.reshape(B, n, 3, heads, dh)
     q, k, v = v5[:, :, 0] * scale, v5[:, :, 1], v5[:, :, 2]
@@ -95,19 +111,19 @@ def test_attention_tokens_matches_torch(dh, n, head_major):
 def test_time_features_adm():
     from ccdm_b200 import _lib as L
     from oracle.vanilla_unet_ref import timestep_embedding
-    dev = torch.device("cuda")
+    dev = DEV
     t = torch.tensor([0, 1, 17, 500, 999], device=dev)
     for dim in (32, 64, 128):
         out = torch.empty(5, dim, device=dev)
         L.check(L.lib().ccdm_time_features_adm(t.data_ptr(), 5, dim, 10000.0, out.data_ptr(), _stream()))
-        torch.cuda.synchronize()
+        _sync()
         assert (out - timestep_embedding(t, dim)).abs().max().item() < 2e-4
 
 
 @pytest.mark.parametrize("cin,cout,hw", [(64, 64, (64, 64)), (128, 128, (32, 32)), (256, 256, (16, 16)), (32, 48, (8, 8))])
 def test_down3x3s2_matches_conv2d(cin, cout, hw):
     from ccdm_b200.backward import conv_forward
-    dev = torch.device("cuda")
+    dev = DEV
     g = torch.Generator().manual_seed(cin + cout)
     x = torch.randn(4, hw[0], hw[1], cin, generator=g).to(dev).to(torch.bfloat16).contiguous()
     w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(dev)
@@ -134,7 +150,7 @@ def _build(sname, seed, dev):
 def test_forward_matches_reference_outputs():
     """Whole network through VanillaEngine vs the reference's own outputs (golden) -- bf16 tolerance 2e-2 (BASELINE.json)."""
     from tests.golden.vanilla_cases import V_BATCH, V_CASES, keep_mask, vanilla_inputs
-    dev = torch.device("cuda")
+    dev = DEV
     for name, (sname, seed, mode, kind) in V_CASES.items():
         spec, net, _ = _build(sname, seed, dev)
         net.train(mode == "train")
@@ -149,7 +165,7 @@ def test_forward_matches_reference_outputs():
 
 def test_guidance_matches_reference_outputs():
     from tests.golden.vanilla_cases import V_CFG_CASES, vanilla_inputs
-    dev = torch.device("cuda")
+    dev = DEV
     for name, (sname, seed, cs, phi) in V_CFG_CASES.items():
         _, net, _ = _build(sname, seed, dev)
         net.eval()
@@ -163,7 +179,7 @@ def test_guidance_matches_reference_outputs():
 def test_rc49_config_pair_batch_and_oracle():
     """RC-49 64x64 script configuration at batch 8: the 2B pair batch equals two forwards, and both match the oracle."""
     from oracle.vanilla_unet_ref import vanilla_unet_forward
-    dev = torch.device("cuda")
+    dev = DEV
     spec, net, sd = _build("v_rc", 9, dev)
     net.eval()
     g = torch.Generator().manual_seed(3)
@@ -189,7 +205,7 @@ def test_sampling_loops_match_reference_outputs():
     from oracle.vanilla_diffusion_ref import v_ddim_sample, v_ddpm_sample
     from oracle.vanilla_unet_ref import vanilla_forward_with_cond_scale
     from tests.golden.vanilla_cases import V_SAMPLER_CASES, V_SIZES, V_SPECS, sampler_classes
-    dev = torch.device("cuda")
+    dev = DEV
     for name, c in V_SAMPLER_CASES.items():
         spec, net, sd = _build(c["spec"], c["seed"], dev)
         net.eval()
@@ -225,7 +241,7 @@ def test_sampling_loops_match_reference_outputs():
                                                       ((256, 512), 8, (4, 4), True, 2)])
 def test_groupnorm_node_backward_matches_autograd(cs, groups, hw, with_ss, act):
     from ccdm_b200.vanilla_train import GroupNormActFn
-    dev = torch.device("cuda")
+    dev = DEV
     g = torch.Generator().manual_seed(21)
     B, (h, w), ctot = 3, hw, sum(cs)
     xs = [(torch.randn(B, h, w, c, generator=g) * 1.5 + 0.3).to(dev).to(torch.bfloat16).requires_grad_(True) for c in cs]
@@ -253,7 +269,7 @@ def test_groupnorm_node_backward_matches_autograd(cs, groups, hw, with_ss, act):
 @pytest.mark.parametrize("dh,n", [(16, 64), (32, 256), (64, 100), (128, 64), (128, 16)])
 def test_attention_tokens_backward_matches_autograd(dh, n):
     from ccdm_b200.vanilla_train import AttnTokensFn
-    dev = torch.device("cuda")
+    dev = DEV
     g = torch.Generator().manual_seed(n + dh)
     B, heads = 3, 4
     hid = heads * dh
@@ -273,7 +289,7 @@ def test_attention_tokens_backward_matches_autograd(dh, n):
 @pytest.mark.parametrize("cin,cout,hw", [(64, 64, (32, 32)), (128, 128, (16, 16)), (32, 48, (8, 8))])
 def test_down3x3s2_gradients_match_autograd(cin, cout, hw):
     from ccdm_b200.train import ConvFn
-    dev = torch.device("cuda")
+    dev = DEV
     g = torch.Generator().manual_seed(cin)
     x = torch.randn(4, hw[0], hw[1], cin, generator=g).to(dev).to(torch.bfloat16).requires_grad_(True)
     w = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).to(dev).requires_grad_(True)
@@ -292,7 +308,7 @@ def test_training_step_gradients_match_oracle_autograd():
     from ccdm_b200.vanilla_train import vanilla_train_forward
     from oracle.vanilla_unet_ref import vanilla_unet_forward
     from tests.golden.vanilla_cases import V_BATCH, keep_mask, vanilla_inputs
-    dev = torch.device("cuda")
+    dev = DEV
     for sname, kind, seed in (("v_tiny", "mixed", 7), ("v_attn", "cond", 8), ("v_rc", "mixed", 9)):
         spec, net, sd = _build(sname, seed, dev)
         net.train()
@@ -319,7 +335,7 @@ def test_p_losses_match_reference_outputs():
     import ccdm_b200.vanilla_unet as VU
     from tests.golden.vanilla_cases import V_BATCH, V_LOSS_CASES, V_LOSS_GRAD_KEYS, V_SIZES, keep_mask, loss_inputs
     gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vanilla_loss.pt"))
-    dev = torch.device("cuda")
+    dev = DEV
     saved = VU.prob_mask_like
     try:
         for name, c in V_LOSS_CASES.items():

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # First GPU call of the next round: everything that was built after the round-1 GPU budget ran out.
 #   gpurun --timeout 1500 -- 'bash tools/r2_first_gpu_pass.sh'
-# 1. the opt-in parity tests of the vanilla (GroupNorm) UNet path   2. its DDIM-250 throughput at the RC-49 script config
+# 1. the opt-in parity tests of the vanilla (GroupNorm) UNet path (all 62 pass in a host dry run, CCDM_GPU_TESTS_ON_HOST=1)   2. its DDIM-250 throughput at the RC-49 script config
 # 3. HBM roofline of the GroupNorm row kernels                       4. the verified suite + headline bench, unchanged
 set -u
 mkdir -p gpurun_out
