@@ -18,9 +18,9 @@ Linears: [B, <= 1024] matrices) runs as PyTorch library calls under autograd, as
 stem and head use zero-padded weights (64 input columns / 8 output rows) built under autograd, so their weight gradients are
 slices of the padded ones.  The network output of this path is the bf16 result of the last tap-GEMM cast to fp32.
 
-STATUS: kernels checked on CPU against autograd through the host build of their source (tests/test_kernels_hostsim.py); the
-node wiring is checked on CPU with the tap-GEMM calls replaced by torch convolutions (tests/test_vanilla_train_emulated.py).
-Not yet run on a GPU (tests/test_gpu_vanilla.py, opt-in).
+STATUS: not yet run on a GPU (tests/test_gpu_vanilla.py, opt-in).  On CPU: the kernels run from their own source (host build,
+tests/hostsim) match autograd; this module, unchanged, over those kernels and C-ABI level stand-ins for the tcgen05 entry
+points reproduces the reference's own loss and gradients (tests/test_vanilla_train_emulated.py, tests/hostpath.py).
 """
 from __future__ import annotations
 

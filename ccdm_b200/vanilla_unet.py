@@ -22,9 +22,9 @@ Boundary glue in PyTorch (layout only): NCHW fp32 -> the first 3 of 64 bf16 NHWC
 The program exposes the same ``x_in / t_in / emb_in / keep / out / run(stream)`` surface as the unified UNet's, so
 :class:`ccdm_b200.VanillaGaussianDiffusion` drives it from the same CUDA-graph sampling loop.
 
-STATUS: host program checked on CPU against the oracle AND the reference's own outputs through the record interpreter
-(tests/test_vanilla_emulated.py: 0.8-1.0 % relative error, the bf16 storage level); the GroupNorm / attention kernels
-compile for sm_100a but have not run on a GPU yet (tests/test_gpu_vanilla.py, opt-in until their first device run).
+STATUS: not yet run on a GPU (tests/test_gpu_vanilla.py, opt-in until the first device run).  On CPU the unchanged product code
+over host builds of its CUDA-core kernels and a C-ABI level stand-in for ccdm_tapgemm reproduces the reference's own outputs
+(0.8-1.0 %, the bf16 storage level) and samples (40-49 dB): tests/test_vanilla_emulated.py, tests/test_sampling_hostpath.py.
 Training (``loss.backward()``) runs through ccdm_b200/vanilla_train.py.
 """
 from __future__ import annotations
