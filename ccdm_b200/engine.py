@@ -662,7 +662,9 @@ class UnetProgram(Program):
         for rep in range(B // xb):
             self.recs.append(TapGemmRec(f"init_conv.{rep}", splan, [nhwc_view(rowimg)], W, H, xb, tile_box(W, H), None,
                                         spack, s_sched, s_rows, co, s_tile, L.EPI_BIAS, stem[rep * xb:(rep + 1) * xb],
-                                        (co, W * co, H * W * co), bias=net.init_conv.bias))
+                                        (co, W * co, H * W * co), bias=net.init_conv.bias,
+                                        # the reference conv is 7x7 over in_channels (3), not over the 64-wide im2row K
+                                        algo_flops=2.0 * xb * H * W * co * net.in_channels * 49))
 
         # ---- down path (unet.py:425-433)
         x, h, w = stem, H, W

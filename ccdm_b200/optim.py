@@ -119,7 +119,14 @@ class FusedAdam(torch.optim.Optimizer):
                                         float(self.max_grad_norm or 0.0), float(g["lr"]), float(g["betas"][0]),
                                         float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
                                         torch.cuda.current_stream().cuda_stream), "fused_adam")
+        self.mark_params_modified()
         return loss
+
+    def mark_params_modified(self):
+        """The kernel writes the parameters through raw pointers, which autograd's version counters do not see; the
+        engines' packed bf16 weight caches are keyed on ``(data_ptr, _version)`` (engine.WeightStore.stamp), so bump
+        them here.  ``GraphedTrainStep`` calls this after every graph replay (no Python ``step`` runs there)."""
+        torch._C._increment_version(self._ps)
 
     # ------------------------------------------------------------------ checkpoints in torch.optim.Adam's layout
     def state_dict(self):
@@ -161,6 +168,7 @@ class MultiLerp:
                 sp.append(s.data_ptr() + 4 * c0)
                 ns.append(min(_CHUNK, d.numel() - c0))
         self.key = tuple(dp) + tuple(sp)
+        self._dst = list(dst)
         with torch.inference_mode(False):
             self.dp = torch.tensor(dp, dtype=torch.int64, device=dev)
             self.sp = torch.tensor(sp, dtype=torch.int64, device=dev)
@@ -171,3 +179,5 @@ class MultiLerp:
         self.w.fill_(float(weight))
         L.check(L.lib().ccdm_multi_lerp(self.dp.data_ptr(), self.sp.data_ptr(), self.ns.data_ptr(), self.ns.numel(),
                                         self.w.data_ptr(), torch.cuda.current_stream().cuda_stream), "multi_lerp")
+        # raw-pointer writes are invisible to autograd's version counters: invalidate the packed-weight caches
+        torch._C._increment_version(self._dst)

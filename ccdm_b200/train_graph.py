@@ -81,4 +81,7 @@ class GraphedTrainStep:
         self.labels.copy_(labels, non_blocking=True)
         self.labels_emb.copy_(labels_emb, non_blocking=True)
         self.graph.replay()
+        # the replayed optimizer kernel wrote the parameters without any Python-side version bump: the eval engines'
+        # packed-weight caches (keyed on _version) must see the change
+        torch._C._increment_version(self.params)
         return self.loss

@@ -371,3 +371,53 @@ def test_trainer_train_runs_optimizer_steps(tmp_path):
     assert float(tr.opt.step_count.item()) == 3.0
     ema_p = torch.cat([p.detach().flatten() for p in tr.ema.ema_model.parameters()])
     assert torch.isfinite(ema_p).all()
+
+
+def test_packed_weight_cache_follows_fused_updates():
+    """FusedAdam / MultiLerp write parameters through raw pointers; the eval engine's packed bf16 weight
+    cache is keyed on (data_ptr, _version) and must be invalidated by them.  eval forward -> fused step / EMA lerp ->
+    eval forward again must equal a freshly built engine on the updated weights."""
+    from ccdm_b200.optim import FusedAdam
+    from ccdm_b200.ema import EMA
+    spec = SPECS["tiny"]
+    net, _ = make_net(spec, 3)
+    net.eval()
+    x, t, emb = (v.cuda() for v in unet_inputs("tiny"))
+    with torch.no_grad():
+        y0 = net(x, t, emb, cond_drop_prob=0.0).clone()
+    # ---- fused optimizer step on synthetic gradients
+    opt = FusedAdam(net.parameters(), lr=5e-2, betas=(0.9, 0.99), max_grad_norm=None)
+    opt.zero_grad()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for p in net.parameters():
+        p.grad.add_(torch.randn(p.shape, device="cuda", generator=g))
+    opt.step()
+    with torch.no_grad():
+        y1 = net(x, t, emb, cond_drop_prob=0.0).clone()
+    net2, _ = make_net(spec, 3)
+    net2.load_state_dict(net.state_dict())
+    net2.eval()
+    with torch.no_grad():
+        y1_fresh = net2(x, t, emb, cond_drop_prob=0.0)
+    assert relerr(y1, y0) > 1e-2, "the optimizer step must change the output"
+    assert relerr(y1, y1_fresh) < 1e-6, relerr(y1, y1_fresh)
+    # ---- EMA lerp into a model whose engine already exists
+    ema = EMA(net, beta=0.5, update_after_step=0, update_every=1)
+    ema.ema_model.eval()
+    with torch.no_grad():
+        e0 = ema.ema_model(x, t, emb, cond_drop_prob=0.0).clone()
+    for _ in range(3):                                   # step 0 copies, later steps lerp through ccdm_multi_lerp
+        opt.zero_grad()
+        for p in net.parameters():
+            p.grad.add_(torch.randn(p.shape, device="cuda", generator=g))
+        opt.step()
+        ema.update()
+    with torch.no_grad():
+        e1 = ema.ema_model(x, t, emb, cond_drop_prob=0.0).clone()
+    net3, _ = make_net(spec, 3)
+    net3.load_state_dict(ema.ema_model.state_dict())
+    net3.eval()
+    with torch.no_grad():
+        e1_fresh = net3(x, t, emb, cond_drop_prob=0.0)
+    assert relerr(e1, e0) > 1e-3
+    assert relerr(e1, e1_fresh) < 1e-6, relerr(e1, e1_fresh)
