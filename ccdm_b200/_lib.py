@@ -87,6 +87,10 @@ SIGNATURES = {
     "ccdm_kexp_bound": (C.c_int, [vp, i32, i32, i32, i32, vp, vp]),
     "ccdm_linattn_fold": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "ccdm_attention_small": (C.c_int, [vp, vp, i32, i32, i32, i32, f32, vp]),
+    "ccdm_linattn_fused_units": (C.c_int, [i32]),
+    "ccdm_linattn_kv_partials": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "ccdm_linattn_fold_partials": (C.c_int, [vp, vp, i32, i32, vp, i32, i32, vp, vp]),
+    "ccdm_linattn_q_out": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, f32, f32, vp, vp]),
     "ccdm_linear_small": (C.c_int, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, i64, vp]),
     "ccdm_time_features": (C.c_int, [vp, i32, i32, vp, vp]),
     "ccdm_select_null": (C.c_int, [vp, vp, i32, vp, i32, i32, vp]),

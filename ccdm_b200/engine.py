@@ -117,6 +117,12 @@ def parity_views(t: torch.Tensor) -> List[ViewRec]:
     return out
 
 
+def fused_linattn_ok(training: bool, heads: int, C: int, n: int) -> bool:
+    """Shapes the fused inference kernels of csrc/linattn_fused.cu cover: a pure function of the layer (never of the batch
+    size), so the choice cannot break batch-shard invariance."""
+    return (not training) and heads == 4 and C <= 128 and C % 8 == 0 and n >= 256 and n % 128 == 0
+
+
 class Program:
     """A flat list of records plus their pre-filled ctypes argument structs."""
 
@@ -229,6 +235,15 @@ def _make_call(lib, r, keep):
     if k == "linattn_fold":
         return lib.ccdm_linattn_fold, (p(a["w_out"]), p(a["ctx"]), p(a["wfold"]), a["B"], a["C"], a["n_rows"],
                                        a["heads"]), k
+    if k == "linattn_kv_partials":
+        return lib.ccdm_linattn_kv_partials, (p(a["x"]), a["B"], a["n"], a["C"], p(a["rowss"]), p(a["wqkv"]), p(a["kbias"]),
+                                              p(a["part"]), p(a["psum"])), k
+    if k == "linattn_fold_partials":
+        return lib.ccdm_linattn_fold_partials, (p(a["part"]), p(a["psum"]), a["B"], a["ups"], p(a["w_out"]), a["C"],
+                                                a["n_rows"], p(a["wfold"])), k
+    if k == "linattn_q_out":
+        return lib.ccdm_linattn_q_out, (p(a["x"]), a["B"], a["n"], a["C"], p(a["rowss"]), p(a["wqkv"]), p(a["wfold"]),
+                                        a["n_rows"], p(a["bias"]), p(a["gain"]), a["gain_mul"], a["q_scale"], p(a["out"])), k
     if k == "attention_small":
         return lib.ccdm_attention_small, (p(a["qkv"]), p(a["out"]), a["B"], a["n"], a["heads"], a["dim_head"],
                                           a["scale"]), k
@@ -526,6 +541,8 @@ class UnetProgram(Program):
         heads, hid = att.heads, att.heads * att.dim_head
         assert att.dim_head == 32, "linear attention kernels are written for dim_head == 32 (unet.py:190)"
         n = h * w
+        if fused_linattn_ok(self.training, heads, C, n):
+            return self._linear_attention_fused(name, pre, att, x, rowss, h, w)
         qkv = self.act(name + ".qkv", h, w, 3 * hid)
         rec = self.conv(name + ".to_qkv", "1x1", [x], att.to_qkv, qkv, L.EPI_ROWSCALE | L.EPI_QSOFTMAX | L.EPI_KEXP,
                         rowss=rowss, cin_gain=pre.norm.g, cin_gain_mul=math.sqrt(C), q=(att.scale, hid))
@@ -577,6 +594,32 @@ class UnetProgram(Program):
         if wide:
             self.kernel("rmsnorm_act", z=dst, out=out, rows=self.B * h * w, C=C, rows_per_sample=h * w,
                         gain=norm_out.g, gain_mul=math.sqrt(C), resid=x, flags=L.EPI_RESID)
+        return out
+
+    def _linear_attention_fused(self, name, pre, att, x, rowss, h, w):
+        """Inference path for C <= 128 and n % 128 == 0 (csrc/linattn_fused.cu): x is read twice, q | k | v never reach HBM.
+        kv-kernel -> per-unit context partials -> fold into to_out's weight -> q-kernel with the output projection, the
+        RMSNorm and the residual in its epilogue."""
+        C, n, hid = x.shape[3], h * w, att.heads * att.dim_head
+        plan = plan_conv("1x1", [C], 3 * hid)
+        n_rows_w, _ = n_tiling(3 * hid, False)
+        pack = self.weights.add(f"{name}.to_qkv/R{plan.R}", att.to_qkv.weight, plan, n_rows_w, pre.norm.g, math.sqrt(C))
+        kbias = self.weights.kexp_bias(pack, hid, 2 * hid)
+        ups = L.lib().ccdm_linattn_fused_units(n)
+        assert ups > 0
+        part = self.buf(name + ".ctx_part", (self.B * ups, 128, 32), torch.float32)
+        psum = self.buf(name + ".ctx_psum", (self.B * ups, 128), torch.float32)
+        conv_out, norm_out = att.to_out[0], att.to_out[1]
+        n_rows, _ = n_tiling(C, True)
+        wfold = self.buf(name + ".wfold", (self.B * n_rows, hid), torch.bfloat16)
+        wfold.zero_()                                       # rows [C, n_rows) are padding and must stay zero
+        out = self.act(name + ".out", h, w, C)
+        self.kernel("linattn_kv_partials", x=x, B=self.B, n=n, C=C, rowss=rowss, wqkv=pack.packed, kbias=kbias, part=part,
+                    psum=psum)
+        self.kernel("linattn_fold_partials", part=part, psum=psum, B=self.B, ups=ups, w_out=conv_out.weight, C=C,
+                    n_rows=n_rows, wfold=wfold)
+        self.kernel("linattn_q_out", x=x, B=self.B, n=n, C=C, rowss=rowss, wqkv=pack.packed, wfold=wfold, n_rows=n_rows,
+                    bias=conv_out.bias, gain=norm_out.g, gain_mul=math.sqrt(C), q_scale=att.scale, out=out)
         return out
 
     def mid_attention(self, name, mod, x, rowss, h, w):

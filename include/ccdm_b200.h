@@ -150,6 +150,28 @@ int ccdm_linattn_fold(const float* w_out, const float* ctx, void* wfold, int32_t
 int ccdm_attention_small(const void* qkv, void* out, int32_t B, int32_t n, int32_t heads, int32_t dim_head,
                          float scale, void* stream);
 
+/* Fused linear attention for inference (heads == 4, dim_head == 32, C <= 128 channels, n a multiple of 128 tokens):
+ * Residual(PreNorm(LinearAttention)) of unet.py:66-72,92-99,202-216 without q | k | v ever reaching HBM.
+ *   x      bf16 [B][n][C] token rows (NHWC), rowss fp32 [B*n] their sums of squares (the producing conv's
+ *          CCDM_EPI_SUMSQ_OUT), wqkv the packed to_qkv weight [384][ceil(C/64)*64] with the PreNorm gain folded in
+ *          (ccdm_pack_weights, cin_gain), kbias [384] the k rows' softmax shifts (ccdm_kexp_bound).
+ * ccdm_linattn_kv_partials: per UNIT (ccdm_linattn_fused_units(n) per sample, a fixed run of 128-token tiles) the
+ *   un-normalised context  part[b][u][h*32+d][e] = sum_{n in unit} p[n,d] v[n,e],  psum[b][u][h*32+d] = sum p[n,d]
+ *   with p = exp(k/|x| - bound), v = v/|x|   (bf16-rounded, fp32 accumulation in TMEM).
+ * ccdm_linattn_fold_partials: sums the units in a fixed order, divides by psum (softmax over tokens, unet.py:208) and
+ *   folds the context into to_out[0]:  wfold[b][c][h*32+d] = sum_e w_out[c][h*32+e] ctx[b][h][d][e]  (bf16, rows >= C
+ *   untouched: keep them zero).
+ * ccdm_linattn_q_out: out = RMSNorm_g( softmax_d(q)*q_scale . wfold_b^T + bias ) * gain_mul + x, bf16 [B][n][C].
+ * Results are independent of the batch size (no atomics, fixed summation order). */
+int ccdm_linattn_fused_units(int32_t n);
+int ccdm_linattn_kv_partials(const void* x, int32_t B, int32_t n, int32_t C, const float* rowss, const void* wqkv,
+                             const float* kbias, float* part, float* psum, void* stream);
+int ccdm_linattn_fold_partials(const float* part, const float* psum, int32_t B, int32_t units_per_sample,
+                               const float* w_out, int32_t C, int32_t n_rows, void* wfold, void* stream);
+int ccdm_linattn_q_out(const void* x, int32_t B, int32_t n, int32_t C, const float* rowss, const void* wqkv,
+                       const void* wfold, int32_t n_rows, const float* bias, const float* gain, float gain_mul,
+                       float q_scale, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Embedding MLPs (unet.py:102-115 sinusoid, :289-312 time / label MLPs with BatchNorm1d, :397-414 null-label
  * select, :158-161 SiLU in front of every tc_mlp).  fp32, batch-sized.

@@ -140,6 +140,8 @@ def run_kernel(r: KernelRec):
         if a.get("wfold") is not None:
             run_kernel(KernelRec("linattn_fold", dict(w_out=a["w_out"], ctx=a["ctx"], wfold=a["wfold"], B=B, C=a["C"],
                                                      n_rows=a["n_rows"], heads=heads)))
+    elif k in ("linattn_kv_partials", "linattn_fold_partials", "linattn_q_out"):
+        run_linattn_fused(k, a)
     elif k == "kexp_bound":
         w = a["wpacked"].float().reshape(a["n_rows"], a["K"])
         bias = a["bias"]
@@ -271,3 +273,63 @@ def run_program(prog, weights):
     if hasattr(prog, "glue_out"):
         prog.glue_out()
     return prog.out
+
+
+def linattn_fused_units(n: int) -> int:
+    """ccdm_linattn_fused_units: units per sample = tiles / (largest divisor of the tile count that is <= 8)."""
+    if n <= 0 or n % 128:
+        return 0
+    tps = n // 128
+    g = next(g for g in range(8, 0, -1) if tps % g == 0)
+    return tps // g
+
+
+def linattn_kv_partials_emu(x, rowss, wqkv, kbias, B, n, C):
+    """x bf16 [B, n, C] (any shape with that many elements), wqkv bf16 [384, K] -> (part [B*ups,128,32], psum [B*ups,128])."""
+    xf = x.float().reshape(B, n, C)
+    K = wqkv.shape[1]
+    w = wqkv.float()[:, :C]
+    rs = 1.0 / rowss.reshape(B, n, 1).sqrt().clamp_min(1e-12)
+    k = xf @ w[128:256].t()
+    v = xf @ w[256:384].t()
+    p = torch.exp2((k * (rs * 1.4426950408889634)) + kbias[128:256].float() * 1.4426950408889634)
+    p = p.to(torch.bfloat16).float()
+    v = (v * rs).to(torch.bfloat16).float()
+    ups = linattn_fused_units(n)
+    pu = p.reshape(B, ups, n // ups, 4, 32)
+    vu = v.reshape(B, ups, n // ups, 4, 32)
+    part = torch.einsum("buthd,buthe->buhde", pu, vu).reshape(B * ups, 128, 32)
+    psum = pu.sum(2).reshape(B * ups, 128)
+    return part, psum
+
+
+def linattn_fold_partials_emu(part, psum, B, ups, w_out, C):
+    ctx = part.reshape(B, ups, 4, 32, 32).sum(1) / psum.reshape(B, ups, 4, 32).sum(1)[..., None]     # [b, h, d, e]
+    w = w_out.detach().float().reshape(C, 4, 32)
+    return torch.einsum("che,bhde->bchd", w, ctx).reshape(B, C, 128).to(torch.bfloat16)
+
+
+def linattn_q_out_emu(x, rowss, wqkv, wfold, B, n, C, n_rows, bias, gain, gain_mul, q_scale):
+    xf = x.float().reshape(B, n, C)
+    w = wqkv.float()[:128, :C]
+    rs = 1.0 / rowss.reshape(B, n, 1).sqrt().clamp_min(1e-12)
+    q = ((xf @ w.t()) * rs).reshape(B, n, 4, 32).softmax(-1) * q_scale
+    q = q.reshape(B, n, 128).to(torch.bfloat16).float()
+    wf = wfold.float().reshape(B, n_rows, 128)[:, :C]
+    y = torch.einsum("bnk,bck->bnc", q, wf) + bias.detach().float()
+    y = y / y.pow(2).sum(-1, keepdim=True).sqrt().clamp_min(1e-12) * (gain.detach().reshape(-1).float() * gain_mul)
+    return (y + xf).to(torch.bfloat16)
+
+
+def run_linattn_fused(k, a):
+    if k == "linattn_kv_partials":
+        part, psum = linattn_kv_partials_emu(a["x"], a["rowss"], a["wqkv"], a["kbias"], a["B"], a["n"], a["C"])
+        a["part"].copy_(part)
+        a["psum"].copy_(psum)
+    elif k == "linattn_fold_partials":
+        wf = linattn_fold_partials_emu(a["part"], a["psum"], a["B"], a["ups"], a["w_out"], a["C"])
+        a["wfold"].reshape(a["B"], a["n_rows"], 128)[:, :a["C"]] = wf
+    else:
+        o = linattn_q_out_emu(a["x"], a["rowss"], a["wqkv"], a["wfold"], a["B"], a["n"], a["C"], a["n_rows"], a["bias"],
+                              a["gain"], a["gain_mul"], a["q_scale"])
+        a["out"].copy_(o.reshape(a["out"].shape))

@@ -16,7 +16,8 @@ from ccdm_b200 import _lib as L
 from ccdm_b200.engine import TapGemmRec, ViewRec
 from ccdm_b200.plan import KB
 from tests.emu import shifted
-from tests.emu_engine import _view_tensor, run_tapgemm
+from tests.emu_engine import (_view_tensor, run_tapgemm, linattn_fused_units, linattn_kv_partials_emu,
+                              linattn_q_out_emu)
 from tests.hostsim.build import build, build_extract
 
 
@@ -35,6 +36,7 @@ class HostLib:
                                             ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"])))
         handles.append(C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights"])))
         handles.append(C.CDLL(build_extract("linattn.cu", ["kexp_bound_kernel"], ["ccdm_kexp_bound"])))
+        handles.append(C.CDLL(build_extract("linattn_fused.cu", ["linattn_fold_parts_kernel"], ["ccdm_linattn_fold_partials"])))
         for name, (res, args) in L.SIGNATURES.items():
             for h in handles:
                 fn = getattr(h, name, None)
@@ -48,6 +50,9 @@ class HostLib:
         self.ccdm_conv_wgrad = wgrad_abi
         self.ccdm_linattn_context = linattn_context_abi
         self.ccdm_linattn_dcontext = linattn_dcontext_abi
+        self.ccdm_linattn_fused_units = linattn_fused_units
+        self.ccdm_linattn_kv_partials = linattn_kv_partials_abi
+        self.ccdm_linattn_q_out = linattn_q_out_abi
 
 
 # ------------------------------------------------------------------------------------------------- C-ABI level ccdm_tapgemm
@@ -118,6 +123,29 @@ def linattn_context_abi(qkv, ctx, colsum, b, n, heads, w_out, wfold, c, n_rows, 
         dst = _flat(wfold, b * n_rows * heads * 32, torch.bfloat16).reshape(b, n_rows, heads * 32)
         dst.zero_()
         dst[:, :c] = wf.to(torch.bfloat16)
+    return 0
+
+
+def linattn_kv_partials_abi(x, b, n, c, rowss, wqkv, kbias, part, psum, stream):
+    """ccdm_linattn_kv_partials (tcgen05, linattn_fused.cu) from its raw pointers."""
+    nkb = (c + 63) // 64
+    ups = linattn_fused_units(n)
+    pt, ps = linattn_kv_partials_emu(_flat(x, b * n * c, torch.bfloat16), _flat(rowss, b * n, torch.float32),
+                                     _flat(wqkv, 384 * nkb * 64, torch.bfloat16).reshape(384, nkb * 64),
+                                     _flat(kbias, 384, torch.float32), b, n, c)
+    _flat(part, b * ups * 128 * 32, torch.float32).copy_(pt.reshape(-1))
+    _flat(psum, b * ups * 128, torch.float32).copy_(ps.reshape(-1))
+    return 0
+
+
+def linattn_q_out_abi(x, b, n, c, rowss, wqkv, wfold, n_rows, bias, gain, gain_mul, q_scale, out, stream):
+    """ccdm_linattn_q_out (tcgen05, linattn_fused.cu) from its raw pointers."""
+    nkb = (c + 63) // 64
+    o = linattn_q_out_emu(_flat(x, b * n * c, torch.bfloat16), _flat(rowss, b * n, torch.float32),
+                          _flat(wqkv, 384 * nkb * 64, torch.bfloat16).reshape(384, nkb * 64),
+                          _flat(wfold, b * n_rows * 128, torch.bfloat16), b, n, c, n_rows, _flat(bias, c, torch.float32),
+                          _flat(gain, c, torch.float32), gain_mul, q_scale)
+    _flat(out, b * n * c, torch.bfloat16).copy_(o.reshape(-1))
     return 0
 
 

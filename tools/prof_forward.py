@@ -28,7 +28,20 @@ def main():
     for _ in range(a.iters):
         eng.forward_pair(x, t, emb)
     torch.cuda.synchronize()
-    print("ok")
+    # record names in launch order (one launch per record): join with an ncu launch list via tools/ncu_layers.py
+    import json
+    from ccdm_b200.engine import TapGemmRec, tapgemm_flops
+    prog = eng.program(2 * B, B, 64, 64, False)
+    recs = []
+    for r in prog.recs:
+        if isinstance(r, TapGemmRec):
+            recs.append({"name": r.name, "kind": r.plan.kind, "flops": tapgemm_flops(r), "grid": [r.gB, r.gH, r.gW],
+                         "cin": sum(r.plan.cins), "N": r.N})
+        else:
+            recs.append({"name": r.kind, "kind": "kernel"})
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(recs, open(os.path.join(ROOT, "gpurun_out", "forward_recs.json"), "w"))
+    print("ok", len(recs), "records per forward")
 
 
 if __name__ == "__main__":
