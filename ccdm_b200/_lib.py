@@ -115,6 +115,7 @@ SIGNATURES = {
     "ccdm_attention_small_bwd": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "ccdm_head_conv1_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "ccdm_stem_unpack_wgrad": (C.c_int, [vp, vp, i32, i32, i32, vp]),
+    "ccdm_gather_augment_u8": (C.c_int, [vp, i64, vp, vp, vp, i32, i32, i32, i32, vp]),
     "ccdm_condbn_coef": (C.c_int, [vp, vp, vp, vp, vp, vp, f32, i32, i32, vp, vp]),
     "ccdm_affine_act": (C.c_int, [vp, vp, i64, i32, i32, vp, i32, i32, i32, vp]),
     "ccdm_channel_stats": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, vp]),

@@ -17,7 +17,10 @@
 // Units never straddle CTAs and their partials are summed in a fixed order, so the result does not depend on how many
 // samples are in the batch (batch-shard invariance, bit-exact) -- no atomics anywhere.
 //
-// Warp roles (both tensor kernels): warp 0 TMA producer, warp 1 tcgen05 issuer, warps 2..9 epilogue.
+// Warp roles (both tensor kernels): warp 0 TMA producer, warp 1 issues the first GEMM (x W^T), warps 2..17 epilogue, warp 18
+// issues the second GEMM (context / output projection): the single issuing lane is a serial chain of uniform-datapath
+// instructions (~100 cycles per MMA), so the two GEMMs get one issuing warp each.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -28,7 +31,10 @@ namespace ccdm {
 int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
                     const cuuint32_t* box);
 
-constexpr int kLaThreads = 320;
+constexpr int kLaEpiWarps = 16;                 // four warps per TMEM lane quarter: latency-bound epilogues need the occupancy
+constexpr int kLaThreads = 64 + 32 * kLaEpiWarps + 32;         // kv kernel: warp 0 TMA, warp 1 GEMM1, 16 epilogue warps, last warp GEMM2
+constexpr int kLaMma2Warp = kLaThreads / 32 - 1;
+constexpr int kLa2Threads = 64 + 32 * kLaEpiWarps;             // q-out kernel: one issuing warp (a second one measured no gain)
 constexpr int kLaTok = 128;                     // tokens per tile = UMMA M
 constexpr int kLaBlk = kLaTok * 128;            // one {64 channels x 128 tokens} shared-memory block: 16 KiB
 constexpr int kLaMaxStages = 4;
@@ -45,7 +51,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
-__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+// MN-major SWIZZLE_128B descriptor from a low word that already holds (address >> 4) | (LBO >> 4) << 16: advancing by k
+// tokens' worth of bytes is one integer add on the low word; the high word (SBO = 1024 B, version, layout) is constant.
+__device__ __forceinline__ uint64_t umma_desc_mn_lo(uint32_t lo) {
+  constexpr uint64_t hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                          (static_cast<uint64_t>(2) << 61);
+  return hi | lo;
+}
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
 
 // ============================================================================ kernel 1: x -> per-unit context partials
 
@@ -89,12 +102,12 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_kv_kernel(const __grid_
     mbar_init(&aux->w_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&aux->d1_full[s], 1);
-      mbar_init(&aux->d1_empty[s], 8);
-      mbar_init(&aux->pv_full[s], 8);
+      mbar_init(&aux->d1_empty[s], kLaEpiWarps);
+      mbar_init(&aux->pv_full[s], kLaEpiWarps);
       mbar_init(&aux->pv_empty[s], 1);
     }
     mbar_init(&aux->d2_full, 1);
-    mbar_init(&aux->d2_empty, 8);
+    mbar_init(&aux->d2_empty, kLaEpiWarps);
     fence_mbar_init();
   }
   for (int i = tid; i < kLaBlk / 4; i += kLaThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;   // bf16 1.0
@@ -138,52 +151,24 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_kv_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ================================================================ tcgen05 issuer
-    const uint32_t idesc1 = umma_idesc_bf16(128, 128);             // [k | v] item: 128 tokens x 128 channels, K-major
-    const uint32_t idesc_ctx = umma_idesc_bf16_mn(128, 128);       // P^T V, both operands token-major
-    const uint32_t idesc_sum = umma_idesc_bf16_mn(128, 16);        // P^T 1
-    const uint32_t ones_addr = smem_u32(ones);
+    // ================================================================ GEMM1 issuer: [k | v] = x W'^T, two 128-column items
+    const uint32_t idesc1 = umma_idesc_bf16(128, 128);             // 128 tokens x 128 channels, both operands K-major
     mbar_wait(&aux->w_full, 0);
     tc_fence_after();
-    auto gemm2 = [&](int t) {                                      // context MMAs of local tile t
-      const int tl = t % p.G, ul = t / p.G;
-      const int buf = t % p.pv_bufs;
-      const uint32_t use = static_cast<uint32_t>(t / p.pv_bufs);
-      if (tl == 0) {                                               // new unit: the previous unit's D2 must have been read
-        mbar_wait(&aux->d2_empty, (static_cast<uint32_t>(ul) & 1u) ^ 1u);
-        tc_fence_after();
-      }
-      mbar_wait(&aux->pv_full[buf], use & 1u);
-      tc_fence_after();
-      const uint32_t base = smem_u32(stg + static_cast<size_t>(buf) * 4 * kLaBlk);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < kLaTok / 16; ++k) {
-          const uint64_t adesc = umma_desc_mn_sw128(base + k * 2048, kLaBlk);                // P^T (128 channels)
-          const uint64_t bdesc = umma_desc_mn_sw128(base + 2 * kLaBlk + k * 2048, kLaBlk);   // V   (128 channels)
-          const uint64_t odesc = umma_desc_mn_sw128(ones_addr + k * 2048, kLaBlk);
-          const uint32_t acc = (tl | k) != 0 ? 1u : 0u;
-          umma_bf16_ss(tmem_base + d2_col, adesc, bdesc, idesc_ctx, acc);
-          umma_bf16_ss(tmem_base + ds_col, adesc, odesc, idesc_sum, acc);
-        }
-        umma_commit(&aux->pv_empty[buf]);
-        if (tl == p.G - 1) umma_commit(&aux->d2_full);
-      }
-      __syncwarp();
-    };
+    const uint32_t w16 = (smem_u32(wres) & 0x3FFFF) >> 4;
     int s = 0;
     uint32_t ph = 0;
     for (int li = 0; li < n_tiles; ++li) {
       mbar_wait(&aux->x_full[s], ph);
       tc_fence_after();
-      const uint32_t xa = smem_u32(xring + static_cast<size_t>(s) * x_stage_bytes);
+      const uint32_t x16 = (smem_u32(xring + static_cast<size_t>(s) * x_stage_bytes) & 0x3FFFF) >> 4;
       for (int j = 0; j < 2; ++j) {
         mbar_wait(&aux->d1_empty[j], (static_cast<uint32_t>(li) & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one()) {
           for (int kb = 0; kb < p.nkb; ++kb) {
-            const uint32_t a16 = ((xa + kb * kLaBlk) & 0x3FFFF) >> 4;
-            const uint32_t b16 = ((smem_u32(wres) + (kb * 2 + j) * kLaBlk) & 0x3FFFF) >> 4;
+            const uint32_t a16 = x16 + kb * (kLaBlk >> 4);
+            const uint32_t b16 = w16 + (kb * 2 + j) * (kLaBlk >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16_ss(tmem_base + j * 128, umma_desc_sw128_a16(a16 + 2 * k), umma_desc_sw128_a16(b16 + 2 * k), idesc1,
@@ -194,45 +179,82 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_kv_kernel(const __grid_
         }
         __syncwarp();
       }
-      if (li > 0) gemm2(li - 1);
       if (++s == p.x_stages) { s = 0; ph ^= 1u; }
     }
-    if (n_tiles > 0) gemm2(n_tiles - 1);
-  } else {
-    // ================================================================ epilogue (8 warps: 128 rows x 2 column halves)
+  } else if (warp == kLaMma2Warp) {
+    // ================================================================ GEMM2 issuer: D2 += P^T V, S += P^T 1 per tile
+    const uint32_t idesc_ctx = umma_idesc_bf16_mn(128, 128);       // both operands token-major (MN-major)
+    const uint32_t idesc_sum = umma_idesc_bf16_mn(128, 16);
+    const uint32_t lbo = static_cast<uint32_t>(kLaBlk >> 4) << 16;
+    const uint32_t ones_lo = ((smem_u32(ones) & 0x3FFFF) >> 4) | lbo;
+    const uint32_t stg_lo = ((smem_u32(stg) & 0x3FFFF) >> 4) | lbo;
+    int buf = 0, tl = 0;
+    uint32_t use = 0, ul = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      if (tl == 0) {                                               // new unit: the previous unit's D2 must have been read
+        mbar_wait(&aux->d2_empty, (ul & 1u) ^ 1u);
+        tc_fence_after();
+      }
+      mbar_wait(&aux->pv_full[buf], use & 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t p_lo = stg_lo + buf * (4 * kLaBlk >> 4);    // P^T: blocks 0, 1; V: blocks 2, 3 of the staging buffer
+        const uint32_t v_lo = p_lo + (2 * kLaBlk >> 4);
+#pragma unroll
+        for (int k = 0; k < kLaTok / 16; ++k) {
+          const uint32_t acc = (tl | k) != 0 ? 1u : 0u;
+          const uint64_t adesc = umma_desc_mn_lo(p_lo + k * (2048 >> 4));
+          umma_bf16_ss(tmem_base + d2_col, adesc, umma_desc_mn_lo(v_lo + k * (2048 >> 4)), idesc_ctx, acc);
+          umma_bf16_ss(tmem_base + ds_col, adesc, umma_desc_mn_lo(ones_lo + k * (2048 >> 4)), idesc_sum, acc);
+        }
+        umma_commit(&aux->pv_empty[buf]);
+        if (tl == p.G - 1) umma_commit(&aux->d2_full);
+      }
+      __syncwarp();
+      if (++buf == p.pv_bufs) { buf = 0; ++use; }
+      if (++tl == p.G) { tl = 0; ++ul; }
+    }
+  } else if (warp < 2 + kLaEpiWarps) {
+    // ================================================================ epilogue (16 warps: 128 rows x 4 column quarters)
     const int ew = warp - 2;
     const int q = warp & 3;                                        // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                                      // 64-channel half of every 128-channel item
+    const int cq = ew >> 2;                                        // 32-channel quarter of every 128-channel item
     const int m = q * 32 + lane;                                   // token row inside the tile
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int blk = cq >> 1, cc = cq & 1;                          // 64-channel staging block and its 32-channel half
     uint32_t r[32];
     int li = 0, pend_u = -1;
     uint32_t flushes = 0;
     auto flush = [&](int u) {                                      // D2 / S of a finished unit -> global partials
       mbar_wait(&aux->d2_full, flushes & 1u);
       tc_fence_after();
-      uint32_t sv[32];
-      tmem_ld32(trow + d2_col + q * 32, r);                        // head q: rows q*32+d, columns q*32 + e
-      tmem_ld32(trow + ds_col, sv);                                // every column of S holds sum_n p[n][q*32+d]
-      tmem_ld_wait();
+      if (cq == 0) {
+        tmem_ld32(trow + d2_col + q * 32, r);                      // head q: rows q*32+d, columns q*32 + e
+        tmem_ld_wait();
+        float4* o = reinterpret_cast<float4*>(p.part + (static_cast<long long>(u) * 128 + m) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                             __uint_as_float(r[4 * j + 3]));
+      } else if (cq == 1) {
+        tmem_ld32(trow + ds_col, r);                               // every column of S holds sum_n p[n][q*32+d]
+        tmem_ld_wait();
+        p.psum[static_cast<long long>(u) * 128 + m] = __uint_as_float(r[0]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&aux->d2_empty);
-      float4* o = reinterpret_cast<float4*>(p.part + (static_cast<long long>(u) * 128 + m) * 32 + half * 16);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o[j] = make_float4(__uint_as_float(r[half * 16 + 4 * j]), __uint_as_float(r[half * 16 + 4 * j + 1]),
-                           __uint_as_float(r[half * 16 + 4 * j + 2]), __uint_as_float(r[half * 16 + 4 * j + 3]));
-      if (half == 0) p.psum[static_cast<long long>(u) * 128 + m] = __uint_as_float(sv[0]);
       ++flushes;
     };
+    int buf = 0;
+    uint32_t use = 0;                                              // how often the current staging buffer has been used
+    const float* rsp = p.rowss + static_cast<long long>(u_begin) * p.G * kLaTok + m;   // units are contiguous token runs
+    float rss_next = n_tiles > 0 ? __ldg(rsp) : 1.f;
     for (int u = u_begin; u < u_end; ++u) {
-      const int b = u / p.ups, tile0 = (u % p.ups) * p.G;
       for (int tl = 0; tl < p.G; ++tl, ++li) {
-        const long long row = static_cast<long long>(b) * p.n + static_cast<long long>(tile0 + tl) * kLaTok + m;
-        const float rs = 1.f / fmaxf(sqrtf(__ldg(p.rowss + row)), 1e-12f);
-        const int buf = li % p.pv_bufs;
-        const uint32_t use = static_cast<uint32_t>(li / p.pv_bufs);
+        const float rs = 1.f / fmaxf(sqrtf(rss_next), 1e-12f);
+        rsp += kLaTok;
+        if (li + 1 < n_tiles) rss_next = __ldg(rsp);               // next tile's row norm: its latency hides behind this tile
         uint8_t* sb = stg + static_cast<size_t>(buf) * 4 * kLaBlk + m * 128;
         mbar_wait(&aux->pv_empty[buf], (use & 1u) ^ 1u);           // the context MMAs that read this buffer are done
         // ---- item 0: p = exp(k / |x| - bound) = 2^(acc * rs*log2e + kbias)
@@ -240,33 +262,28 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_kv_kernel(const __grid_
         tc_fence_after();
         {
           const float2 rs2 = make_float2(rs * kLog2e, rs * kLog2e);
+          tmem_ld32(trow + cq * 32, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&aux->d1_empty[0]);
+          const float2* kb2 = reinterpret_cast<const float2*>(aux->kbias + cq * 32);
+          uint8_t* dst = sb + (0 + blk) * kLaBlk;
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            tmem_ld32(trow + (half * 2 + cc) * 32, r);
-            tmem_ld_wait();
-            if (cc == 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&aux->d1_empty[0]);
+          for (int g = 0; g < 4; ++g) {
+            float2 e[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 a = make_float2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1]));
+              const float2 x2 = __ffma2_rn(a, rs2, kb2[g * 4 + i]);
+              e[i] = make_float2(ex2_fast(x2.x), ex2_fast(x2.y));
             }
-            const float2* kb2 = reinterpret_cast<const float2*>(aux->kbias + (half * 2 + cc) * 32);
-            uint8_t* dst = sb + (0 + half) * kLaBlk;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float2 e[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 a = make_float2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1]));
-                const float2 x2 = __ffma2_rn(a, rs2, kb2[g * 4 + i]);
-                e[i] = make_float2(ex2_fast(x2.x), ex2_fast(x2.y));
-              }
-              uint4 o;
-              o.x = pack_bf16(e[0].x, e[0].y);
-              o.y = pack_bf16(e[1].x, e[1].y);
-              o.z = pack_bf16(e[2].x, e[2].y);
-              o.w = pack_bf16(e[3].x, e[3].y);
-              *reinterpret_cast<uint4*>(dst + (((cc * 4 + g) ^ (m & 7)) << 4)) = o;
-            }
+            uint4 o;
+            o.x = pack_bf16(e[0].x, e[0].y);
+            o.y = pack_bf16(e[1].x, e[1].y);
+            o.z = pack_bf16(e[2].x, e[2].y);
+            o.w = pack_bf16(e[3].x, e[3].y);
+            *reinterpret_cast<uint4*>(dst + (((cc * 4 + g) ^ (m & 7)) << 4)) = o;
           }
         }
         // ---- item 1: v / |x|
@@ -274,34 +291,30 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_kv_kernel(const __grid_
         tc_fence_after();
         {
           const float2 rs2 = make_float2(rs, rs);
+          tmem_ld32(trow + 128 + cq * 32, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&aux->d1_empty[1]);
+          uint8_t* dst = sb + (2 + blk) * kLaBlk;
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            tmem_ld32(trow + 128 + (half * 2 + cc) * 32, r);
-            tmem_ld_wait();
-            if (cc == 1) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&aux->d1_empty[1]);
-            }
-            uint8_t* dst = sb + (2 + half) * kLaBlk;
+          for (int g = 0; g < 4; ++g) {
+            float2 e[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float2 e[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                e[i] = __fmul2_rn(make_float2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1])), rs2);
-              uint4 o;
-              o.x = pack_bf16(e[0].x, e[0].y);
-              o.y = pack_bf16(e[1].x, e[1].y);
-              o.z = pack_bf16(e[2].x, e[2].y);
-              o.w = pack_bf16(e[3].x, e[3].y);
-              *reinterpret_cast<uint4*>(dst + (((cc * 4 + g) ^ (m & 7)) << 4)) = o;
-            }
+            for (int i = 0; i < 4; ++i)
+              e[i] = __fmul2_rn(make_float2(__uint_as_float(r[g * 8 + 2 * i]), __uint_as_float(r[g * 8 + 2 * i + 1])), rs2);
+            uint4 o;
+            o.x = pack_bf16(e[0].x, e[0].y);
+            o.y = pack_bf16(e[1].x, e[1].y);
+            o.z = pack_bf16(e[2].x, e[2].y);
+            o.w = pack_bf16(e[3].x, e[3].y);
+            *reinterpret_cast<uint4*>(dst + (((cc * 4 + g) ^ (m & 7)) << 4)) = o;
           }
         }
         fence_proxy_async_smem();                                  // generic-proxy writes -> visible to the MMA unit
         __syncwarp();
         if (lane == 0) mbar_arrive(&aux->pv_full[buf]);
+        if (++buf == p.pv_bufs) { buf = 0; ++use; }
         // the previous unit's accumulators are read one tile late: its last context MMAs have finished by now
         if (pend_u >= 0) {
           flush(pend_u);
@@ -323,43 +336,74 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_kv_kernel(const __grid_
 // ============================================================================ kernel 2: partials -> folded weights
 
 // One CTA per sample, thread = (head h, channel d).  Sums the sample's unit partials in a fixed order, normalises by the
-// column sum S (softmax over tokens) and folds the context into to_out[0]'s weight (unet.py:198,212-216).
+// column sum S (softmax over tokens) and folds the context into to_out[0]'s weight (unet.py:198,212-216).  W_out is staged
+// in shared memory once per CTA (the first version read it through L1/L2 per output row and was latency-bound: 50-90 us);
+// four output rows are accumulated at a time so the FMA chains overlap.
 __global__ void __launch_bounds__(128) linattn_fold_parts_kernel(const float* __restrict__ part,
                                                                  const float* __restrict__ psum, int ups,
                                                                  const float* __restrict__ w_out, int C, int n_rows,
-                                                                 __nv_bfloat16* __restrict__ wfold) {
-  const int b = blockIdx.x, t = threadIdx.x;                       // t = h*32 + d
+                                                                 __nv_bfloat16* __restrict__ wfold, int B) {
+  extern __shared__ float fold_smem[];                             // [C][128] fp32 copy of W_out
+  const int t = threadIdx.x;                                       // t = h*32 + d
   const int h = t >> 5;
-  float cr[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) cr[e] = 0.f;
-  float s = 0.f;
-  for (int u = 0; u < ups; ++u) {
-    const long long ub = static_cast<long long>(b) * ups + u;
-    const float4* pr = reinterpret_cast<const float4*>(part + (ub * 128 + t) * 32);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 v = __ldg(pr + j);
-      cr[4 * j] += v.x; cr[4 * j + 1] += v.y; cr[4 * j + 2] += v.z; cr[4 * j + 3] += v.w;
-    }
-    s += __ldg(psum + ub * 128 + t);
+  {
+    const float4* src = reinterpret_cast<const float4*>(w_out);
+    float4* dst = reinterpret_cast<float4*>(fold_smem);
+    for (int i = t; i < C * 32; i += 128) dst[i] = __ldg(src + i);
   }
-  const float inv = 1.f / s;
+  __syncthreads();
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float cr[32];
 #pragma unroll
-  for (int e = 0; e < 32; ++e) cr[e] *= inv;
-  __nv_bfloat16* wf = wfold + static_cast<long long>(b) * n_rows * 128 + t;
-  for (int c = 0; c < C; ++c) {
-    const float4* wr = reinterpret_cast<const float4*>(w_out + static_cast<long long>(c) * 128 + h * 32);
-    float acc = 0.f;
+    for (int e = 0; e < 32; ++e) cr[e] = 0.f;
+    float s = 0.f;
+    for (int u = 0; u < ups; ++u) {
+      const long long ub = static_cast<long long>(b) * ups + u;
+      const float4* pr = reinterpret_cast<const float4*>(part + (ub * 128 + t) * 32);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 wv = __ldg(wr + j);
-      acc = fmaf(wv.x, cr[4 * j], acc);
-      acc = fmaf(wv.y, cr[4 * j + 1], acc);
-      acc = fmaf(wv.z, cr[4 * j + 2], acc);
-      acc = fmaf(wv.w, cr[4 * j + 3], acc);
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = __ldg(pr + j);
+        cr[4 * j] += v.x; cr[4 * j + 1] += v.y; cr[4 * j + 2] += v.z; cr[4 * j + 3] += v.w;
+      }
+      s += __ldg(psum + ub * 128 + t);
     }
-    wf[static_cast<long long>(c) * 128] = __float2bfloat16(acc);
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) cr[e] *= inv;
+    __nv_bfloat16* wf = wfold + static_cast<long long>(b) * n_rows * 128 + t;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float4* w0 = reinterpret_cast<const float4*>(fold_smem + (c + 0) * 128 + h * 32);   // warp-uniform: broadcast reads
+      const float4* w1 = reinterpret_cast<const float4*>(fold_smem + (c + 1) * 128 + h * 32);
+      const float4* w2 = reinterpret_cast<const float4*>(fold_smem + (c + 2) * 128 + h * 32);
+      const float4* w3 = reinterpret_cast<const float4*>(fold_smem + (c + 3) * 128 + h * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x0 = w0[j], x1 = w1[j], x2 = w2[j], x3 = w3[j];
+        a0 = fmaf(x0.x, cr[4 * j], a0); a0 = fmaf(x0.y, cr[4 * j + 1], a0); a0 = fmaf(x0.z, cr[4 * j + 2], a0); a0 = fmaf(x0.w, cr[4 * j + 3], a0);
+        a1 = fmaf(x1.x, cr[4 * j], a1); a1 = fmaf(x1.y, cr[4 * j + 1], a1); a1 = fmaf(x1.z, cr[4 * j + 2], a1); a1 = fmaf(x1.w, cr[4 * j + 3], a1);
+        a2 = fmaf(x2.x, cr[4 * j], a2); a2 = fmaf(x2.y, cr[4 * j + 1], a2); a2 = fmaf(x2.z, cr[4 * j + 2], a2); a2 = fmaf(x2.w, cr[4 * j + 3], a2);
+        a3 = fmaf(x3.x, cr[4 * j], a3); a3 = fmaf(x3.y, cr[4 * j + 1], a3); a3 = fmaf(x3.z, cr[4 * j + 2], a3); a3 = fmaf(x3.w, cr[4 * j + 3], a3);
+      }
+      wf[static_cast<long long>(c + 0) * 128] = __float2bfloat16(a0);
+      wf[static_cast<long long>(c + 1) * 128] = __float2bfloat16(a1);
+      wf[static_cast<long long>(c + 2) * 128] = __float2bfloat16(a2);
+      wf[static_cast<long long>(c + 3) * 128] = __float2bfloat16(a3);
+    }
+    for (; c < C; ++c) {
+      const float4* wr = reinterpret_cast<const float4*>(fold_smem + c * 128 + h * 32);
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 wv = wr[j];
+        acc = fmaf(wv.x, cr[4 * j], acc);
+        acc = fmaf(wv.y, cr[4 * j + 1], acc);
+        acc = fmaf(wv.z, cr[4 * j + 2], acc);
+        acc = fmaf(wv.w, cr[4 * j + 3], acc);
+      }
+      wf[static_cast<long long>(c) * 128] = __float2bfloat16(acc);
+    }
   }
 }
 
@@ -380,7 +424,7 @@ struct La2Params {
   float gain_mul, q_scale;
 };
 
-__global__ void __launch_bounds__(kLaThreads, 1) linattn_qout_kernel(const __grid_constant__ CUtensorMap xmap,
+__global__ void __launch_bounds__(kLa2Threads, 1) linattn_qout_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                      const __grid_constant__ CUtensorMap wmap,
                                                                      const __grid_constant__ CUtensorMap fmap,
                                                                      const __grid_constant__ CUtensorMap omap,
@@ -406,21 +450,21 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_qout_kernel(const __gri
   if (tid == 64) {
     for (int s = 0; s < p.x_stages; ++s) {
       mbar_init(&aux->x_full[s], 1);
-      mbar_init(&aux->x_empty[s], 5);                              // GEMM1 commit + the four warps that read the residual
+      mbar_init(&aux->x_empty[s], 1 + kLaEpiWarps / 2);            // GEMM1 commit + the group's warps that read the residual
     }
     mbar_init(&aux->w_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&aux->wf_full[s], 1);
       mbar_init(&aux->wf_empty[s], 1);
       mbar_init(&aux->d1_full[s], 1);
-      mbar_init(&aux->d1_empty[s], 4);
-      mbar_init(&aux->q_full[s], 4);
+      mbar_init(&aux->d1_empty[s], kLaEpiWarps / 2);
+      mbar_init(&aux->q_full[s], kLaEpiWarps / 2);
       mbar_init(&aux->d2_full[s], 1);
-      mbar_init(&aux->d2_empty[s], 4);
+      mbar_init(&aux->d2_empty[s], kLaEpiWarps / 2);
     }
     fence_mbar_init();
   }
-  for (int i = tid; i < 128; i += kLaThreads) {
+  for (int i = tid; i < 128; i += kLa2Threads) {
     aux->bias[i] = i < p.C ? p.bias[i] : 0.f;
     aux->gain[i] = i < p.C ? p.gain[i] * p.gain_mul : 0.f;
   }
@@ -468,32 +512,38 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_qout_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    // ================================================================ tcgen05 issuer
+    // ================================================================ tcgen05 issuers.  GEMM1: q = x W'_q^T; GEMM2: y = q wfold_b^T.
+    // Warp 1 interleaves GEMM1(t) and GEMM2(t-1).  (Giving GEMM2 its own issuing warp, as in the kv kernel, measured 233 vs
+    // 241 us at 64x64 / batch 400: no gain, the epilogue is the limiter here.)
+    const bool do1 = true, do2 = true;
     const uint32_t idesc1 = umma_idesc_bf16(128, 128);
     const uint32_t idesc2 = umma_idesc_bf16(128, static_cast<uint32_t>(p.n_rows));
-    mbar_wait(&aux->w_full, 0);
-    tc_fence_after();
-    int b_prev = -1, sl = -1;
-    auto gemm2 = [&](int t) {                                      // output projection of local tile t
+    const uint32_t w16 = (smem_u32(wres) & 0x3FFFF) >> 4;
+    const uint32_t q16 = (smem_u32(qstg) & 0x3FFFF) >> 4;
+    const uint32_t f16 = (smem_u32(wfr) & 0x3FFFF) >> 4;
+    if (do1) {
+      mbar_wait(&aux->w_full, 0);
+      tc_fence_after();
+    }
+    int b_prev = -1, sl = -1, slot = 0;
+    int b = t_begin / p.tps, ti = t_begin % p.tps;                 // sample / tile-in-sample of the next GEMM2 tile
+    auto gemm2 = [&](int t) {
       const int g = t & 1;
       const uint32_t k2 = static_cast<uint32_t>(t >> 1);
-      const int b = (t_begin + t) / p.tps;
-      const bool last_of_sample = (t == n_tiles - 1) || ((t_begin + t + 1) / p.tps != b);
+      const bool last_of_sample = (t == n_tiles - 1) || (ti == p.tps - 1);
       if (b != b_prev) {
         b_prev = b;
         ++sl;
-        mbar_wait(&aux->wf_full[sl % p.wf_bufs], static_cast<uint32_t>(sl / p.wf_bufs) & 1u);
+        slot = sl % p.wf_bufs;
+        mbar_wait(&aux->wf_full[slot], static_cast<uint32_t>(sl / p.wf_bufs) & 1u);
       }
-      const int slot = sl % p.wf_bufs;
       mbar_wait(&aux->q_full[g], k2 & 1u);
       mbar_wait(&aux->d2_empty[g], (k2 & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t qa = smem_u32(qstg + static_cast<size_t>(g) * 2 * kLaBlk);
-      const uint32_t fa = smem_u32(wfr + static_cast<size_t>(slot) * wf_slot);
       if (elect_one()) {
         for (int kb = 0; kb < 2; ++kb) {
-          const uint32_t a16 = ((qa + kb * kLaBlk) & 0x3FFFF) >> 4;
-          const uint32_t b16 = ((fa + kb * p.n_rows * 128) & 0x3FFFF) >> 4;
+          const uint32_t a16 = q16 + (g * 2 + kb) * (kLaBlk >> 4);
+          const uint32_t b16 = f16 + ((slot * wf_slot + kb * p.n_rows * 128) >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_ss(tmem_base + 256 + g * 128, umma_desc_sw128_a16(a16 + 2 * k), umma_desc_sw128_a16(b16 + 2 * k),
@@ -503,59 +553,85 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_qout_kernel(const __gri
         if (last_of_sample) umma_commit(&aux->wf_empty[slot]);
       }
       __syncwarp();
+      if (++ti == p.tps) { ti = 0; ++b; }
     };
     int s = 0;
     uint32_t ph = 0;
     for (int li = 0; li < n_tiles; ++li) {
-      const int g = li & 1;
-      mbar_wait(&aux->x_full[s], ph);
-      mbar_wait(&aux->d1_empty[g], (static_cast<uint32_t>(li >> 1) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t xa = smem_u32(xring + static_cast<size_t>(s) * x_stage_bytes);
-      if (elect_one()) {
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          const uint32_t a16 = ((xa + kb * kLaBlk) & 0x3FFFF) >> 4;
-          const uint32_t b16 = ((smem_u32(wres) + kb * kLaBlk) & 0x3FFFF) >> 4;
+      if (do1) {
+        const int g = li & 1;
+        mbar_wait(&aux->x_full[s], ph);
+        mbar_wait(&aux->d1_empty[g], (static_cast<uint32_t>(li >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t x16 = (smem_u32(xring + static_cast<size_t>(s) * x_stage_bytes) & 0x3FFFF) >> 4;
+        if (elect_one()) {
+          for (int kb = 0; kb < p.nkb; ++kb) {
+            const uint32_t a16 = x16 + kb * (kLaBlk >> 4);
+            const uint32_t b16 = w16 + kb * (kLaBlk >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_base + g * 128, umma_desc_sw128_a16(a16 + 2 * k), umma_desc_sw128_a16(b16 + 2 * k), idesc1,
-                         (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss(tmem_base + g * 128, umma_desc_sw128_a16(a16 + 2 * k), umma_desc_sw128_a16(b16 + 2 * k), idesc1,
+                           (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&aux->d1_full[g]);
+          umma_commit(&aux->x_empty[s]);
         }
-        umma_commit(&aux->d1_full[g]);
-        umma_commit(&aux->x_empty[s]);
+        __syncwarp();
+        if (++s == p.x_stages) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (li > 0) gemm2(li - 1);
-      if (++s == p.x_stages) { s = 0; ph ^= 1u; }
+      if (do2) {
+        if (do1) {                                                 // interleaved: one tile behind GEMM1
+          if (li > 0) gemm2(li - 1);
+        } else {
+          gemm2(li);
+        }
+      }
     }
-    if (n_tiles > 0) gemm2(n_tiles - 1);
-  } else {
-    // ================================================================ epilogue: group g = tiles of parity g
+    if (do1 && do2 && n_tiles > 0) gemm2(n_tiles - 1);
+  } else if (warp < 2 + kLaEpiWarps) {
+    // ================================================================ epilogue: group g (8 warps) = tiles of parity g;
+    // inside a group the two warps of a TMEM lane quarter split the columns (2 heads each; half of the output channels)
     const int ew = warp - 2;
     const int q = warp & 3;
-    const int g = ew >> 2;
-    const int et_g = (ew & 3) * 32 + lane;
+    const int g = ew >> 3;
+    const int half = (ew >> 2) & 1;
+    const int et_g = (ew & 7) * 32 + lane;
     const int m = q * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* const sq = qstg + static_cast<size_t>(g) * 2 * kLaBlk + m * 128;     // this thread's row in the group's staging
     const int nch = p.n_rows / 32;
+    const int c2_lo = half == 0 ? 0 : (nch + 1) / 2, c2_hi = half == 0 ? (nch + 1) / 2 : nch;   // output chunks of this warp
     uint32_t r[32];
     if (et_g == 0) tma_prefetch_desc(&omap);
+    // running tile coordinates of this group's tiles (no divisions in the loop)
+    int tile = t_begin + g;
+    int b = tile / p.tps, ti = tile % p.tps;
+    int s = g % p.x_stages;
+    const int s_step = 2 % p.x_stages;
+    float rss_next = g < n_tiles ? __ldg(p.rowss + static_cast<long long>(tile) * kLaTok + m) : 1.f;
     for (int li = g; li < n_tiles; li += 2) {
-      const int tile = t_begin + li, b = tile / p.tps, tok0 = (tile % p.tps) * kLaTok;
+      const int tok0 = ti * kLaTok, b_cur = b, s_cur = s;
       const uint32_t k2 = static_cast<uint32_t>(li >> 1);
-      const int s = li % p.x_stages;
-      const float rs = 1.f / fmaxf(sqrtf(__ldg(p.rowss + static_cast<long long>(b) * p.n + tok0 + m)), 1e-12f);
-      // ---- epilogue 1: q = softmax over each head's 32 channels, * scale (unet.py:207,210)
+      const float rs = 1.f / fmaxf(sqrtf(rss_next), 1e-12f);
+      tile += 2;
+      ti += 2;
+      while (ti >= p.tps) { ti -= p.tps; ++b; }
+      s += s_step;
+      if (s >= p.x_stages) s -= p.x_stages;
+      if (li + 2 < n_tiles) rss_next = __ldg(p.rowss + static_cast<long long>(tile) * kLaTok + m);   // tokens are contiguous
+      // ---- epilogue 1: q = softmax over each head's 32 channels, * scale (unet.py:207,210); this warp: heads 2*half, +1
       mbar_wait(&aux->d1_full[g], k2 & 1u);
       tc_fence_after();
       if (et_g == 0) tma_store_wait_read0();                       // the previous tile's bulk store has left this buffer
       group_bar(g);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      const float k1 = rs * kLog2e;
+      const float2 k12 = make_float2(k1, k1);
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         tmem_ld32(trow + g * 128 + c * 32, r);
         tmem_ld_wait();
-        if (c == 3) {
+        if (cc == 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&aux->d1_empty[g]);
@@ -564,8 +640,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_qout_kernel(const __gri
 #pragma unroll
         for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
         // softmax(rs * a): exponent (a - max a) * rs * log2e   (rs > 0, so the max commutes with the scaling)
-        const float k1 = rs * kLog2e;
-        const float2 k12 = make_float2(k1, k1), nm2 = make_float2(-mx * k1, -mx * k1);
+        const float2 nm2 = make_float2(-mx * k1, -mx * k1);
         float2 e[16];
         float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -576,7 +651,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_qout_kernel(const __gri
         }
         const float kk = __fdividef(p.q_scale, sum2.x + sum2.y);
         const float2 kk2 = make_float2(kk, kk);
-        uint8_t* dst = sq + (c >> 1) * kLaBlk;
+        uint8_t* dst = sq + half * kLaBlk;                         // heads 2*half, 2*half+1 = K block `half` of q
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg) {
           uint4 o;
@@ -586,18 +661,19 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_qout_kernel(const __gri
           o.y = pack_bf16(a1.x, a1.y);
           o.z = pack_bf16(a2.x, a2.y);
           o.w = pack_bf16(a3.x, a3.y);
-          *reinterpret_cast<uint4*>(dst + ((((c & 1) * 4 + gg) ^ (m & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(dst + (((cc * 4 + gg) ^ (m & 7)) << 4)) = o;
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&aux->q_full[g]);
       // ---- epilogue 2: y = acc + bias -> RMSNorm * g * sqrt(C) -> + x -> bf16 (unet.py:88-89,198-199,72)
+      const uint8_t* xrow = xring + static_cast<size_t>(s_cur) * x_stage_bytes + m * 128;
       mbar_wait(&aux->d2_full[g], k2 & 1u);
       tc_fence_after();
       const uint32_t d2 = trow + 256 + g * 128;
       float2 sq2 = make_float2(0.f, 0.f);
-      for (int c = 0; c < nch; ++c) {
+      for (int c = 0; c < nch; ++c) {                              // both warps of a quarter need the whole row's norm
         tmem_ld32(d2 + c * 32, r);
         tmem_ld_wait();
         const float2* b2 = reinterpret_cast<const float2*>(aux->bias + c * 32);
@@ -609,48 +685,54 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_qout_kernel(const __gri
       }
       const float inv = 1.f / fmaxf(sqrtf(sq2.x + sq2.y), 1e-12f);
       const float2 inv2 = make_float2(inv, inv);
-      const uint8_t* xrow = xring + static_cast<size_t>(s) * x_stage_bytes + m * 128;
-      for (int c = 0; c < nch; ++c) {
-        tmem_ld32(d2 + c * 32, r);
-        tmem_ld_wait();
-        if (c == nch - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&aux->d2_empty[g]);
-        }
-        const float2* b2 = reinterpret_cast<const float2*>(aux->bias + c * 32);
-        const float2* g2 = reinterpret_cast<const float2*>(aux->gain + c * 32);
-        const bool have_x = (c >> 1) < p.nkb;                      // residual channels beyond the loaded K blocks are padding
 #pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          const int pos = (((c & 1) * 4 + gg) ^ (m & 7)) << 4;
-          uint4 xr = make_uint4(0, 0, 0, 0);
-          if (have_x) xr = *reinterpret_cast<const uint4*>(xrow + (c >> 1) * kLaBlk + pos);
-          float2 v[4];
+      for (int j = 0; j < 2; ++j) {
+        const int c = c2_lo + j;
+        if (c < c2_hi) {
+          uint4 xr[4];                                             // residual rows: requested before the TMEM load completes
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 a = make_float2(__uint_as_float(r[gg * 8 + 2 * i]), __uint_as_float(r[gg * 8 + 2 * i + 1]));
-            v[i] = __fmul2_rn(__fmul2_rn(__fadd2_rn(a, b2[gg * 4 + i]), inv2), g2[gg * 4 + i]);
+          for (int gg = 0; gg < 4; ++gg) {
+            xr[gg] = make_uint4(0, 0, 0, 0);
+            if ((c >> 1) < p.nkb)                                  // channels beyond the loaded K blocks are padding
+              xr[gg] = *reinterpret_cast<const uint4*>(xrow + (c >> 1) * kLaBlk + ((((c & 1) * 4 + gg) ^ (m & 7)) << 4));
           }
-          v[0] = __fadd2_rn(v[0], make_float2(bf16_lo(xr.x), bf16_hi(xr.x)));
-          v[1] = __fadd2_rn(v[1], make_float2(bf16_lo(xr.y), bf16_hi(xr.y)));
-          v[2] = __fadd2_rn(v[2], make_float2(bf16_lo(xr.z), bf16_hi(xr.z)));
-          v[3] = __fadd2_rn(v[3], make_float2(bf16_lo(xr.w), bf16_hi(xr.w)));
-          uint4 o;
-          o.x = pack_bf16(v[0].x, v[0].y);
-          o.y = pack_bf16(v[1].x, v[1].y);
-          o.z = pack_bf16(v[2].x, v[2].y);
-          o.w = pack_bf16(v[3].x, v[3].y);
-          *reinterpret_cast<uint4*>(sq + (c >> 1) * kLaBlk + pos) = o;
+          tmem_ld32(d2 + c * 32, r);
+          tmem_ld_wait();
+          const float2* b2 = reinterpret_cast<const float2*>(aux->bias + c * 32);
+          const float2* g2 = reinterpret_cast<const float2*>(aux->gain + c * 32);
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const uint4 x4 = xr[gg];
+            float2 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 a = make_float2(__uint_as_float(r[gg * 8 + 2 * i]), __uint_as_float(r[gg * 8 + 2 * i + 1]));
+              v[i] = __fmul2_rn(__fmul2_rn(__fadd2_rn(a, b2[gg * 4 + i]), inv2), g2[gg * 4 + i]);
+            }
+            v[0] = __fadd2_rn(v[0], make_float2(bf16_lo(x4.x), bf16_hi(x4.x)));
+            v[1] = __fadd2_rn(v[1], make_float2(bf16_lo(x4.y), bf16_hi(x4.y)));
+            v[2] = __fadd2_rn(v[2], make_float2(bf16_lo(x4.z), bf16_hi(x4.z)));
+            v[3] = __fadd2_rn(v[3], make_float2(bf16_lo(x4.w), bf16_hi(x4.w)));
+            uint4 o;
+            o.x = pack_bf16(v[0].x, v[0].y);
+            o.y = pack_bf16(v[1].x, v[1].y);
+            o.z = pack_bf16(v[2].x, v[2].y);
+            o.w = pack_bf16(v[3].x, v[3].y);
+            *reinterpret_cast<uint4*>(sq + (c >> 1) * kLaBlk + ((((c & 1) * 4 + gg) ^ (m & 7)) << 4)) = o;
+          }
         }
       }
+      tc_fence_before();                                           // all TMEM reads of this tile by this warp are done
       __syncwarp();
-      if (lane == 0) mbar_arrive(&aux->x_empty[s]);                // residual rows read: the x stage may be refilled
+      if (lane == 0) {
+        mbar_arrive(&aux->d2_empty[g]);
+        mbar_arrive(&aux->x_empty[s_cur]);                         // ... and so are the residual reads of the x stage
+      }
       fence_proxy_async_smem();
       group_bar(g);
       if (et_g == 0) {
         const uint8_t* sbuf = qstg + static_cast<size_t>(g) * 2 * kLaBlk;
-        for (int pn = 0; pn * 64 < p.C; ++pn) tma_store_3d(&omap, sbuf + pn * kLaBlk, pn * 64, tok0, b);
+        for (int pn = 0; pn * 64 < p.C; ++pn) tma_store_3d(&omap, sbuf + pn * kLaBlk, pn * 64, tok0, b_cur);
         tma_store_commit();
       }
     }
@@ -744,10 +826,19 @@ extern "C" int ccdm_linattn_kv_partials(const void* x, int32_t B, int32_t n, int
 
 extern "C" int ccdm_linattn_fold_partials(const float* part, const float* psum, int32_t B, int32_t units_per_sample,
                                           const float* w_out, int32_t C, int32_t n_rows, void* wfold, void* stream) {
-  CCDM_REQUIRE(part && psum && w_out && wfold && B > 0 && units_per_sample > 0 && C > 0 && n_rows >= C, CCDM_ERR_BAD_ARG,
-               "linattn_fold_partials: bad args");
-  linattn_fold_parts_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(part, psum, units_per_sample, w_out, C, n_rows,
-                                                                (__nv_bfloat16*)wfold);
+  CCDM_REQUIRE(part && psum && w_out && wfold && B > 0 && units_per_sample > 0 && C > 0 && C <= 128 && n_rows >= C,
+               CCDM_ERR_BAD_ARG, "linattn_fold_partials: bad args (C <= 128)");
+  const size_t smem = (size_t)C * 128 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(linattn_fold_parts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4);
+    if (e != cudaSuccess) return cuda_fail(e, "linattn_fold_parts_kernel: cudaFuncSetAttribute");
+    attr_set = true;
+  }
+  int grid = 3 * num_sms();                                        // <= 64 KB of shared memory each: three CTAs per SM
+  if (grid > B) grid = B;
+  linattn_fold_parts_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(part, psum, units_per_sample, w_out, C, n_rows,
+                                                                      (__nv_bfloat16*)wfold, B);
   return after_launch("linattn_fold_parts_kernel");
 }
 
@@ -800,6 +891,6 @@ extern "C" int ccdm_linattn_q_out(const void* x, int32_t B, int32_t n, int32_t C
     if (e != cudaSuccess) return cuda_fail(e, "linattn_qout_kernel: cudaFuncSetAttribute");
     attr_set = true;
   }
-  linattn_qout_kernel<<<grid, kLaThreads, total(), (cudaStream_t)stream>>>(xmap, wmap, fmap, omap, p);
+  linattn_qout_kernel<<<grid, kLa2Threads, total(), (cudaStream_t)stream>>>(xmap, wmap, fmap, omap, p);
   return after_launch("linattn_qout_kernel");
 }

@@ -364,6 +364,34 @@ __global__ void stem_unpack_wgrad_kernel(const float* __restrict__ packed, float
   dw[idx] = accumulate ? dw[idx] + v : v;
 }
 
+
+// Batch construction on the device (trainer.py:461-482 `process_images`): gather B images of a device-resident uint8
+// dataset [N][C][H][W] by index, apply the per-sample augmentation (rot90 by k quarter turns as np.rot90 over (H, W), then
+// horizontal flip, then vertical flip -- the order of trainer.py:468-474) and normalise to [0, 1] fp32 NCHW (utils.py:182-186).
+// aug[b]: bits 0-1 = k (quarter turns, needs H == W when non-zero), bit 2 = horizontal flip, bit 3 = vertical flip.
+__global__ void gather_augment_u8_kernel(const uint8_t* __restrict__ images, const long long* __restrict__ idx,
+                                         const uint8_t* __restrict__ aug, float* __restrict__ out, int B, int C, int H, int W,
+                                         long long n_images) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int c = (int)((i / ((long long)W * H)) % C);
+    const int b = (int)(i / ((long long)W * H * C));
+    const unsigned a = aug ? aug[b] : 0u;
+    int yy = (a & 8u) ? H - 1 - y : y;                    // undo the vertical flip
+    int xx = (a & 4u) ? W - 1 - x : x;                    // undo the horizontal flip
+    const unsigned k = a & 3u;                            // np.rot90: out[i][j] = in[j][n-1-i] for k = 1
+    int sy = yy, sx = xx;
+    if (k == 1) { sy = xx; sx = W - 1 - yy; }
+    else if (k == 2) { sy = H - 1 - yy; sx = W - 1 - xx; }
+    else if (k == 3) { sy = H - 1 - xx; sx = yy; }
+    long long src = idx[b];
+    src = src < 0 ? 0 : (src >= n_images ? n_images - 1 : src);
+    out[i] = (float)images[((src * C + c) * H + sy) * W + sx] * (1.f / 255.f);
+  }
+}
+
 }  // namespace ccdm
 
 using namespace ccdm;
@@ -471,4 +499,16 @@ extern "C" int ccdm_stem_unpack_wgrad(const float* packed, float* dw, int32_t Co
   const int total = Cout * Cin * 49;
   stem_unpack_wgrad_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(packed, dw, Cout, Cin, accumulate);
   return after_launch("stem_unpack_wgrad_kernel");
+}
+
+extern "C" int ccdm_gather_augment_u8(const uint8_t* images, int64_t n_images, const int64_t* idx, const uint8_t* aug,
+                                      float* out, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+  CCDM_REQUIRE(images && idx && out && n_images > 0 && B > 0 && C > 0 && H > 0 && W > 0, CCDM_ERR_BAD_ARG,
+               "gather_augment_u8: bad args");
+  const long long total = (long long)B * C * H * W;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_augment_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(images, (const long long*)idx, aug, out, B, C,
+                                                                               H, W, (long long)n_images);
+  return after_launch("gather_augment_u8_kernel");
 }

@@ -21,6 +21,20 @@ class EMA(nn.Module):
         self.inv_gamma, self.power, self.min_value = inv_gamma, power, min_value
         self.register_buffer("initted", torch.tensor([False]))
         self.register_buffer("step", torch.tensor([0]))
+        # host shadows of the two buffers: update() must not read the device every training step (a .item() is a full
+        # host-device synchronisation); they are re-read after load_state_dict
+        self._step_host = None
+        self._initted_host = None
+
+    def _sync_host_state(self):
+        if self._step_host is None:
+            self._step_host = int(self.step.item())
+            self._initted_host = bool(self.initted.item())
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._step_host = None
+        return out
 
     def _pairs(self):
         on = dict(self.online_model.named_parameters())
@@ -36,22 +50,26 @@ class EMA(nn.Module):
                 e.copy_(o)
 
     def get_current_decay(self):                     # ema_pytorch.py:124-131
-        epoch = max(int(self.step.item()) - self.update_after_step - 1, 0)
+        self._sync_host_state()
+        epoch = max(self._step_host - self.update_after_step - 1, 0)
         value = 1 - (1 + epoch / self.inv_gamma) ** -self.power
         return 0.0 if epoch <= 0 else min(max(value, self.min_value), self.beta)
 
     @torch.no_grad()
     def update(self):                                # ema_pytorch.py:133-178
-        step = int(self.step.item())
+        self._sync_host_state()
+        step = self._step_host
+        self._step_host += 1
         self.step += 1
         if (step % self.update_every) != 0:
             return
         if step <= self.update_after_step:
             self.copy_params_from_model_to_ema()
             return
-        if not bool(self.initted.item()):
+        if not self._initted_host:
             self.copy_params_from_model_to_ema()
             self.initted.fill_(True)
+            self._initted_host = True
         w = 1.0 - self.get_current_decay()
         pairs = self._pairs()
         if pairs and all(e.is_cuda and e.dtype == torch.float32 for e, _ in pairs):

@@ -18,6 +18,7 @@ Layer -> kernel mapping (reference lines in CCDM_unified/models/unet.py):
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -25,6 +26,8 @@ import torch
 
 from . import _lib as L
 from .plan import ConvPlan, plan_conv, tile_box, can_reuse_rows, n_tiling, KB
+
+_SYNC_EACH = os.environ.get("CCDM_SYNC_EACH") == "1"
 
 
 # --------------------------------------------------------------------------------------------- records
@@ -144,6 +147,16 @@ class Program:
         self.calls = [_make_call(lib, r, self._keep) for r in self.recs]
 
     def run(self, stream: int):
+        if _SYNC_EACH:                                     # debugging aid: attribute an asynchronous fault to its record
+            for fn, args, name in self.calls:
+                rc = fn(*args, stream)
+                if rc != 0:
+                    L.check(rc, name)
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e:
+                    raise RuntimeError(f"device fault in record '{name}': {e}") from e
+            return
         for fn, args, name in self.calls:
             rc = fn(*args, stream)
             if rc != 0:

@@ -14,7 +14,7 @@ Random draws (timesteps, masks, noise) use PyTorch's graph-safe Philox generator
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import Callable, Optional
 
 import torch
 
@@ -23,15 +23,26 @@ from .optim import FusedAdam
 
 
 class GraphedTrainStep:
-    def __init__(self, diffusion, optimizer: torch.optim.Optimizer, images: torch.Tensor, labels: torch.Tensor,
-                 labels_emb: torch.Tensor, *, loss_kwargs: Optional[dict] = None, max_grad_norm: Optional[float] = 1.0,
-                 warmup: int = 3):
-        """``images`` / ``labels`` / ``labels_emb`` are example batches (their shapes are frozen)."""
+    def __init__(self, diffusion, optimizer: torch.optim.Optimizer, images: Optional[torch.Tensor] = None,
+                 labels: Optional[torch.Tensor] = None, labels_emb: Optional[torch.Tensor] = None, *,
+                 loss_kwargs: Optional[dict] = None, max_grad_norm: Optional[float] = 1.0, warmup: int = 3,
+                 batch_fn: Optional[Callable] = None, accumulate: int = 1):
+        """Two ways to feed the step:
+
+        * ``images`` / ``labels`` / ``labels_emb``: example batches (their shapes are frozen); ``__call__`` copies a new batch
+          into the static buffers and replays;
+        * ``batch_fn() -> (images, labels, labels_emb, vicinal_weights, loss_kwargs)``: the batch is BUILT inside the captured
+          step from device ops only (``Trainer.device_batch``: target labels, vicinity search, gather + augmentation), so a
+          training step is one ``replay()`` with no host work at all; ``accumulate`` micro-batches are captured back to back
+          (``gradient_accumulate_every`` of trainer.py:560-720), their losses summed into ``self.loss``.
+        """
         self.gd, self.opt = diffusion, optimizer
         self.kw = dict(loss_kwargs or {})
         self.max_grad_norm = max_grad_norm
+        self.batch_fn, self.accumulate = batch_fn, int(accumulate)
         self.params = [p for p in diffusion.parameters() if p.requires_grad]
         self.fused = isinstance(optimizer, FusedAdam)
+        dev = self.params[0].device
         if self.fused:
             optimizer.max_grad_norm = max_grad_norm               # clipping is part of the fused step
         else:
@@ -41,20 +52,22 @@ class GraphedTrainStep:
                     grp["foreach"] = True
             for st in optimizer.state.values():
                 if "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
-                    st["step"] = st["step"].to(images.device)
-        self.images = images.detach().clone()
-        self.labels = labels.detach().clone()
-        self.labels_emb = labels_emb.detach().clone()
-        self.weights = torch.ones(images.shape[0], device=images.device)
-        self.loss = torch.zeros((), device=images.device)
+                    st["step"] = st["step"].to(dev)
+        if batch_fn is None:
+            self.images = images.detach().clone()
+            self.labels = labels.detach().clone()
+            self.labels_emb = labels_emb.detach().clone()
+            self.weights = torch.ones(images.shape[0], device=dev)
+        self.loss = torch.zeros((), device=dev)
         self.graph = torch.cuda.CUDAGraph()
         diffusion.graph_safe_rng = True
         diffusion.train()
 
+        self.warmup_steps = max(warmup, 1)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(max(warmup, 1)):      # allocator, schedule tables, optimizer state, autograd threads
+            for _ in range(self.warmup_steps):   # allocator, schedule tables, optimizer state, autograd threads
                 self._step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -63,9 +76,19 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
 
     def _step(self):
-        loss = self.gd(self.images, labels_emb=self.labels_emb, labels=self.labels, vicinal_weights=self.weights, **self.kw)
         self.opt.zero_grad(set_to_none=True)
-        loss.backward()
+        total = None
+        for _ in range(self.accumulate):
+            if self.batch_fn is not None:
+                images, labels, emb, weights, kw = self.batch_fn()
+                kw = dict(self.kw, **kw)
+            else:
+                images, labels, emb, weights, kw = self.images, self.labels, self.labels_emb, self.weights, self.kw
+            loss = self.gd(images, labels_emb=emb, labels=labels, vicinal_weights=weights, **kw)
+            if self.accumulate > 1:
+                loss = loss / self.accumulate
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
         if self.fused:
             self.opt.all_reduce_gradients()
         else:
@@ -73,15 +96,20 @@ class GraphedTrainStep:
             if self.max_grad_norm is not None:
                 torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm)
         self.opt.step()
-        self.loss.copy_(loss.detach())
+        self.loss.copy_(total)
 
-    def __call__(self, images: torch.Tensor, labels: torch.Tensor, labels_emb: torch.Tensor) -> torch.Tensor:
-        """Runs one optimizer step on the given batch; returns the (device, 0-dim) loss of that step."""
-        self.images.copy_(images, non_blocking=True)
-        self.labels.copy_(labels, non_blocking=True)
-        self.labels_emb.copy_(labels_emb, non_blocking=True)
+    def replay(self) -> torch.Tensor:
+        """One optimizer step on a batch built inside the graph (``batch_fn`` mode); returns the device loss scalar."""
         self.graph.replay()
         # the replayed optimizer kernel wrote the parameters without any Python-side version bump: the eval engines'
         # packed-weight caches (keyed on _version) must see the change
         torch._C._increment_version(self.params)
         return self.loss
+
+    def __call__(self, images: torch.Tensor, labels: torch.Tensor, labels_emb: torch.Tensor) -> torch.Tensor:
+        """Runs one optimizer step on the given batch; returns the (device, 0-dim) loss of that step."""
+        assert self.batch_fn is None, "this step builds its own batches: call replay()"
+        self.images.copy_(images, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        self.labels_emb.copy_(labels_emb, non_blocking=True)
+        return self.replay()

@@ -357,6 +357,13 @@ int ccdm_head_conv1_bwd(const float* dout_nchw, const void* h, const float* w, v
 /* Inverse of ccdm_stem_pack for the gradient ccdm_conv_wgrad leaves over the im2row tensor: dW [Cout][Cin][7][7]. */
 int ccdm_stem_unpack_wgrad(const float* packed, float* dw, int32_t Cout, int32_t Cin, int32_t accumulate, void* stream);
 
+/* Device-side batch construction (trainer.py:461-482 process_images + utils.py:164-211): out[b] = augment(images[idx[b]]) / 255,
+ * fp32 NCHW in [0, 1] from a device-resident uint8 dataset [n_images][C][H][W].  aug[b] (may be NULL = none): bits 0-1 =
+ * quarter turns k as np.rot90 over (H, W) (needs H == W), bit 2 = horizontal flip, bit 3 = vertical flip, applied in that
+ * order (rotate, hflip, vflip) like the reference's Cell200 pipeline; UTKFace uses the hflip bit only. */
+int ccdm_gather_augment_u8(const uint8_t* images, int64_t n_images, const int64_t* idx, const uint8_t* aug, float* out,
+                           int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Optimizer step: clip_grad_norm_ + Adam of trainer.py:137,724,733-734 in three launches
  * over flat fp32 gradient / moment buffers, and the EMA lerp of ema_pytorch.py:150-178 in one.

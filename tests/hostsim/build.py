@@ -64,6 +64,7 @@ def extract_source(cu_path: str, kernels, entries) -> str:
     body = "namespace ccdm {\n" + "".join(_definition(src, r"__global__ void (?:__launch_bounds__\(\w+\) )?" + k + r"\(")
                                           for k in kernels) + "}\nusing namespace ccdm;\n"
     body += "".join(_definition(src, r'extern "C" int ' + e + r"\(") for e in entries)
+    body = DYN_SMEM_RE.sub(r"float* \1 = g_dyn_smem;", body)       # dynamic shared memory: one 256 KB host buffer
     body, n = _launch_sub(body)
     assert n > 0 and "<<<" not in body
     return '#include "cuda_host_shim.h"\n' + body

@@ -421,3 +421,70 @@ def test_packed_weight_cache_follows_fused_updates():
         e1_fresh = net3(x, t, emb, cond_drop_prob=0.0)
     assert relerr(e1, e0) > 1e-3
     assert relerr(e1, e1_fresh) < 1e-6, relerr(e1, e1_fresh)
+
+
+def test_trainer_graph_path_runs_without_host_syncs(tmp_path):
+    """Trainer.train on the CUDA-graph path: the dataset lives on the device as uint8, a step is one graph
+    replay (batch construction + 2 accumulated micro-batches + clip + Adam inside), and between the log points the loop issues
+    NO host synchronisation -- asserted with torch.cuda.set_sync_debug_mode("error") around the replays."""
+    import numpy as np
+    import ccdm_b200
+    spec = SPECS["rc_small"]
+    net, _ = make_net(spec, 5, p_drop=0.1)
+    gd = ccdm_b200.GaussianDiffusion(net, image_size=16, timesteps=1000, sampling_timesteps=5, objective="pred_x0",
+                                     cond_drop_prob=0.1, vicinity_type="hv").cuda()
+    rng = np.random.RandomState(0)
+    images = rng.randint(0, 256, size=(96, 3, 16, 16)).astype(np.uint8)
+    labels = np.round(rng.rand(96), 2).astype(np.float32)
+    tr = ccdm_b200.Trainer("UTKFace", gd, train_images=images, train_labels=labels,
+                           vicinal_params={"kernel_sigma": 0.05, "kappa": 0.1, "nonzero_soft_weight_threshold": 1e-3},
+                           train_batch_size=8, gradient_accumulate_every=2, train_num_steps=12, save_every=100,
+                           results_folder=str(tmp_path), vicinity_type="hv", kappa=0.1, sigma_delta=0.05,
+                           ema_update_after_step=2, ema_update_every=2)
+    fn_y2h = ccdm_b200.LabelEmbed(y2h_type="sinusoidal", h_dim=128, device=torch.device("cuda")).fn_y2h
+    before = torch.cat([p.detach().flatten().clone() for p in gd.parameters()])
+    gd.train()
+    tr.train_num_steps = 9                                  # builds the graph (3 warm-up steps are real steps) and replays
+    tr.train(fn_y2h)
+    assert tr._graph_step is not None and tr.step == 9
+    assert tr._images_dev.dtype == torch.uint8 and tr._images_dev.is_cuda
+    tr.train_num_steps = 12
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        tr.train(fn_y2h)                                    # steps 9, 10, 11: pure replays, EMA lerps, no log point (step % 500)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert tr.step == 12 and float(tr.opt.step_count.item()) == 12.0
+    after = torch.cat([p.detach().flatten() for p in gd.parameters()])
+    assert torch.isfinite(after).all() and (after - before).abs().max() > 0
+    assert torch.isfinite(tr._graph_step.loss).all() and float(tr._graph_step.loss) > 0
+    ema_p = torch.cat([p.detach().flatten() for p in tr.ema.ema_model.parameters()])
+    assert torch.isfinite(ema_p).all() and (ema_p - before).abs().max() > 0
+    # the eval engine of the EMA model sees the graph-updated weights (packed-weight cache invalidation)
+    y = torch.from_numpy(labels[:2]).cuda()
+    img = tr.ema.ema_model.ddim_sample(labels_emb=fn_y2h(y), labels=y, shape=(2, 3, 16, 16), cond_scale=1.5)
+    assert torch.isfinite(img).all()
+
+
+def test_gather_augment_kernel_matches_numpy():
+    """ccdm_gather_augment_u8 (trainer.py:461-482, utils.py:164-211): every augmentation code against numpy."""
+    import numpy as np
+    from ccdm_b200 import _lib as L
+    rng = np.random.RandomState(3)
+    imgs = rng.randint(0, 256, size=(7, 3, 12, 12)).astype(np.uint8)
+    d_imgs = torch.from_numpy(imgs).cuda()
+    idx = torch.tensor([(3 * i) % 7 for i in range(16)], dtype=torch.int64, device="cuda")
+    aug = torch.arange(16, dtype=torch.uint8, device="cuda")
+    out = torch.empty(16, 3, 12, 12, device="cuda")
+    L.check(L.lib().ccdm_gather_augment_u8(d_imgs.data_ptr(), 7, idx.data_ptr(), aug.data_ptr(), out.data_ptr(), 16, 3, 12, 12,
+                                           torch.cuda.current_stream().cuda_stream), "gather")
+    out = out.cpu().numpy()
+    for b in range(16):
+        k, hf, vf = b & 3, (b >> 2) & 1, (b >> 3) & 1
+        ref = np.rot90(imgs[(3 * b) % 7].astype(np.float32), k=k, axes=(1, 2))
+        if hf:
+            ref = ref[:, :, ::-1]
+        if vf:
+            ref = ref[:, ::-1, :]
+        assert np.allclose(out[b], ref / 255.0, atol=1e-7), b
