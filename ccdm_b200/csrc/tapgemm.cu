@@ -19,6 +19,7 @@
 //                    recomputed by both from TMEM (cheaper than exchanging it).
 //
 // Replaces the nn.Conv2d / nn.Linear call sites listed in include/ccdm_b200.h.
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <mutex>
@@ -61,6 +62,7 @@ struct TapGemmDev {
   float q_scale, gain_mul;
   int q_cols;
   int epi_alt;                            // the two epilogue warp groups take alternate tiles (n_tile <= 64)
+  int pair;                               // CTA pairs: one tcgen05.mma.cta_group::2 (M = 256) covers a tile of each CTA
 };
 
 // aux shared-memory block (after the resident weights and the stage ring)
@@ -87,21 +89,31 @@ __device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) {
 }
 
 // kR vertically adjacent taps x 4 K-steps of one load group, fully unrolled (tap r: r*tw rows further down the box).
-template <int kR>
+template <int kR, bool kPair = false>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t tap16, uint32_t b16,
                                            uint32_t idesc, bool first_group) {
 #pragma unroll
   for (int r = 0; r < kR; ++r) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16_ss(d_tmem, umma_desc_lo(a_lo + r * tap16 + 2 * k), umma_desc_lo(b_lo + r * b16 + 2 * k), idesc,
-                   (r | k) != 0 ? 1u : (first_group ? 0u : 1u));
+    for (int k = 0; k < 4; ++k) {
+      if (kPair)
+        umma_bf16_ss_2sm(d_tmem, umma_desc_lo(a_lo + r * tap16 + 2 * k), umma_desc_lo(b_lo + r * b16 + 2 * k), idesc,
+                         (r | k) != 0 ? 1u : (first_group ? 0u : 1u));
+      else
+        umma_bf16_ss(d_tmem, umma_desc_lo(a_lo + r * tap16 + 2 * k), umma_desc_lo(b_lo + r * b16 + 2 * k), idesc,
+                     (r | k) != 0 ? 1u : (first_group ? 0u : 1u));
+    }
   }
+}
+template <bool kPair>
+__device__ __forceinline__ void commit_bar(uint32_t bar_addr) {
+  if (kPair) umma_commit_2sm_a(bar_addr);
+  else umma_commit_a(bar_addr);
 }
 
 // MMA-issuer loop of the common case (weights resident in shared memory, one N sub-tile, one channel tile per CTA),
 // specialised on the number of vertically adjacent taps: no per-group branching, barrier addresses as plain integers.
-template <int kR>
+template <int kR, bool kPair>
 __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_groups, int n_stages, uint32_t a_lo0,
                                                   uint32_t stage16, uint32_t b_lo0, uint32_t tap16, uint32_t b16,
                                                   uint32_t idesc, uint32_t tmem_base, uint32_t n_tile, int acc_mask,
@@ -121,15 +133,15 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
       mbar_wait_a(full_bar + 8 * s, ph);
       tc_fence_after();
       if (elect_one()) {
-        issue_taps<kR>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
-        umma_commit_a(empty_bar + 8 * s);
+        issue_taps<kR, kPair>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
+        commit_bar<kPair>(empty_bar + 8 * s);
       }
       __syncwarp();
       b_lo += kR * b16;
       a_lo += stage16;
       if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
     }
-    if (elect_one()) umma_commit_a(tfull_bar + 8 * as);
+    if (elect_one()) commit_bar<kPair>(tfull_bar + 8 * as);
     __syncwarp();
   }
 }
@@ -138,7 +150,7 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
 // are resident in shared memory or ride in the stage behind the A box: no per-group branching, barrier addresses as
 // plain integers.  n_inner > 1: every CTA walks several channel tiles of the same boxes (qkv), which stay in the ring
 // until the last channel tile has read them.
-template <int kR, bool kRes, bool kMultiN>
+template <int kR, bool kRes, bool kMultiN, bool kPair = false>
 __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_groups, int n_stages, int n_inner_rt,
                                               uint32_t a_lo0, uint32_t stage16, uint32_t abytes16, uint32_t b_lo0,
                                               uint32_t nkb_b16, uint32_t tap16, uint32_t b16, uint32_t idesc,
@@ -172,15 +184,15 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
           tc_fence_after();
         }
         if (elect_one()) {
-          issue_taps<kR>(d_tmem, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0);
-          if (last_nt) umma_commit_a(empty_bar + 8 * s);   // box reusable once the last MMAs have read it
+          issue_taps<kR, kPair>(d_tmem, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0);
+          if (last_nt) commit_bar<kPair>(empty_bar + 8 * s);   // box reusable once the last MMAs have read it
         }
         __syncwarp();
         b_lo += kR * b16;
         a_lo += stage16;
         if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
       }
-      if (elect_one()) umma_commit_a(tfull_bar + 8 * as);
+      if (elect_one()) commit_bar<kPair>(tfull_bar + 8 * as);
       __syncwarp();
     }
   }
@@ -190,7 +202,9 @@ constexpr uint32_t kRuntimeFlags = 0x80000000u;            // template value: ep
 
 // kFlags: the CCDM_EPI_* set compiled into the epilogue (dead branches vanish), or kRuntimeFlags.
 // kStoreTma: bf16 output through the shared-memory staging tile + TMA bulk store.
-template <uint32_t kFlags, bool kStoreTma>
+// kPair: CTA-pair build (tcgen05 cta_group::2; must be launched as 2-CTA clusters -- a kernel containing cta_group::2
+// instructions cannot be launched without them, hence a separate instantiation).
+template <uint32_t kFlags, bool kStoreTma, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmMaps maps,
                                                               const TapGemmDev p) {
   extern __shared__ __align__(1024) uint8_t smem[];        // 1024-byte aligned: SWIZZLE_128B atoms
@@ -206,14 +220,23 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   const int lane = tid & 31;
   const int z = blockIdx.y / p.n_tiles;
   const int n_base = (blockIdx.y % p.n_tiles) * p.n_tile;       // first output channel of this CTA
-  const int b_bytes = p.n_tile * 128;
+  // CTA pairs: this CTA keeps (and loads) only its half of the weight rows of every K block
+  constexpr bool pair = kPair;
+  uint32_t crank = 0;
+  if constexpr (kPair) crank = cluster_ctarank();
+  const int b_rows = pair ? p.n_tile >> 1 : p.n_tile;
+  const int b_bytes = b_rows * 128;
+  const int w_row0 = n_base + static_cast<int>(crank) * b_rows;  // first weight row this CTA loads (within z)
 
   // ---------------------------------------------------------------- one-time setup
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.b);
     tma_prefetch_desc(&maps.a[0]);
   }
-  if (warp == 1) tmem_alloc(&aux->tmem_slot, p.tmem_cols);
+  if (warp == 1) {
+    if constexpr (kPair) tmem_alloc_2sm(&aux->tmem_slot, p.tmem_cols);
+    else tmem_alloc(&aux->tmem_slot, p.tmem_cols);
+  }
   if (tid == 64) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&aux->a_full[s], 1);
@@ -222,7 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     mbar_init(&aux->b_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&aux->tmem_full[s], 1);
-      mbar_init(&aux->tmem_empty[s], p.epi_alt ? kEpiWarps / 2 : kEpiWarps);
+      // (pair: the epilogue warps of BOTH CTAs release the accumulator stage on the leader's barrier)
+      mbar_init(&aux->tmem_empty[s], (p.epi_alt ? kEpiWarps / 2 : kEpiWarps) * (pair ? 2 : 1));
     }
     fence_mbar_init();
   }
@@ -234,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   for (int i = tid; i < p.ngroups; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();                 // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = aux->tmem_slot;
   const int tiles_per_sample = p.tiles_w * p.tiles_h;
@@ -243,12 +268,19 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   griddep_launch_dependents();
   // contiguous tile range per CTA: neighbouring tiles share halos in L2 and (mostly) the sample's scale/shift
   const int t_begin = blockIdx.x * p.tiles_per_cta;
-  const int t_end = min(p.tiles_m, t_begin + p.tiles_per_cta);
+  // (pair: both CTAs walk the same NUMBER of tiles -- tiles past the end are dummies: TMA zero-fills, nothing is stored)
+  const int t_end = pair ? t_begin + p.tiles_per_cta : min(p.tiles_m, t_begin + p.tiles_per_cta);
 
   if (warp == 0) {
     // ============================================================== TMA producer (warp-uniform loops, one lane issues)
     if (p.w_batch_rows != 0) griddep_wait();               // per-sample weights come from the previous kernel
     if (p.b_resident && elect_one()) {
+      if constexpr (kPair) {                                // both halves complete on the leader's barrier
+        if (crank == 0) mbar_arrive_expect_tx(&aux->b_full, 2u * static_cast<uint32_t>(p.nkb) * b_bytes);
+        for (int kb = 0; kb < p.nkb; ++kb)
+          tma_load_2d_2sm(&maps.b, smem_u32(&aux->b_full), smem_u32(res_b + static_cast<size_t>(kb) * b_bytes),
+                          kb * kBlockK, z * p.n_rows + w_row0);
+      } else {
       mbar_arrive_expect_tx(&aux->b_full, static_cast<uint32_t>(p.nkb * p.n_inner) * b_bytes);
       for (int nt = 0; nt < p.n_inner; ++nt)
         for (int kb = 0; kb < p.nkb; ++kb)
@@ -256,6 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             tma_load_2d(&maps.b, &aux->b_full,
                         res_b + static_cast<size_t>(nt * p.nkb + kb) * b_bytes + sub * p.n_sub * 128, kb * kBlockK,
                         z * p.n_rows + n_base + nt * p.n_tile + sub * p.n_sub);
+      }
     }
     __syncwarp();
     griddep_wait();                                        // activations below are the previous kernels' outputs
@@ -272,7 +305,20 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       const int wrow = b0 * p.w_batch_rows + z * p.n_rows + n_base;
       for (int g = 0; g < n_groups; ++g) {
         mbar_wait(&aux->a_empty[s], ph ^ 1u);
-        if (elect_one()) {
+        if constexpr (kPair) {
+          // Both CTAs fill their own slot s; every byte is accounted on the LEADER's barrier, which its MMA lane waits on.
+          if (elect_one()) {
+            if (crank == 0) mbar_arrive_expect_tx(&aux->a_full[s], 2u * stage_bytes);
+            const int4 e = s_sched[g];
+            const uint32_t st = smem_u32(ring + static_cast<size_t>(s) * stage_bytes);
+            const uint32_t fb = smem_u32(&aux->a_full[s]);
+            tma_load_4d_2sm(&maps.a[e.x], fb, st, e.w, w0 + e.y, h0 + e.z, b0);
+            if (!b_res) {
+              for (int r = 0; r < p.R; ++r)
+                tma_load_2d_2sm(&maps.b, fb, st + p.a_bytes + r * b_bytes, (g * p.R + r) * kBlockK, z * p.n_rows + w_row0);
+            }
+          }
+        } else if (elect_one()) {
           mbar_arrive_expect_tx(&aux->a_full[s], stage_bytes);
           const int4 e = s_sched[g];
           uint8_t* st = ring + static_cast<size_t>(s) * stage_bytes;
@@ -288,9 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         if (++s == n_stages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ============================================================== MMA issuer (warp-uniform loops, one lane issues)
-    const uint32_t idesc = umma_idesc_bf16(kTileM, p.n_sub);
+  } else if (warp == 1 && crank == 0) {
+    // ============================================================== MMA issuer (warp-uniform loops, one lane issues;
+    // in a CTA pair only the leader's: its M = 256 instructions read both CTAs' shared memory and write both TMEMs)
+    const uint32_t idesc = umma_idesc_bf16(pair ? 2 * kTileM : kTileM, p.n_sub);
     const uint32_t ring16 = (smem_u32(ring) & 0x3FFFF) >> 4;       // descriptor address fields, in 16-byte units
     const uint32_t res16 = (smem_u32(res_b) & 0x3FFFF) >> 4;
     const uint32_t stage16 = p.stage_bytes >> 4, abytes16 = p.a_bytes >> 4, b16 = static_cast<uint32_t>(b_bytes) >> 4;
@@ -316,17 +363,36 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   mma_loop_fast<KR, RES, MULTI>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo, nkb_b16, \
                                 tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, \
                                 tempty_bar)
-      if (n_inner > 1) {                                   // several channel tiles per box (qkv): weights always resident
+      if constexpr (kPair) {                               // host guarantees: one channel tile per CTA, R <= 3
+#define CCDM_PAIR_RES(KR)                                                                                                 \
+  mma_loop_resident<KR, true>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base, \
+                              n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar)
+#define CCDM_PAIR_STR(KR)                                                                                                 \
+  mma_loop_fast<KR, false, false, true>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo,  \
+                                        nkb_b16, tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar,     \
+                                        empty_bar, tfull_bar, tempty_bar)
+        if (b_res) {
+          if (R == 3) CCDM_PAIR_RES(3);
+          else if (R == 2) CCDM_PAIR_RES(2);
+          else CCDM_PAIR_RES(1);
+        } else {
+          if (R == 3) CCDM_PAIR_STR(3);
+          else if (R == 2) CCDM_PAIR_STR(2);
+          else CCDM_PAIR_STR(1);
+        }
+#undef CCDM_PAIR_RES
+#undef CCDM_PAIR_STR
+      } else if (n_inner > 1) {                            // several channel tiles per box (qkv): weights always resident
         CCDM_MMA_LOOP(1, true, true);
       } else if (b_res) {
         if (R == 3)
-          mma_loop_resident<3>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+          mma_loop_resident<3, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
                                n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
         else if (R == 2)
-          mma_loop_resident<2>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+          mma_loop_resident<2, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
                                n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
         else
-          mma_loop_resident<1>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+          mma_loop_resident<1, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
                                n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
       } else {
         if (R == 3) CCDM_MMA_LOOP(3, false, false);
@@ -383,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       }
     }
     }  // generic path
-  } else {
+  } else if (warp >= 2) {
     // ============================================================== epilogue (warps 2..9)
     const int ew = warp - 2;
     const int q = warp & 3;                                // TMEM lane quarter this warp may read
@@ -444,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 
       if (tile_ss && b0 != ss_b) {                         // new sample (uniform over the group's threads): refresh
         epi_bar_g(alt, half);                              // everyone is done with the previous sample's vectors
-        const float* ssrow = p.ss + static_cast<long long>(b0) * p.ss_ld + p.ss_off + n_base;
+        const float* ssrow = p.ss + static_cast<long long>(min(b0, p.gB - 1)) * p.ss_ld + p.ss_off + n_base;
         for (int c = et_g; c < p.n_tile; c += g_threads) {
           const bool ok = (n_base + c) < p.N;
           aux->gs[gi][c] = ok ? ((flags & CCDM_EPI_RMSNORM) ? aux->gain[c] : 1.f) * (1.f + ssrow[c]) : 0.f;
@@ -530,7 +596,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         if (c == c_hi - 1) {                               // last TMEM read of this tile by this warp: release
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&aux->tmem_empty[as]);
+          if (lane == 0) {
+            if constexpr (kPair) mbar_arrive_cluster(&aux->tmem_empty[as], 0);
+            else mbar_arrive(&aux->tmem_empty[as]);
+          }
         }
         float2 v[16];
         {
@@ -671,7 +740,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       if (c_lo >= c_hi) {                                  // this warp owns no columns (n_tile == 32): still release
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&aux->tmem_empty[as]);
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_cluster(&aux->tmem_empty[as], 0);
+          else mbar_arrive(&aux->tmem_empty[as]);
+        }
       }
       if ((flags & CCDM_EPI_SUMSQ_OUT) && !alt && half == 1) aux->part[lt & 1][m] = out_ss;   // combine the column halves
       if (kStoreTma) {
@@ -703,9 +775,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   if (kStoreTma && (tid == 64 || (p.epi_alt && tid == 64 + 128))) tma_store_wait_all();   // the threads that issued bulk stores
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();                 // the peer is done with this CTA's barriers, shared memory and TMEM
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if constexpr (kPair) tmem_dealloc_2sm(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -760,12 +834,12 @@ static uint32_t pow2_cols(int n) {
   return c;
 }
 
-template <uint32_t kFlags, bool kStoreTma>
+template <uint32_t kFlags, bool kStoreTma, bool kPair = false>
 static int launch_one(dim3 grid, size_t smem_bytes, cudaStream_t stream, const TapGemmMaps& maps, const TapGemmDev& p) {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(tapgemm_kernel<kFlags, kStoreTma>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    err = cudaFuncSetAttribute(tapgemm_kernel<kFlags, kStoreTma, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                227 * 1024);
   });
   if (err != cudaSuccess) return cuda_fail(err, "tapgemm: cudaFuncSetAttribute");
@@ -775,12 +849,19 @@ static int launch_one(dim3 grid, size_t smem_bytes, cudaStream_t stream, const T
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_kernel<kFlags, kStoreTma>, maps, p);
+  if (kPair) {                                             // CTA pairs: 2-CTA clusters along x (one TPC each)
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_kernel<kFlags, kStoreTma, kPair>, maps, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return cuda_fail(e, "tapgemm_kernel launch");
   return CCDM_OK;
@@ -790,6 +871,23 @@ static int launch_one(dim3 grid, size_t smem_bytes, cudaStream_t stream, const T
 // runtime-flag instantiation (same code, branches kept).
 static int launch_variant(uint32_t flags, bool tma, dim3 grid, size_t smem_bytes, cudaStream_t stream,
                           const TapGemmMaps& maps, const TapGemmDev& p) {
+  if (p.pair) {                                            // CTA-pair builds (always TMA-store epilogues)
+#define CCDM_PAIR_VARIANT(F) \
+  case F:                    \
+    return launch_one<F, true, true>(grid, smem_bytes, stream, maps, p);
+    switch (flags) {
+      CCDM_PAIR_VARIANT(0x1Du)
+      CCDM_PAIR_VARIANT(0x35u)
+      CCDM_PAIR_VARIANT(0xB5u)
+      CCDM_PAIR_VARIANT(0x01u)
+      CCDM_PAIR_VARIANT(0x25u)
+      CCDM_PAIR_VARIANT(0x00u)
+      default:
+        break;
+    }
+#undef CCDM_PAIR_VARIANT
+    return launch_one<kRuntimeFlags, true, true>(grid, smem_bytes, stream, maps, p);
+  }
 #define CCDM_VARIANT(F)                                                                        \
   case F:                                                                                      \
     return tma ? launch_one<F, true>(grid, smem_bytes, stream, maps, p)                        \
@@ -869,16 +967,6 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   const int n_sub = a->n_tile / nsub;
   const int nkb = a->ngroups * a->R;
   CCDM_REQUIRE(n_sub % 16 == 0 && n_sub <= 256, CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: n_sub=%d", n_sub);
-  {
-    const cuuint64_t ktot = (cuuint64_t)nkb * kBlockK;
-    cuuint64_t dims[2] = {ktot, a->w_batch_rows > 0 ? (cuuint64_t)a->w_batch_rows * a->gB
-                                                    : (cuuint64_t)a->n_rows * a->nz};
-    cuuint64_t str[1] = {ktot * 2};
-    cuuint32_t box[2] = {kBlockK, (cuuint32_t)n_sub};
-    CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->wpacked) & 15) == 0, CCDM_ERR_BAD_ARG, "tapgemm: wpacked alignment");
-    int rc = encode_map_bf16(&maps.b, a->wpacked, 2, dims, str, box);
-    if (rc != CCDM_OK) return rc;
-  }
 
   TapGemmDev p;
   std::memset(&p, 0, sizeof(p));
@@ -923,12 +1011,43 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   int gx = sms / combos;                                           // never more CTAs than SMs: no second wave
   if (gx > p.tiles_m) gx = p.tiles_m;
   if (gx < 1) gx = 1;
-  const int tiles_per_cta = (p.tiles_m + gx - 1) / gx;
+  int tiles_per_cta = (p.tiles_m + gx - 1) / gx;
   gx = (p.tiles_m + tiles_per_cta - 1) / tiles_per_cta;            // contiguous ranges: no CTA without work
+  // ---- CTA pairs (tcgen05 cta_group::2): two CTAs on one TPC run ONE M = 256 instruction per K step, each on its own
+  // pixel tile, each holding half of the weight rows.  Halves the single issuing lane's work per tile (the measured
+  // limiter of the 64-channel layers), the weight bytes in shared memory (128 -> 64 3x3 weights become resident) and the
+  // B-operand fetch per MMA.  The i-th tile of the even CTA is multiplied together with the i-th tile of the odd CTA.
+  {
+    // Measured (profiles/r2_pair_layers.txt): pairs win where the K loop is long (>= 16 K blocks: 128 -> 64 3x3 +33 %,
+    // 4x4-s2, every >= 128-channel 3x3) and lose on short, memory-bound layers (1x1, 64 -> 64 + residual), whose
+    // per-tile time is dominated by load / store latency that the pair's cross-SM handshakes lengthen.
+    static const int pair_env = [] { const char* e = getenv("CCDM_TAPGEMM_PAIR"); return e ? atoi(e) : 16; }();
+    p.pair = (pair_env != 0 && nkb >= pair_env && a->w_batch_rows == 0 && nsub == 1 && p.n_inner == 1 && a->R <= 3 && a->n_tile <= 256 &&
+              (a->n_tile / 2) % 16 == 0 && gx >= 2 && tiles_per_cta >= 2 && !(a->flags & CCDM_EPI_OUT_F32)) ? 1 : 0;
+    if (p.pair) {
+      if (gx & 1) ++gx;                                            // whole pairs; a trailing CTA may get dummy tiles only
+      if (gx > sms / combos) {                                     // odd SM budget: re-balance over an even CTA count
+        gx = (sms / combos) & ~1;
+        tiles_per_cta = (p.tiles_m + gx - 1) / gx;
+        gx = (p.tiles_m + tiles_per_cta - 1) / tiles_per_cta;
+        if (gx & 1) ++gx;
+      }
+    }
+  }
   p.tiles_per_cta = tiles_per_cta;
+  {
+    const cuuint64_t ktot = (cuuint64_t)nkb * kBlockK;
+    cuuint64_t dims[2] = {ktot, a->w_batch_rows > 0 ? (cuuint64_t)a->w_batch_rows * a->gB
+                                                    : (cuuint64_t)a->n_rows * a->nz};
+    cuuint64_t str[1] = {ktot * 2};
+    cuuint32_t box[2] = {kBlockK, (cuuint32_t)(p.pair ? n_sub / 2 : n_sub)};
+    CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->wpacked) & 15) == 0, CCDM_ERR_BAD_ARG, "tapgemm: wpacked alignment");
+    int rc = encode_map_bf16(&maps.b, a->wpacked, 2, dims, str, box);
+    if (rc != CCDM_OK) return rc;
+  }
 
   // ---- shared-memory plan
-  const uint32_t b_bytes = (uint32_t)a->n_tile * 128u;
+  const uint32_t b_bytes = (uint32_t)(p.pair ? a->n_tile / 2 : a->n_tile) * 128u;
   p.a_bytes = (uint32_t)(box_h * a->tw * a->tb) * 128u;
   const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)a->ngroups * sizeof(int4);
   size_t budget = 226 * 1024 - aux_bytes - 1024;
@@ -950,7 +1069,8 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   p.stage_bytes = p.a_bytes + (p.b_resident ? 0 : (uint32_t)a->R * b_bytes);
   int stages = (int)((budget - p.res_bytes) / p.stage_bytes);
   int useful = a->ngroups * (tiles_per_cta > 1 ? 2 : 1);           // about two tiles of lookahead ...
-  if (tiles_per_cta > 1 && useful < 4) useful = 4;                 // ... but never fewer than 4 boxes in flight
+  static const int min_stages = [] { const char* e = getenv("CCDM_TAPGEMM_MINSTAGES"); return e ? atoi(e) : 4; }();
+  if (tiles_per_cta > 1 && useful < min_stages) useful = min_stages;   // ... but never fewer than 4 boxes in flight
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > useful) stages = useful;
   if (p.n_inner > 1 && stages < 2 * a->ngroups) stages = 2 * a->ngroups <= kMaxStages ? 2 * a->ngroups : a->ngroups;

@@ -27,9 +27,15 @@ class GaussianFourierProjection(nn.Module):     # label_embedding.py:18-34
         return torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1).view(len(proj), self.embed_dim)
 
 
+_FREQS = {}
+
+
 def _sinusoid(labels, dim):
     half = dim // 2
-    freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(labels.device)
+    key = (half, labels.device)
+    if key not in _FREQS:      # uploaded once per device: no pageable host->device copy inside a captured training step
+        _FREQS[key] = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(labels.device)
+    freqs = _FREQS[key]
     args = labels.view(len(labels))[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:

@@ -463,6 +463,7 @@ def test_trainer_graph_path_runs_without_host_syncs(tmp_path):
     assert torch.isfinite(ema_p).all() and (ema_p - before).abs().max() > 0
     # the eval engine of the EMA model sees the graph-updated weights (packed-weight cache invalidation)
     y = torch.from_numpy(labels[:2]).cuda()
+    tr.ema.ema_model.eval()
     img = tr.ema.ema_model.ddim_sample(labels_emb=fn_y2h(y), labels=y, shape=(2, 3, 16, 16), cond_scale=1.5)
     assert torch.isfinite(img).all()
 
