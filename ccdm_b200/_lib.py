@@ -92,6 +92,7 @@ SIGNATURES = {
     "ccdm_linattn_fold_partials": (C.c_int, [vp, vp, i32, i32, vp, i32, i32, vp, vp]),
     "ccdm_linattn_q_out": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, f32, f32, vp, vp]),
     "ccdm_linear_small": (C.c_int, [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, i64, vp]),
+    "ccdm_groupnorm_rows": (C.c_int, [vp, i32, i32, i32, vp, vp, C.c_float, i32, vp]),
     "ccdm_time_features": (C.c_int, [vp, i32, i32, vp, vp]),
     "ccdm_select_null": (C.c_int, [vp, vp, i32, vp, i32, i32, vp]),
     "ccdm_silu_concat_bf16": (C.c_int, [vp, i32, vp, i32, i32, vp, vp]),

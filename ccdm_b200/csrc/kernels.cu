@@ -406,6 +406,37 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restric
   y[(long long)b * y_ld + o] = act_apply(acc, act);
 }
 
+// nn.GroupNorm(groups, C) on a [B, C] matrix followed by an activation, in place (the learned label-embedding MLPs,
+// models/resnet_y2h.py:143-173, models/resnet_y2cov.py:149-179): one warp per (row, group); biased variance, eps inside
+// the square root (torch semantics), fp32.
+__global__ void __launch_bounds__(256) groupnorm_rows_kernel(float* __restrict__ x, int B, int C, int groups,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps, int act) {
+  const int wid = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= B * groups) return;
+  const int b = wid / groups, g = wid % groups, cg = C / groups;
+  float* xr = x + (long long)b * C + g * cg;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < cg; i += 32) {
+    const float v = xr[i];
+    s1 += v;
+    s2 = fmaf(v, v, s2);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  }
+  const float mean = s1 / cg;
+  const float var = fmaxf(s2 / cg - mean * mean, 0.f);
+  const float inv = rsqrtf(var + eps);
+  for (int i = lane; i < cg; i += 32) {
+    const int c = g * cg + i;
+    xr[i] = act_apply((xr[i] - mean) * inv * gamma[c] + beta[c], act);
+  }
+}
+
 // unet.py:107-115: sin | cos of t * exp(-log(1e4) * i / (half-1))
 __global__ void time_features_kernel(const long long* __restrict__ t, int B, int dim, float* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,6 +610,15 @@ extern "C" int ccdm_linear_small(const float* x, int32_t B, int32_t in_dim, cons
   linear_small_kernel<<<(out_dim + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x, B, in_dim, w, bias, out_dim, bn_w, bn_b,
                                                                            bn_mean, bn_var, bn_train, act, y, y_ld);
   return after_launch("linear_small_kernel");
+}
+
+extern "C" int ccdm_groupnorm_rows(float* x, int32_t B, int32_t C, int32_t groups, const float* gamma, const float* beta,
+                                   float eps, int32_t act, void* stream) {
+  CCDM_REQUIRE(x && gamma && beta && B > 0 && C > 0 && groups > 0 && C % groups == 0, CCDM_ERR_BAD_ARG,
+               "groupnorm_rows: bad args (B=%d C=%d groups=%d)", B, C, groups);
+  const int warps = B * groups;
+  groupnorm_rows_kernel<<<(warps + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, B, C, groups, gamma, beta, eps, act);
+  return after_launch("groupnorm_rows_kernel");
 }
 
 extern "C" int ccdm_time_features(const int64_t* t, int32_t B, int32_t dim, float* out, void* stream) {

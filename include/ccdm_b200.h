@@ -185,6 +185,12 @@ int ccdm_linattn_q_out(const void* x, int32_t B, int32_t n, int32_t C, const flo
 int ccdm_linear_small(const float* x, int32_t B, int32_t in_dim, const float* w, const float* bias, int32_t out_dim,
                       const float* bn_w, const float* bn_b, float* bn_mean, float* bn_var, int32_t bn_train,
                       int32_t act, float* y, int64_t y_ld, void* stream);
+/* x[b, :] = act( GroupNorm(groups, C)(x[b, :]) * gamma + beta ), in place, fp32 [B][C] (nn.GroupNorm on a 2-D input:
+ * statistics over the C/groups channels of each group of each row; biased variance, eps inside the sqrt).  With
+ * ccdm_linear_small this is the forward of the learned label-embedding MLPs model_y2h / model_y2cov
+ * (models/resnet_y2h.py:143-173, models/resnet_y2cov.py:149-179; called from label_embedding.py:1028-1031,1173-1176). */
+int ccdm_groupnorm_rows(float* x, int32_t B, int32_t C, int32_t groups, const float* gamma, const float* beta, float eps,
+                        int32_t act, void* stream);
 int ccdm_time_features(const int64_t* t, int32_t B, int32_t dim, float* out, void* stream);
 /* c[b,:] = keep[b] ? c[b,:] : null_emb[:]   (keep may be NULL with all_null != 0) */
 int ccdm_select_null(float* c, const uint8_t* keep, int32_t all_null, const float* null_emb, int32_t B, int32_t dim,

@@ -194,6 +194,9 @@ def install(monkeypatch):
     import ccdm_b200.vanilla_unet as VU
     monkeypatch.setattr(T, "_require_cuda", lambda x: None)             # the "no CPU fallback" guards of the training forwards
     monkeypatch.setattr(VU, "_require_cuda", lambda x: None)
+    import ccdm_b200.label_embedding as LE
+    monkeypatch.setattr(LE, "_require_cuda", lambda x: None)
+    monkeypatch.setattr(LE, "_stream", lambda: None)
     return lib
 
 
