@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--ddim-steps", type=int, default=250)
     ap.add_argument("--size", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step block")
     return ap.parse_args()
 
 
@@ -290,16 +291,81 @@ def run_b200(args):
                     rows.append({"name": getattr(r, "kind", "?"), "ms": ms_})
             json.dump({"batch": 2 * B, "total_ms": all_ms, "rows": rows}, f, indent=1)
 
+    # ---- training step (BASELINE configs[1]) so that the driver's BENCH / SCALE records carry it at every N
+    train = None
+    if not args.no_train:
+        del prog, timed
+        torch.cuda.empty_cache()
+        try:
+            train = train_block(rank, local_rank, world, dev, peaks)
+        except Exception as e:                                             # never lose the headline line to the extra block
+            train = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config(args, world), "clocks": clocks, "e2e": e2e,
             "gpu_launches": gpu_launches, "roofline": roofline}
+    if train is not None:
+        line["train"] = train
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def train_block(rank, local_rank, world, dev, peaks, batch=128, steps=5, warmup=3):
+    """BASELINE.json configs[1]: UTKFace 64x64 CCDM training step (dim 72, mults 1-2-4-4-8; pred_x0, Hy, hard vicinal weights),
+    batch 128 per GPU, bf16 tensor cores with fp32 master weights.  One step = q_sample -> UNet forward -> vicinal loss ->
+    backward -> gradient all-reduce over NCCL (N > 1) -> clip -> Adam, replayed as ONE CUDA graph (train_graph.py).  CUDA
+    events, max over ranks.  Algorithmic FLOPs = 3 x forward (fwd + dgrad + wgrad), 16.25 GF per image forward."""
+    import math
+    import ccdm_b200
+    from ccdm_b200 import dist as D
+    from ccdm_b200.optim import FusedAdam
+    from ccdm_b200.train_graph import GraphedTrainStep
+    size, gflop = 64, 16.25
+
+    def sinusoid(y, dim):
+        half = dim // 2
+        f = torch.exp(-math.log(10000) * torch.arange(half, device=y.device, dtype=torch.float32) / half)
+        a = y.reshape(-1)[:, None].float() * f[None]
+        return torch.cat([torch.cos(a), torch.sin(a)], -1)
+
+    torch.manual_seed(111)
+    net = ccdm_b200.Unet(dim=72, embed_input_dim=128, cond_drop_prob=0.1, dim_mults=(1, 2, 4, 4, 8), in_channels=3,
+                         attn_dim_head=32, attn_heads=4)
+    n_el = 3 * size * size
+    gd = ccdm_b200.GaussianDiffusion(net, image_size=size, objective="pred_x0", use_Hy=True,
+                                     fn_y2cov=lambda y: (sinusoid(y, n_el) + 1) / 2, cond_drop_prob=0.1, timesteps=1000,
+                                     vicinity_type="hv").to(dev).train()
+    D.broadcast_parameters(gd)
+    opt = FusedAdam([p for p in gd.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99), max_grad_norm=1.0)
+    g = torch.Generator().manual_seed(rank)
+    img = torch.rand(batch, 3, size, size, generator=g).to(dev)
+    labels = torch.rand(batch, generator=g).to(dev)
+    emb = sinusoid(labels, 128)
+    gstep = GraphedTrainStep(gd, opt, img, labels, emb, loss_kwargs=dict(vicinity_type="hv", kappa=0.05), warmup=warmup)
+    gstep(img, labels, emb)
+    torch.cuda.synchronize()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = gstep(img, labels, emb)
+    e1.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+    tflops = 3 * gflop * batch * world / ms
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    return {"workload": "UTKFace 64x64 CCDM training step (dim 72, mults 1-2-4-4-8, pred_x0 + Hy, hard vicinal weights), "
+                        "synthetic batch, whole step as one CUDA graph", "batch_per_gpu": batch, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "images_per_s": batch * world / ms * 1e3,
+            "algorithmic_tflops": tflops, "frac_of_sustained_bf16_peak": tflops / world / peak,
+            "gradient_exchange": "none (1 GPU)" if world == 1 else "NCCL all-reduce of the flat fp32 gradient inside the graph",
+            "loss": float(loss.item()), "dtype": "bf16 (fp32 master weights, fp32 accumulation)"}
 
 
 def main():

@@ -49,7 +49,10 @@ __device__ __forceinline__ CfgCoef cfg_coef(double uc, double cc, float cond_sca
   return r;
 }
 
-// One CTA per sample.
+// One CTA per sample.  kV > 0: the sample's two network outputs live in REGISTERS (kV float4 per thread and tensor, chw <=
+// 512*4*kV) -- global memory is touched once: cond, null, x_t (+ noise) in, x_{t-1} (+ predictions) out, however many
+// reduction passes the guidance needs.  kV == 0: any chw; every pass re-reads global memory (L2 hits after the first).
+template <int kV>
 __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args a) {
   __shared__ double scratch[32 * 4];
   const int b = blockIdx.x;
@@ -58,16 +61,44 @@ __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args 
   const float* nul = a.out_null ? a.out_null + base : nullptr;
   const long long step = a.t_rows ? a.t_rows[b] : (a.step_counter ? (long long)*a.step_counter : 0);
   const float* cf = a.x ? a.coef + step * CCDM_STEP_NCOEF : nullptr;
+  const int nv = a.chw >> 2;                               // (kV > 0: chw % 4 == 0, checked by the launcher)
+
+  float4 cr[kV > 0 ? kV : 1], nr[kV > 0 ? kV : 1];
+  if constexpr (kV > 0) {
+#pragma unroll
+    for (int j = 0; j < kV; ++j) {
+      const int i4 = threadIdx.x + j * 512;
+      cr[j] = i4 < nv ? __ldg(reinterpret_cast<const float4*>(cond) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      nr[j] = (nul && i4 < nv) ? __ldg(reinterpret_cast<const float4*>(nul) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  // f(i, c, n) for every element this thread owns
+  auto each = [&](auto f) {
+    if constexpr (kV > 0) {
+#pragma unroll
+      for (int j = 0; j < kV; ++j) {
+        const int i4 = threadIdx.x + j * 512;
+        if (i4 < nv) {
+          f(4 * i4 + 0, cr[j].x, nr[j].x);
+          f(4 * i4 + 1, cr[j].y, nr[j].y);
+          f(4 * i4 + 2, cr[j].z, nr[j].z);
+          f(4 * i4 + 3, cr[j].w, nr[j].w);
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < a.chw; i += blockDim.x) f(i, cond[i], nul ? nul[i] : 0.f);
+    }
+  };
 
   float a_cond = 1.f, a_null = 0.f, resc = 1.f;
   if (nul) {
     double v[4] = {0, 0, 0, 0};  // <u,c>, <c,c>, sum c, sum c^2
-    for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
-      const double c = cond[i], n = nul[i];
+    each([&](int, float cf_, float nf_) {
+      const double c = cf_, n = nf_;
       v[0] += (c - n) * c;
       v[1] += c * c;
       v[2] += c;
-    }
+    });
     block_sum<4>(v, scratch);
     const CfgCoef k = cfg_coef(v[0], v[1], a.cond_scale, a.remove_parallel, a.keep_parallel_frac);
     a_cond = k.a_cond;
@@ -76,19 +107,19 @@ __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args 
       // unbiased std of cond and of scaled (torch.std default), second pass for centred sums
       const double mean_c = v[2] / a.chw;
       double w[4] = {0, 0, 0, 0};  // sum scaled, sum (c-mean_c)^2
-      for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
-        const double c = cond[i];
-        const double s = (double)(a_cond * cond[i] + a_null * nul[i]);
+      each([&](int, float cf_, float nf_) {
+        const double c = cf_;
+        const double s = (double)(a_cond * cf_ + a_null * nf_);
         w[0] += s;
         w[1] += (c - mean_c) * (c - mean_c);
-      }
+      });
       block_sum<4>(w, scratch);
       const double mean_s = w[0] / a.chw;
       double u[4] = {0, 0, 0, 0};
-      for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
-        const double s = (double)(a_cond * cond[i] + a_null * nul[i]) - mean_s;
+      each([&](int, float cf_, float nf_) {
+        const double s = (double)(a_cond * cf_ + a_null * nf_) - mean_s;
         u[0] += s * s;
-      }
+      });
       block_sum<4>(u, scratch);
       const double std_c = sqrt(w[1] / (a.chw - 1)), std_s = sqrt(u[0] / (a.chw - 1));
       resc = (float)(std_c / std_s) * a.rescaled_phi + (1.f - a.rescaled_phi);
@@ -97,15 +128,10 @@ __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args 
 
   float* x = a.x ? a.x + base : nullptr;
   const float c_recip = x ? cf[0] : 0.f, c_recipm1 = x ? cf[1] : 1.f, c_sa = x ? cf[2] : 0.f, c_s1m = x ? cf[3] : 0.f;
-  for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
-    const float c = cond[i];
-    const float n = nul ? nul[i] : 0.f;
+  // one element of the update: returns x_{t-1} (or the guided output when there is no state); may write the predictions
+  auto elem = [&](int i, float c, float n, float xt, float nz) -> float {
     const float g = (a_cond * c + a_null * n) * resc;  // guided model output
-    if (!x) {                                          // guidance only (ccdm_cfg_combine)
-      a.pred_x0[base + i] = g;
-      continue;
-    }
-    const float xt = x[i];
+    if (!x) return g;                                  // guidance only (ccdm_cfg_combine)
     float x0, eps;
     if (a.objective == CCDM_OBJ_PRED_NOISE) {
       x0 = c_recip * xt - c_recipm1 * g;
@@ -128,22 +154,64 @@ __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args 
     }
     if (a.pred_noise) a.pred_noise[base + i] = eps;
     if (a.pred_x0) a.pred_x0[base + i] = x0;
-    if (a.sampler == 2) continue;  // predictions only
+    if (a.sampler == 2) return xt;  // predictions only: the state is left as it is
     float xn;
     if (a.sampler == 0) {  // DDIM, diffusion.py:450-464
       if (cf[7] != 0.f) {
         xn = x0;
       } else {
         xn = x0 * cf[4] + cf[5] * eps;
-        if (cf[6] != 0.f) xn += cf[6] * a.noise[base + i];
+        if (cf[6] != 0.f) xn += cf[6] * nz;
       }
     } else {               // DDPM, diffusion.py:344-373 (x0 always clamped there)
       const float x0c = fminf(fmaxf(x0, -1.f), 1.f);
       xn = cf[8] * x0c + cf[9] * xt;
-      if (cf[10] != 0.f) xn += cf[10] * a.noise[base + i];
+      if (cf[10] != 0.f) xn += cf[10] * nz;
     }
-    x[i] = xn;
+    return xn;
+  };
+  const bool need_noise = x && a.sampler != 2 && ((a.sampler == 0 && cf[7] == 0.f && cf[6] != 0.f) ||
+                                                  (a.sampler == 1 && cf[10] != 0.f));
+  const float* nzp = need_noise ? a.noise + base : nullptr;
+  if constexpr (kV > 0) {
+    float* dst = x ? x : a.pred_x0 + base;               // guidance only: the guided output goes to pred_x0
+#pragma unroll
+    for (int j = 0; j < kV; ++j) {
+      const int i4 = threadIdx.x + j * 512;
+      if (i4 < nv) {
+        const float4 xt = x ? *(reinterpret_cast<const float4*>(x) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 nz = nzp ? __ldg(reinterpret_cast<const float4*>(nzp) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o;
+        o.x = elem(4 * i4 + 0, cr[j].x, nr[j].x, xt.x, nz.x);
+        o.y = elem(4 * i4 + 1, cr[j].y, nr[j].y, xt.y, nz.y);
+        o.z = elem(4 * i4 + 2, cr[j].z, nr[j].z, xt.z, nz.z);
+        o.w = elem(4 * i4 + 3, cr[j].w, nr[j].w, xt.w, nz.w);
+        if (!x || a.sampler != 2) *(reinterpret_cast<float4*>(dst) + i4) = o;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
+      const float r = elem(i, cond[i], nul ? nul[i] : 0.f, x ? x[i] : 0.f, nzp ? nzp[i] : 0.f);
+      if (!x) a.pred_x0[base + i] = r;
+      else if (a.sampler != 2) x[i] = r;
+    }
   }
+}
+
+// Register-resident variants for chw up to 512 threads * 4 * kV elements (64x64x3 = 12288 -> kV = 6); needs 16-byte
+// aligned rows.  Larger samples (128x128 and up) take the streaming variant.
+static void launch_sampler_step(const ccdm_step_args& k, cudaStream_t s) {
+  const bool vec = (k.chw % 4 == 0) && ((reinterpret_cast<uintptr_t>(k.out_cond) & 15) == 0) &&
+                   (!k.out_null || (reinterpret_cast<uintptr_t>(k.out_null) & 15) == 0) &&
+                   (!k.x || (reinterpret_cast<uintptr_t>(k.x) & 15) == 0) &&
+                   (!k.noise || (reinterpret_cast<uintptr_t>(k.noise) & 15) == 0) &&
+                   (k.x || (reinterpret_cast<uintptr_t>(k.pred_x0) & 15) == 0);
+  const int per_thread = (k.chw / 4 + 511) / 512;
+  if (vec && per_thread <= 2) sampler_step_kernel<2><<<k.B, 512, 0, s>>>(k);
+  else if (vec && per_thread <= 4) sampler_step_kernel<4><<<k.B, 512, 0, s>>>(k);
+  else if (vec && per_thread <= 6) sampler_step_kernel<6><<<k.B, 512, 0, s>>>(k);
+  else if (vec && per_thread <= 8) sampler_step_kernel<8><<<k.B, 512, 0, s>>>(k);
+  else sampler_step_kernel<0><<<k.B, 512, 0, s>>>(k);
 }
 
 // The step counter is bumped by its own 1-thread launch after the step kernel, so every CTA of the step kernel
@@ -275,7 +343,7 @@ extern "C" int ccdm_sampler_step(const ccdm_step_args* a, void* stream) {
   CCDM_REQUIRE(a->x, CCDM_ERR_BAD_ARG, "sampler_step: null state");
   ccdm_step_args k = *a;
   if (k.cond_scale == 1.f) k.out_null = nullptr;
-  sampler_step_kernel<<<k.B, 512, 0, (cudaStream_t)stream>>>(k);
+  launch_sampler_step(k, (cudaStream_t)stream);
   rc = after_launch("sampler_step_kernel");
   if (rc != CCDM_OK) return rc;
   if (a->advance && a->step_counter) {
@@ -309,7 +377,7 @@ extern "C" int ccdm_cfg_combine(const float* cond, const float* null_out, float*
   k.keep_parallel_frac = keep_parallel_frac;
   k.remove_parallel = remove_parallel;
   k.coef = nullptr;  // x == nullptr: guidance only, no sampler coefficients are read
-  sampler_step_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(k);
+  launch_sampler_step(k, (cudaStream_t)stream);
   return after_launch("sampler_step_kernel(cfg)");
 }
 

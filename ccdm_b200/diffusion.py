@@ -291,7 +291,7 @@ class GaussianDiffusion(nn.Module):
 
     # ------------------------------------------------------------------ fused sampling loops
     def _loop(self, kind, labels_emb, labels, shape, cond_scale, rescaled_phi, clip_denoised, trace=None,
-              x_init=None):
+              x_init=None, noise_fn=None):
         """kind: 'ddim' (diffusion.py:402-467) or 'ddpm' (:376-400)."""
         dev = self.device
         unet = self.unet
@@ -339,7 +339,9 @@ class GaussianDiffusion(nn.Module):
         eng.weights.refresh(stream)
 
         for i, draw in enumerate(draws):
-            if draw:
+            if draw and noise_fn is not None:           # test hook: the per-step draw comes from the caller's stream
+                st.noise.copy_(noise_fn().reshape(B, -1))
+            elif draw:
                 st.noise.normal_()                      # == torch.randn_like(img), drawn even when sigma == 0 (Q5)
             st.step()
             if trace is not None:
@@ -347,15 +349,18 @@ class GaussianDiffusion(nn.Module):
         return unnormalize_to_zero_to_one(prog.x_in.clone())
 
     @torch.no_grad()
-    def p_sample_loop(self, labels_emb, labels, shape, cond_scale=6.0, rescaled_phi=0.7, x_init=None):
-        return self._loop("ddpm", labels_emb, labels, shape, cond_scale, rescaled_phi, True, x_init=x_init)
+    def p_sample_loop(self, labels_emb, labels, shape, cond_scale=6.0, rescaled_phi=0.7, x_init=None, noise_fn=None):
+        return self._loop("ddpm", labels_emb, labels, shape, cond_scale, rescaled_phi, True, x_init=x_init,
+                          noise_fn=noise_fn)
 
     @torch.no_grad()
     def ddim_sample(self, labels_emb, labels, shape, cond_scale=6.0, rescaled_phi=0.7, clip_denoised=True,
-                    trace=None, x_init=None):
-        """``trace`` (list) and ``x_init`` (replaces the initial ``torch.randn`` draw) are test hooks beyond the
-        reference signature."""
-        return self._loop("ddim", labels_emb, labels, shape, cond_scale, rescaled_phi, clip_denoised, trace, x_init)
+                    trace=None, x_init=None, noise_fn=None):
+        """``trace`` (list), ``x_init`` (replaces the initial ``torch.randn`` draw) and ``noise_fn`` (``() -> tensor`` replacing
+        each per-step ``torch.randn_like`` draw, so that a CPU-seeded reference run can be replayed on the device) are test
+        hooks beyond the reference signature."""
+        return self._loop("ddim", labels_emb, labels, shape, cond_scale, rescaled_phi, clip_denoised, trace, x_init,
+                          noise_fn)
 
     @torch.no_grad()
     def sample(self, labels_emb, labels, cond_scale=6.0, rescaled_phi=0.7):

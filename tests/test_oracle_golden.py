@@ -47,6 +47,21 @@ def test_unet_forward(name):
             close(upd[k], v)
 
 
+def test_rc64_headline_widths():
+    """The headline network itself (dim 64, mults 1-2-2-4-8 at 64x64): oracle vs the reference's own outputs
+    (tests/golden/rc64.pt, tests/golden/make_golden_rc64.py)."""
+    from tests.golden.make_golden_rc64 import RC64, SEED, rc64_inputs
+    x, t, emb = rc64_inputs()
+    sd = make_state_dict(RC64, SEED)
+    gold = load("rc64")
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        close(unet_forward(sd, RC64, x, t, emb, cond_drop_prob=0.0), gold["cond"], 5e-5)
+        g, n = unet_forward_cfg(sd, RC64, x, t, emb, cond_scale=1.5, rescaled_phi=0.7)
+    close(n, gold["null"], 5e-5)
+    close(g, gold["guided"], 5e-5)
+
+
 @pytest.mark.parametrize("name", list(CFG_CASES))
 def test_cfg(name):
     spec_name, seed, scale, phi = CFG_CASES[name]
