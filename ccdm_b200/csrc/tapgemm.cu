@@ -63,6 +63,10 @@ struct TapGemmDev {
   int q_cols;
   int epi_alt;                            // the two epilogue warp groups take alternate tiles (n_tile <= 64)
   int pair;                               // CTA pairs: one tcgen05.mma.cta_group::2 (M = 256) covers a tile of each CTA
+  int head_n;                             // CCDM_EPI_HEAD: fused 1x1 head to head_n <= 4 fp32 NCHW planes
+  const float *head_w, *head_b;
+  float* head_out;
+  long long hsC, hsB;
 };
 
 // aux shared-memory block (after the resident weights and the stage ring)
@@ -72,6 +76,8 @@ struct __align__(16) TapGemmAux {
   float bias[kMaxN], gain[kMaxN];         // bias[n], g[n]*gain_mul (0 for padded channels)
   float gs[2][kMaxN], sh[2][kMaxN];       // per-tile g*(1+scale[b]), shift[b] (tiles inside one sample)
   float part[2][kTileM];                  // sum-of-squares exchange between the two column halves (tile parity)
+  float headw[4][128];                    // CCDM_EPI_HEAD: head weights (0 for k >= head_n, n >= N)
+  float hpart[2][4][kTileM];              // ... and the exchange of its partial dot products (split mode)
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
@@ -254,6 +260,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const bool ok = (n_base + i) < p.N;
     aux->bias[i] = ((kflags & CCDM_EPI_BIAS) && ok) ? p.bias[n_base + i] : 0.f;
     aux->gain[i] = ((kflags & CCDM_EPI_RMSNORM) && ok) ? p.gain[n_base + i] * p.gain_mul : 0.f;
+  }
+  if (kflags & CCDM_EPI_HEAD) {
+    for (int i = tid; i < 4 * 128; i += kThreads) {
+      const int k = i >> 7, n = i & 127;
+      aux->headw[k][n] = (k < p.head_n && n < p.N) ? p.head_w[k * p.N + n] : 0.f;
+    }
   }
   for (int i = tid; i < p.ngroups; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
   tc_fence_before();
@@ -578,6 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       const long long oo = p.ooff[z] + static_cast<long long>(bs) * p.osB + static_cast<long long>(h) * p.osH +
                            static_cast<long long>(w) * p.osW + n0;
       uint8_t* const stg_row = stg + static_cast<size_t>(lt & ob_mask) * p.out_bytes + m * 128;
+      float hd[4] = {0.f, 0.f, 0.f, 0.f};                  // CCDM_EPI_HEAD: this thread's partial head outputs
       float out_ss = 0.f, out_ss_hi = 0.f;                 // alternate-tile mode keeps the two column halves apart so that
                                                            // the sum rounds exactly as in the split mode (batch-shard invariance)
       if (kStoreTma && alt) {
@@ -698,7 +711,18 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             }
           }
         }
-        if (flags & CCDM_EPI_OUT_F32) {
+        if (flags & CCDM_EPI_HEAD) {                       // the tile is consumed here: 1x1 head, nothing else is stored
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < p.head_n) {
+              const float2* w2 = reinterpret_cast<const float2*>(aux->headw[k] + c * 32);
+              float2 s2 = make_float2(hd[k], 0.f);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) s2 = __ffma2_rn(v[i], w2[i], s2);
+              hd[k] = s2.x + s2.y;
+            }
+          }
+        } else if (flags & CCDM_EPI_OUT_F32) {
           if (valid) {
             float* op = reinterpret_cast<float*>(p.out) + oo + c * 32;
 #pragma unroll
@@ -743,6 +767,23 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         if (lane == 0) {
           if constexpr (kPair) mbar_arrive_cluster(&aux->tmem_empty[as], 0);
           else mbar_arrive(&aux->tmem_empty[as]);
+        }
+      }
+      if (flags & CCDM_EPI_HEAD) {
+        if (!alt) {                                        // split mode: the two column halves hold partial dot products
+          if (half == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) aux->hpart[lt & 1][k][m] = hd[k];
+          }
+          epi_bar();
+          if (half == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hd[k] += aux->hpart[lt & 1][k][m];
+          }
+        }
+        if (valid && (alt || half == 0)) {
+          float* ho = p.head_out + static_cast<long long>(bs) * p.hsB + static_cast<long long>(h) * p.gW + w;
+          for (int k = 0; k < p.head_n; ++k) ho[k * p.hsC] = hd[k] + __ldg(p.head_b + k);
         }
       }
       if ((flags & CCDM_EPI_SUMSQ_OUT) && !alt && half == 1) aux->part[lt & 1][m] = out_ss;   // combine the column halves
@@ -908,6 +949,7 @@ static int launch_variant(uint32_t flags, bool tma, dim3 grid, size_t smem_bytes
   }
 #undef CCDM_VARIANT
   if (flags == 0x101u) return launch_one<0x101u, false>(grid, smem_bytes, stream, maps, p);   // tc_mlp row-GEMM, fp32 out
+  if (flags == 0x1035u) return launch_one<0x1035u, false>(grid, smem_bytes, stream, maps, p); // final block 2 + residual + 1x1 head
   if (flags == 0x901u) return launch_one<0x901u, false>(grid, smem_bytes, stream, maps, p);   // generator output: tanh, fp32
   return tma ? launch_one<kRuntimeFlags, true>(grid, smem_bytes, stream, maps, p)
              : launch_one<kRuntimeFlags, false>(grid, smem_bytes, stream, maps, p);
@@ -933,7 +975,12 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
                CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: N=%d n_rows=%d n_tile=%d", a->N, a->n_rows, a->n_tile);
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_RMSNORM) || a->n_rows == a->n_tile, CCDM_ERR_UNSUPPORTED_SHAPE,
                "tapgemm: the RMSNorm epilogue needs all %d channels in one tile (n_tile=%d)", a->N, a->n_tile);
-  CCDM_REQUIRE(a->sched && a->wpacked && a->out, CCDM_ERR_BAD_ARG, "tapgemm: null sched/wpacked/out");
+  CCDM_REQUIRE(a->sched && a->wpacked && (a->out || (a->flags & CCDM_EPI_HEAD)), CCDM_ERR_BAD_ARG,
+               "tapgemm: null sched/wpacked/out");
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_HEAD) ||
+                   (a->head_w && a->head_b && a->head_out && a->head_n >= 1 && a->head_n <= 4 && a->n_rows == a->n_tile &&
+                    a->n_tile <= 128 && a->nz == 1 && !(a->flags & (CCDM_EPI_OUT_F32 | CCDM_EPI_SUMSQ_OUT))),
+               CCDM_ERR_BAD_ARG, "tapgemm: CCDM_EPI_HEAD needs head_w/head_b/head_out, 1 <= head_n <= 4, one N tile <= 128, nz == 1");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_BIAS) || a->bias, CCDM_ERR_BAD_ARG, "tapgemm: bias flag without pointer");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_ROWSCALE) || a->rowss, CCDM_ERR_BAD_ARG, "tapgemm: rowscale without rowss");
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_RMSNORM) || a->gain, CCDM_ERR_BAD_ARG, "tapgemm: rmsnorm without gain");
@@ -992,6 +1039,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   p.out = a->out; p.osW = a->osW; p.osH = a->osH; p.osB = a->osB;
   for (int i = 0; i < CCDM_MAX_Z; ++i) p.ooff[i] = a->ooff[i];
   p.out_rowss = a->out_rowss; p.q_scale = a->q_scale; p.q_cols = a->q_cols; p.gain_mul = a->gain_mul;
+  p.head_n = a->head_n; p.head_w = a->head_w; p.head_b = a->head_b; p.head_out = a->head_out; p.hsC = a->hsC; p.hsB = a->hsB;
 
   // ---- channel tiles: by default one (z, n-tile) combination per blockIdx.y.  When the layer has several channel
   // tiles with very different epilogue costs (linear-attention qkv: softmax | exp | copy) and all their weights fit in
@@ -1023,7 +1071,8 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
     // per-tile time is dominated by load / store latency that the pair's cross-SM handshakes lengthen.
     static const int pair_env = [] { const char* e = getenv("CCDM_TAPGEMM_PAIR"); return e ? atoi(e) : 16; }();
     p.pair = (pair_env != 0 && nkb >= pair_env && a->w_batch_rows == 0 && nsub == 1 && p.n_inner == 1 && a->R <= 3 && a->n_tile <= 256 &&
-              (a->n_tile / 2) % 16 == 0 && gx >= 2 && tiles_per_cta >= 2 && !(a->flags & CCDM_EPI_OUT_F32)) ? 1 : 0;
+              (a->n_tile / 2) % 16 == 0 && gx >= 2 && tiles_per_cta >= 2 &&
+              !(a->flags & (CCDM_EPI_OUT_F32 | CCDM_EPI_HEAD))) ? 1 : 0;
     if (p.pair) {
       if (gx & 1) ++gx;                                            // whole pairs; a trailing CTA may get dummy tiles only
       if (gx > sms / combos) {                                     // odd SM budget: re-balance over an even CTA count
@@ -1053,7 +1102,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   size_t budget = 226 * 1024 - aux_bytes - 1024;
   // bf16 outputs up to 256 channels per CTA leave through shared memory and TMA bulk stores (coalesced, clipped at the
   // tensor edges); wider tiles (4x4 bottleneck layers) and fp32 outputs keep per-thread stores
-  p.store_tma = (!(a->flags & CCDM_EPI_OUT_F32) && a->n_tile <= 256) ? 1 : 0;
+  p.store_tma = (!(a->flags & (CCDM_EPI_OUT_F32 | CCDM_EPI_HEAD)) && a->n_tile <= 256) ? 1 : 0;
   p.out_bytes = p.store_tma ? (uint32_t)((a->n_tile + 63) / 64) * 16384u : 0;
   p.out_bufs = p.store_tma ? ((tiles_per_cta > 1 && p.out_bytes <= 32768) ? 2 : 1) : 0;
   budget -= (size_t)p.out_bufs * p.out_bytes;

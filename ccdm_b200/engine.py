@@ -93,6 +93,7 @@ class TapGemmRec:
     q_cols: int = 0
     w_batch_rows: int = 0
     algo_flops: Optional[float] = None  # overrides tapgemm_flops (GEMMs that are not a reference convolution)
+    head: Optional[tuple] = None        # CCDM_EPI_HEAD: (weight [k][N] fp32, bias [k], out fp32 NCHW [B][k][H][W])
 
 
 @dataclass
@@ -204,8 +205,12 @@ def _fill_tapgemm(r: TapGemmRec) -> L.TapGemmArgs:
     a.scale_shift, a.ss_ld, a.ss_off = L.ptr(r.ss), r.ss_ld, r.ss_off
     a.resid = L.ptr(r.resid)
     a.rsW, a.rsH, a.rsB = r.resid_strides
-    a.out = r.out.data_ptr()
+    a.out = L.ptr(r.out)
     a.osW, a.osH, a.osB = r.out_strides
+    if r.head is not None:
+        hw_, hb_, ho_ = r.head
+        a.head_n, a.head_w, a.head_b, a.head_out = hw_.shape[0], hw_.data_ptr(), hb_.data_ptr(), ho_.data_ptr()
+        a.hsC, a.hsB = ho_.shape[2] * ho_.shape[3], ho_.shape[1] * ho_.shape[2] * ho_.shape[3]
     for i in range(L.MAX_Z):
         a.ooff[i] = r.ooff[i]
     a.out_rowss, a.q_scale, a.q_cols = L.ptr(r.out_rowss), r.q_scale, r.q_cols
@@ -455,10 +460,16 @@ class UnetProgram(Program):
 
     def conv(self, name, kind, srcs: List[torch.Tensor], conv_mod, out: torch.Tensor, flags=0, *, gain=None,
              ss_off=None, resid=None, out_rowss=None, rowss=None, cin_gain=None, cin_gain_mul=1.0, q=None,
-             views: Optional[List[ViewRec]] = None):
-        """Append one tap-GEMM over NHWC sources.  ``conv_mod`` owns .weight / .bias (nn.Conv2d)."""
+             views: Optional[List[ViewRec]] = None, head=None):
+        """Append one tap-GEMM over NHWC sources.  ``conv_mod`` owns .weight / .bias (nn.Conv2d).  ``head`` = (1x1 conv module,
+        fp32 NCHW output): the tile is not stored but projected by the 1x1 conv in the epilogue (CCDM_EPI_HEAD); ``out`` is then
+        only the (h, w, channels) geometry."""
         cins = [s.shape[3] for s in srcs] if views is None else [v.C for v in views]
         cout = conv_mod.weight.shape[0]
+        out_t = out
+        if head is not None:
+            out_t, out = None, torch.empty((self.B,) + tuple(out), device="meta")
+            flags |= L.EPI_HEAD
         gh, gw = out.shape[1], out.shape[2]
         if kind == "up2x3x3":
             gh, gw = gh // 2, gw // 2
@@ -490,8 +501,11 @@ class UnetProgram(Program):
         if conv_mod.bias is not None:
             flags |= L.EPI_BIAS
         rec = TapGemmRec(name, plan, views, gw, gh, self.B, tile, pack, pack.packed, pack.sched, n_rows,
-                         cout, n_tile, flags, out, ostr, ooff, bias=conv_mod.bias, rowss=rowss, gain=gain,
+                         cout, n_tile, flags, out_t, ostr, ooff, bias=conv_mod.bias, rowss=rowss, gain=gain,
                          gain_mul=math.sqrt(cout) if gain is not None else 1.0, out_rowss=out_rowss)
+        if head is not None:
+            hc, hout = head
+            rec.head = (hc.weight.view(hc.weight.shape[0], -1), hc.bias, hout)
         if ss_off is not None:
             rec.ss, rec.ss_ld, rec.ss_off = self.bufs["ss_all"], self.bufs["ss_all"].shape[1], ss_off
         if resid is not None:
@@ -529,7 +543,7 @@ class UnetProgram(Program):
         return None
 
     # ------------------------------------------------------------------ network pieces
-    def resblock(self, name, mod, srcs, h, w, ss_off, want_rowss=False):
+    def resblock(self, name, mod, srcs, h, w, ss_off, want_rowss=False, head=None):
         cout = mod.dim_out
         h1 = self.act(name + ".h1", h, w, cout)
         self.conv(name + ".block1.proj", "3x3", srcs, mod.block1.proj, h1,
@@ -540,11 +554,12 @@ class UnetProgram(Program):
         else:
             assert len(srcs) == 1
             res = srcs[0]
-        out = self.act(name + ".out", h, w, cout)
+        # head: the block's output feeds only the 1x1 final_conv, which then runs in block 2's epilogue (no 64-channel tensor)
+        out = self.act(name + ".out", h, w, cout) if head is None else (h, w, cout)
         rowss = self.buf(name + ".rowss", (self.B * h * w,), torch.float32) if want_rowss else None
         self.conv(name + ".block2.proj", "3x3", [h1], mod.block2.proj, out,
                   L.EPI_RMSNORM | L.EPI_SILU | L.EPI_RESID | (L.EPI_SUMSQ_OUT if want_rowss else 0),
-                  gain=mod.block2.norm.g, resid=res, out_rowss=rowss)
+                  gain=mod.block2.norm.g, resid=res, out_rowss=rowss, head=head)
         return out, rowss
 
     def linear_attention(self, name, mod, x, rowss, h, w):
@@ -762,9 +777,16 @@ class UnetProgram(Program):
             x = y
 
         # ---- head (unet.py:451-455)
-        x, _ = self.resblock("final_res_block", net.final_res_block, [x, stem], h, w, ss_offs["final_res_block"])
-        self.kernel("head_conv1", x=x, w=net.final_conv.weight, bias=net.final_conv.bias, out=self.out, B=B, H=H, W=W,
-                    Cin=net.init_dim, Cout=net.out_dim)
+        # final_conv (1x1 to out_dim channels, fp32 NCHW) lives in the final block's epilogue when the block's channels fit one
+        # tile and the channel norm is fused (otherwise: the standalone head kernel over the stored bf16 tensor)
+        fuse_head = net.out_dim <= 4 and net.init_dim <= 128
+        if fuse_head:
+            self.resblock("final_res_block", net.final_res_block, [x, stem], h, w, ss_offs["final_res_block"],
+                          head=(net.final_conv, self.out))
+        else:
+            x, _ = self.resblock("final_res_block", net.final_res_block, [x, stem], h, w, ss_offs["final_res_block"])
+            self.kernel("head_conv1", x=x, w=net.final_conv.weight, bias=net.final_conv.bias, out=self.out, B=B, H=H, W=W,
+                        Cin=net.init_dim, Cout=net.out_dim)
 
     def _resblocks(self):
         net = self.net

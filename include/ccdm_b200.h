@@ -57,6 +57,9 @@ int ccdm_struct_size(int which);
                                     the -bound shift from ccdm_kexp_bound, so v <= ~1 and nothing overflows) */
 #define CCDM_EPI_RELU 0x400u     /* v = max(v, 0)   (generator blocks, models/sngan.py:76-80) */
 #define CCDM_EPI_TANH 0x800u     /* v = tanh(v)     (generator output, models/sngan.py:128) */
+#define CCDM_EPI_HEAD 0x1000u    /* fused 1x1 head (unet.py:348,455 final_conv after final_res_block): instead of storing the
+                                    tile, head_out[b][k][h][w] = sum_n v[n]*head_w[k][n] + head_b[k] for k < head_n (fp32
+                                    NCHW); needs one N tile (n_rows == n_tile <= 128), nz == 1; `out` may be NULL */
 
 typedef struct ccdm_view {
   const void* ptr;    /* bf16; first element of the view (already offset for channel slices / parity planes) */
@@ -94,6 +97,13 @@ typedef struct ccdm_tapgemm_args {
   float* out_rowss;
   float q_scale;
   int32_t q_cols;
+  /* CCDM_EPI_HEAD: head_w fp32 [head_n][N], head_b fp32 [head_n], head_out fp32 with plane stride hsC and sample stride
+     hsB (elements; pixel (h, w) at h*gW + w inside a plane), 1 <= head_n <= 4 */
+  int32_t head_n;
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
+  int64_t hsC, hsB;
 } ccdm_tapgemm_args;
 
 int ccdm_tapgemm(const ccdm_tapgemm_args* args, void* stream);

@@ -37,7 +37,7 @@ def run_tapgemm(r: TapGemmRec):
     K = r.plan.nkb * KB
     wp = r.wpacked.reshape(-1, K).float()
     views = [_view_tensor(v) for v in r.views]
-    out_flat = r.out.reshape(-1)
+    out_flat = r.out.reshape(-1) if r.out is not None else None
     for z in range(r.plan.nz):
         acc = torch.zeros(gB, gH, gW, r.N)
         for kb in range(r.plan.nkb):
@@ -82,6 +82,10 @@ def run_tapgemm(r: TapGemmRec):
             rs_ = r.resid_strides
             res = torch.as_strided(r.resid.reshape(-1), (gB, gH, gW, r.N), (rs_[2], rs_[1], rs_[0], 1), 0).float()
             v = v + res
+        if r.flags & L.EPI_HEAD:                                              # fused 1x1 head: nothing else is stored
+            hw_, hb_, ho_ = r.head
+            ho_[:gB].copy_((v @ hw_.detach().float().t() + hb_.detach().float()).permute(0, 3, 1, 2))
+            continue
         os_ = r.out_strides
         dst = torch.as_strided(out_flat, (gB, gH, gW, r.N), (os_[2], os_[1], os_[0], 1),
                                out_flat.storage_offset() + r.ooff[z])

@@ -84,7 +84,7 @@ def tapgemm_abi(argref, stream):
     out_dtype = torch.float32 if a.flags & L.EPI_OUT_F32 else torch.bfloat16
     ooff = tuple(a.ooff[i] for i in range(L.MAX_Z))
     span = max(ooff[:a.nz]) + (a.gB - 1) * a.osB + (a.gH - 1) * a.osH + (a.gW - 1) * a.osW + a.N
-    out = _flat(a.out, span, out_dtype)
+    out = _flat(a.out, span, out_dtype) if a.out else None
     rec = TapGemmRec("abi", plan, views, a.gW, a.gH, a.gB, (a.tw, a.th, a.tb), None, wpacked, None, a.n_rows, a.N, a.n_tile,
                      a.flags, out, (a.osW, a.osH, a.osB), ooff, gain_mul=a.gain_mul, ss_ld=a.ss_ld, ss_off=a.ss_off,
                      q_scale=a.q_scale, q_cols=a.q_cols, w_batch_rows=a.w_batch_rows)
@@ -102,6 +102,10 @@ def tapgemm_abi(argref, stream):
         rec.resid, rec.resid_strides = _flat(a.resid, rspan, torch.bfloat16), (a.rsW, a.rsH, a.rsB)
     if a.out_rowss:
         rec.out_rowss = _flat(a.out_rowss, npix, torch.float32)
+    if a.flags & L.EPI_HEAD:
+        assert a.hsC == a.gH * a.gW and a.hsB == a.head_n * a.hsC
+        rec.head = (_flat(a.head_w, a.head_n * a.N, torch.float32).reshape(a.head_n, a.N), _flat(a.head_b, a.head_n, torch.float32),
+                    _flat(a.head_out, a.gB * a.hsB, torch.float32).reshape(a.gB, a.head_n, a.gH, a.gW))
     with torch.no_grad():
         run_tapgemm(rec)
     return 0
