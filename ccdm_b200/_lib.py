@@ -14,7 +14,7 @@ MAX_SRC, MAX_Z, STEP_NCOEF = 4, 4, 12
 
 EPI_BIAS, EPI_ROWSCALE, EPI_RMSNORM, EPI_SS = 0x1, 0x2, 0x4, 0x8
 EPI_SILU, EPI_RESID, EPI_QSOFTMAX, EPI_SUMSQ_OUT, EPI_OUT_F32, EPI_KEXP = 0x10, 0x20, 0x40, 0x80, 0x100, 0x200
-EPI_RELU, EPI_TANH, EPI_HEAD = 0x400, 0x800, 0x1000
+EPI_RELU, EPI_TANH, EPI_HEAD, EPI_RESACC = 0x400, 0x800, 0x1000, 0x2000
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU = 0, 1, 2, 3
 OBJ = {"pred_noise": 0, "pred_x0": 1, "pred_v": 2}
 
@@ -35,6 +35,7 @@ class TapGemmArgs(C.Structure):
         ("resid", vp), ("rsW", i64), ("rsH", i64), ("rsB", i64),
         ("out", vp), ("osW", i64), ("osH", i64), ("osB", i64), ("ooff", i64 * MAX_Z),
         ("out_rowss", vp), ("q_scale", f32), ("q_cols", i32),
+        ("n_res", i32), ("res_bias", vp),
         ("head_n", i32), ("head_w", vp), ("head_b", vp), ("head_out", vp), ("hsC", i64), ("hsB", i64),
     ]
 
@@ -80,6 +81,7 @@ SIGNATURES = {
     "ccdm_struct_size": (C.c_int, [C.c_int]),
     "ccdm_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), vp]),
     "ccdm_pack_weights": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, vp, vp]),
+    "ccdm_pack_weights_at": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, vp, i32, i32, vp]),
     "ccdm_rmsnorm_act": (C.c_int, [vp, vp, i64, i32, i32, vp, f32, vp, i32, i32, vp, vp, C.c_uint32, vp]),
     "ccdm_stem_im2row": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
     "ccdm_stem_pack": (C.c_int, [vp, vp, i32, i32, i32, vp]),

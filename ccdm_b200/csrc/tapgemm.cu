@@ -41,6 +41,7 @@ struct TapGemmMaps {
   CUtensorMap a[CCDM_MAX_SRC];
   CUtensorMap b;
   CUtensorMap o[CCDM_MAX_Z];              // bf16 output views (one per sub-problem) for the TMA-store epilogue
+  CUtensorMap r[CCDM_MAX_SRC];            // the sources again with a box of th rows: residual groups (one tap, no halo rows)
 };
 
 struct TapGemmDev {
@@ -63,6 +64,9 @@ struct TapGemmDev {
   int q_cols;
   int epi_alt;                            // the two epilogue warp groups take alternate tiles (n_tile <= 64)
   int pair;                               // CTA pairs: one tcgen05.mma.cta_group::2 (M = 256) covers a tile of each CTA
+  int n_res;                              // CCDM_EPI_RESACC: 1x1 load groups after the main ones, accumulated in a SECOND
+  uint32_t a_bytes_res;                   //   TMEM accumulator (res_conv / identity shortcut); their box bytes
+  const float* res_bias;
   int head_n;                             // CCDM_EPI_HEAD: fused 1x1 head to head_n <= 4 fp32 NCHW planes
   const float *head_w, *head_b;
   float* head_out;
@@ -76,6 +80,7 @@ struct __align__(16) TapGemmAux {
   float bias[kMaxN], gain[kMaxN];         // bias[n], g[n]*gain_mul (0 for padded channels)
   float gs[2][kMaxN], sh[2][kMaxN];       // per-tile g*(1+scale[b]), shift[b] (tiles inside one sample)
   float part[2][kTileM];                  // sum-of-squares exchange between the two column halves (tile parity)
+  float bias2[128];                       // CCDM_EPI_RESACC: res_conv bias
   float headw[4][128];                    // CCDM_EPI_HEAD: head weights (0 for k >= head_n, n >= N)
   float hpart[2][4][kTileM];              // ... and the exchange of its partial dot products (split mode)
 };
@@ -124,7 +129,7 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
                                                   uint32_t stage16, uint32_t b_lo0, uint32_t tap16, uint32_t b16,
                                                   uint32_t idesc, uint32_t tmem_base, uint32_t n_tile, int acc_mask,
                                                   int acc_shift, uint32_t full_bar, uint32_t empty_bar,
-                                                  uint32_t tfull_bar, uint32_t tempty_bar) {
+                                                  uint32_t tfull_bar, uint32_t tempty_bar, int n_res, uint32_t res_off) {
   int s = 0;
   uint32_t ph = 0;
   uint32_t a_lo = a_lo0;
@@ -147,6 +152,18 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
       a_lo += stage16;
       if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
     }
+    for (int g = 0; g < n_res; ++g) {                      // shortcut (1x1) groups -> the second accumulator
+      mbar_wait_a(full_bar + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_taps<1, kPair>(d_tmem + res_off, a_lo, b_lo, tap16, b16, idesc, g == 0);
+        commit_bar<kPair>(empty_bar + 8 * s);
+      }
+      __syncwarp();
+      b_lo += b16;
+      a_lo += stage16;
+      if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+    }
     if (elect_one()) commit_bar<kPair>(tfull_bar + 8 * as);
     __syncwarp();
   }
@@ -162,7 +179,7 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
                                               uint32_t nkb_b16, uint32_t tap16, uint32_t b16, uint32_t idesc,
                                               uint32_t tmem_base, uint32_t n_tile, int acc_mask, int acc_shift,
                                               uint32_t full_bar, uint32_t empty_bar, uint32_t tfull_bar,
-                                              uint32_t tempty_bar) {
+                                              uint32_t tempty_bar, int n_res, uint32_t res_off) {
   const int n_inner = kMultiN ? n_inner_rt : 1;             // compile-time 1 for the common case: no restore code
   int s = 0;
   uint32_t ph = 0;
@@ -197,6 +214,20 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
         b_lo += kR * b16;
         a_lo += stage16;
         if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+      }
+      if (!kMultiN) {
+        for (int g = 0; g < n_res; ++g) {                  // shortcut (1x1) groups -> the second accumulator
+          mbar_wait_a(full_bar + 8 * s, ph);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_taps<1, kPair>(d_tmem + res_off, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0);
+            commit_bar<kPair>(empty_bar + 8 * s);
+          }
+          __syncwarp();
+          b_lo += b16;
+          a_lo += stage16;
+          if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+        }
       }
       if (elect_one()) commit_bar<kPair>(tfull_bar + 8 * as);
       __syncwarp();
@@ -267,7 +298,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       aux->headw[k][n] = (k < p.head_n && n < p.N) ? p.head_w[k * p.N + n] : 0.f;
     }
   }
-  for (int i = tid; i < p.ngroups; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
+  if (kflags & CCDM_EPI_RESACC) {
+    for (int i = tid; i < 128; i += kThreads)
+      aux->bias2[i] = (p.res_bias && (n_base + i) < p.N) ? p.res_bias[n_base + i] : 0.f;
+  }
+  // (residual groups follow the nz * ngroups main entries; they exist only with nz == 1)
+  for (int i = tid; i < p.ngroups + p.n_res; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
   tc_fence_before();
   __syncthreads();
   if constexpr (kPair) cluster_sync_all();                 // the peer's barriers are initialised before anyone signals them
@@ -345,6 +381,28 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         __syncwarp();
         if (++s == n_stages) { s = 0; ph ^= 1u; }
       }
+      for (int g = 0; g < p.n_res; ++g) {                  // shortcut sources: one unshifted box of th rows per 64 channels
+        mbar_wait(&aux->a_empty[s], ph ^ 1u);
+        if (elect_one()) {
+          const int4 e = s_sched[n_groups + g];
+          const uint32_t st = smem_u32(ring + static_cast<size_t>(s) * stage_bytes);
+          const uint32_t fb = smem_u32(&aux->a_full[s]);
+          const uint32_t bytes = p.a_bytes_res + (b_res ? 0u : static_cast<uint32_t>(b_bytes));
+          const int kcol = (n_groups * p.R + g) * kBlockK;
+          if constexpr (kPair) {
+            if (crank == 0) mbar_arrive_expect_tx(&aux->a_full[s], 2u * bytes);
+            tma_load_4d_2sm(&maps.r[e.x], fb, st, e.w, w0, h0, b0);
+            if (!b_res) tma_load_2d_2sm(&maps.b, fb, st + p.a_bytes, kcol, z * p.n_rows + w_row0);
+          } else {
+            mbar_arrive_expect_tx(&aux->a_full[s], bytes);
+            tma_load_4d_a(&maps.r[e.x], fb, st, e.w, w0, h0, b0);
+            if (!b_res)
+              tma_load_2d(&maps.b, &aux->a_full[s], ring + static_cast<size_t>(s) * stage_bytes + p.a_bytes, kcol, wrow);
+          }
+        }
+        __syncwarp();
+        if (++s == n_stages) { s = 0; ph ^= 1u; }
+      }
     }
   } else if (warp == 1 && crank == 0) {
     // ============================================================== MMA issuer (warp-uniform loops, one lane issues;
@@ -368,21 +426,23 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const bool b_res = p.b_resident != 0, one_sub = p.nsub == 1;
     const uint32_t n_tile = p.n_tile, nkb_b16 = static_cast<uint32_t>(p.nkb) * b16, rb16 = static_cast<uint32_t>(R) * b16;
     const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages >> 1;
+    const int n_res = p.n_res;
+    const uint32_t res_off = static_cast<uint32_t>(p.acc_stages) * n_tile;   // second accumulators sit behind the main ones
     if (one_sub && R <= 3 && (n_inner == 1 || (R == 1 && b_res))) {
       const uint32_t full_bar = smem_u32(&aux->a_full[0]), empty_bar = smem_u32(&aux->a_empty[0]);
       const uint32_t tfull_bar = smem_u32(&aux->tmem_full[0]), tempty_bar = smem_u32(&aux->tmem_empty[0]);
 #define CCDM_MMA_LOOP(KR, RES, MULTI)                                                                                  \
   mma_loop_fast<KR, RES, MULTI>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo, nkb_b16, \
                                 tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, \
-                                tempty_bar)
+                                tempty_bar, n_res, res_off)
       if constexpr (kPair) {                               // host guarantees: one channel tile per CTA, R <= 3
 #define CCDM_PAIR_RES(KR)                                                                                                 \
   mma_loop_resident<KR, true>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base, \
-                              n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar)
+                              n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off)
 #define CCDM_PAIR_STR(KR)                                                                                                 \
   mma_loop_fast<KR, false, false, true>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo,  \
                                         nkb_b16, tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar,     \
-                                        empty_bar, tfull_bar, tempty_bar)
+                                        empty_bar, tfull_bar, tempty_bar, n_res, res_off)
         if (b_res) {
           if (R == 3) CCDM_PAIR_RES(3);
           else if (R == 2) CCDM_PAIR_RES(2);
@@ -399,13 +459,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       } else if (b_res) {
         if (R == 3)
           mma_loop_resident<3, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
         else if (R == 2)
           mma_loop_resident<2, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
         else
           mma_loop_resident<1, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
       } else {
         if (R == 3) CCDM_MMA_LOOP(3, false, false);
         else if (R == 2) CCDM_MMA_LOOP(2, false, false);
@@ -606,14 +666,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         constexpr int kCMode = decltype(cmode_tag)::value;
         tmem_ld32(trow + c * 32, r);
         tmem_ld_wait();
-        if (c == c_hi - 1) {                               // last TMEM read of this tile by this warp: release
+        auto release_acc = [&]() {                         // last TMEM read of this tile by this warp: release the stage
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             if constexpr (kPair) mbar_arrive_cluster(&aux->tmem_empty[as], 0);
             else mbar_arrive(&aux->tmem_empty[as]);
           }
-        }
+        };
+        if (c == c_hi - 1 && !(flags & CCDM_EPI_RESACC)) release_acc();
         float2 v[16];
         {
           const float2* b2 = reinterpret_cast<const float2*>(s_bias + c * 32);
@@ -697,6 +758,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             v[i].x = ex2_fast(e.x);
             v[i].y = ex2_fast(e.y);
           }
+        }
+        if (flags & CCDM_EPI_RESACC) {                     // shortcut from the second accumulator (+ res_conv bias)
+          tmem_ld32(trow + static_cast<uint32_t>(p.acc_stages * p.n_tile) + c * 32, r);
+          tmem_ld_wait();
+          if (c == c_hi - 1) release_acc();
+          const float2* b2 = reinterpret_cast<const float2*>(aux->bias2 + c * 32);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[i] = __fadd2_rn(v[i], __fadd2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), b2[i]));
         }
         if ((flags & CCDM_EPI_RESID) && valid) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.resid + ro + c * 32);
@@ -923,6 +993,8 @@ static int launch_variant(uint32_t flags, bool tma, dim3 grid, size_t smem_bytes
       CCDM_PAIR_VARIANT(0x01u)
       CCDM_PAIR_VARIANT(0x25u)
       CCDM_PAIR_VARIANT(0x00u)
+      CCDM_PAIR_VARIANT(0x2015u)
+      CCDM_PAIR_VARIANT(0x2095u)
       default:
         break;
     }
@@ -944,12 +1016,15 @@ static int launch_variant(uint32_t flags, bool tma, dim3 grid, size_t smem_bytes
     CCDM_VARIANT(0x21u)   // bias | resid                                   (bottleneck-attention to_out)
     CCDM_VARIANT(0x00u)   // plain                                          (data gradients, per-sample context products)
     CCDM_VARIANT(0x409u)  // bias | scale-shift | relu                      (generator conv1 + CondBN + ReLU)
+    CCDM_VARIANT(0x2015u) // bias | rmsnorm | silu | shortcut accumulator   (Block 2 + res_conv / identity in TMEM)
+    CCDM_VARIANT(0x2095u) //   ... + sum of squares for the next PreNorm
     default:
       break;
   }
 #undef CCDM_VARIANT
   if (flags == 0x101u) return launch_one<0x101u, false>(grid, smem_bytes, stream, maps, p);   // tc_mlp row-GEMM, fp32 out
   if (flags == 0x1035u) return launch_one<0x1035u, false>(grid, smem_bytes, stream, maps, p); // final block 2 + residual + 1x1 head
+  if (flags == 0x3015u) return launch_one<0x3015u, false>(grid, smem_bytes, stream, maps, p); //   ... with the shortcut accumulator
   if (flags == 0x901u) return launch_one<0x901u, false>(grid, smem_bytes, stream, maps, p);   // generator output: tanh, fp32
   return tma ? launch_one<kRuntimeFlags, true>(grid, smem_bytes, stream, maps, p)
              : launch_one<kRuntimeFlags, false>(grid, smem_bytes, stream, maps, p);
@@ -1012,7 +1087,23 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   }
   const int nsub = a->n_tile > 256 ? 2 : 1;
   const int n_sub = a->n_tile / nsub;
-  const int nkb = a->ngroups * a->R;
+  const int n_res = (a->flags & CCDM_EPI_RESACC) ? a->n_res : 0;
+  CCDM_REQUIRE(!(a->flags & CCDM_EPI_RESACC) ||
+                   (a->n_res >= 1 && a->nz == 1 && a->n_tile <= 128 && a->w_batch_rows == 0 && a->R <= 3 &&
+                    !(a->flags & CCDM_EPI_RESID)),
+               CCDM_ERR_BAD_ARG,
+               "tapgemm: CCDM_EPI_RESACC needs n_res >= 1, nz == 1, n_tile <= 128, shared weights, R <= 3 and no CCDM_EPI_RESID");
+  const int nkb = a->ngroups * a->R + n_res;               // K blocks of the packed weights: main taps, then the shortcut's
+  if (n_res > 0) {                                         // shortcut boxes: th rows (one tap, no halo rows)
+    for (int i = 0; i < CCDM_MAX_SRC; ++i) {
+      const ccdm_view& v = a->src[i < a->n_src ? i : 0];
+      cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.B};
+      cuuint64_t str[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sB * 2};
+      cuuint32_t box[4] = {kBlockK, (cuuint32_t)a->tw, (cuuint32_t)a->th, (cuuint32_t)a->tb};
+      int rc = encode_map_bf16(&maps.r[i], v.ptr, 4, dims, str, box);
+      if (rc != CCDM_OK) return rc;
+    }
+  }
   CCDM_REQUIRE(n_sub % 16 == 0 && n_sub <= 256, CCDM_ERR_UNSUPPORTED_SHAPE, "tapgemm: n_sub=%d", n_sub);
 
   TapGemmDev p;
@@ -1031,7 +1122,10 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   p.sched = reinterpret_cast<const int4*>(a->sched);
   p.flags = a->flags;
   p.acc_stages = a->n_tile <= 256 ? 2 : 1;
-  p.tmem_cols = pow2_cols(a->n_tile * p.acc_stages);
+  p.tmem_cols = pow2_cols(a->n_tile * p.acc_stages * (n_res > 0 ? 2 : 1));
+  p.n_res = n_res;
+  p.res_bias = a->res_bias;
+  p.a_bytes_res = (uint32_t)(a->th * a->tw * a->tb) * 128u;
   p.bias = a->bias; p.rowss = a->rowss; p.gain = a->gain; p.ss = a->scale_shift;
   p.ss_ld = a->ss_ld; p.ss_off = a->ss_off;
   p.resid = reinterpret_cast<const __nv_bfloat16*>(a->resid);
@@ -1046,7 +1140,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   // shared memory, every CTA walks ALL channel tiles of its pixel tiles instead: balanced, and A is fetched once.
   {
     const size_t all_b = (size_t)a->n_rows * nkb * 128;
-    const bool plain_epi = !(a->flags & (CCDM_EPI_RMSNORM | CCDM_EPI_SS | CCDM_EPI_RESID | CCDM_EPI_SUMSQ_OUT));
+    const bool plain_epi = !(a->flags & (CCDM_EPI_RMSNORM | CCDM_EPI_SS | CCDM_EPI_RESID | CCDM_EPI_SUMSQ_OUT | CCDM_EPI_RESACC));
     if (p.n_tiles > 1 && a->nz == 1 && a->w_batch_rows == 0 && plain_epi && a->n_rows <= kMaxN &&
         all_b <= 64 * 1024 && a->ngroups <= 2 && a->n_tile <= 256) {
       p.n_inner = p.n_tiles;
@@ -1098,7 +1192,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   // ---- shared-memory plan
   const uint32_t b_bytes = (uint32_t)(p.pair ? a->n_tile / 2 : a->n_tile) * 128u;
   p.a_bytes = (uint32_t)(box_h * a->tw * a->tb) * 128u;
-  const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)a->ngroups * sizeof(int4);
+  const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)(a->ngroups + n_res) * sizeof(int4);
   size_t budget = 226 * 1024 - aux_bytes - 1024;
   // bf16 outputs up to 256 channels per CTA leave through shared memory and TMA bulk stores (coalesced, clipped at the
   // tensor edges); wider tiles (4x4 bottleneck layers) and fp32 outputs keep per-thread stores
@@ -1117,7 +1211,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   p.res_bytes = p.b_resident ? (uint32_t)res_all : 0;
   p.stage_bytes = p.a_bytes + (p.b_resident ? 0 : (uint32_t)a->R * b_bytes);
   int stages = (int)((budget - p.res_bytes) / p.stage_bytes);
-  int useful = a->ngroups * (tiles_per_cta > 1 ? 2 : 1);           // about two tiles of lookahead ...
+  int useful = (a->ngroups + n_res) * (tiles_per_cta > 1 ? 2 : 1); // about two tiles of lookahead ...
   static const int min_stages = [] { const char* e = getenv("CCDM_TAPGEMM_MINSTAGES"); return e ? atoi(e) : 4; }();
   if (tiles_per_cta > 1 && useful < min_stages) useful = min_stages;   // ... but never fewer than 4 boxes in flight
   if (stages > kMaxStages) stages = kMaxStages;
@@ -1155,16 +1249,18 @@ namespace ccdm {
 __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_total, int ntaps,
                                     const int4* __restrict__ psched, int nkb, int n_rows,
                                     const float* __restrict__ cin_gain, float gain_mul,
-                                    __nv_bfloat16* __restrict__ out, long long total) {
-  // one thread per packed element: idx = ((z*n_rows + n)*nkb + kb)*64 + j
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(idx & 63);
-    const long long t = idx >> 6;
+                                    __nv_bfloat16* __restrict__ out, long long total, int nkb_total, int kb0) {
+  // one thread per packed element: logical idx = ((z*n_rows + n)*nkb + kb)*64 + j, stored in a matrix of nkb_total K
+  // blocks per row at block kb0 + kb (two weights -- a conv and its block's shortcut -- share one packed matrix)
+  for (long long lidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; lidx < total;
+       lidx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(lidx & 63);
+    const long long t = lidx >> 6;
     const int kb = (int)(t % nkb);
     const long long zn = t / nkb;
     const int n = (int)(zn % n_rows);
     const int z = (int)(zn / n_rows);
+    const long long idx = ((zn * nkb_total) + kb0 + kb) * 64 + j;
     const int4 e = psched[z * nkb + kb];
     float acc = 0.f;
     if (n < cout && j < e.y) {
@@ -1180,18 +1276,26 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
 }
 }  // namespace ccdm
 
-extern "C" int ccdm_pack_weights(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
-                                 int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain, float gain_mul,
-                                 void* wpacked, void* stream) {
+extern "C" int ccdm_pack_weights_at(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
+                                    int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain, float gain_mul,
+                                    void* wpacked, int32_t nkb_total, int32_t kb0, void* stream) {
   CCDM_REQUIRE(w && psched && wpacked, CCDM_ERR_BAD_ARG, "pack_weights: null pointer");
   CCDM_REQUIRE(cout > 0 && cin_total > 0 && ntaps > 0 && ntaps <= 32 && nz > 0 && nkb > 0 && n_rows >= cout,
                CCDM_ERR_BAD_ARG, "pack_weights: bad sizes cout=%d cin=%d taps=%d nz=%d nkb=%d n_rows=%d", cout,
                cin_total, ntaps, nz, nkb, n_rows);
+  CCDM_REQUIRE(kb0 >= 0 && kb0 + nkb <= nkb_total, CCDM_ERR_BAD_ARG, "pack_weights: K blocks [%d, %d) of %d", kb0,
+               kb0 + nkb, nkb_total);
   const long long total = (long long)nz * n_rows * nkb * 64;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_weights_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, cout, cin_total, ntaps, reinterpret_cast<const int4*>(psched), nkb, n_rows, cin_gain, gain_mul,
-      reinterpret_cast<__nv_bfloat16*>(wpacked), total);
+      reinterpret_cast<__nv_bfloat16*>(wpacked), total, nkb_total, kb0);
   return after_launch("pack_weights_kernel");
+}
+
+extern "C" int ccdm_pack_weights(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
+                                 int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain, float gain_mul,
+                                 void* wpacked, void* stream) {
+  return ccdm_pack_weights_at(w, cout, cin_total, ntaps, psched, nz, nkb, n_rows, cin_gain, gain_mul, wpacked, nkb, 0, stream);
 }

@@ -58,6 +58,8 @@ class PackRec:
     gain_mul: float = 1.0
     row_off: int = 0            # first packed row this weight occupies (tc_mlp layers share one matrix)
     rows_alloc: int = 0
+    nkb_total: int = 0          # > 0: the packed matrix has this many K blocks per row and this weight starts at block kb0
+    kb0: int = 0                #      (a conv and its block's shortcut share one matrix, CCDM_EPI_RESACC)
 
 
 @dataclass
@@ -94,6 +96,10 @@ class TapGemmRec:
     w_batch_rows: int = 0
     algo_flops: Optional[float] = None  # overrides tapgemm_flops (GEMMs that are not a reference convolution)
     head: Optional[tuple] = None        # CCDM_EPI_HEAD: (weight [k][N] fp32, bias [k], out fp32 NCHW [B][k][H][W])
+    n_res: int = 0                      # CCDM_EPI_RESACC: shortcut load groups (sched rows after the main ones)
+    res_sched: Optional[list] = None    # [(view index, 0, 0, c0)]
+    res_bias: Optional[torch.Tensor] = None
+    res_cin: int = 0                    # input channels of a real res_conv (0 for the identity shortcut): FLOP accounting
 
 
 @dataclass
@@ -188,7 +194,7 @@ def tapgemm_flops(r: "TapGemmRec") -> float:
         pos = r.gB * (2 * r.gH) * (2 * r.gW)
     else:
         pos = r.gB * r.gH * r.gW
-    return 2.0 * pos * r.N * cin * r.plan.ntaps
+    return 2.0 * pos * r.N * (cin * r.plan.ntaps + r.res_cin)
 
 
 def _fill_tapgemm(r: TapGemmRec) -> L.TapGemmArgs:
@@ -214,6 +220,7 @@ def _fill_tapgemm(r: TapGemmRec) -> L.TapGemmArgs:
     for i in range(L.MAX_Z):
         a.ooff[i] = r.ooff[i]
     a.out_rowss, a.q_scale, a.q_cols = L.ptr(r.out_rowss), r.q_scale, r.q_cols
+    a.n_res, a.res_bias = r.n_res, L.ptr(r.res_bias)
     return a
 
 
@@ -227,7 +234,11 @@ def _make_call(lib, r, keep):
         w = r.weight
         cout, cin_total = w.shape[0], w.shape[1]
         ntaps = w.numel() // (cout * cin_total)
-        dst = r.packed.data_ptr() + 2 * r.row_off * r.plan.nkb * KB
+        dst = r.packed.data_ptr() + 2 * r.row_off * (r.nkb_total or r.plan.nkb) * KB
+        if r.nkb_total:
+            return lib.ccdm_pack_weights_at, (w.data_ptr(), cout, cin_total, ntaps, r.psched.data_ptr(), r.plan.nz,
+                                              r.plan.nkb, r.n_rows, L.ptr(r.cin_gain), r.gain_mul, dst, r.nkb_total,
+                                              r.kb0), "pack:" + r.name
         return lib.ccdm_pack_weights, (w.data_ptr(), cout, cin_total, ntaps, r.psched.data_ptr(), r.plan.nz, r.plan.nkb,
                                        r.n_rows, L.ptr(r.cin_gain), r.gain_mul, dst), "pack:" + r.name
     k, a = r.kind, r.a
@@ -311,23 +322,32 @@ class WeightStore:
         self._stamp = None
         self._params: List[torch.Tensor] = []
 
-    def add(self, name, weight, plan: ConvPlan, n_rows, cin_gain=None, gain_mul=1.0, shared=None, row_off=0) -> PackRec:
+    def add(self, name, weight, plan: ConvPlan, n_rows, cin_gain=None, gain_mul=1.0, shared=None, row_off=0,
+            nkb_total=0, kb0=0) -> PackRec:
         if name in self.packs:
             return self.packs[name]
         dev = self.device
         if shared is None:
-            packed = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
+            packed = torch.zeros(plan.nz * n_rows, (nkb_total or plan.nkb) * KB, dtype=torch.bfloat16, device=dev)
         else:
             packed = shared
         sched = torch.tensor(plan.sched, dtype=torch.int32, device=dev).contiguous()
         psched = torch.tensor(plan.psched, dtype=torch.int32, device=dev).contiguous()
-        rec = PackRec(name, weight, plan, n_rows, packed, sched, psched, cin_gain, gain_mul, row_off)
+        rec = PackRec(name, weight, plan, n_rows, packed, sched, psched, cin_gain, gain_mul, row_off, nkb_total=nkb_total,
+                      kb0=kb0)
         self.packs[name] = rec
         self.program.recs.append(rec)
         self._params.append(weight)
         if cin_gain is not None:
             self._params.append(cin_gain)
         return rec
+
+    def identity_weight(self, c: int) -> torch.Tensor:
+        """[c, c, 1, 1] identity "1x1 conv" (the shortcut of a ResnetBlock whose channel count does not change, unet.py:165)."""
+        key = f"eye:{c}"
+        if key not in self.packs:
+            self.packs[key] = torch.eye(c, dtype=torch.float32, device=self.device).view(c, c, 1, 1).contiguous()
+        return self.packs[key]
 
     def kexp_bias(self, pack: PackRec, lo: int, hi: int) -> torch.Tensor:
         """Bias vector holding the softmax shift of the k columns of a to_qkv weight (refreshed with the pack)."""
@@ -365,6 +385,9 @@ class WeightStore:
 
 
 # --------------------------------------------------------------------------------------------- program builder
+
+RESACC_ENABLED = os.environ.get("CCDM_RESACC", "1") != "0"      # A/B switch for profiles; the fused shortcut is the default
+
 
 class UnetEngine:
     def __init__(self, net):
@@ -460,7 +483,7 @@ class UnetProgram(Program):
 
     def conv(self, name, kind, srcs: List[torch.Tensor], conv_mod, out: torch.Tensor, flags=0, *, gain=None,
              ss_off=None, resid=None, out_rowss=None, rowss=None, cin_gain=None, cin_gain_mul=1.0, q=None,
-             views: Optional[List[ViewRec]] = None, head=None):
+             views: Optional[List[ViewRec]] = None, head=None, res=None):
         """Append one tap-GEMM over NHWC sources.  ``conv_mod`` owns .weight / .bias (nn.Conv2d).  ``head`` = (1x1 conv module,
         fp32 NCHW output): the tile is not stored but projected by the 1x1 conv in the epilogue (CCDM_EPI_HEAD); ``out`` is then
         only the (h, w, channels) geometry."""
@@ -486,11 +509,30 @@ class UnetProgram(Program):
             return self._conv_split(name, kind, plan, tile, srcs, views, conv_mod, out, flags, gain, ss_off, resid,
                                     out_rowss, gw, gh)
         n_rows, n_tile = n_tiling(cout, full_row)
-        pack = self.weights.add(f"{name}/R{plan.R}", conv_mod.weight, plan, n_rows, cin_gain, cin_gain_mul)
         if views is None:
             views = []
             for s in srcs:
                 views += parity_views(s) if plan.n_views == 4 else [nhwc_view(s)]
+        sched_t, n_res, res_sched, res_bias, res_cin = None, 0, None, None, 0
+        if res is not None:
+            # the block's shortcut (res_conv over the block's inputs, or the identity) as extra 1x1 load groups of THIS
+            # launch, accumulated in a second TMEM accumulator (CCDM_EPI_RESACC): no res_conv launch, no residual tensor
+            res_srcs, res_mod = res
+            rplan = plan_conv("1x1", [t.shape[3] for t in res_srcs], cout)
+            n_res, nkb_total = rplan.ngroups, plan.nkb + rplan.ngroups
+            pack = self.weights.add(f"{name}/R{plan.R}+res", conv_mod.weight, plan, n_rows, cin_gain, cin_gain_mul,
+                                    nkb_total=nkb_total)
+            rw = res_mod.weight if res_mod is not None else self.weights.identity_weight(cout)
+            self.weights.add(f"{name}/res", rw, rplan, n_rows, shared=pack.packed, nkb_total=nkb_total, kb0=plan.nkb)
+            res_sched = [(len(views) + src, 0, 0, c0) for (src, _, _, c0) in rplan.sched]
+            views = views + [nhwc_view(t) for t in res_srcs]
+            assert len(views) <= L.MAX_SRC
+            sched_t = torch.tensor(list(plan.sched) + res_sched, dtype=torch.int32, device=self.device).contiguous()
+            res_bias = res_mod.bias if res_mod is not None else None
+            res_cin = sum(rplan.cins) if res_mod is not None else 0
+            flags |= L.EPI_RESACC
+        else:
+            pack = self.weights.add(f"{name}/R{plan.R}", conv_mod.weight, plan, n_rows, cin_gain, cin_gain_mul)
         co = out.shape[3]
         if plan.out_parity:
             ostr = (2 * co, 2 * out.shape[2] * co, out.shape[1] * out.shape[2] * co)
@@ -500,9 +542,11 @@ class UnetProgram(Program):
             ooff = (0, 0, 0, 0)
         if conv_mod.bias is not None:
             flags |= L.EPI_BIAS
-        rec = TapGemmRec(name, plan, views, gw, gh, self.B, tile, pack, pack.packed, pack.sched, n_rows,
+        rec = TapGemmRec(name, plan, views, gw, gh, self.B, tile, pack, pack.packed,
+                         pack.sched if sched_t is None else sched_t, n_rows,
                          cout, n_tile, flags, out_t, ostr, ooff, bias=conv_mod.bias, rowss=rowss, gain=gain,
-                         gain_mul=math.sqrt(cout) if gain is not None else 1.0, out_rowss=out_rowss)
+                         gain_mul=math.sqrt(cout) if gain is not None else 1.0, out_rowss=out_rowss, n_res=n_res,
+                         res_sched=res_sched, res_bias=res_bias, res_cin=res_cin)
         if head is not None:
             hc, hout = head
             rec.head = (hc.weight.view(hc.weight.shape[0], -1), hc.bias, hout)
@@ -548,7 +592,17 @@ class UnetProgram(Program):
         h1 = self.act(name + ".h1", h, w, cout)
         self.conv(name + ".block1.proj", "3x3", srcs, mod.block1.proj, h1,
                   L.EPI_RMSNORM | L.EPI_SS | L.EPI_SILU, gain=mod.block1.norm.g, ss_off=ss_off)
-        if isinstance(mod.res_conv, torch.nn.Conv2d):
+        has_conv = isinstance(mod.res_conv, torch.nn.Conv2d)
+        # shortcut inside block 2's launch when its channels fit one <= 128-wide tile with the fused norm (second TMEM
+        # accumulator); wider / split layers keep the separate res_conv launch and the residual read in the epilogue
+        tile = tile_box(w, h, square=True)
+        m_tiles = ((w + tile[0] - 1) // tile[0]) * ((h + tile[1] - 1) // tile[1]) * ((self.B + tile[2] - 1) // tile[2])
+        fuse_res = (RESACC_ENABLED and cout <= 128 and not (cout >= 256 and m_tiles < 100) and
+                    len(srcs) + 1 <= L.MAX_SRC and sum(-(-t.shape[3] // KB) for t in srcs) <= 8)
+        res_arg = None
+        if fuse_res:
+            res, res_arg = None, (srcs, mod.res_conv if has_conv else None)
+        elif has_conv:
             res = self.act(name + ".res", h, w, cout)
             self.conv(name + ".res_conv", "1x1", srcs, mod.res_conv, res)
         else:
@@ -558,8 +612,8 @@ class UnetProgram(Program):
         out = self.act(name + ".out", h, w, cout) if head is None else (h, w, cout)
         rowss = self.buf(name + ".rowss", (self.B * h * w,), torch.float32) if want_rowss else None
         self.conv(name + ".block2.proj", "3x3", [h1], mod.block2.proj, out,
-                  L.EPI_RMSNORM | L.EPI_SILU | L.EPI_RESID | (L.EPI_SUMSQ_OUT if want_rowss else 0),
-                  gain=mod.block2.norm.g, resid=res, out_rowss=rowss, head=head)
+                  L.EPI_RMSNORM | L.EPI_SILU | (0 if fuse_res else L.EPI_RESID) | (L.EPI_SUMSQ_OUT if want_rowss else 0),
+                  gain=mod.block2.norm.g, resid=res, out_rowss=rowss, head=head, res=res_arg)
         return out, rowss
 
     def linear_attention(self, name, mod, x, rowss, h, w):

@@ -57,6 +57,11 @@ int ccdm_struct_size(int which);
                                     the -bound shift from ccdm_kexp_bound, so v <= ~1 and nothing overflows) */
 #define CCDM_EPI_RELU 0x400u     /* v = max(v, 0)   (generator blocks, models/sngan.py:76-80) */
 #define CCDM_EPI_TANH 0x800u     /* v = tanh(v)     (generator output, models/sngan.py:128) */
+#define CCDM_EPI_RESACC 0x2000u  /* shortcut in the SAME launch (ResnetBlock: h + res_conv(x), unet.py:165,187): n_res extra load
+                                    groups -- unshifted 64-channel boxes of the sources named by sched entries
+                                    [nz*ngroups, +n_res) -- are multiplied with the last n_res K blocks of wpacked into a
+                                    second TMEM accumulator, and v += acc2[n] + res_bias[n] after the tail (identity
+                                    shortcut = identity K block).  nz == 1, n_tile <= 128, shared weights, no CCDM_EPI_RESID */
 #define CCDM_EPI_HEAD 0x1000u    /* fused 1x1 head (unet.py:348,455 final_conv after final_res_block): instead of storing the
                                     tile, head_out[b][k][h][w] = sum_n v[n]*head_w[k][n] + head_b[k] for k < head_n (fp32
                                     NCHW); needs one N tile (n_rows == n_tile <= 128), nz == 1; `out` may be NULL */
@@ -99,6 +104,8 @@ typedef struct ccdm_tapgemm_args {
   int32_t q_cols;
   /* CCDM_EPI_HEAD: head_w fp32 [head_n][N], head_b fp32 [head_n], head_out fp32 with plane stride hsC and sample stride
      hsB (elements; pixel (h, w) at h*gW + w inside a plane), 1 <= head_n <= 4 */
+  int32_t n_res;         /* CCDM_EPI_RESACC: shortcut load groups; wpacked then has ngroups*R + n_res K blocks per row */
+  const float* res_bias; /* fp32 [N] or NULL */
   int32_t head_n;
   const float* head_w;
   const float* head_b;
@@ -115,6 +122,11 @@ int ccdm_tapgemm(const ccdm_tapgemm_args* args, void* stream);
 int ccdm_pack_weights(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
                       int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain, float gain_mul, void* wpacked,
                       void* stream);
+/* The same, into K blocks [kb0, kb0 + nkb) of a packed matrix with nkb_total K blocks per row (a conv and its block's shortcut
+ * share one matrix, CCDM_EPI_RESACC). */
+int ccdm_pack_weights_at(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
+                         int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain, float gain_mul, void* wpacked,
+                         int32_t nkb_total, int32_t kb0, void* stream);
 
 /* Standalone channel RMSNorm + tail for rows of C contiguous bf16 channels (unet.py:88-89,145-151), used when a
  * layer's channels do not fit one tap-GEMM tile (C > 512) or its GEMM is split over output channels:

@@ -26,15 +26,16 @@ def run_pack(r: PackRec):
     w4 = w.reshape(w.shape[0], w.shape[1], -1, 1)
     g = r.cin_gain.detach().reshape(-1).float() if r.cin_gain is not None else None
     packed = pack_weights_emu(r.plan, w4, r.n_rows, g, r.gain_mul)          # [nz, n_rows, K]
-    K = r.plan.nkb * KB
+    K = (r.nkb_total or r.plan.nkb) * KB
     dst = r.packed.reshape(-1, K)
+    c0 = r.kb0 * KB
     for z in range(r.plan.nz):
-        dst[r.row_off + z * r.n_rows: r.row_off + (z + 1) * r.n_rows] = packed[z].to(torch.bfloat16)
+        dst[r.row_off + z * r.n_rows: r.row_off + (z + 1) * r.n_rows, c0: c0 + r.plan.nkb * KB] = packed[z].to(torch.bfloat16)
 
 
 def run_tapgemm(r: TapGemmRec):
     gB, gH, gW = r.gB, r.gH, r.gW
-    K = r.plan.nkb * KB
+    K = (r.plan.nkb + r.n_res) * KB
     wp = r.wpacked.reshape(-1, K).float()
     views = [_view_tensor(v) for v in r.views]
     out_flat = r.out.reshape(-1) if r.out is not None else None
@@ -78,6 +79,15 @@ def run_tapgemm(r: TapGemmRec):
         if r.flags & L.EPI_KEXP:
             qc = r.q_cols
             v = torch.cat([v[..., :qc], v[..., qc:2 * qc].exp(), v[..., 2 * qc:]], -1)
+        if r.flags & L.EPI_RESACC:                                           # shortcut: 1x1 groups in a second accumulator
+            acc2 = torch.zeros(gB, gH, gW, r.N)
+            for g2, (src, _, _, c0) in enumerate(r.res_sched):
+                a2 = shifted(views[src], 0, 0, gH, gW, c0)[:gB]
+                kb = r.plan.nkb + g2
+                acc2 += a2 @ wp[: r.N, kb * KB:(kb + 1) * KB].t()
+            if r.res_bias is not None:
+                acc2 = acc2 + r.res_bias.detach().float()[: r.N]
+            v = v + acc2
         if r.flags & L.EPI_RESID:
             rs_ = r.resid_strides
             res = torch.as_strided(r.resid.reshape(-1), (gB, gH, gW, r.N), (rs_[2], rs_[1], rs_[0], 1), 0).float()

@@ -34,7 +34,7 @@ class HostLib:
                                               "optim.cu")]
         handles.append(C.CDLL(build_extract("wgrad.cu", ["unpack_wgrad_kernel", "pack_weights_t_kernel"],
                                             ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"])))
-        handles.append(C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights"])))
+        handles.append(C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights_at", "ccdm_pack_weights"])))
         handles.append(C.CDLL(build_extract("linattn.cu", ["kexp_bound_kernel"], ["ccdm_kexp_bound"])))
         handles.append(C.CDLL(build_extract("linattn_fused.cu", ["linattn_fold_parts_kernel"], ["ccdm_linattn_fold_partials"])))
         for name, (res, args) in L.SIGNATURES.items():
@@ -63,9 +63,11 @@ class _Plan:
     def __init__(self, a):
         self.nz, self.ngroups, self.R = a.nz, a.ngroups, a.R
         self.nkb = a.ngroups * a.R
-        n = a.nz * a.ngroups * 4
+        n_res = a.n_res if a.flags & L.EPI_RESACC else 0
+        n = (a.nz * a.ngroups + n_res) * 4
         s = torch.frombuffer((C.c_int32 * n).from_address(a.sched), dtype=torch.int32).reshape(-1, 4).tolist()
-        self.sched = [tuple(r) for r in s]
+        self.sched = [tuple(r) for r in s[: a.nz * a.ngroups]]
+        self.res_sched = [tuple(r) for r in s[a.nz * a.ngroups:]]
 
 
 def tapgemm_abi(argref, stream):
@@ -78,7 +80,7 @@ def tapgemm_abi(argref, stream):
         span = (v.B - 1) * v.sB + (v.H - 1) * v.sH + (v.W - 1) * v.sW + v.C
         views.append(ViewRec(_flat(v.ptr, span, torch.bfloat16), 0, v.C, v.W, v.H, v.B, v.sW, v.sH, v.sB))
     plan = _Plan(a)
-    K_ = plan.nkb * KB
+    K_ = (plan.nkb + len(plan.res_sched)) * KB
     rows = (a.gB * a.w_batch_rows) if a.w_batch_rows else a.nz * a.n_rows
     wpacked = _flat(a.wpacked, rows * K_, torch.bfloat16).reshape(rows, K_)
     out_dtype = torch.float32 if a.flags & L.EPI_OUT_F32 else torch.bfloat16
@@ -102,6 +104,10 @@ def tapgemm_abi(argref, stream):
         rec.resid, rec.resid_strides = _flat(a.resid, rspan, torch.bfloat16), (a.rsW, a.rsH, a.rsB)
     if a.out_rowss:
         rec.out_rowss = _flat(a.out_rowss, npix, torch.float32)
+    if a.flags & L.EPI_RESACC:
+        rec.n_res, rec.res_sched = len(plan.res_sched), plan.res_sched
+        if a.res_bias:
+            rec.res_bias = _flat(a.res_bias, a.N, torch.float32)
     if a.flags & L.EPI_HEAD:
         assert a.hsC == a.gH * a.gW and a.hsB == a.head_n * a.hsC
         rec.head = (_flat(a.head_w, a.head_n * a.N, torch.float32).reshape(a.head_n, a.N), _flat(a.head_b, a.head_n, torch.float32),

@@ -18,7 +18,7 @@ EMULATED = {"linattn_context", "linattn_kv_partials", "linattn_q_out"}          
 class HostLib:
     def __init__(self):
         handles = [C.CDLL(build("kernels.cu")), C.CDLL(build("train_kernels.cu")), C.CDLL(build("groupnorm.cu")),
-                   C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights"])),
+                   C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights_at", "ccdm_pack_weights"])),
                    C.CDLL(build_extract("linattn.cu", ["kexp_bound_kernel"], ["ccdm_kexp_bound"])),
                    C.CDLL(build_extract("linattn_fused.cu", ["linattn_fold_parts_kernel"], ["ccdm_linattn_fold_partials"]))]
         for name, (res, args) in L.SIGNATURES.items():

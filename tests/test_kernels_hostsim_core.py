@@ -422,10 +422,10 @@ def test_multi_lerp(opt):
 @pytest.fixture(scope="module")
 def packlib():
     from tests.hostsim.build import build_extract
-    a = C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights"]))
+    a = C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights_at", "ccdm_pack_weights"]))
     b = C.CDLL(build_extract("wgrad.cu", ["unpack_wgrad_kernel", "pack_weights_t_kernel"],
                              ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"]))
-    for h, names in ((a, ["ccdm_pack_weights"]), (b, ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"])):
+    for h, names in ((a, ["ccdm_pack_weights", "ccdm_pack_weights_at"]), (b, ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"])):
         for n in names:
             fn = getattr(h, n)
             fn.restype, fn.argtypes = L.SIGNATURES[n]
