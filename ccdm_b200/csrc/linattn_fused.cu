@@ -418,7 +418,6 @@ struct La2Aux {
 
 struct La2Params {
   int n, nkb, tps, tiles_total, tiles_per_cta, x_stages, wf_bufs, C, n_rows;
-  int sq_exchange;                              // the two column halves exchange partial row norms through shared memory
   const float* rowss;
   const float* bias;                            // to_out[0].bias [C]
   const float* gain;                            // to_out[1].g [C]
@@ -439,7 +438,6 @@ __global__ void __launch_bounds__(kLa2Threads, 1) linattn_qout_kernel(const __gr
   uint8_t* wfr = xring + static_cast<size_t>(p.x_stages) * p.nkb * kLaBlk;    // [buf][2][n_rows][128 B]
   uint8_t* qstg = wfr + static_cast<size_t>(p.wf_bufs) * wf_slot;  // [group][2][128 tok][128 B]; reused as output staging
   La2Aux* aux = reinterpret_cast<La2Aux*>(qstg + 4 * kLaBlk);
-  float* sqpart = reinterpret_cast<float*>(aux + 1);               // [group][column half][row] (only with sq_exchange)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 0 && lane == 0) {
@@ -674,11 +672,8 @@ __global__ void __launch_bounds__(kLa2Threads, 1) linattn_qout_kernel(const __gr
       mbar_wait(&aux->d2_full[g], k2 & 1u);
       tc_fence_after();
       const uint32_t d2 = trow + 256 + g * 128;
-      // The row norm needs all channels, a warp owns half of them: each warp reads only ITS chunks from TMEM (the TMEM read
-      // port, 64 B/clk/SM, is this kernel's scarcest resource) and the two partial sums meet in shared memory.
       float2 sq2 = make_float2(0.f, 0.f);
-      const bool xch = p.sq_exchange != 0;
-      for (int c = xch ? c2_lo : 0; c < (xch ? c2_hi : nch); ++c) {
+      for (int c = 0; c < nch; ++c) {                              // both warps of a quarter need the whole row's norm
         tmem_ld32(d2 + c * 32, r);
         tmem_ld_wait();
         const float2* b2 = reinterpret_cast<const float2*>(aux->bias + c * 32);
@@ -688,15 +683,7 @@ __global__ void __launch_bounds__(kLa2Threads, 1) linattn_qout_kernel(const __gr
           sq2 = __ffma2_rn(v, v, sq2);
         }
       }
-      const bool keep_r = xch && (c2_hi - c2_lo) == 1;             // one chunk: its accumulators are still in registers
-      float ssq = sq2.x + sq2.y;
-      if (xch) {
-        sqpart[(g * 2 + half) * kLaTok + m] = ssq;
-        group_bar(g);
-        // fixed summation order (column half 0 first): both warps of a row compute bit-identical norms
-        ssq = sqpart[(g * 2) * kLaTok + m] + sqpart[(g * 2 + 1) * kLaTok + m];
-      }
-      const float inv = 1.f / fmaxf(sqrtf(ssq), 1e-12f);
+      const float inv = 1.f / fmaxf(sqrtf(sq2.x + sq2.y), 1e-12f);
       const float2 inv2 = make_float2(inv, inv);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -709,10 +696,8 @@ __global__ void __launch_bounds__(kLa2Threads, 1) linattn_qout_kernel(const __gr
             if ((c >> 1) < p.nkb)                                  // channels beyond the loaded K blocks are padding
               xr[gg] = *reinterpret_cast<const uint4*>(xrow + (c >> 1) * kLaBlk + ((((c & 1) * 4 + gg) ^ (m & 7)) << 4));
           }
-          if (!keep_r) {
-            tmem_ld32(d2 + c * 32, r);
-            tmem_ld_wait();
-          }
+          tmem_ld32(d2 + c * 32, r);
+          tmem_ld_wait();
           const float2* b2 = reinterpret_cast<const float2*>(aux->bias + c * 32);
           const float2* g2 = reinterpret_cast<const float2*>(aux->gain + c * 32);
 #pragma unroll
@@ -882,16 +867,9 @@ extern "C" int ccdm_linattn_q_out(const void* x, int32_t B, int32_t n, int32_t C
   const size_t budget = 227 * 1024;
   p.x_stages = 4;
   p.wf_bufs = 2;
-  // Measured (B = 400, 64x64, C = 64): exchanging the partial row norms saves 2/3 of the epilogue's TMEM reads but the extra
-  // group barrier costs more -- 278 us vs 231 us with both warps reading the whole row.  Off; CCDM_LA2_SQX=1 re-enables it.
-  static const int sqx_env = [] { const char* e = getenv("CCDM_LA2_SQX"); return e ? atoi(e) : 0; }();
-  p.sq_exchange = sqx_env;
-  auto total = [&]() {
-    return fixed + (size_t)p.x_stages * p.nkb * kLaBlk + (size_t)p.wf_bufs * wf_slot + (p.sq_exchange ? 4 * kLaTok * sizeof(float) : 0);
-  };
+  auto total = [&]() { return fixed + (size_t)p.x_stages * p.nkb * kLaBlk + (size_t)p.wf_bufs * wf_slot; };
   if (total() > budget) p.x_stages = 3;
   if (total() > budget) p.wf_bufs = 1;
-  if (total() > budget) p.sq_exchange = 0;                         // 128-channel levels: every byte is spoken for
   CCDM_REQUIRE(total() <= budget, CCDM_ERR_UNSUPPORTED_SHAPE, "linattn_q_out: shared memory plan does not fit");
   CUtensorMap xmap, wmap, fmap, omap;
   int rc = la_xmap(&xmap, x, C, n, B);
