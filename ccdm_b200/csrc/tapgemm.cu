@@ -1164,8 +1164,9 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
     // 4x4-s2, every >= 128-channel 3x3) and lose on short, memory-bound layers (1x1, 64 -> 64 + residual), whose
     // per-tile time is dominated by load / store latency that the pair's cross-SM handshakes lengthen.
     static const int pair_env = [] { const char* e = getenv("CCDM_TAPGEMM_PAIR"); return e ? atoi(e) : 16; }();
+    static const int pair_min_tiles = [] { const char* e = getenv("CCDM_TAPGEMM_PAIR_MINTILES"); return e ? atoi(e) : 1; }();
     p.pair = (pair_env != 0 && nkb >= pair_env && a->w_batch_rows == 0 && nsub == 1 && p.n_inner == 1 && a->R <= 3 && a->n_tile <= 256 &&
-              (a->n_tile / 2) % 16 == 0 && gx >= 2 && tiles_per_cta >= 2 &&
+              (a->n_tile / 2) % 16 == 0 && gx >= 2 && tiles_per_cta >= pair_min_tiles &&
               !(a->flags & (CCDM_EPI_OUT_F32 | CCDM_EPI_HEAD))) ? 1 : 0;
     if (p.pair) {
       if (gx & 1) ++gx;                                            // whole pairs; a trailing CTA may get dummy tiles only

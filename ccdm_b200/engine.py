@@ -508,7 +508,7 @@ class UnetProgram(Program):
         if split:
             return self._conv_split(name, kind, plan, tile, srcs, views, conv_mod, out, flags, gain, ss_off, resid,
                                     out_rowss, gw, gh)
-        n_rows, n_tile = n_tiling(cout, full_row)
+        n_rows, n_tile = n_tiling(cout, full_row, plan.nkb >= 16)
         if views is None:
             views = []
             for s in srcs:
@@ -564,7 +564,7 @@ class UnetProgram(Program):
                     gw, gh):
         """conv + bias as a channel-split tap-GEMM into a bf16 scratch, then ccdm_rmsnorm_act for the tail."""
         cout = conv_mod.weight.shape[0]
-        n_rows, n_tile = n_tiling(cout, False)
+        n_rows, n_tile = n_tiling(cout, False, plan.nkb >= 16)
         pack = self.weights.add(f"{name}/R{plan.R}/split", conv_mod.weight, plan, n_rows)
         if views is None:
             views = []

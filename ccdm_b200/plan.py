@@ -15,6 +15,7 @@ Reference call sites: CCDM_unified/models/unet.py:74-81 (Upsample / Downsample),
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import List, Sequence, Tuple
 
@@ -246,11 +247,14 @@ def _plan_dgrad(fwd_kind, cins, cout, reuse_rows, emit, sched, psched):
     raise ValueError(fwd_kind)
 
 
-def n_tiling(cout: int, full_row: bool) -> Tuple[int, int]:
+def n_tiling(cout: int, full_row: bool, long_k: bool = False) -> Tuple[int, int]:
     """(n_rows, n_tile): packed row count and output channels per CTA.
 
     ``full_row`` (RMSNorm / sum-of-squares epilogues) keeps every channel of a pixel in one CTA (<= 512 TMEM
-    columns).  Otherwise wide outputs are split into 128-channel tiles so that several CTAs share an SM.
+    columns).  Otherwise wide outputs are split into 128-channel tiles so that several CTAs share an SM -- or, for layers
+    with a long K loop (``long_k``: >= 16 K blocks, which run as CTA pairs), into 256-channel tiles: a pair then reads each
+    A box for twice as many columns and the B operand fetch per MMA balances the tensor time (4x4-level 3x3 convs of the
+    RC-49 model: 52 -> 41 us, profiles/r2_notes.md).
     """
     pad32 = (cout + 31) // 32 * 32
     if full_row:
@@ -259,5 +263,5 @@ def n_tiling(cout: int, full_row: bool) -> Tuple[int, int]:
         return pad32, pad32
     if pad32 <= 256:
         return pad32, pad32
-    n_tile = 128
+    n_tile = 256 if long_k else 128
     return (cout + n_tile - 1) // n_tile * n_tile, n_tile
