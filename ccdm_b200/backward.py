@@ -201,6 +201,41 @@ def conv_dgrad(kind: str, dy: torch.Tensor, weight: torch.Tensor, cins: Sequence
     return outs
 
 
+class ZeroArena:
+    """Pre-zeroed fp32 scratch for the backward pass: the packed weight-gradient accumulators (one per convolution, red.add
+    targets) and the per-(sample, channel) sums of the block-tail backward each needed their own ``torch.zeros`` -- ~160 fill
+    launches per step.  ``begin_step`` zeroes ONE arena sized by the previous step's demand; ``zeros`` hands out slices.
+    Only for buffers that die inside the node that asked for them (nothing taken from here may be returned to autograd)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+        self.used = 0          # elements handed out since the last begin_step
+        self.clean = 0         # elements zeroed by the last begin_step (slices beyond it fall back to torch.zeros)
+        self.demand = 0        # elements asked for since the last begin_step (sizes the next one)
+
+    def begin_step(self, device):
+        need = self.demand
+        if need and (self.buf is None or self.buf.numel() < need or self.buf.device != device):
+            self.buf = torch.empty(need + need // 8, dtype=torch.float32, device=device)
+        self.clean = 0
+        if self.buf is not None and self.buf.device == device and need:
+            self.clean = min(need, self.buf.numel())
+            self.buf[:self.clean].zero_()
+        self.used, self.demand = 0, 0
+
+    def zeros(self, n: int, device) -> torch.Tensor:
+        n_al = (n + 63) // 64 * 64                        # 256-byte aligned slices (red.global.add.v4 targets)
+        self.demand += n_al
+        if self.buf is not None and self.buf.device == device and self.used + n_al <= self.clean:
+            out = self.buf[self.used:self.used + n]
+            self.used += n_al
+            return out
+        return torch.zeros(n, dtype=torch.float32, device=device)
+
+
+ARENA = ZeroArena()
+
+
 @functools.lru_cache(maxsize=None)
 def _plan_cached_stem(cout: int) -> ConvPlan:
     return plan_conv("stem7", (64,), cout)
@@ -210,7 +245,7 @@ def wgrad_packed(plan: ConvPlan, tile, views: List[L.View], dz: torch.Tensor, gw
                  cout: int, n_rows: int, ksplit: int = 0, timing: Optional[list] = None) -> torch.Tensor:
     """fp32 [nz*n_rows, nkb*64] weight gradient in the packed layout of the forward weights (ccdm_conv_wgrad)."""
     dev = dz.device
-    gpacked = torch.zeros(plan.nz * n_rows, plan.nkb * KB, dtype=torch.float32, device=dev)
+    gpacked = ARENA.zeros(plan.nz * n_rows * plan.nkb * KB, dev).view(plan.nz * n_rows, plan.nkb * KB)
     a = L.WgradArgs()
     a.n_src = len(views)
     for i, v in enumerate(views):
@@ -277,8 +312,11 @@ def block_backward(dy: torch.Tensor, z: torch.Tensor, gain: torch.Tensor, scale_
     dev = z.device
     flags = (L.EPI_SILU if silu else 0) | (L.EPI_SS if scale_shift is not None else 0)
     dz = torch.empty_like(z)
-    zbuf = torch.zeros(3 * b * c + 2 * c, dtype=torch.float32, device=dev)          # one fill: sums | dgain | dbias
-    sums, dgain, dbias = zbuf[:3 * b * c], zbuf[3 * b * c:3 * b * c + c], zbuf[3 * b * c + c:]
+    sums = ARENA.zeros(3 * b * c, dev)
+    dgain = dbias = None
+    if dgain_into is None or dbias_into is None:          # returned to autograd: never arena memory
+        zbuf = torch.zeros(2 * c, dtype=torch.float32, device=dev)
+        dgain, dbias = zbuf[:c], zbuf[c:]
     ld = scale_shift.shape[1] if scale_shift is not None else 0
     gm = math.sqrt(c)
     g = gain.reshape(-1)

@@ -303,10 +303,8 @@ def time_features(t: torch.Tensor, dim: int) -> torch.Tensor:
     return torch.cat((ang.sin(), ang.cos()), dim=-1)
 
 
-def _resblock(mod, srcs, tc):
-    """ResnetBlock.forward (unet.py:167-187)."""
-    lin = mod.tc_mlp[1]
-    ss = F.linear(tc, lin.weight, lin.bias)                        # [B, 2*Cout]: scale | shift
+def _resblock(mod, srcs, ss):
+    """ResnetBlock.forward (unet.py:167-187); ``ss`` = this block's tc_mlp output [B, 2*Cout] (scale | shift)."""
     b1, b2 = mod.block1, mod.block2
     h1 = ConvBlockFn.apply("3x3", True, b1.proj.weight, b1.proj.bias, b1.norm.g, ss, None, *srcs)
     if isinstance(mod.res_conv, nn.Conv2d):
@@ -351,28 +349,40 @@ def unet_train_forward(net, x: torch.Tensor, t: torch.Tensor, labels_emb: torch.
     te = time_features(t, net.dim)
     te = net.time_mlp[3](net.time_mlp[2](net.time_mlp[1](te)))
     tc = F.silu(torch.cat((te, c), dim=1))
+    # every ResnetBlock's tc_mlp Linear (unet.py:158-161,171-176) reads the same [SiLU(t) | SiLU(c)] rows: ONE library GEMM over
+    # the concatenated weights (and one dgrad + one wgrad GEMM in the backward) instead of 23-31 small ones
+    blocks = []
+    for lvl in net.downs:
+        blocks += [lvl[0], lvl[1]]
+    blocks += [net.mid_block1, net.mid_block2]
+    for lvl in net.ups:
+        blocks += [lvl[0], lvl[1]]
+    blocks.append(net.final_res_block)
+    ss_all = F.linear(tc, torch.cat([m.tc_mlp[1].weight for m in blocks]), torch.cat([m.tc_mlp[1].bias for m in blocks]))
+    ss_it = iter(torch.split(ss_all, [m.tc_mlp[1].weight.shape[0] for m in blocks], dim=1))
+    K.ARENA.begin_step(x.device)
 
     stem = StemFn.apply(x.float(), net.init_conv.weight, net.init_conv.bias)
     h = stem
     skips = []
     nlev = len(net.downs)
     for k, (b1, b2, attn, down) in enumerate(net.downs):
-        h = _resblock(b1, [h], tc)
+        h = _resblock(b1, [h], next(ss_it))
         skips.append(h)
-        h = _resblock(b2, [h], tc)
+        h = _resblock(b2, [h], next(ss_it))
         h = _linear_attention(attn, h)
         skips.append(h)
         h = ConvFn.apply("3x3" if k == nlev - 1 else "down4x4s2", down.weight, down.bias, None, h)
-    h = _resblock(net.mid_block1, [h], tc)
+    h = _resblock(net.mid_block1, [h], next(ss_it))
     h = _mid_attention(net.mid_attn, h)
-    h = _resblock(net.mid_block2, [h], tc)
+    h = _resblock(net.mid_block2, [h], next(ss_it))
     for k, (b1, b2, attn, up) in enumerate(net.ups):
-        h = _resblock(b1, [h, skips.pop()], tc)
-        h = _resblock(b2, [h, skips.pop()], tc)
+        h = _resblock(b1, [h, skips.pop()], next(ss_it))
+        h = _resblock(b2, [h, skips.pop()], next(ss_it))
         h = _linear_attention(attn, h)
         if k == nlev - 1:
             h = ConvFn.apply("3x3", up.weight, up.bias, None, h)
         else:
             h = ConvFn.apply("up2x3x3", up[1].weight, up[1].bias, None, h)
-    h = _resblock(net.final_res_block, [h, stem], tc)
+    h = _resblock(net.final_res_block, [h, stem], next(ss_it))
     return HeadFn.apply(h, net.final_conv.weight, net.final_conv.bias)

@@ -63,7 +63,7 @@ class _Plan:
     def __init__(self, a):
         self.nz, self.ngroups, self.R = a.nz, a.ngroups, a.R
         self.nkb = a.ngroups * a.R
-        n_res = a.n_res if a.flags & L.EPI_RESACC else 0
+        n_res = a.n_res if (getattr(a, "flags", 0) & L.EPI_RESACC) else 0
         n = (a.nz * a.ngroups + n_res) * 4
         s = torch.frombuffer((C.c_int32 * n).from_address(a.sched), dtype=torch.int32).reshape(-1, 4).tolist()
         self.sched = [tuple(r) for r in s[: a.nz * a.ngroups]]
