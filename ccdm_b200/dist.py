@@ -115,3 +115,33 @@ def all_reduce_gradients(params, bucket_bytes: int = 64 << 20):
         if size >= bucket_bytes:
             flush()
     flush()
+
+
+def early_gradient_params(model):
+    """Parameters of the UNet's decoder half (``ups``, ``final_res_block``, ``final_conv``; unet.py:330-348) except the
+    ``tc_mlp`` Linears, whose gradients come out of the batched conditioning GEMM at the very end of the backward.  Their
+    weight gradients are complete when the backward pass reaches the bottleneck -- ``FusedAdam(early_params=...)`` puts them
+    in one contiguous segment and ``wire_overlap`` starts that segment's all-reduce from a hook at that point."""
+    net = getattr(model, "unet", model)
+    net = getattr(net, "module", net)
+    out, skip = [], set()
+    for name in ("ups", "final_res_block", "final_conv"):
+        mod = getattr(net, name, None)
+        if mod is None:
+            return []
+        for n, p in mod.named_parameters():
+            if "tc_mlp" in n or id(p) in skip:
+                continue
+            skip.add(id(p))
+            out.append(p)
+    return out
+
+
+def wire_overlap(model, opt) -> bool:
+    """Lets the training forward (train.unet_train_forward) call ``opt.launch_early_bucket`` from a gradient hook on the
+    decoder's input.  Returns whether the overlap is active (fused optimizer with an early segment, world size > 1)."""
+    net = getattr(model, "unet", model)
+    net = getattr(net, "module", net)
+    ok = hasattr(opt, "launch_early_bucket") and getattr(opt, "early_start", 0) < opt.flat_grad.numel() and dist.is_initialized() and dist.get_world_size() > 1
+    net._early_grad_hook = opt.launch_early_bucket if ok else None
+    return ok

@@ -38,13 +38,21 @@ def _chunk_tables(tensors, offsets, device):
 
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, max_grad_norm: Optional[float] = None):
+                 weight_decay: float = 0.0, max_grad_norm: Optional[float] = None,
+                 early_params: Optional[Iterable[torch.nn.Parameter]] = None):
+        """``early_params``: parameters whose gradients are complete early in the backward pass (the UNet's decoder half,
+        ``dist.early_gradient_params``).  They are laid out at the END of the flat buffers, so that their all-reduce is one
+        contiguous NCCL call that ``launch_early_bucket`` starts on a side stream while the encoder's backward still runs
+        (overlap of the gradient exchange with the backward)."""
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
             raise ValueError("FusedAdam keeps one flat buffer: pass a single parameter group")
         self.max_grad_norm = max_grad_norm
-        ps = [p for p in self.param_groups[0]["params"] if p.requires_grad]
+        all_ps = list(self.param_groups[0]["params"])
+        # torch.optim.Adam numbers its state by position in the FULL parameter group (frozen parameters included)
+        self._index = [i for i, p in enumerate(all_ps) if p.requires_grad]
+        ps = [p for p in all_ps if p.requires_grad]
         if not ps:
             raise ValueError("FusedAdam: no trainable parameters")
         dev = ps[0].device
@@ -52,10 +60,17 @@ class FusedAdam(torch.optim.Optimizer):
             if not (p.is_cuda and p.dtype == torch.float32 and p.device == dev and p.is_contiguous()):
                 raise RuntimeError("FusedAdam needs contiguous CUDA fp32 parameters on one device (no CPU fallback)")
         self._ps = ps
-        self._offsets, total = [], 0
-        for p in ps:
-            self._offsets.append(total)
-            total += (p.numel() + 3) // 4 * 4                      # 16-byte aligned views
+        early = {id(p) for p in early_params} if early_params is not None else set()
+        self._offsets, total = [0] * len(ps), 0
+        for want_early in (False, True):                           # flat layout: [late ... | early ...]
+            if want_early:
+                self.early_start = total
+            for i, p in enumerate(ps):
+                if (id(p) in early) == want_early:
+                    self._offsets[i] = total
+                    total += (p.numel() + 3) // 4 * 4              # 16-byte aligned views
+        self._side = None
+        self._early_armed = self._early_launched = False
         with torch.inference_mode(False):
             self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
             self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -85,11 +100,35 @@ class FusedAdam(torch.optim.Optimizer):
         self.flat_grad.zero_()
         self._attach()
 
+    def arm_early_bucket(self, on: bool = True):
+        """Called by the step driver before the backward of the LAST micro-batch of an optimizer step."""
+        self._early_armed = bool(on) and self.early_start < self.flat_grad.numel()
+
+    def launch_early_bucket(self):
+        """Runs inside the backward pass (a tensor hook on the decoder's input, train.py) once every early parameter's
+        gradient is in the flat buffer: their all-reduce starts on a side stream and overlaps the rest of the backward."""
+        if not (self._early_armed and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.flat_grad[self.early_start:], op=dist.ReduceOp.SUM)
+        self._early_armed, self._early_launched = False, True
+
     def all_reduce_gradients(self):
-        """Data-parallel exchange: one NCCL all-reduce over the flat buffer, then the mean."""
+        """Data-parallel exchange: NCCL all-reduce over the flat buffer (one call, or the late segment
+        here + the early segment already in flight on the side stream), then the mean."""
         if dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            if self._early_launched:
+                dist.all_reduce(self.flat_grad[:self.early_start], op=dist.ReduceOp.SUM)
+                torch.cuda.current_stream().wait_stream(self._side)
+                self._early_launched = False
+            else:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
             self.flat_grad.div_(dist.get_world_size())
+        self._early_armed = False
 
     @property
     def grad_norm(self) -> torch.Tensor:
@@ -131,23 +170,26 @@ class FusedAdam(torch.optim.Optimizer):
     # ------------------------------------------------------------------ checkpoints in torch.optim.Adam's layout
     def state_dict(self):
         state = {}
-        for i, p in enumerate(self._ps):
-            off, n = self._offsets[i], p.numel()
+        for j, p in enumerate(self._ps):
+            i, off, n = self._index[j], self._offsets[j], p.numel()
             state[i] = {"step": self.step_count[0].clone(), "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
                         "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
         grp = {k: v for k, v in self.param_groups[0].items() if k != "params"}
-        grp["params"] = list(range(len(self._ps)))
+        grp["params"] = list(range(len(self.param_groups[0]["params"])))
         return {"state": state, "param_groups": [grp]}
 
     def load_state_dict(self, sd):
         for k in ("lr", "betas", "eps", "weight_decay"):
             if k in sd["param_groups"][0]:
                 self.param_groups[0][k] = sd["param_groups"][0][k]
-        for i, p in enumerate(self._ps):
+        for j, p in enumerate(self._ps):
+            i = self._index[j]
             st = sd["state"].get(i, sd["state"].get(str(i)))
             if st is None:
                 continue
-            off, n = self._offsets[i], p.numel()
+            off, n = self._offsets[j], p.numel()
+            if st["exp_avg"].numel() != n or st["exp_avg_sq"].numel() != n:
+                raise ValueError(f"FusedAdam.load_state_dict: state {i} has {st['exp_avg'].numel()} elements, the parameter {n}")
             self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
             self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
             self.step_count.fill_(float(st["step"]))

@@ -376,6 +376,11 @@ def unet_train_forward(net, x: torch.Tensor, t: torch.Tensor, labels_emb: torch.
     h = _resblock(net.mid_block1, [h], next(ss_it))
     h = _mid_attention(net.mid_attn, h)
     h = _resblock(net.mid_block2, [h], next(ss_it))
+    hook = getattr(net, "_early_grad_hook", None)
+    if hook is not None and h.requires_grad:
+        # the gradient of the decoder's input exists once every decoder node has run, i.e. once all decoder weight gradients
+        # are in the optimizer's flat buffer: start their all-reduce now, under the encoder's backward (dist.wire_overlap)
+        h.register_hook(lambda g, _hook=hook: (_hook(), None)[1])
     for k, (b1, b2, attn, up) in enumerate(net.ups):
         h = _resblock(b1, [h, skips.pop()], next(ss_it))
         h = _resblock(b2, [h, skips.pop()], next(ss_it))

@@ -45,6 +45,7 @@ class GraphedTrainStep:
         dev = self.params[0].device
         if self.fused:
             optimizer.max_grad_norm = max_grad_norm               # clipping is part of the fused step
+            ccdm_dist.wire_overlap(diffusion, optimizer)          # early-bucket all-reduce under the encoder's backward
         else:
             for grp in optimizer.param_groups:
                 grp["capturable"] = True
@@ -78,7 +79,9 @@ class GraphedTrainStep:
     def _step(self):
         self.opt.zero_grad(set_to_none=True)
         total = None
-        for _ in range(self.accumulate):
+        for mb in range(self.accumulate):
+            if self.fused:
+                self.opt.arm_early_bucket(mb == self.accumulate - 1)
             if self.batch_fn is not None:
                 images, labels, emb, weights, kw = self.batch_fn()
                 kw = dict(self.kw, **kw)

@@ -71,7 +71,9 @@ class Trainer(object):
         self.on_cuda = bool(params) and params[0].is_cuda
         if self.on_cuda:
             # clip_grad_norm_ + Adam fused over flat buffers (ccdm_b200/optim.py); same arithmetic as torch's Adam
-            self.opt = FusedAdam(params, lr=train_lr, betas=adam_betas, max_grad_norm=max_grad_norm)
+            self.opt = FusedAdam(params, lr=train_lr, betas=adam_betas, max_grad_norm=max_grad_norm,
+                                 early_params=ccdm_dist.early_gradient_params(diffusion_model))
+            ccdm_dist.wire_overlap(diffusion_model, self.opt)
         else:
             self.opt = Adam(params, lr=train_lr, betas=adam_betas)
         self.ema = EMA(diffusion_model, update_after_step=ema_update_after_step, beta=ema_decay,
@@ -391,7 +393,9 @@ class Trainer(object):
 
     def _eager_step(self, fn_y2h):
         total = torch.zeros((), device=self.device)
-        for _ in range(self.gradient_accumulate_every):
+        for mb in range(self.gradient_accumulate_every):
+            if isinstance(self.opt, FusedAdam):
+                self.opt.arm_early_bucket(mb == self.gradient_accumulate_every - 1)
             images, labels, emb, weights, kw = self.device_batch(fn_y2h)
             loss = self.model(images, labels_emb=emb, labels=labels, vicinal_weights=weights, **kw)
             loss = loss / self.gradient_accumulate_every

@@ -69,7 +69,10 @@ def main():
         opt = torch.optim.Adam([p for p in gd.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99))
     else:
         opt = ccdm_b200.optim.FusedAdam([p for p in gd.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99),
-                                        max_grad_norm=1.0)
+                                        max_grad_norm=1.0,
+                                        early_params=None if os.environ.get("CCDM_NO_OVERLAP") else D.early_gradient_params(gd))
+    if not a.torch_adam:
+        D.wire_overlap(gd, opt)                                        # decoder-segment all-reduce under the encoder's backward
     g = torch.Generator().manual_seed(rank)
     B = a.batch
     img = torch.rand(B, 3, m["size"], m["size"], generator=g).cuda()
@@ -89,6 +92,8 @@ def main():
         if ev:
             ev[1].record()
         opt.zero_grad(set_to_none=True)
+        if not a.torch_adam:
+            opt.arm_early_bucket(True)
         loss.backward()
         if ev:
             ev[2].record()
