@@ -134,31 +134,35 @@ SIGNATURES = {
     "ccdm_multi_lerp": (C.c_int, [vp, vp, vp, i32, vp, vp]),
 }
 
-_lib = None
+_libs = {}
+# Precision tiers = builds of the same sources (csrc/ptx.cuh): "bf16" stores activations / packed weights as bfloat16,
+# "fp16" as IEEE binary16 (TF32's 10-bit mantissa); both accumulate in fp32 on tcgen05.mma kind::f16.
+LIB_PATHS = {"bf16": LIB_PATH, "fp16": os.path.join(_HERE, "libccdm_b200_f16.so")}
 
 
-def lib():
-    """The loaded library; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def lib(precision: str = "bf16"):
+    """The loaded library of a precision tier; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    handle = _libs.get(precision)
+    if handle is None:
+        path = LIB_PATHS[precision]
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `make -C ccdm_b200/csrc` (there is no CPU or PyTorch fallback)")
-        handle = C.CDLL(LIB_PATH)
+                f"{path} is missing: build it with `make -C ccdm_b200/csrc` (there is no CPU or PyTorch fallback)")
+        handle = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the header and the library disagree
             fn.restype, fn.argtypes = res, args
         for which, struct in enumerate((TapGemmArgs, View, StepArgs, QSampleArgs, LossArgs, WgradArgs)):
             if handle.ccdm_struct_size(which) != C.sizeof(struct):
                 raise RuntimeError(f"ABI mismatch: {struct.__name__} is {C.sizeof(struct)} bytes here, "
-                                   f"{handle.ccdm_struct_size(which)} in {LIB_PATH}")
-        _lib = handle
-    return _lib
+                                   f"{handle.ccdm_struct_size(which)} in {path}")
+        _libs[precision] = handle
+    return handle
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "", precision: str = "bf16"):
     if rc != 0:
-        msg = lib().ccdm_last_error().decode(errors="replace")
+        msg = lib(precision).ccdm_last_error().decode(errors="replace")
         raise RuntimeError(f"ccdm_b200 {what} failed ({rc}): {msg}")
 
 

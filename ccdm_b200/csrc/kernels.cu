@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) rmsnorm_act_kernel(const uint4* __restric
           float2 t = __ffma2_rn(__fmul2_rn(v[k][j], inv2), a[k][j], sh[k][j]);
           if (flags & CCDM_EPI_SILU) {                             // t * sigmoid(t) = h + h * tanh(h), h = t / 2
             const float2 h = __fmul2_rn(t, make_float2(0.5f, 0.5f));
-            t = __ffma2_rn(h, make_float2(tanh_fast(h.x), tanh_fast(h.y)), h);
+            t = __ffma2_rn(h, make_float2(tanh_silu(h.x), tanh_silu(h.y)), h);
           }
           o[j] = t;
         }

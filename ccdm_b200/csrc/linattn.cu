@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kCtxThreads, 1) linattn_context_mma_kernel(con
     mbar_init(&aux->acc_empty, 4);
     fence_mbar_init();
   }
-  for (int i = tid; i < kCtxBlock / 4; i += kCtxThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+  for (int i = tid; i < kCtxBlock / 4; i += kCtxThreads) reinterpret_cast<uint32_t*>(ones)[i] = CCDM_ONE_PAIR;
   fence_proxy_async_smem();                                        // generic-proxy writes -> visible to the MMA
   tc_fence_before();
   __syncthreads();
@@ -243,7 +243,9 @@ __global__ void kexp_bound_kernel(const __nv_bfloat16* __restrict__ wp, int n_ro
       s = fmaf(w, w, s);
     }
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) bias[row] = (row >= lo && row < hi) ? -1.01f * sqrtf(s) - 1e-3f : 0.f;
+  // binary16 build: p = exp(k - bound) would underflow where bfloat16 (fp32's exponent range) does not; a constant shift of
+  // +10 (p <= e^10 = 22026 < 65504) moves the numerators into binary16's normal range and cancels in sum(p v) / sum(p)
+  if (lane == 0) bias[row] = (row >= lo && row < hi) ? -1.01f * sqrtf(s) - 1e-3f + CCDM_KEXP_SHIFT : 0.f;
 }
 
 }  // namespace ccdm

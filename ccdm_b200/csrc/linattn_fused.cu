@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kLaThreads, 1) linattn_kv_kernel(const __grid_
     mbar_init(&aux->d2_empty, kLaEpiWarps);
     fence_mbar_init();
   }
-  for (int i = tid; i < kLaBlk / 4; i += kLaThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;   // bf16 1.0
+  for (int i = tid; i < kLaBlk / 4; i += kLaThreads) reinterpret_cast<uint32_t*>(ones)[i] = CCDM_ONE_PAIR;   // bf16 1.0
   for (int i = tid; i < 128; i += kLaThreads) aux->kbias[i] = p.kbias[128 + i] * kLog2e;
   fence_proxy_async_smem();
   tc_fence_before();

@@ -6,6 +6,25 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+// Precision tiers.  The library is built twice from the same sources: libccdm_b200.so stores activations and packed weights
+// as bfloat16 (8-bit mantissa); libccdm_b200_f16.so (-DCCDM_ACT_F16) stores them as IEEE binary16 -- the 10-bit mantissa of
+// TF32 -- and feeds them to the same tcgen05.mma kind::f16 with fp32 accumulation.  Only the 2-byte element format changes:
+// layouts, TMA boxes, shared-memory plans and schedules are identical.  Everything below the macro layer is written against
+// the bf16 names.
+#ifdef CCDM_ACT_F16
+#include <cuda_fp16.h>
+#define __nv_bfloat16 __half
+#define __float2bfloat16 __float2half_rn
+#define __bfloat162float __half2float
+#define CCDM_ONE_PAIR 0x3C003C00u               // two binary16 1.0
+#define CCDM_MMA_AB_FORMAT 0u                   // tcgen05 instruction descriptor: A / B format F16
+#define CCDM_KEXP_SHIFT 10.0f                   // see kexp_bound_kernel (linattn.cu)
+#else
+#define CCDM_ONE_PAIR 0x3F803F80u               // two bfloat16 1.0
+#define CCDM_MMA_AB_FORMAT 1u                   // A / B format BF16
+#define CCDM_KEXP_SHIFT 0.0f
+#endif
+
 namespace ccdm {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -236,7 +255,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 
 // Instruction descriptor for kind::f16: A/B = bf16 (format 1), D = fp32 (format 1), both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+  return (1u << 4) | (CCDM_MMA_AB_FORMAT << 7) | (CCDM_MMA_AB_FORMAT << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // MN-major SWIZZLE_128B operand: LBO = stride between 64-element MN blocks, SBO = stride between 8-row K groups.
@@ -250,7 +269,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+  return (1u << 4) | (CCDM_MMA_AB_FORMAT << 7) | (CCDM_MMA_AB_FORMAT << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues on behalf of the CTA.
@@ -315,6 +335,16 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// tanh of the SiLU epilogues (x*sigmoid(x) = h + h*tanh(h), h = x/2).  bf16 build: tanh.approx (one MUFU, relative error
+// 2^-11 -- below bfloat16's rounding).  binary16 build: that error would be as large as the storage rounding itself, so
+// tanh(h) = 1 - 2/(1 + e^{2h}) from ex2.approx and a fast division (~1e-7).
+__device__ __forceinline__ float tanh_silu(float h) {
+#ifdef CCDM_ACT_F16
+  return 1.f - __fdividef(2.f, ex2_fast(h * 2.8853900817779268f) + 1.f);
+#else
+  return tanh_fast(h);
+#endif
+}
 // sigmoid(x) = 0.5 + 0.5 tanh(x/2): one MUFU, no division
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
@@ -332,11 +362,20 @@ __device__ __forceinline__ float seg_sum(float v, int gl, int G, int lane) {
   return __shfl_sync(0xffffffffu, v, lane - gl);
 }
 
+#ifdef CCDM_ACT_F16
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFFu))); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16))); }
+#else
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+#endif
 
 }  // namespace ccdm

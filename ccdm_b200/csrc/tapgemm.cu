@@ -64,6 +64,8 @@ struct TapGemmDev {
   int q_cols;
   int epi_alt;                            // the two epilogue warp groups take alternate tiles (n_tile <= 64)
   int pair;                               // CTA pairs: one tcgen05.mma.cta_group::2 (M = 256) covers a tile of each CTA
+  int srcC[CCDM_MAX_SRC];                 // channel extents of the sources: a 64-channel K block that sticks out of its source
+  int has_ks;                             //   (dim-72 models: 72 = 64 + 8) only issues the K = 16 steps that hold data
   int n_res;                              // CCDM_EPI_RESACC: 1x1 load groups after the main ones, accumulated in a SECOND
   uint32_t a_bytes_res;                   //   TMEM accumulator (res_conv / identity shortcut); their box bytes
   const float* res_bias;
@@ -102,11 +104,12 @@ __device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) {
 // kR vertically adjacent taps x 4 K-steps of one load group, fully unrolled (tap r: r*tw rows further down the box).
 template <int kR, bool kPair = false>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t tap16, uint32_t b16,
-                                           uint32_t idesc, bool first_group) {
+                                           uint32_t idesc, bool first_group, int ks = 4) {
 #pragma unroll
   for (int r = 0; r < kR; ++r) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+      if (k >= ks) continue;                               // K steps past the source's last channel multiply TMA zero fill
       if (kPair)
         umma_bf16_ss_2sm(d_tmem, umma_desc_lo(a_lo + r * tap16 + 2 * k), umma_desc_lo(b_lo + r * b16 + 2 * k), idesc,
                          (r | k) != 0 ? 1u : (first_group ? 0u : 1u));
@@ -129,7 +132,8 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
                                                   uint32_t stage16, uint32_t b_lo0, uint32_t tap16, uint32_t b16,
                                                   uint32_t idesc, uint32_t tmem_base, uint32_t n_tile, int acc_mask,
                                                   int acc_shift, uint32_t full_bar, uint32_t empty_bar,
-                                                  uint32_t tfull_bar, uint32_t tempty_bar, int n_res, uint32_t res_off) {
+                                                  uint32_t tfull_bar, uint32_t tempty_bar, int n_res, uint32_t res_off,
+                                                  const int* s_ks) {
   int s = 0;
   uint32_t ph = 0;
   uint32_t a_lo = a_lo0;
@@ -141,10 +145,11 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
     const uint32_t d_tmem = tmem_base + as * n_tile;
     uint32_t b_lo = b_lo0;
     for (int g = 0; g < n_groups; ++g) {
+      const int ks = s_ks ? s_ks[g] : 4;
       mbar_wait_a(full_bar + 8 * s, ph);
       tc_fence_after();
       if (elect_one()) {
-        issue_taps<kR, kPair>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
+        issue_taps<kR, kPair>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0, ks);
         commit_bar<kPair>(empty_bar + 8 * s);
       }
       __syncwarp();
@@ -153,10 +158,11 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
       if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
     }
     for (int g = 0; g < n_res; ++g) {                      // shortcut (1x1) groups -> the second accumulator
+      const int ks = s_ks ? s_ks[n_groups + g] : 4;
       mbar_wait_a(full_bar + 8 * s, ph);
       tc_fence_after();
       if (elect_one()) {
-        issue_taps<1, kPair>(d_tmem + res_off, a_lo, b_lo, tap16, b16, idesc, g == 0);
+        issue_taps<1, kPair>(d_tmem + res_off, a_lo, b_lo, tap16, b16, idesc, g == 0, ks);
         commit_bar<kPair>(empty_bar + 8 * s);
       }
       __syncwarp();
@@ -179,7 +185,7 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
                                               uint32_t nkb_b16, uint32_t tap16, uint32_t b16, uint32_t idesc,
                                               uint32_t tmem_base, uint32_t n_tile, int acc_mask, int acc_shift,
                                               uint32_t full_bar, uint32_t empty_bar, uint32_t tfull_bar,
-                                              uint32_t tempty_bar, int n_res, uint32_t res_off) {
+                                              uint32_t tempty_bar, int n_res, uint32_t res_off, const int* s_ks) {
   const int n_inner = kMultiN ? n_inner_rt : 1;             // compile-time 1 for the common case: no restore code
   int s = 0;
   uint32_t ph = 0;
@@ -206,8 +212,9 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
           mbar_wait_a(full_bar + 8 * s, ph);
           tc_fence_after();
         }
+        const int ks = s_ks ? s_ks[g] : 4;
         if (elect_one()) {
-          issue_taps<kR, kPair>(d_tmem, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0);
+          issue_taps<kR, kPair>(d_tmem, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0, ks);
           if (last_nt) commit_bar<kPair>(empty_bar + 8 * s);   // box reusable once the last MMAs have read it
         }
         __syncwarp();
@@ -219,8 +226,9 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
         for (int g = 0; g < n_res; ++g) {                  // shortcut (1x1) groups -> the second accumulator
           mbar_wait_a(full_bar + 8 * s, ph);
           tc_fence_after();
+          const int ks = s_ks ? s_ks[n_groups + g] : 4;
           if (elect_one()) {
-            issue_taps<1, kPair>(d_tmem + res_off, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0);
+            issue_taps<1, kPair>(d_tmem + res_off, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0, ks);
             commit_bar<kPair>(empty_bar + 8 * s);
           }
           __syncwarp();
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   uint8_t* stg = ring + static_cast<size_t>(p.stages) * p.stage_bytes;   // output staging (TMA-store epilogue)
   TapGemmAux* aux = reinterpret_cast<TapGemmAux*>(stg + static_cast<size_t>(p.out_bufs) * p.out_bytes);
   int4* s_sched = reinterpret_cast<int4*>(aux + 1);
+  int* s_ks_all = reinterpret_cast<int*>(s_sched + p.ngroups + p.n_res);   // K = 16 steps with data, per load group
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -303,7 +312,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       aux->bias2[i] = (p.res_bias && (n_base + i) < p.N) ? p.res_bias[n_base + i] : 0.f;
   }
   // (residual groups follow the nz * ngroups main entries; they exist only with nz == 1)
-  for (int i = tid; i < p.ngroups + p.n_res; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
+  for (int i = tid; i < p.ngroups + p.n_res; i += kThreads) {
+    const int4 e = p.sched[z * p.ngroups + i];
+    s_sched[i] = e;
+    const int left = p.srcC[e.x & (CCDM_MAX_SRC - 1)] - e.w;     // channels of this source from the block's first one on
+    s_ks_all[i] = left >= 64 ? 4 : (left <= 0 ? 1 : (left + 15) >> 4);
+  }
   tc_fence_before();
   __syncthreads();
   if constexpr (kPair) cluster_sync_all();                 // the peer's barriers are initialised before anyone signals them
@@ -428,21 +442,22 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages >> 1;
     const int n_res = p.n_res;
     const uint32_t res_off = static_cast<uint32_t>(p.acc_stages) * n_tile;   // second accumulators sit behind the main ones
+    const int* s_ks = p.has_ks ? s_ks_all : nullptr;
     if (one_sub && R <= 3 && (n_inner == 1 || (R == 1 && b_res))) {
       const uint32_t full_bar = smem_u32(&aux->a_full[0]), empty_bar = smem_u32(&aux->a_empty[0]);
       const uint32_t tfull_bar = smem_u32(&aux->tmem_full[0]), tempty_bar = smem_u32(&aux->tmem_empty[0]);
 #define CCDM_MMA_LOOP(KR, RES, MULTI)                                                                                  \
   mma_loop_fast<KR, RES, MULTI>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo, nkb_b16, \
                                 tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, \
-                                tempty_bar, n_res, res_off)
+                                tempty_bar, n_res, res_off, s_ks)
       if constexpr (kPair) {                               // host guarantees: one channel tile per CTA, R <= 3
 #define CCDM_PAIR_RES(KR)                                                                                                 \
   mma_loop_resident<KR, true>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base, \
-                              n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off)
+                              n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks)
 #define CCDM_PAIR_STR(KR)                                                                                                 \
   mma_loop_fast<KR, false, false, true>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo,  \
                                         nkb_b16, tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar,     \
-                                        empty_bar, tfull_bar, tempty_bar, n_res, res_off)
+                                        empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks)
         if (b_res) {
           if (R == 3) CCDM_PAIR_RES(3);
           else if (R == 2) CCDM_PAIR_RES(2);
@@ -459,13 +474,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       } else if (b_res) {
         if (R == 3)
           mma_loop_resident<3, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks);
         else if (R == 2)
           mma_loop_resident<2, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks);
         else
           mma_loop_resident<1, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks);
       } else {
         if (R == 3) CCDM_MMA_LOOP(3, false, false);
         else if (R == 2) CCDM_MMA_LOOP(2, false, false);
@@ -717,9 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 hx = __fmul2_rn(v[i], half2);
-            float2 t;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(hx.x));
-            asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(hx.y));
+            const float2 t = make_float2(tanh_silu(hx.x), tanh_silu(hx.y));
             v[i] = __ffma2_rn(hx, t, hx);
           }
         }
@@ -1125,6 +1138,11 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   p.tmem_cols = pow2_cols(a->n_tile * p.acc_stages * (n_res > 0 ? 2 : 1));
   p.n_res = n_res;
   p.res_bias = a->res_bias;
+  for (int i = 0; i < CCDM_MAX_SRC; ++i) {
+    p.srcC[i] = a->src[i < a->n_src ? i : 0].C;
+    const int tail = p.srcC[i] % 64;
+    if (i < a->n_src && tail != 0 && tail <= 48) p.has_ks = 1;
+  }
   p.a_bytes_res = (uint32_t)(a->th * a->tw * a->tb) * 128u;
   p.bias = a->bias; p.rowss = a->rowss; p.gain = a->gain; p.ss = a->scale_shift;
   p.ss_ld = a->ss_ld; p.ss_off = a->ss_off;
@@ -1193,7 +1211,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   // ---- shared-memory plan
   const uint32_t b_bytes = (uint32_t)(p.pair ? a->n_tile / 2 : a->n_tile) * 128u;
   p.a_bytes = (uint32_t)(box_h * a->tw * a->tb) * 128u;
-  const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)(a->ngroups + n_res) * sizeof(int4);
+  const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)(a->ngroups + n_res) * (sizeof(int4) + sizeof(int));
   size_t budget = 226 * 1024 - aux_bytes - 1024;
   // bf16 outputs up to 256 channels per CTA leave through shared memory and TMA bulk stores (coalesced, clipped at the
   // tensor edges); wider tiles (4x4 bottleneck layers) and fp32 outputs keep per-thread stores

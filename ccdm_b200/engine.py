@@ -136,8 +136,9 @@ def fused_linattn_ok(training: bool, heads: int, C: int, n: int) -> bool:
 class Program:
     """A flat list of records plus their pre-filled ctypes argument structs."""
 
-    def __init__(self, device):
+    def __init__(self, device, precision: str = "bf16"):
         self.device = device
+        self.precision = precision          # which build of the library runs this program (ccdm_b200._lib.LIB_PATHS)
         self.recs: List[object] = []
         self.calls: List[tuple] = []        # (fn, args tuple without the stream)
         self.bufs: Dict[str, torch.Tensor] = {}
@@ -150,7 +151,7 @@ class Program:
         return t
 
     def finalize(self):
-        lib = L.lib()
+        lib = L.lib(self.precision)
         self.calls = [_make_call(lib, r, self._keep) for r in self.recs]
 
     def run(self, stream: int):
@@ -158,7 +159,7 @@ class Program:
             for fn, args, name in self.calls:
                 rc = fn(*args, stream)
                 if rc != 0:
-                    L.check(rc, name)
+                    L.check(rc, name, self.precision)
                 try:
                     torch.cuda.synchronize()
                 except Exception as e:
@@ -167,7 +168,7 @@ class Program:
         for fn, args, name in self.calls:
             rc = fn(*args, stream)
             if rc != 0:
-                L.check(rc, name)
+                L.check(rc, name, self.precision)
 
     def run_timed(self):
         """Eager run on torch's current stream with a CUDA event between launches.
@@ -178,7 +179,7 @@ class Program:
         for i, (fn, args, name) in enumerate(self.calls):
             rc = fn(*args, stream)
             if rc != 0:
-                L.check(rc, name)
+                L.check(rc, name, self.precision)
             evs[i + 1].record()
         torch.cuda.synchronize()
         return [(self.recs[i], evs[i].elapsed_time(evs[i + 1])) for i in range(len(self.calls))]
@@ -315,10 +316,10 @@ class WeightStore:
     The fp32 ``nn.Parameter`` tensors stay the source of truth (optimizer, EMA ``lerp_``, ``load_state_dict`` all
     write them in place and bump ``_version``), so the packed copies are a cache keyed on those versions."""
 
-    def __init__(self, device):
+    def __init__(self, device, precision: str = "bf16"):
         self.device = device
         self.packs: Dict[str, PackRec] = {}
-        self.program = Program(device)
+        self.program = Program(device, precision)
         self._stamp = None
         self._params: List[torch.Tensor] = []
 
@@ -393,7 +394,8 @@ class UnetEngine:
     def __init__(self, net):
         self.net = net
         self.device = net.init_conv.weight.device
-        self.weights = WeightStore(self.device)
+        self.precision = getattr(net, "precision", "bf16")
+        self.weights = WeightStore(self.device, self.precision)
         self.programs: Dict[tuple, "UnetProgram"] = {}
         self._ptr_stamp = None
 
@@ -404,7 +406,7 @@ class UnetEngine:
         ptrs = self._param_ptrs()
         if ptrs != self._ptr_stamp:        # parameters were re-allocated (.to(), load with assign): rebuild all
             self.programs.clear()
-            self.weights = WeightStore(self.device)
+            self.weights = WeightStore(self.device, self.precision)
             self._ptr_stamp = ptrs
         key = (B, x_batch, H, W, bool(training))
         prog = self.programs.get(key)
@@ -466,7 +468,7 @@ class UnetEngine:
 
 class UnetProgram(Program):
     def __init__(self, net, weights: WeightStore, B, x_batch, H, W, training):
-        super().__init__(net.init_conv.weight.device)
+        super().__init__(net.init_conv.weight.device, getattr(weights.program, "precision", "bf16"))
         self.net, self.weights = net, weights
         self.B, self.x_batch, self.H, self.W, self.training = B, x_batch, H, W, training
         self.pair_keep = None

@@ -89,8 +89,15 @@ class SinusoidalPosEmb(nn.Module):              # unet.py:102-115 (parameter-fre
 class Unet(nn.Module):
     def __init__(self, dim, embed_input_dim=128, cond_drop_prob=0.5, init_dim=None, out_dim=None,
                  dim_mults=(1, 2, 4, 8), in_channels=3, learned_variance=False, learned_sinusoidal_cond=False,
-                 random_fourier_features=False, learned_sinusoidal_dim=16, attn_dim_head=32, attn_heads=4):
+                 random_fourier_features=False, learned_sinusoidal_dim=16, attn_dim_head=32, attn_heads=4,
+                 precision="bf16"):
+        """``precision`` (beyond the reference's signature) selects the inference tier: "bf16" (default) or "fp16" -- IEEE
+        binary16 storage of activations and kernel weights, i.e. TF32's 10-bit mantissa on the same tcgen05 kernels with fp32
+        accumulation (BASELINE.json north_star: the fp32/TF32 tolerance tier).  Training always uses the bf16 kernels."""
         super().__init__()
+        if precision not in ("bf16", "fp16"):
+            raise ValueError(f"precision must be 'bf16' or 'fp16' (got {precision!r})")
+        self.precision = precision
         if learned_sinusoidal_cond or random_fourier_features:
             # GaussianDiffusion refuses such a model anyway (diffusion.py:135)
             raise NotImplementedError("random / learned sinusoidal time embeddings are outside the hot path")

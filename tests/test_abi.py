@@ -14,9 +14,11 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(ccdm_[a-z0-9_]+)\s*\(", text)))
 
 
-def test_header_symbols_exported_and_bound():
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_header_symbols_exported_and_bound(precision):
+    """Both builds of the library (csrc/ptx.cuh: bf16 storage and the binary16 / TF32-class tier) export the whole header."""
     from ccdm_b200 import _lib
-    handle = _lib.lib()
+    handle = _lib.lib(precision)
     names = declared_symbols()
     assert len(names) >= 20
     for n in names:
@@ -26,9 +28,10 @@ def test_header_symbols_exported_and_bound():
     assert handle.ccdm_version() >= 100
 
 
-def test_struct_mirrors_match_library():
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_struct_mirrors_match_library(precision):
     from ccdm_b200 import _lib
-    handle = _lib.lib()
+    handle = _lib.lib(precision)
     for which, struct in enumerate((_lib.TapGemmArgs, _lib.View, _lib.StepArgs, _lib.QSampleArgs, _lib.LossArgs)):
         assert handle.ccdm_struct_size(which) == ctypes.sizeof(struct)
 
