@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--sampling-steps", type=int, default=0, help="override the number of denoising steps")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: fixed total batch, split over the ranks")
     a = ap.parse_args()
     rank, local, world = D.env_world()
     torch.cuda.set_device(local)
@@ -62,7 +63,7 @@ def main():
         gd = ccdm_b200.GaussianDiffusion(net, image_size=m["size"], objective=m["objective"], use_Hy=m["use_Hy"],
                                          fn_y2cov=(lambda y: (sinusoid(y, n_el) + 1) / 2) if m["use_Hy"] else None,
                                          cond_drop_prob=0.1, timesteps=1000, sampling_timesteps=S).to(dev).eval()
-    B = a.batch
+    B = a.batch if not a.global_batch else a.global_batch // world
     labels = torch.linspace(0, 1, B * world, device=dev)[rank * B:(rank + 1) * B]
     emb = sinusoid(labels, 128)
     shape = (B, 3, m["size"], m["size"])
@@ -90,7 +91,7 @@ def main():
         peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
         tf = 2 * S * m["gflop"] * B * world / ms                       # two UNet forwards per denoising step
         rec = dict(metric=f"{m['sampler']} images/s", model=a.model, image_size=m["size"], sampling_steps=S,
-                   per_gpu_batch=B, n_gpus=world, ms_per_sampling=round(ms, 1), images_per_s=round(B * world / ms * 1e3, 2),
+                   per_gpu_batch=B, scaling="strong" if a.global_batch else "weak", n_gpus=world, ms_per_sampling=round(ms, 1), images_per_s=round(B * world / ms * 1e3, 2),
                    algorithmic_tflops=round(tf, 1), frac_of_sustained_bf16_peak=round(tf / world / peaks["bf16_tflops_sustained"], 3),
                    finite=bool(torch.isfinite(img).all()), in_unit_range=bool(img.min() >= 0 and img.max() <= 1))
         print(json.dumps(rec), flush=True)

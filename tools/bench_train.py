@@ -24,6 +24,8 @@ MODELS = {
     # forward GFLOP per image from SURVEY.md section 8d (conv + linear + bmm, 2*MAC)
     "uk64": dict(dim=72, dim_mults=(1, 2, 4, 4, 8), size=64, gflop=16.25),
     "rc64": dict(dim=64, dim_mults=(1, 2, 2, 4, 8), size=64, gflop=11.00),
+    # BASELINE configs[4]: UTKFace 192x192 (UK192/run_ccdm.sh:18-33: dim 64, mults 1-2-2-4-4-8-8, 16 per GPU x accum 4)
+    "uk192": dict(dim=64, dim_mults=(1, 2, 2, 4, 4, 8, 8), size=192, gflop=94.99),
     # vanilla (GroupNorm) tree, RC-49 64x64 script configuration (V/scripts/run_train_ccdm.sh: batch 128, pred_x0); eager only
     "vrc64": dict(vanilla=True, size=64, gflop=21.8),
 }
@@ -45,6 +47,7 @@ def main():
     ap.add_argument("--breakdown", action="store_true")
     ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam + clip_grad_norm_ instead of FusedAdam")
     ap.add_argument("--graph", action="store_true", help="capture the whole step into a CUDA graph (train_graph.py)")
+    ap.add_argument("--accum", type=int, default=1, help="micro-batches per optimizer step (gradient_accumulate_every); --graph only")
     a = ap.parse_args()
     rank, local, world = D.env_world()
     torch.cuda.set_device(local)
@@ -109,8 +112,13 @@ def main():
 
     if a.graph:
         from ccdm_b200.train_graph import GraphedTrainStep
-        gstep = GraphedTrainStep(gd, opt, img, labels, emb, loss_kwargs=dict(vicinity_type="hv", kappa=0.05))
-        step = lambda ev=None: gstep(img, labels, emb)
+        if a.accum > 1:                                                # micro-batches built inside the graph (same tensors: a throughput run)
+            batch_fn = lambda: (img, labels, emb, ones, dict(vicinity_type="hv", kappa=0.05))
+            gstep = GraphedTrainStep(gd, opt, batch_fn=batch_fn, accumulate=a.accum)
+            step = lambda ev=None: gstep.replay()
+        else:
+            gstep = GraphedTrainStep(gd, opt, img, labels, emb, loss_kwargs=dict(vicinity_type="hv", kappa=0.05))
+            step = lambda ev=None: gstep(img, labels, emb)
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
@@ -128,9 +136,9 @@ def main():
     launches = (lib.ccdm_launch_count() - l0) // a.steps
     if rank == 0:
         peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
-        tflops = 3 * m["gflop"] * B * world / ms                         # GFLOP / ms = TFLOP/s
-        rec = dict(metric="train step", mode="cuda-graph" if a.graph else "eager", optimizer="torch" if a.torch_adam else "fused", model=a.model, per_gpu_batch=B, n_gpus=world, ms_per_step=round(ms, 2),
-                   images_per_s=round(B * world / ms * 1e3, 1), algorithmic_tflops=round(tflops, 1),
+        tflops = 3 * m["gflop"] * B * a.accum * world / ms               # GFLOP / ms = TFLOP/s
+        rec = dict(metric="train step", mode="cuda-graph" if a.graph else "eager", optimizer="torch" if a.torch_adam else "fused", model=a.model, per_gpu_batch=B, accumulate=a.accum, n_gpus=world, ms_per_step=round(ms, 2),
+                   images_per_s=round(B * a.accum * world / ms * 1e3, 1), algorithmic_tflops=round(tflops, 1),
                    frac_of_sustained_bf16_peak=round(tflops / world / peaks["bf16_tflops_sustained"], 3),
                    kernel_launches_per_step=int(launches), loss=round(loss.item(), 5),
                    peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
