@@ -461,9 +461,12 @@ class GaussianDiffusion(nn.Module):
         scale_all = None
         if vicinal_weights is not None:
             row_w = self._batch_weights(labels, keep_u8, kwargs)
-            if labels.dim() == 2 and labels.shape[1] == 1:
+            sliced_vt = kwargs.get("vicinity_type", self.vicinity_type) in ("shv", "ssv")
+            if labels.dim() == 2 and labels.shape[1] == 1 and (sliced_vt or kwargs.get("distance", "l2") != "l1"):
                 # [B,1] labels: the reference's weights come out [B,1] and broadcast against the [B] losses to a
-                # [B,B] product (diffusion.py:713-730), i.e. loss = (sum_i w_i)(sum_j l_j)/(bchw).  Kept.
+                # [B,B] product (diffusion.py:713-730), i.e. loss = (sum_i w_i)(sum_j l_j)/(bchw).  Kept.  Not for
+                # distance == "l1": there abs(diff).sum(dim=2) collapses the trailing axis (diffusion.py:684-692) and the
+                # weights are an ordinary [B] vector.
                 scale_all = row_w.sum()
                 row_w = None
         per = torch.empty(b, dtype=torch.float32, device=dev)

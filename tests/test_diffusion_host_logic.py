@@ -64,6 +64,9 @@ CASES = {
     "hv_multi": dict(objective="pred_x0", vic="hv", use_Hy=False, label_dim=3, kappa=0.35),
     "hv_col_labels": dict(objective="pred_x0", vic="hv", use_Hy=False, label_dim=-1, kappa=0.12),      # labels shaped [B,1]
     "novic_eps": dict(objective="pred_noise", vic=None, use_Hy=False, label_dim=1, kappa=0.1),
+    # distance l1 with [B,1] labels: abs(diff).sum(dim=2) gives ordinary [B] weights -- no broadcast quirk (diffusion.py:684-692)
+    "hv_col_labels_l1": dict(objective="pred_x0", vic="hv", use_Hy=False, label_dim=-1, kappa=0.12, distance="l1"),
+    "sv_multi_l1": dict(objective="pred_x0", vic="sv", use_Hy=False, label_dim=3, kappa=0.5, distance="l1"),
 }
 
 
@@ -88,6 +91,8 @@ def test_p_losses_host_logic_matches_oracle(host_sampler, name):
         vec = torch.randn(c.get("nproj", 1), max(d, 1), generator=g)
         extra = dict(vicinity_type=c["vic"], kappa=c["kappa"], vector_type="gaussian", num_projections=c.get("nproj", 1),
                      cached_vectors=vec)
+        if "distance" in c:
+            extra["distance"] = c["distance"]
         kw.update(extra)
         okw.update(extra)
     # ---- product code (forward draws t, then p_losses draws the mask and the noise)
