@@ -265,7 +265,7 @@ def run_b200(args):
             assert tapgemm_flops(r) / ms_ / 1e9 <= burst, (r.name, tapgemm_flops(r) / ms_ / 1e9, "TFLOP/s > burst peak")
     traffic = None                      # dram read+write bytes per launch (avg) from the committed ncu capture
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_tapgemm_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_tapgemm_traffic.json")))
         if B == 200 and size == 64:
             traffic = tr["traffic_bytes_per_launch_avg"]
     except Exception:

@@ -35,7 +35,7 @@ class TapGemmArgs(C.Structure):
         ("resid", vp), ("rsW", i64), ("rsH", i64), ("rsB", i64),
         ("out", vp), ("osW", i64), ("osH", i64), ("osB", i64), ("ooff", i64 * MAX_Z),
         ("out_rowss", vp), ("q_scale", f32), ("q_cols", i32),
-        ("n_res", i32), ("res_bias", vp),
+        ("halo", i32), ("n_res", i32), ("res_bias", vp),
         ("head_n", i32), ("head_w", vp), ("head_b", vp), ("head_out", vp), ("hsC", i64), ("hsB", i64),
     ]
 

@@ -64,8 +64,8 @@ struct TapGemmDev {
   int q_cols;
   int epi_alt;                            // the two epilogue warp groups take alternate tiles (n_tile <= 64)
   int pair;                               // CTA pairs: one tcgen05.mma.cta_group::2 (M = 256) covers a tile of each CTA
-  int srcC[CCDM_MAX_SRC];                 // channel extents of the sources: a 64-channel K block that sticks out of its source
-  int has_ks;                             //   (dim-72 models: 72 = 64 + 8) only issues the K = 16 steps that hold data
+  int halo;                               // 3x3 taps out of one halo box per 64-channel block (R == 9)
+  uint32_t stage_tx;                      // bytes TMA delivers into one main stage (the stage stride is rounded to 1 KiB)
   int n_res;                              // CCDM_EPI_RESACC: 1x1 load groups after the main ones, accumulated in a SECOND
   uint32_t a_bytes_res;                   //   TMEM accumulator (res_conv / identity shortcut); their box bytes
   const float* res_bias;
@@ -101,15 +101,40 @@ __device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) {
   return (kUmmaDescSw128 & 0xFFFFFFFF00000000ull) | lo;
 }
 
+// Halo boxes (3x3, one box {64 ch, tw + 2, th + 2} per 64-channel block, tw == 8): tap (r, q) starts (r * (tw + 2) + q) rows
+// = 128-byte units into the box -- NOT a multiple of the 8-row swizzle atom -- and the 8-row groups of the operand (one image
+// row each) are (tw + 2) rows = 1280 bytes apart.  SWIZZLE_128B is a pure function of the shared-memory address for TMA and
+// tcgen05.mma alike, so plain descriptors with that start address and SBO read the shifted windows correctly (base offset
+// field 0; tools/ubench/shift_desc.cu is the experiment, profiles/r2_ubench_shift_desc.txt its output).
+__device__ __forceinline__ uint64_t umma_desc_lo_halo(uint32_t lo) {
+  constexpr uint64_t hi = (static_cast<uint64_t>(1280 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61);
+  return hi | lo;
+}
+
 // kR vertically adjacent taps x 4 K-steps of one load group, fully unrolled (tap r: r*tw rows further down the box).
 template <int kR, bool kPair = false>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t tap16, uint32_t b16,
-                                           uint32_t idesc, bool first_group, int ks = 4) {
+                                           uint32_t idesc, bool first_group) {
+  if constexpr (kR == 9) {                                 // halo box: 3 x 3 taps, 10-row image pitch (tw == 8)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const uint32_t a_t = a_lo + static_cast<uint32_t>((t / 3) * 10 + (t % 3)) * 8u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (kPair)
+          umma_bf16_ss_2sm(d_tmem, umma_desc_lo_halo(a_t + 2 * k), umma_desc_lo(b_lo + t * b16 + 2 * k), idesc,
+                           (t | k) != 0 ? 1u : (first_group ? 0u : 1u));
+        else
+          umma_bf16_ss(d_tmem, umma_desc_lo_halo(a_t + 2 * k), umma_desc_lo(b_lo + t * b16 + 2 * k), idesc,
+                       (t | k) != 0 ? 1u : (first_group ? 0u : 1u));
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < kR; ++r) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (k >= ks) continue;                               // K steps past the source's last channel multiply TMA zero fill
       if (kPair)
         umma_bf16_ss_2sm(d_tmem, umma_desc_lo(a_lo + r * tap16 + 2 * k), umma_desc_lo(b_lo + r * b16 + 2 * k), idesc,
                          (r | k) != 0 ? 1u : (first_group ? 0u : 1u));
@@ -132,8 +157,7 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
                                                   uint32_t stage16, uint32_t b_lo0, uint32_t tap16, uint32_t b16,
                                                   uint32_t idesc, uint32_t tmem_base, uint32_t n_tile, int acc_mask,
                                                   int acc_shift, uint32_t full_bar, uint32_t empty_bar,
-                                                  uint32_t tfull_bar, uint32_t tempty_bar, int n_res, uint32_t res_off,
-                                                  const int* s_ks) {
+                                                  uint32_t tfull_bar, uint32_t tempty_bar, int n_res, uint32_t res_off) {
   int s = 0;
   uint32_t ph = 0;
   uint32_t a_lo = a_lo0;
@@ -145,11 +169,10 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
     const uint32_t d_tmem = tmem_base + as * n_tile;
     uint32_t b_lo = b_lo0;
     for (int g = 0; g < n_groups; ++g) {
-      const int ks = s_ks ? s_ks[g] : 4;
       mbar_wait_a(full_bar + 8 * s, ph);
       tc_fence_after();
       if (elect_one()) {
-        issue_taps<kR, kPair>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0, ks);
+        issue_taps<kR, kPair>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
         commit_bar<kPair>(empty_bar + 8 * s);
       }
       __syncwarp();
@@ -158,11 +181,10 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
       if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
     }
     for (int g = 0; g < n_res; ++g) {                      // shortcut (1x1) groups -> the second accumulator
-      const int ks = s_ks ? s_ks[n_groups + g] : 4;
       mbar_wait_a(full_bar + 8 * s, ph);
       tc_fence_after();
       if (elect_one()) {
-        issue_taps<1, kPair>(d_tmem + res_off, a_lo, b_lo, tap16, b16, idesc, g == 0, ks);
+        issue_taps<1, kPair>(d_tmem + res_off, a_lo, b_lo, tap16, b16, idesc, g == 0);
         commit_bar<kPair>(empty_bar + 8 * s);
       }
       __syncwarp();
@@ -185,7 +207,7 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
                                               uint32_t nkb_b16, uint32_t tap16, uint32_t b16, uint32_t idesc,
                                               uint32_t tmem_base, uint32_t n_tile, int acc_mask, int acc_shift,
                                               uint32_t full_bar, uint32_t empty_bar, uint32_t tfull_bar,
-                                              uint32_t tempty_bar, int n_res, uint32_t res_off, const int* s_ks) {
+                                              uint32_t tempty_bar, int n_res, uint32_t res_off) {
   const int n_inner = kMultiN ? n_inner_rt : 1;             // compile-time 1 for the common case: no restore code
   int s = 0;
   uint32_t ph = 0;
@@ -212,9 +234,8 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
           mbar_wait_a(full_bar + 8 * s, ph);
           tc_fence_after();
         }
-        const int ks = s_ks ? s_ks[g] : 4;
         if (elect_one()) {
-          issue_taps<kR, kPair>(d_tmem, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0, ks);
+          issue_taps<kR, kPair>(d_tmem, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0);
           if (last_nt) commit_bar<kPair>(empty_bar + 8 * s);   // box reusable once the last MMAs have read it
         }
         __syncwarp();
@@ -226,9 +247,8 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
         for (int g = 0; g < n_res; ++g) {                  // shortcut (1x1) groups -> the second accumulator
           mbar_wait_a(full_bar + 8 * s, ph);
           tc_fence_after();
-          const int ks = s_ks ? s_ks[n_groups + g] : 4;
           if (elect_one()) {
-            issue_taps<1, kPair>(d_tmem + res_off, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0, ks);
+            issue_taps<1, kPair>(d_tmem + res_off, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0);
             commit_bar<kPair>(empty_bar + 8 * s);
           }
           __syncwarp();
@@ -259,7 +279,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   uint8_t* stg = ring + static_cast<size_t>(p.stages) * p.stage_bytes;   // output staging (TMA-store epilogue)
   TapGemmAux* aux = reinterpret_cast<TapGemmAux*>(stg + static_cast<size_t>(p.out_bufs) * p.out_bytes);
   int4* s_sched = reinterpret_cast<int4*>(aux + 1);
-  int* s_ks_all = reinterpret_cast<int*>(s_sched + p.ngroups + p.n_res);   // K = 16 steps with data, per load group
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -312,12 +331,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       aux->bias2[i] = (p.res_bias && (n_base + i) < p.N) ? p.res_bias[n_base + i] : 0.f;
   }
   // (residual groups follow the nz * ngroups main entries; they exist only with nz == 1)
-  for (int i = tid; i < p.ngroups + p.n_res; i += kThreads) {
-    const int4 e = p.sched[z * p.ngroups + i];
-    s_sched[i] = e;
-    const int left = p.srcC[e.x & (CCDM_MAX_SRC - 1)] - e.w;     // channels of this source from the block's first one on
-    s_ks_all[i] = left >= 64 ? 4 : (left <= 0 ? 1 : (left + 15) >> 4);
-  }
+  for (int i = tid; i < p.ngroups + p.n_res; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
   tc_fence_before();
   __syncthreads();
   if constexpr (kPair) cluster_sync_all();                 // the peer's barriers are initialised before anyone signals them
@@ -370,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         if constexpr (kPair) {
           // Both CTAs fill their own slot s; every byte is accounted on the LEADER's barrier, which its MMA lane waits on.
           if (elect_one()) {
-            if (crank == 0) mbar_arrive_expect_tx(&aux->a_full[s], 2u * stage_bytes);
+            if (crank == 0) mbar_arrive_expect_tx(&aux->a_full[s], 2u * p.stage_tx);
             const int4 e = s_sched[g];
             const uint32_t st = smem_u32(ring + static_cast<size_t>(s) * stage_bytes);
             const uint32_t fb = smem_u32(&aux->a_full[s]);
@@ -381,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             }
           }
         } else if (elect_one()) {
-          mbar_arrive_expect_tx(&aux->a_full[s], stage_bytes);
+          mbar_arrive_expect_tx(&aux->a_full[s], p.stage_tx);
           const int4 e = s_sched[g];
           uint8_t* st = ring + static_cast<size_t>(s) * stage_bytes;
           tma_load_4d(&maps.a[e.x], &aux->a_full[s], st, e.w, w0 + e.y, h0 + e.z, b0);
@@ -442,28 +456,29 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const int acc_mask = p.acc_stages - 1, acc_shift = p.acc_stages >> 1;
     const int n_res = p.n_res;
     const uint32_t res_off = static_cast<uint32_t>(p.acc_stages) * n_tile;   // second accumulators sit behind the main ones
-    const int* s_ks = p.has_ks ? s_ks_all : nullptr;
-    if (one_sub && R <= 3 && (n_inner == 1 || (R == 1 && b_res))) {
+    if (one_sub && (R <= 3 || p.halo) && (n_inner == 1 || (R == 1 && b_res))) {
       const uint32_t full_bar = smem_u32(&aux->a_full[0]), empty_bar = smem_u32(&aux->a_empty[0]);
       const uint32_t tfull_bar = smem_u32(&aux->tmem_full[0]), tempty_bar = smem_u32(&aux->tmem_empty[0]);
 #define CCDM_MMA_LOOP(KR, RES, MULTI)                                                                                  \
   mma_loop_fast<KR, RES, MULTI>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo, nkb_b16, \
                                 tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, \
-                                tempty_bar, n_res, res_off, s_ks)
+                                tempty_bar, n_res, res_off)
       if constexpr (kPair) {                               // host guarantees: one channel tile per CTA, R <= 3
 #define CCDM_PAIR_RES(KR)                                                                                                 \
   mma_loop_resident<KR, true>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base, \
-                              n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks)
+                              n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off)
 #define CCDM_PAIR_STR(KR)                                                                                                 \
   mma_loop_fast<KR, false, false, true>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo,  \
                                         nkb_b16, tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar,     \
-                                        empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks)
+                                        empty_bar, tfull_bar, tempty_bar, n_res, res_off)
         if (b_res) {
-          if (R == 3) CCDM_PAIR_RES(3);
+          if (R == 9) CCDM_PAIR_RES(9);
+          else if (R == 3) CCDM_PAIR_RES(3);
           else if (R == 2) CCDM_PAIR_RES(2);
           else CCDM_PAIR_RES(1);
         } else {
-          if (R == 3) CCDM_PAIR_STR(3);
+          if (R == 9) CCDM_PAIR_STR(9);
+          else if (R == 3) CCDM_PAIR_STR(3);
           else if (R == 2) CCDM_PAIR_STR(2);
           else CCDM_PAIR_STR(1);
         }
@@ -472,17 +487,21 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       } else if (n_inner > 1) {                            // several channel tiles per box (qkv): weights always resident
         CCDM_MMA_LOOP(1, true, true);
       } else if (b_res) {
-        if (R == 3)
+        if (R == 9)
+          mma_loop_resident<9, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
+        else if (R == 3)
           mma_loop_resident<3, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
         else if (R == 2)
           mma_loop_resident<2, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
         else
           mma_loop_resident<1, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_ks);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
       } else {
-        if (R == 3) CCDM_MMA_LOOP(3, false, false);
+        if (R == 9) CCDM_MMA_LOOP(9, false, false);
+        else if (R == 3) CCDM_MMA_LOOP(3, false, false);
         else if (R == 2) CCDM_MMA_LOOP(2, false, false);
         else CCDM_MMA_LOOP(1, false, false);
       }
@@ -1052,8 +1071,10 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   CCDM_REQUIRE(a->n_src >= 1 && a->n_src <= CCDM_MAX_SRC, CCDM_ERR_BAD_ARG, "tapgemm: n_src=%d", a->n_src);
   CCDM_REQUIRE(a->tw > 0 && a->th > 0 && a->tb > 0 && a->tw * a->th * a->tb == kTileM, CCDM_ERR_BAD_ARG,
                "tapgemm: tile box %dx%dx%d must hold 128 positions", a->tw, a->th, a->tb);
-  CCDM_REQUIRE(a->nz >= 1 && a->nz <= CCDM_MAX_Z && a->ngroups >= 1 && a->R >= 1 && a->R <= 4, CCDM_ERR_BAD_ARG,
-               "tapgemm: nz=%d ngroups=%d R=%d", a->nz, a->ngroups, a->R);
+  CCDM_REQUIRE(a->nz >= 1 && a->nz <= CCDM_MAX_Z && a->ngroups >= 1 && a->R >= 1 && (a->R <= 4 || (a->halo && a->R == 9)),
+               CCDM_ERR_BAD_ARG, "tapgemm: nz=%d ngroups=%d R=%d", a->nz, a->ngroups, a->R);
+  CCDM_REQUIRE(!a->halo || (a->R == 9 && a->tb == 1 && a->tw == 8 && a->nz == 1 && a->w_batch_rows == 0 && a->n_tile <= 256),
+               CCDM_ERR_BAD_ARG, "tapgemm: halo boxes need R == 9, tile 8 x th x 1, nz == 1, shared weights, n_tile <= 256");
   CCDM_REQUIRE(a->R == 1 || (a->tb == 1 && a->tw % 8 == 0), CCDM_ERR_BAD_ARG,
                "tapgemm: vertical tap reuse (R=%d) needs tb == 1 and tw %% 8 == 0 (tile %dx%dx%d)", a->R, a->tw, a->th,
                a->tb);
@@ -1082,8 +1103,9 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   CCDM_REQUIRE(a->w_batch_rows == 0 || (a->tb == 1 && a->nz == 1 && a->w_batch_rows >= a->n_rows), CCDM_ERR_BAD_ARG,
                "tapgemm: per-sample weights need tb == 1, nz == 1 and w_batch_rows >= n_rows");
 
-  const int box_h = a->th + a->R - 1;
-  CCDM_REQUIRE(a->tw <= 256 && box_h <= 256 && a->tb <= 256, CCDM_ERR_BAD_ARG, "tapgemm: TMA box too large");
+  const int box_h = a->halo ? a->th + 2 : a->th + a->R - 1;
+  const int box_w = a->halo ? a->tw + 2 : a->tw;
+  CCDM_REQUIRE(box_w <= 256 && box_h <= 256 && a->tb <= 256, CCDM_ERR_BAD_ARG, "tapgemm: TMA box too large");
   TapGemmMaps maps;
   std::memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < CCDM_MAX_SRC; ++i) {
@@ -1094,7 +1116,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
                  CCDM_ERR_BAD_ARG, "tapgemm: source %d extents/strides (strides must be multiples of 8 elements)", i);
     cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.B};
     cuuint64_t str[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sB * 2};
-    cuuint32_t box[4] = {kBlockK, (cuuint32_t)a->tw, (cuuint32_t)box_h, (cuuint32_t)a->tb};
+    cuuint32_t box[4] = {kBlockK, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)a->tb};
     int rc = encode_map_bf16(&maps.a[i], v.ptr, 4, dims, str, box);
     if (rc != CCDM_OK) return rc;
   }
@@ -1138,11 +1160,6 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   p.tmem_cols = pow2_cols(a->n_tile * p.acc_stages * (n_res > 0 ? 2 : 1));
   p.n_res = n_res;
   p.res_bias = a->res_bias;
-  for (int i = 0; i < CCDM_MAX_SRC; ++i) {
-    p.srcC[i] = a->src[i < a->n_src ? i : 0].C;
-    const int tail = p.srcC[i] % 64;
-    if (i < a->n_src && tail != 0 && tail <= 48) p.has_ks = 1;
-  }
   p.a_bytes_res = (uint32_t)(a->th * a->tw * a->tb) * 128u;
   p.bias = a->bias; p.rowss = a->rowss; p.gain = a->gain; p.ss = a->scale_shift;
   p.ss_ld = a->ss_ld; p.ss_off = a->ss_off;
@@ -1210,8 +1227,10 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
 
   // ---- shared-memory plan
   const uint32_t b_bytes = (uint32_t)(p.pair ? a->n_tile / 2 : a->n_tile) * 128u;
-  p.a_bytes = (uint32_t)(box_h * a->tw * a->tb) * 128u;
-  const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)(a->ngroups + n_res) * (sizeof(int4) + sizeof(int));
+  const uint32_t a_tx = (uint32_t)(box_h * box_w * a->tb) * 128u;        // bytes one A box delivers
+  p.a_bytes = (a_tx + 1023u) & ~1023u;                                   // stage layout: 1 KiB granules (halo boxes: 23040 B)
+  p.halo = a->halo ? 1 : 0;
+  const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)(a->ngroups + n_res) * sizeof(int4);
   size_t budget = 226 * 1024 - aux_bytes - 1024;
   // bf16 outputs up to 256 channels per CTA leave through shared memory and TMA bulk stores (coalesced, clipped at the
   // tensor edges); wider tiles (4x4 bottleneck layers) and fp32 outputs keep per-thread stores
@@ -1229,6 +1248,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   }
   p.res_bytes = p.b_resident ? (uint32_t)res_all : 0;
   p.stage_bytes = p.a_bytes + (p.b_resident ? 0 : (uint32_t)a->R * b_bytes);
+  p.stage_tx = a_tx + (p.b_resident ? 0 : (uint32_t)a->R * b_bytes);
   int stages = (int)((budget - p.res_bytes) / p.stage_bytes);
   int useful = (a->ngroups + n_res) * (tiles_per_cta > 1 ? 2 : 1); // about two tiles of lookahead ...
   static const int min_stages = [] { const char* e = getenv("CCDM_TAPGEMM_MINSTAGES"); return e ? atoi(e) : 4; }();

@@ -25,7 +25,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _lib as L
-from .plan import ConvPlan, plan_conv, tile_box, can_reuse_rows, n_tiling, KB
+from .plan import ConvPlan, plan_conv, tile_box, can_reuse_rows, n_tiling, halo_ok, HALO_TILE, KB
 
 _SYNC_EACH = os.environ.get("CCDM_SYNC_EACH") == "1"
 
@@ -206,6 +206,7 @@ def _fill_tapgemm(r: TapGemmRec) -> L.TapGemmArgs:
     a.gW, a.gH, a.gB = r.gW, r.gH, r.gB
     a.tw, a.th, a.tb = r.tile
     a.nz, a.ngroups, a.R = r.plan.nz, r.plan.ngroups, r.plan.R
+    a.halo = int(getattr(r.plan, "halo", False))
     a.sched, a.wpacked = r.sched.data_ptr(), r.wpacked.data_ptr()
     a.n_rows, a.w_batch_rows, a.N, a.n_tile, a.flags = r.n_rows, r.w_batch_rows, r.N, r.n_tile, r.flags
     a.bias, a.rowss, a.gain, a.gain_mul = L.ptr(r.bias), L.ptr(r.rowss), L.ptr(r.gain), r.gain_mul
@@ -388,6 +389,7 @@ class WeightStore:
 # --------------------------------------------------------------------------------------------- program builder
 
 RESACC_ENABLED = os.environ.get("CCDM_RESACC", "1") != "0"      # A/B switch for profiles; the fused shortcut is the default
+HALO_ENABLED = os.environ.get("CCDM_HALO", "1") != "0"          # A/B switch: one halo box per 3x3 tile instead of three boxes
 
 
 class UnetEngine:
@@ -501,6 +503,16 @@ class UnetProgram(Program):
         tile = tile_box(gw, gh, square=(kind != "1x1"))
         reuse = kind != "1x1" and can_reuse_rows(tile)
         plan = plan_conv(kind, cins, cout, reuse_rows=reuse)
+        # 3x3 layers whose weights stay resident in shared memory read ALL nine taps out of one halo box per 64-channel block
+        # (a third of the TMA fills and L2 -> SM bytes of the three shifted boxes): the <= 64-wide layers of the 64x64 / 32x32
+        # levels, i.e. exactly the ones bound by the shared-memory port
+        if HALO_ENABLED and views is None and halo_ok(kind, gw, gh) and cout <= 128:
+            n_res_kb = sum(-(-t.shape[3] // KB) for t in res[0]) if res is not None else 0
+            nkb_tot = 9 * sum(-(-c // KB) for c in cins) + n_res_kb
+            pad = (cout + 31) // 32 * 32
+            resident = nkb_tot * pad * 128 // (2 if nkb_tot >= 16 else 1)
+            if resident <= 96 * 1024:
+                plan, tile = plan_conv(kind, cins, cout, halo=True), HALO_TILE
         full_row = bool(flags & (L.EPI_RMSNORM | L.EPI_SUMSQ_OUT))
         # A fused channel norm needs the whole row in one CTA (<= 512 TMEM columns).  Wider layers (dim-72 models:
         # 576) and layers with too few pixel tiles to fill the GPU (4x4 / 8x8 levels) run the GEMM split over output

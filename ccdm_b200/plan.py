@@ -87,6 +87,8 @@ class ConvPlan:
     out_parity: bool = False              # nz == 4 output parity planes (nearest-2x + 3x3)
     stride: int = 1
     transposed: bool = False              # data-gradient plan: pack W with input/output channel roles swapped
+    halo: bool = False                    # 3x3: ONE box {64, tw+2, th+2} per 64-channel block feeds all nine taps (R == 9;
+                                          # K block g*9 + r*3 + q = tap (r, q)); tile 8 x 16 x 1
 
     @property
     def nkb(self) -> int:
@@ -101,7 +103,15 @@ def _chunks(c: int):
     return [(c0, min(KB, c - c0)) for c0 in range(0, c, KB)]
 
 
-def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = False) -> ConvPlan:
+HALO_TILE = (8, 16, 1)
+
+
+def halo_ok(kind: str, gw: int, gh: int) -> bool:
+    """A 3x3 stride-1 layer whose output grid is covered by 8 x 16 tiles can read its taps out of one halo box per tile."""
+    return kind == "3x3" and gw % HALO_TILE[0] == 0 and gh % HALO_TILE[1] == 0
+
+
+def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = False, halo: bool = False) -> ConvPlan:
     """kind: '1x1' | '3x3' | 'down4x4s2' | 'down3x3s2' | 'up2x3x3' | 'up2x1x1' | 'stem7' | '<kind>_dgrad'.  ``reuse_rows`` groups vertically adjacent taps (R > 1)."""
     cins = tuple(int(c) for c in cins)
     offs = [sum(cins[:i]) for i in range(len(cins))]
@@ -130,6 +140,13 @@ def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = Fals
             emit(s, s, 0, [(0, 1)])
         R = 1
         return ConvPlan(kind, cins, cout, 1, 1, len(sched), 1, sched, psched)
+    if kind == "3x3" and halo:
+        for s in range(len(cins)):
+            for c0, nv in _chunks(cins[s]):
+                sched.append((s, -1, -1, c0))
+                for t in range(9):
+                    psched.append((offs[s] + c0, nv, 1 << t, 0))          # tap (r, q) = divmod(t, 3)
+        return ConvPlan(kind, cins, cout, 9, 1, len(sched), 9, sched, psched, halo=True)
     if kind == "3x3":
         for q in range(3):
             for s in range(len(cins)):

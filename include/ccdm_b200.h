@@ -104,6 +104,8 @@ typedef struct ccdm_tapgemm_args {
   int32_t q_cols;
   /* CCDM_EPI_HEAD: head_w fp32 [head_n][N], head_b fp32 [head_n], head_out fp32 with plane stride hsC and sample stride
      hsB (elements; pixel (h, w) at h*gW + w inside a plane), 1 <= head_n <= 4 */
+  int32_t halo;          /* 1: 3x3 (R == 9): every load group is ONE box {64 ch, tw+2, th+2} at (dw, dh0) = (-1, -1) feeding all nine
+                            taps (K block g*9 + r*3 + q = tap (r, q)); needs tile 8 x th x 1.  A third of the fills of R == 3 */
   int32_t n_res;         /* CCDM_EPI_RESACC: shortcut load groups; wpacked then has ngroups*R + n_res K blocks per row */
   const float* res_bias; /* fp32 [N] or NULL */
   int32_t head_n;

@@ -66,7 +66,10 @@ def tapgemm_emu(plan: ConvPlan, srcs, w, gh, gw, n_rows=None, cin_gain=None, n_o
             src, dw, dh0, c0 = plan.sched[z * plan.ngroups + g]
             for r in range(plan.R):
                 kb = g * plan.R + r
-                a = shifted(views[src], dh0 + r, dw, gh, gw, c0)
+                if getattr(plan, "halo", False):                      # nine taps of one halo box: (r, q) = divmod(tap, 3)
+                    a = shifted(views[src], dh0 + r // 3, dw + r % 3, gh, gw, c0)
+                else:
+                    a = shifted(views[src], dh0 + r, dw, gh, gw, c0)
                 acc = acc + a @ packed[z, :nout, kb * KB:(kb + 1) * KB].t()
         outs.append(acc)
     return torch.stack(outs)

@@ -44,7 +44,10 @@ def run_tapgemm(r: TapGemmRec):
         for kb in range(r.plan.nkb):
             g, rr = divmod(kb, r.plan.R)
             src, dw, dh0, c0 = r.plan.sched[z * r.plan.ngroups + g]
-            a = shifted(views[src], dh0 + rr, dw, gH, gW, c0)                # [vB, gH, gW, 64]
+            if getattr(r.plan, "halo", False):                                # nine taps of one halo box
+                a = shifted(views[src], dh0 + rr // 3, dw + rr % 3, gH, gW, c0)
+            else:
+                a = shifted(views[src], dh0 + rr, dw, gH, gW, c0)            # [vB, gH, gW, 64]
             a = a[:gB]
             if r.w_batch_rows:
                 wrows = torch.stack([wp[b * r.w_batch_rows: b * r.w_batch_rows + r.N, kb * KB:(kb + 1) * KB]

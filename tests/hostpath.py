@@ -62,6 +62,7 @@ class _Plan:
 
     def __init__(self, a):
         self.nz, self.ngroups, self.R = a.nz, a.ngroups, a.R
+        self.halo = bool(getattr(a, "halo", 0))
         self.nkb = a.ngroups * a.R
         n_res = a.n_res if (getattr(a, "flags", 0) & L.EPI_RESACC) else 0
         n = (a.nz * a.ngroups + n_res) * 4
@@ -195,7 +196,7 @@ def install(monkeypatch):
     """ccdm_b200.backward / train / diffusion run UNCHANGED (plans, weight packing, argument structs); only the library handle is
     swapped: CUDA-core kernels from source, the tcgen05 entry points at the C-ABI level."""
     lib = HostLib()
-    monkeypatch.setattr(L, "lib", lambda: lib)
+    monkeypatch.setattr(L, "lib", lambda precision="bf16": lib)
     monkeypatch.setattr(K, "_stream", lambda: None)
     monkeypatch.setattr(K, "_check", lambda t, what: None)             # "expected a CUDA tensor": host pointers are fine here
     from ccdm_b200.diffusion import GaussianDiffusion

@@ -163,6 +163,9 @@ static inline void load8(const float* p, float (&o)[8]) { for (int j = 0; j < 8;
 static inline float silu_f(float v) { return v / (1.0f + expf(-v)); }
 static inline float ex2_fast(float x) { return exp2f(x); }
 static inline float tanh_fast(float x) { return tanhf(x); }
+#define CCDM_KEXP_SHIFT 0.0f
+#define CCDM_ONE_PAIR 0x3F803F80u
+static inline float tanh_silu(float x) { return tanhf(x); }
 static inline float sigmoid_fast(float x) { return fmaf(0.5f, tanhf(0.5f * x), 0.5f); }
 static inline float seg_sum(float v, int gl, int G, int lane) {
   if ((G & (G - 1)) == 0) {

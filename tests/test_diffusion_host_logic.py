@@ -50,7 +50,7 @@ def host_sampler(monkeypatch):
         setattr(lib, name, fn)
     h.hostsim_last_error.restype = C.c_char_p
     lib.ccdm_last_error = h.hostsim_last_error
-    monkeypatch.setattr(L, "lib", lambda: lib)
+    monkeypatch.setattr(L, "lib", lambda precision="bf16": lib)
     monkeypatch.setattr(GaussianDiffusion, "_stream", staticmethod(lambda: None))
 
 
