@@ -1124,10 +1124,10 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   const int n_sub = a->n_tile / nsub;
   const int n_res = (a->flags & CCDM_EPI_RESACC) ? a->n_res : 0;
   CCDM_REQUIRE(!(a->flags & CCDM_EPI_RESACC) ||
-                   (a->n_res >= 1 && a->nz == 1 && a->n_tile <= 128 && a->w_batch_rows == 0 && a->R <= 3 &&
+                   (a->n_res >= 1 && a->nz == 1 && a->n_tile <= 128 && a->w_batch_rows == 0 && (a->R <= 3 || a->halo) &&
                     !(a->flags & CCDM_EPI_RESID)),
                CCDM_ERR_BAD_ARG,
-               "tapgemm: CCDM_EPI_RESACC needs n_res >= 1, nz == 1, n_tile <= 128, shared weights, R <= 3 and no CCDM_EPI_RESID");
+               "tapgemm: CCDM_EPI_RESACC needs n_res >= 1, nz == 1, n_tile <= 128, shared weights, R <= 3 (or halo boxes) and no CCDM_EPI_RESID");
   const int nkb = a->ngroups * a->R + n_res;               // K blocks of the packed weights: main taps, then the shortcut's
   if (n_res > 0) {                                         // shortcut boxes: th rows (one tap, no halo rows)
     for (int i = 0; i < CCDM_MAX_SRC; ++i) {
@@ -1200,7 +1200,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
     // per-tile time is dominated by load / store latency that the pair's cross-SM handshakes lengthen.
     static const int pair_env = [] { const char* e = getenv("CCDM_TAPGEMM_PAIR"); return e ? atoi(e) : 16; }();
     static const int pair_min_tiles = [] { const char* e = getenv("CCDM_TAPGEMM_PAIR_MINTILES"); return e ? atoi(e) : 1; }();
-    p.pair = (pair_env != 0 && nkb >= pair_env && a->w_batch_rows == 0 && nsub == 1 && p.n_inner == 1 && a->R <= 3 && a->n_tile <= 256 &&
+    p.pair = (pair_env != 0 && nkb >= pair_env && a->w_batch_rows == 0 && nsub == 1 && p.n_inner == 1 && (a->R <= 3 || a->halo) && a->n_tile <= 256 &&
               (a->n_tile / 2) % 16 == 0 && gx >= 2 && tiles_per_cta >= pair_min_tiles &&
               !(a->flags & (CCDM_EPI_OUT_F32 | CCDM_EPI_HEAD))) ? 1 : 0;
     if (p.pair) {

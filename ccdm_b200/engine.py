@@ -511,7 +511,10 @@ class UnetProgram(Program):
             nkb_tot = 9 * sum(-(-c // KB) for c in cins) + n_res_kb
             pad = (cout + 31) // 32 * 32
             resident = nkb_tot * pad * 128 // (2 if nkb_tot >= 16 else 1)
-            if resident <= 96 * 1024:
+            # (measured: with >= 2 shortcut groups AND an output staging buffer the 23 KB stages leave too little lookahead --
+            # ups.4.x block2 202 -> 210-224 us -- while the head-fused final block, which stages nothing, gains 12 us)
+            crowded = n_res_kb >= 2 and head is None
+            if resident <= 96 * 1024 and not crowded:
                 plan, tile = plan_conv(kind, cins, cout, halo=True), HALO_TILE
         full_row = bool(flags & (L.EPI_RMSNORM | L.EPI_SUMSQ_OUT))
         # A fused channel norm needs the whole row in one CTA (<= 512 TMEM columns).  Wider layers (dim-72 models:
