@@ -64,6 +64,11 @@ class LossArgs(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("w", vp), ("out", vp), ("psched", vp), ("mode", i32), ("cout", i32), ("cin_total", i32), ("ntaps", i32),
+                ("nkb", i32), ("n_rows", i32), ("n_off", i32), ("n_count", i32), ("total", i64)]
+
+
 class WgradArgs(C.Structure):
     _fields_ = [
         ("n_src", i32), ("src", View * MAX_SRC), ("dz", vp), ("dsW", i64), ("dsH", i64), ("dsB", i64),
@@ -81,6 +86,7 @@ SIGNATURES = {
     "ccdm_struct_size": (C.c_int, [C.c_int]),
     "ccdm_tapgemm": (C.c_int, [C.POINTER(TapGemmArgs), vp]),
     "ccdm_pack_weights": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, vp, vp]),
+    "ccdm_pack_multi": (C.c_int, [vp, i32, vp]),
     "ccdm_pack_weights_at": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, vp, i32, i32, vp]),
     "ccdm_rmsnorm_act": (C.c_int, [vp, vp, i64, i32, i32, vp, f32, vp, i32, i32, vp, vp, C.c_uint32, vp]),
     "ccdm_stem_im2row": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),

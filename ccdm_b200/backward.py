@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import weakref
 import math
 from typing import List, Optional, Sequence, Tuple
 
@@ -122,10 +123,11 @@ def conv_forward(kind: str, srcs: Sequence[torch.Tensor], weight: torch.Tensor, 
     plan, tile = _plan_for(kind, [s.shape[3] for s in srcs], cout, gw, gh)
     n_rows, n_tile = n_tiling(cout, False)
     dev = weight.device
-    packed = torch.empty(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
     sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
-    L.check(L.lib().ccdm_pack_weights(weight.data_ptr(), cout, weight.shape[1], _KIND_TAPS[kind], psched.data_ptr(),
-                                      plan.nz, plan.nkb, n_rows, None, 1.0, packed.data_ptr(), _stream()), "pack_weights")
+    packed, need = PACKS.get(weight, 0, kind, plan, n_rows, 0, cout, psched)
+    if need:
+        L.check(L.lib().ccdm_pack_weights(weight.data_ptr(), cout, weight.shape[1], _KIND_TAPS[kind], psched.data_ptr(),
+                                          plan.nz, plan.nkb, n_rows, None, 1.0, packed.data_ptr(), _stream()), "pack_weights")
     views: List[L.View] = []
     for s in srcs:
         views += _parity_views(s) if plan.n_views == 4 else [_view(s)]
@@ -187,11 +189,12 @@ def conv_dgrad(kind: str, dy: torch.Tensor, weight: torch.Tensor, cins: Sequence
     for cin in cins:
         plan, tile = _plan_for(kind + "_dgrad", (cout,), cin, gw, gh)
         n_rows, n_tile = n_tiling(cin, False)
-        packed = torch.empty(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=dev)
         sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
-        L.check(L.lib().ccdm_pack_weights_t(weight.data_ptr(), cout, weight.shape[1], _KIND_TAPS[kind], psched.data_ptr(),
-                                            plan.nz, plan.nkb, n_rows, n_off, cin, packed.data_ptr(), _stream()),
-                "pack_weights_t")
+        packed, need = PACKS.get(weight, 1, kind, plan, n_rows, n_off, cin, psched)
+        if need:
+            L.check(L.lib().ccdm_pack_weights_t(weight.data_ptr(), cout, weight.shape[1], _KIND_TAPS[kind], psched.data_ptr(),
+                                                plan.nz, plan.nkb, n_rows, n_off, cin, packed.data_ptr(), _stream()),
+                    "pack_weights_t")
         views = _parity_views(dy) if plan.n_views == 4 else [_view(dy)]
         dx = torch.empty(b, h, w, cin, dtype=torch.bfloat16, device=dev)
         ostr, ooff = _out_geometry(dx, plan.out_parity)
@@ -234,6 +237,66 @@ class ZeroArena:
 
 
 ARENA = ZeroArena()
+
+
+class PackCache:
+    """Persistent packed bf16 copies of the convolution weights of the TRAINING path (forward layout and the transposed layout of
+    the data gradient) plus the job table of ``ccdm_pack_multi``: ``begin_step`` re-packs every known weight in ONE launch
+    (weights change once per optimizer step), so ``conv_forward`` / ``conv_dgrad`` launch their own pack only for a weight they
+    see for the first time or whose ``_version`` moved since the batched launch."""
+
+    def __init__(self):
+        self.entries = {}                 # key -> [packed, weakref(weight), version stamp, job index]
+        self.jobs = []                    # L.PackJob structs (host)
+        self.table = None                 # device copy of the job table
+        self.table_len = 0
+
+    def get(self, weight, mode, kind, plan, n_rows, n_off, n_count, psched):
+        """(packed tensor, True when the caller has to pack it now)."""
+        key = (weight.data_ptr(), tuple(weight.shape), mode, plan.kind, plan.cins, plan.cout, plan.R, n_rows, n_off)
+        ent = self.entries.get(key)
+        if ent is not None and ent[1]() is weight:
+            stale = ent[2] != weight._version
+            ent[2] = weight._version
+            return ent[0], stale
+        with torch.inference_mode(False):
+            packed = torch.empty(plan.nz * n_rows, plan.nkb * KB, dtype=torch.bfloat16, device=weight.device)
+        job = L.PackJob()
+        job.w, job.out, job.psched = weight.data_ptr(), packed.data_ptr(), psched.data_ptr()
+        job.mode, job.cout, job.cin_total, job.ntaps = mode, weight.shape[0], weight.shape[1], _KIND_TAPS[kind]
+        job.nkb, job.n_rows, job.n_off, job.n_count = plan.nkb, n_rows, n_off, n_count
+        job.total = plan.nz * n_rows * plan.nkb * KB
+        if ent is not None:               # same storage, another tensor object: rebind the slot
+            self.jobs[ent[3]] = job
+            idx = ent[3]
+        else:
+            self.jobs.append(job)
+            idx = len(self.jobs) - 1
+        self.entries[key] = [packed, weakref.ref(weight), weight._version, idx, psched]
+        self.table = None                 # rebuilt by the next begin_step
+        return packed, True
+
+    def begin_step(self, device):
+        """One ccdm_pack_multi launch over every known weight (none on the very first step: the layers register themselves)."""
+        dead = [k for k, e in self.entries.items() if e[1]() is None]
+        if dead:                          # a model went away: forget its weights (pointers in the table would dangle)
+            self.entries, self.jobs, self.table = {}, [], None
+            return
+        if not self.jobs:
+            return
+        if self.table is None or self.table_len != len(self.jobs):
+            raw = b"".join(bytes(j) for j in self.jobs)
+            with torch.inference_mode(False):
+                self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+            self.table_len = len(self.jobs)
+        L.check(L.lib().ccdm_pack_multi(self.table.data_ptr(), len(self.jobs), _stream()), "pack_multi")
+        for e in self.entries.values():
+            w = e[1]()
+            if w is not None:
+                e[2] = w._version
+
+
+PACKS = PackCache()
 
 
 @functools.lru_cache(maxsize=None)

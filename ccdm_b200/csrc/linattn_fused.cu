@@ -639,15 +639,18 @@ __global__ void __launch_bounds__(kLa2Threads, 1) linattn_qout_kernel(const __gr
         float mx = __uint_as_float(r[0]);
 #pragma unroll
         for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        // softmax(rs * a): exponent (a - max a) * rs * log2e   (rs > 0, so the max commutes with the scaling)
+        // softmax(rs * a): exponent (a - max a) * rs * log2e   (rs > 0, so the max commutes with the scaling).  The
+        // exponentials overwrite the accumulator registers: 18 warps leave 96 registers per thread, a second 32-value array
+        // spilled.
         const float2 nm2 = make_float2(-mx * k1, -mx * k1);
-        float2 e[16];
         float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 x2 = __ffma2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), k12, nm2);
-          e[i] = make_float2(ex2_fast(x2.x), ex2_fast(x2.y));
-          sum2 = __fadd2_rn(sum2, e[i]);
+          const float2 ei = make_float2(ex2_fast(x2.x), ex2_fast(x2.y));
+          r[2 * i] = __float_as_uint(ei.x);
+          r[2 * i + 1] = __float_as_uint(ei.y);
+          sum2 = __fadd2_rn(sum2, ei);
         }
         const float kk = __fdividef(p.q_scale, sum2.x + sum2.y);
         const float2 kk2 = make_float2(kk, kk);
@@ -655,8 +658,10 @@ __global__ void __launch_bounds__(kLa2Threads, 1) linattn_qout_kernel(const __gr
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg) {
           uint4 o;
-          const float2 a0 = __fmul2_rn(e[gg * 4 + 0], kk2), a1 = __fmul2_rn(e[gg * 4 + 1], kk2);
-          const float2 a2 = __fmul2_rn(e[gg * 4 + 2], kk2), a3 = __fmul2_rn(e[gg * 4 + 3], kk2);
+#define CCDM_E2(j) make_float2(__uint_as_float(r[2 * (j)]), __uint_as_float(r[2 * (j) + 1]))
+          const float2 a0 = __fmul2_rn(CCDM_E2(gg * 4 + 0), kk2), a1 = __fmul2_rn(CCDM_E2(gg * 4 + 1), kk2);
+          const float2 a2 = __fmul2_rn(CCDM_E2(gg * 4 + 2), kk2), a3 = __fmul2_rn(CCDM_E2(gg * 4 + 3), kk2);
+#undef CCDM_E2
           o.x = pack_bf16(a0.x, a0.y);
           o.y = pack_bf16(a1.x, a1.y);
           o.z = pack_bf16(a2.x, a2.y);

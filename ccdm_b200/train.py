@@ -361,6 +361,7 @@ def unet_train_forward(net, x: torch.Tensor, t: torch.Tensor, labels_emb: torch.
     ss_all = F.linear(tc, torch.cat([m.tc_mlp[1].weight for m in blocks]), torch.cat([m.tc_mlp[1].bias for m in blocks]))
     ss_it = iter(torch.split(ss_all, [m.tc_mlp[1].weight.shape[0] for m in blocks], dim=1))
     K.ARENA.begin_step(x.device)
+    K.PACKS.begin_step(x.device)                                   # every conv weight re-packed (both layouts) in one launch
 
     stem = StemFn.apply(x.float(), net.init_conv.weight, net.init_conv.bias)
     h = stem

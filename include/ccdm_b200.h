@@ -124,6 +124,17 @@ int ccdm_tapgemm(const ccdm_tapgemm_args* args, void* stream);
 int ccdm_pack_weights(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,
                       int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain, float gain_mul, void* wpacked,
                       void* stream);
+/* Multi-tensor form of ccdm_pack_weights (mode 0) / ccdm_pack_weights_t (mode 1) for the training step, where every
+ * convolution weight is re-packed once per optimizer step (autograd of the nn.Conv2d sites reached from trainer.py:724): one
+ * launch over a DEVICE-resident job table.  total = nz * n_rows * nkb * 64 packed elements. */
+typedef struct ccdm_pack_job {
+  const float* w;
+  void* out;
+  const int32_t* psched;
+  int32_t mode, cout, cin_total, ntaps, nkb, n_rows, n_off, n_count;
+  int64_t total;
+} ccdm_pack_job;
+int ccdm_pack_multi(const ccdm_pack_job* jobs, int32_t njobs, void* stream);
 /* The same, into K blocks [kb0, kb0 + nkb) of a packed matrix with nkb_total K blocks per row (a conv and its block's shortcut
  * share one matrix, CCDM_EPI_RESACC). */
 int ccdm_pack_weights_at(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,

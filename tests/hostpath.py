@@ -31,7 +31,7 @@ class HostLib:
 
     def __init__(self):
         handles = [C.CDLL(build(f)) for f in ("kernels.cu", "train_kernels.cu", "backward.cu", "sampler.cu", "groupnorm.cu",
-                                              "optim.cu")]
+                                              "optim.cu", "packmulti.cu")]
         handles.append(C.CDLL(build_extract("wgrad.cu", ["unpack_wgrad_kernel", "pack_weights_t_kernel"],
                                             ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"])))
         handles.append(C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights_at", "ccdm_pack_weights"])))
