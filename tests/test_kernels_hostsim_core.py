@@ -41,7 +41,7 @@ def samp():
 def kern():
     return _load("kernels.cu", ["ccdm_rmsnorm_act", "ccdm_affine_act", "ccdm_head_conv1", "ccdm_attention_small",
                                 "ccdm_linear_small", "ccdm_time_features", "ccdm_select_null", "ccdm_silu_concat_bf16",
-                                "ccdm_condbn_coef"])
+                                "ccdm_condbn_coef", "ccdm_groupnorm_rows"])
 
 
 @pytest.fixture(scope="module")
@@ -490,3 +490,69 @@ def test_transposed_pack_kernel_matches_the_emulator(packlib, kind, cin, cout, r
                                   packed.data_ptr(), None) == 0
     want = pack_weights_emu(plan, w, n_rows).reshape(plan.nz * n_rows, -1)
     assert torch.equal(packed, want.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------- round-2 additions
+
+@pytest.mark.parametrize("B,C_,groups,act", [(5, 128, 8, 1), (33, 512, 8, 1), (2, 48, 4, 0), (7, 4096, 8, 1)])
+def test_groupnorm_rows_matches_torch(kern, B, C_, groups, act):
+    """ccdm_groupnorm_rows = nn.GroupNorm(groups, C) on a [B, C] matrix + ReLU, in place (the learned label MLPs,
+    models/resnet_y2h.py:143-173)."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, C_, generator=g) * 3 + 1
+    gamma, beta = 1 + 0.3 * torch.randn(C_, generator=g), 0.2 * torch.randn(C_, generator=g)
+    want = F.group_norm(x, groups, gamma, beta, 1e-5)
+    want = F.relu(want) if act == 1 else want
+    y = x.clone()
+    assert kern.ccdm_groupnorm_rows(y.data_ptr(), B, C_, groups, gamma.data_ptr(), beta.data_ptr(), 1e-5, act, None) == 0
+    assert rel(y, want) < 2e-6
+    assert kern.ccdm_groupnorm_rows(y.data_ptr(), B, 50, 8, gamma.data_ptr(), beta.data_ptr(), 1e-5, act, None) == -1   # C % groups
+
+
+def test_pack_multi_and_pack_at_match_the_single_tensor_kernels(packlib):
+    """ccdm_pack_multi (one launch over a job table: the training step's weight re-pack, both layouts) and
+    ccdm_pack_weights_at (a conv and its block's shortcut in ONE packed matrix, CCDM_EPI_RESACC) against the emulator."""
+    from ccdm_b200.plan import KB, plan_conv
+    from tests.emu import pack_weights_emu
+    from tests.hostsim.build import build
+    pm = C.CDLL(build("packmulti.cu"))
+    pm.ccdm_pack_multi.restype, pm.ccdm_pack_multi.argtypes = L.SIGNATURES["ccdm_pack_multi"]
+    pk, _ = packlib
+    g = torch.Generator().manual_seed(21)
+    specs = [("3x3", (40, 24), 24, 0), ("3x3", (72,), 72, 0), ("1x1", (96,), 32, 0), ("3x3_dgrad", (24,), 40, 1)]
+    jobs, outs, wants, keep = [], [], [], []
+    for kind, cins, cout, mode in specs:
+        base = kind[:-6] if mode else kind
+        taps = 9 if base == "3x3" else 1
+        k = 3 if taps == 9 else 1
+        plan = plan_conv(kind, cins, cout, reuse_rows=(taps == 9))
+        n_rows = (cout + 31) // 32 * 32
+        # forward weights are [Cout, Cin, k, k]; a dgrad plan packs the FORWARD weight [Cout_fwd = cins[0], Cin_fwd >= cout, ...]
+        w = torch.randn(cout, sum(cins), k, k, generator=g) if not mode else torch.randn(cins[0], cout + 8, k, k, generator=g)
+        packed = torch.full((plan.nz * n_rows, plan.nkb * KB), 7.0).to(torch.bfloat16)
+        ps = _i32(plan.psched)
+        j = L.PackJob()
+        j.w, j.out, j.psched, j.mode = w.data_ptr(), packed.data_ptr(), ps.data_ptr(), mode
+        j.cout, j.cin_total, j.ntaps, j.nkb, j.n_rows = w.shape[0], w.shape[1], taps, plan.nkb, n_rows
+        j.n_off, j.n_count, j.total = (4 if mode else 0), cout, plan.nz * n_rows * plan.nkb * KB
+        jobs.append(j)
+        outs.append(packed)
+        wants.append(pack_weights_emu(plan, w, n_rows, n_off=j.n_off, n_count=cout if mode else None).reshape(plan.nz * n_rows, -1))
+        keep += [w, ps]
+    table = torch.frombuffer(bytearray(b"".join(bytes(j) for j in jobs)), dtype=torch.uint8)
+    assert pm.ccdm_pack_multi(table.data_ptr(), len(jobs), None) == 0
+    for got, want in zip(outs, wants):
+        assert torch.equal(got, want.to(torch.bfloat16))
+    # pack_weights_at: main 3x3 weight in K blocks [0, 9), the 1x1 shortcut weight in block 9 of the same matrix
+    main, sc = plan_conv("3x3", (48,), 32, reuse_rows=True), plan_conv("1x1", (48,), 32)
+    w3, w1 = torch.randn(32, 48, 3, 3, generator=g), torch.randn(32, 48, 1, 1, generator=g)
+    both = torch.full((32, (main.nkb + sc.nkb) * KB), 5.0).to(torch.bfloat16)
+    p3, p1 = _i32(main.psched), _i32(sc.psched)
+    assert pk.ccdm_pack_weights_at(w3.data_ptr(), 32, 48, 9, p3.data_ptr(), 1, main.nkb, 32, None, 1.0, both.data_ptr(),
+                                   main.nkb + sc.nkb, 0, None) == 0
+    assert pk.ccdm_pack_weights_at(w1.data_ptr(), 32, 48, 1, p1.data_ptr(), 1, sc.nkb, 32, None, 1.0, both.data_ptr(),
+                                   main.nkb + sc.nkb, main.nkb, None) == 0
+    want = torch.cat([pack_weights_emu(main, w3, 32)[0], pack_weights_emu(sc, w1, 32)[0]], dim=1)
+    assert torch.equal(both, want.to(torch.bfloat16))
+    assert pk.ccdm_pack_weights_at(w1.data_ptr(), 32, 48, 1, p1.data_ptr(), 1, sc.nkb, 32, None, 1.0, both.data_ptr(),
+                                   main.nkb, main.nkb, None) == -1                       # K blocks out of range

@@ -145,3 +145,23 @@ def test_dgrad_plans(kind, cin, cout, hw, reuse):
         got2 = tapgemm_emu(plan_conv("3x3_dgrad", (cout,), cin - half, reuse_rows=reuse), [nhwc(dy)], w, hw[0], hw[1],
                            n_off=half, n_count=cin - half)[0]
         assert rel(got2, nhwc(dx)[..., half:]) < 1e-5
+
+
+@pytest.mark.parametrize("cins,cout", [((64,), 64), ((64, 64), 64), ((72,), 72), ((40, 24), 32)])
+def test_halo_plan_equals_conv(cins, cout):
+    """3x3 with ONE halo box per 64-channel block (plan.halo, R = 9: K block g*9 + r*3 + q = tap (r, q), box origin (-1, -1)):
+    the tap-GEMM semantics reproduce F.conv2d(padding=1), exactly like the three-box plan."""
+    import torch.nn.functional as F
+    from ccdm_b200.plan import plan_conv, halo_ok, HALO_TILE
+    from tests.emu import tapgemm_emu
+    g = torch.Generator().manual_seed(31)
+    B, H, W = 2, 16, 8
+    assert halo_ok("3x3", W, H) and not halo_ok("3x3", 12, 16) and not halo_ok("1x1", W, H) and HALO_TILE == (8, 16, 1)
+    srcs = [torch.randn(B, H, W, c, generator=g) for c in cins]
+    w = torch.randn(cout, sum(cins), 3, 3, generator=g)
+    plan = plan_conv("3x3", cins, cout, halo=True)
+    assert plan.halo and plan.R == 9 and plan.ngroups == sum(-(-c // 64) for c in cins) and plan.nkb == 9 * plan.ngroups
+    assert all(e[1] == -1 and e[2] == -1 for e in plan.sched)
+    got = tapgemm_emu(plan, srcs, w, H, W)[0]
+    want = F.conv2d(torch.cat(srcs, -1).permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
+    assert (got - want).abs().max() < 1e-3 * want.abs().max()
