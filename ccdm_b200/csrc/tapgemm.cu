@@ -116,17 +116,24 @@ template <int kR, bool kPair = false>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t tap16, uint32_t b16,
                                            uint32_t idesc, bool first_group) {
   if constexpr (kR == 9) {                                 // halo box: 3 x 3 taps, 10-row image pitch (tw == 8)
+    // One filter row (12 MMAs) per loop iteration: fully unrolled, the 72 descriptor words of a group overflow the uniform
+    // register file and every R2UR.FILL of a spilled one stalls the issuing lane (26 % of its samples in ncu).
+    uint32_t b_t = b_lo;
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+      uint32_t a_t = a_lo + static_cast<uint32_t>(r) * 80u;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const uint32_t a_t = a_lo + static_cast<uint32_t>((t / 3) * 10 + (t % 3)) * 8u;
+      for (int q = 0; q < 3; ++q) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (kPair)
-          umma_bf16_ss_2sm(d_tmem, umma_desc_lo_halo(a_t + 2 * k), umma_desc_lo(b_lo + t * b16 + 2 * k), idesc,
-                           (t | k) != 0 ? 1u : (first_group ? 0u : 1u));
-        else
-          umma_bf16_ss(d_tmem, umma_desc_lo_halo(a_t + 2 * k), umma_desc_lo(b_lo + t * b16 + 2 * k), idesc,
-                       (t | k) != 0 ? 1u : (first_group ? 0u : 1u));
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t acc = (r | q | k) != 0 ? 1u : (first_group ? 0u : 1u);
+          if (kPair)
+            umma_bf16_ss_2sm(d_tmem, umma_desc_lo_halo(a_t + 2 * k), umma_desc_lo(b_t + 2 * k), idesc, acc);
+          else
+            umma_bf16_ss(d_tmem, umma_desc_lo_halo(a_t + 2 * k), umma_desc_lo(b_t + 2 * k), idesc, acc);
+        }
+        a_t += 8u;
+        b_t += b16;
       }
     }
     return;

@@ -16,13 +16,16 @@ from ccdm_b200.engine import Program, TapGemmRec, WeightStore, nhwc_view, tapgem
 from ccdm_b200.plan import plan_conv, tile_box, n_tiling, can_reuse_rows  # noqa: E402
 
 
-def build(kind, B, H, W, cins, cout, flags, dev, tile=None, n_tile=None, reuse=True):
+def build(kind, B, H, W, cins, cout, flags, dev, tile=None, n_tile=None, reuse=True, halo=False):
     xs = [torch.randn(B, H, W, c, device=dev).to(torch.bfloat16) for c in cins]
     k = {"1x1": 1, "3x3": 3}[kind]
     conv = torch.nn.Conv2d(sum(cins), cout, k).to(dev)
     ws, prog = WeightStore(dev), Program(dev)
     tile = tile or tile_box(W, H, square=(kind != "1x1"))
     plan = plan_conv(kind, cins, cout, reuse_rows=(reuse and kind != "1x1" and can_reuse_rows(tile)))
+    if halo and kind == "3x3":
+        from ccdm_b200.plan import HALO_TILE
+        plan, tile = plan_conv(kind, cins, cout, halo=True), HALO_TILE
     n_rows, nt = n_tiling(cout, bool(flags & (L.EPI_RMSNORM | L.EPI_SUMSQ_OUT)))
     nt = n_tile or nt
     pack = ws.add("w", conv.weight, plan, n_rows)
@@ -53,6 +56,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--tile", default=None, help="tw,th,tb override")
     ap.add_argument("--no-reuse", action="store_true")
+    ap.add_argument("--halo", action="store_true", help="3x3 layers read their nine taps out of one halo box per tile")
     a = ap.parse_args()
     tile = tuple(int(v) for v in a.tile.split(",")) if a.tile else None
     dev = torch.device("cuda")
@@ -67,7 +71,7 @@ def main():
     }
     names = list(cases) if a.which == "all" else a.which.split(",")
     for nm in names:
-        prog, rec = build(*cases[nm], dev, tile=tile, reuse=not a.no_reuse)
+        prog, rec = build(*cases[nm], dev, tile=tile, reuse=not a.no_reuse, halo=a.halo)
         s = torch.cuda.current_stream().cuda_stream
         prog.run(s)
         torch.cuda.synchronize()
