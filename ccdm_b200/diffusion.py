@@ -227,6 +227,11 @@ class GaussianDiffusion(nn.Module):
     def _ddim_tables(self):
         """Per-step rows for DDIM (diffusion.py:422-428, 454-460), computed with the reference's fp32 tensor math."""
         T, S, eta = self.num_timesteps, self.sampling_timesteps, self.ddim_sampling_eta
+        # ~8 tiny device ops per step: computed once per (steps, eta, schedule) instead of on every ddim_sample call
+        key = (T, S, float(eta), str(self.device), self.alphas_cumprod.data_ptr(), self.alphas_cumprod._version)
+        cache = self.__dict__.setdefault("_ddim_table_cache", {})
+        if key in cache:
+            return cache[key]
         times = torch.linspace(-1, T - 1, steps=S + 1)
         times = list(reversed(times.int().tolist()))
         pairs = list(zip(times[:-1], times[1:]))
@@ -243,6 +248,8 @@ class GaussianDiffusion(nn.Module):
             rows[i, 4] = an.sqrt()
             rows[i, 5] = (1 - an - sigma ** 2).sqrt()
             rows[i, 6] = sigma
+        cache.clear()
+        cache[key] = (pairs, tvals, rows)
         return pairs, tvals, rows
 
     # ------------------------------------------------------------------ model predictions (API method)

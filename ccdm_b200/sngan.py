@@ -127,11 +127,31 @@ class sngan_generator(nn.Module):                   # noqa: N801  (the reference
                           resid, flags=flags | (L.EPI_OUT_F32 if out_f32 else 0), ss=ss)
         return out
 
-    def _coef(self, bn: nn.BatchNorm2d, y: Optional[torch.Tensor], cbn: Optional[ConditionalBatchNorm2d], b: int):
-        """[B, 2C] scale | shift of (Conditional)BatchNorm2d in eval mode."""
+    def _batch_stats(self, bn: nn.BatchNorm2d, x: torch.Tensor):
+        """Training-mode BatchNorm2d statistics of a bf16 NHWC tensor (sngan.py:23,30: ``self.bn(x)`` with the module in
+        train mode): per-(sample, channel) sums by ``ccdm_channel_stats``, folded over the batch; biased variance for the
+        normalisation, running statistics updated with momentum and the unbiased variance exactly like nn.BatchNorm2d."""
+        b, h, w, c = x.shape
+        sums = torch.empty(b, 2, c, dtype=torch.float32, device=x.device)
+        L.check(L.lib().ccdm_channel_stats(x.data_ptr(), b, h * w, c, sums.data_ptr(), c, 0, 1, _stream()), "channel_stats")
+        n = b * h * w
+        tot = sums.sum(0)
+        mean = tot[0] / n
+        var = (tot[1] / n - mean * mean).clamp_min_(0.0)
+        if bn.track_running_stats and bn.running_mean is not None:
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var * (n / max(n - 1, 1)), alpha=m)
+            bn.num_batches_tracked += 1
+        return mean.contiguous(), var.contiguous()
+
+    def _coef(self, bn: nn.BatchNorm2d, y: Optional[torch.Tensor], cbn: Optional[ConditionalBatchNorm2d], b: int,
+              stats=None):
+        """[B, 2C] scale | shift of (Conditional)BatchNorm2d: running statistics (eval) or the given batch ``stats``."""
         lib, st = L.lib(), _stream()
         c = bn.num_features
         dev = bn.running_mean.device
+        mean, var = (bn.running_mean, bn.running_var) if stats is None else stats
         gamma = beta = None
         if cbn is not None:
             gamma = torch.empty(b, c, dtype=torch.float32, device=dev)
@@ -141,8 +161,8 @@ class sngan_generator(nn.Module):                   # noqa: N801  (the reference
                                               None, 0, L.ACT_NONE, dst.data_ptr(), c, st), "linear_small")
         ss = torch.empty(b, 2 * c, dtype=torch.float32, device=dev)
         L.check(lib.ccdm_condbn_coef(L.ptr(gamma), L.ptr(beta), L.ptr(bn.weight) if bn.affine else None,
-                                     L.ptr(bn.bias) if bn.affine else None, bn.running_mean.data_ptr(),
-                                     bn.running_var.data_ptr(), float(bn.eps), b, c, ss.data_ptr(), st), "condbn_coef")
+                                     L.ptr(bn.bias) if bn.affine else None, mean.data_ptr(),
+                                     var.data_ptr(), float(bn.eps), b, c, ss.data_ptr(), st), "condbn_coef")
         return ss
 
     @staticmethod
@@ -156,10 +176,11 @@ class sngan_generator(nn.Module):                   # noqa: N801  (the reference
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def forward(self, z, y):
-        """sngan.py:130-139; ``y`` is the embedded label ``fn_y2h(labels)`` [B, dim_embed].  Returns NCHW fp32 in (-1, 1)."""
-        if self.training:
-            raise NotImplementedError("ccdm_b200.sngan_generator: only the eval-mode forward (running BatchNorm statistics) "
-                                      "runs on the CUDA path; training the generator is outside this round's scope")
+        """sngan.py:130-139; ``y`` is the embedded label ``fn_y2h(labels)`` [B, dim_embed].  Returns NCHW fp32 in (-1, 1).
+        Eval mode: running BatchNorm statistics, the second CondBN + ReLU of every block fused into conv1's epilogue.
+        Train mode (forward only -- the generator's backward belongs to the out-of-scope DMD2 trainer): batch statistics,
+        running statistics updated in place as nn.BatchNorm2d does; conv1's output is then normalised by a separate pass."""
+        train = self.training
         _require_cuda(z)
         if y is None:
             raise NotImplementedError("the unconditional branch (sngan.py:84-85) is never taken by dmd.py")
@@ -177,14 +198,19 @@ class sngan_generator(nn.Module):                   # noqa: N801  (the reference
         x = self._conv("1x1", zb.view(1, 1, b, -1), self._cache["dense_w"], self._cache["dense_b"])
         x = x.view(b, s, s, c0)
         for blk in self._blocks():
-            ss1 = self._coef(blk.condbn1.bn, y, blk.condbn1, b)
-            ss2 = self._coef(blk.condbn2.bn, y, blk.condbn2, b)
+            ss1 = self._coef(blk.condbn1.bn, y, blk.condbn1, b, self._batch_stats(blk.condbn1.bn, x) if train else None)
             h0 = self._affine_relu(x, ss1)
-            h1 = self._conv("up2x3x3", h0, blk.conv1.weight, blk.conv1.bias, flags=L.EPI_RELU, ss=ss2)
+            if train:                                             # batch statistics of conv1's output: cannot live in its epilogue
+                h1raw = self._conv("up2x3x3", h0, blk.conv1.weight, blk.conv1.bias)
+                ss2 = self._coef(blk.condbn2.bn, y, blk.condbn2, b, self._batch_stats(blk.condbn2.bn, h1raw))
+                h1 = self._affine_relu(h1raw, ss2)
+            else:
+                ss2 = self._coef(blk.condbn2.bn, y, blk.condbn2, b)
+                h1 = self._conv("up2x3x3", h0, blk.conv1.weight, blk.conv1.bias, flags=L.EPI_RELU, ss=ss2)
             by = self._conv("up2x1x1", x, blk.bypass_conv.weight, blk.bypass_conv.bias)
             x = self._conv("3x3", h1, blk.conv2.weight, blk.conv2.bias, resid=by)
         bn, conv = self.final[0], self.final[2]
-        h = self._affine_relu(x, self._coef(bn, None, None, b))
+        h = self._affine_relu(x, self._coef(bn, None, None, b, self._batch_stats(bn, x) if train else None))
         # output conv: nc (3) rows padded to 8 (the GEMM's channel granularity); fp32 NHWC, tanh in the epilogue
         key = (conv.weight.data_ptr(), conv.weight._version, conv.bias._version)
         if self._cache.get("final_key") != key:

@@ -116,34 +116,41 @@ def make_state_dict(spec: GenSpec, seed: int = 0) -> Dict[str, Tensor]:
     return out
 
 
-def _bn_eval(sd, name, x, affine):
-    """nn.BatchNorm2d in eval mode (running statistics), sngan.py:23,54,58,122."""
+def _bn_eval(sd, name, x, affine, stats=None):
+    """nn.BatchNorm2d, sngan.py:23,54,58,122: eval mode (running statistics) or, with ``stats`` (a dict that receives the
+    updated running statistics), training mode: batch statistics, momentum 0.1, unbiased variance in the running update."""
     w = sd[f"{name}.weight"] if affine else None
     b = sd[f"{name}.bias"] if affine else None
-    return F.batch_norm(x, sd[f"{name}.running_mean"], sd[f"{name}.running_var"], w, b, False, 0.0, 1e-5)
+    if stats is None:
+        return F.batch_norm(x, sd[f"{name}.running_mean"], sd[f"{name}.running_var"], w, b, False, 0.0, 1e-5)
+    rm, rv = sd[f"{name}.running_mean"].clone(), sd[f"{name}.running_var"].clone()
+    out = F.batch_norm(x, rm, rv, w, b, True, 0.1, 1e-5)
+    stats[f"{name}.running_mean"], stats[f"{name}.running_var"] = rm, rv
+    return out
 
 
-def _condbn(sd, name, x, y):
+def _condbn(sd, name, x, y, stats=None):
     """ConditionalBatchNorm2d.forward, sngan.py:28-36."""
-    out = _bn_eval(sd, f"{name}.bn", x, False)
+    out = _bn_eval(sd, f"{name}.bn", x, False, stats)
     gamma = F.linear(y, sd[f"{name}.embed_gamma.weight"])[:, :, None, None]
     beta = F.linear(y, sd[f"{name}.embed_beta.weight"])[:, :, None, None]
     return out + out * gamma + beta
 
 
-def generator_forward(sd: Dict[str, Tensor], spec: GenSpec, z: Tensor, y: Tensor) -> Tensor:
-    """sngan_generator.forward, sngan.py:130-139, eval mode, conditional branch (sngan.py:73-83)."""
+def generator_forward(sd: Dict[str, Tensor], spec: GenSpec, z: Tensor, y: Tensor, stats=None) -> Tensor:
+    """sngan_generator.forward, sngan.py:130-139, conditional branch (sngan.py:73-83); eval mode, or training mode when a
+    ``stats`` dict is passed (it receives the updated running statistics)."""
     c0 = spec.gene_ch * spec.ch_multi[0]
     out = F.linear(z.view(z.size(0), -1), sd["dense.weight"], sd["dense.bias"]).view(-1, c0, spec.init_size, spec.init_size)
     for i in range(len(spec.block_channels)):
         n = f"genblock{i}"
-        h = F.relu(_condbn(sd, f"{n}.condbn1", out, y))
+        h = F.relu(_condbn(sd, f"{n}.condbn1", out, y, stats))
         h = F.interpolate(h, scale_factor=2, mode="nearest")
         h = F.conv2d(h, sd[f"{n}.conv1.weight"], sd[f"{n}.conv1.bias"], padding=1)
-        h = F.relu(_condbn(sd, f"{n}.condbn2", h, y))
+        h = F.relu(_condbn(sd, f"{n}.condbn2", h, y, stats))
         h = F.conv2d(h, sd[f"{n}.conv2.weight"], sd[f"{n}.conv2.bias"], padding=1)
         by = F.conv2d(F.interpolate(out, scale_factor=2, mode="nearest"), sd[f"{n}.bypass_conv.weight"],
                       sd[f"{n}.bypass_conv.bias"])
         out = h + by
-    out = F.relu(_bn_eval(sd, "final.0", out, True))
+    out = F.relu(_bn_eval(sd, "final.0", out, True, stats))
     return torch.tanh(F.conv2d(out, sd["final.2.weight"], sd["final.2.bias"], padding=1))

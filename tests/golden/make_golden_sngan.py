@@ -35,6 +35,15 @@ def main():
         with torch.no_grad():
             out[name] = {"out": net(z, y).clone(), "keys": list(net.state_dict().keys())}
         print(name, tuple(out[name]["out"].shape), float(out[name]["out"].abs().mean()))
+        if name == "g64":
+            # training mode (batch-statistics BatchNorm2d, sngan.py:19-36): output and the updated running statistics
+            z, y = gen_inputs(s, 6, seed=51)
+            net.train()
+            with torch.no_grad():
+                o = net(z, y).clone()
+            out["g64_train"] = {"out": o, "stats": {k: v.clone() for k, v in net.state_dict().items()
+                                                     if "running_" in k or "num_batches" in k}}
+            print("g64_train", tuple(o.shape), float(o.abs().mean()))
     torch.save(out, os.path.join(HERE, "sngan.pt"))
 
 

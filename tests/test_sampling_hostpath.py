@@ -175,6 +175,30 @@ def test_generator_forward_matches_the_reference(monkeypatch, name):
     assert err < 2e-2
 
 
+def test_generator_train_mode_matches_the_reference(monkeypatch):
+    """Training-mode forward of the product generator on CPU (ccdm_channel_stats / ccdm_condbn_coef / ccdm_affine_act from their
+    own sources): batch-statistics BatchNorm2d output and updated running statistics vs the reference module's own."""
+    from oracle.sngan_ref import make_state_dict as g_sd
+    from tests.golden.sngan_cases import GEN_CASES, GEN_SPECS, gen_inputs
+    hostpath.install_engine(monkeypatch)
+    s = GEN_SPECS["g64"]
+    net = ccdm_b200.sngan_generator(dim_z=s.dim_z, dim_embed=s.dim_embed, nc=s.nc, img_size=s.img_size, gene_ch=s.gene_ch)
+    net.load_state_dict(g_sd(s, GEN_CASES["g64"][1]), strict=True)
+    net.train()
+    z, y = gen_inputs(s, 6, seed=51)
+    out = net(z, y)
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "sngan.pt"))["g64_train"]
+    err = rel(out, gold["out"])
+    print(f"g64 train mode: rel L2 err vs the reference's output {err:.3e}")
+    assert err < 2e-2
+    got = net.state_dict()
+    for k, v in gold["stats"].items():
+        if "num_batches" in k:
+            assert int(got[k]) == int(v)
+        else:
+            assert rel(got[k], v) < 2e-2, k
+
+
 # ------------------------------------------------------------------------------------------------- wider shapes, API methods
 
 @pytest.mark.parametrize("spec_name", ["uk64", "wide"])

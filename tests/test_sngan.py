@@ -49,8 +49,46 @@ def test_cpu_call_fails_loudly():
     net = make_gen(GEN_SPECS["g64"]).eval()
     with pytest.raises(RuntimeError):
         net(torch.randn(2, 32), torch.rand(2, 16))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         net.train()(torch.randn(2, 32), torch.rand(2, 16))
+
+
+def test_oracle_train_mode_vs_reference_golden():
+    """Training-mode forward (batch-statistics BatchNorm2d, sngan.py:19-36): the oracle restatement reproduces the reference
+    module's output and its updated running statistics (tests/golden/sngan.pt, case g64_train)."""
+    spec = GEN_SPECS["g64"]
+    sd = make_state_dict(spec, GEN_CASES["g64"][1])
+    z, y = gen_inputs(spec, 6, seed=51)
+    gold = torch.load(os.path.join(G, "sngan.pt"), weights_only=True)["g64_train"]
+    stats = {}
+    with torch.no_grad():
+        out = generator_forward(sd, spec, z, y, stats=stats)
+    assert ((out - gold["out"]).norm() / gold["out"].norm()).item() < 1e-5
+    for k, v in stats.items():
+        assert ((v - gold["stats"][k]).norm() / gold["stats"][k].norm().clamp_min(1e-12)).item() < 1e-5, k
+
+
+@pytest.mark.gpu
+def test_generator_train_mode_vs_reference_golden():
+    """The CUDA path in training mode: ccdm_channel_stats batch statistics -> ccdm_condbn_coef -> affine + ReLU, running
+    statistics updated like nn.BatchNorm2d; against the reference module's own train-mode output."""
+    spec = GEN_SPECS["g64"]
+    sd = make_state_dict(spec, GEN_CASES["g64"][1])
+    net = make_gen(spec)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    z, y = gen_inputs(spec, 6, seed=51)
+    out = net(z.cuda(), y.cuda()).cpu()
+    gold = torch.load(os.path.join(G, "sngan.pt"), weights_only=True)["g64_train"]
+    e = ((out - gold["out"]).norm() / gold["out"].norm()).item()
+    print(f"g64 train mode: rel err vs reference {e:.3e}")
+    assert e < 2e-2
+    got = net.state_dict()
+    for k, v in gold["stats"].items():
+        if "num_batches" in k:
+            assert int(got[k]) == int(v), k
+        else:
+            assert ((got[k].cpu() - v).norm() / v.norm().clamp_min(1e-12)).item() < 2e-2, k
 
 
 @pytest.mark.gpu
