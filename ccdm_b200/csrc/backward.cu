@@ -9,14 +9,25 @@ namespace ccdm {
 constexpr int kBwdThreads = 256;
 constexpr int kBwdMaxC = 1024;
 
-template <int kChunks>   // G lanes share one row; each owns kChunks chunks of 8 channels (see row_lane_plan)
-__global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
-                                                                uint4* __restrict__ dz, int rows_per_sample,
-                                                                int rows_per_block, int C, const float* __restrict__ gain,
-                                                                float gain_mul, const float* __restrict__ ss, int ss_ld,
-                                                                int ss_off, float* __restrict__ sums, int B,
-                                                                uint32_t flags, int G) {
+// Per-thread asynchronous staging ring (LDGSTS): every thread copies the 16-byte vectors it will consume itself kStages - 1
+// row groups ahead into its OWN shared-memory slots, so the bytes in flight per SM no longer depend on registers or on the
+// number of resident warps (the first version kept one row group ahead in registers and ran at 14-30 % of the HBM peak with
+// 8-16 warps per SM).  No block barrier is needed in the row loop: a slot is written and read by the same thread.
+constexpr int bwd_stages(int chunks) { return chunks == 1 ? 6 : chunks == 2 ? 4 : 3; }
+
+// G lanes share one row; each owns kChunks chunks of 8 channels (see row_lane_plan); kMinCtas resident CTAs per SM
+template <int kChunks, int kMinCtas>
+__global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
+                                                                          uint4* __restrict__ dz, int rows_per_sample,
+                                                                          int rows_per_block, int C, const float* __restrict__ gain,
+                                                                          float gain_mul, const float* __restrict__ ss, int ss_ld,
+                                                                          int ss_off, float* __restrict__ sums, int B,
+                                                                          uint32_t flags, int G) {
+  constexpr int kStages = bwd_stages(kChunks);
   __shared__ float acc_s[3][kBwdMaxC];
+  __shared__ float coef_s[2][kBwdMaxC];                            // a = gain * (1 + scale), shift
+  extern __shared__ float bwd_ring_f[];                            // [stage][chunk][z | dy][thread] 16-byte slots
+  uint4* const ring = reinterpret_cast<uint4*>(bwd_ring_f);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunk = C >> 3;                                       // 8 channels (16 bytes) per chunk
   const int kRowsPerWarp = 32 / G;
@@ -25,63 +36,54 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(r0 + rows_per_block, rows_per_sample);
   for (int i = tid; i < 3 * C; i += kBwdThreads) (&acc_s[0][0])[(i / C) * kBwdMaxC + (i % C)] = 0.f;
+  for (int c = tid; c < C; c += kBwdThreads) {
+    float sc = 0.f, sf = 0.f;
+    if (flags & CCDM_EPI_SS) {
+      sc = ss[(size_t)b * ss_ld + ss_off + c];
+      sf = ss[(size_t)b * ss_ld + ss_off + C + c];
+    }
+    coef_s[0][c] = gain[c] * gain_mul * (1.f + sc);
+    coef_s[1][c] = sf;
+  }
   __syncthreads();
 
-  float a[kChunks][8], sh[kChunks][8];
   float s1[kChunks][8], s2[kChunks][8], s3[kChunks][8];
 #pragma unroll
-  for (int k = 0; k < kChunks; ++k) {
-    const int ch = gl + G * k;
-    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (ch < nchunk) {
-      load8(gain + ch * 8, g);
-      if (flags & CCDM_EPI_SS) {
-        load8(ss + (size_t)b * ss_ld + ss_off + ch * 8, sc);
-        load8(ss + (size_t)b * ss_ld + ss_off + C + ch * 8, sf);
-      }
-    }
+  for (int k = 0; k < kChunks; ++k)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a[k][j] = g[j] * gain_mul * (1.f + sc[j]);
-      sh[k][j] = sf[j];
-      s1[k][j] = s2[k][j] = s3[k][j] = 0.f;
-    }
-  }
-  // software pipeline: the loads of the next row group are issued before the current one is processed
+    for (int j = 0; j < 8; ++j) s1[k][j] = s2[k][j] = s3[k][j] = 0.f;
+
   const int rstep = (kBwdThreads / 32) * kRowsPerWarp;
-  uint4 zn[kChunks], dn[kChunks];                                 // next row group, loaded one iteration ahead
-  auto fetch = [&](int rb) {
+  const int rb0 = r0 + warp * kRowsPerWarp;
+  auto slot = [&](int st, int k, int which) { return ring + ((st * kChunks + k) * 2 + which) * kBwdThreads + tid; };
+  auto fetch = [&](int rb, int st) {                               // one commit group per row group, also when it is empty
     const int r = rb + sub;
     const bool ok = sub < kRowsPerWarp && r < r1;
-    const size_t off = ((size_t)b * rows_per_sample + r) * nchunk;
+    const size_t off = ((size_t)b * rows_per_sample + (ok ? r : r0)) * nchunk;
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
       const int ch = gl + G * k;
-      zn[k] = dn[k] = make_uint4(0, 0, 0, 0);
-      if (ok && ch < nchunk) {
-        zn[k] = __ldg(z + off + ch);
-        dn[k] = __ldg(dy + off + ch);
-      }
+      const bool v = ok && ch < nchunk;
+      cp_async16(slot(st, k, 0), z + off + (v ? ch : 0), v);
+      cp_async16(slot(st, k, 1), dy + off + (v ? ch : 0), v);
     }
+    cp_async_commit();
   };
-  fetch(r0 + warp * kRowsPerWarp);
-  for (int rb = r0 + warp * kRowsPerWarp; rb < r1; rb += rstep) {
+#pragma unroll
+  for (int st = 0; st < kStages - 1; ++st) fetch(rb0 + st * rstep, st);
+  int st_rd = 0, st_wr = kStages - 1;
+  for (int rb = rb0; rb < r1; rb += rstep) {
     const int r = rb + sub;
     const bool live = sub < kRowsPerWarp && r < r1;
     const size_t rowoff = ((size_t)b * rows_per_sample + r) * nchunk;
-    uint4 zc[kChunks], dc[kChunks];
-#pragma unroll
-    for (int k = 0; k < kChunks; ++k) {
-      zc[k] = zn[k];
-      dc[k] = dn[k];
-    }
-    if (rb + rstep < r1) fetch(rb + rstep);
-    // packed fp32x2 arithmetic throughout (FFMA2 / FMUL2 / FADD2): the kernel is issue-bound, not DRAM-bound
+    fetch(rb + (kStages - 1) * rstep, st_wr);                      // rows past r1 become zero-filled slots
+    cp_async_wait<kStages - 1>();
+    // packed fp32x2 arithmetic throughout (FFMA2 / FMUL2 / FADD2)
     float2 zf[kChunks][4], gy[kChunks][4];
     float2 sq2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
-      const uint4 zu = zc[k], du = dc[k];
+      const uint4 zu = *slot(st_rd, k, 0), du = *slot(st_rd, k, 1);
       zf[k][0] = make_float2(bf16_lo(zu.x), bf16_hi(zu.x));
       zf[k][1] = make_float2(bf16_lo(zu.y), bf16_hi(zu.y));
       zf[k][2] = make_float2(bf16_lo(zu.z), bf16_hi(zu.z));
@@ -93,6 +95,8 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
 #pragma unroll
       for (int j = 0; j < 4; ++j) sq2 = __ffma2_rn(zf[k][j], zf[k][j], sq2);
     }
+    if (++st_rd == kStages) st_rd = 0;
+    if (++st_wr == kStages) st_wr = 0;
     const float sq = seg_sum(sq2.x + sq2.y, gl, G, lane);
     const float inv = rsqrtf(fmaxf(sq, 1e-24f));                   // 1 / max(|z|, 1e-12)
     const float2 inv2 = make_float2(inv, inv);
@@ -100,14 +104,23 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
     float2 dot2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
+      const int c0 = min(gl + G * k, nchunk - 1) * 8;              // lanes past the row read a valid coefficient slot
+      const float4 a_lo = *reinterpret_cast<const float4*>(&coef_s[0][c0]);
+      const float4 a_hi = *reinterpret_cast<const float4*>(&coef_s[0][c0 + 4]);
+      const float4 h_lo = *reinterpret_cast<const float4*>(&coef_s[1][c0]);
+      const float4 h_hi = *reinterpret_cast<const float4*>(&coef_s[1][c0 + 4]);
+      const float2 av[4] = {make_float2(a_lo.x, a_lo.y), make_float2(a_lo.z, a_lo.w), make_float2(a_hi.x, a_hi.y),
+                            make_float2(a_hi.z, a_hi.w)};
+      const float2 hv[4] = {make_float2(h_lo.x, h_lo.y), make_float2(h_lo.z, h_lo.w), make_float2(h_hi.x, h_hi.y),
+                            make_float2(h_hi.z, h_hi.w)};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 aj = make_float2(a[k][2 * j], a[k][2 * j + 1]);
+        const float2 aj = av[j];
         const float2 zh = __fmul2_rn(zf[k][j], inv2);
         float2 du = gy[k][j];
         if (flags & CCDM_EPI_SILU) {
           // silu'(u) = sig * (1 + u * (1 - sig)),  sig = 0.5 + 0.5 tanh(u / 2)
-          const float2 u = __ffma2_rn(zh, aj, make_float2(sh[k][2 * j], sh[k][2 * j + 1]));
+          const float2 u = __ffma2_rn(zh, aj, hv[j]);
           const float2 hu = __fmul2_rn(u, half2);
           const float2 sig = __ffma2_rn(make_float2(tanh_fast(hu.x), tanh_fast(hu.y)), half2, half2);
           const float2 t = __ffma2_rn(u, make_float2(1.f - sig.x, 1.f - sig.y), one2);
@@ -138,6 +151,7 @@ __global__ void __launch_bounds__(kBwdThreads) block_bwd_kernel(const uint4* __r
                                      pack_bf16(o[3].x, o[3].y));
     }
   }
+  cp_async_wait<0>();
 #pragma unroll
   for (int k = 0; k < kChunks; ++k) {
     const int ch = gl + G * k;
@@ -223,9 +237,19 @@ extern "C" int ccdm_block_bwd(const void* dy, const void* z, void* dz, int64_t r
   per_sample = (rows_per_sample + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)per_sample, (unsigned)B);
 #define CCDM_BWD(K)                                                                                                   \
-  block_bwd_kernel<K><<<grid, kBwdThreads, 0, s>>>((const uint4*)dy, (const uint4*)z, (uint4*)dz, rows_per_sample,    \
-                                                   rows_per_block, C, gain, gain_mul, scale_shift, ss_ld, ss_off, sums, \
-                                                   B, flags, G)
+  do {                                                                                                                \
+    constexpr int ring_bytes = bwd_stages(K) * K * 2 * kBwdThreads * 16;                                              \
+    constexpr int min_ctas = K <= 2 ? 2 : 1;                                                                          \
+    static bool attr_done = false;                                                                                    \
+    if (!attr_done) {                                                                                                 \
+      cudaError_t e = cudaFuncSetAttribute(block_bwd_kernel<K, min_ctas>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes); \
+      if (e != cudaSuccess) return cuda_fail(e, "block_bwd: cudaFuncSetAttribute");                                   \
+      attr_done = true;                                                                                               \
+    }                                                                                                                 \
+    block_bwd_kernel<K, min_ctas><<<grid, kBwdThreads, ring_bytes, s>>>((const uint4*)dy, (const uint4*)z, (uint4*)dz, \
+                                                              rows_per_sample, rows_per_block, C, gain, gain_mul,    \
+                                                              scale_shift, ss_ld, ss_off, sums, B, flags, G);         \
+  } while (0)
   if (kv == 1) CCDM_BWD(1);
   else if (kv == 2) CCDM_BWD(2);
   else if (kv == 3) CCDM_BWD(3);

@@ -1,6 +1,7 @@
 // Guidance + sampler-step kernel and the training-side elementwise kernels (q_sample, vicinal loss).
 // All HBM-bound: one pass (or a few L2-resident passes) over [B][C*H*W] fp32 state.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace ccdm {
 
@@ -49,84 +50,85 @@ __device__ __forceinline__ CfgCoef cfg_coef(double uc, double cc, float cond_sca
   return r;
 }
 
-// One CTA per sample.  kV > 0: the sample's two network outputs live in REGISTERS (kV float4 per thread and tensor, chw <=
-// 512*4*kV) -- global memory is touched once: cond, null, x_t (+ noise) in, x_{t-1} (+ predictions) out, however many
-// reduction passes the guidance needs.  kV == 0: any chw; every pass re-reads global memory (L2 hits after the first).
-template <int kV>
-__global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args a) {
-  __shared__ double scratch[32 * 4];
+// One CTA per sample.  kStage: the sample's two network outputs are copied ONCE into shared memory (LDGSTS, no register
+// round trip, every thread copies the vectors it reads itself so no block barrier is needed) and the state x_t is
+// prefetched into registers while the reduction runs -- global memory is touched once: cond, null, x_t (+ noise) in,
+// x_{t-1} (+ predictions) out.  64x64x3 samples need 96 KB, so two CTAs are resident per SM and a batch of up to 296
+// samples is one wave.  !kStage: any chw; the second pass re-reads global memory (L2 hits).
+// The guidance needs per-sample reductions (unet.py:51-62, 365-371): <cond - null, cond>, |cond|^2 and, for the std rescale,
+// the unbiased std of cond and of the guided output.  All of them follow from ONE pass of second moments
+// (sum c, n, c^2, n^2, cn accumulated in double: every product of two floats is exact there), instead of three dependent
+// block reductions.
+constexpr int kStepThreads = 512;
+constexpr int kStepXPre = 6;                              // float4 of x_t prefetched per thread (64x64x3 / 4 / 512)
+
+template <bool kStage>
+__global__ void __launch_bounds__(kStepThreads, kStage ? 2 : 1) sampler_step_kernel(const ccdm_step_args a) {
+  __shared__ double scratch[32 * 6];
+  extern __shared__ float step_stage_f[];                  // kStage: [cond | null][chw]
   const int b = blockIdx.x;
   const long long base = (long long)b * a.chw;
   const float* cond = a.out_cond + base;
   const float* nul = a.out_null ? a.out_null + base : nullptr;
+  const int nv = a.chw >> 2;                               // (kStage: chw % 4 == 0, checked by the launcher)
+  float* x = a.x ? a.x + base : nullptr;
+  float4* const sc4 = reinterpret_cast<float4*>(step_stage_f);
+  float4* const sn4 = sc4 + nv;
+  float4 xpre[kStepXPre];
+  if constexpr (kStage) {
+    for (int i4 = threadIdx.x; i4 < nv; i4 += kStepThreads) {
+      cp_async16(sc4 + i4, reinterpret_cast<const float4*>(cond) + i4, true);
+      if (nul) cp_async16(sn4 + i4, reinterpret_cast<const float4*>(nul) + i4, true);
+    }
+    cp_async_commit();
+#pragma unroll
+    for (int j = 0; j < kStepXPre; ++j) {
+      const int i4 = threadIdx.x + j * kStepThreads;
+      xpre[j] = (x && i4 < nv) ? *(reinterpret_cast<const float4*>(x) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_wait<0>();
+  }
   const long long step = a.t_rows ? a.t_rows[b] : (a.step_counter ? (long long)*a.step_counter : 0);
   const float* cf = a.x ? a.coef + step * CCDM_STEP_NCOEF : nullptr;
-  const int nv = a.chw >> 2;                               // (kV > 0: chw % 4 == 0, checked by the launcher)
-
-  float4 cr[kV > 0 ? kV : 1], nr[kV > 0 ? kV : 1];
-  if constexpr (kV > 0) {
-#pragma unroll
-    for (int j = 0; j < kV; ++j) {
-      const int i4 = threadIdx.x + j * 512;
-      cr[j] = i4 < nv ? __ldg(reinterpret_cast<const float4*>(cond) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      nr[j] = (nul && i4 < nv) ? __ldg(reinterpret_cast<const float4*>(nul) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-  // f(i, c, n) for every element this thread owns
-  auto each = [&](auto f) {
-    if constexpr (kV > 0) {
-#pragma unroll
-      for (int j = 0; j < kV; ++j) {
-        const int i4 = threadIdx.x + j * 512;
-        if (i4 < nv) {
-          f(4 * i4 + 0, cr[j].x, nr[j].x);
-          f(4 * i4 + 1, cr[j].y, nr[j].y);
-          f(4 * i4 + 2, cr[j].z, nr[j].z);
-          f(4 * i4 + 3, cr[j].w, nr[j].w);
-        }
-      }
-    } else {
-      for (int i = threadIdx.x; i < a.chw; i += blockDim.x) f(i, cond[i], nul ? nul[i] : 0.f);
-    }
-  };
 
   float a_cond = 1.f, a_null = 0.f, resc = 1.f;
   if (nul) {
-    double v[4] = {0, 0, 0, 0};  // <u,c>, <c,c>, sum c, sum c^2
-    each([&](int, float cf_, float nf_) {
+    double v[6] = {0, 0, 0, 0, 0, 0};  // <u,c>, sum c^2, sum c, sum n, sum n^2, sum cn
+    auto acc = [&](float cf_, float nf_) {
       const double c = cf_, n = nf_;
       v[0] += (c - n) * c;
       v[1] += c * c;
       v[2] += c;
-    });
-    block_sum<4>(v, scratch);
+      v[3] += n;
+      v[4] += n * n;
+      v[5] += c * n;
+    };
+    if constexpr (kStage) {
+      for (int i4 = threadIdx.x; i4 < nv; i4 += kStepThreads) {
+        const float4 c = sc4[i4], n = sn4[i4];
+        acc(c.x, n.x);
+        acc(c.y, n.y);
+        acc(c.z, n.z);
+        acc(c.w, n.w);
+      }
+    } else {
+      for (int i = threadIdx.x; i < a.chw; i += blockDim.x) acc(cond[i], nul[i]);
+    }
+    block_sum<6>(v, scratch);
     const CfgCoef k = cfg_coef(v[0], v[1], a.cond_scale, a.remove_parallel, a.keep_parallel_frac);
     a_cond = k.a_cond;
     a_null = k.a_null;
     if (a.rescaled_phi != 0.f) {
-      // unbiased std of cond and of scaled (torch.std default), second pass for centred sums
-      const double mean_c = v[2] / a.chw;
-      double w[4] = {0, 0, 0, 0};  // sum scaled, sum (c-mean_c)^2
-      each([&](int, float cf_, float nf_) {
-        const double c = cf_;
-        const double s = (double)(a_cond * cf_ + a_null * nf_);
-        w[0] += s;
-        w[1] += (c - mean_c) * (c - mean_c);
-      });
-      block_sum<4>(w, scratch);
-      const double mean_s = w[0] / a.chw;
-      double u[4] = {0, 0, 0, 0};
-      each([&](int, float cf_, float nf_) {
-        const double s = (double)(a_cond * cf_ + a_null * nf_) - mean_s;
-        u[0] += s * s;
-      });
-      block_sum<4>(u, scratch);
-      const double std_c = sqrt(w[1] / (a.chw - 1)), std_s = sqrt(u[0] / (a.chw - 1));
-      resc = (float)(std_c / std_s) * a.rescaled_phi + (1.f - a.rescaled_phi);
+      // unbiased std of cond and of scaled = a_cond * cond + a_null * null (torch.std default) from the moments
+      const double N = (double)a.chw, ac = (double)a_cond, an = (double)a_null;
+      const double var_c = fmax(v[1] - v[2] * v[2] / N, 0.0) / (N - 1.0);
+      const double sum_s = ac * v[2] + an * v[3];
+      const double sq_s = ac * ac * v[1] + 2.0 * ac * an * v[5] + an * an * v[4];
+      const double var_s = fmax(sq_s - sum_s * sum_s / N, 0.0) / (N - 1.0);
+      resc = (float)(sqrt(var_c) / sqrt(var_s)) * a.rescaled_phi + (1.f - a.rescaled_phi);
     }
   }
 
-  float* x = a.x ? a.x + base : nullptr;
   const float c_recip = x ? cf[0] : 0.f, c_recipm1 = x ? cf[1] : 1.f, c_sa = x ? cf[2] : 0.f, c_s1m = x ? cf[3] : 0.f;
   // one element of the update: returns x_{t-1} (or the guided output when there is no state); may write the predictions
   auto elem = [&](int i, float c, float n, float xt, float nz) -> float {
@@ -173,22 +175,25 @@ __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args 
   const bool need_noise = x && a.sampler != 2 && ((a.sampler == 0 && cf[7] == 0.f && cf[6] != 0.f) ||
                                                   (a.sampler == 1 && cf[10] != 0.f));
   const float* nzp = need_noise ? a.noise + base : nullptr;
-  if constexpr (kV > 0) {
+  if constexpr (kStage) {
     float* dst = x ? x : a.pred_x0 + base;               // guidance only: the guided output goes to pred_x0
+    auto one = [&](int i4, float4 xt) {
+      const float4 c = sc4[i4], n = nul ? sn4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 nz = nzp ? __ldg(reinterpret_cast<const float4*>(nzp) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 o;
+      o.x = elem(4 * i4 + 0, c.x, n.x, xt.x, nz.x);
+      o.y = elem(4 * i4 + 1, c.y, n.y, xt.y, nz.y);
+      o.z = elem(4 * i4 + 2, c.z, n.z, xt.z, nz.z);
+      o.w = elem(4 * i4 + 3, c.w, n.w, xt.w, nz.w);
+      if (!x || a.sampler != 2) *(reinterpret_cast<float4*>(dst) + i4) = o;
+    };
 #pragma unroll
-    for (int j = 0; j < kV; ++j) {
-      const int i4 = threadIdx.x + j * 512;
-      if (i4 < nv) {
-        const float4 xt = x ? *(reinterpret_cast<const float4*>(x) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 nz = nzp ? __ldg(reinterpret_cast<const float4*>(nzp) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 o;
-        o.x = elem(4 * i4 + 0, cr[j].x, nr[j].x, xt.x, nz.x);
-        o.y = elem(4 * i4 + 1, cr[j].y, nr[j].y, xt.y, nz.y);
-        o.z = elem(4 * i4 + 2, cr[j].z, nr[j].z, xt.z, nz.z);
-        o.w = elem(4 * i4 + 3, cr[j].w, nr[j].w, xt.w, nz.w);
-        if (!x || a.sampler != 2) *(reinterpret_cast<float4*>(dst) + i4) = o;
-      }
+    for (int j = 0; j < kStepXPre; ++j) {
+      const int i4 = threadIdx.x + j * kStepThreads;
+      if (i4 < nv) one(i4, xpre[j]);
     }
+    for (int i4 = threadIdx.x + kStepXPre * kStepThreads; i4 < nv; i4 += kStepThreads)
+      one(i4, x ? *(reinterpret_cast<const float4*>(x) + i4) : make_float4(0.f, 0.f, 0.f, 0.f));
   } else {
     for (int i = threadIdx.x; i < a.chw; i += blockDim.x) {
       const float r = elem(i, cond[i], nul ? nul[i] : 0.f, x ? x[i] : 0.f, nzp ? nzp[i] : 0.f);
@@ -198,20 +203,27 @@ __global__ void __launch_bounds__(512) sampler_step_kernel(const ccdm_step_args 
   }
 }
 
-// Register-resident variants for chw up to 512 threads * 4 * kV elements (64x64x3 = 12288 -> kV = 6); needs 16-byte
-// aligned rows.  Larger samples (128x128 and up) take the streaming variant.
-static void launch_sampler_step(const ccdm_step_args& k, cudaStream_t s) {
+// Staged variant for samples whose two network outputs fit the shared memory of one CTA (chw * 8 bytes <= 200 KB, i.e.
+// up to 80x80x4); needs 16-byte aligned rows.  Larger samples (128x128 and up) take the streaming variant.
+static int launch_sampler_step(const ccdm_step_args& k, cudaStream_t s) {
   const bool vec = (k.chw % 4 == 0) && ((reinterpret_cast<uintptr_t>(k.out_cond) & 15) == 0) &&
                    (!k.out_null || (reinterpret_cast<uintptr_t>(k.out_null) & 15) == 0) &&
                    (!k.x || (reinterpret_cast<uintptr_t>(k.x) & 15) == 0) &&
                    (!k.noise || (reinterpret_cast<uintptr_t>(k.noise) & 15) == 0) &&
                    (k.x || (reinterpret_cast<uintptr_t>(k.pred_x0) & 15) == 0);
-  const int per_thread = (k.chw / 4 + 511) / 512;
-  if (vec && per_thread <= 2) sampler_step_kernel<2><<<k.B, 512, 0, s>>>(k);
-  else if (vec && per_thread <= 4) sampler_step_kernel<4><<<k.B, 512, 0, s>>>(k);
-  else if (vec && per_thread <= 6) sampler_step_kernel<6><<<k.B, 512, 0, s>>>(k);
-  else if (vec && per_thread <= 8) sampler_step_kernel<8><<<k.B, 512, 0, s>>>(k);
-  else sampler_step_kernel<0><<<k.B, 512, 0, s>>>(k);
+  const size_t stage_bytes = (size_t)k.chw * 8;
+  if (vec && stage_bytes <= 200 * 1024) {
+    static size_t attr_bytes = 0;
+    if (stage_bytes > attr_bytes) {
+      cudaError_t e = cudaFuncSetAttribute(sampler_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return cuda_fail(e, "sampler_step: cudaFuncSetAttribute");
+      attr_bytes = 200 * 1024;
+    }
+    sampler_step_kernel<true><<<k.B, kStepThreads, stage_bytes, s>>>(k);
+  } else {
+    sampler_step_kernel<false><<<k.B, kStepThreads, 0, s>>>(k);
+  }
+  return CCDM_OK;
 }
 
 // The step counter is bumped by its own 1-thread launch after the step kernel, so every CTA of the step kernel
@@ -343,7 +355,8 @@ extern "C" int ccdm_sampler_step(const ccdm_step_args* a, void* stream) {
   CCDM_REQUIRE(a->x, CCDM_ERR_BAD_ARG, "sampler_step: null state");
   ccdm_step_args k = *a;
   if (k.cond_scale == 1.f) k.out_null = nullptr;
-  launch_sampler_step(k, (cudaStream_t)stream);
+  rc = launch_sampler_step(k, (cudaStream_t)stream);
+  if (rc != CCDM_OK) return rc;
   rc = after_launch("sampler_step_kernel");
   if (rc != CCDM_OK) return rc;
   if (a->advance && a->step_counter) {
@@ -377,7 +390,8 @@ extern "C" int ccdm_cfg_combine(const float* cond, const float* null_out, float*
   k.keep_parallel_frac = keep_parallel_frac;
   k.remove_parallel = remove_parallel;
   k.coef = nullptr;  // x == nullptr: guidance only, no sampler coefficients are read
-  launch_sampler_step(k, (cudaStream_t)stream);
+  const int rc = launch_sampler_step(k, (cudaStream_t)stream);
+  if (rc != CCDM_OK) return rc;
   return after_launch("sampler_step_kernel(cfg)");
 }
 

@@ -25,7 +25,7 @@ def _launch_sub(src: str):
     (LAUNCH_SEQ), which is much faster than a fiber each."""
     def repl(m):
         base = m.group(1).split("<")[0]
-        body = _definition(src, r"__global__ void (?:__launch_bounds__\([\w, ]+\) )?" + base + r"\(")
+        body = _definition(src, r"__global__ void (?:__launch_bounds__\([^)]+\) )?" + base + r"\(")
         macro = "LAUNCH" if SYNC_RE.search(body) else "LAUNCH_SEQ"
         return f"{macro}(({m.group(1)}), ({m.group(2)}), ({m.group(3)}), {m.group(6)});"
     return LAUNCH_RE.subn(repl, src)
@@ -61,7 +61,7 @@ def extract_source(cu_path: str, kernels, entries) -> str:
     """A .cu file that also holds tcgen05 / TMA code cannot be compiled for the host as a whole: take only the named
     CUDA-core kernels and C entry points (verbatim) out of it."""
     src = open(cu_path).read()
-    body = "namespace ccdm {\n" + "".join(_definition(src, r"__global__ void (?:__launch_bounds__\(\w+\) )?" + k + r"\(")
+    body = "namespace ccdm {\n" + "".join(_definition(src, r"__global__ void (?:__launch_bounds__\([^)]+\) )?" + k + r"\(")
                                           for k in kernels) + "}\nusing namespace ccdm;\n"
     body += "".join(_definition(src, r'extern "C" int ' + e + r"\(") for e in entries)
     body = DYN_SMEM_RE.sub(r"float* \1 = g_dyn_smem;", body)       # dynamic shared memory: one 256 KB host buffer

@@ -178,6 +178,9 @@ static inline float seg_sum(float v, int gl, int G, int lane) {
   }
   return __shfl_sync(0xffffffffu, v, lane - gl);
 }
+static inline void cp_async16(void* dst, const void* src, bool valid) { if (valid) memcpy(dst, src, 16); else memset(dst, 0, 16); }
+static inline void cp_async_commit() {}
+template <int kPending> static inline void cp_async_wait() {}
 static inline void griddep_wait() {}
 static inline void griddep_launch_dependents() {}
 }  // namespace ccdm

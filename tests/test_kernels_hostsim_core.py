@@ -330,7 +330,8 @@ def test_time_features_select_null_silu_concat(kern):
 # ------------------------------------------------------------------------------------------------- backward.cu / train_kernels.cu
 
 @pytest.mark.parametrize("C_,use_ss,silu,rows", [(64, True, True, 40), (72, False, True, 33), (128, True, False, 12),
-                                                 (576, True, True, 6)])
+                                                 (576, True, True, 6), (64, True, True, 300), (144, True, True, 100),
+                                                 (288, True, True, 70), (576, False, True, 30)])
 def test_block_backward_matches_autograd(bwd, C_, use_ss, silu, rows):
     g = torch.Generator().manual_seed(11)
     B = 3
