@@ -16,7 +16,25 @@ constexpr int kBwdMaxC = 1024;
 constexpr int bwd_stages(int chunks) { return chunks == 1 ? 6 : chunks == 2 ? 4 : 3; }
 
 // G lanes share one row; each owns kChunks chunks of 8 channels (see row_lane_plan); kMinCtas resident CTAs per SM
-template <int kChunks, int kMinCtas>
+// Sum over the G lanes of a row segment, broadcast to all of them; branch-free (the generic seg_sum loops over a run-time G).
+__device__ __forceinline__ float bwd_seg_sum(float v, int gl, int G, int lane) {
+  if ((G & (G - 1)) == 0) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float o = __shfl_xor_sync(0xffffffffu, v, off);
+      v += off < G ? o : 0.f;
+    }
+    return v;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float o = __shfl_down_sync(0xffffffffu, v, off);
+    v += gl + off < G ? o : 0.f;
+  }
+  return __shfl_sync(0xffffffffu, v, lane - gl);
+}
+
+template <int kChunks, int kMinCtas, bool kSilu>
 __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
                                                                           uint4* __restrict__ dz, int rows_per_sample,
                                                                           int rows_per_block, int C, const float* __restrict__ gain,
@@ -24,7 +42,6 @@ __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const 
                                                                           int ss_off, float* __restrict__ sums, int B,
                                                                           uint32_t flags, int G) {
   constexpr int kStages = bwd_stages(kChunks);
-  __shared__ float acc_s[3][kBwdMaxC];
   __shared__ float coef_s[2][kBwdMaxC];                            // a = gain * (1 + scale), shift
   extern __shared__ float bwd_ring_f[];                            // [stage][chunk][z | dy][thread] 16-byte slots
   uint4* const ring = reinterpret_cast<uint4*>(bwd_ring_f);
@@ -35,7 +52,6 @@ __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const 
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(r0 + rows_per_block, rows_per_sample);
-  for (int i = tid; i < 3 * C; i += kBwdThreads) (&acc_s[0][0])[(i / C) * kBwdMaxC + (i % C)] = 0.f;
   for (int c = tid; c < C; c += kBwdThreads) {
     float sc = 0.f, sf = 0.f;
     if (flags & CCDM_EPI_SS) {
@@ -97,7 +113,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const 
     }
     if (++st_rd == kStages) st_rd = 0;
     if (++st_wr == kStages) st_wr = 0;
-    const float sq = seg_sum(sq2.x + sq2.y, gl, G, lane);
+    const float sq = bwd_seg_sum(sq2.x + sq2.y, gl, G, lane);
     const float inv = rsqrtf(fmaxf(sq, 1e-24f));                   // 1 / max(|z|, 1e-12)
     const float2 inv2 = make_float2(inv, inv);
     const float2 one2 = make_float2(1.f, 1.f), half2 = make_float2(0.5f, 0.5f);
@@ -118,7 +134,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const 
         const float2 aj = av[j];
         const float2 zh = __fmul2_rn(zf[k][j], inv2);
         float2 du = gy[k][j];
-        if (flags & CCDM_EPI_SILU) {
+        if constexpr (kSilu) {
           // silu'(u) = sig * (1 + u * (1 - sig)),  sig = 0.5 + 0.5 tanh(u / 2)
           const float2 u = __ffma2_rn(zh, aj, hv[j]);
           const float2 hu = __fmul2_rn(u, half2);
@@ -128,14 +144,15 @@ __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const 
         }
         const float2 s1v = __ffma2_rn(du, zh, make_float2(s1[k][2 * j], s1[k][2 * j + 1]));
         s1[k][2 * j] = s1v.x; s1[k][2 * j + 1] = s1v.y;
-        s2[k][2 * j] += du.x; s2[k][2 * j + 1] += du.y;
+        const float2 s2v = __fadd2_rn(make_float2(s2[k][2 * j], s2[k][2 * j + 1]), du);
+        s2[k][2 * j] = s2v.x; s2[k][2 * j + 1] = s2v.y;
         const float2 dzh = __fmul2_rn(du, aj);
         dot2 = __ffma2_rn(zh, dzh, dot2);
         zf[k][j] = zh;
         gy[k][j] = dzh;
       }
     }
-    const float dot = seg_sum(dot2.x + dot2.y, gl, G, lane);
+    const float dot = bwd_seg_sum(dot2.x + dot2.y, gl, G, lane);
     const float2 ndot2 = make_float2(-dot, -dot);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
@@ -144,7 +161,8 @@ __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         o[j] = __fmul2_rn(__ffma2_rn(zf[k][j], ndot2, gy[k][j]), inv2);
-        s3[k][2 * j] += o[j].x; s3[k][2 * j + 1] += o[j].y;
+        const float2 s3v = __fadd2_rn(make_float2(s3[k][2 * j], s3[k][2 * j + 1]), o[j]);
+        s3[k][2 * j] = s3v.x; s3[k][2 * j + 1] = s3v.y;
       }
       if (live && ch < nchunk)
         dz[rowoff + ch] = make_uint4(pack_bf16(o[0].x, o[0].y), pack_bf16(o[1].x, o[1].y), pack_bf16(o[2].x, o[2].y),
@@ -152,22 +170,36 @@ __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const 
     }
   }
   cp_async_wait<0>();
+  __syncthreads();                                                 // every thread is done with its ring slots
+  // Column sums without shared-memory atomics (24 x kChunks of them per thread, up to 32 threads per address, made the first
+  // version's tail longer than its row loop at C = 288): rows of one warp are folded with shuffles, each warp leaves its
+  // partial in its own slab of the (now free) ring, and every output gets ONE global atomic per CTA.
+  float* const slab = bwd_ring_f + warp * 3 * C;                   // [warp][3][C]; 8 * 3 * C * 4 <= ring bytes (launcher)
 #pragma unroll
   for (int k = 0; k < kChunks; ++k) {
     const int ch = gl + G * k;
-    if (ch < nchunk) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&acc_s[0][ch * 8 + j], s1[k][j]);
-        atomicAdd(&acc_s[1][ch * 8 + j], s2[k][j]);
-        atomicAdd(&acc_s[2][ch * 8 + j], s3[k][j]);
+    for (int j = 0; j < 8; ++j) {
+      float v1 = s1[k][j], v2 = s2[k][j], v3 = s3[k][j];
+      for (int r = 1; r < kRowsPerWarp; ++r) {                     // lanes of row `sub` = 0 collect the other rows
+        v1 += __shfl_down_sync(0xffffffffu, s1[k][j], r * G);
+        v2 += __shfl_down_sync(0xffffffffu, s2[k][j], r * G);
+        v3 += __shfl_down_sync(0xffffffffu, s3[k][j], r * G);
+      }
+      if (sub == 0 && ch < nchunk) {
+        slab[ch * 8 + j] = v1;
+        slab[C + ch * 8 + j] = v2;
+        slab[2 * C + ch * 8 + j] = v3;
       }
     }
   }
   __syncthreads();
   for (int i = tid; i < 3 * C; i += kBwdThreads) {
-    const int w = i / C, c = i - w * C;
-    atomicAdd(&sums[((size_t)w * B + b) * C + c], acc_s[w][c]);
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBwdThreads / 32; ++w) v += bwd_ring_f[w * 3 * C + i];
+    const int w3 = i / C, c = i - w3 * C;
+    atomicAdd(&sums[((size_t)w3 * B + b) * C + c], v);
   }
 }
 
@@ -228,27 +260,50 @@ extern "C" int ccdm_block_bwd(const void* dy, const void* z, void* dz, int64_t r
   int kv, G;
   row_lane_plan(C / 8, 4, &kv, &G);
   CCDM_REQUIRE(B <= 65535, CCDM_ERR_UNSUPPORTED_SHAPE, "block_bwd: %d samples", B);
-  // a few CTAs per SM, slabs of >= 64 rows of one sample each
-  int per_sample = (num_sms() * 3 + B - 1) / B;
-  const int max_split = (rows_per_sample + 63) / 64;
-  if (per_sample > max_split) per_sample = max_split;
-  if (per_sample < 1) per_sample = 1;
+  // Slabs of rows of one sample per CTA.  The number of slabs per sample minimises (waves of resident CTAs) x (row-loop
+  // iterations per CTA + ~3 iterations' worth of prologue / column-sum epilogue): the first heuristic (3 CTAs per SM) left
+  // 2-3 iterations per CTA at 16x16 / 8x8 resolutions, all overhead.
+  const int slots = num_sms() * (kv <= 2 ? 2 : 1);
+  const int rstep = (kBwdThreads / 32) * (32 / G);
+  int max_split = (rows_per_sample + 63) / 64;
+  if (max_split > 64) max_split = 64;
+  int per_sample = 1;
+  long long best_cost = -1;
+  for (int p = 1; p <= max_split; ++p) {
+    const int rpb = (rows_per_sample + p - 1) / p;
+    const long long waves = ((long long)B * ((rows_per_sample + rpb - 1) / rpb) + slots - 1) / slots;
+    const long long cost = waves * ((rpb + rstep - 1) / rstep + 3);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      per_sample = p;
+    }
+  }
   const int rows_per_block = (rows_per_sample + per_sample - 1) / per_sample;
   per_sample = (rows_per_sample + rows_per_block - 1) / rows_per_block;
   dim3 grid((unsigned)per_sample, (unsigned)B);
+  const bool silu = (flags & CCDM_EPI_SILU) != 0;
 #define CCDM_BWD(K)                                                                                                   \
   do {                                                                                                                \
     constexpr int ring_bytes = bwd_stages(K) * K * 2 * kBwdThreads * 16;                                              \
     constexpr int min_ctas = K <= 2 ? 2 : 1;                                                                          \
     static bool attr_done = false;                                                                                    \
     if (!attr_done) {                                                                                                 \
-      cudaError_t e = cudaFuncSetAttribute(block_bwd_kernel<K, min_ctas>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes); \
+      cudaError_t e = cudaFuncSetAttribute(block_bwd_kernel<K, min_ctas, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           ring_bytes);                                                               \
+      if (e == cudaSuccess)                                                                                           \
+        e = cudaFuncSetAttribute(block_bwd_kernel<K, min_ctas, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 ring_bytes);                                                                         \
       if (e != cudaSuccess) return cuda_fail(e, "block_bwd: cudaFuncSetAttribute");                                   \
       attr_done = true;                                                                                               \
     }                                                                                                                 \
-    block_bwd_kernel<K, min_ctas><<<grid, kBwdThreads, ring_bytes, s>>>((const uint4*)dy, (const uint4*)z, (uint4*)dz, \
-                                                              rows_per_sample, rows_per_block, C, gain, gain_mul,    \
-                                                              scale_shift, ss_ld, ss_off, sums, B, flags, G);         \
+    if (silu)                                                                                                         \
+      block_bwd_kernel<K, min_ctas, true><<<grid, kBwdThreads, ring_bytes, s>>>(                                      \
+          (const uint4*)dy, (const uint4*)z, (uint4*)dz, rows_per_sample, rows_per_block, C, gain, gain_mul, scale_shift, \
+          ss_ld, ss_off, sums, B, flags, G);                                                                          \
+    else                                                                                                              \
+      block_bwd_kernel<K, min_ctas, false><<<grid, kBwdThreads, ring_bytes, s>>>(                                     \
+          (const uint4*)dy, (const uint4*)z, (uint4*)dz, rows_per_sample, rows_per_block, C, gain, gain_mul, scale_shift, \
+          ss_ld, ss_off, sums, B, flags, G);                                                                          \
   } while (0)
   if (kv == 1) CCDM_BWD(1);
   else if (kv == 2) CCDM_BWD(2);

@@ -3,19 +3,24 @@
 //
 //   dW[co][ci][tap] = sum over output positions p of dZ[p][co] * X[p + shift(tap)][ci]
 //
-// Per load group of the FORWARD schedule (source view, dw, dh0, 64-channel slice c0; R vertically adjacent taps) this
-// is R GEMMs over the position axis that share their operands:
+// Per load group of the FORWARD schedule (source view, dw, dh0, 64-channel slice c0; R vertically adjacent taps) these are
+// R GEMMs over the position axis that share their operands.  The ACTIVATIONS are the A operand and the taps are stacked
+// along M (two taps per instruction), the output gradient is the B operand:
 //
-//   D_r[128 co x 64 ci] = dZ^T[128 co x 128 pos] . X_r[128 pos x 64 ci]          r = 0..R-1
+//   D_p[(tap t0 | tap t0+1) x 64 ci][n co] = [X_t0 | X_t0+1]^T[128 x 128 pos] . dZ[128 pos x n co]     n = Cout tile <= 128
 //
 // Activations are position-major (channels contiguous), so both operands are "MN-major" for UMMA: a TMA box of
 // {64 channels, tw, th, tb} lands as one 128-byte row per position in the SWIZZLE_128B layout.  The X box carries
-// R-1 extra rows, exactly like the forward kernel: tap r starts r*tw rows (r*tw*128 bytes) into it, i.e. the K offset
-// of the B descriptor.  Out-of-image positions are zero-filled by TMA (= the convolution's zero padding), out-of-range
-// channels likewise (so M is always 128, which costs the same tensor-core time as 64).
+// R-1 extra rows, exactly like the forward kernel: tap r starts r*tw rows (r*tw*128 bytes, a multiple of the 1024-byte
+// swizzle atom) into it -- which is both the start offset of the A descriptor and its leading-dimension byte offset, i.e.
+// rows 64..127 of A are the NEXT tap's view of the same box.  R = 3 issues the pairs (0,1) and (1,2) and drops the
+// duplicate; R = 1 wastes half of M.  (The first version had dZ as A with M = 128 output channels and one N = 64
+// instruction per tap: 3 instructions of 6 KB of shared-memory operand reads per K step against 2 of 6.5 KB here, and the
+// shared-memory port, not the tensor pipe, is what bounds these shapes -- profiles/r2_notes.md.)
+// Out-of-image positions are zero-filled by TMA (= the convolution's zero padding), out-of-range channels likewise.
 //
 // Work split: blockIdx.y = (z, group, 128-channel output tile), blockIdx.x = slice of the position tiles (split-K).
-// Each CTA accumulates its slice in TMEM and adds it into the fp32 gradient with vector reductions.  The gradient is
+// Each CTA accumulates its slice in TMEM and adds it into the fp32 gradient with reductions (coalesced over ci).  The gradient is
 // produced in the PACKED layout of the forward weights ([z][row][kb*64 + j], kb = group*R + r); ccdm_unpack_wgrad
 // maps it back to [Cout][Cin][kh*kw] (summing the folded taps of the nearest-2x upsampling convolution).
 #include <cstring>
@@ -47,26 +52,25 @@ struct WgDev {
   float* out;
   int ngroups, R, nkb, m_tiles, n_rows;
   int tw, th, tb, tiles_w, tiles_h, tiles_m, tiles_per_cta;
-  int stages;
-  uint32_t b_bytes, stage_bytes, tx_bytes;
+  int stages, N;
+  uint32_t b_bytes, stage_bytes;
 };
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
+// First tap of pair p: R = 3 -> (0,1), (1,2); R = 2 -> (0,1); R = 1 -> (0, unused).
+__host__ __device__ constexpr int wg_pair_t0(int R, int p) { return R >= 2 ? (2 * p < R - 2 ? 2 * p : R - 2) : 0; }
 
-// R taps x 8 K-steps (16 positions each) of one position tile; descriptor low words hold (address >> 4) | LBO.
+// Tap pairs x 8 K-steps (16 positions each) of one position tile; descriptor low words hold (address >> 4) | LBO.
 template <int kR>
-__device__ __forceinline__ void wgrad_taps(uint32_t tmem_base, uint32_t a_lo, uint32_t b_lo, uint32_t tap16,
+__device__ __forceinline__ void wgrad_taps(uint32_t tmem_base, uint32_t x_lo, uint32_t dz_lo, uint32_t tap16,
                                            uint32_t idesc, uint32_t acc_first) {
   constexpr uint64_t hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
                           (static_cast<uint64_t>(2) << 61);
 #pragma unroll
-  for (int r = 0; r < kR; ++r) {
+  for (int pr = 0; pr < (kR + 1) / 2; ++pr) {
+    const uint32_t a_lo = x_lo + wg_pair_t0(kR, pr) * tap16;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      umma_bf16_ss(tmem_base + r * 64, hi | (a_lo + k * 128), hi | (b_lo + r * tap16 + k * 128), idesc,
-                   k != 0 ? 1u : acc_first);
+      umma_bf16_ss(tmem_base + pr * 128, hi | (a_lo + k * 128), hi | (dz_lo + k * 128), idesc, k != 0 ? 1u : acc_first);
   }
 }
 
@@ -83,6 +87,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   const int4 e = __ldg(&p.sched[z * p.ngroups + g]);               // {source view, dw, dh0, c0}
   const int t0 = blockIdx.x * p.tiles_per_cta;
   const int t1 = min(t0 + p.tiles_per_cta, p.tiles_m);
+  const int n_here = min(128, p.N - mt * 128);                    // output channels of this tile
+  const int ncols = (n_here + 15) & ~15;                           // N of the instruction
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.src[e.x]);
@@ -117,9 +123,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
       mbar_wait_a(empty_bar + 8 * s, ph ^ 1u);
       if (elect_one()) {
         const int cw = tx * p.tw, chh = ty * p.th, cb = tz * p.tb;
-        mbar_arrive_expect_tx_a(full_bar + 8 * s, p.tx_bytes);
+        mbar_arrive_expect_tx_a(full_bar + 8 * s, (ncols > 64 ? 2 : 1) * kWgABlock + p.b_bytes);
         tma_load_4d_a(dzm, full_bar + 8 * s, st_a, mt * 128, cw, chh, cb);
-        tma_load_4d_a(dzm, full_bar + 8 * s, st_a + kWgABlock, mt * 128 + 64, cw, chh, cb);
+        if (ncols > 64) tma_load_4d_a(dzm, full_bar + 8 * s, st_a + kWgABlock, mt * 128 + 64, cw, chh, cb);
         tma_load_4d_a(srm, full_bar + 8 * s, st_a + 2 * kWgABlock, e.w, cw + e.y, chh + e.z, cb);
       }
       __syncwarp();
@@ -131,55 +137,55 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
     // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, one elected lane).
     // The lane is latency-bound: descriptors advance by integer adds on a precomputed low word (address >> 4 | LBO),
     // the taps are unrolled per R, barriers are addressed as integers.
-    const uint32_t idesc = umma_idesc_bf16_mn(128, 64);
+    const uint32_t idesc = umma_idesc_bf16_mn(128, static_cast<uint32_t>(ncols));
     const uint32_t full_bar = smem_u32(&aux->full[0]), empty_bar = smem_u32(&aux->empty[0]);
-    const uint32_t lo_flags = static_cast<uint32_t>((kWgABlock >> 4) & 0x3FFF) << 16;       // LBO = 16 KiB block stride
-    const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFF) >> 4) | lo_flags;
     const uint32_t stage16 = p.stage_bytes >> 4, tap16 = static_cast<uint32_t>(p.tw) * 8;
+    const uint32_t dz_flags = static_cast<uint32_t>((kWgABlock >> 4) & 0x3FFF) << 16;       // B: LBO = 16 KiB block stride
+    const uint32_t x_flags = (tap16 & 0x3FFF) << 16;                                        // A: LBO = one tap (tw rows)
+    const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFF) >> 4) | dz_flags;
+    const uint32_t x_lo0 = (((smem_u32(ring) + 2 * kWgABlock) & 0x3FFFF) >> 4) | x_flags;
     const int n_stages = p.stages;
     int s = 0;
-    uint32_t ph = 0, a_lo = a_lo0;
+    uint32_t ph = 0, a_lo = a_lo0, x_lo = x_lo0;
     uint32_t first = 0;                                    // 0 for the first position tile: overwrite the accumulators
     for (int t = t0; t < t1; ++t) {
       mbar_wait_a(full_bar + 8 * s, ph);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t b_lo = a_lo + ((2 * kWgABlock) >> 4);
-        if (p.R == 3) wgrad_taps<3>(tmem_base, a_lo, b_lo, tap16, idesc, first);
-        else if (p.R == 2) wgrad_taps<2>(tmem_base, a_lo, b_lo, tap16, idesc, first);
-        else wgrad_taps<1>(tmem_base, a_lo, b_lo, tap16, idesc, first);
+        if (p.R == 3) wgrad_taps<3>(tmem_base, x_lo, a_lo, tap16, idesc, first);
+        else if (p.R == 2) wgrad_taps<2>(tmem_base, x_lo, a_lo, tap16, idesc, first);
+        else wgrad_taps<1>(tmem_base, x_lo, a_lo, tap16, idesc, first);
         umma_commit_a(empty_bar + 8 * s);
       }
       __syncwarp();
       first = 1;
       a_lo += stage16;
-      if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; }
+      x_lo += stage16;
+      if (++s == n_stages) { s = 0; ph ^= 1u; a_lo = a_lo0; x_lo = x_lo0; }
     }
     if (t1 > t0) {
       if (elect_one()) umma_commit(&aux->acc_full);
       __syncwarp();
     }
   } else if (t1 > t0) {
-    // ---------------------------------------------------------------- epilogue: row co = TMEM lane
+    // ---------------------------------------------------------------- epilogue: TMEM lane = (tap of the pair, ci), column = co
     const int q = warp & 3;
-    const int row = mt * 128 + q * 32 + lane;
+    const int half = q >> 1, ci = (q & 1) * 32 + lane;
     mbar_wait(&aux->acc_full, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    float* orow = p.out + ((size_t)z * p.n_rows + row) * ((size_t)p.nkb * 64) + (size_t)g * p.R * 64;
-    for (int r = 0; r < p.R; ++r) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+    const size_t row_ld = (size_t)p.nkb * 64;
+    for (int pr = 0; pr < (p.R + 1) / 2; ++pr) {
+      const int tap = wg_pair_t0(p.R, pr) + half;
+      if (tap >= p.R || tap < 2 * pr) continue;                    // unused half (R = 1) or the duplicate of pair (1,2)
+      float* obase = p.out + ((size_t)z * p.n_rows + (size_t)mt * 128) * row_ld + (size_t)(g * p.R + tap) * 64 + ci;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(trow + r * 64 + half * 32, v);
+        tmem_ld32(trow + pr * 128 + c0, v);
         tmem_ld_wait();
-        if (row < p.n_rows) {
-          float* o = orow + r * 64 + half * 32;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            red_add_v4(o + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        }
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < n_here) atomicAdd(obase + (size_t)(c0 + i) * row_ld, __uint_as_float(v[i]));   // RED, 128 B per warp
       }
     }
     tc_fence_before();
@@ -305,12 +311,13 @@ extern "C" int ccdm_conv_wgrad(const ccdm_wgrad_args* a, void* stream) {
   if (ksplit > p.tiles_m) ksplit = p.tiles_m;
   p.tiles_per_cta = (p.tiles_m + ksplit - 1) / ksplit;
   ksplit = (p.tiles_m + p.tiles_per_cta - 1) / p.tiles_per_cta;    // no CTA without work
+  p.N = a->N;
   p.b_bytes = (uint32_t)(box_h * a->tw * a->tb) * 128u;
-  p.tx_bytes = 2 * kWgABlock + p.b_bytes;
-  p.stage_bytes = p.tx_bytes;
+  p.stage_bytes = 2 * kWgABlock + p.b_bytes;
   p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
   p.stages = p.tiles_per_cta < kWgMaxStages ? (p.tiles_per_cta < 2 ? 2 : p.tiles_per_cta) : kWgMaxStages;
-  const size_t smem = (size_t)p.stages * p.stage_bytes + sizeof(WgAux) + 1024;
+  // R = 1: rows 64..127 of the A operand (the unused "next tap") reach up to tw rows past the box of the last stage
+  const size_t smem = (size_t)p.stages * p.stage_bytes + sizeof(WgAux) + 1024 + (a->R == 1 ? (size_t)a->tw * 128 : 0);
   CCDM_REQUIRE(smem <= 227 * 1024, CCDM_ERR_UNSUPPORTED_SHAPE, "conv_wgrad: %zu bytes of shared memory", smem);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {

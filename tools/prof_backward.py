@@ -29,7 +29,9 @@ def main():
     B = int(os.environ.get("B", 128))
     out = []
     shapes = [("3x3", (64,), 64, 64), ("3x3", (128,), 128, 32), ("3x3", (128, 128), 128, 32), ("3x3", (256,), 256, 16),
-              ("3x3", (512,), 512, 8), ("down4x4s2", (64,), 64, 64), ("up2x3x3", (128,), 64, 32), ("1x1", (64,), 384, 64)]
+              ("3x3", (512,), 512, 8), ("down4x4s2", (64,), 64, 64), ("up2x3x3", (128,), 64, 32), ("1x1", (64,), 384, 64),
+              # UTKFace widths (dim 72): BASELINE configs[1], the training step bench.py reports
+              ("3x3", (72,), 72, 64), ("3x3", (72, 72), 72, 64), ("3x3", (144,), 144, 32), ("3x3", (288,), 288, 16)]
     for kind, cins, cout, hw in shapes:
         xs = [torch.randn(B, hw, hw, c, device="cuda").bfloat16() for c in cins]
         k = {"1x1": 1, "3x3": 3, "down4x4s2": 4, "up2x3x3": 3}[kind]

@@ -33,7 +33,7 @@ def main():
     lib = L.lib()
     st = torch.cuda.current_stream().cuda_stream
     out = []
-    for c, hw in [(64, 64), (72, 64), (128, 32), (144, 32), (256, 16), (512, 8), (576, 8)]:
+    for c, hw in [(64, 64), (72, 64), (128, 32), (144, 32), (256, 16), (288, 16), (512, 8), (576, 8)]:
         rows = B * hw * hw
         z = torch.randn(B, hw, hw, c, device="cuda").bfloat16()
         dy = torch.randn_like(z)
