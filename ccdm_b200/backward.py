@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import os
 import weakref
 import math
 from typing import List, Optional, Sequence, Tuple
@@ -24,7 +25,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from .plan import KB, ConvPlan, can_reuse_rows, n_tiling, plan_conv, tile_box
+from .plan import HALO_TILE, KB, ConvPlan, can_reuse_rows, halo_ok, n_tiling, plan_conv, tile_box
 
 _KIND_TAPS = {"1x1": 1, "3x3": 9, "down4x4s2": 16, "down3x3s2": 9, "up2x3x3": 9}
 
@@ -73,6 +74,22 @@ def _plan_cached(kind, cins, cout, gw, gh):
     tile = tile_box(gw, gh, square=(base != "1x1"))
     reuse = base != "1x1" and can_reuse_rows(tile)
     return plan_conv(kind, cins, cout, reuse_rows=reuse), tile
+
+
+WGRAD_HALO = os.environ.get("CCDM_WGRAD_HALO", "1") != "0"       # A/B switch
+
+
+@functools.lru_cache(maxsize=None)
+def _wgrad_plan_for(kind, cins, cout, gw, gh):
+    """Weight-gradient plan: 3x3 layers on grids of 8 x 16 tiles take the halo plan (R == 9 in ccdm_wgrad_args: one dZ box
+    and one X halo box per tile feed all nine taps, so dZ and X cross L2 -> SM once per 64-channel block instead of three
+    times); everything else follows the forward's load groups."""
+    # Measured (profiles/r2_notes.md): the halo kernel wins whenever the last 128-channel tile of the output would be mostly
+    # padding for the group kernel (Cout = 64, 72, 144, 288 ...); for Cout = 128 / 256 its 96-column accumulators need one
+    # more pass over X than the group kernel's 128-row tiles and it loses 8-15 %.
+    if WGRAD_HALO and halo_ok(kind, gw, gh) and 0 < cout % 128 <= 96:
+        return plan_conv(kind, cins, cout, halo=True), HALO_TILE
+    return _plan_cached(kind, cins, cout, gw, gh)
 
 
 def _launch_tapgemm(plan: ConvPlan, tile, views: List[L.View], gw, gh, gb, wpacked, sched, n_rows, n, n_tile, out,
@@ -345,7 +362,7 @@ def conv_wgrad(kind: str, srcs: Sequence[torch.Tensor], dz: torch.Tensor, ksplit
     _, oh, ow, cout = dz.shape
     gh, gw = (h, w) if kind == "up2x3x3" else (oh, ow)
     cins = [s.shape[3] for s in srcs]
-    plan, tile = _plan_for(kind, cins, cout, gw, gh)
+    plan, tile = _wgrad_plan_for(kind, tuple(cins), cout, gw, gh)
     dev = dz.device
     n_rows = (cout + 31) // 32 * 32
     sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)

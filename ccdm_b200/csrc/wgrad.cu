@@ -198,6 +198,166 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 layers on grids of 8 x 16 tiles: ALL nine taps of a 64-channel block out of ONE halo box.
+//
+// The kernel above is bound by L2 -> SM traffic, not by the tensor pipe: every (channel block, dw) group is its own CTA
+// unit and re-reads the whole dZ tensor and a shifted copy of X (72 -> 72 at 64x64, batch 128: 6 units x 150 MB = 900 MB
+// through L2 per launch, 189 us).  Here a unit is (channel block, <= 96 output channels): per 8 x 16 position tile ONE dZ
+// box and ONE X box {64 ch, 10, 18} are loaded and the nine taps are addressed inside it.  SWIZZLE_128B is a pure function
+// of the shared-memory address, so an operand may start at any 128-byte row (profiles/r2_ubench_shift_desc.txt; the
+// forward's halo plan relies on the same fact): a K step is 16 positions = two image rows of 8 pixels, i.e. two 8-row
+// groups 1280 bytes apart in the box (SBO = 1280); tap (r, q) starts (r*10 + q) rows into it.  Taps are stacked two per
+// instruction along M exactly as above (LBO = the byte distance between the two taps' views):
+//   pair 0..2: taps (0,q) | (1,q)  LBO = 10 rows;   pair 3: (2,0) | (2,1)  LBO = 1 row;   pair 4: (2,2) | unused.
+// Five accumulators of <= 96 columns (480 of the 512 TMEM columns); packed K block of tap (r, q) = g*9 + r*3 + q, the
+// layout of the forward's halo plan (plan.py: plan_conv(halo=True)), so ccdm_unpack_wgrad takes that plan's schedule.
+constexpr uint32_t kWhXBytes = 10 * 18 * 128;             // halo box
+constexpr uint32_t kWhXSlot = 23 * 1024;                  // + 512 bytes the unused half of pair 4 may read past the box
+constexpr int kWhAccStride = 96;
+
+struct WhDev {
+  const int4* sched;
+  float* out;
+  int ngroups, nkb, n_tiles, n_tile, n_rows, N;
+  int tiles_w, tiles_h, tiles_m, tiles_per_cta;
+  int stages, dz_blocks;
+  uint32_t stage_bytes;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgMaps maps, const WhDev p) {
+  extern __shared__ __align__(1024) uint8_t wg_smem[];
+  uint8_t* ring = wg_smem;
+  WgAux* aux = reinterpret_cast<WgAux*>(ring + (size_t)p.stages * p.stage_bytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const int unit = blockIdx.y;
+  const int nt = unit % p.n_tiles;
+  const int g = (unit / p.n_tiles) % p.ngroups;
+  const int z = unit / (p.n_tiles * p.ngroups);
+  const int4 e = __ldg(&p.sched[z * p.ngroups + g]);               // {source view, -1, -1, c0}
+  const int t0 = blockIdx.x * p.tiles_per_cta;
+  const int t1 = min(t0 + p.tiles_per_cta, p.tiles_m);
+  const int n0 = nt * p.n_tile;
+  const int n_here = min(p.n_tile, p.N - n0);                      // output channels of this unit
+  const int ncols = (n_here + 15) & ~15;                           // N of the instruction
+  const uint32_t x_off = static_cast<uint32_t>(p.dz_blocks) * kWgABlock;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.src[e.x]);
+    tma_prefetch_desc(&maps.dz[z]);
+  }
+  if (warp == 1) tmem_alloc(&aux->tmem_slot, 512);
+  if (tid == 64) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&aux->full[s], 1);
+      mbar_init(&aux->empty[s], 1);
+    }
+    mbar_init(&aux->acc_full, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = aux->tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    int tx = t0 % p.tiles_w, ty = (t0 / p.tiles_w) % p.tiles_h, tz = t0 / (p.tiles_w * p.tiles_h);
+    const uint32_t full_bar = smem_u32(&aux->full[0]), empty_bar = smem_u32(&aux->empty[0]);
+    const uint32_t ring_a = smem_u32(ring);
+    const int n_stages = p.stages;
+    const CUtensorMap* const dzm = &maps.dz[z];
+    const CUtensorMap* const srm = &maps.src[e.x];
+    const uint32_t tx_bytes = (ncols > 64 ? 2u : 1u) * kWgABlock + kWhXBytes;
+    int s = 0;
+    uint32_t ph = 0, st_a = ring_a;
+    for (int t = t0; t < t1; ++t) {
+      mbar_wait_a(empty_bar + 8 * s, ph ^ 1u);
+      if (elect_one()) {
+        const int cw = tx * 8, chh = ty * 16;
+        mbar_arrive_expect_tx_a(full_bar + 8 * s, tx_bytes);
+        tma_load_4d_a(dzm, full_bar + 8 * s, st_a, n0, cw, chh, tz);
+        if (ncols > 64) tma_load_4d_a(dzm, full_bar + 8 * s, st_a + kWgABlock, n0 + 64, cw, chh, tz);
+        tma_load_4d_a(srm, full_bar + 8 * s, st_a + x_off, e.w, cw + e.y, chh + e.z, tz);
+      }
+      __syncwarp();
+      if (++tx == p.tiles_w) { tx = 0; if (++ty == p.tiles_h) { ty = 0; ++tz; } }
+      st_a += p.stage_bytes;
+      if (++s == n_stages) { s = 0; ph ^= 1u; st_a = ring_a; }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer: 5 tap pairs x 8 K steps per tile
+    const uint32_t idesc = umma_idesc_bf16_mn(128, static_cast<uint32_t>(ncols));
+    const uint32_t full_bar = smem_u32(&aux->full[0]), empty_bar = smem_u32(&aux->empty[0]);
+    constexpr uint64_t hi_x = (static_cast<uint64_t>(1280 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                              (static_cast<uint64_t>(2) << 61);
+    constexpr uint64_t hi_dz = (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+                               (static_cast<uint64_t>(2) << 61);
+    const uint32_t stage16 = p.stage_bytes >> 4;
+    const uint32_t dz_lo0 = ((smem_u32(ring) & 0x3FFFF) >> 4) | (static_cast<uint32_t>((kWgABlock >> 4) & 0x3FFF) << 16);
+    const uint32_t x_lo0 = ((smem_u32(ring) + x_off) & 0x3FFFF) >> 4;
+    const int n_stages = p.stages;
+    int s = 0;
+    uint32_t ph = 0, dz_lo = dz_lo0, x_lo = x_lo0;
+    uint32_t first = 0;                                    // 0 for the first position tile: overwrite the accumulators
+    for (int t = t0; t < t1; ++t) {
+      mbar_wait_a(full_bar + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll 1
+        for (int pr = 0; pr < 5; ++pr) {
+          // start row of the pair's first tap in the box (8 sixteen-byte units per row) | LBO between its two taps
+          const uint32_t row0 = pr < 3 ? static_cast<uint32_t>(pr) : (pr == 3 ? 20u : 22u);
+          const uint32_t a_lo = x_lo + row0 * 8 + ((pr < 3 ? 80u : 8u) << 16);
+          const uint32_t d = tmem_base + pr * kWhAccStride;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)                     // K step k = image rows 2k, 2k+1 of the tile: 20 box rows on
+            umma_bf16_ss(d, hi_x | (a_lo + k * 160), hi_dz | (dz_lo + k * 128), idesc, k != 0 ? 1u : first);
+        }
+        umma_commit_a(empty_bar + 8 * s);
+      }
+      __syncwarp();
+      first = 1;
+      dz_lo += stage16;
+      x_lo += stage16;
+      if (++s == n_stages) { s = 0; ph ^= 1u; dz_lo = dz_lo0; x_lo = x_lo0; }
+    }
+    if (t1 > t0) {
+      if (elect_one()) umma_commit(&aux->acc_full);
+      __syncwarp();
+    }
+  } else if (t1 > t0) {
+    // ---------------------------------------------------------------- epilogue: TMEM lane = (tap of the pair, ci), column = co
+    const int q = warp & 3;
+    const int half = q >> 1, ci = (q & 1) * 32 + lane;
+    mbar_wait(&aux->acc_full, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const size_t row_ld = (size_t)p.nkb * 64;
+    for (int pr = 0; pr < 5; ++pr) {
+      const int tap = pr < 3 ? pr + 3 * half : (pr == 3 ? 6 + half : (half == 0 ? 8 : -1));
+      if (tap < 0) continue;
+      float* obase = p.out + ((size_t)z * p.n_rows + (size_t)n0) * row_ld + (size_t)(g * 9 + tap) * 64 + ci;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + pr * kWhAccStride + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < n_here) atomicAdd(obase + (size_t)(c0 + i) * row_ld, __uint_as_float(v[i]));   // RED, 128 B per warp
+      }
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // dW[n][cin0+j][t] += gain * packed[z][n][kb*64 + j] for every tap t in the block's tapmask (scatter; dW zeroed or
 // accumulated by the caller -- the folded taps of the nearest-2x convolution land on the same element from several
 // blocks, hence atomics)
@@ -260,15 +420,19 @@ extern "C" int ccdm_conv_wgrad(const ccdm_wgrad_args* a, void* stream) {
   CCDM_REQUIRE(a->n_src >= 1 && a->n_src <= CCDM_MAX_SRC, CCDM_ERR_BAD_ARG, "conv_wgrad: n_src=%d", a->n_src);
   CCDM_REQUIRE(a->tw > 0 && a->th > 0 && a->tb > 0 && a->tw * a->th * a->tb == 128, CCDM_ERR_BAD_ARG,
                "conv_wgrad: tile box %dx%dx%d must hold 128 positions", a->tw, a->th, a->tb);
-  CCDM_REQUIRE(a->nz >= 1 && a->nz <= CCDM_MAX_Z && a->ngroups >= 1 && a->R >= 1 && a->R <= 3, CCDM_ERR_BAD_ARG,
+  CCDM_REQUIRE(a->nz >= 1 && a->nz <= CCDM_MAX_Z && a->ngroups >= 1 && a->R >= 1 && (a->R <= 3 || a->R == 9), CCDM_ERR_BAD_ARG,
                "conv_wgrad: nz=%d ngroups=%d R=%d", a->nz, a->ngroups, a->R);
-  CCDM_REQUIRE(a->R == 1 || (a->tb == 1 && a->tw % 8 == 0), CCDM_ERR_BAD_ARG,
+  CCDM_REQUIRE(a->R == 1 || a->R == 9 || (a->tb == 1 && a->tw % 8 == 0), CCDM_ERR_BAD_ARG,
                "conv_wgrad: vertical tap reuse (R=%d) needs tb == 1 and tw %% 8 == 0", a->R);
   CCDM_REQUIRE(a->sched && a->dz && a->wgrad_packed, CCDM_ERR_BAD_ARG, "conv_wgrad: null sched/dz/wgrad_packed");
   CCDM_REQUIRE(a->N >= 1 && a->N % 8 == 0 && a->n_rows >= a->N, CCDM_ERR_UNSUPPORTED_SHAPE, "conv_wgrad: N=%d n_rows=%d",
                a->N, a->n_rows);
   CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->wgrad_packed) & 15) == 0, CCDM_ERR_BAD_ARG, "conv_wgrad: output alignment");
-  const int box_h = a->th + a->R - 1;
+  const bool halo = a->R == 9;                                     // plan_conv(halo=True): one box, nine taps
+  CCDM_REQUIRE(a->R <= 3 || (halo && a->tw == 8 && a->th == 16 && a->tb == 1 && a->nz == 1), CCDM_ERR_BAD_ARG,
+               "conv_wgrad: R=%d needs the 8 x 16 x 1 halo tile and nz == 1", a->R);
+  const int box_h = halo ? 18 : a->th + a->R - 1;
+  const int box_w = halo ? 10 : a->tw;
   WgMaps maps;
   std::memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < CCDM_MAX_SRC; ++i) {
@@ -279,7 +443,7 @@ extern "C" int ccdm_conv_wgrad(const ccdm_wgrad_args* a, void* stream) {
                  CCDM_ERR_BAD_ARG, "conv_wgrad: source %d extents/strides", i);
     cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.B};
     cuuint64_t str[3] = {(cuuint64_t)v.sW * 2, (cuuint64_t)v.sH * 2, (cuuint64_t)v.sB * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)a->tw, (cuuint32_t)box_h, (cuuint32_t)a->tb};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)a->tb};
     int rc = encode_map_bf16(&maps.src[i], v.ptr, 4, dims, str, box);
     if (rc != CCDM_OK) return rc;
   }
@@ -293,6 +457,40 @@ extern "C" int ccdm_conv_wgrad(const ccdm_wgrad_args* a, void* stream) {
     cuuint32_t box[4] = {64, (cuuint32_t)a->tw, (cuuint32_t)a->th, (cuuint32_t)a->tb};
     int rc = encode_map_bf16(&maps.dz[zz], reinterpret_cast<const __nv_bfloat16*>(a->dz) + a->doff[zi], 4, dims, str, box);
     if (rc != CCDM_OK) return rc;
+  }
+  if (halo) {
+    WhDev h;
+    std::memset(&h, 0, sizeof(h));
+    h.sched = reinterpret_cast<const int4*>(a->sched);
+    h.out = a->wgrad_packed;
+    h.ngroups = a->ngroups; h.nkb = a->ngroups * 9;
+    h.n_tiles = (a->N + kWhAccStride - 1) / kWhAccStride;          // <= 96 output channels per unit, evenly split
+    h.n_tile = (((a->N + h.n_tiles - 1) / h.n_tiles) + 15) & ~15;
+    h.n_tiles = (a->N + h.n_tile - 1) / h.n_tile;
+    h.n_rows = a->n_rows; h.N = a->N;
+    h.tiles_w = (a->gW + 7) / 8;
+    h.tiles_h = (a->gH + 15) / 16;
+    h.tiles_m = h.tiles_w * h.tiles_h * a->gB;
+    const int units = a->ngroups * h.n_tiles;
+    int ksplit = a->ksplit > 0 ? a->ksplit : num_sms() / units;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > h.tiles_m) ksplit = h.tiles_m;
+    h.tiles_per_cta = (h.tiles_m + ksplit - 1) / ksplit;
+    ksplit = (h.tiles_m + h.tiles_per_cta - 1) / h.tiles_per_cta;
+    h.dz_blocks = h.n_tile > 64 ? 2 : 1;
+    h.stage_bytes = (uint32_t)h.dz_blocks * kWgABlock + kWhXSlot;
+    const int max_stages = h.dz_blocks == 2 ? 3 : 4;
+    h.stages = h.tiles_per_cta < max_stages ? (h.tiles_per_cta < 2 ? 2 : h.tiles_per_cta) : max_stages;
+    const size_t smem = (size_t)h.stages * h.stage_bytes + sizeof(WgAux) + 1024;
+    CCDM_REQUIRE(smem <= 227 * 1024, CCDM_ERR_UNSUPPORTED_SHAPE, "conv_wgrad(halo): %zu bytes of shared memory", smem);
+    static size_t attr_smem_h = 0;
+    if (smem > attr_smem_h) {
+      cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "conv_wgrad(halo): cudaFuncSetAttribute");
+      attr_smem_h = smem;
+    }
+    conv_wgrad_halo_kernel<<<dim3((unsigned)ksplit, (unsigned)units), kWgThreads, smem, (cudaStream_t)stream>>>(maps, h);
+    return after_launch("conv_wgrad_halo_kernel");
   }
   WgDev p;
   std::memset(&p, 0, sizeof(p));

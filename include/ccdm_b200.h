@@ -336,7 +336,10 @@ int ccdm_pack_weights_t(const float* w, int32_t cout, int32_t cin_total, int32_t
  * layout of the forward weights:  wgrad_packed[z][n][(g*R+r)*64 + j] += sum_p dZ_z[p][n] * src[g][p + tap(g,r)][c0[g]+j].
  * src / gW..tb / nz / ngroups / R / sched are the forward layer's; dz is the gradient w.r.t. the conv output (bias
  * included, before any norm), bf16, addressed like the forward `out` (strides dsW/dsH/dsB, plane offsets doff[z]).
- * ksplit = number of position slices (CTAs per (z, group, 128-row tile)); 0 = fill the GPU once. */
+ * ksplit = number of position slices (CTAs per (z, group, 128-row tile)); 0 = fill the GPU once.
+ * R == 9 selects the HALO plan of a 3x3 / stride-1 layer (tile 8 x 16 x 1, nz == 1): a group is one 64-channel block
+ * {source view, -1, -1, c0} and K block g*9 + r*3 + q is filter tap (r, q); one dZ box and one X box {64, 10, 18} per
+ * tile feed all nine taps. */
 typedef struct ccdm_wgrad_args {
   int32_t n_src;
   ccdm_view src[CCDM_MAX_SRC];

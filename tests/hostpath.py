@@ -179,7 +179,10 @@ def wgrad_abi(argref, stream):
         for kb in range(plan.nkb):
             grp, r = divmod(kb, plan.R)
             src, dw, dh0, c0 = plan.sched[z * plan.ngroups + grp]
-            x = shifted(views[src], dh0 + r, dw, a.gH, a.gW, c0)[: a.gB]
+            q = 0
+            if plan.R == 9:                                             # halo plan: K block g*9 + r*3 + q = tap (r, q)
+                r, q = divmod(r, 3)
+            x = shifted(views[src], dh0 + r, dw + q, a.gH, a.gW, c0)[: a.gB]
             g[z * a.n_rows: z * a.n_rows + a.N, kb * KB:(kb + 1) * KB] += torch.einsum("bhwn,bhwk->nk", d, x)
     return 0
 
