@@ -74,7 +74,7 @@ class WgradArgs(C.Structure):
         ("n_src", i32), ("src", View * MAX_SRC), ("dz", vp), ("dsW", i64), ("dsH", i64), ("dsB", i64),
         ("doff", i64 * MAX_Z), ("gW", i32), ("gH", i32), ("gB", i32), ("tw", i32), ("th", i32), ("tb", i32),
         ("nz", i32), ("ngroups", i32), ("R", i32), ("sched", vp), ("N", i32), ("n_rows", i32), ("wgrad_packed", vp),
-        ("ksplit", i32),
+        ("ksplit", i32), ("slots", i32), ("slot_stride", i64),
     ]
 
 
@@ -114,6 +114,7 @@ SIGNATURES = {
     "ccdm_pack_weights_t": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, vp, vp]),
     "ccdm_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), vp]),
     "ccdm_unpack_wgrad": (C.c_int, [vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, i32, vp]),
+    "ccdm_unpack_wgrad_slots": (C.c_int, [vp, i32, i64, vp, i32, i32, i32, vp, i32, i32, i32, vp, f32, i32, vp]),
     "ccdm_block_bwd": (C.c_int, [vp, vp, vp, i64, i32, i32, vp, f32, vp, i32, i32, vp, C.c_uint32, vp]),
     "ccdm_block_bwd_finish": (C.c_int, [vp, i32, i32, vp, f32, vp, i32, i32, vp, vp, vp, vp]),
     "ccdm_colsum_bf16": (C.c_int, [vp, i64, i32, vp, vp]),

@@ -256,6 +256,26 @@ class ZeroArena:
 ARENA = ZeroArena()
 
 
+class Scratch:
+    """Un-initialised fp32 scratch that dies inside the node that asked for it (the partial weight gradients of one
+    convolution: written by ccdm_conv_wgrad, summed by ccdm_unpack_wgrad_slots right after, on the same stream).  ONE buffer
+    per device, grown to the largest request -- stream order keeps consecutive users apart, and its address is stable once
+    grown, which CUDA-graph capture needs (the warm-up steps before capture see every request size)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def take(self, n: int, device) -> torch.Tensor:
+        b = self.buf.get(device)
+        if b is None or b.numel() < n:
+            b = torch.empty(n + n // 8, dtype=torch.float32, device=device)
+            self.buf[device] = b
+        return b[:n]
+
+
+SCRATCH = Scratch()
+
+
 class PackCache:
     """Persistent packed bf16 copies of the convolution weights of the TRAINING path (forward layout and the transposed layout of
     the data gradient) plus the job table of ``ccdm_pack_multi``: ``begin_step`` re-packs every known weight in ONE launch
@@ -321,11 +341,38 @@ def _plan_cached_stem(cout: int) -> ConvPlan:
     return plan_conv("stem7", (64,), cout)
 
 
+def _sm_count(dev) -> int:
+    return torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 148
+
+
+def wgrad_slots(plan: ConvPlan, tile, gw: int, gh: int, gb: int, cout: int, dev) -> int:
+    """Position slices (split-K CTAs per unit) of one weight-gradient launch: about one wave of CTAs, as the library's own
+    default -- computed here because in PARTIAL mode (ccdm_wgrad_args.slots) the caller owns one gradient slot per slice."""
+    tw, th, tb = tile
+    tiles_m = -(-gw // tw) * -(-gh // th) * -(-gb // tb)
+    if plan.halo:
+        n_tiles = -(-cout // 96)
+        n_tile = (-(-cout // n_tiles) + 15) // 16 * 16
+        units = plan.ngroups * -(-cout // n_tile)
+    else:
+        units = plan.nz * plan.ngroups * -(-cout // 128)
+    return max(1, min(_sm_count(dev) // units, tiles_m))
+
+
 def wgrad_packed(plan: ConvPlan, tile, views: List[L.View], dz: torch.Tensor, gw: int, gh: int, sched: torch.Tensor,
-                 cout: int, n_rows: int, ksplit: int = 0, timing: Optional[list] = None) -> torch.Tensor:
-    """fp32 [nz*n_rows, nkb*64] weight gradient in the packed layout of the forward weights (ccdm_conv_wgrad)."""
+                 cout: int, n_rows: int, ksplit: int = 0, timing: Optional[list] = None, partial: bool = False):
+    """fp32 weight gradient in the packed layout of the forward weights (ccdm_conv_wgrad).  ``partial`` = False: ONE
+    [nz*n_rows, nkb*64] accumulator (pre-zeroed arena memory, red.global.add from every position slice).  ``partial`` = True:
+    returns (buffer, nslots, slot_stride): every slice STORES its partial into its own slot (nothing to zero, no atomics)
+    and ccdm_unpack_wgrad_slots sums them -- the red.add throughput of L2 bounded the split-K layers."""
     dev = dz.device
-    gpacked = ARENA.zeros(plan.nz * n_rows * plan.nkb * KB, dev).view(plan.nz * n_rows, plan.nkb * KB)
+    size = plan.nz * n_rows * plan.nkb * KB
+    slots = wgrad_slots(plan, tile, gw, gh, dz.shape[0], cout, dev) if partial else 0
+    if partial:
+        stride = (size + 63) // 64 * 64
+        gpacked = SCRATCH.take(slots * stride, dev)
+    else:
+        gpacked = ARENA.zeros(size, dev).view(plan.nz * n_rows, plan.nkb * KB)
     a = L.WgradArgs()
     a.n_src = len(views)
     for i, v in enumerate(views):
@@ -341,6 +388,7 @@ def wgrad_packed(plan: ConvPlan, tile, views: List[L.View], dz: torch.Tensor, gw
     a.N, a.n_rows = cout, n_rows
     a.wgrad_packed = gpacked.data_ptr()
     a.ksplit = ksplit
+    a.slots, a.slot_stride = (slots, stride) if partial else (0, 0)
     if timing is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -348,7 +396,7 @@ def wgrad_packed(plan: ConvPlan, tile, views: List[L.View], dz: torch.Tensor, gw
     if timing is not None:
         ev1.record()
         timing.append((ev0, ev1))
-    return gpacked
+    return (gpacked, slots, stride) if partial else gpacked
 
 
 def conv_wgrad(kind: str, srcs: Sequence[torch.Tensor], dz: torch.Tensor, ksplit: int = 0,
@@ -369,12 +417,12 @@ def conv_wgrad(kind: str, srcs: Sequence[torch.Tensor], dz: torch.Tensor, ksplit
     views: List[L.View] = []
     for s in srcs:
         views += _parity_views(s) if plan.n_views == 4 else [_view(s)]
-    gpacked = wgrad_packed(plan, tile, views, dz, gw, gh, sched, cout, n_rows, ksplit, timing)
+    gpacked, nslots, stride = wgrad_packed(plan, tile, views, dz, gw, gh, sched, cout, n_rows, ksplit, timing, partial=True)
     k = int(math.isqrt(_KIND_TAPS[kind]))
     dw = accumulate_into if accumulate_into is not None else torch.empty(cout, sum(cins), k, k, dtype=torch.float32, device=dev)
-    L.check(L.lib().ccdm_unpack_wgrad(gpacked.data_ptr(), dw.data_ptr(), cout, sum(cins), _KIND_TAPS[kind],
-                                      psched.data_ptr(), plan.nz, plan.nkb, n_rows, None, 1.0,
-                                      1 if accumulate_into is not None else 0, _stream()), "unpack_wgrad")
+    L.check(L.lib().ccdm_unpack_wgrad_slots(gpacked.data_ptr(), nslots, stride, dw.data_ptr(), cout, sum(cins),
+                                            _KIND_TAPS[kind], psched.data_ptr(), plan.nz, plan.nkb, n_rows, None, 1.0,
+                                            1 if accumulate_into is not None else 0, _stream()), "unpack_wgrad")
     return dw
 
 

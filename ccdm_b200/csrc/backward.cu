@@ -16,24 +16,6 @@ constexpr int kBwdMaxC = 1024;
 constexpr int bwd_stages(int chunks) { return chunks == 1 ? 6 : chunks == 2 ? 4 : 3; }
 
 // G lanes share one row; each owns kChunks chunks of 8 channels (see row_lane_plan); kMinCtas resident CTAs per SM
-// Sum over the G lanes of a row segment, broadcast to all of them; branch-free (the generic seg_sum loops over a run-time G).
-__device__ __forceinline__ float bwd_seg_sum(float v, int gl, int G, int lane) {
-  if ((G & (G - 1)) == 0) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float o = __shfl_xor_sync(0xffffffffu, v, off);
-      v += off < G ? o : 0.f;
-    }
-    return v;
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const float o = __shfl_down_sync(0xffffffffu, v, off);
-    v += gl + off < G ? o : 0.f;
-  }
-  return __shfl_sync(0xffffffffu, v, lane - gl);
-}
-
 template <int kChunks, int kMinCtas, bool kSilu>
 __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ z,
                                                                           uint4* __restrict__ dz, int rows_per_sample,
@@ -113,7 +95,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const 
     }
     if (++st_rd == kStages) st_rd = 0;
     if (++st_wr == kStages) st_wr = 0;
-    const float sq = bwd_seg_sum(sq2.x + sq2.y, gl, G, lane);
+    const float sq = seg_sum(sq2.x + sq2.y, gl, G, lane);
     const float inv = rsqrtf(fmaxf(sq, 1e-24f));                   // 1 / max(|z|, 1e-12)
     const float2 inv2 = make_float2(inv, inv);
     const float2 one2 = make_float2(1.f, 1.f), half2 = make_float2(0.5f, 0.5f);
@@ -152,7 +134,7 @@ __global__ void __launch_bounds__(kBwdThreads, kMinCtas) block_bwd_kernel(const 
         gy[k][j] = dzh;
       }
     }
-    const float dot = bwd_seg_sum(dot2.x + dot2.y, gl, G, lane);
+    const float dot = seg_sum(dot2.x + dot2.y, gl, G, lane);
     const float2 ndot2 = make_float2(-dot, -dot);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {

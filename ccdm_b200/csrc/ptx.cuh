@@ -358,16 +358,22 @@ __device__ __forceinline__ float tanh_silu(float h) {
 // sigmoid(x) = 0.5 + 0.5 tanh(x/2): one MUFU, no division
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
-// Sum over the G lanes of a row segment, broadcast to all of them.  Power-of-two G: xor butterfly.
+// Sum over the G lanes of a row segment, broadcast to all of them.  Power-of-two G: xor butterfly.  Branch-free: five
+// fixed shuffle steps whose contribution is masked (a loop over the run-time G compiled to a divergent-capable loop with
+// BRA.DIV per step and showed up in the row kernels' issue budget).
 __device__ __forceinline__ float seg_sum(float v, int gl, int G, int lane) {
   if ((G & (G - 1)) == 0) {
-    for (int off = G >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float o = __shfl_xor_sync(0xffffffffu, v, off);
+      v += off < G ? o : 0.f;
+    }
     return v;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     const float o = __shfl_down_sync(0xffffffffu, v, off);
-    if (gl + off < G) v += o;
+    v += gl + off < G ? o : 0.f;
   }
   return __shfl_sync(0xffffffffu, v, lane - gl);
 }

@@ -52,7 +52,8 @@ struct WgDev {
   float* out;
   int ngroups, R, nkb, m_tiles, n_rows;
   int tw, th, tb, tiles_w, tiles_h, tiles_m, tiles_per_cta;
-  int stages, N;
+  int stages, N, partial;
+  long long slot_stride;
   uint32_t b_bytes, stage_bytes;
 };
 
@@ -167,25 +168,43 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
       if (elect_one()) umma_commit(&aux->acc_full);
       __syncwarp();
     }
-  } else if (t1 > t0) {
+  } else if (t1 > t0 || p.partial) {
     // ---------------------------------------------------------------- epilogue: TMEM lane = (tap of the pair, ci), column = co
+    // partial mode: plain stores into this slice's slot (zeros when the slice has no positions); else red.global.add --
+    // whose throughput at L2 (one fp32 per clock and slice), not the tensor pipe, bounded the split-K layers: ~150 CTAs x
+    // 37 k elements onto the same 37 k addresses cost 30-40 us of a 67 us launch.
     const int q = warp & 3;
     const int half = q >> 1, ci = (q & 1) * 32 + lane;
-    mbar_wait(&aux->acc_full, 0);
-    tc_fence_after();
+    const bool have = t1 > t0;
+    if (have) {
+      mbar_wait(&aux->acc_full, 0);
+      tc_fence_after();
+    }
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const size_t row_ld = (size_t)p.nkb * 64;
+    float* const out = p.out + (p.partial ? (size_t)blockIdx.x * (size_t)p.slot_stride : 0);
     for (int pr = 0; pr < (p.R + 1) / 2; ++pr) {
       const int tap = wg_pair_t0(p.R, pr) + half;
       if (tap >= p.R || tap < 2 * pr) continue;                    // unused half (R = 1) or the duplicate of pair (1,2)
-      float* obase = p.out + ((size_t)z * p.n_rows + (size_t)mt * 128) * row_ld + (size_t)(g * p.R + tap) * 64 + ci;
+      float* obase = out + ((size_t)z * p.n_rows + (size_t)mt * 128) * row_ld + (size_t)(g * p.R + tap) * 64 + ci;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(trow + pr * 128 + c0, v);
-        tmem_ld_wait();
+        if (have) {
+          tmem_ld32(trow + pr * 128 + c0, v);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < n_here) atomicAdd(obase + (size_t)(c0 + i) * row_ld, __uint_as_float(v[i]));   // RED, 128 B per warp
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (p.partial) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < n_here) obase[(size_t)(c0 + i) * row_ld] = __uint_as_float(v[i]);           // 128 B per warp
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < n_here) atomicAdd(obase + (size_t)(c0 + i) * row_ld, __uint_as_float(v[i]));   // RED
+        }
       }
     }
     tc_fence_before();
@@ -221,7 +240,8 @@ struct WhDev {
   float* out;
   int ngroups, nkb, n_tiles, n_tile, n_rows, N;
   int tiles_w, tiles_h, tiles_m, tiles_per_cta;
-  int stages, dz_blocks;
+  int stages, dz_blocks, partial;
+  long long slot_stride;
   uint32_t stage_bytes;
 };
 
@@ -327,25 +347,41 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_halo_kernel(const __
       if (elect_one()) umma_commit(&aux->acc_full);
       __syncwarp();
     }
-  } else if (t1 > t0) {
+  } else if (t1 > t0 || p.partial) {
     // ---------------------------------------------------------------- epilogue: TMEM lane = (tap of the pair, ci), column = co
+    // (partial mode / red.add: see conv_wgrad_kernel)
     const int q = warp & 3;
     const int half = q >> 1, ci = (q & 1) * 32 + lane;
-    mbar_wait(&aux->acc_full, 0);
-    tc_fence_after();
+    const bool have = t1 > t0;
+    if (have) {
+      mbar_wait(&aux->acc_full, 0);
+      tc_fence_after();
+    }
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const size_t row_ld = (size_t)p.nkb * 64;
+    float* const out = p.out + (p.partial ? (size_t)blockIdx.x * (size_t)p.slot_stride : 0);
     for (int pr = 0; pr < 5; ++pr) {
       const int tap = pr < 3 ? pr + 3 * half : (pr == 3 ? 6 + half : (half == 0 ? 8 : -1));
       if (tap < 0) continue;
-      float* obase = p.out + ((size_t)z * p.n_rows + (size_t)n0) * row_ld + (size_t)(g * 9 + tap) * 64 + ci;
+      float* obase = out + ((size_t)z * p.n_rows + (size_t)n0) * row_ld + (size_t)(g * 9 + tap) * 64 + ci;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(trow + pr * kWhAccStride + c0, v);
-        tmem_ld_wait();
+        if (have) {
+          tmem_ld32(trow + pr * kWhAccStride + c0, v);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < n_here) atomicAdd(obase + (size_t)(c0 + i) * row_ld, __uint_as_float(v[i]));   // RED, 128 B per warp
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (p.partial) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < n_here) obase[(size_t)(c0 + i) * row_ld] = __uint_as_float(v[i]);           // 128 B per warp
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < n_here) atomicAdd(obase + (size_t)(c0 + i) * row_ld, __uint_as_float(v[i]));   // RED
+        }
       }
     }
     tc_fence_before();
@@ -361,8 +397,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_halo_kernel(const __
 // dW[n][cin0+j][t] += gain * packed[z][n][kb*64 + j] for every tap t in the block's tapmask (scatter; dW zeroed or
 // accumulated by the caller -- the folded taps of the nearest-2x convolution land on the same element from several
 // blocks, hence atomics)
-__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ dw, int cout, int cin_total,
-                                    int ntaps, const int4* __restrict__ psched, int nkb, int n_rows,
+__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int nslots, long long slot_stride,
+                                    float* __restrict__ dw, int cout, int cin_total, int ntaps,
+                                    const int4* __restrict__ psched, int nkb, int n_rows,
                                     const float* __restrict__ cin_gain, float gain_mul, long long total) {
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -375,7 +412,9 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
     const int4 e = __ldg(&psched[z * nkb + kb]);
     if (n >= cout || j >= e.y) continue;
     const int ci = e.x + j;
-    const float v = packed[idx] * gain_mul * (cin_gain ? cin_gain[ci] : 1.f);
+    float acc = 0.f;
+    for (int sl = 0; sl < nslots; ++sl) acc += packed[(long long)sl * slot_stride + idx];   // fixed order: reproducible
+    const float v = acc * gain_mul * (cin_gain ? cin_gain[ci] : 1.f);
     float* dst = dw + ((long long)n * cin_total + ci) * ntaps;
     unsigned mask = (unsigned)e.z;
     while (mask) {
@@ -428,6 +467,9 @@ extern "C" int ccdm_conv_wgrad(const ccdm_wgrad_args* a, void* stream) {
   CCDM_REQUIRE(a->N >= 1 && a->N % 8 == 0 && a->n_rows >= a->N, CCDM_ERR_UNSUPPORTED_SHAPE, "conv_wgrad: N=%d n_rows=%d",
                a->N, a->n_rows);
   CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->wgrad_packed) & 15) == 0, CCDM_ERR_BAD_ARG, "conv_wgrad: output alignment");
+  CCDM_REQUIRE(a->slots >= 0 && a->slots <= 65535 &&
+                   (a->slots == 0 || a->slot_stride >= (int64_t)a->nz * a->n_rows * a->ngroups * a->R * 64),
+               CCDM_ERR_BAD_ARG, "conv_wgrad: slots=%d slot_stride=%lld", a->slots, (long long)a->slot_stride);
   const bool halo = a->R == 9;                                     // plan_conv(halo=True): one box, nine taps
   CCDM_REQUIRE(a->R <= 3 || (halo && a->tw == 8 && a->th == 16 && a->tb == 1 && a->nz == 1), CCDM_ERR_BAD_ARG,
                "conv_wgrad: R=%d needs the 8 x 16 x 1 halo tile and nz == 1", a->R);
@@ -472,11 +514,13 @@ extern "C" int ccdm_conv_wgrad(const ccdm_wgrad_args* a, void* stream) {
     h.tiles_h = (a->gH + 15) / 16;
     h.tiles_m = h.tiles_w * h.tiles_h * a->gB;
     const int units = a->ngroups * h.n_tiles;
-    int ksplit = a->ksplit > 0 ? a->ksplit : num_sms() / units;
+    int ksplit = a->slots > 0 ? a->slots : (a->ksplit > 0 ? a->ksplit : num_sms() / units);
     if (ksplit < 1) ksplit = 1;
-    if (ksplit > h.tiles_m) ksplit = h.tiles_m;
+    if (ksplit > h.tiles_m && a->slots == 0) ksplit = h.tiles_m;
     h.tiles_per_cta = (h.tiles_m + ksplit - 1) / ksplit;
-    ksplit = (h.tiles_m + h.tiles_per_cta - 1) / h.tiles_per_cta;
+    if (a->slots == 0) ksplit = (h.tiles_m + h.tiles_per_cta - 1) / h.tiles_per_cta;
+    h.partial = a->slots > 0;
+    h.slot_stride = a->slot_stride;
     h.dz_blocks = h.n_tile > 64 ? 2 : 1;
     h.stage_bytes = (uint32_t)h.dz_blocks * kWgABlock + kWhXSlot;
     const int max_stages = h.dz_blocks == 2 ? 3 : 4;
@@ -504,11 +548,13 @@ extern "C" int ccdm_conv_wgrad(const ccdm_wgrad_args* a, void* stream) {
   p.tiles_h = (a->gH + a->th - 1) / a->th;
   p.tiles_m = p.tiles_w * p.tiles_h * ((a->gB + a->tb - 1) / a->tb);
   const int units = a->nz * a->ngroups * p.m_tiles;
-  int ksplit = a->ksplit > 0 ? a->ksplit : num_sms() / units;      // split-K so that about one wave of CTAs runs
+  int ksplit = a->slots > 0 ? a->slots : (a->ksplit > 0 ? a->ksplit : num_sms() / units);   // about one wave of CTAs
   if (ksplit < 1) ksplit = 1;
-  if (ksplit > p.tiles_m) ksplit = p.tiles_m;
+  if (ksplit > p.tiles_m && a->slots == 0) ksplit = p.tiles_m;
   p.tiles_per_cta = (p.tiles_m + ksplit - 1) / ksplit;
-  ksplit = (p.tiles_m + p.tiles_per_cta - 1) / p.tiles_per_cta;    // no CTA without work
+  if (a->slots == 0) ksplit = (p.tiles_m + p.tiles_per_cta - 1) / p.tiles_per_cta;    // no CTA without work (partial mode:
+  p.partial = a->slots > 0;                                                            // such a slice stores zeros)
+  p.slot_stride = a->slot_stride;
   p.N = a->N;
   p.b_bytes = (uint32_t)(box_h * a->tw * a->tb) * 128u;
   p.stage_bytes = 2 * kWgABlock + p.b_bytes;
@@ -527,24 +573,34 @@ extern "C" int ccdm_conv_wgrad(const ccdm_wgrad_args* a, void* stream) {
   return after_launch("conv_wgrad_kernel");
 }
 
-extern "C" int ccdm_unpack_wgrad(const float* packed, float* dw, int32_t cout, int32_t cin_total, int32_t ntaps,
-                                 const int32_t* psched, int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain,
-                                 float gain_mul, int32_t accumulate, void* stream) {
+extern "C" int ccdm_unpack_wgrad_slots(const float* packed, int32_t nslots, int64_t slot_stride, float* dw, int32_t cout,
+                                       int32_t cin_total, int32_t ntaps, const int32_t* psched, int32_t nz, int32_t nkb,
+                                       int32_t n_rows, const float* cin_gain, float gain_mul, int32_t accumulate,
+                                       void* stream) {
   CCDM_REQUIRE(packed && dw && psched, CCDM_ERR_BAD_ARG, "unpack_wgrad: null pointer");
   CCDM_REQUIRE(cout > 0 && cin_total > 0 && ntaps > 0 && ntaps <= 32 && nz > 0 && nkb > 0 && n_rows >= cout,
                CCDM_ERR_BAD_ARG, "unpack_wgrad: bad sizes");
+  const long long total = (long long)nz * n_rows * nkb * 64;
+  CCDM_REQUIRE(nslots >= 1 && (nslots == 1 || slot_stride >= total), CCDM_ERR_BAD_ARG,
+               "unpack_wgrad: nslots=%d slot_stride=%lld", nslots, (long long)slot_stride);
   cudaStream_t s = (cudaStream_t)stream;
   if (!accumulate) {
     cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)cout * cin_total * ntaps * sizeof(float), s);
     if (e != cudaSuccess) return cuda_fail(e, "unpack_wgrad: cudaMemsetAsync");
   }
-  const long long total = (long long)nz * n_rows * nkb * 64;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_wgrad_kernel<<<(unsigned)blocks, 256, 0, s>>>(packed, dw, cout, cin_total, ntaps,
+  unpack_wgrad_kernel<<<(unsigned)blocks, 256, 0, s>>>(packed, nslots, (long long)slot_stride, dw, cout, cin_total, ntaps,
                                                        reinterpret_cast<const int4*>(psched), nkb, n_rows, cin_gain,
                                                        gain_mul, total);
   return after_launch("unpack_wgrad_kernel");
+}
+
+extern "C" int ccdm_unpack_wgrad(const float* packed, float* dw, int32_t cout, int32_t cin_total, int32_t ntaps,
+                                 const int32_t* psched, int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain,
+                                 float gain_mul, int32_t accumulate, void* stream) {
+  return ccdm_unpack_wgrad_slots(packed, 1, 0, dw, cout, cin_total, ntaps, psched, nz, nkb, n_rows, cin_gain, gain_mul,
+                                 accumulate, stream);
 }
 
 extern "C" int ccdm_pack_weights_t(const float* w, int32_t cout, int32_t cin_total, int32_t ntaps, const int32_t* psched,

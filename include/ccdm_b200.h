@@ -353,6 +353,12 @@ typedef struct ccdm_wgrad_args {
   int32_t N, n_rows;
   float* wgrad_packed;
   int32_t ksplit;
+  /* slots > 0: PARTIAL mode.  Exactly `slots` position slices are launched (ksplit is ignored) and slice s STORES its
+   * partial gradient (no atomics, no pre-zeroed buffer; a slice without positions stores zeros) at
+   * wgrad_packed + s*slot_stride; ccdm_unpack_wgrad_slots sums the slices in a fixed order (bit-reproducible).
+   * slots == 0: every slice adds into wgrad_packed with red.global.add (buffer zeroed or accumulated by the caller). */
+  int32_t slots;
+  int64_t slot_stride;
 } ccdm_wgrad_args;
 int ccdm_conv_wgrad(const ccdm_wgrad_args* args, void* stream);
 /* Packed gradient -> dW[cout][cin_total][ntaps] (= or +=): every (ci, t) gathers the packed blocks that hold it
@@ -360,6 +366,10 @@ int ccdm_conv_wgrad(const ccdm_wgrad_args* args, void* stream);
 int ccdm_unpack_wgrad(const float* packed, float* dw, int32_t cout, int32_t cin_total, int32_t ntaps,
                       const int32_t* psched, int32_t nz, int32_t nkb, int32_t n_rows, const float* cin_gain,
                       float gain_mul, int32_t accumulate, void* stream);
+/* Same, over `nslots` partial gradients `slot_stride` elements apart (ccdm_wgrad_args.slots), summed in slot order. */
+int ccdm_unpack_wgrad_slots(const float* packed, int32_t nslots, int64_t slot_stride, float* dw, int32_t cout,
+                            int32_t cin_total, int32_t ntaps, const int32_t* psched, int32_t nz, int32_t nkb,
+                            int32_t n_rows, const float* cin_gain, float gain_mul, int32_t accumulate, void* stream);
 
 /* Backward of the Block tail (unet.py:88-89,145-151): with zh = z/max(|z|,1e-12), n = zh*gain*gain_mul,
  * u = n*(1+scale[b]) + shift[b], y = silu(u):

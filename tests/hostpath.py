@@ -33,7 +33,7 @@ class HostLib:
         handles = [C.CDLL(build(f)) for f in ("kernels.cu", "train_kernels.cu", "backward.cu", "sampler.cu", "groupnorm.cu",
                                               "optim.cu", "packmulti.cu")]
         handles.append(C.CDLL(build_extract("wgrad.cu", ["unpack_wgrad_kernel", "pack_weights_t_kernel"],
-                                            ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"])))
+                                            ["ccdm_unpack_wgrad_slots", "ccdm_unpack_wgrad", "ccdm_pack_weights_t"])))
         handles.append(C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights_at", "ccdm_pack_weights"])))
         handles.append(C.CDLL(build_extract("linattn.cu", ["kexp_bound_kernel"], ["ccdm_kexp_bound"])))
         handles.append(C.CDLL(build_extract("linattn_fused.cu", ["linattn_fold_parts_kernel"], ["ccdm_linattn_fold_partials"])))
@@ -173,7 +173,12 @@ def wgrad_abi(argref, stream):
     doff = [a.doff[i] for i in range(L.MAX_Z)]
     span = max(doff[:a.nz]) + (a.gB - 1) * a.dsB + (a.gH - 1) * a.dsH + (a.gW - 1) * a.dsW + a.N
     dz_flat = _flat(a.dz, span, torch.bfloat16)
-    g = _flat(a.wgrad_packed, a.nz * a.n_rows * plan.nkb * KB, torch.float32).reshape(a.nz * a.n_rows, plan.nkb * KB)
+    size = a.nz * a.n_rows * plan.nkb * KB
+    if a.slots > 0:          # PARTIAL mode: slice s stores at s*slot_stride (no pre-zeroed buffer): slice 0 gets the sum here
+        allb = _flat(a.wgrad_packed, (a.slots - 1) * a.slot_stride + size, torch.float32)
+        for sl in range(a.slots):
+            allb[sl * a.slot_stride: sl * a.slot_stride + size].zero_()
+    g = _flat(a.wgrad_packed, size, torch.float32).reshape(a.nz * a.n_rows, plan.nkb * KB)
     for z in range(a.nz):
         d = torch.as_strided(dz_flat, (a.gB, a.gH, a.gW, a.N), (a.dsB, a.dsH, a.dsW, 1), doff[z]).float()
         for kb in range(plan.nkb):
