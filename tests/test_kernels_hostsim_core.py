@@ -425,8 +425,9 @@ def packlib():
     from tests.hostsim.build import build_extract
     a = C.CDLL(build_extract("tapgemm.cu", ["pack_weights_kernel"], ["ccdm_pack_weights_at", "ccdm_pack_weights"]))
     b = C.CDLL(build_extract("wgrad.cu", ["unpack_wgrad_kernel", "pack_weights_t_kernel"],
-                             ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"]))
-    for h, names in ((a, ["ccdm_pack_weights", "ccdm_pack_weights_at"]), (b, ["ccdm_unpack_wgrad", "ccdm_pack_weights_t"])):
+                             ["ccdm_unpack_wgrad_slots", "ccdm_unpack_wgrad", "ccdm_pack_weights_t"]))
+    for h, names in ((a, ["ccdm_pack_weights", "ccdm_pack_weights_at"]),
+                     (b, ["ccdm_unpack_wgrad", "ccdm_unpack_wgrad_slots", "ccdm_pack_weights_t"])):
         for n in names:
             fn = getattr(h, n)
             fn.restype, fn.argtypes = L.SIGNATURES[n]
@@ -557,3 +558,32 @@ def test_pack_multi_and_pack_at_match_the_single_tensor_kernels(packlib):
     assert torch.equal(both, want.to(torch.bfloat16))
     assert pk.ccdm_pack_weights_at(w1.data_ptr(), 32, 48, 1, p1.data_ptr(), 1, sc.nkb, 32, None, 1.0, both.data_ptr(),
                                    main.nkb, main.nkb, None) == -1                       # K blocks out of range
+
+
+def test_unpack_wgrad_slots_sums_partial_gradients_in_order(packlib):
+    """ccdm_unpack_wgrad_slots over three partial gradients (ccdm_wgrad_args.slots, padded slot stride) equals
+    ccdm_unpack_wgrad of their sum -- for the halo plan's K-block order too (tap (r, q) = block g*9 + r*3 + q)."""
+    from ccdm_b200.plan import KB, plan_conv
+    _, wg = packlib
+    g = torch.Generator().manual_seed(21)
+    for plan in (plan_conv("3x3", (72,), 40, halo=True), plan_conv("3x3", (40, 24), 24, reuse_rows=True)):
+        cout, cin = plan.cout, sum(plan.cins)
+        n_rows = (cout + 31) // 32 * 32
+        size = plan.nz * n_rows * plan.nkb * KB
+        stride = size + 192
+        parts = torch.randn(3, stride, generator=g)
+        ps = _i32(plan.psched)
+        got = torch.empty(cout, cin, 3, 3)
+        assert wg.ccdm_unpack_wgrad_slots(parts.data_ptr(), 3, stride, got.data_ptr(), cout, cin, 9, ps.data_ptr(), plan.nz,
+                                          plan.nkb, n_rows, None, 1.0, 0, None) == 0
+        total = ((parts[0, :size] + parts[1, :size]) + parts[2, :size]).contiguous()
+        want = torch.empty_like(got)
+        assert wg.ccdm_unpack_wgrad(total.data_ptr(), want.data_ptr(), cout, cin, 9, ps.data_ptr(), plan.nz, plan.nkb, n_rows,
+                                    None, 1.0, 0, None) == 0
+        assert torch.equal(got, want)
+        acc = torch.ones_like(got)                                 # accumulate = 1 adds to what is there
+        assert wg.ccdm_unpack_wgrad_slots(parts.data_ptr(), 3, stride, acc.data_ptr(), cout, cin, 9, ps.data_ptr(), plan.nz,
+                                          plan.nkb, n_rows, None, 1.0, 1, None) == 0
+        assert torch.allclose(acc, want + 1, atol=1e-6)
+        assert wg.ccdm_unpack_wgrad_slots(parts.data_ptr(), 3, size - 1, got.data_ptr(), cout, cin, 9, ps.data_ptr(), plan.nz,
+                                          plan.nkb, n_rows, None, 1.0, 0, None) != 0      # slots must not overlap
