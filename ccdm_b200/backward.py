@@ -92,6 +92,25 @@ def _wgrad_plan_for(kind, cins, cout, gw, gh):
     return _plan_cached(kind, cins, cout, gw, gh)
 
 
+TRAIN_HALO = os.environ.get("CCDM_TRAIN_HALO", "1") != "0"       # A/B switch
+
+
+@functools.lru_cache(maxsize=None)
+def _conv_plan_for(kind, cins, cout, gw, gh):
+    """Plan of a training-mode forward convolution or data gradient: 3x3 layers whose (pair-split) weights stay resident in
+    shared memory take the halo plan (one box per 64-channel block and tile instead of three), under the inference engine's
+    criterion.  Measured (profiles/r2_notes.md): 64 -> 64 at 64x64, batch 128: forward 57 -> 51 us, data gradient 57 -> 54 us;
+    the 72-channel layers, whose 108 KB of weights only fit next to three boxes without the second output staging buffer,
+    LOSE with it (forward 116 -> 145 us) and stay on the three-box plan."""
+    base = kind[:-6] if kind.endswith("_dgrad") else kind
+    if TRAIN_HALO and halo_ok(base, gw, gh) and cout <= 128:
+        nkb = 9 * sum(-(-c // KB) for c in cins)
+        resident = nkb * ((cout + 31) // 32 * 32) * 128 // (2 if nkb >= 16 else 1)
+        if resident <= 96 * 1024:
+            return plan_conv(kind, cins, cout, halo=True), HALO_TILE
+    return _plan_cached(kind, cins, cout, gw, gh)
+
+
 def _launch_tapgemm(plan: ConvPlan, tile, views: List[L.View], gw, gh, gb, wpacked, sched, n_rows, n, n_tile, out,
                     ostr, ooff, bias=None, resid: Optional[torch.Tensor] = None, w_batch_rows: int = 0, out_c_off: int = 0,
                     flags: int = 0, ss: Optional[torch.Tensor] = None):
@@ -102,6 +121,7 @@ def _launch_tapgemm(plan: ConvPlan, tile, views: List[L.View], gw, gh, gb, wpack
     a.gW, a.gH, a.gB = gw, gh, gb
     a.tw, a.th, a.tb = tile
     a.nz, a.ngroups, a.R = plan.nz, plan.ngroups, plan.R
+    a.halo = int(plan.halo)
     a.sched, a.wpacked = sched.data_ptr(), wpacked.data_ptr()
     a.n_rows, a.w_batch_rows, a.N, a.n_tile = n_rows, w_batch_rows, n, n_tile
     a.flags = flags | (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESID if resid is not None else 0)
@@ -137,7 +157,7 @@ def conv_forward(kind: str, srcs: Sequence[torch.Tensor], weight: torch.Tensor, 
     oh, ow = {"1x1": (h, w), "3x3": (h, w), "down4x4s2": (h // 2, w // 2), "down3x3s2": ((h + 1) // 2, (w + 1) // 2),
               "up2x3x3": (2 * h, 2 * w)}[kind]
     gh, gw = (h, w) if kind == "up2x3x3" else (oh, ow)
-    plan, tile = _plan_for(kind, [s.shape[3] for s in srcs], cout, gw, gh)
+    plan, tile = _conv_plan_for(kind, tuple(s.shape[3] for s in srcs), cout, gw, gh)
     n_rows, n_tile = n_tiling(cout, False)
     dev = weight.device
     sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
@@ -204,7 +224,7 @@ def conv_dgrad(kind: str, dy: torch.Tensor, weight: torch.Tensor, cins: Sequence
     outs = []
     n_off = 0
     for cin in cins:
-        plan, tile = _plan_for(kind + "_dgrad", (cout,), cin, gw, gh)
+        plan, tile = _conv_plan_for(kind + "_dgrad", (cout,), cin, gw, gh)
         n_rows, n_tile = n_tiling(cin, False)
         sched, psched = _dev_i32(plan.sched, dev), _dev_i32(plan.psched, dev)
         packed, need = PACKS.get(weight, 1, kind, plan, n_rows, n_off, cin, psched)

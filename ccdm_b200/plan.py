@@ -204,11 +204,11 @@ def plan_conv(kind: str, cins: Sequence[int], cout: int, reuse_rows: bool = Fals
                 emit(s, s, 0, [(0, 1)])
         return ConvPlan(kind, cins, cout, 1, 4, len(sched) // 4, 1, sched, psched, out_parity=True)
     if kind.endswith("_dgrad"):
-        return _plan_dgrad(kind[:-6], cins, cout, reuse_rows, emit, sched, psched)
+        return _plan_dgrad(kind[:-6], cins, cout, reuse_rows, emit, sched, psched, halo)
     raise ValueError(kind)
 
 
-def _plan_dgrad(fwd_kind, cins, cout, reuse_rows, emit, sched, psched):
+def _plan_dgrad(fwd_kind, cins, cout, reuse_rows, emit, sched, psched, halo=False):
     """dX = conv^T(dY): `cins` = (forward Cout,) are the channels of dY, `cout` the forward input channels produced.
 
     3x3 / 1x1:  dx[h,w] = sum_{r,q} dy[h+1-r, w+1-q] W[r,q]           -> same taps with the filter flipped
@@ -220,6 +220,13 @@ def _plan_dgrad(fwd_kind, cins, cout, reuse_rows, emit, sched, psched):
     if fwd_kind == "1x1":
         emit(0, 0, 0, [(0, 1)])
         return ConvPlan("1x1_dgrad", cins, cout, 1, 1, len(sched), 1, sched, psched, transposed=True)
+    if fwd_kind == "3x3" and halo:                     # one halo box per 64-channel block of dy, flipped filter
+        for c0, nv in _chunks(cins[0]):
+            sched.append((0, -1, -1, c0))
+            for t in range(9):
+                r, q = divmod(t, 3)
+                psched.append((c0, nv, 1 << ((2 - r) * 3 + (2 - q)), 0))
+        return ConvPlan("3x3_dgrad", cins, cout, 9, 1, len(sched), 9, sched, psched, transposed=True, halo=True)
     if fwd_kind == "3x3":
         for q in range(3):
             emit(0, 0, q - 1, [(r - 1, 1 << ((2 - r) * 3 + (2 - q))) for r in range(3)])

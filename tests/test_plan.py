@@ -165,3 +165,22 @@ def test_halo_plan_equals_conv(cins, cout):
     got = tapgemm_emu(plan, srcs, w, H, W)[0]
     want = F.conv2d(torch.cat(srcs, -1).permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
     assert (got - want).abs().max() < 1e-3 * want.abs().max()
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (72, 72), (40, 96)])
+def test_halo_dgrad_plan_equals_autograd(cin, cout):
+    """Data gradient of a 3x3 conv on halo boxes (plan_conv('3x3_dgrad', halo=True): one box per 64-channel block of dy,
+    flipped filter taps), incl. the output-channel window of a concatenated forward input."""
+    torch.manual_seed(9)
+    H, W = 16, 8
+    x = torch.randn(2, cin, H, W)
+    w = torch.randn(cout, cin, 3, 3)
+    dy, dx = _dgrad_ref(lambda a, b: F.conv2d(a, b, padding=1), x, w)
+    plan = plan_conv("3x3_dgrad", (cout,), cin, halo=True)
+    assert plan.halo and plan.transposed and plan.R == 9 and plan.ngroups == -(-cout // 64)
+    got = tapgemm_emu(plan, [nhwc(dy)], w, H, W)[0]
+    assert rel(got, nhwc(dx)) < 1e-5
+    half = cin // 2
+    got2 = tapgemm_emu(plan_conv("3x3_dgrad", (cout,), cin - half, halo=True), [nhwc(dy)], w, H, W, n_off=half,
+                       n_count=cin - half)[0]
+    assert rel(got2, nhwc(dx)[..., half:]) < 1e-5
