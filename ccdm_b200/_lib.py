@@ -37,6 +37,7 @@ class TapGemmArgs(C.Structure):
         ("out_rowss", vp), ("q_scale", f32), ("q_cols", i32),
         ("halo", i32), ("n_res", i32), ("res_bias", vp),
         ("head_n", i32), ("head_w", vp), ("head_b", vp), ("head_out", vp), ("hsC", i64), ("hsB", i64),
+        ("ksteps", vp),
     ]
 
 

@@ -77,6 +77,7 @@ def _plan_cached(kind, cins, cout, gw, gh):
 
 
 WGRAD_HALO = os.environ.get("CCDM_WGRAD_HALO", "1") != "0"       # A/B switch
+KSTEPS = os.environ.get("CCDM_KSTEPS", "1") != "0"               # A/B switch: skip the empty K steps of partial channel blocks
 
 
 @functools.lru_cache(maxsize=None)
@@ -123,6 +124,7 @@ def _launch_tapgemm(plan: ConvPlan, tile, views: List[L.View], gw, gh, gb, wpack
     a.nz, a.ngroups, a.R = plan.nz, plan.ngroups, plan.R
     a.halo = int(plan.halo)
     a.sched, a.wpacked = sched.data_ptr(), wpacked.data_ptr()
+    a.ksteps = _dev_i32(plan.ksteps, sched.device).data_ptr() if (KSTEPS and plan.ksteps is not None) else None
     a.n_rows, a.w_batch_rows, a.N, a.n_tile = n_rows, w_batch_rows, n, n_tile
     a.flags = flags | (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESID if resid is not None else 0)
     a.bias = L.ptr(bias)

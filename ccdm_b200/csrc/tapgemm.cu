@@ -49,8 +49,10 @@ struct TapGemmDev {
   int ngroups, R, nkb, n_rows, N, n_tile, n_sub, nsub, stages, acc_stages, w_batch_rows, b_resident;
   int n_inner;                            // channel tiles walked by the SAME CTA per pixel tile (1: one per blockIdx.y)
   uint32_t a_bytes, stage_bytes, res_bytes, out_bytes;
+  uint32_t out_pitch;                     // dense-row output staging: bytes per pixel row (0: swizzled 64-channel panels)
   int tiles_per_cta, out_bufs, store_tma;
   const int4* sched;
+  const int* ksteps;                      // [nz * ngroups] K steps (16 channels each) that hold data per load group, or nullptr
   uint32_t flags, tmem_cols;
   const float *bias, *rowss, *gain, *ss;
   int ss_ld, ss_off;
@@ -114,7 +116,7 @@ __device__ __forceinline__ uint64_t umma_desc_lo_halo(uint32_t lo) {
 // kR vertically adjacent taps x 4 K-steps of one load group, fully unrolled (tap r: r*tw rows further down the box).
 template <int kR, bool kPair = false>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t tap16, uint32_t b16,
-                                           uint32_t idesc, bool first_group) {
+                                           uint32_t idesc, bool first_group, int nk = 4) {
   if constexpr (kR == 9) {                                 // halo box: 3 x 3 taps, 10-row image pitch (tw == 8)
     // One filter row (12 MMAs) per loop iteration: fully unrolled, the 72 descriptor words of a group overflow the uniform
     // register file and every R2UR.FILL of a spilled one stalls the issuing lane (26 % of its samples in ncu).
@@ -134,6 +136,24 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_lo, uint3
         }
         a_t += 8u;
         b_t += b16;
+      }
+    }
+    return;
+  }
+  if (nk != 4) {
+    // A load group whose 64-channel block is only partly real (72 = 64 + 8 channels: the dim-72 models) issues the K steps
+    // that hold data and nothing else -- one warp-uniform branch per GROUP (a predicate per instruction slowed the issuing
+    // lane by 10 %): 45 instead of 72 instructions per tile for a 72 -> 72 3x3 layer.
+#pragma unroll
+    for (int r = 0; r < kR; ++r) {
+#pragma unroll 1
+      for (int k = 0; k < nk; ++k) {
+        if (kPair)
+          umma_bf16_ss_2sm(d_tmem, umma_desc_lo(a_lo + r * tap16 + 2 * k), umma_desc_lo(b_lo + r * b16 + 2 * k), idesc,
+                           (r | k) != 0 ? 1u : (first_group ? 0u : 1u));
+        else
+          umma_bf16_ss(d_tmem, umma_desc_lo(a_lo + r * tap16 + 2 * k), umma_desc_lo(b_lo + r * b16 + 2 * k), idesc,
+                       (r | k) != 0 ? 1u : (first_group ? 0u : 1u));
       }
     }
     return;
@@ -164,7 +184,8 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
                                                   uint32_t stage16, uint32_t b_lo0, uint32_t tap16, uint32_t b16,
                                                   uint32_t idesc, uint32_t tmem_base, uint32_t n_tile, int acc_mask,
                                                   int acc_shift, uint32_t full_bar, uint32_t empty_bar,
-                                                  uint32_t tfull_bar, uint32_t tempty_bar, int n_res, uint32_t res_off) {
+                                                  uint32_t tfull_bar, uint32_t tempty_bar, int n_res, uint32_t res_off,
+                                                  const int* s_nk) {
   int s = 0;
   uint32_t ph = 0;
   uint32_t a_lo = a_lo0;
@@ -176,10 +197,11 @@ __device__ __forceinline__ void mma_loop_resident(int t_begin, int t_end, int n_
     const uint32_t d_tmem = tmem_base + as * n_tile;
     uint32_t b_lo = b_lo0;
     for (int g = 0; g < n_groups; ++g) {
+      const int nk = s_nk ? s_nk[g] : 4;                   // (read before the wait: its latency hides behind the barrier)
       mbar_wait_a(full_bar + 8 * s, ph);
       tc_fence_after();
       if (elect_one()) {
-        issue_taps<kR, kPair>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
+        issue_taps<kR, kPair>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0, nk);
         commit_bar<kPair>(empty_bar + 8 * s);
       }
       __syncwarp();
@@ -214,7 +236,7 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
                                               uint32_t nkb_b16, uint32_t tap16, uint32_t b16, uint32_t idesc,
                                               uint32_t tmem_base, uint32_t n_tile, int acc_mask, int acc_shift,
                                               uint32_t full_bar, uint32_t empty_bar, uint32_t tfull_bar,
-                                              uint32_t tempty_bar, int n_res, uint32_t res_off) {
+                                              uint32_t tempty_bar, int n_res, uint32_t res_off, const int* s_nk) {
   const int n_inner = kMultiN ? n_inner_rt : 1;             // compile-time 1 for the common case: no restore code
   int s = 0;
   uint32_t ph = 0;
@@ -237,12 +259,13 @@ __device__ __forceinline__ void mma_loop_fast(int t_begin, int t_end, int n_grou
       uint32_t b_lo = b_nt;
       const bool last_nt = !kMultiN || nt == n_inner - 1;
       for (int g = 0; g < n_groups; ++g) {
+        const int nk = s_nk ? s_nk[g] : 4;
         if (!kMultiN || nt == 0) {
           mbar_wait_a(full_bar + 8 * s, ph);
           tc_fence_after();
         }
         if (elect_one()) {
-          issue_taps<kR, kPair>(d_tmem, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0);
+          issue_taps<kR, kPair>(d_tmem, a_lo, kRes ? b_lo : a_lo + abytes16, tap16, b16, idesc, g == 0, nk);
           if (last_nt) commit_bar<kPair>(empty_bar + 8 * s);   // box reusable once the last MMAs have read it
         }
         __syncwarp();
@@ -339,6 +362,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   }
   // (residual groups follow the nz * ngroups main entries; they exist only with nz == 1)
   for (int i = tid; i < p.ngroups + p.n_res; i += kThreads) s_sched[i] = p.sched[z * p.ngroups + i];
+  int* const s_nk_tab = reinterpret_cast<int*>(s_sched + p.ngroups + p.n_res);
+  if (p.ksteps)
+    for (int i = tid; i < p.ngroups; i += kThreads) s_nk_tab[i] = min(4, max(1, p.ksteps[z * p.ngroups + i]));
+  const int* const s_nk = p.ksteps ? s_nk_tab : nullptr;
   tc_fence_before();
   __syncthreads();
   if constexpr (kPair) cluster_sync_all();                 // the peer's barriers are initialised before anyone signals them
@@ -469,15 +496,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 #define CCDM_MMA_LOOP(KR, RES, MULTI)                                                                                  \
   mma_loop_fast<KR, RES, MULTI>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo, nkb_b16, \
                                 tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, \
-                                tempty_bar, n_res, res_off)
+                                tempty_bar, n_res, res_off, s_nk)
       if constexpr (kPair) {                               // host guarantees: one channel tile per CTA, R <= 3
 #define CCDM_PAIR_RES(KR)                                                                                                 \
   mma_loop_resident<KR, true>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base, \
-                              n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off)
+                              n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_nk)
 #define CCDM_PAIR_STR(KR)                                                                                                 \
   mma_loop_fast<KR, false, false, true>(t_begin, t_end, n_groups, n_stages, n_inner, a_lo0, stage16, abytes16, b_res_lo,  \
                                         nkb_b16, tap16, b16, idesc, tmem_base, n_tile, acc_mask, acc_shift, full_bar,     \
-                                        empty_bar, tfull_bar, tempty_bar, n_res, res_off)
+                                        empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_nk)
         if (b_res) {
           if (R == 9) CCDM_PAIR_RES(9);
           else if (R == 3) CCDM_PAIR_RES(3);
@@ -496,16 +523,16 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       } else if (b_res) {
         if (R == 9)
           mma_loop_resident<9, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_nk);
         else if (R == 3)
           mma_loop_resident<3, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_nk);
         else if (R == 2)
           mma_loop_resident<2, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_nk);
         else
           mma_loop_resident<1, false>(t_begin, t_end, n_groups, n_stages, a_lo0, stage16, b_res_lo, tap16, b16, idesc, tmem_base,
-                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off);
+                               n_tile, acc_mask, acc_shift, full_bar, empty_bar, tfull_bar, tempty_bar, n_res, res_off, s_nk);
       } else {
         if (R == 9) CCDM_MMA_LOOP(9, false, false);
         else if (R == 3) CCDM_MMA_LOOP(3, false, false);
@@ -538,10 +565,11 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
           if (!b_res) b_lo = a_lo + abytes16;
           if (elect_one()) {
             if (one_sub) {
-              if (R == 3) issue_taps<3>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
-              else if (R == 1) issue_taps<1>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
-              else if (R == 2) issue_taps<2>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
-              else issue_taps<4>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0);
+              const int nk = s_nk ? s_nk[g] : 4;
+              if (R == 3) issue_taps<3>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0, nk);
+              else if (R == 1) issue_taps<1>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0, nk);
+              else if (R == 2) issue_taps<2>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0, nk);
+              else issue_taps<4>(d_tmem, a_lo, b_lo, tap16, b16, idesc, g == 0, nk);
             } else {
               for (int r = 0; r < R; ++r) {
 #pragma unroll
@@ -690,7 +718,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
                                ? p.ss + static_cast<long long>(bs) * p.ss_ld + p.ss_off + n0 : nullptr;
       const long long oo = p.ooff[z] + static_cast<long long>(bs) * p.osB + static_cast<long long>(h) * p.osH +
                            static_cast<long long>(w) * p.osW + n0;
-      uint8_t* const stg_row = stg + static_cast<size_t>(lt & ob_mask) * p.out_bytes + m * 128;
+      const uint32_t dense_pitch = p.out_pitch;            // != 0: whole pixel rows, un-swizzled (see the launcher)
+      uint8_t* const stg_row = stg + static_cast<size_t>(lt & ob_mask) * p.out_bytes + m * (dense_pitch ? dense_pitch : 128u);
       float hd[4] = {0.f, 0.f, 0.f, 0.f};                  // CCDM_EPI_HEAD: this thread's partial head outputs
       float out_ss = 0.f, out_ss_hi = 0.f;                 // alternate-tile mode keeps the two column halves apart so that
                                                            // the sum rounds exactly as in the split mode (batch-shard invariance)
@@ -850,8 +879,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
             u.y = pack_bf16(v[g * 4 + 1].x, v[g * 4 + 1].y);
             u.z = pack_bf16(v[g * 4 + 2].x, v[g * 4 + 2].y);
             u.w = pack_bf16(v[g * 4 + 3].x, v[g * 4 + 3].y);
-            if (kStoreTma)                                               // swizzled like a TMA SWIZZLE_128B box
-              *reinterpret_cast<uint4*>(srow + (((j0 + g) ^ (m & 7)) << 4)) = u;
+            if (kStoreTma) {
+              if (dense_pitch) {                                         // dense pixel row
+                if (n0 + c * 32 + g * 8 < p.N) *reinterpret_cast<uint4*>(stg_row + c * 64 + g * 16) = u;
+              } else {                                                   // swizzled like a TMA SWIZZLE_128B box
+                *reinterpret_cast<uint4*>(srow + (((j0 + g) ^ (m & 7)) << 4)) = u;
+              }
+            }
             else if (valid && n0 + c * 32 + g * 8 < p.N)
               *reinterpret_cast<uint4*>(op + g * 8) = u;
             if ((flags & CCDM_EPI_SUMSQ_OUT) && n0 + c * 32 + g * 8 < p.N) {
@@ -904,8 +938,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         epi_bar_g(alt, half);
         if (et_g == 0) {
           const uint8_t* sbuf = stg + static_cast<size_t>(lt & ob_mask) * p.out_bytes;
-          for (int pn = 0; pn < npanels; ++pn)
-            if (n0 + pn * 64 < p.N) tma_store_4d(&maps.o[z], sbuf + pn * 16384, n0 + pn * 64, w0, h0, b0);
+          if (p.out_pitch) {
+            tma_store_4d(&maps.o[z], sbuf, n0, w0, h0, b0);
+          } else {
+            for (int pn = 0; pn < npanels; ++pn)
+              if (n0 + pn * 64 < p.N) tma_store_4d(&maps.o[z], sbuf + pn * 16384, n0 + pn * 64, w0, h0, b0);
+          }
           tma_store_commit();
           if (p.out_bufs == 1) tma_store_wait_read0();
         }
@@ -975,6 +1013,21 @@ int encode_map_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t
                (unsigned long long)strides_b[0], (unsigned long long)(rank > 2 ? strides_b[1] : 0),
                (unsigned long long)(rank > 3 ? strides_b[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0,
                rank > 3 ? box[3] : 0);
+  return CCDM_OK;
+}
+
+// Un-swizzled box (inner extent up to 256 elements): the dense-row output staging of layers whose channel count is not a
+// multiple of 64.
+static int encode_map_bf16_plain(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                                 const cuuint64_t* strides_b, const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  CCDM_REQUIRE(enc != nullptr, CCDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_b, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CCDM_REQUIRE(r == CUDA_SUCCESS, CCDM_ERR_BAD_ARG, "cuTensorMapEncodeTiled (plain) failed (%d): box=%u,%u,%u,%u", (int)r,
+               box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
   return CCDM_OK;
 }
 
@@ -1162,6 +1215,7 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   p.w_batch_rows = a->w_batch_rows;
   p.n_rows = a->n_rows; p.N = a->N; p.n_tile = a->n_tile; p.n_sub = n_sub; p.nsub = nsub;
   p.sched = reinterpret_cast<const int4*>(a->sched);
+  p.ksteps = a->halo ? nullptr : a->ksteps;
   p.flags = a->flags;
   p.acc_stages = a->n_tile <= 256 ? 2 : 1;
   p.tmem_cols = pow2_cols(a->n_tile * p.acc_stages * (n_res > 0 ? 2 : 1));
@@ -1237,15 +1291,23 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
   const uint32_t a_tx = (uint32_t)(box_h * box_w * a->tb) * 128u;        // bytes one A box delivers
   p.a_bytes = (a_tx + 1023u) & ~1023u;                                   // stage layout: 1 KiB granules (halo boxes: 23040 B)
   p.halo = a->halo ? 1 : 0;
-  const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)(a->ngroups + n_res) * sizeof(int4);
+  const size_t aux_bytes = sizeof(TapGemmAux) + (size_t)(a->ngroups + n_res) * (sizeof(int4) + sizeof(int));
   size_t budget = 226 * 1024 - aux_bytes - 1024;
   // bf16 outputs up to 256 channels per CTA leave through shared memory and TMA bulk stores (coalesced, clipped at the
   // tensor edges); wider tiles (4x4 bottleneck layers) and fp32 outputs keep per-thread stores
   p.store_tma = (!(a->flags & (CCDM_EPI_OUT_F32 | CCDM_EPI_HEAD)) && a->n_tile <= 256) ? 1 : 0;
   p.out_bytes = p.store_tma ? (uint32_t)((a->n_tile + 63) / 64) * 16384u : 0;
   p.out_bufs = p.store_tma ? ((tiles_per_cta > 1 && p.out_bytes <= 32768) ? 2 : 1) : 0;
-  budget -= (size_t)p.out_bufs * p.out_bytes;
   const size_t res_all = (size_t)nkb * b_bytes * p.n_inner;
+  // Resident weights matter more than a second output staging buffer: streamed, the weight blocks of every load group ride
+  // with every box and cross L2 -> SM once per TILE (72 -> 72 3x3 at 64x64, batch 128: 1017 MB of L2 reads per launch, half of
+  // them weights, 9.7 TB/s = the L2 limit; profiles/r2_notes.md).  Give the buffer up when that is what makes them fit.
+  static const int res1_env = [] { const char* e = getenv("CCDM_TAPGEMM_RESIDENT_1BUF"); return e ? atoi(e) : 1; }();
+  if (res1_env && p.out_bufs == 2 && a->w_batch_rows == 0 && tiles_per_cta >= 2 &&
+      res_all + 3 * (size_t)p.a_bytes > budget - 2 * (size_t)p.out_bytes &&
+      res_all + 3 * (size_t)p.a_bytes <= budget - (size_t)p.out_bytes)
+    p.out_bufs = 1;
+  budget -= (size_t)p.out_bufs * p.out_bytes;
   p.b_resident = (a->w_batch_rows == 0 && (tiles_per_cta >= 2 || p.n_inner > 1) &&
                   res_all + 3 * (size_t)p.a_bytes <= budget) ? 1 : 0;
   if (p.n_inner > 1 && !p.b_resident) {           // cannot happen with the limits above; keep the simple mode if so
@@ -1271,6 +1333,15 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
                "tapgemm: one pipeline stage (%u bytes) does not fit shared memory", p.stage_bytes);
   p.stages = stages;
   const size_t smem_bytes = p.res_bytes + (size_t)stages * p.stage_bytes + (size_t)p.out_bufs * p.out_bytes + aux_bytes + 1024;
+  // Outputs whose channel count is not a multiple of 64 (the dim-72 models: 72, 144, ...) leave as ONE un-swizzled box of
+  // whole pixel rows.  As 64-channel panels their last panel is a box clipped to a few channels and every 128-byte row of
+  // the others starts off a 32-byte sector (row pitch 144 B): partial-sector writes, which tools/ubench/tma_rate.cu measures
+  // at 2.5x the cost of aligned rows (profiles/r2_ubench_tma_rate.jsonl) and which made the stores, not the MMAs, the
+  // limiter of those layers.
+  static const int dense_env = [] { const char* e = getenv("CCDM_TAPGEMM_DENSE_STORE"); return e ? atoi(e) : 1; }();
+  p.out_pitch = (dense_env && p.store_tma && a->N > 64 && a->N % 64 != 0 && a->N % 8 == 0 && a->N <= 256 && p.n_tiles == 1 &&
+                 p.n_inner == 1)
+                    ? (uint32_t)a->N * 2u : 0u;
   if (p.store_tma) {
     CCDM_REQUIRE((reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->osW % 8 == 0 && a->osH % 8 == 0 && a->osB % 8 == 0,
                  CCDM_ERR_BAD_ARG, "tapgemm: output view must be 16-byte aligned with strides in multiples of 8");
@@ -1279,8 +1350,10 @@ extern "C" int ccdm_tapgemm(const ccdm_tapgemm_args* a, void* stream) {
       CCDM_REQUIRE(a->ooff[zi] % 8 == 0, CCDM_ERR_BAD_ARG, "tapgemm: ooff[%d] must be a multiple of 8 elements", zi);
       cuuint64_t dims[4] = {(cuuint64_t)a->N, (cuuint64_t)a->gW, (cuuint64_t)a->gH, (cuuint64_t)a->gB};
       cuuint64_t str[3] = {(cuuint64_t)a->osW * 2, (cuuint64_t)a->osH * 2, (cuuint64_t)a->osB * 2};
-      cuuint32_t box[4] = {kBlockK, (cuuint32_t)a->tw, (cuuint32_t)a->th, (cuuint32_t)a->tb};
-      int rc = encode_map_bf16(&maps.o[zz], reinterpret_cast<const __nv_bfloat16*>(a->out) + a->ooff[zi], 4, dims, str, box);
+      cuuint32_t box[4] = {p.out_pitch ? (cuuint32_t)a->N : kBlockK, (cuuint32_t)a->tw, (cuuint32_t)a->th, (cuuint32_t)a->tb};
+      const __nv_bfloat16* obase = reinterpret_cast<const __nv_bfloat16*>(a->out) + a->ooff[zi];
+      int rc = p.out_pitch ? encode_map_bf16_plain(&maps.o[zz], obase, 4, dims, str, box)
+                           : encode_map_bf16(&maps.o[zz], obase, 4, dims, str, box);
       if (rc != CCDM_OK) return rc;
     }
   }

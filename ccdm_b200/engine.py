@@ -198,6 +198,21 @@ def tapgemm_flops(r: "TapGemmRec") -> float:
     return 2.0 * pos * r.N * (cin * r.plan.ntaps + r.res_cin)
 
 
+KSTEPS_ENABLED = os.environ.get("CCDM_KSTEPS", "1") != "0"      # A/B switch: skip the empty K steps of partial channel blocks
+_KSTEPS_DEV: Dict[tuple, tuple] = {}
+
+
+def _ksteps_dev(table, device) -> torch.Tensor:
+    """One device copy per (K-step table of a plan, device); the table object is kept alive with its copy."""
+    key = (id(table), str(device))
+    hit = _KSTEPS_DEV.get(key)
+    if hit is None or hit[0] is not table:
+        with torch.inference_mode(False):
+            hit = (table, torch.tensor(table, dtype=torch.int32, device=device).contiguous())
+        _KSTEPS_DEV[key] = hit
+    return hit[1]
+
+
 def _fill_tapgemm(r: TapGemmRec) -> L.TapGemmArgs:
     a = L.TapGemmArgs()
     a.n_src = len(r.views)
@@ -207,6 +222,8 @@ def _fill_tapgemm(r: TapGemmRec) -> L.TapGemmArgs:
     a.tw, a.th, a.tb = r.tile
     a.nz, a.ngroups, a.R = r.plan.nz, r.plan.ngroups, r.plan.R
     a.halo = int(getattr(r.plan, "halo", False))
+    ks = getattr(r.plan, "ksteps", None) if KSTEPS_ENABLED else None
+    a.ksteps = _ksteps_dev(ks, r.sched.device).data_ptr() if ks is not None else None
     a.sched, a.wpacked = r.sched.data_ptr(), r.wpacked.data_ptr()
     a.n_rows, a.w_batch_rows, a.N, a.n_tile, a.flags = r.n_rows, r.w_batch_rows, r.N, r.n_tile, r.flags
     a.bias, a.rowss, a.gain, a.gain_mul = L.ptr(r.bias), L.ptr(r.rowss), L.ptr(r.gain), r.gain_mul

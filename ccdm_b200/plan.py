@@ -95,6 +95,20 @@ class ConvPlan:
         return self.ngroups * self.R
 
     @property
+    def ksteps(self):
+        """[nz*ngroups] K steps (16 channels) of each load group's 64-channel block that hold data, or None when every block is
+        full (or the plan has no packing schedule / uses halo boxes): ``ccdm_tapgemm_args.ksteps``.  Cached on the plan."""
+        tab = self.__dict__.get("_ksteps", 0)
+        if tab == 0:
+            tab = None
+            if self.psched and not self.halo and len(self.psched) == self.nz * self.nkb:
+                t = [[max(1, -(-self.psched[g * self.R][1] // 16))] for g in range(self.nz * self.ngroups)]
+                if any(v[0] != 4 for v in t):
+                    tab = t
+            self.__dict__["_ksteps"] = tab
+        return tab
+
+    @property
     def n_src(self) -> int:
         return len(self.cins) * self.n_views
 

@@ -113,6 +113,10 @@ typedef struct ccdm_tapgemm_args {
   const float* head_b;
   float* head_out;
   int64_t hsC, hsB;
+  /* device int32 [nz*ngroups] or NULL: K steps (16 input channels each, 1..4) of each load group's 64-channel block that
+     hold data; the rest are neither issued nor read from wpacked (a 72-channel source is a full block plus a block with ONE
+     live K step).  NULL = 4 everywhere.  Ignored with halo boxes. */
+  const int32_t* ksteps;
 } ccdm_tapgemm_args;
 
 int ccdm_tapgemm(const ccdm_tapgemm_args* args, void* stream);

@@ -587,3 +587,16 @@ def test_unpack_wgrad_slots_sums_partial_gradients_in_order(packlib):
         assert torch.allclose(acc, want + 1, atol=1e-6)
         assert wg.ccdm_unpack_wgrad_slots(parts.data_ptr(), 3, size - 1, got.data_ptr(), cout, cin, 9, ps.data_ptr(), plan.nz,
                                           plan.nkb, n_rows, None, 1.0, 0, None) != 0      # slots must not overlap
+
+
+def test_plan_ksteps_tables():
+    """ConvPlan.ksteps (ccdm_tapgemm_args.ksteps): live K steps of every load group's 64-channel block."""
+    from ccdm_b200.plan import plan_conv
+    assert plan_conv("3x3", (64,), 64, reuse_rows=True).ksteps is None
+    assert plan_conv("3x3", (72,), 72, reuse_rows=True).ksteps == [[4], [1]] * 3
+    assert plan_conv("3x3", (288,), 288, reuse_rows=True).ksteps == [[4], [4], [4], [4], [2]] * 3
+    assert plan_conv("1x1", (72, 144), 72).ksteps == [[4], [1], [4], [4], [1]]
+    assert plan_conv("3x3_dgrad", (72,), 144, reuse_rows=True).ksteps == [[4], [1]] * 3
+    assert plan_conv("3x3", (72,), 72, halo=True).ksteps is None          # halo boxes issue whole blocks
+    up = plan_conv("up2x3x3", (72,), 72, reuse_rows=True)
+    assert up.ksteps is not None and len(up.ksteps) == up.nz * up.ngroups and {v[0] for v in up.ksteps} == {1, 4}

@@ -64,6 +64,7 @@ def main():
     cases = {
         "conv64": ("3x3", B, 64, 64, (64,), 64, L.EPI_RMSNORM | L.EPI_SS | L.EPI_SILU),
         "conv64plain": ("3x3", B, 64, 64, (64,), 64, 0),
+        "conv72plain": ("3x3", B, 64, 64, (72,), 72, 0),          # UTKFace widths: a full block + an 8-channel block
         "conv128": ("3x3", B, 64, 64, (64, 64), 64, L.EPI_RMSNORM | L.EPI_SS | L.EPI_SILU),
         "conv128x128": ("3x3", B, 32, 32, (128,), 128, L.EPI_RMSNORM | L.EPI_SILU | L.EPI_RESID),
         "qkv": ("1x1", B, 64, 64, (64,), 384, L.EPI_ROWSCALE | L.EPI_QSOFTMAX),
